@@ -1,0 +1,247 @@
+/* sem2d_b200.h -- C-ABI of the B200-native SEM2DPACK time-stepping engine.
+ *
+ * This is the drop-in boundary for ONE path of SEM2DPACK (jpampuero/sem2dpack): the explicit
+ * time step `solve(pb)` (SRC/solver.f90:20-84,140-160) with everything it calls per step --
+ * compute_Fint / MAT_Fint / MAT_ELAST_f (SRC/solver.f90:273-320, SRC/mat_gen.f90:418-460,
+ * SRC/mat_elastic.f90:396-799), SO_add (SRC/src_gen.f90:290-317), BC_apply
+ * (SRC/bc_gen.f90:256-308), REC_store (SRC/receivers.f90:309-344) and BC_write
+ * (SRC/bc_gen.f90:313-337) -- kept resident on one GPU.  The reference has no FFI layer; its
+ * boundary is the Fortran module API of one executable.  Each entry point below names the
+ * Fortran interface (file:line under SRC/) whose data it receives or whose work it replaces;
+ * INTEGRATION.md shows the ISO_C_BINDING stubs that bind them.
+ *
+ * Conventions (the reference's own, so the Fortran host passes its arrays untouched):
+ *   - every pointer is a HOST pointer unless the name says `_dev`; data are copied at call time and
+ *     the caller keeps ownership;
+ *   - arrays are column-major, indices (nodes, elements, boundary nodes) are 1-based, integers
+ *     are 32-bit, reals are IEEE double regardless of the engine's compute precision;
+ *   - fields are (npoin, ndof): component c of node k at [k-1 + npoin*c];
+ *   - every function returns 0 on success or a negative S2D_E* code; s2d_last_error() gives the
+ *     text the shim passes to IO_abort (SRC/stdio.f90:205-214);
+ *   - one handle per process / GPU; calls on one handle are not re-entrant across threads.
+ * There is no CPU fallback: if no CUDA device is usable s2d_create fails with S2D_ENODEV.
+ */
+#ifndef SEM2D_B200_H
+#define SEM2D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2D_OK 0
+#define S2D_EINVAL (-1)   /* bad argument */
+#define S2D_ENODEV (-2)   /* no usable CUDA device */
+#define S2D_ECUDA (-3)    /* CUDA runtime error (text in s2d_last_error) */
+#define S2D_ESTATE (-4)   /* call out of order (e.g. step before commit) */
+#define S2D_ESOLVER (-5)  /* device-side abort: NR_Solver exceeded 200 iterations (bc_dynflt_rsf.f90:463-466) */
+#define S2D_ENOMEM (-6)
+
+typedef struct s2d_engine* s2d_handle;
+
+/* timescheme_type (SRC/time.f90:5-11); kind 0 = 'leapfrog' (solver.f90:140-160), 1 = 'newmark'
+ * (solver.f90:42-84).  alpha is carried for CoefA2Vrhs but HHT-alpha stepping is not provided. */
+typedef struct {
+  int32_t kind;
+  double dt, beta, gamma, alpha;
+} s2d_scheme;
+
+/* element-force / assembly kernel variants */
+#define S2D_ASM_PATCH 0    /* default: CTA-patch kernel, in-patch colours + ordered halo sums (deterministic) */
+#define S2D_ASM_COLOR 1    /* one launch per greedy mesh colour (deterministic) */
+#define S2D_ASM_ATOMIC 2   /* one launch, atomicAdd assembly (measured alternative, not deterministic) */
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+
+/* Receives what init_main (SRC/init.f90:16-131) has built: sem_grid_type%ibool(ngll,ngll,nelem)
+ * and %hprime (SRC/spec_grid.f90:49-64), the inverted mass `rmass` (init.f90:112-116), the time
+ * scheme.  precision = 8 (FP64, parity mode) or 4 (FP32 fields and coefficients).
+ * device < 0 selects the current CUDA device. */
+int s2d_create(s2d_handle* h, int32_t ngll, int32_t ndof, int32_t nelem, int32_t npoin,
+               const int32_t* ibool, const double* hprime, const double* rmass, int32_t precision,
+               const s2d_scheme* scheme, int32_t device);
+int s2d_destroy(s2d_handle h);
+const char* s2d_last_error(s2d_handle h);
+const char* s2d_version(void);
+
+/* matwrk_elast_type%a (SRC/mat_elastic.f90:11-14,290-360): ncoefsets blocks a(ngll,ngll,nelast),
+ * elem2set(nelem) 1-based block of each element (mat_gen.f90:357-365 shares one block between
+ * homogeneous elements).  nelast = 2|3 (SH flat|general), 6|10 (P-SV flat|general).
+ * kd2 != 0 selects the ELAST_KD2_* form the reference uses when ngll == OPT_NGLL
+ * (mat_elastic.f90:412-423,612), 0 the ELAST_KD1_* form (:489). */
+int s2d_set_elastic(s2d_handle h, int32_t nelast, int32_t ncoefsets, const double* a,
+                    const int32_t* elem2set, int32_t kd2);
+
+/* matwrk_kv_type%eta (SRC/mat_kelvin_voigt.f90:117-150): eta(ngll,ngll,nkv), already times dt
+ * when ETAxDT; elem_ids(nkv) 1-based elements carrying it. */
+int s2d_set_kv(s2d_handle h, int32_t nkv, const int32_t* elem_ids, const double* eta);
+
+/* assembled nodal mass (SRC/mat_mass.f90:29-61, column 1) before BC_init touched it; only needed
+ * for s2d_energy (SRC/energy.f90:49-106). */
+int s2d_set_mass(s2d_handle h, const double* mass);
+
+/* bc_abso_type (SRC/bc_abso.f90:38-46), built by BC_ABSO_init (:115-266): node(np) bulk nodes,
+ * C(np,ndof); is_flat=0 needs n(np,2); stacey!=0 needs bibool(ngll,nbe) and K(ngll,2,nbe). */
+int s2d_add_abso(s2d_handle h, int32_t np, const int32_t* node, const double* C, int32_t is_flat,
+                 const double* n, int32_t stacey, int32_t nbe, const int32_t* bibool,
+                 const double* K);
+
+/* bc_dirneu_type (SRC/bc_dirneu.f90:17-23): kind 1 = Neumann, 2 = Dirichlet per component.
+ * A Neumann component with a source time function adds stf(t)*B(np) (:148-169); its amplitude
+ * comes per step through s2d_step's `bc_ampli` (NULL B = homogeneous Neumann, a no-op). */
+int s2d_add_dirneu(s2d_handle h, int32_t np, const int32_t* node, int32_t kind_h, int32_t kind_v,
+                   const double* B_h, const double* B_v);
+
+/* bc_dynflt_type (SRC/bc_dynflt.f90:18-38) after BC_DYNFLT_init (:231-520). */
+typedef struct {
+  int32_t np;
+  const int32_t* node1;    /* (np) */
+  const int32_t* node2;    /* (np) or NULL: one-sided fault, tags(2)=0 (:700-716) */
+  const double* n1;        /* (np,2) */
+  const double* B;         /* (np,ndof) */
+  const double* invM1;     /* (np,ndof) */
+  const double* invM2;     /* (np,ndof) or NULL */
+  const double* Z;         /* (np,ndof) */
+  const double* T0;        /* (np,2) */
+  const double* cohesion;  /* (np) */
+  const double* coord;     /* (2,np) */
+  const double* V0;        /* (np,ndof) initial bc%V (RSF: &BC_DYNFLT V) or NULL = 0 */
+  double CoefA2V, CoefA2D; /* time.f90:426-456 */
+  int32_t allow_opening;
+  /* slip weakening, swf_type (bc_dynflt_swf.f90:12-20); swf_kind 0 = absent */
+  int32_t swf_kind, swf_healing;
+  const double *swf_dc, *swf_mus, *swf_mud, *swf_p, *swf_alpha, *swf_theta; /* (np) each */
+  /* rate and state, rsf_type (bc_dynflt_rsf.f90:14-22); rsf_kind 0 = absent */
+  int32_t rsf_kind;
+  const double *rsf_dc, *rsf_mus, *rsf_a, *rsf_b, *rsf_Vstar, *rsf_theta, *rsf_Vc; /* (np) each */
+  /* time weakening, twf_type (bc_dynflt_twf.f90:12-16); twf_kind 0 = absent */
+  int32_t twf_kind;
+  double twf_X, twf_Z, twf_mus, twf_mud, twf_mu0, twf_L, twf_V, twf_T, twf_Dc;
+  /* normal stress response, normal_type (bc_dynflt_normal.f90:8-13), kinds 0..3 */
+  int32_t normal_kind;
+  double normal_T, normal_L, normal_V;
+  /* outputs (bc_dynflt.f90:455-458): records of nodes oix1:oixn:oixd every oitd steps from step
+   * oit on; nt_max = number of steps the history buffers must hold (time%nt) */
+  int32_t oix1, oixn, oixd, oit, oitd, nt_max;
+} s2d_dynflt_desc;
+int s2d_add_dynflt(s2d_handle h, const s2d_dynflt_desc* desc, int32_t* fault_id);
+
+/* src_force_type (SRC/src_force.f90:77-90): f(iglob,:) += dir(:)*ampli(t); returns source index. */
+int s2d_add_force(s2d_handle h, int32_t iglob, const double dir[2], int32_t* src_id);
+
+/* rec_type (SRC/receivers.f90:9-20): field 'D','V' or 'A'; nt_rec = time%nt/isamp+1 (:188);
+ * at_node: iglob(nx); else einterp(nx) + interp(ngll*ngll,nx) (:231-303). */
+int s2d_add_receivers(s2d_handle h, int32_t nx, char field, int32_t isamp, int32_t nt_rec,
+                      int32_t at_node, const int32_t* iglob, const int32_t* einterp,
+                      const double* interp);
+
+/* Freezes the configuration: builds the colouring / patch plan, uploads tables, writes the it=0
+ * fault record (bc_gen.f90:249) and the it=0 seismogram sample (main.f90:35). */
+int s2d_commit(s2d_handle h, int32_t assembly_variant);
+
+/* ---- time loop -------------------------------------------------------------------------- */
+
+/* FIELDS (SRC/fields.f90:7-11); any pointer may be NULL.  Only for init / snapshots / exit. */
+int s2d_set_fields(s2d_handle h, const double* displ, const double* veloc, const double* accel);
+int s2d_get_fields(s2d_handle h, double* displ, double* veloc, double* accel);
+
+/* nsteps iterations of the body of main.f90:51-99: it=it+1, time=it*dt, solve, REC_store,
+ * BC_write -- without host traffic.  src_ampli[nsteps][nsrc] = STF_get(t-tdelay)*ampli per source
+ * (src_gen.f90:300-303), bc_ampli[nsteps][2*ndirneu] = Neumann stf values; NULL when none. */
+int s2d_step(s2d_handle h, int32_t nsteps, const double* src_ampli, const double* bc_ampli);
+
+/* One compute_Fint (solver.f90:273-320) on the current displ/veloc, no time integration:
+ * fint(npoin,ndof) = -K d.  For kernel parity tests. */
+int s2d_compute_fint(s2d_handle h, double* fint);
+
+int s2d_get_it(s2d_handle h, int32_t* it);
+
+/* REC_write's payload (receivers.f90:351-392): sis(nt_rec,nx,ndof) float32. */
+int s2d_get_seis(s2d_handle h, float* sis);
+
+/* BC_DYNFLT_write's payload (bc_dynflt.f90:751-778): records[nout][6][onx] float32 in file order
+ * (D, V, T1, T2, MU, Tstick); potency[ncalls][2*(ndof+1)] (one line of FltXX_potency_sem2d.tab
+ * per BC_write call, the it=0 call included).  Either pointer may be NULL; counts always set. */
+int s2d_get_fault(s2d_handle h, int32_t fault_id, float* records, int32_t* nout, double* potency,
+                  int32_t* ncalls);
+/* current FP64 fault state, (np,*) column-major: D,V (np,ndof); T,Tstick (np,2); MU,theta,sigma (np) */
+int s2d_get_fault_state(s2d_handle h, int32_t fault_id, double* D, double* V, double* T,
+                        double* Tstick, double* MU, double* theta, double* sigma);
+
+/* main.f90:73-76 progress line: maxval|veloc|, maxval|displ|. */
+int s2d_progress(s2d_handle h, double* vmax, double* dmax);
+/* energy.f90:49-106 kinetic energy 0.5*sum(M v.v) (needs s2d_set_mass). */
+int s2d_energy(s2d_handle h, double* E_k);
+
+/* ---- plan introspection (parity of the colouring) ------------------------------ */
+/* greedy first-fit colours (ascending element id, conflict = shares a GLL node), 0-based, as used
+ * by S2D_ASM_COLOR; computed on the device side of the library.  color(nelem). */
+int s2d_get_coloring(s2d_handle h, int32_t* ncolors, int32_t* color);
+
+/* ---- measurement hooks ------------------------------------------------------------------- */
+/* Times `reps` launches of the element-force+assembly stage alone (CUDA events on the engine's
+ * stream), fields untouched apart from accel; returns average milliseconds per launch. */
+int s2d_time_fint(s2d_handle h, int32_t reps, float* ms_avg);
+/* Times nsteps full steps on the engine stream with CUDA events (no host traffic inside). */
+int s2d_time_steps(s2d_handle h, int32_t nsteps, float* ms_total);
+/* number of kernels the engine has launched so far */
+int s2d_launch_count(s2d_handle h, int64_t* n);
+/* raw CUDA stream (cudaStream_t) the engine launches on, for external event timing */
+int s2d_stream(s2d_handle h, void** stream);
+
+/* ---- device-side structured builder (mesh_cartesian.f90:219-314 + init on the GPU) --------- */
+/* Builds, directly in HBM, a MESH_CART problem: nx*nz Q4 elements on [x0,x1]x[z0,z1], optional
+ * horizontal split-node fault after element row ezflt (0 = none), natural (row-major) element
+ * order, GLL numbering by the rule of SE_init_numbering (spec_grid.f90:198-314), flat-grid
+ * coefficient planes (mat_elastic.f90:323-358) and mass (mat_mass.f90:50-57).
+ * Material: seed != 0 -> the heterogeneous hash model of the synthetic benchmark (cs,cp,rho per
+ * global GLL lattice point; lattice origin (ix0,iz0) so x-strips of one global mesh agree),
+ * seed == 0 -> homogeneous rho,cp,cs.  Boundaries are added afterwards with the s2d_cart_add_*
+ * calls, then s2d_commit. */
+typedef struct {
+  int32_t ngll, ndof, nx, nz, ezflt;
+  double x0, x1, z0, z1;
+  uint64_t seed;
+  int64_t ix0, iz0;       /* lattice offset of this strip inside the global mesh */
+  double rho, cp, cs;     /* homogeneous material when seed == 0 */
+  int32_t precision;      /* 8 | 4 */
+  s2d_scheme scheme;      /* dt <= 0: dt = courant / max(c/dx) as CHECK_grid + TIME_init do */
+  double courant;
+  int32_t device;
+  int32_t halo_left, halo_right; /* strip has a neighbour on that side (no physical boundary there) */
+} s2d_cart_desc;
+int s2d_cart_create(s2d_handle* h, const s2d_cart_desc* desc);
+/* BC_ABSO_init on mesh side tag 1 bottom, 2 right, 3 top, 4 left (mesh_structured.f90:86-196);
+ * adds CoefA2Vrhs*C to the mass like bc_abso.f90:243.  Must precede s2d_cart_add_fault when the
+ * reference deck lists ABSORB first. */
+int s2d_cart_add_abso(s2d_handle h, int32_t side_tag, int32_t stacey);
+/* two-sided DYNFLT on tags 5,6 with linear slip weakening: uniform Dc, MuS, MuD, Tn, Tt, and Tt_nuc
+ * where |x - x_nuc| <= half_nuc (the PWCONR patch of the TPV3 deck). */
+int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, double Tn, double Tt,
+                           double Tt_nuc, double x_nuc, double half_nuc, int32_t oixd, int32_t oitd,
+                           int32_t nt_max, int32_t* fault_id);
+int s2d_cart_add_force(s2d_handle h, double x, double z, const double dir[2], int32_t* src_id);
+int s2d_cart_add_receivers(s2d_handle h, int32_t nx, double xa, double za, double xb, double zb,
+                           char field, int32_t isamp, int32_t nt_rec);
+int s2d_cart_info(s2d_handle h, int64_t* npoin, int64_t* nelem, double* dt);
+/* copies of builder outputs for parity tests against the oracle (host pointers, may be NULL) */
+int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double* coord);
+
+/* ---- x-strip halo (multi-GPU) --------------------------------------------------- */
+/* Number of values in one interface column (nodes * ndof), and device pointers of the send /
+ * receive staging buffers: [0] left, [1] right.  After every force evaluation the engine packs
+ * its partial sums of the interface nodes into send[side], calls the registered exchange hook,
+ * and adds recv[side] (left partial + right partial on both ranks, so both stay bit-identical). */
+int s2d_halo_info(s2d_handle h, int64_t* count, void** send_dev, void** recv_dev);
+typedef int (*s2d_exchange_fn)(void* user, void* stream);
+int s2d_halo_set_exchange(s2d_handle h, s2d_exchange_fn fn, void* user);
+/* peer-to-peer variant: write partial sums straight into the neighbour's recv buffer (pointer
+ * obtained through CUDA IPC by the host) and signal with a flag; no host hook on the step path. */
+int s2d_halo_set_peers(s2d_handle h, void* left_recv_dev, void* right_recv_dev,
+                       void* left_flag_dev, void* right_flag_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEM2D_B200_H */

@@ -1,0 +1,383 @@
+// Element internal-force kernels: replace compute_Fint's element loop (SRC/solver.f90:291-299),
+// FIELD_get_elem_sub / FIELD_add_elem (SRC/fields.f90:173-189,113-129), MAT_KV_add_etav
+// (SRC/mat_kelvin_voigt.f90:137-150) and ELAST_KD1/KD2_{SH,PSV} (SRC/mat_elastic.f90:464-775)
+// with mxm / My_MATMUL (SRC/mxmlib.f90:12-184, mat_elastic.f90:779-799) folded in.
+//
+// Operator (mat_elastic.f90:600-619 for P-SV flat; the planes a(:,:,q) already hold -w*|J|*c*metric):
+//   Uxi = Ht U, Ueta = U H               (H(i,j) = h'_i(x_j), Ht its transpose)
+//   f_c = H (tH_c) + (tHt_c) Ht          with tH_c, tHt_c pointwise combinations of a and gradients.
+#pragma once
+#include "common.cuh"
+
+namespace s2d {
+
+template <typename T>
+struct ElemArgs {
+  const int* elist;     // element ids (0-based) handled by this launch, or nullptr = 0..ne-1
+  int ne;               // number of elements of this launch
+  const int* ibool;     // (N*N, nelem), 1-based node ids as received (spec_grid.f90:52)
+  const T* a;           // (N*N, nelast, ncoefsets)
+  const int* elem2set;  // (nelem) 0-based
+  const int* elem2kv;   // (nelem) -1 | 0-based KV slot, or nullptr
+  const T* eta;         // (N*N, nkv)
+  const T* H;           // (N,N) column-major hprime
+  const T* d;
+  const T* v;
+  T* f;
+  size_t npoin;
+  int nelast;
+  int kd2;
+};
+
+// pointwise stage: from the 2*NDOF gradients at one GLL point and the planes of that point, the
+// values to be left-multiplied by H (tH) and right-multiplied by Ht (tHt).
+template <typename T, int NDOF>
+__device__ __forceinline__ void pointwise_stage(const T* __restrict__ a, int nelast, int kd2,
+                                                const T gxi[NDOF], const T get[NDOF], T tH[NDOF],
+                                                T tHt[NDOF]) {
+  if (NDOF == 1) {
+    if (nelast == 2) {  // ELAST_KD*_SH flat (mat_elastic.f90:751-762)
+      tH[0] = a[0] * gxi[0];
+      tHt[0] = a[1] * get[0];
+    } else {  // general SH (mat_elastic.f90:663-676)
+      tH[0] = a[0] * gxi[0] + a[2] * get[0];
+      tHt[0] = a[2] * gxi[0] + a[1] * get[0];
+    }
+  } else {
+    const T uxx = gxi[0], uzx = gxi[NDOF - 1], uxe = get[0], uze = get[NDOF - 1];
+    if (nelast == 6) {  // P-SV flat (mat_elastic.f90:484-496 KD1, :600-619 KD2)
+      tH[0] = a[0] * uxx + a[1] * uze;
+      tHt[0] = kd2 ? a[3] * (uxe + uzx) : a[3] * uxe + a[4] * uzx;
+      tH[NDOF - 1] = a[4] * uxe + a[5] * uzx;
+      tHt[NDOF - 1] = a[1] * uxx + a[2] * uze;
+    } else {  // general P-SV, 10 planes (mat_elastic.f90:497-515)
+      tH[0] = a[0] * uxx + a[6] * uxe + a[7] * uzx + a[1] * uze;
+      tHt[0] = a[6] * uxx + a[3] * uxe + a[4] * uzx + a[8] * uze;
+      tH[NDOF - 1] = a[7] * uxx + a[4] * uxe + a[5] * uzx + a[9] * uze;
+      tHt[NDOF - 1] = a[1] * uxx + a[8] * uxe + a[9] * uzx + a[2] * uze;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// v1: one thread per GLL node, EPB elements per CTA, scatter straight to the global force array.
+// Used with one launch per mesh colour (deterministic) or in a single launch with atomicAdd.
+template <typename T, int N, int NDOF, bool ATOMIC>
+__global__ void __launch_bounds__(256) k_elem_node(ElemArgs<T> A) {
+  constexpr int N2 = N * N;
+  constexpr int EPB = 256 / N2;
+  __shared__ T sH[N2];
+  __shared__ T sU[EPB][NDOF][N2];
+  __shared__ T sP[EPB][NDOF][N2];  // tH
+  __shared__ T sQ[EPB][NDOF][N2];  // tHt
+  const int t = threadIdx.x;
+  if (t < N2) sH[t] = A.H[t];
+  const int slot = t / N2;
+  const int k = t - slot * N2;
+  const int i = k % N, j = k / N;
+  const long long eidx = (long long)blockIdx.x * EPB + slot;
+  const bool active = (slot < EPB) && (eidx < A.ne);
+  size_t node = 0;
+  T ar[10];
+  if (active) {
+    const int e = A.elist ? A.elist[eidx] : (int)eidx;
+    node = (size_t)(A.ibool[(size_t)e * N2 + k] - 1);
+    const T* ap = A.a + (size_t)A.elem2set[e] * A.nelast * N2 + k;
+#pragma unroll
+    for (int q = 0; q < 10; ++q)
+      if (q < A.nelast) ar[q] = ap[(size_t)q * N2];
+    T etav = 0;
+    const int ikv = A.elem2kv ? A.elem2kv[e] : -1;
+    if (ikv >= 0) etav = A.eta[(size_t)ikv * N2 + k];
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c) {
+      T u = A.d[node + A.npoin * c];
+      if (ikv >= 0) u = u + etav * A.v[node + A.npoin * c];  // mat_kelvin_voigt.f90:147
+      sU[slot][c][k] = u;
+    }
+  }
+  __syncthreads();
+  if (active) {
+    T gxi[NDOF], get[NDOF], tH[NDOF], tHt[NDOF];
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c) {
+      T s1 = 0, s2 = 0;
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        s1 += sH[m + N * i] * sU[slot][c][m + N * j];  // (Ht U)(i,j)
+        s2 += sU[slot][c][i + N * m] * sH[m + N * j];  // (U H)(i,j)
+      }
+      gxi[c] = s1;
+      get[c] = s2;
+    }
+    pointwise_stage<T, NDOF>(ar, A.nelast, A.kd2, gxi, get, tH, tHt);
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c) {
+      sP[slot][c][k] = tH[c];
+      sQ[slot][c][k] = tHt[c];
+    }
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c) {
+      T s1 = 0, s2 = 0;
+#pragma unroll
+      for (int m = 0; m < N; ++m) {
+        s1 += sH[i + N * m] * sP[slot][c][m + N * j];  // (H tH)(i,j)
+        s2 += sQ[slot][c][i + N * m] * sH[j + N * m];  // (tHt Ht)(i,j)
+      }
+      const T val = s1 + s2;
+      T* dst = A.f + node + A.npoin * c;
+      if (ATOMIC)
+        atomicAdd(dst, val);
+      else
+        *dst += val;
+    }
+  }
+}
+
+template <typename T, int NDOF, bool ATOMIC>
+inline void launch_elem_node(int ngll, const ElemArgs<T>& A, cudaStream_t s) {
+  if (A.ne <= 0) return;
+#define S2D_CASE(NN)                                                        \
+  case NN: {                                                                \
+    constexpr int EPB = 256 / (NN * NN);                                    \
+    k_elem_node<T, NN, NDOF, ATOMIC><<<ceil_div(A.ne, EPB), 256, 0, s>>>(A); \
+  } break;
+  switch (ngll) {
+    S2D_CASE(3)
+    S2D_CASE(4)
+    S2D_CASE(5)
+    S2D_CASE(6)
+    S2D_CASE(7)
+    S2D_CASE(8)
+    S2D_CASE(9)
+    S2D_CASE(10)
+    default:
+      throw ArgError("ngll must be in 3..10");
+  }
+#undef S2D_CASE
+}
+
+
+// =============================================================================================
+// v2: CTA-patch kernel (default).  One CTA owns a patch of up to EP clustered elements; one thread
+// owns one GLL column (fixed j) of one element, i.e. N nodes, so the xi-contractions run out of
+// registers with hprime as constant-bank operands and only the eta-contractions go through shared
+// memory.  Element forces are summed per patch in shared memory in the order of the in-patch
+// greedy colours (no atomics); nodes private to the patch are stored straight to the global force
+// array, partial sums of nodes shared with other patches go to their halo slot, and k_halo_sum
+// adds the slots of each shared node in ascending patch order.  Every node is written exactly once
+// per step, so the force array needs no zero fill.
+template <typename T, int N>
+struct PatchArgs {
+  int npatch, EP, max_nloc, max_colors;
+  const int* pelem_start;   // (npatch+1)
+  const int* gidx;          // (N*N, nelem patch-major) 0-based global node
+  const uint16_t* lidx;     // (N*N, nelem patch-major) patch-local node
+  const int* ecolor;        // (nelem patch-major)
+  const int* pnode_start;   // (npatch+1)
+  const int* pnode;         // global node (0-based) of each patch-local node
+  const int* pslot;         // -1 | halo slot
+  const int* eset;          // (nelem patch-major) coefficient set when !hetero
+  const int* ekv;           // (nelem patch-major) KV slot | -1, or nullptr
+  const T* a;               // hetero: per patch [nelast][N(i)][cnt*N(t)] ; else (N*N,nelast,nsets)
+  const T* eta;             // (N*N, nkv)
+  const T* d;
+  const T* v;
+  T* f;
+  T* fhalo;                 // (nslots, ndof)
+  size_t npoin, nslots;
+  int nelast, kd2, hetero;
+  T H[N * N];               // hprime, column-major: read as constant-bank operands
+};
+
+// elements per patch: as many as keep the CTA at <= 384 threads (one thread per GLL column)
+constexpr int patch_ep(int ngll) { return (384 / ngll) > 64 ? 64 : ((384 / ngll) < 8 ? 8 : (384 / ngll)); }
+
+template <typename T, int N, int NDOF>
+__global__ void __launch_bounds__(patch_ep(N) * N) k_elem_patch(const __grid_constant__ PatchArgs<T, N> A) {
+  constexpr int N2 = N * N;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sU = reinterpret_cast<T*>(smem_raw);   // [EP][NDOF][N2] displacement tiles, then tHt tiles
+  T* sF = sU + (size_t)A.EP * NDOF * N2;    // [NDOF][max_nloc] patch force accumulators
+  T* sH = sF + (size_t)NDOF * A.max_nloc;   // [N2]
+  const int p = blockIdx.x;
+  const int t = threadIdx.x;
+  const int es = A.pelem_start[p];
+  const int cnt = A.pelem_start[p + 1] - es;
+  const int el = t / N;
+  const int j = t - el * N;
+  const bool active = el < cnt;
+  const int q = es + el;
+  const int ps = A.pnode_start[p];
+  const int nloc = A.pnode_start[p + 1] - ps;
+
+  if (t < N2) sH[t] = A.H[t];
+  for (int l = t; l < NDOF * A.max_nloc; l += blockDim.x) sF[l] = 0;
+
+  T* myU = sU + (size_t)el * NDOF * N2;
+  T ucol[NDOF][N];
+  if (active) {
+    const int ikv = A.ekv ? A.ekv[q] : -1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const size_t node = (size_t)A.gidx[(size_t)q * N2 + i + N * j];
+      T etav = 0;
+      if (ikv >= 0) etav = A.eta[(size_t)ikv * N2 + i + N * j];
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) {
+        T u = A.d[node + A.npoin * c];
+        if (ikv >= 0) u = u + etav * A.v[node + A.npoin * c];  // mat_kelvin_voigt.f90:147
+        ucol[c][i] = u;
+        myU[c * N2 + i + N * j] = u;
+      }
+    }
+  }
+  __syncthreads();
+
+  T fcol[NDOF][N];   // force column accumulated in registers
+  T tHt[NDOF][N];    // values that go through the tile exchange
+  T HTj[N];          // H(j,m)
+  if (active) {
+    T Hj[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      Hj[m] = sH[m + N * j];   // H(m,j)
+      HTj[m] = sH[j + N * m];  // H(j,m)
+    }
+    T gxi[NDOF][N], get[NDOF][N];
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        T s1 = 0, s2 = 0;
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+          s1 += A.H[m + N * i] * ucol[c][m];      // (Ht U)(i,j), column in registers
+          s2 += myU[c * N2 + i + N * m] * Hj[m];  // (U H)(i,j), row from the tile
+        }
+        gxi[c][i] = s1;
+        get[c][i] = s2;
+      }
+    // pointwise stage with the coefficient planes of this column
+    const T* ap;
+    size_t qstride, istride;
+    if (A.hetero) {
+      ap = A.a + (size_t)es * A.nelast * N2 + t;
+      istride = (size_t)cnt * N;
+      qstride = (size_t)N * istride;
+    } else {
+      ap = A.a + (size_t)A.eset[q] * A.nelast * N2 + N * j;
+      qstride = N2;
+      istride = 1;
+    }
+    T tH[NDOF][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      T ar[10];
+#pragma unroll
+      for (int pl = 0; pl < 10; ++pl)
+        if (pl < A.nelast) ar[pl] = ap[pl * qstride + i * istride];
+      T g1[NDOF], g2[NDOF], o1[NDOF], o2[NDOF];
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) {
+        g1[c] = gxi[c][i];
+        g2[c] = get[c][i];
+      }
+      pointwise_stage<T, NDOF>(ar, A.nelast, A.kd2, g1, g2, o1, o2);
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) {
+        tH[c][i] = o1[c];
+        tHt[c][i] = o2[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        T s1 = 0;
+#pragma unroll
+        for (int m = 0; m < N; ++m) s1 += A.H[i + N * m] * tH[c][m];  // (H tH)(i,j)
+        fcol[c][i] = s1;
+      }
+  }
+  __syncthreads();  // all reads of the displacement tiles are done
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i) myU[c * N2 + i + N * j] = tHt[c][i];
+  }
+  __syncthreads();
+  int mycol = -1;
+  int li[N];
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        T s2 = 0;
+#pragma unroll
+        for (int m = 0; m < N; ++m) s2 += myU[c * N2 + i + N * m] * HTj[m];  // (tHt Ht)(i,j)
+        fcol[c][i] += s2;
+      }
+    mycol = A.ecolor[q];
+#pragma unroll
+    for (int i = 0; i < N; ++i) li[i] = A.lidx[(size_t)q * N2 + i + N * j];
+  }
+  // in-patch assembly, one colour at a time (elements of one colour share no node)
+  for (int col = 0; col < A.max_colors; ++col) {
+    if (mycol == col) {
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i) sF[c * A.max_nloc + li[i]] += fcol[c][i];
+    }
+    __syncthreads();
+  }
+  for (int l = t; l < nloc; l += blockDim.x) {
+    const int g = A.pnode[ps + l];
+    const int slot = A.pslot[ps + l];
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c) {
+      const T val = sF[c * A.max_nloc + l];
+      if (slot < 0)
+        A.f[(size_t)g + A.npoin * c] = val;
+      else
+        A.fhalo[(size_t)slot + A.nslots * c] = val;
+    }
+  }
+}
+
+// adds the halo slots of each node shared between patches, in ascending patch order
+template <typename T>
+__global__ void k_halo_sum(T* __restrict__ f, const T* __restrict__ fhalo, const int* __restrict__ snode,
+                           const int* __restrict__ sstart, int nshared, size_t npoin, size_t nslots,
+                           int ndof) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nshared) return;
+  const size_t g = (size_t)snode[s];
+  const int b = sstart[s], e = sstart[s + 1];
+  for (int c = 0; c < ndof; ++c) {
+    T acc = fhalo[(size_t)b + nslots * c];
+    for (int k = b + 1; k < e; ++k) acc += fhalo[(size_t)k + nslots * c];
+    f[g + npoin * c] = acc;
+  }
+}
+
+template <typename T, int N, int NDOF>
+inline void launch_elem_patch_n(const PatchArgs<T, N>& A, cudaStream_t s) {
+  if (A.npatch <= 0) return;
+  const size_t smem = ((size_t)A.EP * NDOF * N * N + (size_t)NDOF * A.max_nloc + N * N) * sizeof(T);
+  static size_t configured = 0;
+  if (smem > configured) {
+    S2D_CUDA(cudaFuncSetAttribute(k_elem_patch<T, N, NDOF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    configured = smem;
+  }
+  k_elem_patch<T, N, NDOF><<<A.npatch, A.EP * N, smem, s>>>(A);
+}
+
+}  // namespace s2d

@@ -1,0 +1,954 @@
+// Engine core: device-resident state of one SEM2DPACK problem and the per-step launch sequence
+// of solve_leapfrog / solve_Newmark (SRC/solver.f90:42-84,140-160) + REC_store + BC_write.
+#pragma once
+#include <cmath>
+#include <memory>
+
+#include "bc_kernels.cuh"
+#include "common.cuh"
+#include "elem_kernels.cuh"
+#include "plan.hpp"
+
+namespace s2d {
+
+enum BcKind { BC_ABSO = 1, BC_DIRNEU = 2, BC_DYNFLT = 3 };
+
+struct AbsoBc {
+  AbsoDev dev{};
+  DevBuf<int> node, st_start, st_elem, st_loc, bibool;
+  DevBuf<double> C, n, K, Ht;
+};
+struct DirneuBc {
+  int np = 0, kind_h = 1, kind_v = 1, slot = 0;
+  DevBuf<int> node;
+  DevBuf<double> B_h, B_v;
+};
+struct FaultBc {
+  FaultDev dev{};
+  DevBuf<int> node1, node2, ostate;
+  DevBuf<double> n1, B, invM1, invM2, Z, T0, cohesion, coord, T, Tstick, V, D, MU, sigma;
+  DevBuf<double> swf_dc, swf_mus, swf_mud, swf_p, swf_alpha, swf_theta;
+  DevBuf<double> rsf_dc, rsf_mus, rsf_a, rsf_b, rsf_Vstar, rsf_Vc, rsf_Tc, rsf_coeft, rsf_theta;
+  DevBuf<float> records;
+  DevBuf<double> potency;
+};
+struct BcRef {
+  int kind;
+  int index;
+};
+
+struct Receivers {
+  bool present = false;
+  char field = 'V';
+  RecDev dev{};
+  DevBuf<int> iglob, einterp;
+  DevBuf<double> interp;
+  DevBuf<float> sis;
+};
+
+class EngineBase {
+ public:
+  virtual ~EngineBase() {}
+  int ngll = 0, ndof = 0, nelem = 0, prec = 8;
+  size_t npoin = 0;
+  s2d_scheme scheme{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool committed = false;
+  int variant = S2D_ASM_PATCH;
+  int it = 0;  // host mirror of ctl.it
+  int64_t launches = 0;
+
+  virtual void set_elastic(int nelast, int ncoefsets, const double* a, const int32_t* elem2set, int kd2) = 0;
+  virtual void set_kv(int nkv, const int32_t* elem_ids, const double* eta) = 0;
+  virtual void set_mass(const double* mass) = 0;
+  virtual void add_abso(int np, const int32_t* node, const double* C, int is_flat, const double* n,
+                        int stacey, int nbe, const int32_t* bibool, const double* K) = 0;
+  virtual void add_dirneu(int np, const int32_t* node, int kind_h, int kind_v, const double* B_h,
+                          const double* B_v) = 0;
+  virtual int add_dynflt(const s2d_dynflt_desc& d) = 0;
+  virtual int add_force(int iglob, const double dir[2]) = 0;
+  virtual void add_receivers(int nx, char field, int isamp, int nt_rec, int at_node, const int32_t* iglob,
+                             const int32_t* einterp, const double* interp) = 0;
+  virtual void commit(int variant) = 0;
+  virtual void set_fields(const double* d, const double* v, const double* a) = 0;
+  virtual void get_fields(double* d, double* v, double* a) = 0;
+  virtual void step(int nsteps, const double* src_ampli, const double* bc_ampli) = 0;
+  virtual void compute_fint(double* fint) = 0;
+  virtual void get_seis(float* sis) = 0;
+  virtual void get_fault(int id, float* records, int32_t* nout, double* potency, int32_t* ncalls) = 0;
+  virtual void get_fault_state(int id, double* D, double* V, double* T, double* Tstick, double* MU,
+                               double* theta, double* sigma) = 0;
+  virtual void progress(double* vmax, double* dmax) = 0;
+  virtual double energy() = 0;
+  virtual void get_coloring(int32_t* ncolors, int32_t* color) = 0;
+  virtual float time_fint(int reps) = 0;
+  virtual float time_steps(int nsteps) = 0;
+};
+
+template <typename T>
+class Engine : public EngineBase {
+ public:
+  // grid
+  std::vector<int32_t> h_ibool;  // kept on the host for planning
+  DevBuf<int> ibool;
+  DevBuf<T> H;
+  std::vector<double> h_H;
+  // fields
+  DevBuf<T> d, v, a, rmass, scratch;
+  // material
+  int nelast = 0, ncoefsets = 0, kd2 = 0, nkv = 0;
+  DevBuf<T> coef, eta;
+  DevBuf<int> elem2set, elem2kv;
+  std::vector<int32_t> h_elem2set, h_elem2kv;
+  std::vector<double> h_coef;
+  DevBuf<double> mass;
+  // boundary conditions in registration order
+  std::vector<std::unique_ptr<AbsoBc>> abso;
+  std::vector<std::unique_ptr<DirneuBc>> dirneu;
+  std::vector<std::unique_ptr<FaultBc>> faults;
+  std::vector<BcRef> bc_order;
+  int n_neumann_slots = 0;
+  // sources
+  std::vector<int32_t> h_src_iglob;
+  std::vector<double> h_src_dir;
+  DevBuf<int> src_iglob;
+  DevBuf<double> src_dir, src_ampli, bc_ampli;
+  size_t src_ampli_cap = 0, bc_ampli_cap = 0;
+  Receivers rec;
+  // control
+  DevBuf<StepCtl> ctl;
+  DevBuf<double> partial;
+  // colour plan
+  int ncolors = 0;
+  std::vector<int32_t> h_color;
+  std::vector<int32_t> color_start;  // (ncolors+1)
+  DevBuf<int> color_elems;
+  // patch plan
+  PatchPlan plan;
+  DevBuf<int> p_pelem_start, p_gidx, p_ecolor, p_pnode_start, p_pnode, p_pslot, p_eset, p_ekv, p_snode, p_sstart;
+  DevBuf<uint16_t> p_lidx;
+  DevBuf<T> p_coef, fhalo;
+  bool p_hetero = false;
+
+  Engine(int ngll_, int ndof_, int nelem_, size_t npoin_, const int32_t* ibool_, const double* hprime,
+         const double* rmass_, const s2d_scheme& sch, int dev) {
+    ngll = ngll_;
+    ndof = ndof_;
+    nelem = nelem_;
+    npoin = npoin_;
+    prec = (int)sizeof(T);
+    scheme = sch;
+    device = dev;
+    S2D_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    const size_t n2 = (size_t)ngll * ngll;
+    h_ibool.assign(ibool_, ibool_ + n2 * nelem);
+    for (size_t q = 0; q < h_ibool.size(); ++q)
+      S2D_REQUIRE(h_ibool[q] >= 1 && (size_t)h_ibool[q] <= npoin, "ibool entry out of range");
+    ibool.upload(h_ibool);
+    h_H.assign(hprime, hprime + n2);
+    upload_as(H, hprime, n2);
+    const size_t nd = npoin * ndof;
+    d.alloc(nd);
+    v.alloc(nd);
+    a.alloc(nd);
+    d.zero();
+    v.zero();
+    a.zero();
+    upload_as(rmass, rmass_, nd);
+    StepCtl c0{0, 1, 0, 1};
+    ctl.upload(&c0, 1);
+    partial.alloc(1024);
+  }
+  ~Engine() override {
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  // ---- configuration -------------------------------------------------------------------
+  void set_elastic(int nelast_, int ncoefsets_, const double* a_, const int32_t* e2s, int kd2_) override {
+    S2D_REQUIRE(!committed, "set_elastic after commit");
+    S2D_REQUIRE((ndof == 1 && (nelast_ == 2 || nelast_ == 3)) || (ndof == 2 && (nelast_ == 6 || nelast_ == 10)),
+                "nelast does not match ndof (mat_elastic.f90:255-268)");
+    S2D_REQUIRE(ncoefsets_ >= 1, "ncoefsets < 1");
+    nelast = nelast_;
+    ncoefsets = ncoefsets_;
+    kd2 = kd2_ ? 1 : 0;
+    const size_t n2 = (size_t)ngll * ngll;
+    h_coef.assign(a_, a_ + n2 * nelast * ncoefsets);
+    upload_as(coef, a_, h_coef.size());
+    h_elem2set.resize(nelem);
+    for (int e = 0; e < nelem; ++e) {
+      S2D_REQUIRE(e2s[e] >= 1 && e2s[e] <= ncoefsets, "elem2set entry out of range");
+      h_elem2set[e] = e2s[e] - 1;
+    }
+    elem2set.upload(h_elem2set);
+  }
+  void set_kv(int nkv_, const int32_t* elem_ids, const double* eta_) override {
+    S2D_REQUIRE(!committed, "set_kv after commit");
+    nkv = nkv_;
+    h_elem2kv.assign(nelem, -1);
+    for (int k = 0; k < nkv; ++k) {
+      S2D_REQUIRE(elem_ids[k] >= 1 && elem_ids[k] <= nelem, "KV element id out of range");
+      h_elem2kv[elem_ids[k] - 1] = k;
+    }
+    if (nkv > 0) {
+      elem2kv.upload(h_elem2kv);
+      upload_as(eta, eta_, (size_t)ngll * ngll * nkv);
+    }
+  }
+  void set_mass(const double* m) override { mass.upload(m, npoin); }
+
+  void check_nodes(int np, const int32_t* node, const char* what) {
+    for (int k = 0; k < np; ++k)
+      if (node[k] < 1 || (size_t)node[k] > npoin) throw ArgError(std::string(what) + ": node id out of range");
+  }
+
+  void add_abso(int np, const int32_t* node, const double* C, int is_flat, const double* n, int stacey,
+                int nbe, const int32_t* bibool, const double* K) override {
+    S2D_REQUIRE(!committed, "add_abso after commit");
+    S2D_REQUIRE(np > 0 && node && C, "add_abso: empty boundary");
+    check_nodes(np, node, "add_abso");
+    auto b = std::make_unique<AbsoBc>();
+    b->node.upload(node, np);
+    b->C.upload(C, (size_t)np * ndof);
+    if (!is_flat && ndof == 2) {
+      S2D_REQUIRE(n != nullptr, "add_abso: non-flat boundary needs normals");
+      b->n.upload(n, (size_t)np * 2);
+    }
+    AbsoDev& A = b->dev;
+    A.np = np;
+    A.ndof = ndof;
+    A.is_flat = is_flat;
+    A.stacey = (stacey && ndof == 2) ? 1 : 0;
+    A.ngll = ngll;
+    if (A.stacey) {
+      S2D_REQUIRE(nbe > 0 && bibool && K, "add_abso: Stacey needs bibool and K");
+      std::vector<int> start(np + 1, 0), el, lc;
+      for (size_t q = 0; q < (size_t)ngll * nbe; ++q) {
+        S2D_REQUIRE(bibool[q] >= 1 && bibool[q] <= np, "add_abso: bibool out of range");
+        start[bibool[q]]++;
+      }
+      for (int k = 0; k < np; ++k) start[k + 1] += start[k];
+      el.resize(start[np]);
+      lc.resize(start[np]);
+      std::vector<int> fill(start.begin(), start.end() - 1);
+      for (int e = 0; e < nbe; ++e)  // ascending element, then local index: the reference's order
+        for (int i = 0; i < ngll; ++i) {
+          const int bn = bibool[i + (size_t)ngll * e] - 1;
+          el[fill[bn]] = e;
+          lc[fill[bn]] = i;
+          fill[bn]++;
+        }
+      b->st_start.upload(start);
+      b->st_elem.upload(el);
+      b->st_loc.upload(lc);
+      b->bibool.upload(bibool, (size_t)ngll * nbe);
+      b->K.upload(K, (size_t)ngll * 2 * nbe);
+      std::vector<double> Ht((size_t)ngll * ngll);
+      for (int i = 0; i < ngll; ++i)
+        for (int k = 0; k < ngll; ++k) Ht[i + ngll * k] = h_H[k + ngll * i];
+      b->Ht.upload(Ht);
+    }
+    A.node = b->node.p;
+    A.C = b->C.p;
+    A.n = b->n.p;
+    A.st_start = b->st_start.p;
+    A.st_elem = b->st_elem.p;
+    A.st_loc = b->st_loc.p;
+    A.bibool = b->bibool.p;
+    A.K = b->K.p;
+    A.Ht = b->Ht.p;
+    abso.push_back(std::move(b));
+    bc_order.push_back({BC_ABSO, (int)abso.size() - 1});
+  }
+
+  void add_dirneu(int np, const int32_t* node, int kind_h, int kind_v, const double* B_h,
+                  const double* B_v) override {
+    S2D_REQUIRE(!committed, "add_dirneu after commit");
+    S2D_REQUIRE(np > 0 && node, "add_dirneu: empty boundary");
+    check_nodes(np, node, "add_dirneu");
+    auto b = std::make_unique<DirneuBc>();
+    b->np = np;
+    b->kind_h = kind_h;
+    b->kind_v = kind_v;
+    b->node.upload(node, np);
+    if (B_h) b->B_h.upload(B_h, np);
+    if (B_v) b->B_v.upload(B_v, np);
+    b->slot = n_neumann_slots;
+    n_neumann_slots += 2;
+    dirneu.push_back(std::move(b));
+    bc_order.push_back({BC_DIRNEU, (int)dirneu.size() - 1});
+  }
+
+  int add_dynflt(const s2d_dynflt_desc& D) override {
+    S2D_REQUIRE(!committed, "add_dynflt after commit");
+    const int np = D.np;
+    S2D_REQUIRE(np > 0 && D.node1 && D.n1 && D.B && D.invM1 && D.Z && D.T0 && D.cohesion && D.coord,
+                "add_dynflt: missing array");
+    check_nodes(np, D.node1, "add_dynflt");
+    if (D.node2) check_nodes(np, D.node2, "add_dynflt");
+    S2D_REQUIRE(!D.node2 || D.invM2, "add_dynflt: two-sided fault needs invM2");
+    S2D_REQUIRE(!(D.swf_kind && D.rsf_kind), "add_dynflt: SWF and RSF are exclusive (bc_dynflt.f90:168-183)");
+    auto b = std::make_unique<FaultBc>();
+    FaultDev& F = b->dev;
+    std::memset(&F, 0, sizeof(F));
+    F.np = np;
+    F.ndof = ndof;
+    F.two_sides = D.node2 ? 1 : 0;
+    F.allow_opening = D.allow_opening;
+    F.CoefA2V = D.CoefA2V;
+    F.CoefA2D = D.CoefA2D;
+    F.dt = scheme.dt;
+    auto up = [&](DevBuf<double>& buf, const double* src, size_t n) -> const double* {
+      if (!src) return nullptr;
+      buf.upload(src, n);
+      return buf.p;
+    };
+    b->node1.upload(D.node1, np);
+    F.node1 = b->node1.p;
+    if (D.node2) {
+      b->node2.upload(D.node2, np);
+      F.node2 = b->node2.p;
+    }
+    F.n1 = up(b->n1, D.n1, (size_t)np * 2);
+    F.B = up(b->B, D.B, (size_t)np * ndof);
+    F.invM1 = up(b->invM1, D.invM1, (size_t)np * ndof);
+    F.invM2 = up(b->invM2, D.invM2, (size_t)np * ndof);
+    F.Z = up(b->Z, D.Z, (size_t)np * ndof);
+    F.T0 = up(b->T0, D.T0, (size_t)np * 2);
+    F.cohesion = up(b->cohesion, D.cohesion, np);
+    F.coord = up(b->coord, D.coord, (size_t)np * 2);
+    std::vector<double> zero((size_t)np * 2, 0.0);
+    b->T.upload(zero);
+    b->Tstick.upload(zero);
+    b->D.upload(zero.data(), (size_t)np * ndof);
+    if (D.V0)
+      b->V.upload(D.V0, (size_t)np * ndof);
+    else
+      b->V.upload(zero.data(), (size_t)np * ndof);
+    F.T = b->T.p;
+    F.Tstick = b->Tstick.p;
+    F.D = b->D.p;
+    F.V = b->V.p;
+    // normal stress (bc_dynflt_normal.f90:96-114)
+    F.normal_kind = D.normal_kind;
+    F.normal_V = D.normal_V;
+    F.normal_coef = 0.0;
+    if (D.normal_kind == 2) F.normal_coef = std::exp(-scheme.dt / D.normal_T);
+    if (D.normal_kind == 3) F.normal_coef = scheme.dt / D.normal_L;
+    std::vector<double> sigma(D.T0 + np, D.T0 + 2 * (size_t)np);
+    b->sigma.upload(sigma);
+    F.sigma = b->sigma.p;
+    std::vector<double> MU(np, 0.0);
+    // friction
+    F.swf_kind = D.swf_kind;
+    F.swf_healing = D.swf_healing;
+    F.rsf_kind = D.rsf_kind;
+    F.twf_kind = D.twf_kind;
+    F.twf_X = D.twf_X; F.twf_Z = D.twf_Z; F.twf_mus = D.twf_mus; F.twf_mud = D.twf_mud;
+    F.twf_mu0 = D.twf_mu0; F.twf_L = D.twf_L; F.twf_V = D.twf_V; F.twf_T = D.twf_T; F.twf_Dc = D.twf_Dc;
+    if (D.swf_kind) {
+      S2D_REQUIRE(D.swf_dc && D.swf_mus && D.swf_mud && D.swf_p && D.swf_alpha, "add_dynflt: SWF arrays missing");
+      F.swf_dc = up(b->swf_dc, D.swf_dc, np);
+      F.swf_mus = up(b->swf_mus, D.swf_mus, np);
+      F.swf_mud = up(b->swf_mud, D.swf_mud, np);
+      F.swf_p = up(b->swf_p, D.swf_p, np);
+      F.swf_alpha = up(b->swf_alpha, D.swf_alpha, np);
+      if (D.swf_theta)
+        b->swf_theta.upload(D.swf_theta, np);
+      else
+        b->swf_theta.upload(zero.data(), np);
+      F.swf_theta = b->swf_theta.p;
+    }
+    if (D.rsf_kind) {
+      S2D_REQUIRE(D.rsf_dc && D.rsf_mus && D.rsf_a && D.rsf_b && D.rsf_Vstar && D.rsf_theta && D.rsf_Vc,
+                  "add_dynflt: RSF arrays missing");
+      F.rsf_dc = up(b->rsf_dc, D.rsf_dc, np);
+      F.rsf_mus = up(b->rsf_mus, D.rsf_mus, np);
+      F.rsf_a = up(b->rsf_a, D.rsf_a, np);
+      F.rsf_b = up(b->rsf_b, D.rsf_b, np);
+      F.rsf_Vstar = up(b->rsf_Vstar, D.rsf_Vstar, np);
+      F.rsf_Vc = up(b->rsf_Vc, D.rsf_Vc, np);
+      b->rsf_theta.upload(D.rsf_theta, np);
+      F.rsf_theta = b->rsf_theta.p;
+      std::vector<double> Tc(np), coeft(np);  // rsf_init (bc_dynflt_rsf.f90:152-156)
+      for (int k = 0; k < np; ++k) {
+        Tc[k] = D.rsf_dc[k] / D.rsf_Vstar[k];
+        coeft[k] = std::exp(-scheme.dt / Tc[k]);
+      }
+      b->rsf_Tc.upload(Tc);
+      b->rsf_coeft.upload(coeft);
+      F.rsf_Tc = b->rsf_Tc.p;
+      F.rsf_coeft = b->rsf_coeft.p;
+    }
+    // initial friction coefficient (bc_dynflt.f90:404-417) -- evaluated on the host once
+    for (int k = 0; k < np; ++k) {
+      const double BIG = 1.7976931348623157e308;
+      auto twf0 = [&]() {  // twf_mu at time 0, slip 0
+        double t, r = 0, mu = BIG;
+        const double dist = std::sqrt((D.coord[2 * k] - D.twf_X) * (D.coord[2 * k] - D.twf_X) +
+                                      (D.coord[2 * k + 1] - D.twf_Z) * (D.coord[2 * k + 1] - D.twf_Z));
+        if (D.twf_kind == 1) {
+          t = (D.twf_mus - D.twf_mu0) * D.twf_L / ((D.twf_mus - D.twf_mud) * D.twf_V);
+          if (t > D.twf_T) t = 0.0;
+          r = D.twf_V * t;
+        } else if (D.twf_kind == 2) {
+          t = 0.5 * D.twf_T * (1.0 - std::sqrt(1.0 - 4.0 * (D.twf_mus - D.twf_mu0) * D.twf_L /
+                                                         ((D.twf_mus - D.twf_mud) * D.twf_T * D.twf_V)));
+          t = std::min(t, D.twf_T);
+          r = D.twf_V * t * (1.0 - t / D.twf_T);
+        }
+        if (D.twf_kind == 1 || D.twf_kind == 2) {
+          const double rr = dist - r;
+          if (rr < -D.twf_L) mu = D.twf_mud;
+          else if (rr <= D.twf_L) mu = D.twf_mus + (D.twf_mus - D.twf_mud) / D.twf_L * rr;
+        } else {
+          if (dist <= D.twf_V * D.twf_T && 0.0 <= D.twf_Dc) {
+            if (dist < -D.twf_L) mu = D.twf_mud;
+            else if (dist <= 0.0) mu = D.twf_mus + (D.twf_mus - D.twf_mud) / D.twf_L * dist;
+          }
+        }
+        return mu;
+      };
+      if (D.swf_kind) {
+        const double th = D.swf_theta ? D.swf_theta[k] : 0.0;
+        double mu = 0;
+        if (D.swf_kind == 1) mu = D.swf_mus[k] - (D.swf_mus[k] - D.swf_mud[k]) * std::min(th / D.swf_dc[k], 1.0);
+        else if (D.swf_kind == 2) mu = D.swf_mud[k] - (D.swf_mud[k] - D.swf_mus[k]) * std::exp(-th / D.swf_dc[k]);
+        else if (D.swf_kind == 3) mu = D.swf_mud[k] + (D.swf_mus[k] - D.swf_mud[k]) / std::pow(1.0 + th / D.swf_dc[k], D.swf_p[k]);
+        MU[k] = mu + D.swf_alpha[k] * th;
+        if (D.twf_kind) MU[k] = std::min(MU[k], twf0());
+      } else if (D.rsf_kind) {
+        const double vv = std::fabs(D.V0 ? D.V0[k] : 0.0), th = D.rsf_theta[k];
+        if (D.rsf_kind == 1)
+          MU[k] = D.rsf_mus[k] + D.rsf_a[k] * vv / (vv + D.rsf_Vstar[k]) - D.rsf_b[k] * th / (th + D.rsf_dc[k]);
+        else {
+          const double arg = (D.rsf_kind == 4) ? D.rsf_Vc[k] * th / D.rsf_dc[k] + 1.0 : D.rsf_Vstar[k] * th / D.rsf_dc[k];
+          MU[k] = D.rsf_a[k] * std::asinh(vv / (2.0 * D.rsf_Vstar[k]) *
+                                          std::exp((D.rsf_mus[k] + D.rsf_b[k] * std::log(arg)) / D.rsf_a[k]));
+        }
+        if (D.twf_kind) MU[k] = std::min(MU[k], twf0());
+      } else if (D.twf_kind) {
+        MU[k] = twf0();
+      }
+    }
+    b->MU.upload(MU);
+    F.MU = b->MU.p;
+    // outputs
+    F.oix1 = std::max(D.oix1, 1);
+    F.oixn = std::min(D.oixn, np);
+    F.oixd = std::max(D.oixd, 1);
+    F.oitd = std::max(D.oitd, 1);
+    F.onx = (F.oixn >= F.oix1) ? (F.oixn - F.oix1) / F.oixd + 1 : 0;
+    const int nt_max = std::max(D.nt_max, 0);
+    F.ncall_max = nt_max + 1;
+    F.nrec_max = nt_max / F.oitd + 2;
+    b->records.alloc((size_t)F.nrec_max * 6 * std::max(F.onx, 1));
+    b->records.zero();
+    b->potency.alloc((size_t)F.ncall_max * 2 * (ndof + 1));
+    b->potency.zero();
+    std::vector<int> ost = {D.oit, 0, 0};
+    b->ostate.upload(ost);
+    F.ostate = b->ostate.p;
+    F.records = b->records.p;
+    F.potency = b->potency.p;
+    faults.push_back(std::move(b));
+    bc_order.push_back({BC_DYNFLT, (int)faults.size() - 1});
+    return (int)faults.size() - 1;
+  }
+
+  int add_force(int iglob, const double dir[2]) override {
+    S2D_REQUIRE(!committed, "add_force after commit");
+    S2D_REQUIRE(iglob >= 1 && (size_t)iglob <= npoin, "add_force: node id out of range");
+    h_src_iglob.push_back(iglob);
+    h_src_dir.push_back(dir[0]);
+    h_src_dir.push_back(dir[1]);
+    return (int)h_src_iglob.size() - 1;
+  }
+
+  void add_receivers(int nx, char field, int isamp, int nt_rec, int at_node, const int32_t* iglob,
+                     const int32_t* einterp, const double* interp) override {
+    S2D_REQUIRE(!committed, "add_receivers after commit");
+    S2D_REQUIRE(nx > 0 && isamp > 0 && nt_rec > 0, "add_receivers: bad sizes");
+    S2D_REQUIRE(field == 'D' || field == 'V' || field == 'A', "add_receivers: field must be D, V or A");
+    rec.present = true;
+    rec.field = field;
+    RecDev& R = rec.dev;
+    R.nx = nx;
+    R.ndof = ndof;
+    R.isamp = isamp;
+    R.nt = nt_rec;
+    R.at_node = at_node;
+    R.ngll = ngll;
+    if (at_node) {
+      S2D_REQUIRE(iglob != nullptr, "add_receivers: iglob missing");
+      check_nodes(nx, iglob, "add_receivers");
+      rec.iglob.upload(iglob, nx);
+    } else {
+      S2D_REQUIRE(einterp && interp, "add_receivers: einterp/interp missing");
+      for (int n = 0; n < nx; ++n) S2D_REQUIRE(einterp[n] >= 1 && einterp[n] <= nelem, "add_receivers: element out of range");
+      rec.einterp.upload(einterp, nx);
+      rec.interp.upload(interp, (size_t)ngll * ngll * nx);
+    }
+    rec.sis.alloc((size_t)nt_rec * nx * ndof);
+    rec.sis.zero();
+    R.iglob = rec.iglob.p;
+    R.einterp = rec.einterp.p;
+    R.interp = rec.interp.p;
+    R.ibool = ibool.p;
+    R.sis = rec.sis.p;
+  }
+
+  // ---- planning ------------------------------------------------------------------------
+  void build_color_plan() {
+    const int n2 = ngll * ngll;
+    ncolors = greedy_coloring(h_ibool.data(), n2, nelem, npoin, h_color);
+    color_start.assign(ncolors + 1, 0);
+    for (int e = 0; e < nelem; ++e) color_start[h_color[e] + 1]++;
+    for (int c = 0; c < ncolors; ++c) color_start[c + 1] += color_start[c];
+    std::vector<int> list(nelem), fill(color_start.begin(), color_start.end() - 1);
+    for (int e = 0; e < nelem; ++e) list[fill[h_color[e]]++] = e;
+    color_elems.upload(list);
+  }
+  static int patch_EP(int ngll) { return patch_ep(ngll); }
+  void build_patch_plan_dev() {
+    const int n2 = ngll * ngll;
+    build_patch_plan(h_ibool.data(), n2, nelem, npoin, patch_EP(ngll), plan);
+    upload_patch_plan();
+  }
+  void upload_patch_plan() {
+    const int n2 = ngll * ngll;
+    PatchPlan& P = plan;
+    std::vector<int> gidx((size_t)nelem * n2), eset(nelem), ekv(nelem, -1);
+    for (int q = 0; q < nelem; ++q) {
+      const int e = P.elems[q];
+      for (int k = 0; k < n2; ++k) gidx[(size_t)q * n2 + k] = h_ibool[(size_t)e * n2 + k] - 1;
+      eset[q] = h_elem2set[e];
+      if (nkv > 0) ekv[q] = h_elem2kv[e];
+    }
+    p_pelem_start.upload(P.pelem_start);
+    p_gidx.upload(gidx);
+    p_lidx.upload(P.lidx);
+    p_ecolor.upload(P.ecolor);
+    p_pnode_start.upload(P.pnode_start);
+    p_pnode.upload(P.pnode);
+    p_pslot.upload(P.pslot);
+    p_eset.upload(eset);
+    if (nkv > 0) p_ekv.upload(ekv);
+    p_snode.upload(P.snode);
+    p_sstart.upload(P.sstart);
+    fhalo.alloc(std::max<size_t>(P.nslots, 1) * ndof);
+    fhalo.zero();
+    // heterogeneous media (one coefficient block per element): re-lay the planes patch-major so
+    // that each thread of the patch kernel streams them with unit stride
+    p_hetero = (ncoefsets == nelem);
+    if (p_hetero) {
+      std::vector<T> pc((size_t)nelem * nelast * n2);
+      for (int p = 0; p < P.npatch; ++p) {
+        const int es = P.pelem_start[p], cnt = P.pelem_start[p + 1] - es;
+        const size_t base = (size_t)es * nelast * n2;
+        const size_t nthr = (size_t)cnt * ngll;
+        for (int el = 0; el < cnt; ++el) {
+          const double* src = h_coef.data() + (size_t)h_elem2set[P.elems[es + el]] * nelast * n2;
+          for (int pl = 0; pl < nelast; ++pl)
+            for (int j = 0; j < ngll; ++j)
+              for (int i = 0; i < ngll; ++i)
+                pc[base + ((size_t)pl * ngll + i) * nthr + (size_t)el * ngll + j] =
+                    (T)src[(size_t)pl * n2 + i + ngll * j];
+        }
+      }
+      p_coef.upload(pc);
+    }
+  }
+
+  void commit(int variant_) override {
+    S2D_REQUIRE(!committed, "commit called twice");
+    S2D_REQUIRE(nelast > 0, "commit: s2d_set_elastic was not called");
+    S2D_REQUIRE(variant_ >= 0 && variant_ <= 2, "commit: unknown assembly variant");
+    variant = variant_;
+    if (nkv == 0) h_elem2kv.assign(nelem, -1);
+    build_color_plan();
+    if (variant == S2D_ASM_PATCH) build_patch_plan_dev();
+    if (!h_src_iglob.empty()) {
+      src_iglob.upload(h_src_iglob);
+      src_dir.upload(h_src_dir);
+    }
+    committed = true;
+    // it = 0 outputs: BC_write(bc,0) at the end of BC_init (bc_gen.f90:249), REC_store(rec,0) (main.f90:35)
+    launch_outputs();
+    S2D_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  // ---- launches ------------------------------------------------------------------------
+  int grid_for(size_t n, int block = 256) const {
+    size_t g = (n + block - 1) / block;
+    return (int)std::min<size_t>(g, 148 * 16);
+  }
+
+  bool needs_zero_f() const { return variant != S2D_ASM_PATCH; }
+
+  // f = -K d  (compute_Fint, solver.f90:273-320); f must be zero on entry unless the patch variant
+  void launch_fint(const T* dd, const T* vv, T* ff) {
+    if (variant == S2D_ASM_PATCH) {
+      launch_patch(dd, vv, ff);
+      return;
+    }
+    ElemArgs<T> A{};
+    A.ibool = ibool.p;
+    A.a = coef.p;
+    A.elem2set = elem2set.p;
+    A.elem2kv = nkv > 0 ? elem2kv.p : nullptr;
+    A.eta = eta.p;
+    A.H = H.p;
+    A.d = dd;
+    A.v = vv;
+    A.f = ff;
+    A.npoin = npoin;
+    A.nelast = nelast;
+    A.kd2 = kd2;
+    if (variant == S2D_ASM_ATOMIC) {
+      A.elist = nullptr;
+      A.ne = nelem;
+      if (ndof == 1) launch_elem_node<T, 1, true>(ngll, A, stream);
+      else launch_elem_node<T, 2, true>(ngll, A, stream);
+      launches++;
+    } else {
+      for (int c = 0; c < ncolors; ++c) {
+        A.elist = color_elems.p + color_start[c];
+        A.ne = color_start[c + 1] - color_start[c];
+        if (ndof == 1) launch_elem_node<T, 1, false>(ngll, A, stream);
+        else launch_elem_node<T, 2, false>(ngll, A, stream);
+        launches++;
+      }
+    }
+    S2D_CUDA(cudaGetLastError());
+  }
+
+  template <int N>
+  void launch_patch_n(const T* dd, const T* vv, T* ff) {
+    PatchArgs<T, N> A{};
+    A.npatch = plan.npatch;
+    A.EP = plan.EP;
+    A.max_nloc = plan.max_nloc;
+    A.max_colors = plan.max_colors;
+    A.pelem_start = p_pelem_start.p;
+    A.gidx = p_gidx.p;
+    A.lidx = p_lidx.p;
+    A.ecolor = p_ecolor.p;
+    A.pnode_start = p_pnode_start.p;
+    A.pnode = p_pnode.p;
+    A.pslot = p_pslot.p;
+    A.eset = p_eset.p;
+    A.ekv = nkv > 0 ? p_ekv.p : nullptr;
+    A.a = p_hetero ? p_coef.p : coef.p;
+    A.eta = eta.p;
+    A.d = dd;
+    A.v = vv;
+    A.f = ff;
+    A.fhalo = fhalo.p;
+    A.npoin = npoin;
+    A.nslots = std::max<size_t>(plan.nslots, 1);
+    A.nelast = nelast;
+    A.kd2 = kd2;
+    A.hetero = p_hetero ? 1 : 0;
+    for (int k = 0; k < N * N; ++k) A.H[k] = (T)h_H[k];
+    if (ndof == 1) launch_elem_patch_n<T, N, 1>(A, stream);
+    else launch_elem_patch_n<T, N, 2>(A, stream);
+    launches++;
+    const int ns = (int)plan.snode.size();
+    if (ns > 0) {
+      k_halo_sum<T><<<ceil_div(ns, 256), 256, 0, stream>>>(ff, fhalo.p, p_snode.p, p_sstart.p, ns, npoin,
+                                                           A.nslots, ndof);
+      launches++;
+    }
+    S2D_CUDA(cudaGetLastError());
+  }
+  void launch_patch(const T* dd, const T* vv, T* ff) {
+    switch (ngll) {
+      case 3: launch_patch_n<3>(dd, vv, ff); break;
+      case 4: launch_patch_n<4>(dd, vv, ff); break;
+      case 5: launch_patch_n<5>(dd, vv, ff); break;
+      case 6: launch_patch_n<6>(dd, vv, ff); break;
+      case 7: launch_patch_n<7>(dd, vv, ff); break;
+      case 8: launch_patch_n<8>(dd, vv, ff); break;
+      case 9: launch_patch_n<9>(dd, vv, ff); break;
+      case 10: launch_patch_n<10>(dd, vv, ff); break;
+      default: throw ArgError("ngll must be in 3..10");
+    }
+  }
+
+  void launch_bcs() {
+    const T* D = d.p;
+    const T* V = v.p;
+    T* f = a.p;
+    // bc_gen.f90:273-281: absorbing boundaries first, then the others in input order
+    for (auto& r : bc_order)
+      if (r.kind == BC_ABSO) {
+        AbsoBc& b = *abso[r.index];
+        k_abso<T><<<ceil_div(b.dev.np, 128), 128, 0, stream>>>(b.dev, D, V, f, npoin);
+        launches++;
+      }
+    for (auto& r : bc_order) {
+      if (r.kind == BC_DIRNEU) {
+        DirneuBc& b = *dirneu[r.index];
+        const bool has_stf = b.B_h.p || b.B_v.p;
+        if (b.kind_h == 2 || b.kind_v == 2 || has_stf) {
+          k_dirneu<T><<<ceil_div(b.np, 128), 128, 0, stream>>>(f, npoin, ndof, b.np, b.node.p, b.kind_h, b.kind_v,
+                                                               b.B_h.p, b.B_v.p, bc_ampli.p, n_neumann_slots,
+                                                               b.slot, ctl.p);
+          launches++;
+        }
+      } else if (r.kind == BC_DYNFLT) {
+        FaultBc& b = *faults[r.index];
+        k_dynflt<T><<<ceil_div(b.dev.np, 64), 64, 0, stream>>>(b.dev, f, V, D, npoin, ctl.p);
+        launches++;
+      }
+    }
+  }
+
+  void launch_outputs() {
+    if (rec.present) {
+      const T* fld = rec.field == 'D' ? d.p : (rec.field == 'V' ? v.p : a.p);
+      k_rec_store<T><<<ceil_div((long long)rec.dev.nx * ndof, 128), 128, 0, stream>>>(rec.dev, fld, npoin, ctl.p);
+      launches++;
+    }
+    for (auto& b : faults) {
+      k_dynflt_write<T><<<1, 256, 0, stream>>>(b->dev, d.p, v.p, npoin, ctl.p);
+      launches++;
+    }
+  }
+
+  void launch_step() {
+    const size_t nd = npoin * ndof;
+    const T dt = (T)scheme.dt;
+    k_tick<<<1, 1, 0, stream>>>(ctl.p);
+    launches++;
+    const int zf = needs_zero_f() ? 1 : 0;
+    if (scheme.kind == 0) {
+      k_predict_leapfrog<T><<<grid_for(nd), 256, 0, stream>>>(d.p, v.p, a.p, nd, dt, zf);
+    } else {
+      const T c1 = (T)((0.5 - scheme.beta) * scheme.dt * scheme.dt), c2 = (T)((1.0 - scheme.gamma) * scheme.dt);
+      k_predict_newmark<T><<<grid_for(nd), 256, 0, stream>>>(d.p, v.p, a.p, nd, dt, c1, c2, zf);
+    }
+    launches++;
+    launch_fint(d.p, v.p, a.p);
+    if (!h_src_iglob.empty()) {
+      const int ns = (int)h_src_iglob.size();
+      k_sources<T><<<ceil_div(ns, 32), 32, 0, stream>>>(a.p, npoin, ndof, ns, src_iglob.p, src_dir.p,
+                                                        src_ampli.p, ctl.p);
+      launches++;
+    }
+    launch_bcs();
+    T c3, c4;
+    if (scheme.kind == 0) {
+      c3 = dt;
+      c4 = 0;
+    } else {
+      c3 = (T)(scheme.gamma * scheme.dt);
+      c4 = (T)(scheme.beta * scheme.dt * scheme.dt);
+    }
+    k_correct<T><<<grid_for(nd), 256, 0, stream>>>(d.p, v.p, a.p, rmass.p, nd, c3, c4);
+    launches++;
+    launch_outputs();
+  }
+
+  void check_device_error() {
+    StepCtl c;
+    S2D_CUDA(cudaMemcpyAsync(&c, ctl.p, sizeof(c), cudaMemcpyDeviceToHost, stream));
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    if (c.err == 1) throw StateError("NR_Solver has exceeded the maximum iterations (200)");
+    if (c.err == 2) throw StateError("NR_Solver could not bracket a root");
+  }
+
+  void step(int nsteps, const double* srca, const double* bca) override {
+    S2D_REQUIRE(committed, "step before commit");
+    S2D_REQUIRE(nsteps >= 0, "nsteps < 0");
+    if (nsteps == 0) return;
+    const size_t ns = h_src_iglob.size();
+    if (ns > 0) {
+      S2D_REQUIRE(srca != nullptr, "step: src_ampli missing");
+      const size_t need = ns * nsteps;
+      if (need > src_ampli_cap) {
+        S2D_CUDA(cudaStreamSynchronize(stream));
+        src_ampli.alloc(need);
+        src_ampli_cap = need;
+      }
+      S2D_CUDA(cudaMemcpyAsync(src_ampli.p, srca, need * sizeof(double), cudaMemcpyHostToDevice, stream));
+    }
+    bool any_stf = false;
+    for (auto& b : dirneu) any_stf = any_stf || b->B_h.p || b->B_v.p;
+    if (any_stf) {
+      S2D_REQUIRE(bca != nullptr, "step: bc_ampli missing");
+      const size_t need = (size_t)n_neumann_slots * nsteps;
+      if (need > bc_ampli_cap) {
+        S2D_CUDA(cudaStreamSynchronize(stream));
+        bc_ampli.alloc(need);
+        bc_ampli_cap = need;
+      }
+      S2D_CUDA(cudaMemcpyAsync(bc_ampli.p, bca, need * sizeof(double), cudaMemcpyHostToDevice, stream));
+    }
+    const int it0 = it + 1;
+    S2D_CUDA(cudaMemcpyAsync(&ctl.p->it0, &it0, sizeof(int), cudaMemcpyHostToDevice, stream));
+    S2D_CUDA(cudaMemcpyAsync(&ctl.p->nrows, &nsteps, sizeof(int), cudaMemcpyHostToDevice, stream));
+    for (int k = 0; k < nsteps; ++k) launch_step();
+    it += nsteps;
+    S2D_CUDA(cudaGetLastError());
+    check_device_error();
+  }
+
+  void compute_fint(double* out) override {
+    S2D_REQUIRE(committed, "compute_fint before commit");
+    const size_t nd = npoin * ndof;
+    if (scratch.n != nd) scratch.alloc(nd);
+    scratch.zero(stream);
+    launch_fint(d.p, v.p, scratch.p);
+    download(scratch, out);
+  }
+
+  // ---- field transfer ------------------------------------------------------------------
+  void upload_field(DevBuf<T>& dst, const double* src) {
+    if (!src) return;
+    const size_t nd = npoin * ndof;
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    if (sizeof(T) == 8) {
+      S2D_CUDA(cudaMemcpy(dst.p, src, nd * 8, cudaMemcpyHostToDevice));
+    } else {
+      std::vector<T> tmp(nd);
+      for (size_t q = 0; q < nd; ++q) tmp[q] = (T)src[q];
+      S2D_CUDA(cudaMemcpy(dst.p, tmp.data(), nd * sizeof(T), cudaMemcpyHostToDevice));
+    }
+  }
+  void download(const DevBuf<T>& src, double* dst) {
+    if (!dst) return;
+    const size_t nd = npoin * ndof;
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    if (sizeof(T) == 8) {
+      S2D_CUDA(cudaMemcpy(dst, src.p, nd * 8, cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<T> tmp(nd);
+      S2D_CUDA(cudaMemcpy(tmp.data(), src.p, nd * sizeof(T), cudaMemcpyDeviceToHost));
+      for (size_t q = 0; q < nd; ++q) dst[q] = (double)tmp[q];
+    }
+  }
+  void set_fields(const double* dd, const double* vv, const double* aa) override {
+    upload_field(d, dd);
+    upload_field(v, vv);
+    upload_field(a, aa);
+  }
+  void get_fields(double* dd, double* vv, double* aa) override {
+    download(d, dd);
+    download(v, vv);
+    download(a, aa);
+  }
+
+  void get_seis(float* sis) override {
+    S2D_REQUIRE(rec.present, "get_seis: no receivers");
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    rec.sis.download(sis);
+  }
+  void get_fault(int id, float* records, int32_t* nout, double* potency, int32_t* ncalls) override {
+    S2D_REQUIRE(id >= 0 && id < (int)faults.size(), "get_fault: bad fault id");
+    FaultBc& b = *faults[id];
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    std::vector<int> ost = b.ostate.to_host();
+    if (nout) *nout = ost[1];
+    if (ncalls) *ncalls = ost[2];
+    if (records && ost[1] > 0)
+      S2D_CUDA(cudaMemcpy(records, b.records.p, (size_t)ost[1] * 6 * b.dev.onx * sizeof(float), cudaMemcpyDeviceToHost));
+    if (potency && ost[2] > 0)
+      S2D_CUDA(cudaMemcpy(potency, b.potency.p, (size_t)ost[2] * 2 * (ndof + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  void get_fault_state(int id, double* D, double* V, double* T_, double* Tstick, double* MU, double* theta,
+                       double* sigma) override {
+    S2D_REQUIRE(id >= 0 && id < (int)faults.size(), "get_fault_state: bad fault id");
+    FaultBc& b = *faults[id];
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    if (D) b.D.download(D);
+    if (V) b.V.download(V);
+    if (T_) b.T.download(T_);
+    if (Tstick) b.Tstick.download(Tstick);
+    if (MU) b.MU.download(MU);
+    if (sigma) b.sigma.download(sigma);
+    if (theta) {
+      if (b.dev.rsf_kind) b.rsf_theta.download(theta);
+      else if (b.dev.swf_kind) b.swf_theta.download(theta);
+      else std::fill(theta, theta + b.dev.np, 0.0);
+    }
+  }
+
+  double reduce_absmax(const DevBuf<T>& x) {
+    const int g = std::min<int>(1024, grid_for(x.n));
+    k_absmax<T><<<g, 256, 0, stream>>>(x.p, x.n, partial.p);
+    launches++;
+    std::vector<double> h(g);
+    S2D_CUDA(cudaMemcpyAsync(h.data(), partial.p, g * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    double m = 0;
+    for (double x_ : h) m = std::max(m, x_);
+    return m;
+  }
+  void progress(double* vmax, double* dmax) override {
+    if (vmax) *vmax = reduce_absmax(v);
+    if (dmax) *dmax = reduce_absmax(d);
+  }
+  double energy() override {
+    S2D_REQUIRE(mass.n == npoin, "energy: s2d_set_mass was not called");
+    const int g = std::min<int>(1024, grid_for(npoin));
+    k_kinetic<T><<<g, 256, 0, stream>>>(v.p, mass.p, npoin, ndof, partial.p);
+    launches++;
+    std::vector<double> h(g);
+    S2D_CUDA(cudaMemcpyAsync(h.data(), partial.p, g * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    double s = 0;
+    for (double x_ : h) s += x_;
+    return 0.5 * s;
+  }
+  void get_coloring(int32_t* nc, int32_t* color) override {
+    S2D_REQUIRE(committed, "get_coloring before commit");
+    if (nc) *nc = ncolors;
+    if (color) std::copy(h_color.begin(), h_color.end(), color);
+  }
+
+  float time_fint(int reps) override {
+    S2D_REQUIRE(committed && reps > 0, "time_fint: not committed or reps <= 0");
+    const size_t nd = npoin * ndof;
+    if (scratch.n != nd) scratch.alloc(nd);
+    scratch.zero(stream);
+    cudaEvent_t e0, e1;
+    S2D_CUDA(cudaEventCreate(&e0));
+    S2D_CUDA(cudaEventCreate(&e1));
+    launch_fint(d.p, v.p, scratch.p);  // warm
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    S2D_CUDA(cudaEventRecord(e0, stream));
+    for (int r = 0; r < reps; ++r) launch_fint(d.p, v.p, scratch.p);
+    S2D_CUDA(cudaEventRecord(e1, stream));
+    S2D_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    S2D_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms / reps;
+  }
+  float time_steps(int nsteps) override {
+    S2D_REQUIRE(committed && nsteps > 0, "time_steps: not committed or nsteps <= 0");
+    S2D_REQUIRE(h_src_iglob.empty() || src_ampli_cap > 0, "time_steps: call s2d_step once first to load the stf table");
+    cudaEvent_t e0, e1;
+    S2D_CUDA(cudaEventCreate(&e0));
+    S2D_CUDA(cudaEventCreate(&e1));
+    // the stf tables of the last s2d_step call are replayed cyclically (row = (it-it0) mod nrows)
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    S2D_CUDA(cudaEventRecord(e0, stream));
+    for (int k = 0; k < nsteps; ++k) launch_step();
+    S2D_CUDA(cudaEventRecord(e1, stream));
+    S2D_CUDA(cudaEventSynchronize(e1));
+    it += nsteps;
+    float ms = 0;
+    S2D_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    check_device_error();
+    return ms;
+  }
+};
+
+}  // namespace s2d

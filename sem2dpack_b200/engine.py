@@ -1,0 +1,195 @@
+"""Object wrapper over the C-ABI handle.  Method names follow the reference's module entry points
+they stand for (SRC/solver.f90 `solve`, SRC/bc_gen.f90 `BC_*`, SRC/receivers.f90 `REC_*`)."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import (S2D_ASM_PATCH, DynfltDesc, S2DError, Scheme, _f64, _i32, _pd, _pi, _ptr)
+
+
+class Engine:
+    """One device-resident SEM2DPACK problem (problem_type, SRC/problem_class.f90:19-46)."""
+
+    def __init__(self, ngll, ndof, ibool, hprime, rmass, scheme_kind, dt, beta=0.0, gamma=0.5, alpha=1.0,
+                 precision=8, device=-1, _handle=None):
+        self.L = capi.lib()
+        self._keep = []
+        if _handle is not None:
+            self.h = _handle
+            return
+        ibool = _i32(ibool)
+        rmass = _f64(rmass)
+        hprime = _f64(hprime)
+        n2 = ngll * ngll
+        nelem = ibool.size // n2
+        npoin = rmass.size // ndof
+        self.ngll, self.ndof, self.nelem, self.npoin = ngll, ndof, nelem, npoin
+        self.dt = dt
+        sch = Scheme(scheme_kind, dt, beta, gamma, alpha)
+        h = C.c_void_p()
+        rc = self.L.s2d_create(C.byref(h), ngll, ndof, nelem, npoin, _ptr(ibool), _ptr(hprime), _ptr(rmass),
+                               precision, C.byref(sch), device)
+        if rc != 0:
+            raise S2DError(rc, self.L.s2d_last_error(None).decode())
+        self.h = h
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise S2DError(rc, self.L.s2d_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.s2d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration (what init_main hands over, SRC/init.f90:16-131) ---------------------
+    def set_elastic(self, nelast, a, elem2set, kd2):
+        a = _f64(a)
+        ncoefsets = a.size // (self.ngll * self.ngll * nelast)
+        self._ck(self.L.s2d_set_elastic(self.h, nelast, ncoefsets, _ptr(a), _ptr(_i32(elem2set)), int(kd2)))
+
+    def set_kv(self, elem_ids, eta):
+        elem_ids = _i32(elem_ids)
+        self._ck(self.L.s2d_set_kv(self.h, elem_ids.size, _ptr(elem_ids), _ptr(_f64(eta))))
+
+    def set_mass(self, mass):
+        self._ck(self.L.s2d_set_mass(self.h, _ptr(_f64(mass))))
+
+    def add_abso(self, node, Cmat, is_flat=True, n=None, stacey=False, bibool=None, K=None):
+        node = _i32(node)
+        bibool = _i32(bibool)
+        nbe = 0 if bibool is None else bibool.size // self.ngll
+        self._ck(self.L.s2d_add_abso(self.h, node.size, _ptr(node), _ptr(_f64(Cmat)), int(is_flat), _ptr(_f64(n)),
+                                     int(stacey), nbe, _ptr(bibool), _ptr(_f64(K))))
+
+    def add_dirneu(self, node, kind_h, kind_v, B_h=None, B_v=None):
+        node = _i32(node)
+        self._ck(self.L.s2d_add_dirneu(self.h, node.size, _ptr(node), kind_h, kind_v, _ptr(_f64(B_h)),
+                                       _ptr(_f64(B_v))))
+
+    def add_dynflt(self, **kw):
+        """Keyword names are the fields of s2d_dynflt_desc."""
+        d = DynfltDesc()
+        keep = []
+        for name, ctype in DynfltDesc._fields_:
+            val = kw.get(name)
+            if ctype is capi._PD:
+                arr = _f64(val)
+                keep.append(arr)
+                setattr(d, name, _pd(arr))
+            elif ctype is capi._PI:
+                arr = _i32(val)
+                keep.append(arr)
+                setattr(d, name, _pi(arr))
+            elif val is not None:
+                setattr(d, name, val)
+        fid = C.c_int32(-1)
+        self._ck(self.L.s2d_add_dynflt(self.h, C.byref(d), C.byref(fid)))
+        return fid.value
+
+    def add_force(self, iglob, direction):
+        sid = C.c_int32(-1)
+        self._ck(self.L.s2d_add_force(self.h, int(iglob), _ptr(_f64(direction)), C.byref(sid)))
+        return sid.value
+
+    def add_receivers(self, field, isamp, nt_rec, iglob=None, einterp=None, interp=None):
+        at_node = iglob is not None
+        nx = (_i32(iglob) if at_node else _i32(einterp)).size
+        self.rec_shape = (self.ndof, nx, nt_rec)
+        self._ck(self.L.s2d_add_receivers(self.h, nx, field.encode()[:1], isamp, nt_rec, int(at_node),
+                                          _ptr(_i32(iglob)), _ptr(_i32(einterp)), _ptr(_f64(interp))))
+
+    def commit(self, variant=S2D_ASM_PATCH):
+        self._ck(self.L.s2d_commit(self.h, variant))
+
+    # -- time loop ----------------------------------------------------------------------------
+    def set_fields(self, d=None, v=None, a=None):
+        self._ck(self.L.s2d_set_fields(self.h, _ptr(_f64(d)), _ptr(_f64(v)), _ptr(_f64(a))))
+
+    def get_fields(self):
+        n = self.npoin * self.ndof
+        d, v, a = np.empty(n), np.empty(n), np.empty(n)
+        self._ck(self.L.s2d_get_fields(self.h, _ptr(d), _ptr(v), _ptr(a)))
+        return d, v, a
+
+    def step(self, nsteps=1, src_ampli=None, bc_ampli=None):
+        """nsteps passes of the loop body of SRC/main.f90:51-99 (solve + REC_store + BC_write)."""
+        self._ck(self.L.s2d_step(self.h, nsteps, _ptr(_f64(src_ampli)), _ptr(_f64(bc_ampli))))
+
+    def compute_fint(self):
+        f = np.empty(self.npoin * self.ndof)
+        self._ck(self.L.s2d_compute_fint(self.h, _ptr(f)))
+        return f
+
+    @property
+    def it(self):
+        v = C.c_int32()
+        self._ck(self.L.s2d_get_it(self.h, C.byref(v)))
+        return v.value
+
+    def seis(self):
+        """(nt, nx, ndof) float32 like rec%sis (SRC/receivers.f90:12)."""
+        nd, nx, nt = self.rec_shape
+        s = np.empty(nd * nx * nt, np.float32)
+        self._ck(self.L.s2d_get_seis(self.h, _ptr(s)))
+        return s.reshape(nd, nx, nt).transpose(2, 1, 0)
+
+    def fault(self, fid, onx):
+        nout, ncalls = C.c_int32(), C.c_int32()
+        self._ck(self.L.s2d_get_fault(self.h, fid, None, C.byref(nout), None, C.byref(ncalls)))
+        rec = np.empty((max(nout.value, 0), 6, onx), np.float32)
+        pot = np.empty((max(ncalls.value, 0), 2 * (self.ndof + 1)))
+        self._ck(self.L.s2d_get_fault(self.h, fid, _ptr(rec), C.byref(nout), _ptr(pot), C.byref(ncalls)))
+        return rec, pot
+
+    def fault_state(self, fid, np_):
+        nd = self.ndof
+        out = dict(D=np.empty(np_ * nd), V=np.empty(np_ * nd), T=np.empty(np_ * 2), Tstick=np.empty(np_ * 2),
+                   MU=np.empty(np_), theta=np.empty(np_), sigma=np.empty(np_))
+        self._ck(self.L.s2d_get_fault_state(self.h, fid, *[_ptr(out[k]) for k in
+                                                           ("D", "V", "T", "Tstick", "MU", "theta", "sigma")]))
+        return out
+
+    def progress(self):
+        vm, dm = C.c_double(), C.c_double()
+        self._ck(self.L.s2d_progress(self.h, C.byref(vm), C.byref(dm)))
+        return vm.value, dm.value
+
+    def energy(self):
+        e = C.c_double()
+        self._ck(self.L.s2d_energy(self.h, C.byref(e)))
+        return e.value
+
+    def coloring(self):
+        nc = C.c_int32()
+        col = np.empty(self.nelem, np.int32)
+        self._ck(self.L.s2d_get_coloring(self.h, C.byref(nc), _ptr(col)))
+        return nc.value, col
+
+    def time_fint(self, reps):
+        ms = C.c_float()
+        self._ck(self.L.s2d_time_fint(self.h, reps, C.byref(ms)))
+        return ms.value
+
+    def time_steps(self, nsteps):
+        ms = C.c_float()
+        self._ck(self.L.s2d_time_steps(self.h, nsteps, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_int64()
+        self._ck(self.L.s2d_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def stream(self):
+        p = C.c_void_p()
+        self._ck(self.L.s2d_stream(self.h, C.byref(p)))
+        return p.value
