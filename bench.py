@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- GLL DOF-updates/s of the device-resident SEM2DPACK time loop on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nx NX --nz NZ]
+
+Workload (BASELINE.json configs[4]): synthetic Q4 structured mesh, NGLL=5, P-SV (ndof=2),
+heterogeneous elastic medium (one coefficient block per element), planar two-sided slip-weakening
+fault at mid height, absorbing boundaries on the 4 sides, Ricker point force, 128 receivers, leapfrog,
+Courant 0.5, FP64.  One step = one pass of the loop body of SRC/main.f90:51-99.
+At N > 1 each rank owns one x-strip of NX element columns (weak scaling, global mesh N*NX x NZ).
+Prints ONE JSON line (rank 0).  --impl reference times the CPU oracle (a port of the reference's
+serial Fortran path: no Fortran compiler exists in this image) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SEED = 20261017
+H = 100.0
+NGLL, NDOF, NELAST = 5, 2, 6
+W8 = 8
+# algorithmic bytes per DOF: K1 = read d, write f, read a, read ibool; step adds the node update
+B_K1 = (2 * NDOF * (NGLL - 1) ** 2 * W8 + NELAST * NGLL ** 2 * W8 + 4 * NGLL ** 2) / (NDOF * (NGLL - 1) ** 2)
+B_STEP = B_K1 + 6 * W8
+METRIC = "GLL DOF-updates/sec"
+UNIT = "DOF-updates/s"
+CPU_SAMPLE_N = 384      # oracle sample mesh (elements per side)
+CPU_SAMPLE_STEPS = 10
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                j = json.load(f)
+            if "hbm_gbs" in j:
+                return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_deck(nx, nz, nsteps):
+    """The same problem as build_engine() as a Par.inp for the oracle (tests/harness.cart_deck)."""
+    import harness
+    return harness.cart_deck(nx, nz, ngll=NGLL, ndof=NDOF, ezflt=nz // 2, scheme="leapfrog", courant=0.5,
+                             nsteps=nsteps, h=H, nrec=0)
+
+
+def cpu_oracle_rate(nx, nz, nsteps):
+    """DOF-updates/s of the CPU oracle (1 thread; the reference solver is serial) on a bounded sample."""
+    import orc
+    o = orc.Oracle(synthetic_deck(nx, nz, nsteps + 2), synthetic_seed=SEED)
+    ndofs = o.i("npoin") * o.i("ndof")
+    o.time_solve(1)
+    t = o.time_solve(nsteps)
+    o.close()
+    return ndofs * nsteps / t, t
+
+
+def build_engine(nx, nz, rank, world, device, nt_max, precision=8):
+    from sem2dpack_b200 import CartEngine
+    ez = nz // 2
+    e = CartEngine(NGLL, NDOF, nx, nz, (rank * nx * H, (rank + 1) * nx * H), (0.0, nz * H), ezflt=ez, seed=SEED,
+                   scheme_kind=0, courant=0.5, precision=precision, device=device, ix0=rank * nx * (NGLL - 1), iz0=0,
+                   halo_left=rank > 0, halo_right=rank < world - 1)
+    xg = world * nx * H
+    e.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, xg / 2, 1500.0, oixd=max(1, (nx * 4 + 1) // 512),
+                    oitd=10, nt_max=nt_max)
+    sides = [1, 3] + ([4] if rank == 0 else []) + ([2] if rank == world - 1 else [])
+    for s in sorted(sides):
+        e.add_abso_side(s, False)
+    nsrc = 0
+    xs, zs = 0.37 * xg, 0.61 * nz * H
+    if rank * nx * H <= xs < (rank + 1) * nx * H:
+        e.add_force_at(xs, zs, [-0.5, 0.8660254037844386])
+        nsrc = 1
+    x0, x1 = rank * nx * H, (rank + 1) * nx * H
+    e.add_receiver_line(128, (x0 + 0.05 * nx * H, 0.75 * nz * H), (x1 - 0.05 * nx * H, 0.75 * nz * H), "V", 1, nt_max + 1)
+    return e, nsrc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = CPU_SAMPLE_N
+    rates = []
+    t0 = time.time()
+    for _ in range(max(1, min(args.steps, 3))):
+        r, _ = cpu_oracle_rate(n, n, CPU_SAMPLE_STEPS)
+        rates.append(r)
+        if time.time() - t0 > 150:
+            break
+    val = statistics.median(rates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic {args.nx}x{args.nz} Q4, NGLL=5, P-SV heterogeneous + planar fault, leapfrog"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"oracle (C++ port of the serial Fortran path; no Fortran compiler in the image), "
+                                   f"{n}x{n}-element sample of the same workload, {CPU_SAMPLE_STEPS} solve() steps x "
+                                   f"{len(rates)} repeats, 1 thread (the reference is serial)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--nx", type=int, default=8192)
+    ap.add_argument("--nz", type=int, default=8192)
+    ap.add_argument("--precision", type=int, default=8)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fint-reps", type=int, default=10)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sem2dpack_b200 import S2DError
+    from sem2dpack_b200.stf import Ricker
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, args.warmup
+    nt_max = 2 * (K + W) + 16
+    # build, falling back to a shorter mesh if 180 GB cannot hold the requested one
+    nx, nz = args.nx, args.nz
+    e = None
+    tried = []
+    for nzt in [nz, (nz * 3) // 4, nz // 2, nz // 4]:
+        try:
+            e, nsrc = build_engine(nx, nzt, rank, world, local, nt_max, args.precision)
+            e.commit()
+            nz = nzt
+            break
+        except S2DError as ex:
+            tried.append(f"{nx}x{nzt}: {ex}")
+            e = None
+            torch.cuda.empty_cache()
+    if e is None:
+        raise SystemExit("could not build the workload: " + "; ".join(tried))
+    if world > 1:
+        from sem2dpack_b200.strips import attach_halo_exchange
+        attach_halo_exchange(e, rank, world)
+    ndofs_rank = e.npoin * NDOF
+    ric = Ricker(2.0, 0.6, 1.0e9)
+
+    def table(it_first, n):
+        return ric.table(it_first, n, e.dt) if nsrc else None
+
+    # warm-up (also loads the stf table that the timed replay cycles through)
+    barrier()
+    e.step(W, table(1, W))
+    barrier()
+    # --- device-resident timing: K steps between CUDA events on the engine stream
+    l0 = e.launch_count()
+    clk = ClockSampler(local)
+    barrier()
+    ms = e.time_steps(K)
+    barrier()
+    clocks = clk.stop()
+    launches = e.launch_count() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = ndofs_rank * world * K / (ms_max * 1e-3)
+    # --- dominant kernel alone (element force + assembly), CUDA events
+    barrier()
+    ms_fint = e.time_fint(args.fint_reps)
+    barrier()
+    peak, peak_src = peaks()
+    ach = B_K1 * ndofs_rank / (ms_fint * 1e-3) / 1e9
+    # --- end to end through the public API with host buffers: one s2d_step per step with that
+    # step's stf row (H2D) and a read-back of the step's seismogram row (D2H)
+    it0 = e.it
+    n_e2e = max(5, min(K, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        e.step(1, table(it0 + 1 + k, 1))
+        row = e.seis_row(it0 + 1 + k)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = ndofs_rank * world * n_e2e / float(te.item())
+    vmax, dmax = e.progress()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if args.precision == 8 else "f32", "data": "synthetic",
+        "config": {"workload": f"synthetic {nx * world}x{nz} Q4 structured mesh ({nx}x{nz} x-strip per GPU), NGLL=5, "
+                               "ndof=2 heterogeneous elastic (one a(5,5,6) block per element) + planar two-sided SWF "
+                               "fault + ABSORB on 4 sides, leapfrog, Courant 0.5, 128 receivers/GPU",
+                   "npoin_per_gpu": e.npoin, "nelem_per_gpu": e.nelem, "dt": e.dt,
+                   "l2_policy": "working set (>=100 GB per GPU at the default size) far exceeds the 126 MB L2",
+                   "requested": f"{args.nx}x{args.nz}", "fallbacks_tried": tried},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "k_elem_patch + k_cart_halo_sum (K1)",
+                     "algorithmic_bytes_per_dof": B_K1, "ms_per_launch": ms_fint,
+                     "full_step": {"algorithmic_bytes_per_dof": B_STEP,
+                                   "achieved": B_STEP * value / world / 1e9, "frac": B_STEP * value / world / 1e9 / peak}},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 8 * nsrc, "d2h_bytes_per_step": int(row.nbytes),
+                "steps": n_e2e},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "check": {"vmax": vmax, "dmax": dmax},
+    }
+    if rank == 0 and not args.no_cpu:
+        r, tcpu = cpu_oracle_rate(CPU_SAMPLE_N, CPU_SAMPLE_N, CPU_SAMPLE_STEPS)
+        line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"oracle (C++ port of the serial Fortran path), {CPU_SAMPLE_N}x{CPU_SAMPLE_N}"
+                                          f"-element sample of the same workload, {CPU_SAMPLE_STEPS} solve() steps, "
+                                          f"{tcpu:.1f} s, 1 thread; of {os.cpu_count()} host cores"}
+    if rank == 0:
+        print(json.dumps(line))
+    e.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -160,6 +160,9 @@ int s2d_get_it(s2d_handle h, int32_t* it);
 /* REC_write's payload (receivers.f90:351-392): sis(nt_rec,nx,ndof) float32. */
 int s2d_get_seis(s2d_handle h, float* sis);
 
+/* one sample of every trace: row(nx,ndof) float32 = sis(it/isamp+1,:,:); it must be a sampled step. */
+int s2d_get_seis_row(s2d_handle h, int32_t it, float* row);
+
 /* BC_DYNFLT_write's payload (bc_dynflt.f90:751-778): records[nout][6][onx] float32 in file order
  * (D, V, T1, T2, MU, Tstick); potency[ncalls][2*(ndof+1)] (one line of FltXX_potency_sem2d.tab
  * per BC_write call, the it=0 call included).  Either pointer may be NULL; counts always set. */

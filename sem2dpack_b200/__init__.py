@@ -5,6 +5,6 @@ include/sem2d_b200.h).  There is no CPU implementation here: importing works wit
 C-ABI can be inspected), but creating an engine without a CUDA device raises S2DError(S2D_ENODEV).
 """
 from .capi import (LEAPFROG, NEWMARK, S2D_ASM_ATOMIC, S2D_ASM_COLOR, S2D_ASM_PATCH, S2DError, lib)
-from .engine import Engine
+from .engine import CartEngine, Engine
 
-__all__ = ["Engine", "S2DError", "lib", "LEAPFROG", "NEWMARK", "S2D_ASM_PATCH", "S2D_ASM_COLOR", "S2D_ASM_ATOMIC"]
+__all__ = ["Engine", "CartEngine", "S2DError", "lib", "LEAPFROG", "NEWMARK", "S2D_ASM_PATCH", "S2D_ASM_COLOR", "S2D_ASM_ATOMIC"]

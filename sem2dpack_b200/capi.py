@@ -84,6 +84,7 @@ _SIGS = {
     "s2d_compute_fint": [C.c_void_p, C.c_void_p],
     "s2d_get_it": [C.c_void_p, C.POINTER(C.c_int32)],
     "s2d_get_seis": [C.c_void_p, C.c_void_p],
+    "s2d_get_seis_row": [C.c_void_p, C.c_int32, C.c_void_p],
     "s2d_get_fault": [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)],
     "s2d_get_fault_state": [C.c_void_p, C.c_int32] + [C.c_void_p] * 7,
     "s2d_progress": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],

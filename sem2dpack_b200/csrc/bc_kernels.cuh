@@ -51,6 +51,13 @@ __global__ void k_correct(T* __restrict__ d, T* __restrict__ v, T* __restrict__ 
   }
 }
 
+// rmass = 1/M once every boundary condition has had its say on M (init.f90:112-116)
+template <typename T>
+__global__ void k_invert(T* x, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) x[q] = (T)1 / x[q];
+}
+
 // ------------------------------------------------------------------------------------------
 // point forces: f(iglob,:) += dir*ampli(it)
 template <typename T>

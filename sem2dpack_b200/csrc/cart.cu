@@ -1,18 +1,963 @@
-// placeholder until the structured builder lands
+// Device-side structured builder: MESH_CART problems are generated directly in HBM.
+//
+// Restates, for the flat Cartesian Q4 box, what the reference's init does on the host:
+//   CART_build            SRC/mesh_cartesian.f90:219-314 (+ mesh_structured.f90:12-196), natural
+//                         element order (the OPT_RENUMBER=.false. setting of constants.f90:11)
+//   SE_init_numbering     SRC/spec_grid.f90:198-314   -> closed-form node ids (cart_node_id)
+//   MAT_ELAST_init_a      SRC/mat_elastic.f90:290-360 -> flat-grid planes (nelast 2 | 6)
+//   MAT_MASS_init         SRC/mat_mass.f90:29-61
+//   CHECK_grid/TIME_init  SRC/init.f90:145-289, SRC/time.f90:323-341 -> dt from the Courant number
+//   BC_ABSO_init          SRC/bc_abso.f90:115-266     (flat sides, P1 or Stacey)
+//   BC_DYNFLT_init        SRC/bc_dynflt.f90:231-520   (two-sided fault on tags 5,6, linear SWF)
+// and lays the result out for the CTA-patch kernel: rectangular tiles of elements, congruent tiles
+// sharing one cache-resident shape table, halo slots addressed in closed form.
+// The heterogeneous material is the counter-based hash model of the synthetic benchmark
+// (SURVEY.md 8d): values depend only on the global GLL lattice coordinates, so x-strips of one
+// global mesh built on different GPUs agree bit for bit.
+#include <map>
+
 #include "engine.hpp"
+
 namespace s2d {
-void cart_free(void*) {}
+
+// ---------------------------------------------------------------------------------------------
+// hash material (the benchmark's stand-in for a user-supplied heterogeneous model)
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
 }
+__host__ __device__ inline double hash_u(uint64_t seed, uint64_t ix, uint64_t iz, uint64_t k) {
+  uint64_t h = splitmix64(seed ^ splitmix64(ix * 0x9E3779B97F4A7C15ull + k) ^
+                          splitmix64(iz * 0xC2B2AE3D27D4EB4Full + 0x165667B19E3779F9ull * (k + 1)));
+  return (double)(h >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+}
+
+struct CartGeom {
+  int N, ndof, nx, nz, ezflt;
+  double x0, z0, hx, hz;
+  uint64_t seed;
+  long long ix0, iz0;
+  double rho, cp, cs;
+  int halo_left, halo_right;
+  // tiles
+  int PX, PZ, ntx, ntz_lo, ntz, Pmax, LXmax, LZmax;
+  double xgll[10], wgll[10];
+};
+
+__host__ __device__ inline bool row_detached(const CartGeom& G, int iz) {  // no element below shares nodes
+  return iz == 0 || (G.ezflt > 0 && iz == G.ezflt);
+}
+// new GLL nodes created by the first / any other element of a row (see the header comment)
+__host__ __device__ inline long long c_first(const CartGeom& G, bool B) {
+  const int m = G.N - 2;
+  return (long long)m * m + (long long)m * ((B ? 1 : 0) + 3) + (B ? 2 : 0) + 2;
+}
+__host__ __device__ inline long long c_other(const CartGeom& G, bool B) {
+  const int m = G.N - 2;
+  return (long long)m * m + (long long)m * ((B ? 1 : 0) + 2) + (B ? 1 : 0) + 1;
+}
+__host__ __device__ inline long long row_count(const CartGeom& G, bool B) {
+  return c_first(G, B) + (long long)(G.nx - 1) * c_other(G, B);
+}
+__host__ __device__ inline long long elem_base(const CartGeom& G, int ix, int iz) {
+  long long nB = 0;
+  if (iz > 0) nB = 1 + ((G.ezflt > 0 && iz > G.ezflt) ? 1 : 0);
+  long long base = nB * row_count(G, true) + ((long long)iz - nB) * row_count(G, false);
+  const bool B = row_detached(G, iz);
+  if (ix > 0) base += c_first(G, B) + (long long)(ix - 1) * c_other(G, B);
+  return base;
+}
+__host__ __device__ inline long long cart_npoin(const CartGeom& G) {
+  const long long nB = 1 + (G.ezflt > 0 ? 1 : 0);
+  return nB * row_count(G, true) + ((long long)G.nz - nB) * row_count(G, false);
+}
+// Global node id (1-based) of GLL point (i,j) (1-based) of element (ix,iz) (0-based) under the
+// traversal of SE_init_numbering (spec_grid.f90:249-287) in natural element order: the point is
+// first moved to the earliest element that contains it, where it is "new"; there the ids run
+// interior (i fastest), then the new edges in the order D,R,U,L with their counter-clockwise
+// interior points, then the new vertices SW,SE,NE,NW.
+__host__ __device__ inline long long cart_node_id(const CartGeom& G, int ix, int iz, int i, int j) {
+  const int N = G.N;
+  if (i == 1 && ix > 0) {
+    ix -= 1;
+    i = N;
+  }
+  if (j == 1 && !row_detached(G, iz)) {
+    iz -= 1;
+    j = N;
+  }
+  const bool B = row_detached(G, iz);
+  const bool Lf = (ix == 0);
+  const int m = N - 2;
+  long long o;
+  const bool ii = (i > 1 && i < N), jj = (j > 1 && j < N);
+  if (ii && jj) {
+    o = (i - 2) + (long long)m * (j - 2);
+  } else {
+    o = (long long)m * m;
+    const long long eD = o, eR = eD + (B ? m : 0), eU = eR + m, eL = eU + m, vs = eL + (Lf ? m : 0);
+    if (jj) {                    // vertical edges
+      if (i == N) o = eR + (j - 2);
+      else o = eL + (N - 1 - j);           // L edge, counter-clockwise = j descending
+    } else if (ii) {             // horizontal edges
+      if (j == 1) o = eD + (i - 2);
+      else o = eU + (N - 1 - i);           // U edge, counter-clockwise = i descending
+    } else {                     // vertices SW,SE,NE,NW
+      const long long vSW = vs, vSE = vSW + ((Lf && B) ? 1 : 0), vNE = vSE + (B ? 1 : 0), vNW = vNE + 1;
+      if (i == 1 && j == 1) o = vSW;
+      else if (i == N && j == 1) o = vSE;
+      else if (i == N && j == N) o = vNE;
+      else o = vNW;
+    }
+  }
+  return elem_base(G, ix, iz) + o + 1;
+}
+
+// material at GLL point (i,j) (0-based) of element (ix,iz)
+__host__ __device__ inline void cart_material(const CartGeom& G, int ix, int iz, int i, int j, double& rho,
+                                              double& cp, double& cs) {
+  if (G.seed == 0) {
+    rho = G.rho;
+    cp = G.cp;
+    cs = G.cs;
+    return;
+  }
+  const uint64_t gx = (uint64_t)(G.ix0 + (long long)ix * (G.N - 1) + i);
+  const uint64_t gz = (uint64_t)(G.iz0 + (long long)iz * (G.N - 1) + j);
+  const double u1 = hash_u(G.seed, gx, gz, 1), u2 = hash_u(G.seed, gx, gz, 2), u3 = hash_u(G.seed, gx, gz, 3);
+  cs = 3464.0 * (1.0 + 0.10 * u1);
+  cp = 1.7321 * cs * (1.0 + 0.02 * u2);
+  rho = 2670.0 * (1.0 + 0.05 * u3);
+}
+
+// tile geometry
+struct Tile {
+  int ex0, ez0, cx, cz;       // first element, extent in elements
+  int hasL, hasR, hasD, hasU; // connected neighbour tiles
+};
+__host__ __device__ inline Tile tile_of(const CartGeom& G, int tx, int tz) {
+  Tile t;
+  t.ex0 = tx * G.PX;
+  t.cx = min(G.PX, G.nx - t.ex0);
+  int zend;
+  if (tz < G.ntz_lo) {
+    t.ez0 = tz * G.PZ;
+    zend = G.ezflt;
+  } else {
+    t.ez0 = G.ezflt + (tz - G.ntz_lo) * G.PZ;
+    zend = G.nz;
+  }
+  t.cz = min(G.PZ, zend - t.ez0);
+  t.hasL = tx > 0;
+  t.hasR = tx < G.ntx - 1;
+  t.hasD = tz > 0 && tz != G.ntz_lo;
+  t.hasU = tz < G.ntz - 1 && tz != G.ntz_lo - 1;
+  return t;
+}
+__host__ __device__ inline int perim_index(int a, int b, int LX, int LZ) {
+  if (b == 0) return a;
+  if (b == LZ - 1) return LX + a;
+  if (a == 0) return 2 * LX + (b - 1);
+  return 2 * LX + (LZ - 2) + (b - 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+__global__ void k_cart_pnode(CartGeom G, const long long* __restrict__ pnode_start, int* __restrict__ pnode) {
+  const int p = blockIdx.x;
+  const int tx = p % G.ntx, tz = p / G.ntx;
+  const Tile t = tile_of(G, tx, tz);
+  const int LX = t.cx * (G.N - 1) + 1, LZ = t.cz * (G.N - 1) + 1;
+  const long long ps = pnode_start[p];
+  for (int l = threadIdx.x; l < LX * LZ; l += blockDim.x) {
+    const int a = l % LX, b = l / LX;
+    const int lx = min(a / (G.N - 1), t.cx - 1), lz = min(b / (G.N - 1), t.cz - 1);
+    const int i = a - lx * (G.N - 1), j = b - lz * (G.N - 1);
+    pnode[ps + l] = (int)(cart_node_id(G, t.ex0 + lx, t.ez0 + lz, i + 1, j + 1) - 1);
+  }
+}
+
+// flat-grid coefficient planes (mat_elastic.f90:323-358), written patch-major [plane][i][thread]
+template <typename T>
+__global__ void k_cart_coef(CartGeom G, const int* __restrict__ pelem_start, T* __restrict__ coef, int nelast) {
+  const int p = blockIdx.x;
+  const int tx = p % G.ntx, tz = p / G.ntx;
+  const Tile t = tile_of(G, tx, tz);
+  const int N = G.N, N2 = N * N;
+  const int cnt = t.cx * t.cz;
+  const size_t base = (size_t)pelem_start[p] * nelast * N2;
+  const size_t nthr = (size_t)cnt * N;
+  const double DxiDx = 2.0 / G.hx, DetaDz = 2.0 / G.hz;
+  const double det = (0.5 * G.hx) * (0.5 * G.hz);
+  for (int w = threadIdx.x; w < cnt * N2; w += blockDim.x) {
+    const int el = w / N2, k = w - el * N2;
+    const int i = k % N, j = k / N;
+    const int lx = el % t.cx, lz = el / t.cx;
+    double rho, cp, cs;
+    cart_material(G, t.ex0 + lx, t.ez0 + lz, i, j, rho, cp, cs);
+    const double la = rho * (cp * cp - 2.0 * cs * cs);
+    const double mu = rho * cs * cs;
+    const double weights = det * (G.wgll[i] * G.wgll[j]);
+    double av[6];
+    if (nelast == 2) {
+      av[0] = mu * DxiDx * DxiDx;
+      av[1] = mu * DetaDz * DetaDz;
+    } else {
+      const double Kx = la + 2.0 * mu;
+      av[0] = Kx * DxiDx * DxiDx;
+      av[1] = la * DxiDx * DetaDz;
+      av[2] = Kx * DetaDz * DetaDz;
+      av[3] = mu * DetaDz * DetaDz;
+      av[4] = mu * DxiDx * DetaDz;
+      av[5] = mu * DxiDx * DxiDx;
+    }
+    for (int pl = 0; pl < nelast; ++pl)
+      coef[base + ((size_t)pl * N + i) * nthr + (size_t)el * N + j] = (T)(-weights * av[pl]);
+  }
+}
+
+// assembled mass (mat_mass.f90:50-57): each node is summed by its first element, over the elements
+// that share it in ascending element order; virtual neighbour columns stand in for the elements of
+// an adjacent x-strip so that interface nodes carry the full mass on both ranks.
+template <typename T>
+__global__ void k_cart_mass(CartGeom G, T* __restrict__ mass, size_t npoin) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = G.N, N2 = N * N;
+  const long long total = (long long)G.nx * G.nz * N2;
+  if (w >= total) return;
+  const long long e = w / N2;
+  const int k = (int)(w - e * N2);
+  const int i = k % N, j = k / N;
+  const int ix = (int)(e % G.nx), iz = (int)(e / G.nx);
+  // canonical owner?
+  if (i == 0 && ix > 0) return;
+  if (j == 0 && !row_detached(G, iz)) return;
+  const double det = (0.5 * G.hx) * (0.5 * G.hz);
+  double sum = 0.0;
+  const bool up_ok = (j == N - 1) && (iz + 1 < G.nz) && !row_detached(G, iz + 1);
+  for (int dz = 0; dz <= (up_ok ? 1 : 0); ++dz)
+    for (int dx = -1; dx <= 1; ++dx) {
+      // elements containing the node in this row: dx=0 always; dx=+1 when on the right edge;
+      // dx=-1 only as the virtual column of the left neighbour strip
+      int eix = ix + dx, li = i;
+      if (dx == 1) {
+        if (i != N - 1) continue;
+        if (eix >= G.nx && !G.halo_right) continue;
+        li = 0;
+      } else if (dx == -1) {
+        if (!(i == 0 && ix == 0 && G.halo_left)) continue;
+        li = N - 1;
+      }
+      const int eiz = iz + dz;
+      const int lj = dz ? 0 : j;
+      double rho, cp, cs;
+      cart_material(G, eix, eiz, li, lj, rho, cp, cs);
+      sum = sum + rho * (det * (G.wgll[li] * G.wgll[lj]));
+    }
+  const size_t node = (size_t)(cart_node_id(G, ix, iz, i + 1, j + 1) - 1);
+  for (int c = 0; c < G.ndof; ++c) mass[node + npoin * c] = (T)sum;
+}
+
+// max over the grid of c / min(dx,dz) (CHECK_grid, init.f90:187-225)
+__global__ void k_cart_cfl(CartGeom G, unsigned long long* out) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = G.N, N2 = N * N;
+  const long long total = (long long)G.nx * G.nz * N2;
+  double r = 0.0;
+  if (w < total) {
+    const long long e = w / N2;
+    const int k = (int)(w - e * N2);
+    const int i = k % N, j = k / N;
+    if (i < N - 1 && j < N - 1) {
+      double rho, cp, cs;
+      cart_material(G, (int)(e % G.nx), (int)(e / G.nx), i, j, rho, cp, cs);
+      const double dx = 0.5 * G.hx * (G.xgll[i + 1] - G.xgll[i]);
+      const double dz = 0.5 * G.hz * (G.xgll[j + 1] - G.xgll[j]);
+      r = (G.ndof == 2 ? cp : cs) / fmin(dx, dz);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+  if ((threadIdx.x & 31) == 0 && r > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(r));
+}
+
+template <typename T>
+__global__ void k_add_mass(T* mass, size_t npoin, int ndof, int np, const int* node, const double* C, double coef) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= np) return;
+  for (int c = 0; c < ndof; ++c) {
+    const size_t q = (size_t)(node[k] - 1) + npoin * c;
+    mass[q] = (T)((double)mass[q] + coef * C[k + (size_t)np * c]);  // bc_abso.f90:243
+  }
+}
+template <typename T>
+__global__ void k_gather_nodes(const T* src, size_t npoin, int ndof, int np, const int* node, double* out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= np) return;
+  for (int c = 0; c < ndof; ++c) out[k + (size_t)np * c] = (double)src[(size_t)(node[k] - 1) + npoin * c];
+}
+
+// halo sum in closed form: one thread per (tile, perimeter node); the tile that holds the node on
+// neither a connected left nor a connected lower side owns it and adds the partial sums of the
+// tiles around it in ascending tile order.
+template <typename T>
+__global__ void k_cart_halo_sum(CartGeom G, T* __restrict__ f, const T* __restrict__ fhalo,
+                                const long long* __restrict__ pnode_start, const int* __restrict__ pnode,
+                                size_t npoin, size_t nslots) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long p = w / G.Pmax;
+  const int idx = (int)(w - p * G.Pmax);
+  if (p >= (long long)G.ntx * G.ntz) return;
+  const int tx = (int)(p % G.ntx), tz = (int)(p / G.ntx);
+  const Tile t = tile_of(G, tx, tz);
+  const int LX = t.cx * (G.N - 1) + 1, LZ = t.cz * (G.N - 1) + 1;
+  if (idx >= 2 * LX + 2 * (LZ - 2)) return;
+  int a, b;
+  if (idx < LX) { a = idx; b = 0; }
+  else if (idx < 2 * LX) { a = idx - LX; b = LZ - 1; }
+  else if (idx < 2 * LX + LZ - 2) { a = 0; b = idx - 2 * LX + 1; }
+  else { a = LX - 1; b = idx - (2 * LX + LZ - 2) + 1; }
+  const bool onL = (a == 0) && t.hasL, onR = (a == LX - 1) && t.hasR;
+  const bool onD = (b == 0) && t.hasD, onU = (b == LZ - 1) && t.hasU;
+  if (onL || onD) return;        // a lower-numbered tile owns it
+  if (!(onR || onU)) return;     // private node
+  const size_t g = (size_t)pnode[pnode_start[p] + a + (long long)LX * b];
+  for (int c = 0; c < G.ndof; ++c) {
+    const T* fh = fhalo + nslots * c;
+    T acc = fh[(size_t)p * G.Pmax + idx];
+    if (onR) {  // right tile: same row of tiles (same cz), node at (0,b)
+      const Tile tr = tile_of(G, tx + 1, tz);
+      acc += fh[(size_t)(p + 1) * G.Pmax + perim_index(0, b, tr.cx * (G.N - 1) + 1, LZ)];
+    }
+    if (onU) {  // upper tile: same cx, node at (a,0)
+      acc += fh[(size_t)(p + G.ntx) * G.Pmax + a];
+    }
+    if (onR && onU) acc += fh[(size_t)(p + G.ntx + 1) * G.Pmax + 0];
+    f[g + npoin * c] = acc;
+  }
+}
+
+// ibool in the reference layout (ngll,ngll,nelem), natural element order
+__global__ void k_cart_ibool(CartGeom G, int* __restrict__ ibool) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N2 = G.N * G.N;
+  const long long total = (long long)G.nx * G.nz * N2;
+  if (w >= total) return;
+  const long long e = w / N2;
+  const int k = (int)(w - e * N2);
+  ibool[w] = (int)cart_node_id(G, (int)(e % G.nx), (int)(e / G.nx), k % G.N + 1, k / G.N + 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GLL points, weights and derivative matrix (the quantities of SRC/gll.f90 get_GLL_info,
+// computed here by Newton iteration on (1-x^2) P'_{n-1}(x))
+static void legendre(int p, double x, double& P, double& dP) {
+  double p0 = 1.0, p1 = x;
+  if (p == 0) { P = 1.0; dP = 0.0; return; }
+  for (int k = 2; k <= p; ++k) {
+    const double pk = ((2.0 * k - 1.0) * x * p1 - (k - 1.0) * p0) / k;
+    p0 = p1;
+    p1 = pk;
+  }
+  P = p1;
+  dP = (x * x == 1.0) ? 0.5 * p * (p + 1) * ((p % 2 == 0 || x > 0) ? 1.0 : -1.0) : p * (p0 - x * p1) / (1.0 - x * x);
+}
+static void gll_tables(int n, double* x, double* w, double* H /* H[i + n*j] = h'_i(x_j) */) {
+  const int p = n - 1;
+  const double PI = 3.141592653589793;
+  x[0] = -1.0;
+  x[p] = 1.0;
+  for (int k = 1; k < p; ++k) {
+    double z = -std::cos(PI * k / p);
+    for (int itn = 0; itn < 100; ++itn) {
+      double P, dP;
+      legendre(p, z, P, dP);
+      // q(z) = P'_p(z); q'(z) from the Legendre ODE: (1-z^2) P'' = 2 z P' - p(p+1) P
+      const double ddP = (2.0 * z * dP - p * (p + 1.0) * P) / (1.0 - z * z);
+      const double dz = dP / ddP;
+      z -= dz;
+      if (std::fabs(dz) < 1e-16) break;
+    }
+    x[k] = z;
+  }
+  for (int k = 0; k <= p / 2; ++k) {  // enforce symmetry, middle point exactly 0 (gll.f90:27-28)
+    const double s = 0.5 * (x[p - k] - x[k]);
+    x[k] = -s;
+    x[p - k] = s;
+  }
+  if (n % 2 == 1) x[p / 2] = 0.0;
+  std::vector<double> Pv(n);
+  for (int k = 0; k < n; ++k) {
+    double P, dP;
+    legendre(p, x[k], P, dP);
+    Pv[k] = P;
+    w[k] = 2.0 / (p * (p + 1.0) * P * P);
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double v;
+      if (i != j) v = Pv[j] / (Pv[i] * (x[j] - x[i]));
+      else if (i == 0) v = -0.25 * p * (p + 1.0);
+      else if (i == p) v = 0.25 * p * (p + 1.0);
+      else v = 0.0;
+      H[i + n * j] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct CartState {
+  CartGeom G;
+  s2d_scheme scheme;
+  double courant, dt, grid_cfl;
+  double H[100];
+  bool mass_inverted = false;
+  double CoefA2V() const { return scheme.kind == 1 ? scheme.gamma * scheme.dt : scheme.dt; }        // time.f90:443-456
+  double CoefA2D() const { return scheme.kind == 1 ? scheme.beta * scheme.dt * scheme.dt : 0.0; }    // time.f90:426-440
+  double CoefA2Vrhs() const { return scheme.kind == 1 ? scheme.alpha * CoefA2V() : 0.5 * CoefA2V(); }  // :465-486
+};
+
+void cart_free(void* c) { delete (CartState*)c; }
+
+int select_device(int device, std::string& err);
+s2d_handle wrap_engine(std::unique_ptr<EngineBase> impl, void* cart);
+void* engine_cart(s2d_handle h);
+EngineBase* engine_impl(s2d_handle h);
+void set_error(s2d_handle h, const std::string& m);
+
+template <typename T>
+static void cart_build(Engine<T>& E, CartState& S) {
+  CartGeom& G = S.G;
+  const int N = G.N, N2 = N * N;
+  const int npatch = G.ntx * G.ntz;
+  const int nelast = (G.ndof == 1) ? 2 : 6;
+  cudaStream_t st = E.stream;
+  // per-patch prefix tables + shapes (host; npatch entries)
+  std::vector<int> pelem_start(npatch + 1, 0), pshape(npatch);
+  std::vector<long long> pnode_start(npatch + 1, 0), pslot_base(npatch);
+  std::map<std::vector<int>, int> shape_ids;
+  std::vector<Tile> shape_tiles;
+  for (int tz = 0; tz < G.ntz; ++tz)
+    for (int tx = 0; tx < G.ntx; ++tx) {
+      const int p = tx + G.ntx * tz;
+      const Tile t = tile_of(G, tx, tz);
+      pelem_start[p + 1] = pelem_start[p] + t.cx * t.cz;
+      pnode_start[p + 1] = pnode_start[p] + (long long)(t.cx * (N - 1) + 1) * (t.cz * (N - 1) + 1);
+      pslot_base[p] = (long long)p * G.Pmax;
+      std::vector<int> key = {t.cx, t.cz, t.hasL, t.hasR, t.hasD, t.hasU};
+      auto it = shape_ids.find(key);
+      if (it == shape_ids.end()) {
+        it = shape_ids.emplace(key, (int)shape_tiles.size()).first;
+        shape_tiles.push_back(t);
+      }
+      pshape[p] = it->second;
+    }
+  const int EP = G.PX * G.PZ;
+  const int max_nloc = G.LXmax * G.LZmax;
+  const int nshape = (int)shape_tiles.size();
+  std::vector<uint16_t> lidx((size_t)nshape * EP * N2, 0);
+  std::vector<uint8_t> ecol((size_t)nshape * EP, 0);
+  std::vector<int> slot((size_t)nshape * max_nloc, -1);
+  for (int s = 0; s < nshape; ++s) {
+    const Tile& t = shape_tiles[s];
+    const int LX = t.cx * (N - 1) + 1, LZ = t.cz * (N - 1) + 1;
+    for (int lz = 0; lz < t.cz; ++lz)
+      for (int lx = 0; lx < t.cx; ++lx) {
+        const int el = lx + t.cx * lz;
+        ecol[(size_t)s * EP + el] = (uint8_t)((lx & 1) + 2 * (lz & 1));
+        for (int j = 0; j < N; ++j)
+          for (int i = 0; i < N; ++i)
+            lidx[((size_t)s * EP + el) * N2 + i + N * j] = (uint16_t)((lx * (N - 1) + i) + LX * (lz * (N - 1) + j));
+      }
+    for (int b = 0; b < LZ; ++b)
+      for (int a = 0; a < LX; ++a) {
+        const bool sh = (a == 0 && t.hasL) || (a == LX - 1 && t.hasR) || (b == 0 && t.hasD) || (b == LZ - 1 && t.hasU);
+        if (sh) slot[(size_t)s * max_nloc + a + LX * b] = perim_index(a, b, LX, LZ);
+      }
+  }
+  E.pp_npatch = npatch;
+  E.pp_EP = EP;
+  E.pp_max_nloc = max_nloc;
+  E.pp_max_colors = 4;
+  E.pp_nslots = (size_t)npatch * G.Pmax;
+  E.p_pelem_start.upload(pelem_start);
+  E.p_pshape.upload(pshape);
+  E.p_sh_lidx.upload(lidx);
+  E.p_sh_ecolor.upload(ecol);
+  E.p_sh_slot.upload(slot);
+  E.p_pslot_base.upload(pslot_base);
+  E.p_pnode_start.upload(pnode_start);
+  E.p_pnode.alloc((size_t)pnode_start[npatch]);
+  E.fhalo.alloc(E.pp_nslots * G.ndof);
+  E.fhalo.zero(st);
+  k_cart_pnode<<<npatch, 256, 0, st>>>(G, E.p_pnode_start.p, E.p_pnode.p);
+  // coefficient planes
+  E.nelast = nelast;
+  E.kd2 = (N == 5) ? 1 : 0;  // OPT_NGLL (constants.f90:6, mat_elastic.f90:412)
+  E.nkv = 0;
+  if (G.seed != 0) {
+    E.ncoefsets = E.nelem;
+    E.p_hetero = true;
+    E.p_coef.alloc((size_t)E.nelem * nelast * N2);
+    k_cart_coef<T><<<npatch, 256, 0, st>>>(G, E.p_pelem_start.p, E.p_coef.p, nelast);
+  } else {
+    // homogeneous: one shared block (mat_gen.f90:357-365), computed from element 1
+    E.ncoefsets = 1;
+    E.p_hetero = false;
+    std::vector<double> a((size_t)nelast * N2);
+    const double DxiDx = 2.0 / G.hx, DetaDz = 2.0 / G.hz, det = (0.5 * G.hx) * (0.5 * G.hz);
+    const double mu = G.rho * G.cs * G.cs, la = G.rho * (G.cp * G.cp - 2.0 * G.cs * G.cs);
+    for (int j = 0; j < N; ++j)
+      for (int i = 0; i < N; ++i) {
+        const double w = det * (G.wgll[i] * G.wgll[j]);
+        double av[6];
+        if (nelast == 2) {
+          av[0] = mu * DxiDx * DxiDx;
+          av[1] = mu * DetaDz * DetaDz;
+        } else {
+          const double Kx = la + 2.0 * mu;
+          av[0] = Kx * DxiDx * DxiDx; av[1] = la * DxiDx * DetaDz; av[2] = Kx * DetaDz * DetaDz;
+          av[3] = mu * DetaDz * DetaDz; av[4] = mu * DxiDx * DetaDz; av[5] = mu * DxiDx * DxiDx;
+        }
+        for (int pl = 0; pl < nelast; ++pl) a[(size_t)pl * N2 + i + N * j] = -w * av[pl];
+      }
+    upload_as(E.coef, a.data(), a.size());
+    E.p_eset.alloc(E.nelem);
+    E.p_eset.zero(st);
+  }
+  // mass (kept un-inverted in rmass until commit)
+  const long long tot = (long long)E.nelem * N2;
+  k_cart_mass<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(G, E.rmass.p, E.npoin);
+  S2D_CUDA(cudaGetLastError());
+  CartGeom Gc = G;
+  E.cart_halo_sum = [&E, Gc](T* ff) {
+    const long long n = (long long)Gc.ntx * Gc.ntz * Gc.Pmax;
+    k_cart_halo_sum<T><<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(Gc, ff, E.fhalo.p, E.p_pnode_start.p,
+                                                                         E.p_pnode.p, E.npoin, E.pp_nslots);
+    E.launches++;
+  };
+  S2D_CUDA(cudaStreamSynchronize(st));
+}
+
+template <typename T>
+static Engine<T>* as_engine(EngineBase* b) {
+  return static_cast<Engine<T>*>(b);
+}
+
+// coordinates of GLL point (i,j) (0-based) of element (ix,iz)
+static inline double gx_of(const CartGeom& G, int ix, int i) { return G.x0 + G.hx * (ix + 0.5 * (G.xgll[i] + 1.0)); }
+static inline double gz_of(const CartGeom& G, int iz, int j) { return G.z0 + G.hz * (iz + 0.5 * (G.xgll[j] + 1.0)); }
+
+// nearest GLL lattice position along one axis: element index and local index
+static void nearest_1d(const CartGeom& G, double x, double x0, double h, int n, int& e, int& i) {
+  double best = 1e300;
+  e = 0;
+  i = 0;
+  int ec = (int)std::floor((x - x0) / h);
+  for (int ee = std::max(0, ec - 1); ee <= std::min(n - 1, ec + 1); ++ee)
+    for (int k = 0; k < G.N; ++k) {
+      const double xx = x0 + h * (ee + 0.5 * (G.xgll[k] + 1.0));
+      const double dd = std::fabs(xx - x);
+      if (dd <= best) {  // ties -> later (higher id), as SE_find_nearest_node does (spec_grid.f90:423-429)
+        best = dd;
+        e = ee;
+        i = k;
+      }
+    }
+}
+
+}  // namespace s2d
+
+using namespace s2d;
+
+#define CART_GUARD_BEGIN                                              \
+  if (!h || !engine_impl(h) || !engine_cart(h)) return S2D_EINVAL;    \
+  EngineBase* Eb = engine_impl(h);                                    \
+  CartState& S = *(CartState*)engine_cart(h);                         \
+  (void)S;                                                            \
+  try {                                                               \
+    S2D_CUDA(cudaSetDevice(Eb->device));
+#define CART_GUARD_END                                                \
+    return S2D_OK;                                                    \
+  } catch (const ArgError& e) {                                       \
+    set_error(h, e.what());                                           \
+    return S2D_EINVAL;                                                \
+  } catch (const StateError& e) {                                     \
+    set_error(h, e.what());                                           \
+    return S2D_ESTATE;                                                \
+  } catch (const std::exception& e) {                                 \
+    set_error(h, e.what());                                           \
+    return S2D_ECUDA;                                                 \
+  }
+
+static thread_local std::string g_cart_err;
+
 extern "C" {
-int s2d_cart_create(s2d_handle*, const s2d_cart_desc*) { return S2D_ESTATE; }
-int s2d_cart_add_abso(s2d_handle, int32_t, int32_t) { return S2D_ESTATE; }
-int s2d_cart_add_fault_swf(s2d_handle, double, double, double, double, double, double, double, double, int32_t,
-                           int32_t, int32_t, int32_t*) { return S2D_ESTATE; }
-int s2d_cart_add_force(s2d_handle, double, double, const double*, int32_t*) { return S2D_ESTATE; }
-int s2d_cart_add_receivers(s2d_handle, int32_t, double, double, double, double, char, int32_t, int32_t) { return S2D_ESTATE; }
-int s2d_cart_info(s2d_handle, int64_t*, int64_t*, double*) { return S2D_ESTATE; }
-int s2d_cart_get(s2d_handle, int32_t*, double*, double*, double*) { return S2D_ESTATE; }
+
+int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
+  if (!out || !D) return S2D_EINVAL;
+  *out = nullptr;
+  if (D->ngll < 3 || D->ngll > 10 || (D->ndof != 1 && D->ndof != 2) || D->nx < 1 || D->nz < 1 || D->ezflt < 0 ||
+      D->ezflt >= D->nz || !(D->x1 > D->x0) || !(D->z1 > D->z0) || (D->precision != 8 && D->precision != 4) ||
+      (D->scheme.kind != 0 && D->scheme.kind != 1))
+    return S2D_EINVAL;
+  std::string err;
+  const int dev = select_device(D->device, err);
+  if (dev < 0) return S2D_ENODEV;
+  try {
+    std::unique_ptr<CartState> S(new CartState());
+    CartGeom& G = S->G;
+    G.N = D->ngll;
+    G.ndof = D->ndof;
+    G.nx = D->nx;
+    G.nz = D->nz;
+    G.ezflt = D->ezflt;
+    G.x0 = D->x0;
+    G.z0 = D->z0;
+    G.hx = (D->x1 - D->x0) / (double)D->nx;
+    G.hz = (D->z1 - D->z0) / (double)D->nz;
+    G.seed = D->seed;
+    G.ix0 = D->ix0;
+    G.iz0 = D->iz0;
+    G.rho = D->rho;
+    G.cp = D->cp;
+    G.cs = D->cs;
+    G.halo_left = D->halo_left;
+    G.halo_right = D->halo_right;
+    gll_tables(G.N, G.xgll, G.wgll, S->H);
+    // tiles: as square as the patch size allows
+    const int EP = patch_ep(G.N);
+    int PX = 1;
+    while ((PX + 1) * (PX + 1) <= EP) ++PX;
+    int PZ = EP / PX;
+    G.PX = std::min(PX, G.nx);
+    G.PZ = std::min(PZ, G.nz);
+    G.ntx = (G.nx + G.PX - 1) / G.PX;
+    G.ntz_lo = G.ezflt > 0 ? (G.ezflt + G.PZ - 1) / G.PZ : 0;
+    G.ntz = G.ntz_lo + (G.nz - G.ezflt + G.PZ - 1) / G.PZ;
+    G.LXmax = G.PX * (G.N - 1) + 1;
+    G.LZmax = G.PZ * (G.N - 1) + 1;
+    G.Pmax = 2 * G.LXmax + 2 * (G.LZmax - 2);
+    const long long npoin = cart_npoin(G);
+    const long long nelem = (long long)G.nx * G.nz;
+    if (npoin > 2147483647LL || nelem * G.N * G.N > (1LL << 40)) {
+      g_cart_err = "mesh too large for 32-bit node ids";
+      return S2D_EINVAL;
+    }
+    S->scheme = D->scheme;
+    S->courant = D->courant;
+    // dt from the Courant number (init.f90:187-225, time.f90:334-341)
+    {
+      DevBuf<unsigned long long> mx;
+      mx.alloc(1);
+      mx.zero();
+      const long long tot = nelem * G.N * G.N;
+      k_cart_cfl<<<(unsigned)((tot + 255) / 256), 256>>>(G, mx.p);
+      unsigned long long bits = 0;
+      S2D_CUDA(cudaMemcpy(&bits, mx.p, 8, cudaMemcpyDeviceToHost));
+      double v;
+      std::memcpy(&v, &bits, 8);
+      S->grid_cfl = v;
+    }
+    if (!(S->scheme.dt > 0.0)) S->scheme.dt = D->courant / S->grid_cfl;
+    S->dt = S->scheme.dt;
+    std::unique_ptr<EngineBase> impl;
+    if (D->precision == 8) {
+      auto* E = new Engine<double>(Engine<double>::Raw(), G.N, G.ndof, (int)nelem, (size_t)npoin, S->H, S->scheme, dev);
+      impl.reset(E);
+      cart_build<double>(*E, *S);
+    } else {
+      auto* E = new Engine<float>(Engine<float>::Raw(), G.N, G.ndof, (int)nelem, (size_t)npoin, S->H, S->scheme, dev);
+      impl.reset(E);
+      cart_build<float>(*E, *S);
+    }
+    *out = wrap_engine(std::move(impl), S.release());
+    return S2D_OK;
+  } catch (const std::exception& e) {
+    g_cart_err = e.what();
+    fprintf(stderr, "s2d_cart_create: %s\n", e.what());
+    return S2D_ECUDA;
+  }
+}
+
+int s2d_cart_info(s2d_handle h, int64_t* npoin, int64_t* nelem, double* dt) {
+  CART_GUARD_BEGIN
+  if (npoin) *npoin = (int64_t)Eb->npoin;
+  if (nelem) *nelem = (int64_t)Eb->nelem;
+  if (dt) *dt = S.dt;
+  CART_GUARD_END
+}
+
+// BC_ABSO_init for one flat side of the box (bc_abso.f90:115-266)
+int s2d_cart_add_abso(s2d_handle h, int32_t side, int32_t stacey) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(side >= 1 && side <= 4, "cart_add_abso: side tag must be 1..4");
+  S2D_REQUIRE(!Eb->committed, "cart_add_abso after commit");
+  const CartGeom& G = S.G;
+  S2D_REQUIRE(!(side == 4 && G.halo_left) && !(side == 2 && G.halo_right),
+              "cart_add_abso: that side is a strip interface, not a physical boundary");
+  const int N = G.N, ndof = G.ndof;
+  const bool horiz = (side == 1 || side == 3);
+  const int ne = horiz ? G.nx : G.nz;
+  const int np = ne * (N - 1) + 1;
+  std::vector<int> node(np), bibool((size_t)N * ne);
+  std::vector<double> C((size_t)np * ndof, 0.0), K;
+  const bool st = stacey && ndof == 2;
+  if (st) K.assign((size_t)N * 2 * ne, 0.0);
+  // GeoDimTan/Nor (bc_abso.f90:146-160): horizontal boundary -> tangent x (1), normal z (2)
+  const int GeoDimTan = horiz ? 1 : 2, GeoDimNor = horiz ? 2 : 1;
+  const double jac1d = horiz ? 0.5 * G.hx : 0.5 * G.hz;
+  const double dloc_dglob = 1.0 / jac1d;  // DLocDGlob(LocDimTan,GeoDimTan)
+  // virtual boundary elements of neighbour strips complete C at the two interface corner nodes
+  const int e_lo = (horiz && G.halo_left) ? -1 : 0, e_hi = (horiz && G.halo_right) ? ne : ne - 1;
+  for (int e = e_lo; e <= e_hi; ++e) {
+    for (int k = 0; k < N; ++k) {  // k-th point of the edge in counter-clockwise order
+      int ix, iz, i, j, pos;       // pos = position along the sorted (ascending coordinate) node list
+      switch (side) {
+        case 1: ix = e; iz = 0; i = k; j = 0; pos = e * (N - 1) + i; break;                 // edge_D
+        case 2: ix = G.nx - 1; iz = e; i = N - 1; j = k; pos = e * (N - 1) + j; break;      // edge_R
+        case 3: ix = e; iz = G.nz - 1; i = N - 1 - k; j = N - 1; pos = e * (N - 1) + i; break;  // edge_U
+        default: ix = 0; iz = e; i = 0; j = N - 1 - k; pos = e * (N - 1) + j; break;        // edge_L
+      }
+      if (pos < 0 || pos >= np) continue;  // virtual element: only its node on the interface counts
+      double rho, cp, cs;
+      cart_material(G, ix, iz, i, j, rho, cp, cs);
+      const double CoefIntegr = G.wgll[k] * jac1d;
+      double c[3];
+      c[GeoDimNor] = cp;
+      c[GeoDimTan] = cs;
+      if (ndof == 1) {
+        C[pos] += rho * cs * CoefIntegr;
+      } else {
+        C[pos] += rho * c[1] * CoefIntegr;
+        C[pos + np] += rho * c[2] * CoefIntegr;
+      }
+      if (e >= 0 && e < ne) {
+        node[pos] = (int)cart_node_id(G, ix, iz, i + 1, j + 1);
+        bibool[k + (size_t)N * e] = pos + 1;
+        if (st) {
+          const double kv = CoefIntegr * dloc_dglob * rho * c[GeoDimTan] * (2.0 * c[GeoDimTan] - c[GeoDimNor]);
+          for (int cc = 0; cc < 2; ++cc)
+            K[k + (size_t)N * (cc + 2 * (size_t)e)] = (cc == GeoDimTan - 1) ? -kv : kv;
+        }
+      }
+    }
+  }
+  Eb->add_abso(np, node.data(), C.data(), 1, nullptr, st ? 1 : 0, ne, bibool.data(), st ? K.data() : nullptr);
+  // bc_abso.f90:243: the implicit treatment of C*v augments the mass
+  DevBuf<int> dn;
+  DevBuf<double> dC;
+  dn.upload(node);
+  dC.upload(C);
+  if (Eb->prec == 8)
+    k_add_mass<double><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<double>(Eb)->rmass.p, Eb->npoin, ndof, np, dn.p, dC.p, S.CoefA2Vrhs());
+  else
+    k_add_mass<float><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<float>(Eb)->rmass.p, Eb->npoin, ndof, np, dn.p, dC.p, S.CoefA2Vrhs());
+  S2D_CUDA(cudaStreamSynchronize(Eb->stream));
+  CART_GUARD_END
+}
+
+// BC_DYNFLT_init for the split-node fault of MESH_CART ezflt (tags 5 = lower side, 6 = upper side)
+int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, double Tn, double Tt, double Tt_nuc,
+                           double x_nuc, double half_nuc, int32_t oixd, int32_t oitd, int32_t nt_max,
+                           int32_t* fault_id) {
+  CART_GUARD_BEGIN
+  const CartGeom& G = S.G;
+  S2D_REQUIRE(G.ezflt > 0, "cart_add_fault_swf: the mesh has no fault (ezflt = 0)");
+  S2D_REQUIRE(!Eb->committed, "cart_add_fault_swf after commit");
+  const int N = G.N, ndof = G.ndof;
+  const int np = G.nx * (N - 1) + 1;
+  std::vector<int> node1(np), node2(np);
+  std::vector<double> n1((size_t)np * 2), B((size_t)np * ndof, 0.0), T0((size_t)np * 2), coh(np, 0.0), coord((size_t)np * 2);
+  std::vector<double> dc(np, Dc), mus(np, MuS), mud(np, MuD), pw(np, 3.0), alpha(np, 0.0);
+  const int e_lo = G.halo_left ? -1 : 0, e_hi = G.halo_right ? G.nx : G.nx - 1;
+  for (int e = e_lo; e <= e_hi; ++e)
+    for (int i = 0; i < N; ++i) {
+      const int pos = e * (N - 1) + i;
+      if (pos < 0 || pos >= np) continue;
+      B[pos] += G.wgll[i] * (0.5 * G.hx);  // BC_get_normal_and_weights (spec_grid.f90:961-1011)
+      if (e < 0 || e >= G.nx) continue;
+      node1[pos] = (int)cart_node_id(G, e, G.ezflt - 1, i + 1, N);
+      node2[pos] = (int)cart_node_id(G, e, G.ezflt, i + 1, 1);
+      const double x = gx_of(G, e, i);
+      coord[2 * pos] = x;
+      coord[2 * pos + 1] = G.z0 + G.hz * G.ezflt;
+      n1[pos] = 0.0;       // outward normal of the lower side (edge_U): (t_z,-t_x) with t = (-1,0)
+      n1[pos + np] = 1.0;
+      const bool nuc = std::fabs(x - x_nuc) <= half_nuc;  // DIST_PWCONR with one radius (distribution_pwconr.f90:69-85)
+      T0[pos] = nuc ? Tt_nuc : Tt;                        // bc_dynflt.f90:392-400 with no background stress
+      T0[pos + np] = Tn;
+    }
+  if (ndof == 2)
+    for (int k = 0; k < np; ++k) B[k + np] = B[k];
+  // invM at the fault nodes from the current mass (bc_dynflt.f90:338-343)
+  std::vector<double> m1((size_t)np * ndof), m2((size_t)np * ndof);
+  {
+    DevBuf<int> dn1, dn2;
+    DevBuf<double> o1, o2;
+    dn1.upload(node1);
+    dn2.upload(node2);
+    o1.alloc((size_t)np * ndof);
+    o2.alloc((size_t)np * ndof);
+    if (Eb->prec == 8) {
+      k_gather_nodes<double><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<double>(Eb)->rmass.p, Eb->npoin, ndof, np, dn1.p, o1.p);
+      k_gather_nodes<double><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<double>(Eb)->rmass.p, Eb->npoin, ndof, np, dn2.p, o2.p);
+    } else {
+      k_gather_nodes<float><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<float>(Eb)->rmass.p, Eb->npoin, ndof, np, dn1.p, o1.p);
+      k_gather_nodes<float><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<float>(Eb)->rmass.p, Eb->npoin, ndof, np, dn2.p, o2.p);
+    }
+    S2D_CUDA(cudaStreamSynchronize(Eb->stream));
+    o1.download(m1.data());
+    o2.download(m2.data());
+  }
+  std::vector<double> invM1(m1.size()), invM2(m2.size()), Z(m1.size());
+  const double A2V = S.CoefA2V();
+  for (size_t q = 0; q < m1.size(); ++q) {
+    invM1[q] = 1.0 / m1[q];
+    invM2[q] = 1.0 / m2[q];
+    Z[q] = 1.0 / (A2V * B[q] * (invM1[q] + invM2[q]));  // bc_dynflt.f90:349-354
+  }
+  s2d_dynflt_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.np = np;
+  d.node1 = node1.data();
+  d.node2 = node2.data();
+  d.n1 = n1.data();
+  d.B = B.data();
+  d.invM1 = invM1.data();
+  d.invM2 = invM2.data();
+  d.Z = Z.data();
+  d.T0 = T0.data();
+  d.cohesion = coh.data();
+  d.coord = coord.data();
+  d.CoefA2V = A2V;
+  d.CoefA2D = S.CoefA2D();
+  d.allow_opening = 1;
+  d.swf_kind = 1;
+  d.swf_dc = dc.data();
+  d.swf_mus = mus.data();
+  d.swf_mud = mud.data();
+  d.swf_p = pw.data();
+  d.swf_alpha = alpha.data();
+  d.normal_kind = 1;
+  d.normal_T = d.normal_L = d.normal_V = 1.0;
+  d.oix1 = 1;
+  d.oixn = np;
+  d.oixd = oixd;
+  d.oit = 0;
+  d.oitd = oitd;
+  d.nt_max = nt_max;
+  const int id = Eb->add_dynflt(d);
+  if (fault_id) *fault_id = id;
+  CART_GUARD_END
+}
+
+int s2d_cart_add_force(s2d_handle h, double x, double z, const double* dir, int32_t* src_id) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(dir, "cart_add_force: null dir");
+  const CartGeom& G = S.G;
+  int ex, i, ez, j;
+  nearest_1d(G, x, G.x0, G.hx, G.nx, ex, i);
+  nearest_1d(G, z, G.z0, G.hz, G.nz, ez, j);
+  const int id = Eb->add_force((int)cart_node_id(G, ex, ez, i + 1, j + 1), dir);
+  if (src_id) *src_id = id;
+  CART_GUARD_END
+}
+
+int s2d_cart_add_receivers(s2d_handle h, int32_t nx, double xa, double za, double xb, double zb, char field,
+                           int32_t isamp, int32_t nt_rec) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(nx >= 1, "cart_add_receivers: nx < 1");
+  const CartGeom& G = S.G;
+  std::vector<int> ig;
+  for (int n = 0; n < nx; ++n) {  // REC_LINE (receivers.f90:120-130) + nearest node, duplicates dropped (:255)
+    const double w = nx > 1 ? (double)n / (double)(nx - 1) : 0.0;
+    int ex, i, ez, j;
+    nearest_1d(G, xa + w * (xb - xa), G.x0, G.hx, G.nx, ex, i);
+    nearest_1d(G, za + w * (zb - za), G.z0, G.hz, G.nz, ez, j);
+    const int id = (int)cart_node_id(G, ex, ez, i + 1, j + 1);
+    bool dup = false;
+    if (ig.size() > 1)
+      for (int v : ig) dup = dup || (v == id);
+    if (!dup) ig.push_back(id);
+  }
+  Eb->add_receivers((int)ig.size(), field, isamp, nt_rec, 1, ig.data(), nullptr, nullptr);
+  CART_GUARD_END
+}
+
+int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double* coord) {
+  CART_GUARD_BEGIN
+  const CartGeom& G = S.G;
+  const int N = G.N, N2 = N * N;
+  const long long tot = (long long)Eb->nelem * N2;
+  if (ibool) {
+    DevBuf<int> ib;
+    ib.alloc((size_t)tot);
+    k_cart_ibool<<<(unsigned)((tot + 255) / 256), 256, 0, Eb->stream>>>(G, ib.p);
+    S2D_CUDA(cudaStreamSynchronize(Eb->stream));
+    ib.download(ibool);
+  }
+  if (a) {
+    // reference layout a(ngll,ngll,nelast,nelem) from the patch-major planes
+    const int nelast = (G.ndof == 1) ? 2 : 6;
+    std::vector<double> pc;
+    bool hetero;
+    if (Eb->prec == 8) {
+      auto* E = as_engine<double>(Eb);
+      hetero = E->p_hetero;
+      pc = hetero ? E->p_coef.to_host() : E->coef.to_host();
+    } else {
+      auto* E = as_engine<float>(Eb);
+      hetero = E->p_hetero;
+      std::vector<float> t = hetero ? E->p_coef.to_host() : E->coef.to_host();
+      pc.assign(t.begin(), t.end());
+    }
+    if (!hetero) {
+      std::copy(pc.begin(), pc.end(), a);
+    } else {
+      size_t es = 0;
+      for (int tz = 0; tz < G.ntz; ++tz)
+        for (int tx = 0; tx < G.ntx; ++tx) {
+          const Tile t = tile_of(G, tx, tz);
+          const int cnt = t.cx * t.cz;
+          const size_t base = es * nelast * N2, nthr = (size_t)cnt * N;
+          for (int el = 0; el < cnt; ++el) {
+            const size_t e = (size_t)(t.ex0 + el % t.cx) + (size_t)G.nx * (t.ez0 + el / t.cx);
+            for (int pl = 0; pl < nelast; ++pl)
+              for (int j = 0; j < N; ++j)
+                for (int i = 0; i < N; ++i)
+                  a[(e * nelast + pl) * N2 + i + N * j] = pc[base + ((size_t)pl * N + i) * nthr + (size_t)el * N + j];
+          }
+          es += cnt;
+        }
+    }
+  }
+  if (rmass) {
+    const size_t nd = Eb->npoin * G.ndof;
+    if (Eb->prec == 8) {
+      as_engine<double>(Eb)->rmass.download(rmass);
+    } else {
+      std::vector<float> t = as_engine<float>(Eb)->rmass.to_host();
+      for (size_t q = 0; q < nd; ++q) rmass[q] = t[q];
+    }
+    if (!Eb->committed)
+      for (size_t q = 0; q < nd; ++q) rmass[q] = 1.0 / rmass[q];
+  }
+  if (coord) {
+    for (int iz = 0; iz < G.nz; ++iz)
+      for (int ix = 0; ix < G.nx; ++ix)
+        for (int j = 0; j < N; ++j)
+          for (int i = 0; i < N; ++i) {
+            const size_t nd = (size_t)(cart_node_id(G, ix, iz, i + 1, j + 1) - 1);
+            coord[2 * nd] = gx_of(G, ix, i);
+            coord[2 * nd + 1] = gz_of(G, iz, j);
+          }
+  }
+  CART_GUARD_END
+}
+
 int s2d_halo_info(s2d_handle, int64_t*, void**, void**) { return S2D_ESTATE; }
 int s2d_halo_set_exchange(s2d_handle, s2d_exchange_fn, void*) { return S2D_ESTATE; }
 int s2d_halo_set_peers(s2d_handle, void*, void*, void*, void*) { return S2D_ESTATE; }
-}
+
+}  // extern "C"

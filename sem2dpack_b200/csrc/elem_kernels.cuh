@@ -162,80 +162,108 @@ inline void launch_elem_node(int ngll, const ElemArgs<T>& A, cudaStream_t s) {
 
 
 // =============================================================================================
-// v2: CTA-patch kernel (default).  One CTA owns a patch of up to EP clustered elements; one thread
-// owns one GLL column (fixed j) of one element, i.e. N nodes, so the xi-contractions run out of
-// registers with hprime as constant-bank operands and only the eta-contractions go through shared
-// memory.  Element forces are summed per patch in shared memory in the order of the in-patch
-// greedy colours (no atomics); nodes private to the patch are stored straight to the global force
-// array, partial sums of nodes shared with other patches go to their halo slot, and k_halo_sum
-// adds the slots of each shared node in ascending patch order.  Every node is written exactly once
-// per step, so the force array needs no zero fill.
+// v2: CTA-patch kernel (default).  One CTA owns a patch of up to EP clustered elements.
+//   stage   : the patch's unique nodes are read once from HBM into shared memory (sD);
+//   compute : one thread owns one GLL column (fixed j) of one element, i.e. N nodes, so the
+//             xi-contractions run out of registers with hprime as constant-bank operands and only
+//             the eta-contractions go through a shared-memory tile;
+//   assemble: element forces are summed per patch in shared memory in the order of the in-patch
+//             greedy colours (no atomics); nodes private to the patch are stored straight to the
+//             global force array, partial sums of nodes shared with other patches go to a halo
+//             slot, and a second small kernel adds the slots of each shared node in ascending
+//             patch order.  Every node is written exactly once per step: no zero fill, no RMW.
+// Index tables are split into a per-patch part (pnode: the global node of every patch-local node)
+// and a per-SHAPE part (local indices, colours, slot offsets) that structured meshes share between
+// all congruent patches, so it stays cache resident.
 template <typename T, int N>
 struct PatchArgs {
   int npatch, EP, max_nloc, max_colors;
-  const int* pelem_start;   // (npatch+1)
-  const int* gidx;          // (N*N, nelem patch-major) 0-based global node
-  const uint16_t* lidx;     // (N*N, nelem patch-major) patch-local node
-  const int* ecolor;        // (nelem patch-major)
-  const int* pnode_start;   // (npatch+1)
-  const int* pnode;         // global node (0-based) of each patch-local node
-  const int* pslot;         // -1 | halo slot
-  const int* eset;          // (nelem patch-major) coefficient set when !hetero
-  const int* ekv;           // (nelem patch-major) KV slot | -1, or nullptr
-  const T* a;               // hetero: per patch [nelast][N(i)][cnt*N(t)] ; else (N*N,nelast,nsets)
-  const T* eta;             // (N*N, nkv)
+  const int* pelem_start;     // (npatch+1) offsets into the patch-major element order
+  const int* pshape;          // (npatch) shape id
+  const uint16_t* sh_lidx;    // [shape][EP*N*N] patch-local node of each element node
+  const uint8_t* sh_ecolor;   // [shape][EP] in-patch colour
+  const int* sh_slot;         // [shape][max_nloc] -1 = private node, else slot offset
+  const long long* pslot_base;  // (npatch) first halo slot of the patch (added to sh_slot)
+  const long long* pnode_start; // (npatch+1)
+  const int* pnode;           // global node (0-based) of each patch-local node
+  const int* eset;            // (nelem patch-major) coefficient set when !hetero
+  const int* ekv;             // (nelem patch-major) KV slot | -1, or nullptr
+  const T* a;                 // hetero: per patch [nelast][N(i)][cnt*N(t)] ; else (N*N,nelast,nsets)
+  const T* eta;               // (N*N, nkv)
   const T* d;
   const T* v;
   T* f;
-  T* fhalo;                 // (nslots, ndof)
+  T* fhalo;                   // (nslots, ndof)
   size_t npoin, nslots;
   int nelast, kd2, hetero;
-  T H[N * N];               // hprime, column-major: read as constant-bank operands
+  T H[N * N];                 // hprime, column-major: read as constant-bank operands
 };
 
 // elements per patch: as many as keep the CTA at <= 384 threads (one thread per GLL column)
 constexpr int patch_ep(int ngll) { return (384 / ngll) > 64 ? 64 : ((384 / ngll) < 8 ? 8 : (384 / ngll)); }
+constexpr int patch_min_ctas(int ngll, int ndof, int tsize) {
+  return (ngll <= 6 || tsize == 4) ? 2 : 1;
+}
 
 template <typename T, int N, int NDOF>
-__global__ void __launch_bounds__(patch_ep(N) * N) k_elem_patch(const __grid_constant__ PatchArgs<T, N> A) {
+__global__ void __launch_bounds__(patch_ep(N) * N, patch_min_ctas(N, NDOF, sizeof(T)))
+    k_elem_patch(const __grid_constant__ PatchArgs<T, N> A) {
   constexpr int N2 = N * N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sU = reinterpret_cast<T*>(smem_raw);   // [EP][NDOF][N2] displacement tiles, then tHt tiles
-  T* sF = sU + (size_t)A.EP * NDOF * N2;    // [NDOF][max_nloc] patch force accumulators
-  T* sH = sF + (size_t)NDOF * A.max_nloc;   // [N2]
+  T* sF = sU + (size_t)A.EP * NDOF * N2;    // [NDOF][max_nloc] force accumulators (velocity stage for KV)
+  T* sD = sF + (size_t)NDOF * A.max_nloc;   // [NDOF][max_nloc] staged displacement
+  T* sH = sD + (size_t)NDOF * A.max_nloc;   // [N2]
   const int p = blockIdx.x;
   const int t = threadIdx.x;
   const int es = A.pelem_start[p];
   const int cnt = A.pelem_start[p + 1] - es;
+  const int shape = A.pshape[p];
   const int el = t / N;
   const int j = t - el * N;
   const bool active = el < cnt;
   const int q = es + el;
-  const int ps = A.pnode_start[p];
-  const int nloc = A.pnode_start[p + 1] - ps;
+  const long long ps = A.pnode_start[p];
+  const int nloc = (int)(A.pnode_start[p + 1] - ps);
+  const bool kv = A.ekv != nullptr;
 
   if (t < N2) sH[t] = A.H[t];
-  for (int l = t; l < NDOF * A.max_nloc; l += blockDim.x) sF[l] = 0;
+  for (int l = t; l < nloc; l += blockDim.x) {
+    const size_t g = (size_t)A.pnode[ps + l];
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c) {
+      sD[c * A.max_nloc + l] = A.d[g + A.npoin * c];
+      sF[c * A.max_nloc + l] = kv ? A.v[g + A.npoin * c] : (T)0;
+    }
+  }
+  int li[N];
+  if (active) {
+    const uint16_t* lp = A.sh_lidx + ((size_t)shape * A.EP + el) * N2 + N * j;
+#pragma unroll
+    for (int i = 0; i < N; ++i) li[i] = lp[i];
+  }
+  __syncthreads();
 
   T* myU = sU + (size_t)el * NDOF * N2;
   T ucol[NDOF][N];
   if (active) {
-    const int ikv = A.ekv ? A.ekv[q] : -1;
+    const int ikv = kv ? A.ekv[q] : -1;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const size_t node = (size_t)A.gidx[(size_t)q * N2 + i + N * j];
       T etav = 0;
       if (ikv >= 0) etav = A.eta[(size_t)ikv * N2 + i + N * j];
 #pragma unroll
       for (int c = 0; c < NDOF; ++c) {
-        T u = A.d[node + A.npoin * c];
-        if (ikv >= 0) u = u + etav * A.v[node + A.npoin * c];  // mat_kelvin_voigt.f90:147
+        T u = sD[c * A.max_nloc + li[i]];
+        if (ikv >= 0) u = u + etav * sF[c * A.max_nloc + li[i]];  // mat_kelvin_voigt.f90:147
         ucol[c][i] = u;
         myU[c * N2 + i + N * j] = u;
       }
     }
   }
   __syncthreads();
+  if (kv)
+    for (int l = t; l < NDOF * A.max_nloc; l += blockDim.x) sF[l] = 0;
 
   T fcol[NDOF][N];   // force column accumulated in registers
   T tHt[NDOF][N];    // values that go through the tile exchange
@@ -312,7 +340,6 @@ __global__ void __launch_bounds__(patch_ep(N) * N) k_elem_patch(const __grid_con
   }
   __syncthreads();
   int mycol = -1;
-  int li[N];
   if (active) {
 #pragma unroll
     for (int c = 0; c < NDOF; ++c)
@@ -323,9 +350,7 @@ __global__ void __launch_bounds__(patch_ep(N) * N) k_elem_patch(const __grid_con
         for (int m = 0; m < N; ++m) s2 += myU[c * N2 + i + N * m] * HTj[m];  // (tHt Ht)(i,j)
         fcol[c][i] += s2;
       }
-    mycol = A.ecolor[q];
-#pragma unroll
-    for (int i = 0; i < N; ++i) li[i] = A.lidx[(size_t)q * N2 + i + N * j];
+    mycol = A.sh_ecolor[(size_t)shape * A.EP + el];
   }
   // in-patch assembly, one colour at a time (elements of one colour share no node)
   for (int col = 0; col < A.max_colors; ++col) {
@@ -337,21 +362,22 @@ __global__ void __launch_bounds__(patch_ep(N) * N) k_elem_patch(const __grid_con
     }
     __syncthreads();
   }
+  const int* slotp = A.sh_slot + (size_t)shape * A.max_nloc;
+  const long long sbase = A.pslot_base[p];
   for (int l = t; l < nloc; l += blockDim.x) {
-    const int g = A.pnode[ps + l];
-    const int slot = A.pslot[ps + l];
+    const int so = slotp[l];
 #pragma unroll
     for (int c = 0; c < NDOF; ++c) {
       const T val = sF[c * A.max_nloc + l];
-      if (slot < 0)
-        A.f[(size_t)g + A.npoin * c] = val;
+      if (so < 0)
+        A.f[(size_t)A.pnode[ps + l] + A.npoin * c] = val;
       else
-        A.fhalo[(size_t)slot + A.nslots * c] = val;
+        A.fhalo[(size_t)(sbase + so) + A.nslots * c] = val;
     }
   }
 }
 
-// adds the halo slots of each node shared between patches, in ascending patch order
+// adds the halo slots of each node shared between patches, in ascending patch order (generic plan)
 template <typename T>
 __global__ void k_halo_sum(T* __restrict__ f, const T* __restrict__ fhalo, const int* __restrict__ snode,
                            const int* __restrict__ sstart, int nshared, size_t npoin, size_t nslots,
@@ -370,7 +396,8 @@ __global__ void k_halo_sum(T* __restrict__ f, const T* __restrict__ fhalo, const
 template <typename T, int N, int NDOF>
 inline void launch_elem_patch_n(const PatchArgs<T, N>& A, cudaStream_t s) {
   if (A.npatch <= 0) return;
-  const size_t smem = ((size_t)A.EP * NDOF * N * N + (size_t)NDOF * A.max_nloc + N * N) * sizeof(T);
+  const size_t smem =
+      ((size_t)A.EP * NDOF * N * N + 2 * (size_t)NDOF * A.max_nloc + N * N) * sizeof(T);
   static size_t configured = 0;
   if (smem > configured) {
     S2D_CUDA(cudaFuncSetAttribute(k_elem_patch<T, N, NDOF>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -196,6 +196,12 @@ int s2d_get_seis(s2d_handle h, float* sis) {
     E.get_seis(sis);
   });
 }
+int s2d_get_seis_row(s2d_handle h, int32_t it, float* row) {
+  return guard(h, [&](EngineBase& E) {
+    S2D_REQUIRE(row, "s2d_get_seis_row: null pointer");
+    E.get_seis_row(it, row);
+  });
+}
 int s2d_get_fault(s2d_handle h, int32_t fault_id, float* records, int32_t* nout, double* potency, int32_t* ncalls) {
   return guard(h, [&](EngineBase& E) { E.get_fault(fault_id, records, nout, potency, ncalls); });
 }

@@ -2,6 +2,7 @@
 // of solve_leapfrog / solve_Newmark (SRC/solver.f90:42-84,140-160) + REC_store + BC_write.
 #pragma once
 #include <cmath>
+#include <functional>
 #include <memory>
 
 #include "bc_kernels.cuh"
@@ -76,6 +77,7 @@ class EngineBase {
   virtual void step(int nsteps, const double* src_ampli, const double* bc_ampli) = 0;
   virtual void compute_fint(double* fint) = 0;
   virtual void get_seis(float* sis) = 0;
+  virtual void get_seis_row(int it, float* row) = 0;
   virtual void get_fault(int id, float* records, int32_t* nout, double* potency, int32_t* ncalls) = 0;
   virtual void get_fault_state(int id, double* D, double* V, double* T, double* Tstick, double* MU,
                                double* theta, double* sigma) = 0;
@@ -124,12 +126,47 @@ class Engine : public EngineBase {
   std::vector<int32_t> h_color;
   std::vector<int32_t> color_start;  // (ncolors+1)
   DevBuf<int> color_elems;
-  // patch plan
+  // patch plan (device tables of the CTA-patch kernel)
   PatchPlan plan;
-  DevBuf<int> p_pelem_start, p_gidx, p_ecolor, p_pnode_start, p_pnode, p_pslot, p_eset, p_ekv, p_snode, p_sstart;
-  DevBuf<uint16_t> p_lidx;
+  int pp_npatch = 0, pp_EP = 0, pp_max_nloc = 0, pp_max_colors = 0;
+  size_t pp_nslots = 0;
+  DevBuf<int> p_pelem_start, p_pshape, p_sh_slot, p_pnode, p_eset, p_ekv, p_snode, p_sstart;
+  DevBuf<long long> p_pslot_base, p_pnode_start;
+  DevBuf<uint16_t> p_sh_lidx;
+  DevBuf<uint8_t> p_sh_ecolor;
   DevBuf<T> p_coef, fhalo;
   bool p_hetero = false;
+  bool cart_mode = false;  // structured builder: no host ibool, closed-form halo sum
+  std::function<void(T*)> cart_halo_sum;
+
+  // bare engine for the structured builder (cart.cu fills the tables on the device)
+  struct Raw {};
+  Engine(Raw, int ngll_, int ndof_, int nelem_, size_t npoin_, const double* hprime, const s2d_scheme& sch,
+         int dev) {
+    ngll = ngll_;
+    ndof = ndof_;
+    nelem = nelem_;
+    npoin = npoin_;
+    prec = (int)sizeof(T);
+    scheme = sch;
+    device = dev;
+    cart_mode = true;
+    S2D_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    const size_t n2 = (size_t)ngll * ngll;
+    h_H.assign(hprime, hprime + n2);
+    upload_as(H, hprime, n2);
+    const size_t nd = npoin * ndof;
+    d.alloc(nd);
+    v.alloc(nd);
+    a.alloc(nd);
+    d.zero();
+    v.zero();
+    a.zero();
+    rmass.alloc(nd);
+    StepCtl c0{0, 1, 0, 1};
+    ctl.upload(&c0, 1);
+    partial.alloc(1024);
+  }
 
   Engine(int ngll_, int ndof_, int nelem_, size_t npoin_, const int32_t* ibool_, const double* hprime,
          const double* rmass_, const s2d_scheme& sch, int dev) {
@@ -519,25 +556,44 @@ class Engine : public EngineBase {
   void upload_patch_plan() {
     const int n2 = ngll * ngll;
     PatchPlan& P = plan;
-    std::vector<int> gidx((size_t)nelem * n2), eset(nelem), ekv(nelem, -1);
-    for (int q = 0; q < nelem; ++q) {
-      const int e = P.elems[q];
-      for (int k = 0; k < n2; ++k) gidx[(size_t)q * n2 + k] = h_ibool[(size_t)e * n2 + k] - 1;
-      eset[q] = h_elem2set[e];
-      if (nkv > 0) ekv[q] = h_elem2kv[e];
+    const int EP = P.EP;
+    pp_npatch = P.npatch;
+    pp_EP = EP;
+    pp_max_nloc = P.max_nloc;
+    pp_max_colors = P.max_colors;
+    pp_nslots = std::max<size_t>(P.nslots, 1);
+    std::vector<int> eset(nelem), ekv(nelem, -1), pshape(P.npatch);
+    std::vector<uint16_t> lidx((size_t)P.npatch * EP * n2, 0);
+    std::vector<uint8_t> ecol((size_t)P.npatch * EP, 0);
+    std::vector<int> slot((size_t)P.npatch * P.max_nloc, -1);
+    std::vector<long long> sbase(P.npatch, 0), pns(P.npatch + 1);
+    for (int p = 0; p < P.npatch; ++p) {
+      pshape[p] = p;  // unstructured plan: every patch is its own shape
+      const int es = P.pelem_start[p], cnt = P.pelem_start[p + 1] - es;
+      for (int el = 0; el < cnt; ++el) {
+        const int e = P.elems[es + el];
+        eset[es + el] = h_elem2set[e];
+        if (nkv > 0) ekv[es + el] = h_elem2kv[e];
+        ecol[(size_t)p * EP + el] = (uint8_t)P.ecolor[es + el];
+        for (int k = 0; k < n2; ++k) lidx[((size_t)p * EP + el) * n2 + k] = P.lidx[(size_t)(es + el) * n2 + k];
+      }
+      const int ns = P.pnode_start[p], nl = P.pnode_start[p + 1] - ns;
+      for (int l = 0; l < nl; ++l) slot[(size_t)p * P.max_nloc + l] = P.pslot[ns + l];
     }
+    for (int p = 0; p <= P.npatch; ++p) pns[p] = P.pnode_start[p];
     p_pelem_start.upload(P.pelem_start);
-    p_gidx.upload(gidx);
-    p_lidx.upload(P.lidx);
-    p_ecolor.upload(P.ecolor);
-    p_pnode_start.upload(P.pnode_start);
+    p_pshape.upload(pshape);
+    p_sh_lidx.upload(lidx);
+    p_sh_ecolor.upload(ecol);
+    p_sh_slot.upload(slot);
+    p_pslot_base.upload(sbase);
+    p_pnode_start.upload(pns);
     p_pnode.upload(P.pnode);
-    p_pslot.upload(P.pslot);
     p_eset.upload(eset);
     if (nkv > 0) p_ekv.upload(ekv);
     p_snode.upload(P.snode);
     p_sstart.upload(P.sstart);
-    fhalo.alloc(std::max<size_t>(P.nslots, 1) * ndof);
+    fhalo.alloc(pp_nslots * ndof);
     fhalo.zero();
     // heterogeneous media (one coefficient block per element): re-lay the planes patch-major so
     // that each thread of the patch kernel streams them with unit stride
@@ -566,9 +622,14 @@ class Engine : public EngineBase {
     S2D_REQUIRE(nelast > 0, "commit: s2d_set_elastic was not called");
     S2D_REQUIRE(variant_ >= 0 && variant_ <= 2, "commit: unknown assembly variant");
     variant = variant_;
-    if (nkv == 0) h_elem2kv.assign(nelem, -1);
-    build_color_plan();
-    if (variant == S2D_ASM_PATCH) build_patch_plan_dev();
+    if (cart_mode) {
+      S2D_REQUIRE(variant == S2D_ASM_PATCH, "commit: the structured builder only provides the patch plan");
+      k_invert<T><<<grid_for(rmass.n), 256, 0, stream>>>(rmass.p, rmass.n);
+    } else {
+      if (nkv == 0) h_elem2kv.assign(nelem, -1);
+      build_color_plan();
+      if (variant == S2D_ASM_PATCH) build_patch_plan_dev();
+    }
     if (!h_src_iglob.empty()) {
       src_iglob.upload(h_src_iglob);
       src_dir.upload(h_src_dir);
@@ -627,17 +688,18 @@ class Engine : public EngineBase {
   template <int N>
   void launch_patch_n(const T* dd, const T* vv, T* ff) {
     PatchArgs<T, N> A{};
-    A.npatch = plan.npatch;
-    A.EP = plan.EP;
-    A.max_nloc = plan.max_nloc;
-    A.max_colors = plan.max_colors;
+    A.npatch = pp_npatch;
+    A.EP = pp_EP;
+    A.max_nloc = pp_max_nloc;
+    A.max_colors = pp_max_colors;
     A.pelem_start = p_pelem_start.p;
-    A.gidx = p_gidx.p;
-    A.lidx = p_lidx.p;
-    A.ecolor = p_ecolor.p;
+    A.pshape = p_pshape.p;
+    A.sh_lidx = p_sh_lidx.p;
+    A.sh_ecolor = p_sh_ecolor.p;
+    A.sh_slot = p_sh_slot.p;
+    A.pslot_base = p_pslot_base.p;
     A.pnode_start = p_pnode_start.p;
     A.pnode = p_pnode.p;
-    A.pslot = p_pslot.p;
     A.eset = p_eset.p;
     A.ekv = nkv > 0 ? p_ekv.p : nullptr;
     A.a = p_hetero ? p_coef.p : coef.p;
@@ -647,7 +709,7 @@ class Engine : public EngineBase {
     A.f = ff;
     A.fhalo = fhalo.p;
     A.npoin = npoin;
-    A.nslots = std::max<size_t>(plan.nslots, 1);
+    A.nslots = pp_nslots;
     A.nelast = nelast;
     A.kd2 = kd2;
     A.hetero = p_hetero ? 1 : 0;
@@ -655,11 +717,15 @@ class Engine : public EngineBase {
     if (ndof == 1) launch_elem_patch_n<T, N, 1>(A, stream);
     else launch_elem_patch_n<T, N, 2>(A, stream);
     launches++;
-    const int ns = (int)plan.snode.size();
-    if (ns > 0) {
-      k_halo_sum<T><<<ceil_div(ns, 256), 256, 0, stream>>>(ff, fhalo.p, p_snode.p, p_sstart.p, ns, npoin,
-                                                           A.nslots, ndof);
-      launches++;
+    if (cart_mode) {
+      cart_halo_sum(ff);
+    } else {
+      const int ns = (int)plan.snode.size();
+      if (ns > 0) {
+        k_halo_sum<T><<<ceil_div(ns, 256), 256, 0, stream>>>(ff, fhalo.p, p_snode.p, p_sstart.p, ns, npoin,
+                                                             pp_nslots, ndof);
+        launches++;
+      }
     }
     S2D_CUDA(cudaGetLastError());
   }
@@ -846,6 +912,14 @@ class Engine : public EngineBase {
     S2D_CUDA(cudaStreamSynchronize(stream));
     rec.sis.download(sis);
   }
+  void get_seis_row(int it_, float* row) override {
+    S2D_REQUIRE(rec.present, "get_seis_row: no receivers");
+    S2D_REQUIRE(it_ >= 0 && it_ % rec.dev.isamp == 0 && it_ / rec.dev.isamp < rec.dev.nt, "get_seis_row: step not sampled");
+    const size_t r = (size_t)(it_ / rec.dev.isamp);
+    S2D_CUDA(cudaMemcpy2DAsync(row, sizeof(float), rec.sis.p + r, (size_t)rec.dev.nt * sizeof(float), sizeof(float),
+                               (size_t)rec.dev.nx * ndof, cudaMemcpyDeviceToHost, stream));
+    S2D_CUDA(cudaStreamSynchronize(stream));
+  }
   void get_fault(int id, float* records, int32_t* nout, double* potency, int32_t* ncalls) override {
     S2D_REQUIRE(id >= 0 && id < (int)faults.size(), "get_fault: bad fault id");
     FaultBc& b = *faults[id];
@@ -905,6 +979,7 @@ class Engine : public EngineBase {
   }
   void get_coloring(int32_t* nc, int32_t* color) override {
     S2D_REQUIRE(committed, "get_coloring before commit");
+    S2D_REQUIRE(!cart_mode, "get_coloring: not available for builder-made meshes");
     if (nc) *nc = ncolors;
     if (color) std::copy(h_color.begin(), h_color.end(), color);
   }

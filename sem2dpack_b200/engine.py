@@ -142,6 +142,12 @@ class Engine:
         self._ck(self.L.s2d_get_seis(self.h, _ptr(s)))
         return s.reshape(nd, nx, nt).transpose(2, 1, 0)
 
+    def seis_row(self, it):
+        nd, nx, _ = self.rec_shape
+        row = np.empty(nd * nx, np.float32)
+        self._ck(self.L.s2d_get_seis_row(self.h, it, _ptr(row)))
+        return row.reshape(nd, nx)
+
     def fault(self, fid, onx):
         nout, ncalls = C.c_int32(), C.c_int32()
         self._ck(self.L.s2d_get_fault(self.h, fid, None, C.byref(nout), None, C.byref(ncalls)))
@@ -193,3 +199,63 @@ class Engine:
         p = C.c_void_p()
         self._ck(self.L.s2d_stream(self.h, C.byref(p)))
         return p.value
+
+
+class CartEngine(Engine):
+    """A MESH_CART problem (SRC/mesh_cartesian.f90) generated on the device by the structured
+    builder; afterwards it is driven exactly like an `Engine`."""
+
+    def __init__(self, ngll, ndof, nx, nz, xlim, zlim, ezflt=0, seed=0, rho=0.0, cp=0.0, cs=0.0, scheme_kind=0,
+                 dt=0.0, courant=0.5, beta=0.0, gamma=0.5, alpha=1.0, precision=8, device=-1, ix0=0, iz0=0,
+                 halo_left=False, halo_right=False):
+        L = capi.lib()
+        d = capi.CartDesc()
+        d.ngll, d.ndof, d.nx, d.nz, d.ezflt = ngll, ndof, nx, nz, ezflt
+        d.x0, d.x1 = xlim
+        d.z0, d.z1 = zlim
+        d.seed, d.ix0, d.iz0 = seed, ix0, iz0
+        d.rho, d.cp, d.cs = rho, cp, cs
+        d.precision = precision
+        d.scheme = Scheme(scheme_kind, dt, beta, gamma, alpha)
+        d.courant = courant
+        d.device = device
+        d.halo_left, d.halo_right = int(halo_left), int(halo_right)
+        h = C.c_void_p()
+        rc = L.s2d_cart_create(C.byref(h), C.byref(d))
+        if rc != 0:
+            raise S2DError(rc, "s2d_cart_create failed (see stderr)")
+        super().__init__(ngll, ndof, None, None, None, scheme_kind, dt, _handle=h)
+        self.ngll, self.ndof = ngll, ndof
+        npoin, nelem, dtv = C.c_int64(), C.c_int64(), C.c_double()
+        self._ck(self.L.s2d_cart_info(self.h, C.byref(npoin), C.byref(nelem), C.byref(dtv)))
+        self.npoin, self.nelem, self.dt = npoin.value, nelem.value, dtv.value
+        self.nx, self.nz = nx, nz
+
+    def add_abso_side(self, side, stacey=False):
+        self._ck(self.L.s2d_cart_add_abso(self.h, side, int(stacey)))
+
+    def add_fault_swf(self, Dc, MuS, MuD, Tn, Tt, Tt_nuc, x_nuc, half_nuc, oixd=1, oitd=1, nt_max=0):
+        fid = C.c_int32(-1)
+        self._ck(self.L.s2d_cart_add_fault_swf(self.h, Dc, MuS, MuD, Tn, Tt, Tt_nuc, x_nuc, half_nuc, oixd, oitd,
+                                               nt_max, C.byref(fid)))
+        return fid.value
+
+    def add_force_at(self, x, z, direction):
+        sid = C.c_int32(-1)
+        self._ck(self.L.s2d_cart_add_force(self.h, x, z, _ptr(_f64(direction)), C.byref(sid)))
+        return sid.value
+
+    def add_receiver_line(self, nx, first, last, field, isamp, nt_rec):
+        self.rec_shape = (self.ndof, nx, nt_rec)  # stations must snap to distinct nodes
+        self._ck(self.L.s2d_cart_add_receivers(self.h, nx, first[0], first[1], last[0], last[1],
+                                               field.encode()[:1], isamp, nt_rec))
+
+    def get_tables(self, ibool=True, a=False, rmass=True, coord=False, nelast=None):
+        n2 = self.ngll * self.ngll
+        ib = np.empty(self.nelem * n2, np.int32) if ibool else None
+        nel = nelast or (2 if self.ndof == 1 else 6)
+        aa = np.empty(self.nelem * n2 * nel) if a else None
+        rm = np.empty(self.npoin * self.ndof) if rmass else None
+        co = np.empty(self.npoin * 2) if coord else None
+        self._ck(self.L.s2d_cart_get(self.h, _ptr(ib), _ptr(aa), _ptr(rm), _ptr(co)))
+        return ib, aa, rm, co

@@ -31,7 +31,7 @@ def cart_deck(nx, nz, ngll=5, ndof=2, ezflt=0, scheme="leapfrog", courant=0.5, n
          f"&MESH_CART xlim=0d0,{nx*h}d0, zlim=0d0,{nz*h}d0, nelem={nx},{nz}" + (f", ezflt={ezflt}" if ezflt else "") + " /",
          "&MATERIAL tag=1, kind='ELAST' /",
          "&MAT_ELASTIC rho=2670.d0, cp=6000.d0, cs=3464.d0 /"]
-    if ezflt:
+    if ezflt and fault:
         L += ["&BC_DEF tags=5,6, kind='DYNFLT' /"]
         if fault == "swf":
             L += ["&BC_DYNFLT friction='SWF', Tn=-120.d6, TtH='PWCONR' /",

@@ -1,0 +1,109 @@
+"""Structured (MESH_CART) device-side builder against the oracle run with OPT_RENUMBER=.false.
+(natural element order): bit-exact ibool, coefficient planes / inverse mass to rounding, and the
+whole time loop of the synthetic benchmark family at test size."""
+import numpy as np
+import pytest
+
+import harness
+import orc
+from harness import rel_l2
+from sem2dpack_b200 import CartEngine
+
+pytestmark = pytest.mark.gpu
+SEED = 20261017
+
+
+def _oracle(nx, nz, **kw):
+    return orc.Oracle(harness.cart_deck(nx, nz, **kw), synthetic_seed=kw.pop("seed", SEED), renumber=False)
+
+
+@pytest.mark.parametrize("ngll,nx,nz,ezflt", [(5, 8, 8, 0), (5, 19, 13, 0), (5, 19, 21, 8), (5, 17, 16, 5),
+                                             (6, 11, 9, 4), (9, 7, 8, 3), (3, 30, 30, 15), (4, 5, 3, 1)])
+def test_ibool_bit_exact(ngll, nx, nz, ezflt):
+    o = orc.Oracle(harness.cart_deck(nx, nz, ngll=ngll, ezflt=ezflt, nrec=0, src=False, abso=(), fault=None),
+                   renumber=False)
+    e = CartEngine(ngll, 2, nx, nz, (0.0, nx * 100.0), (0.0, nz * 100.0), ezflt=ezflt, rho=2670.0, cp=6000.0, cs=3464.0)
+    assert e.npoin == o.i("npoin")
+    ib, _, _, co = e.get_tables(ibool=True, rmass=False, coord=True)
+    assert np.array_equal(ib, o.arr("ibool"))
+    assert np.abs(co - o.arr("coord")).max() <= 1e-9
+    e.close()
+    o.close()
+
+
+@pytest.mark.parametrize("ndof", [1, 2])
+@pytest.mark.parametrize("seed", [0, SEED])
+def test_operator_tables(ndof, seed):
+    nx, nz = 19, 13
+    o = orc.Oracle(harness.cart_deck(nx, nz, ndof=ndof, nrec=0, src=False, abso=()), synthetic_seed=seed, renumber=False)
+    e = CartEngine(5, ndof, nx, nz, (0.0, nx * 100.0), (0.0, nz * 100.0), seed=seed, rho=2670.0, cp=6000.0, cs=3464.0)
+    assert abs(e.dt - o.f("dt")) <= 1e-13 * e.dt
+    _, a, rm, _ = e.get_tables(ibool=False, a=(seed != 0), rmass=True)
+    assert rel_l2(rm, o.arr("rmass")) <= 1e-13
+    if seed != 0:
+        assert rel_l2(a, o.arr("a")) <= 1e-13
+    d = np.random.default_rng(3).standard_normal(e.npoin * ndof)
+    e.commit()
+    e.set_fields(d, d)
+    o.set_fields(d, d)
+    assert rel_l2(e.compute_fint(), o.compute_fint()) <= 1e-12
+    e.close()
+    o.close()
+
+
+@pytest.mark.parametrize("scheme,stacey,nx,nz,ezflt", [("leapfrog", False, 24, 16, 8), ("newmark", True, 19, 21, 9),
+                                                      ("leapfrog", False, 40, 24, 16)])
+def test_synthetic_benchmark_family(scheme, stacey, nx, nz, ezflt):
+    """heterogeneous P-SV box, two-sided SWF fault on tags 5,6 with a nucleation patch, absorbing
+    sides 1-4, force source, receivers: 300 steps, builder-made engine vs oracle."""
+    nsteps = 300
+    h = 100.0
+    o = orc.Oracle(harness.cart_deck(nx, nz, ezflt=ezflt, scheme=scheme, stacey=stacey, nsteps=nsteps),
+                   synthetic_seed=SEED, renumber=False)
+    kind = 0 if scheme == "leapfrog" else 1
+    e = CartEngine(5, 2, nx, nz, (0.0, nx * h), (0.0, nz * h), ezflt=ezflt, seed=SEED, scheme_kind=kind, courant=0.5)
+    assert abs(e.dt - o.f("dt")) <= 1e-13 * e.dt
+    # same order as the deck: DYNFLT first, then ABSORB 1..4 (bc_gen.f90:229-246)
+    fid = e.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, nx * h / 2, max(3 * h, 0.1 * nx * h), nt_max=nsteps)
+    for side in (1, 2, 3, 4):
+        e.add_abso_side(side, stacey)
+    e.add_force_at(0.37 * nx * h, 0.61 * nz * h, [o.f("src.0.dir1"), o.f("src.0.dir2")])
+    e.add_receiver_line(8, (0.1 * nx * h, 0.3 * nz * h), (0.9 * nx * h, 0.8 * nz * h), "V", 1, nsteps + 1)
+    e.commit()
+    tab = np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)])
+    e.step(nsteps, tab)
+    o.step(nsteps)
+    d, v, a = e.get_fields()
+    assert rel_l2(d, o.arr("d")) <= 1e-10
+    assert rel_l2(v, o.arr("v")) <= 1e-10
+    assert rel_l2(a, o.arr("acc")) <= 1e-10
+    s_ref, s_got = o.seis(), e.seis()
+    assert np.abs(s_got - s_ref).max() <= 2e-7 * np.abs(s_ref).max()
+    np_f = o.i("bc.0.np")
+    st = e.fault_state(fid, np_f)
+    for k in ("D", "V", "T", "MU"):
+        assert rel_l2(st[k], o.arr("bc.0." + k)) <= 1e-10, k
+    assert np.abs(st["D"]).max() > 1e-3
+    rec, pot = e.fault(fid, np_f)
+    assert rec.shape[0] == nsteps + 1
+    ref = o.arr("bc.0.out").reshape(-1, 6, np_f)
+    for c in range(6):
+        assert np.abs(rec[:, c] - ref[:, c]).max() <= 2e-7 * max(np.abs(ref[:, c]).max(), 1e-30)
+    e.close()
+    o.close()
+
+
+def test_fp32_builder():
+    nx, nz, nsteps = 24, 16, 200
+    o = orc.Oracle(harness.cart_deck(nx, nz, nsteps=nsteps, abso=(1, 2, 3, 4)), synthetic_seed=SEED, renumber=False)
+    e = CartEngine(5, 2, nx, nz, (0.0, nx * 100.0), (0.0, nz * 100.0), seed=SEED, precision=4)
+    for side in (1, 2, 3, 4):
+        e.add_abso_side(side)
+    e.add_force_at(0.37 * nx * 100, 0.61 * nz * 100, [o.f("src.0.dir1"), o.f("src.0.dir2")])
+    e.commit()
+    e.step(nsteps, np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)]))
+    o.step(nsteps)
+    d, v, _ = e.get_fields()
+    assert rel_l2(d, o.arr("d")) <= 1e-5
+    assert rel_l2(v, o.arr("v")) <= 1e-5
+    e.close()
