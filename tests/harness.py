@@ -23,6 +23,12 @@ def refdata():
     return np.load(os.path.join(GOLDEN, "refdata.npz"))
 
 
+def nuc_radius(nx, h=100.0):
+    """nucleation half-width: deliberately not a multiple of the GLL spacing, so that no node sits on
+    the patch edge where a last-bit difference in its coordinate would flip the `<=` test"""
+    return max(3 * h, 0.1 * nx * h) + 0.37 * h
+
+
 def cart_deck(nx, nz, ngll=5, ndof=2, ezflt=0, scheme="leapfrog", courant=0.5, nsteps=50, h=100.0, fault="swf",
               abso=(1, 2, 3, 4), stacey=False, nrec=8, src=True):
     """A MESH_CART deck of the synthetic benchmark family at test size."""
@@ -36,7 +42,7 @@ def cart_deck(nx, nz, ngll=5, ndof=2, ezflt=0, scheme="leapfrog", courant=0.5, n
         if fault == "swf":
             L += ["&BC_DYNFLT friction='SWF', Tn=-120.d6, TtH='PWCONR' /",
                   "&DIST_PWCONR num=2, ref=%gd0,%gd0 /" % (nx * h / 2, ezflt * h),
-                  "     %gd0" % (max(3 * h, 0.1 * nx * h)),
+                  "     %gd0" % nuc_radius(nx, h),
                   "81.6d6 70.d6",
                   "&BC_DYNFLT_SWF Dc=0.4d0, MuS=0.677d0, MuD=0.525d0 /"]
     for t in abso:

@@ -64,7 +64,7 @@ def test_synthetic_benchmark_family(scheme, stacey, nx, nz, ezflt):
     e = CartEngine(5, 2, nx, nz, (0.0, nx * h), (0.0, nz * h), ezflt=ezflt, seed=SEED, scheme_kind=kind, courant=0.5)
     assert abs(e.dt - o.f("dt")) <= 1e-13 * e.dt
     # same order as the deck: DYNFLT first, then ABSORB 1..4 (bc_gen.f90:229-246)
-    fid = e.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, nx * h / 2, max(3 * h, 0.1 * nx * h), nt_max=nsteps)
+    fid = e.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, nx * h / 2, harness.nuc_radius(nx, h), nt_max=nsteps)
     for side in (1, 2, 3, 4):
         e.add_abso_side(side, stacey)
     e.add_force_at(0.37 * nx * h, 0.61 * nz * h, [o.f("src.0.dir1"), o.f("src.0.dir2")])
