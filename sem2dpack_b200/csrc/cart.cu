@@ -699,7 +699,10 @@ int s2d_cart_add_abso(s2d_handle h, int32_t side, int32_t stacey) {
   const int N = G.N, ndof = G.ndof;
   const bool horiz = (side == 1 || side == 3);
   const int ne = horiz ? G.nx : G.nz;
-  const int np = ne * (N - 1) + 1;
+  // a vertical side crosses the split-node fault: its two coincident nodes are both on the boundary, the
+  // lower one first (stable sort of BC_set_bulk_node, spec_grid.f90:801-818)
+  const int split = (!horiz && G.ezflt > 0) ? 1 : 0;
+  const int np = ne * (N - 1) + 1 + split;
   std::vector<int> node(np), bibool((size_t)N * ne);
   std::vector<double> C((size_t)np * ndof, 0.0), K;
   const bool st = stacey && ndof == 2;
@@ -715,9 +718,9 @@ int s2d_cart_add_abso(s2d_handle h, int32_t side, int32_t stacey) {
       int ix, iz, i, j, pos;       // pos = position along the sorted (ascending coordinate) node list
       switch (side) {
         case 1: ix = e; iz = 0; i = k; j = 0; pos = e * (N - 1) + i; break;                 // edge_D
-        case 2: ix = G.nx - 1; iz = e; i = N - 1; j = k; pos = e * (N - 1) + j; break;      // edge_R
+        case 2: ix = G.nx - 1; iz = e; i = N - 1; j = k; pos = e * (N - 1) + j + ((split && e >= G.ezflt) ? 1 : 0); break;  // edge_R
         case 3: ix = e; iz = G.nz - 1; i = N - 1 - k; j = N - 1; pos = e * (N - 1) + i; break;  // edge_U
-        default: ix = 0; iz = e; i = 0; j = N - 1 - k; pos = e * (N - 1) + j; break;        // edge_L
+        default: ix = 0; iz = e; i = 0; j = N - 1 - k; pos = e * (N - 1) + j + ((split && e >= G.ezflt) ? 1 : 0); break;  // edge_L
       }
       if (pos < 0 || pos >= np) continue;  // virtual element: only its node on the interface counts
       double rho, cp, cs;

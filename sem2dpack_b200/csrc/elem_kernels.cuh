@@ -175,6 +175,20 @@ inline void launch_elem_node(int ngll, const ElemArgs<T>& A, cudaStream_t s) {
 // Index tables are split into a per-patch part (pnode: the global node of every patch-local node)
 // and a per-SHAPE part (local indices, colours, slot offsets) that structured meshes share between
 // all congruent patches, so it stays cache resident.
+__device__ __forceinline__ void l2_prefetch(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// bulk L2 prefetch of a byte range (cp.async.bulk.prefetch: 16-byte aligned address and size)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, size_t bytes) {
+  const size_t a0 = (size_t)p & ~(size_t)15;
+  size_t n = ((size_t)p + bytes - a0 + 15) & ~(size_t)15;
+  while (n > 0) {
+    const unsigned chunk = (unsigned)(n > 65536 ? 65536 : n);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0 + ((((size_t)p + bytes - a0 + 15) & ~(size_t)15) - n)), "r"(chunk) : "memory");
+    n -= chunk;
+  }
+}
+
 template <typename T, int N>
 struct PatchArgs {
   int npatch, EP, max_nloc, max_colors;
@@ -196,6 +210,7 @@ struct PatchArgs {
   T* fhalo;                   // (nslots, ndof)
   size_t npoin, nslots;
   int nelast, kd2, hetero;
+  int pf_dist;                // software prefetch distance in patches (0 = off)
   T H[N * N];                 // hprime, column-major: read as constant-bank operands
 };
 
@@ -227,6 +242,26 @@ __global__ void __launch_bounds__(patch_ep(N) * N, patch_min_ctas(N, NDOF, sizeo
   const int nloc = (int)(A.pnode_start[p + 1] - ps);
   const bool kv = A.ekv != nullptr;
 
+  // Software prefetch into L2.  CTAs are dispatched in blockIdx order, so patch p + pf_dist runs
+  // about pf_dist / (resident CTAs) CTA-lifetimes from now: its coefficient block (one contiguous
+  // run in the patch-major layout) and its node list are pulled into L2 by bulk prefetches, and at
+  // the end of this CTA the displacement sectors of patch p + pf_dist are touched through that
+  // list.  The own coefficient block is requested first so it is on its way during the staging.
+  if (A.pf_dist > 0 && t < 3) {
+    int pf = p;
+    if (t == 1) pf = p + A.pf_dist;
+    if (t == 2) pf = p + 2 * A.pf_dist;
+    if (pf < A.npatch) {
+      if (t < 2) {
+        if (A.hetero) {
+          const int e0 = A.pelem_start[pf], e1 = A.pelem_start[pf + 1];
+          l2_prefetch_bulk(A.a + (size_t)e0 * A.nelast * N2, (size_t)(e1 - e0) * A.nelast * N2 * sizeof(T));
+        }
+      } else {
+        l2_prefetch_bulk(A.pnode + A.pnode_start[pf], (size_t)(A.pnode_start[pf + 1] - A.pnode_start[pf]) * sizeof(int));
+      }
+    }
+  }
   if (t < N2) sH[t] = A.H[t];
   for (int l = t; l < nloc; l += blockDim.x) {
     const size_t g = (size_t)A.pnode[ps + l];
@@ -373,6 +408,18 @@ __global__ void __launch_bounds__(patch_ep(N) * N, patch_min_ctas(N, NDOF, sizeo
         A.f[(size_t)A.pnode[ps + l] + A.npoin * c] = val;
       else
         A.fhalo[(size_t)(sbase + so) + A.nslots * c] = val;
+    }
+  }
+  if (A.pf_dist > 0 && p + A.pf_dist < A.npatch) {
+    const long long pfs = A.pnode_start[p + A.pf_dist];
+    const int pfn = (int)(A.pnode_start[p + A.pf_dist + 1] - pfs);
+    for (int l = t; l < pfn; l += blockDim.x) {
+      const size_t g = (size_t)A.pnode[pfs + l];
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) {
+        l2_prefetch(A.d + g + A.npoin * c);
+        if (kv) l2_prefetch(A.v + g + A.npoin * c);
+      }
     }
   }
 }

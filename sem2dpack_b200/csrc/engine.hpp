@@ -2,6 +2,7 @@
 // of solve_leapfrog / solve_Newmark (SRC/solver.f90:42-84,140-160) + REC_store + BC_write.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 
@@ -11,6 +12,11 @@
 #include "plan.hpp"
 
 namespace s2d {
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
 
 enum BcKind { BC_ABSO = 1, BC_DIRNEU = 2, BC_DYNFLT = 3 };
 
@@ -136,6 +142,7 @@ class Engine : public EngineBase {
   DevBuf<uint8_t> p_sh_ecolor;
   DevBuf<T> p_coef, fhalo;
   bool p_hetero = false;
+  int pf_dist = env_int("S2D_PF_DIST", 444);  // L2 software-prefetch distance of the patch kernel
   bool cart_mode = false;  // structured builder: no host ibool, closed-form halo sum
   std::function<void(T*)> cart_halo_sum;
 
@@ -713,6 +720,7 @@ class Engine : public EngineBase {
     A.nelast = nelast;
     A.kd2 = kd2;
     A.hetero = p_hetero ? 1 : 0;
+    A.pf_dist = pf_dist;
     for (int k = 0; k < N * N; ++k) A.H[k] = (T)h_H[k];
     if (ndof == 1) launch_elem_patch_n<T, N, 1>(A, stream);
     else launch_elem_patch_n<T, N, 2>(A, stream);
