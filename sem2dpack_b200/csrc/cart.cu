@@ -626,10 +626,17 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
     G.halo_right = D->halo_right;
     gll_tables(G.N, G.xgll, G.wgll, S->H);
     // tiles: as square as the patch size allows
-    const int EP = patch_ep(G.N);
-    int PX = 1;
-    while ((PX + 1) * (PX + 1) <= EP) ++PX;
-    int PZ = EP / PX;
+    const int EP = Engine<double>::patch_EP(G.N);
+    // tile PX x PZ <= EP elements, at most twice as wide as tall (rows of a tile are runs of
+    // consecutive node ids, so wide is cheaper than tall), as many elements as possible
+    int PX = 1, PZ = 1;
+    for (int pz = 1; pz * pz <= EP; ++pz) {
+      const int px = std::min(EP / pz, 2 * pz);
+      if (px * pz >= PX * PZ) {
+        PX = px;
+        PZ = pz;
+      }
+    }
     G.PX = std::min(PX, G.nx);
     G.PZ = std::min(PZ, G.nz);
     G.ntx = (G.nx + G.PX - 1) / G.PX;

@@ -211,6 +211,7 @@ struct PatchArgs {
   size_t npoin, nslots;
   int nelast, kd2, hetero;
   int pf_dist;                // software prefetch distance in patches (0 = off)
+  int use_bulk;               // stream the coefficient block into shared memory with one TMA bulk copy
   T H[N * N];                 // hprime, column-major: read as constant-bank operands
 };
 
@@ -220,15 +221,53 @@ constexpr int patch_min_ctas(int ngll, int ndof, int tsize) {
   return (ngll <= 6 || tsize == 4) ? 2 : 1;
 }
 
+// ---- asynchronous copy helpers (sm_90+/sm_100a) ---------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* dst, const void* src) {  // SASS: LDGSTS
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
 template <typename T, int N, int NDOF>
 __global__ void __launch_bounds__(patch_ep(N) * N, patch_min_ctas(N, NDOF, sizeof(T)))
     k_elem_patch(const __grid_constant__ PatchArgs<T, N> A) {
   constexpr int N2 = N * N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sU = reinterpret_cast<T*>(smem_raw);   // [EP][NDOF][N2] displacement tiles, then tHt tiles
-  T* sF = sU + (size_t)A.EP * NDOF * N2;    // [NDOF][max_nloc] force accumulators (velocity stage for KV)
-  T* sD = sF + (size_t)NDOF * A.max_nloc;   // [NDOF][max_nloc] staged displacement
-  T* sH = sD + (size_t)NDOF * A.max_nloc;   // [N2]
+  __shared__ __align__(8) unsigned long long bar;
+  // shared-memory map (every region 16-byte aligned)
+  T* sU = reinterpret_cast<T*>(smem_raw);                        // [EP][NDOF][N2] displacement, then tHt tiles
+  T* sF = sU + align16((size_t)A.EP * NDOF * N2 * sizeof(T)) / sizeof(T);      // [NDOF][max_nloc] force sums
+  T* sD = sF + align16((size_t)NDOF * A.max_nloc * sizeof(T)) / sizeof(T);     // [NDOF][max_nloc] staged displ
+  T* sH = sD + align16((size_t)NDOF * A.max_nloc * sizeof(T)) / sizeof(T);     // [N2]
+  T* sA = sH + align16((size_t)N2 * sizeof(T)) / sizeof(T);                     // [nelast][N][cnt*N] planes
   const int p = blockIdx.x;
   const int t = threadIdx.x;
   const int es = A.pelem_start[p];
@@ -242,33 +281,53 @@ __global__ void __launch_bounds__(patch_ep(N) * N, patch_min_ctas(N, NDOF, sizeo
   const int nloc = (int)(A.pnode_start[p + 1] - ps);
   const bool kv = A.ekv != nullptr;
 
-  // Software prefetch into L2.  CTAs are dispatched in blockIdx order, so patch p + pf_dist runs
-  // about pf_dist / (resident CTAs) CTA-lifetimes from now: its coefficient block (one contiguous
-  // run in the patch-major layout) and its node list are pulled into L2 by bulk prefetches, and at
-  // the end of this CTA the displacement sectors of patch p + pf_dist are touched through that
-  // list.  The own coefficient block is requested first so it is on its way during the staging.
-  if (A.pf_dist > 0 && t < 3) {
-    int pf = p;
-    if (t == 1) pf = p + A.pf_dist;
-    if (t == 2) pf = p + 2 * A.pf_dist;
-    if (pf < A.npatch) {
-      if (t < 2) {
-        if (A.hetero) {
-          const int e0 = A.pelem_start[pf], e1 = A.pelem_start[pf + 1];
-          l2_prefetch_bulk(A.a + (size_t)e0 * A.nelast * N2, (size_t)(e1 - e0) * A.nelast * N2 * sizeof(T));
-        }
-      } else {
-        l2_prefetch_bulk(A.pnode + A.pnode_start[pf], (size_t)(A.pnode_start[pf + 1] - A.pnode_start[pf]) * sizeof(int));
+  // (1) the patch's coefficient block -- the bulk of the bytes -- starts streaming into shared
+  // memory through the TMA unit before anything else; it is consumed after the gradient stage.
+  const T* ablock = A.a + (size_t)es * A.nelast * N2;
+  const unsigned abytes = (unsigned)((size_t)cnt * A.nelast * N2 * sizeof(T));
+  const bool bulk = A.use_bulk && A.hetero && (((size_t)ablock & 15) == 0) && ((abytes & 15) == 0);
+  if (t == 0) {
+    if (bulk) {
+      mbar_init(&bar, 1);
+      mbar_expect_tx(&bar, abytes);
+      for (unsigned off = 0; off < abytes; off += 32768u) {
+        const unsigned n = (abytes - off) < 32768u ? (abytes - off) : 32768u;
+        bulk_g2s(reinterpret_cast<unsigned char*>(sA) + off, reinterpret_cast<const unsigned char*>(ablock) + off, n, &bar);
+      }
+    }
+    // software prefetch into L2 for the patch that will run pf_dist CTAs from now
+    if (A.pf_dist > 0 && p + A.pf_dist < A.npatch) {
+      const int pf = p + A.pf_dist;
+      if (A.hetero) {
+        const int e0 = A.pelem_start[pf], e1 = A.pelem_start[pf + 1];
+        l2_prefetch_bulk(A.a + (size_t)e0 * A.nelast * N2, (size_t)(e1 - e0) * A.nelast * N2 * sizeof(T));
+      }
+      if (p + 2 * A.pf_dist < A.npatch) {
+        const int pf2 = p + 2 * A.pf_dist;
+        l2_prefetch_bulk(A.pnode + A.pnode_start[pf2], (size_t)(A.pnode_start[pf2 + 1] - A.pnode_start[pf2]) * sizeof(int));
       }
     }
   }
+  // (2) stage the patch's unique nodes: index loads first, then asynchronous copies (LDGSTS)
   if (t < N2) sH[t] = A.H[t];
-  for (int l = t; l < nloc; l += blockDim.x) {
-    const size_t g = (size_t)A.pnode[ps + l];
+  for (int l0 = t; l0 < nloc; l0 += 4 * blockDim.x) {
+    int g[4];
 #pragma unroll
-    for (int c = 0; c < NDOF; ++c) {
-      sD[c * A.max_nloc + l] = A.d[g + A.npoin * c];
-      sF[c * A.max_nloc + l] = kv ? A.v[g + A.npoin * c] : (T)0;
+    for (int u = 0; u < 4; ++u) {
+      const int l = l0 + u * blockDim.x;
+      g[u] = l < nloc ? A.pnode[ps + l] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int l = l0 + u * blockDim.x;
+      if (g[u] >= 0) {
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) {
+          cp_async<sizeof(T)>(&sD[c * A.max_nloc + l], A.d + (size_t)g[u] + A.npoin * c);
+          if (kv) cp_async<sizeof(T)>(&sF[c * A.max_nloc + l], A.v + (size_t)g[u] + A.npoin * c);
+          else sF[c * A.max_nloc + l] = (T)0;
+        }
+      }
     }
   }
   int li[N];
@@ -277,6 +336,7 @@ __global__ void __launch_bounds__(patch_ep(N) * N, patch_min_ctas(N, NDOF, sizeo
 #pragma unroll
     for (int i = 0; i < N; ++i) li[i] = lp[i];
   }
+  cp_async_wait_all();
   __syncthreads();
 
   T* myU = sU + (size_t)el * NDOF * N2;
@@ -328,7 +388,7 @@ __global__ void __launch_bounds__(patch_ep(N) * N, patch_min_ctas(N, NDOF, sizeo
     const T* ap;
     size_t qstride, istride;
     if (A.hetero) {
-      ap = A.a + (size_t)es * A.nelast * N2 + t;
+      ap = (bulk ? sA : ablock) + t;
       istride = (size_t)cnt * N;
       qstride = (size_t)N * istride;
     } else {
@@ -336,6 +396,7 @@ __global__ void __launch_bounds__(patch_ep(N) * N, patch_min_ctas(N, NDOF, sizeo
       qstride = N2;
       istride = 1;
     }
+    if (bulk) mbar_wait(&bar, 0);
     T tH[NDOF][N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -401,11 +462,12 @@ __global__ void __launch_bounds__(patch_ep(N) * N, patch_min_ctas(N, NDOF, sizeo
   const long long sbase = A.pslot_base[p];
   for (int l = t; l < nloc; l += blockDim.x) {
     const int so = slotp[l];
+    const size_t g = (size_t)A.pnode[ps + l];
 #pragma unroll
     for (int c = 0; c < NDOF; ++c) {
       const T val = sF[c * A.max_nloc + l];
       if (so < 0)
-        A.f[(size_t)A.pnode[ps + l] + A.npoin * c] = val;
+        A.f[g + A.npoin * c] = val;
       else
         A.fhalo[(size_t)(sbase + so) + A.nslots * c] = val;
     }
@@ -423,6 +485,7 @@ __global__ void __launch_bounds__(patch_ep(N) * N, patch_min_ctas(N, NDOF, sizeo
     }
   }
 }
+
 
 // adds the halo slots of each node shared between patches, in ascending patch order (generic plan)
 template <typename T>
@@ -443,8 +506,9 @@ __global__ void k_halo_sum(T* __restrict__ f, const T* __restrict__ fhalo, const
 template <typename T, int N, int NDOF>
 inline void launch_elem_patch_n(const PatchArgs<T, N>& A, cudaStream_t s) {
   if (A.npatch <= 0) return;
-  const size_t smem =
-      ((size_t)A.EP * NDOF * N * N + 2 * (size_t)NDOF * A.max_nloc + N * N) * sizeof(T);
+  size_t smem = align16((size_t)A.EP * NDOF * N * N * sizeof(T)) + 2 * align16((size_t)NDOF * A.max_nloc * sizeof(T)) +
+                align16((size_t)N * N * sizeof(T));
+  if (A.use_bulk && A.hetero) smem += align16((size_t)A.EP * A.nelast * N * N * sizeof(T));
   static size_t configured = 0;
   if (smem > configured) {
     S2D_CUDA(cudaFuncSetAttribute(k_elem_patch<T, N, NDOF>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -143,6 +143,7 @@ class Engine : public EngineBase {
   DevBuf<T> p_coef, fhalo;
   bool p_hetero = false;
   int pf_dist = env_int("S2D_PF_DIST", 444);  // L2 software-prefetch distance of the patch kernel
+  int use_bulk = env_int("S2D_BULK", 1);      // TMA bulk copy of the coefficient block into shared memory
   bool cart_mode = false;  // structured builder: no host ibool, closed-form halo sum
   std::function<void(T*)> cart_halo_sum;
 
@@ -554,7 +555,11 @@ class Engine : public EngineBase {
     for (int e = 0; e < nelem; ++e) list[fill[h_color[e]]++] = e;
     color_elems.upload(list);
   }
-  static int patch_EP(int ngll) { return patch_ep(ngll); }
+  static int patch_EP(int ngll) {
+    const int cap = patch_ep(ngll);
+    const int want = env_int("S2D_EP", ngll <= 6 ? 32 : cap);
+    return std::max(4, std::min(cap, want));
+  }
   void build_patch_plan_dev() {
     const int n2 = ngll * ngll;
     build_patch_plan(h_ibool.data(), n2, nelem, npoin, patch_EP(ngll), plan);
@@ -721,6 +726,7 @@ class Engine : public EngineBase {
     A.kd2 = kd2;
     A.hetero = p_hetero ? 1 : 0;
     A.pf_dist = pf_dist;
+    A.use_bulk = use_bulk;
     for (int k = 0; k < N * N; ++k) A.H[k] = (T)h_H[k];
     if (ndof == 1) launch_elem_patch_n<T, N, 1>(A, stream);
     else launch_elem_patch_n<T, N, 2>(A, stream);
