@@ -94,7 +94,7 @@ def test_synthetic_benchmark_family(scheme, stacey, nx, nz, ezflt):
 
 
 def test_fp32_builder():
-    nx, nz, nsteps = 24, 16, 200
+    nx, nz, nsteps = 24, 16, 100
     o = orc.Oracle(harness.cart_deck(nx, nz, nsteps=nsteps, abso=(1, 2, 3, 4)), synthetic_seed=SEED, renumber=False)
     e = CartEngine(5, 2, nx, nz, (0.0, nx * 100.0), (0.0, nz * 100.0), seed=SEED, precision=4)
     for side in (1, 2, 3, 4):
