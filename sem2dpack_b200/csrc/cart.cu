@@ -41,8 +41,7 @@ struct CartGeom {
   long long ix0, iz0;
   double rho, cp, cs;
   int halo_left, halo_right;
-  // tiles
-  int PX, PZ, ntx, ntz_lo, ntz, Pmax, LXmax, LZmax;
+  StripGeom S;  // lattice / strip decomposition of the z-marching kernel
   double xgll[10], wgll[10];
 };
 
@@ -114,6 +113,11 @@ __host__ __device__ inline long long cart_node_id(const CartGeom& G, int ix, int
   }
   return elem_base(G, ix, iz) + o + 1;
 }
+// Internal (device) numbering: the GLL lattice, row-major, the split fault row stored twice.
+// 1-based like every node id that crosses the engine's add_* calls.  (i,j) 0-based here.
+__host__ __device__ inline long long cart_lat_id(const CartGeom& G, int ix, int iz, int i, int j) {
+  return (long long)strip_lat_row(G.S, iz, j) * G.S.LX + (long long)ix * (G.N - 1) + i + 1;
+}
 
 // material at GLL point (i,j) (0-based) of element (ix,iz)
 __host__ __device__ inline void cart_material(const CartGeom& G, int ix, int iz, int i, int j, double& rho,
@@ -132,90 +136,46 @@ __host__ __device__ inline void cart_material(const CartGeom& G, int ix, int iz,
   rho = 2670.0 * (1.0 + 0.05 * u3);
 }
 
-// tile geometry
-struct Tile {
-  int ex0, ez0, cx, cz;       // first element, extent in elements
-  int hasL, hasR, hasD, hasU; // connected neighbour tiles
-};
-__host__ __device__ inline Tile tile_of(const CartGeom& G, int tx, int tz) {
-  Tile t;
-  t.ex0 = tx * G.PX;
-  t.cx = min(G.PX, G.nx - t.ex0);
-  int zend;
-  if (tz < G.ntz_lo) {
-    t.ez0 = tz * G.PZ;
-    zend = G.ezflt;
+// flat-grid coefficient planes a(i,j,plane) (mat_elastic.f90:323-358)
+__host__ __device__ inline void cart_planes(const CartGeom& G, double rho, double cp, double cs, int i, int j,
+                                            int nelast, double* av) {
+  const double DxiDx = 2.0 / G.hx, DetaDz = 2.0 / G.hz;
+  const double det = (0.5 * G.hx) * (0.5 * G.hz);
+  const double la = rho * (cp * cp - 2.0 * cs * cs);
+  const double mu = rho * cs * cs;
+  const double weights = det * (G.wgll[i] * G.wgll[j]);
+  if (nelast == 2) {
+    av[0] = mu * DxiDx * DxiDx;
+    av[1] = mu * DetaDz * DetaDz;
   } else {
-    t.ez0 = G.ezflt + (tz - G.ntz_lo) * G.PZ;
-    zend = G.nz;
+    const double Kx = la + 2.0 * mu;
+    av[0] = Kx * DxiDx * DxiDx;
+    av[1] = la * DxiDx * DetaDz;
+    av[2] = Kx * DetaDz * DetaDz;
+    av[3] = mu * DetaDz * DetaDz;
+    av[4] = mu * DxiDx * DetaDz;
+    av[5] = mu * DxiDx * DxiDx;
   }
-  t.cz = min(G.PZ, zend - t.ez0);
-  t.hasL = tx > 0;
-  t.hasR = tx < G.ntx - 1;
-  t.hasD = tz > 0 && tz != G.ntz_lo;
-  t.hasU = tz < G.ntz - 1 && tz != G.ntz_lo - 1;
-  return t;
-}
-__host__ __device__ inline int perim_index(int a, int b, int LX, int LZ) {
-  if (b == 0) return a;
-  if (b == LZ - 1) return LX + a;
-  if (a == 0) return 2 * LX + (b - 1);
-  return 2 * LX + (LZ - 2) + (b - 1);
+  for (int pl = 0; pl < nelast; ++pl) av[pl] = -weights * av[pl];
 }
 
 // ---------------------------------------------------------------------------------------------
 // kernels
-__global__ void k_cart_pnode(CartGeom G, const long long* __restrict__ pnode_start, int* __restrict__ pnode) {
-  const int p = blockIdx.x;
-  const int tx = p % G.ntx, tz = p / G.ntx;
-  const Tile t = tile_of(G, tx, tz);
-  const int LX = t.cx * (G.N - 1) + 1, LZ = t.cz * (G.N - 1) + 1;
-  const long long ps = pnode_start[p];
-  for (int l = threadIdx.x; l < LX * LZ; l += blockDim.x) {
-    const int a = l % LX, b = l / LX;
-    const int lx = min(a / (G.N - 1), t.cx - 1), lz = min(b / (G.N - 1), t.cz - 1);
-    const int i = a - lx * (G.N - 1), j = b - lz * (G.N - 1);
-    pnode[ps + l] = (int)(cart_node_id(G, t.ex0 + lx, t.ez0 + lz, i + 1, j + 1) - 1);
-  }
-}
-
-// flat-grid coefficient planes (mat_elastic.f90:323-358), written patch-major [plane][i][thread]
+// coefficient planes in the strip layout of strip_kernels.cuh; one thread per GLL point of an element
 template <typename T>
-__global__ void k_cart_coef(CartGeom G, const int* __restrict__ pelem_start, T* __restrict__ coef, int nelast) {
-  const int p = blockIdx.x;
-  const int tx = p % G.ntx, tz = p / G.ntx;
-  const Tile t = tile_of(G, tx, tz);
+__global__ void k_cart_coef(CartGeom G, T* __restrict__ coef, int nelast) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int N = G.N, N2 = N * N;
-  const int cnt = t.cx * t.cz;
-  const size_t base = (size_t)pelem_start[p] * nelast * N2;
-  const size_t nthr = (size_t)cnt * N;
-  const double DxiDx = 2.0 / G.hx, DetaDz = 2.0 / G.hz;
-  const double det = (0.5 * G.hx) * (0.5 * G.hz);
-  for (int w = threadIdx.x; w < cnt * N2; w += blockDim.x) {
-    const int el = w / N2, k = w - el * N2;
-    const int i = k % N, j = k / N;
-    const int lx = el % t.cx, lz = el / t.cx;
-    double rho, cp, cs;
-    cart_material(G, t.ex0 + lx, t.ez0 + lz, i, j, rho, cp, cs);
-    const double la = rho * (cp * cp - 2.0 * cs * cs);
-    const double mu = rho * cs * cs;
-    const double weights = det * (G.wgll[i] * G.wgll[j]);
-    double av[6];
-    if (nelast == 2) {
-      av[0] = mu * DxiDx * DxiDx;
-      av[1] = mu * DetaDz * DetaDz;
-    } else {
-      const double Kx = la + 2.0 * mu;
-      av[0] = Kx * DxiDx * DxiDx;
-      av[1] = la * DxiDx * DetaDz;
-      av[2] = Kx * DetaDz * DetaDz;
-      av[3] = mu * DetaDz * DetaDz;
-      av[4] = mu * DxiDx * DetaDz;
-      av[5] = mu * DxiDx * DxiDx;
-    }
-    for (int pl = 0; pl < nelast; ++pl)
-      coef[base + ((size_t)pl * N + i) * nthr + (size_t)el * N + j] = (T)(-weights * av[pl]);
-  }
+  const long long total = (long long)G.nx * G.nz * N2;
+  if (w >= total) return;
+  const long long e = w / N2;
+  const int k = (int)(w - e * N2);
+  const int i = k % N, j = k / N;
+  const int ix = (int)(e % G.nx), iz = (int)(e / G.nx);
+  double rho, cp, cs, av[6];
+  cart_material(G, ix, iz, i, j, rho, cp, cs);
+  cart_planes(G, rho, cp, cs, i, j, nelast, av);
+  for (int pl = 0; pl < nelast; ++pl) coef[strip_coef_index(G.S, nelast, ix, iz, i, j, pl)] = (T)av[pl];
 }
 
 // assembled mass (mat_mass.f90:50-57): each node is summed by its first element, over the elements
@@ -256,7 +216,7 @@ __global__ void k_cart_mass(CartGeom G, T* __restrict__ mass, size_t npoin) {
       cart_material(G, eix, eiz, li, lj, rho, cp, cs);
       sum = sum + rho * (det * (G.wgll[li] * G.wgll[lj]));
     }
-  const size_t node = (size_t)(cart_node_id(G, ix, iz, i + 1, j + 1) - 1);
+  const size_t node = (size_t)(cart_lat_id(G, ix, iz, i, j) - 1);
   for (int c = 0; c < G.ndof; ++c) mass[node + npoin * c] = (T)sum;
 }
 
@@ -298,46 +258,6 @@ __global__ void k_gather_nodes(const T* src, size_t npoin, int ndof, int np, con
   for (int c = 0; c < ndof; ++c) out[k + (size_t)np * c] = (double)src[(size_t)(node[k] - 1) + npoin * c];
 }
 
-// halo sum in closed form: one thread per (tile, perimeter node); the tile that holds the node on
-// neither a connected left nor a connected lower side owns it and adds the partial sums of the
-// tiles around it in ascending tile order.
-template <typename T>
-__global__ void k_cart_halo_sum(CartGeom G, T* __restrict__ f, const T* __restrict__ fhalo,
-                                const long long* __restrict__ pnode_start, const int* __restrict__ pnode,
-                                size_t npoin, size_t nslots) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long p = w / G.Pmax;
-  const int idx = (int)(w - p * G.Pmax);
-  if (p >= (long long)G.ntx * G.ntz) return;
-  const int tx = (int)(p % G.ntx), tz = (int)(p / G.ntx);
-  const Tile t = tile_of(G, tx, tz);
-  const int LX = t.cx * (G.N - 1) + 1, LZ = t.cz * (G.N - 1) + 1;
-  if (idx >= 2 * LX + 2 * (LZ - 2)) return;
-  int a, b;
-  if (idx < LX) { a = idx; b = 0; }
-  else if (idx < 2 * LX) { a = idx - LX; b = LZ - 1; }
-  else if (idx < 2 * LX + LZ - 2) { a = 0; b = idx - 2 * LX + 1; }
-  else { a = LX - 1; b = idx - (2 * LX + LZ - 2) + 1; }
-  const bool onL = (a == 0) && t.hasL, onR = (a == LX - 1) && t.hasR;
-  const bool onD = (b == 0) && t.hasD, onU = (b == LZ - 1) && t.hasU;
-  if (onL || onD) return;        // a lower-numbered tile owns it
-  if (!(onR || onU)) return;     // private node
-  const size_t g = (size_t)pnode[pnode_start[p] + a + (long long)LX * b];
-  for (int c = 0; c < G.ndof; ++c) {
-    const T* fh = fhalo + nslots * c;
-    T acc = fh[(size_t)p * G.Pmax + idx];
-    if (onR) {  // right tile: same row of tiles (same cz), node at (0,b)
-      const Tile tr = tile_of(G, tx + 1, tz);
-      acc += fh[(size_t)(p + 1) * G.Pmax + perim_index(0, b, tr.cx * (G.N - 1) + 1, LZ)];
-    }
-    if (onU) {  // upper tile: same cx, node at (a,0)
-      acc += fh[(size_t)(p + G.ntx) * G.Pmax + a];
-    }
-    if (onR && onU) acc += fh[(size_t)(p + G.ntx + 1) * G.Pmax + 0];
-    f[g + npoin * c] = acc;
-  }
-}
-
 // ibool in the reference layout (ngll,ngll,nelem), natural element order
 __global__ void k_cart_ibool(CartGeom G, int* __restrict__ ibool) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,6 +267,28 @@ __global__ void k_cart_ibool(CartGeom G, int* __restrict__ ibool) {
   const long long e = w / N2;
   const int k = (int)(w - e * N2);
   ibool[w] = (int)cart_node_id(G, (int)(e % G.nx), (int)(e / G.nx), k % G.N + 1, k / G.N + 1);
+}
+
+// field transfer between the caller's numbering (SE_init_numbering ids) and the lattice:
+// to_ref != 0: ref[id] = lat[lattice];  else lat[lattice] = ref[id].  Nodes shared by several
+// elements are written several times with the same value.
+template <typename TS, typename TD>
+__global__ void k_cart_permute(CartGeom G, const TS* __restrict__ src, TD* __restrict__ dst, size_t npoin,
+                               int ncomp, int to_ref) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = G.N, N2 = N * N;
+  const long long total = (long long)G.nx * G.nz * N2;
+  if (w >= total) return;
+  const long long e = w / N2;
+  const int k = (int)(w - e * N2);
+  const int i = k % N, j = k / N;
+  const int ix = (int)(e % G.nx), iz = (int)(e / G.nx);
+  const size_t r = (size_t)(cart_node_id(G, ix, iz, i + 1, j + 1) - 1);
+  const size_t l = (size_t)(cart_lat_id(G, ix, iz, i, j) - 1);
+  for (int c = 0; c < ncomp; ++c) {
+    if (to_ref) dst[r + npoin * c] = (TD)src[l + npoin * c];
+    else dst[l + npoin * c] = (TD)src[r + npoin * c];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -429,112 +371,37 @@ template <typename T>
 static void cart_build(Engine<T>& E, CartState& S) {
   CartGeom& G = S.G;
   const int N = G.N, N2 = N * N;
-  const int npatch = G.ntx * G.ntz;
   const int nelast = (G.ndof == 1) ? 2 : 6;
   cudaStream_t st = E.stream;
-  // per-patch prefix tables + shapes (host; npatch entries)
-  std::vector<int> pelem_start(npatch + 1, 0), pshape(npatch);
-  std::vector<long long> pnode_start(npatch + 1, 0), pslot_base(npatch);
-  std::map<std::vector<int>, int> shape_ids;
-  std::vector<Tile> shape_tiles;
-  for (int tz = 0; tz < G.ntz; ++tz)
-    for (int tx = 0; tx < G.ntx; ++tx) {
-      const int p = tx + G.ntx * tz;
-      const Tile t = tile_of(G, tx, tz);
-      pelem_start[p + 1] = pelem_start[p] + t.cx * t.cz;
-      pnode_start[p + 1] = pnode_start[p] + (long long)(t.cx * (N - 1) + 1) * (t.cz * (N - 1) + 1);
-      pslot_base[p] = (long long)p * G.Pmax;
-      std::vector<int> key = {t.cx, t.cz, t.hasL, t.hasR, t.hasD, t.hasU};
-      auto it = shape_ids.find(key);
-      if (it == shape_ids.end()) {
-        it = shape_ids.emplace(key, (int)shape_tiles.size()).first;
-        shape_tiles.push_back(t);
-      }
-      pshape[p] = it->second;
-    }
-  const int EP = G.PX * G.PZ;
-  const int max_nloc = G.LXmax * G.LZmax;
-  const int nshape = (int)shape_tiles.size();
-  std::vector<uint16_t> lidx((size_t)nshape * EP * N2, 0);
-  std::vector<uint8_t> ecol((size_t)nshape * EP, 0);
-  std::vector<int> slot((size_t)nshape * max_nloc, -1);
-  for (int s = 0; s < nshape; ++s) {
-    const Tile& t = shape_tiles[s];
-    const int LX = t.cx * (N - 1) + 1, LZ = t.cz * (N - 1) + 1;
-    for (int lz = 0; lz < t.cz; ++lz)
-      for (int lx = 0; lx < t.cx; ++lx) {
-        const int el = lx + t.cx * lz;
-        ecol[(size_t)s * EP + el] = (uint8_t)((lx & 1) + 2 * (lz & 1));
-        for (int j = 0; j < N; ++j)
-          for (int i = 0; i < N; ++i)
-            lidx[((size_t)s * EP + el) * N2 + i + N * j] = (uint16_t)((lx * (N - 1) + i) + LX * (lz * (N - 1) + j));
-      }
-    for (int b = 0; b < LZ; ++b)
-      for (int a = 0; a < LX; ++a) {
-        const bool sh = (a == 0 && t.hasL) || (a == LX - 1 && t.hasR) || (b == 0 && t.hasD) || (b == LZ - 1 && t.hasU);
-        if (sh) slot[(size_t)s * max_nloc + a + LX * b] = perim_index(a, b, LX, LZ);
-      }
-  }
-  E.pp_npatch = npatch;
-  E.pp_EP = EP;
-  E.pp_max_nloc = max_nloc;
-  E.pp_max_colors = 4;
-  E.pp_nslots = (size_t)npatch * G.Pmax;
-  E.p_pelem_start.upload(pelem_start);
-  E.p_pshape.upload(pshape);
-  E.p_sh_lidx.upload(lidx);
-  E.p_sh_ecolor.upload(ecol);
-  E.p_sh_slot.upload(slot);
-  E.p_pslot_base.upload(pslot_base);
-  E.p_pnode_start.upload(pnode_start);
-  E.p_pnode.alloc((size_t)pnode_start[npatch]);
-  E.fhalo.alloc(E.pp_nslots * G.ndof);
-  E.fhalo.zero(st);
-  k_cart_pnode<<<npatch, 256, 0, st>>>(G, E.p_pnode_start.p, E.p_pnode.p);
-  // coefficient planes
+  const long long tot = (long long)E.nelem * N2;
+  const unsigned nblk = (unsigned)((tot + 255) / 256);
+  // coefficient planes, one block per element (mat_gen.f90:357-365 would share one block between
+  // homogeneous elements; the strip kernel streams its planes, so they are materialised per element)
   E.nelast = nelast;
   E.kd2 = (N == 5) ? 1 : 0;  // OPT_NGLL (constants.f90:6, mat_elastic.f90:412)
   E.nkv = 0;
-  if (G.seed != 0) {
-    E.ncoefsets = E.nelem;
-    E.p_hetero = true;
-    E.p_coef.alloc((size_t)E.nelem * nelast * N2);
-    k_cart_coef<T><<<npatch, 256, 0, st>>>(G, E.p_pelem_start.p, E.p_coef.p, nelast);
-  } else {
-    // homogeneous: one shared block (mat_gen.f90:357-365), computed from element 1
-    E.ncoefsets = 1;
-    E.p_hetero = false;
-    std::vector<double> a((size_t)nelast * N2);
-    const double DxiDx = 2.0 / G.hx, DetaDz = 2.0 / G.hz, det = (0.5 * G.hx) * (0.5 * G.hz);
-    const double mu = G.rho * G.cs * G.cs, la = G.rho * (G.cp * G.cp - 2.0 * G.cs * G.cs);
-    for (int j = 0; j < N; ++j)
-      for (int i = 0; i < N; ++i) {
-        const double w = det * (G.wgll[i] * G.wgll[j]);
-        double av[6];
-        if (nelast == 2) {
-          av[0] = mu * DxiDx * DxiDx;
-          av[1] = mu * DetaDz * DetaDz;
-        } else {
-          const double Kx = la + 2.0 * mu;
-          av[0] = Kx * DxiDx * DxiDx; av[1] = la * DxiDx * DetaDz; av[2] = Kx * DetaDz * DetaDz;
-          av[3] = mu * DetaDz * DetaDz; av[4] = mu * DxiDx * DetaDz; av[5] = mu * DxiDx * DxiDx;
-        }
-        for (int pl = 0; pl < nelast; ++pl) a[(size_t)pl * N2 + i + N * j] = -w * av[pl];
-      }
-    upload_as(E.coef, a.data(), a.size());
-    E.p_eset.alloc(E.nelem);
-    E.p_eset.zero(st);
-  }
+  E.ncoefsets = G.seed != 0 ? E.nelem : 1;
+  E.p_hetero = true;
+  E.p_coef.alloc((size_t)E.nelem * nelast * N2);
+  k_cart_coef<T><<<nblk, 256, 0, st>>>(G, E.p_coef.p, nelast);
   // mass (kept un-inverted in rmass until commit)
-  const long long tot = (long long)E.nelem * N2;
-  k_cart_mass<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(G, E.rmass.p, E.npoin);
+  k_cart_mass<T><<<nblk, 256, 0, st>>>(G, E.rmass.p, E.npoin);
   S2D_CUDA(cudaGetLastError());
-  CartGeom Gc = G;
-  E.cart_halo_sum = [&E, Gc](T* ff) {
-    const long long n = (long long)Gc.ntx * Gc.ntz * Gc.Pmax;
-    k_cart_halo_sum<T><<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(Gc, ff, E.fhalo.p, E.p_pnode_start.p,
-                                                                         E.p_pnode.p, E.npoin, E.pp_nslots);
-    E.launches++;
+  // halo arrays of the strip kernel
+  E.cart_S = G.S;
+  E.cart_hx.alloc((size_t)G.ndof * std::max(G.S.nstrips - 1, 0) * G.S.LZ + 1);
+  E.cart_hz.alloc((size_t)G.ndof * G.S.nseg * G.S.nstrips * G.S.WL + 1);
+  E.cart_hx.zero(st);
+  E.cart_hz.zero(st);
+  const CartGeom Gc = G;
+  Engine<T>* Ep = &E;
+  E.cart_to_ref = [Ep, Gc, nblk](const T* lat, double* ref) {
+    k_cart_permute<T, double><<<nblk, 256, 0, Ep->stream>>>(Gc, lat, ref, Ep->npoin, Gc.ndof, 1);
+    S2D_CUDA(cudaGetLastError());
+  };
+  E.cart_from_ref = [Ep, Gc, nblk](const double* ref, T* lat) {
+    k_cart_permute<double, T><<<nblk, 256, 0, Ep->stream>>>(Gc, ref, lat, Ep->npoin, Gc.ndof, 0);
+    S2D_CUDA(cudaGetLastError());
   };
   S2D_CUDA(cudaStreamSynchronize(st));
 }
@@ -625,28 +492,31 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
     G.halo_left = D->halo_left;
     G.halo_right = D->halo_right;
     gll_tables(G.N, G.xgll, G.wgll, S->H);
-    // tiles: as square as the patch size allows
-    const int EP = Engine<double>::patch_EP(G.N);
-    // tile PX x PZ <= EP elements, at most twice as wide as tall (rows of a tile are runs of
-    // consecutive node ids, so wide is cheaper than tall), as many elements as possible
-    int PX = 1, PZ = 1;
-    for (int pz = 1; pz * pz <= EP; ++pz) {
-      const int px = std::min(EP / pz, 2 * pz);
-      if (px * pz >= PX * PZ) {
-        PX = px;
-        PZ = pz;
-      }
+    // strip decomposition of the z-marching kernel (strip_kernels.cuh)
+    {
+      StripGeom& Q = G.S;
+      Q.N = G.N;
+      Q.ndof = G.ndof;
+      Q.nx = G.nx;
+      Q.nz = G.nz;
+      Q.ezflt = G.ezflt;
+      Q.EPW = 32 / G.N;
+      Q.W = Q.EPW * (G.N - 1);
+      Q.WL = Q.W + 1;
+      Q.nstrips = (G.nx + Q.EPW - 1) / Q.EPW;
+      Q.SEG = std::max(1, env_int("S2D_SEG", 32));
+      Q.nseg_lo = G.ezflt > 0 ? (G.ezflt + Q.SEG - 1) / Q.SEG : 0;
+      Q.nseg = Q.nseg_lo + (G.nz - G.ezflt + Q.SEG - 1) / Q.SEG;
+      Q.LX = G.nx * (G.N - 1) + 1;
+      Q.LZ = G.nz * (G.N - 1) + 1 + (G.ezflt > 0 ? 1 : 0);
+      Q.nitems = (long long)Q.nseg * Q.nstrips;
     }
-    G.PX = std::min(PX, G.nx);
-    G.PZ = std::min(PZ, G.nz);
-    G.ntx = (G.nx + G.PX - 1) / G.PX;
-    G.ntz_lo = G.ezflt > 0 ? (G.ezflt + G.PZ - 1) / G.PZ : 0;
-    G.ntz = G.ntz_lo + (G.nz - G.ezflt + G.PZ - 1) / G.PZ;
-    G.LXmax = G.PX * (G.N - 1) + 1;
-    G.LZmax = G.PZ * (G.N - 1) + 1;
-    G.Pmax = 2 * G.LXmax + 2 * (G.LZmax - 2);
     const long long npoin = cart_npoin(G);
     const long long nelem = (long long)G.nx * G.nz;
+    if (npoin != (long long)G.S.LX * G.S.LZ) {
+      g_cart_err = "internal error: lattice size does not match the node count";
+      return S2D_EINVAL;
+    }
     if (npoin > 2147483647LL || nelem * G.N * G.N > (1LL << 40)) {
       g_cart_err = "mesh too large for 32-bit node ids";
       return S2D_EINVAL;
@@ -743,7 +613,7 @@ int s2d_cart_add_abso(s2d_handle h, int32_t side, int32_t stacey) {
         C[pos + np] += rho * c[2] * CoefIntegr;
       }
       if (e >= 0 && e < ne) {
-        node[pos] = (int)cart_node_id(G, ix, iz, i + 1, j + 1);
+        node[pos] = (int)cart_lat_id(G, ix, iz, i, j);
         bibool[k + (size_t)N * e] = pos + 1;
         if (st) {
           const double kv = CoefIntegr * dloc_dglob * rho * c[GeoDimTan] * (2.0 * c[GeoDimTan] - c[GeoDimNor]);
@@ -787,8 +657,8 @@ int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, doub
       if (pos < 0 || pos >= np) continue;
       B[pos] += G.wgll[i] * (0.5 * G.hx);  // BC_get_normal_and_weights (spec_grid.f90:961-1011)
       if (e < 0 || e >= G.nx) continue;
-      node1[pos] = (int)cart_node_id(G, e, G.ezflt - 1, i + 1, N);
-      node2[pos] = (int)cart_node_id(G, e, G.ezflt, i + 1, 1);
+      node1[pos] = (int)cart_lat_id(G, e, G.ezflt - 1, i, N - 1);
+      node2[pos] = (int)cart_lat_id(G, e, G.ezflt, i, 0);
       const double x = gx_of(G, e, i);
       coord[2 * pos] = x;
       coord[2 * pos + 1] = G.z0 + G.hz * G.ezflt;
@@ -869,7 +739,7 @@ int s2d_cart_add_force(s2d_handle h, double x, double z, const double* dir, int3
   int ex, i, ez, j;
   nearest_1d(G, x, G.x0, G.hx, G.nx, ex, i);
   nearest_1d(G, z, G.z0, G.hz, G.nz, ez, j);
-  const int id = Eb->add_force((int)cart_node_id(G, ex, ez, i + 1, j + 1), dir);
+  const int id = Eb->add_force((int)cart_lat_id(G, ex, ez, i, j), dir);
   if (src_id) *src_id = id;
   CART_GUARD_END
 }
@@ -885,7 +755,7 @@ int s2d_cart_add_receivers(s2d_handle h, int32_t nx, double xa, double za, doubl
     int ex, i, ez, j;
     nearest_1d(G, xa + w * (xb - xa), G.x0, G.hx, G.nx, ex, i);
     nearest_1d(G, za + w * (zb - za), G.z0, G.hz, G.nz, ez, j);
-    const int id = (int)cart_node_id(G, ex, ez, i + 1, j + 1);
+    const int id = (int)cart_lat_id(G, ex, ez, i, j);
     bool dup = false;
     if (ig.size() > 1)
       for (int v : ig) dup = dup || (v == id);
@@ -908,48 +778,35 @@ int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double*
     ib.download(ibool);
   }
   if (a) {
-    // reference layout a(ngll,ngll,nelast,nelem) from the patch-major planes
+    // reference layout a(ngll,ngll,nelast,nelem) from the strip layout
     const int nelast = (G.ndof == 1) ? 2 : 6;
     std::vector<double> pc;
-    bool hetero;
     if (Eb->prec == 8) {
-      auto* E = as_engine<double>(Eb);
-      hetero = E->p_hetero;
-      pc = hetero ? E->p_coef.to_host() : E->coef.to_host();
+      pc = as_engine<double>(Eb)->p_coef.to_host();
     } else {
-      auto* E = as_engine<float>(Eb);
-      hetero = E->p_hetero;
-      std::vector<float> t = hetero ? E->p_coef.to_host() : E->coef.to_host();
+      std::vector<float> t = as_engine<float>(Eb)->p_coef.to_host();
       pc.assign(t.begin(), t.end());
     }
-    if (!hetero) {
-      std::copy(pc.begin(), pc.end(), a);
-    } else {
-      size_t es = 0;
-      for (int tz = 0; tz < G.ntz; ++tz)
-        for (int tx = 0; tx < G.ntx; ++tx) {
-          const Tile t = tile_of(G, tx, tz);
-          const int cnt = t.cx * t.cz;
-          const size_t base = es * nelast * N2, nthr = (size_t)cnt * N;
-          for (int el = 0; el < cnt; ++el) {
-            const size_t e = (size_t)(t.ex0 + el % t.cx) + (size_t)G.nx * (t.ez0 + el / t.cx);
-            for (int pl = 0; pl < nelast; ++pl)
-              for (int j = 0; j < N; ++j)
-                for (int i = 0; i < N; ++i)
-                  a[(e * nelast + pl) * N2 + i + N * j] = pc[base + ((size_t)pl * N + i) * nthr + (size_t)el * N + j];
-          }
-          es += cnt;
-        }
-    }
+    for (int iz = 0; iz < G.nz; ++iz)
+      for (int ix = 0; ix < G.nx; ++ix) {
+        const size_t e = (size_t)ix + (size_t)G.nx * iz;
+        for (int pl = 0; pl < nelast; ++pl)
+          for (int j = 0; j < N; ++j)
+            for (int i = 0; i < N; ++i)
+              a[(e * nelast + pl) * N2 + i + N * j] = pc[strip_coef_index(G.S, nelast, ix, iz, i, j, pl)];
+      }
   }
   if (rmass) {
     const size_t nd = Eb->npoin * G.ndof;
-    if (Eb->prec == 8) {
-      as_engine<double>(Eb)->rmass.download(rmass);
-    } else {
-      std::vector<float> t = as_engine<float>(Eb)->rmass.to_host();
-      for (size_t q = 0; q < nd; ++q) rmass[q] = t[q];
-    }
+    DevBuf<double> tmp;
+    tmp.alloc(nd);
+    const unsigned nblk = (unsigned)((tot + 255) / 256);
+    if (Eb->prec == 8)
+      k_cart_permute<double, double><<<nblk, 256, 0, Eb->stream>>>(G, as_engine<double>(Eb)->rmass.p, tmp.p, Eb->npoin, G.ndof, 1);
+    else
+      k_cart_permute<float, double><<<nblk, 256, 0, Eb->stream>>>(G, as_engine<float>(Eb)->rmass.p, tmp.p, Eb->npoin, G.ndof, 1);
+    S2D_CUDA(cudaStreamSynchronize(Eb->stream));
+    tmp.download(rmass);
     if (!Eb->committed)
       for (size_t q = 0; q < nd; ++q) rmass[q] = 1.0 / rmass[q];
   }

@@ -504,11 +504,15 @@ __global__ void k_halo_sum(T* __restrict__ f, const T* __restrict__ fhalo, const
 }
 
 template <typename T, int N, int NDOF>
-inline void launch_elem_patch_n(const PatchArgs<T, N>& A, cudaStream_t s) {
-  if (A.npatch <= 0) return;
-  size_t smem = align16((size_t)A.EP * NDOF * N * N * sizeof(T)) + 2 * align16((size_t)NDOF * A.max_nloc * sizeof(T)) +
-                align16((size_t)N * N * sizeof(T));
-  if (A.use_bulk && A.hetero) smem += align16((size_t)A.EP * A.nelast * N * N * sizeof(T));
+inline void launch_elem_patch_n(const PatchArgs<T, N>& A0, cudaStream_t s) {
+  if (A0.npatch <= 0) return;
+  PatchArgs<T, N> A = A0;
+  const size_t base = align16((size_t)A.EP * NDOF * N * N * sizeof(T)) + 2 * align16((size_t)NDOF * A.max_nloc * sizeof(T)) +
+                      align16((size_t)N * N * sizeof(T));
+  const size_t blk = align16((size_t)A.EP * A.nelast * N * N * sizeof(T));
+  // the TMA-staged coefficient block is optional: drop it when it does not fit beside two resident CTAs
+  if (A.use_bulk && A.hetero && base + blk > 100 * 1024) A.use_bulk = 0;
+  const size_t smem = base + ((A.use_bulk && A.hetero) ? blk : 0);
   static size_t configured = 0;
   if (smem > configured) {
     S2D_CUDA(cudaFuncSetAttribute(k_elem_patch<T, N, NDOF>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "elem_kernels.cuh"
 #include "plan.hpp"
+#include "strip_kernels.cuh"
 
 namespace s2d {
 
@@ -144,8 +145,13 @@ class Engine : public EngineBase {
   bool p_hetero = false;
   int pf_dist = env_int("S2D_PF_DIST", 444);  // L2 software-prefetch distance of the patch kernel
   int use_bulk = env_int("S2D_BULK", 1);      // TMA bulk copy of the coefficient block into shared memory
-  bool cart_mode = false;  // structured builder: no host ibool, closed-form halo sum
-  std::function<void(T*)> cart_halo_sum;
+  // structured builder (cart.cu): fields live on the GLL lattice, forces come from the z-marching
+  // strip kernel; the hooks translate to / from the caller's node numbering at the API boundary
+  bool cart_mode = false;
+  StripGeom cart_S{};
+  DevBuf<T> cart_hx, cart_hz;
+  std::function<void(const T*, double*)> cart_to_ref;    // lattice (T) -> reference numbering (FP64), device to device
+  std::function<void(const double*, T*)> cart_from_ref;  // reference numbering (FP64) -> lattice (T)
 
   // bare engine for the structured builder (cart.cu fills the tables on the device)
   struct Raw {};
@@ -662,6 +668,10 @@ class Engine : public EngineBase {
 
   // f = -K d  (compute_Fint, solver.f90:273-320); f must be zero on entry unless the patch variant
   void launch_fint(const T* dd, const T* vv, T* ff) {
+    if (cart_mode) {
+      launches += launch_elem_strip<T>(cart_S, p_coef.p, dd, ff, cart_hx.p, cart_hz.p, npoin, h_H.data(), stream);
+      return;
+    }
     if (variant == S2D_ASM_PATCH) {
       launch_patch(dd, vv, ff);
       return;
@@ -731,15 +741,11 @@ class Engine : public EngineBase {
     if (ndof == 1) launch_elem_patch_n<T, N, 1>(A, stream);
     else launch_elem_patch_n<T, N, 2>(A, stream);
     launches++;
-    if (cart_mode) {
-      cart_halo_sum(ff);
-    } else {
-      const int ns = (int)plan.snode.size();
-      if (ns > 0) {
-        k_halo_sum<T><<<ceil_div(ns, 256), 256, 0, stream>>>(ff, fhalo.p, p_snode.p, p_sstart.p, ns, npoin,
-                                                             pp_nslots, ndof);
-        launches++;
-      }
+    const int ns = (int)plan.snode.size();
+    if (ns > 0) {
+      k_halo_sum<T><<<ceil_div(ns, 256), 256, 0, stream>>>(ff, fhalo.p, p_snode.p, p_sstart.p, ns, npoin,
+                                                           pp_nslots, ndof);
+      launches++;
     }
     S2D_CUDA(cudaGetLastError());
   }
@@ -890,6 +896,13 @@ class Engine : public EngineBase {
     if (!src) return;
     const size_t nd = npoin * ndof;
     S2D_CUDA(cudaStreamSynchronize(stream));
+    if (cart_mode) {
+      DevBuf<double> tmp;
+      tmp.upload(src, nd);
+      cart_from_ref(tmp.p, dst.p);
+      S2D_CUDA(cudaStreamSynchronize(stream));
+      return;
+    }
     if (sizeof(T) == 8) {
       S2D_CUDA(cudaMemcpy(dst.p, src, nd * 8, cudaMemcpyHostToDevice));
     } else {
@@ -902,6 +915,14 @@ class Engine : public EngineBase {
     if (!dst) return;
     const size_t nd = npoin * ndof;
     S2D_CUDA(cudaStreamSynchronize(stream));
+    if (cart_mode) {
+      DevBuf<double> tmp;
+      tmp.alloc(nd);
+      cart_to_ref(src.p, tmp.p);
+      S2D_CUDA(cudaStreamSynchronize(stream));
+      tmp.download(dst);
+      return;
+    }
     if (sizeof(T) == 8) {
       S2D_CUDA(cudaMemcpy(dst, src.p, nd * 8, cudaMemcpyDeviceToHost));
     } else {

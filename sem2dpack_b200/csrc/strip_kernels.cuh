@@ -1,0 +1,398 @@
+// Element-force + assembly kernel for structured (MESH_CART) grids: the z-marching strip kernel.
+//
+// Replaces, for the flat Cartesian box, compute_Fint's element loop (SRC/solver.f90:291-299), the
+// gather/scatter of SRC/fields.f90:173-189,113-129 and ELAST_KD1/KD2_{SH,PSV} with mxm/My_MATMUL
+// folded in (SRC/mat_elastic.f90:464-775, SRC/mxmlib.f90).  Same operator as elem_kernels.cuh:
+//   Uxi = Ht U, Ueta = U H,  f = H (tH) + (tHt) Ht      (H(i,j) = h'_i(x_j))
+//
+// Layout.  Fields live on the GLL LATTICE: node (gx,gz) at gz*LX + gx, LX = nx*(N-1)+1; the row of
+// split fault nodes is stored twice (lower side, then upper side).  The box is cut into vertical
+// strips EPW = floor(32/N) elements wide and horizontal bands of SEG element rows; one WARP owns one
+// (band, strip) item and marches through it upward, one element row per iteration:
+//   * lane (el,i) owns lattice column i of element el and keeps that column's N values of the
+//     current element row in registers, so eta-contractions (along z) are register-local with
+//     hprime as constant-bank operands, and xi-contractions go through a warp-private
+//     shared-memory tile read back as 128-bit rows (__syncwarp only, no CTA barrier anywhere);
+//   * the top node of a row is the bottom node of the next: its displacement and its partial
+//     force sum are carried in registers (vertical assembly costs one add, no memory);
+//   * columns shared by two elements of the strip are merged with one warp shuffle;
+//   * every lattice node is written exactly once; only the strip's right edge column and the band's
+//     top row leave partial sums in small halo arrays, folded in by k_strip_halo_sum in a fixed
+//     order (deterministic, no atomics).
+// Coefficient planes are stored per (band, strip, element row) as [plane pair][j][lane] 16-byte
+// vectors: every warp load is one contiguous run, the whole array is read exactly once per step.
+#pragma once
+#include "common.cuh"
+#include "elem_kernels.cuh"
+
+namespace s2d {
+
+struct StripGeom {
+  int N, ndof;
+  int nx, nz, ezflt;       // elements; split-node fault after element row ezflt (0 = none)
+  int EPW, W, WL;          // elements per strip, lattice columns per full strip, W+1
+  int nstrips, SEG, nseg_lo, nseg;
+  int LX, LZ;              // lattice extent (LZ counts the duplicated fault row)
+  long long nitems;
+};
+
+__host__ __device__ inline void strip_seg_rows(const StripGeom& G, int seg, int& ez0, int& ez1) {
+  if (seg < G.nseg_lo) {
+    ez0 = seg * G.SEG;
+    ez1 = min(ez0 + G.SEG, G.ezflt);
+  } else {
+    ez0 = G.ezflt + (seg - G.nseg_lo) * G.SEG;
+    ez1 = min(ez0 + G.SEG, G.nz);
+  }
+}
+__host__ __device__ inline int strip_seg_of(const StripGeom& G, int ez) {
+  if (G.ezflt > 0 && ez < G.ezflt) return ez / G.SEG;
+  return G.nseg_lo + (ez - G.ezflt) / G.SEG;
+}
+__host__ __device__ inline int strip_lat_row(const StripGeom& G, int ez, int j) {
+  return ez * (G.N - 1) + j + ((G.ezflt > 0 && ez >= G.ezflt) ? 1 : 0);
+}
+__host__ __device__ inline bool strip_row_detached(const StripGeom& G, int ez) {  // no element below shares nodes
+  return ez == 0 || (G.ezflt > 0 && ez == G.ezflt);
+}
+// first element (in units of elements) of the coefficient block of element row ez of (seg, strip)
+__host__ __device__ inline long long strip_elem_off(const StripGeom& G, int seg, int strip, int ez) {
+  int ez0, ez1;
+  strip_seg_rows(G, seg, ez0, ez1);
+  const int ex0 = strip * G.EPW;
+  const int cx = min(G.EPW, G.nx - ex0);
+  return (long long)ez0 * G.nx + (long long)ex0 * (ez1 - ez0) + (long long)(ez - ez0) * cx;
+}
+// position (in scalars) of a(i,j,plane) of element (ix,iz) inside the strip layout
+__host__ __device__ inline size_t strip_coef_index(const StripGeom& G, int nelast, int ix, int iz, int i, int j,
+                                                   int pl) {
+  const int N = G.N;
+  const int seg = strip_seg_of(G, iz), strip = ix / G.EPW;
+  const int ex0 = strip * G.EPW, el = ix - ex0;
+  const int cx = min(G.EPW, G.nx - ex0);
+  const size_t base = (size_t)strip_elem_off(G, seg, strip, iz) * nelast * N * N;
+  return base + 2 * ((size_t)((pl >> 1) * N + j) * (cx * N) + el * N + i) + (pl & 1);
+}
+
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+template <typename T, int N>
+struct StripArgs {
+  StripGeom G;
+  const T* coef;
+  const T* d;
+  T* f;
+  T* halo_x;   // [c][nstrips-1][LZ]      partial sums of the column shared with the strip to the right
+  T* halo_z;   // [c][nseg][nstrips][WL]  partial sums of the row shared with the band above
+  size_t npoin;
+  T H[N * N];  // hprime, column-major (constant bank)
+};
+
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
+
+constexpr int strip_warps() { return 4; }
+constexpr int strip_min_ctas(int N, int tsize) { return N <= 6 ? 3 : (tsize == 4 ? 2 : 1); }
+
+template <typename T, int N, int NDOF>
+__global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T)))
+    k_elem_strip(const __grid_constant__ StripArgs<T, N> A) {
+  constexpr int WARPS = strip_warps();
+  constexpr int NEL = NDOF == 1 ? 2 : 6;
+  constexpr int KD2 = (N == 5) ? 1 : 0;  // OPT_NGLL (constants.f90:6, mat_elastic.f90:412)
+  constexpr int EPW = 32 / N;
+  constexpr int NP = (N + 1) & ~1;       // tile rows padded to an even count: 16-byte vector reads
+  constexpr unsigned FULL = 0xffffffffu;
+  using V2 = typename Vec2<T>::type;
+  __shared__ __align__(16) T tile[WARPS][NDOF][N][EPW][NP];
+  const StripGeom& G = A.G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * WARPS + warp;
+  if (item >= G.nitems) return;  // whole warps leave; no CTA barrier is used below
+  const int seg = (int)(item / G.nstrips), strip = (int)(item - (long long)seg * G.nstrips);
+  int ez0, ez1;
+  strip_seg_rows(G, seg, ez0, ez1);
+  const int ex0 = strip * EPW;
+  const int cx = min(EPW, G.nx - ex0);
+  int el = lane / N;
+  const int i = lane - el * N;
+  const bool real = el < cx;
+  if (!real) el = cx - 1;  // shadow lanes mirror the last element (same cache lines), never store
+  const int lanep = el * N + i;
+  const bool dup = (i == N - 1) && (el < cx - 1);    // column owned by lane+1 (i = 0 of the next element)
+  const bool redge = (i == N - 1) && (el == cx - 1);  // strip's right edge
+  const bool merge = real && (i == 0) && (el > 0);
+  const bool to_halo = redge && (strip < G.nstrips - 1);
+  const bool st_ok = real && !dup;
+  const size_t LX = (size_t)G.LX;
+  const int gx = (ex0 + el) * (N - 1) + i;
+  const T* up = A.d + gx;
+  T* sp;
+  size_t rstride, cstride;
+  if (to_halo) {
+    sp = A.halo_x + (size_t)strip * G.LZ;
+    rstride = 1;
+    cstride = (size_t)(G.nstrips - 1) * G.LZ;
+  } else {
+    sp = A.f + gx;
+    rstride = LX;
+    cstride = A.npoin;
+  }
+  T(*tl)[N][EPW][NP] = tile[warp];
+  T Hi[N], HTi[N];
+#pragma unroll
+  for (int m = 0; m < N; ++m) {
+    Hi[m] = A.H[m + N * i];   // H(m,i)
+    HTi[m] = A.H[i + N * m];  // H(i,m)
+  }
+  T U[NDOF][N], Fc[NDOF];
+  {
+    const size_t r0 = (size_t)strip_lat_row(G, ez0, 0) * LX;
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c) {
+      U[c][0] = up[A.npoin * c + r0];
+      Fc[c] = 0;
+    }
+  }
+  const int cxN = cx * N;
+  const V2* cp = reinterpret_cast<const V2*>(A.coef) +
+                 (size_t)strip_elem_off(G, seg, strip, ez0) * (NEL * N * N / 2) + lanep;
+  const size_t cp_row = (size_t)cx * (NEL * N * N / 2);
+
+  for (int ez = ez0; ez < ez1; ++ez, cp += cp_row) {
+    const size_t grow = (size_t)strip_lat_row(G, ez, 0);
+    const size_t rowbase = grow * LX;
+    // ---- loads of this element row: displacement rows j = 1..N-1, coefficient planes
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+      for (int j = 1; j < N; ++j) U[c][j] = up[A.npoin * c + rowbase + (size_t)j * LX];
+    V2 a2[NEL / 2][N];
+#pragma unroll
+    for (int pp = 0; pp < NEL / 2; ++pp)
+#pragma unroll
+      for (int j = 0; j < N; ++j) a2[pp][j] = ld_stream(cp + (size_t)(pp * N + j) * cxN);
+    // ---- gradients: xi through the warp tile, eta in registers
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+      for (int j = 0; j < N; ++j) tl[c][j][el][i] = U[c][j];
+    __syncwarp();
+    T gxi[NDOF][N], get[NDOF][N];
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        T row[NP];
+        const V2* rp = reinterpret_cast<const V2*>(&tl[c][j][el][0]);
+#pragma unroll
+        for (int m = 0; m < NP / 2; ++m) {
+          const V2 t = rp[m];
+          row[2 * m] = t.x;
+          row[2 * m + 1] = t.y;
+        }
+        T s1 = 0, s2 = 0;
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+          s1 += Hi[m] * row[m];               // (Ht U)(i,j)
+          s2 += U[c][m] * A.H[m + N * j];     // (U H)(i,j)
+        }
+        gxi[c][j] = s1;
+        get[c][j] = s2;
+      }
+    __syncwarp();
+    // ---- pointwise stage (mat_elastic.f90:600-619 / :484-496 / :751-762)
+    T tH[NDOF][N], tHt[NDOF][N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      T ar[NEL], g1[NDOF], g2[NDOF], o1[NDOF], o2[NDOF];
+#pragma unroll
+      for (int pp = 0; pp < NEL / 2; ++pp) {
+        ar[2 * pp] = a2[pp][j].x;
+        ar[2 * pp + 1] = a2[pp][j].y;
+      }
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) {
+        g1[c] = gxi[c][j];
+        g2[c] = get[c][j];
+      }
+      pointwise_stage<T, NDOF>(ar, NEL, KD2, g1, g2, o1, o2);
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) {
+        tH[c][j] = o1[c];
+        tHt[c][j] = o2[c];
+      }
+    }
+    // ---- second contractions: H tH through the tile, tHt Ht in registers
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+      for (int j = 0; j < N; ++j) tl[c][j][el][i] = tH[c][j];
+    __syncwarp();
+    T f[NDOF][N];
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        T row[NP];
+        const V2* rp = reinterpret_cast<const V2*>(&tl[c][j][el][0]);
+#pragma unroll
+        for (int m = 0; m < NP / 2; ++m) {
+          const V2 t = rp[m];
+          row[2 * m] = t.x;
+          row[2 * m + 1] = t.y;
+        }
+        T s1 = 0, s2 = 0;
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+          s1 += HTi[m] * row[m];               // (H tH)(i,j)
+          s2 += tHt[c][m] * A.H[j + N * m];    // (tHt Ht)(i,j)
+        }
+        f[c][j] = s1 + s2;
+      }
+    __syncwarp();
+    // ---- assembly: merge the column shared with the element to the left, add the carried row
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const T t = __shfl_up_sync(FULL, f[c][j], 1);
+        if (merge) f[c][j] += t;
+      }
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c) {
+      f[c][0] += Fc[c];
+      Fc[c] = f[c][N - 1];
+      U[c][0] = U[c][N - 1];
+    }
+    if (st_ok) {
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+        for (int j = 0; j < N - 1; ++j) sp[cstride * c + (grow + j) * rstride] = f[c][j];
+    }
+  }
+  // ---- top row of the band: private when nothing above shares it, else a partial sum for the band above
+  if (st_ok) {
+    if (ez1 == G.nz || (G.ezflt > 0 && ez1 == G.ezflt)) {
+      const size_t gt = (size_t)strip_lat_row(G, ez1 - 1, N - 1);
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) sp[cstride * c + gt * rstride] = Fc[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c)
+        A.halo_z[((size_t)(c * G.nseg + seg) * G.nstrips + strip) * G.WL + el * (N - 1) + i] = Fc[c];
+    }
+  }
+}
+
+// Adds the partial sums left in the halo arrays.  One thread per halo node, fixed order of additions
+// ((f + left strip) + band below + band below of the left strip): deterministic.
+template <typename T>
+__global__ void k_strip_halo_sum(StripGeom G, T* __restrict__ f, const T* __restrict__ halo_x,
+                                 const T* __restrict__ halo_z, size_t npoin) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nA = (long long)(G.nstrips - 1) * G.LZ;
+  const int nsh_lo = G.nseg_lo > 0 ? G.nseg_lo - 1 : 0;
+  const int nsh = nsh_lo + (G.nseg - G.nseg_lo - 1);
+  const size_t hz_c = (size_t)G.nseg * G.nstrips * G.WL;
+  const size_t hx_c = (size_t)(G.nstrips - 1) * G.LZ;
+  if (w < nA) {  // strip-boundary columns, all rows
+    const int b = 1 + (int)(w / G.LZ), gz = (int)(w - (long long)(b - 1) * G.LZ);
+    const size_t node = (size_t)gz * G.LX + (size_t)b * G.W;
+    // is gz the bottom row of a band that shares it with the band below?
+    int seg_l = -1;
+    {
+      int g = gz, lower = 1;
+      if (G.ezflt > 0 && gz >= G.ezflt * (G.N - 1) + 1) {
+        g = gz - 1;
+        lower = 0;
+      }
+      if (g % (G.N - 1) == 0) {
+        const int ez = g / (G.N - 1);
+        if (G.ezflt > 0 && lower) {
+          if (ez > 0 && ez < G.ezflt && ez % G.SEG == 0) seg_l = ez / G.SEG - 1;
+        } else {
+          if (ez > G.ezflt && ez < G.nz && (ez - G.ezflt) % G.SEG == 0) seg_l = G.nseg_lo + (ez - G.ezflt) / G.SEG - 1;
+        }
+      }
+    }
+    for (int c = 0; c < G.ndof; ++c) {
+      T acc = f[node + npoin * c] + halo_x[hx_c * c + (size_t)(b - 1) * G.LZ + gz];
+      if (seg_l >= 0) {
+        acc += halo_z[hz_c * c + ((size_t)seg_l * G.nstrips + b) * G.WL];
+        acc += halo_z[hz_c * c + ((size_t)seg_l * G.nstrips + (b - 1)) * G.WL + G.W];
+      }
+      f[node + npoin * c] = acc;
+    }
+    return;
+  }
+  const long long w2 = w - nA;
+  if (w2 >= (long long)nsh * G.LX) return;
+  const int r = (int)(w2 / G.LX), gx = (int)(w2 - (long long)r * G.LX);
+  const int seg_u = r < nsh_lo ? r + 1 : G.nseg_lo + 1 + (r - nsh_lo);
+  int strip = gx / G.W, lc = gx - strip * G.W;
+  if (strip >= G.nstrips) {
+    strip = G.nstrips - 1;
+    lc = gx - strip * G.W;
+  } else if (lc == 0 && strip > 0) {
+    return;  // strip-boundary column: handled above
+  }
+  int ez0, ez1;
+  strip_seg_rows(G, seg_u, ez0, ez1);
+  const size_t node = (size_t)strip_lat_row(G, ez0, 0) * G.LX + gx;
+  for (int c = 0; c < G.ndof; ++c)
+    f[node + npoin * c] += halo_z[hz_c * c + ((size_t)(seg_u - 1) * G.nstrips + strip) * G.WL + lc];
+}
+
+template <typename T, int N, int NDOF>
+inline void launch_elem_strip_n(const StripArgs<T, N>& A, cudaStream_t s) {
+  const long long nblk = (A.G.nitems + strip_warps() - 1) / strip_warps();
+  k_elem_strip<T, N, NDOF><<<(unsigned)nblk, strip_warps() * 32, 0, s>>>(A);
+}
+
+// f = -K d on the lattice: strip kernel + halo fold (2 launches)
+template <typename T>
+inline int launch_elem_strip(const StripGeom& G, const T* coef, const T* d, T* f, T* halo_x, T* halo_z,
+                             size_t npoin, const double* hprime, cudaStream_t s) {
+#define S2D_STRIP_CASE(NN)                                             \
+  case NN: {                                                           \
+    StripArgs<T, NN> A{};                                              \
+    A.G = G;                                                           \
+    A.coef = coef;                                                     \
+    A.d = d;                                                           \
+    A.f = f;                                                           \
+    A.halo_x = halo_x;                                                 \
+    A.halo_z = halo_z;                                                 \
+    A.npoin = npoin;                                                   \
+    for (int k = 0; k < NN * NN; ++k) A.H[k] = (T)hprime[k];           \
+    if (G.ndof == 1) launch_elem_strip_n<T, NN, 1>(A, s);              \
+    else launch_elem_strip_n<T, NN, 2>(A, s);                          \
+  } break;
+  switch (G.N) {
+    S2D_STRIP_CASE(3)
+    S2D_STRIP_CASE(4)
+    S2D_STRIP_CASE(5)
+    S2D_STRIP_CASE(6)
+    S2D_STRIP_CASE(7)
+    S2D_STRIP_CASE(8)
+    S2D_STRIP_CASE(9)
+    S2D_STRIP_CASE(10)
+    default:
+      throw ArgError("ngll must be in 3..10");
+  }
+#undef S2D_STRIP_CASE
+  int n = 1;
+  const int nsh = (G.nseg_lo > 0 ? G.nseg_lo - 1 : 0) + (G.nseg - G.nseg_lo - 1);
+  const long long nh = (long long)(G.nstrips - 1) * G.LZ + (long long)nsh * G.LX;
+  if (nh > 0) {
+    k_strip_halo_sum<T><<<(unsigned)((nh + 255) / 256), 256, 0, s>>>(G, f, halo_x, halo_z, npoin);
+    n++;
+  }
+  S2D_CUDA(cudaGetLastError());
+  return n;
+}
+
+}  // namespace s2d
