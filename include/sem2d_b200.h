@@ -228,6 +228,10 @@ int s2d_cart_add_force(s2d_handle h, double x, double z, const double dir[2], in
 int s2d_cart_add_receivers(s2d_handle h, int32_t nx, double xa, double za, double xb, double zb,
                            char field, int32_t isamp, int32_t nt_rec);
 int s2d_cart_info(s2d_handle h, int64_t* npoin, int64_t* nelem, double* dt);
+/* Overrides the time step (time%dt) before any boundary is added.  x-strips of one global mesh
+ * must agree on dt: the host takes the minimum of the per-strip Courant steps (the reference takes
+ * the maximum of c/dx over the whole grid, init.f90:187-225) and sets it on every strip. */
+int s2d_cart_set_dt(s2d_handle h, double dt);
 /* copies of builder outputs for parity tests against the oracle (host pointers, may be NULL) */
 int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double* coord);
 

@@ -354,6 +354,7 @@ struct CartState {
   double courant, dt, grid_cfl;
   double H[100];
   bool mass_inverted = false;
+  bool bc_added = false;
   double CoefA2V() const { return scheme.kind == 1 ? scheme.gamma * scheme.dt : scheme.dt; }        // time.f90:443-456
   double CoefA2D() const { return scheme.kind == 1 ? scheme.beta * scheme.dt * scheme.dt : 0.0; }    // time.f90:426-440
   double CoefA2Vrhs() const { return scheme.kind == 1 ? scheme.alpha * CoefA2V() : 0.5 * CoefA2V(); }  // :465-486
@@ -510,6 +511,11 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
       Q.LX = G.nx * (G.N - 1) + 1;
       Q.LZ = G.nz * (G.N - 1) + 1 + (G.ezflt > 0 ? 1 : 0);
       Q.nitems = (long long)Q.nseg * Q.nstrips;
+      Q.it_strip0 = 0;
+      Q.it_nstr = Q.nstrips;
+      Q.it_step = 1;
+      Q.xhalo_left = G.halo_left ? 1 : 0;
+      Q.xhalo_right = G.halo_right ? 1 : 0;
     }
     const long long npoin = cart_npoin(G);
     const long long nelem = (long long)G.nx * G.nz;
@@ -565,11 +571,22 @@ int s2d_cart_info(s2d_handle h, int64_t* npoin, int64_t* nelem, double* dt) {
   CART_GUARD_END
 }
 
+int s2d_cart_set_dt(s2d_handle h, double dt) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(dt > 0.0, "cart_set_dt: dt must be positive");
+  S2D_REQUIRE(!Eb->committed && !S.bc_added, "cart_set_dt: must precede the first boundary condition");
+  S.scheme.dt = dt;
+  S.dt = dt;
+  Eb->scheme.dt = dt;
+  CART_GUARD_END
+}
+
 // BC_ABSO_init for one flat side of the box (bc_abso.f90:115-266)
 int s2d_cart_add_abso(s2d_handle h, int32_t side, int32_t stacey) {
   CART_GUARD_BEGIN
   S2D_REQUIRE(side >= 1 && side <= 4, "cart_add_abso: side tag must be 1..4");
   S2D_REQUIRE(!Eb->committed, "cart_add_abso after commit");
+  S.bc_added = true;
   const CartGeom& G = S.G;
   S2D_REQUIRE(!(side == 4 && G.halo_left) && !(side == 2 && G.halo_right),
               "cart_add_abso: that side is a strip interface, not a physical boundary");
@@ -645,6 +662,7 @@ int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, doub
   const CartGeom& G = S.G;
   S2D_REQUIRE(G.ezflt > 0, "cart_add_fault_swf: the mesh has no fault (ezflt = 0)");
   S2D_REQUIRE(!Eb->committed, "cart_add_fault_swf after commit");
+  S.bc_added = true;
   const int N = G.N, ndof = G.ndof;
   const int np = G.nx * (N - 1) + 1;
   std::vector<int> node1(np), node2(np);
@@ -823,8 +841,20 @@ int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double*
   CART_GUARD_END
 }
 
-int s2d_halo_info(s2d_handle, int64_t*, void**, void**) { return S2D_ESTATE; }
-int s2d_halo_set_exchange(s2d_handle, s2d_exchange_fn, void*) { return S2D_ESTATE; }
-int s2d_halo_set_peers(s2d_handle, void*, void*, void*, void*) { return S2D_ESTATE; }
+int s2d_halo_info(s2d_handle h, int64_t* count, void** send_dev, void** recv_dev) {
+  CART_GUARD_BEGIN
+  Eb->halo_info(count, send_dev, recv_dev);
+  CART_GUARD_END
+}
+int s2d_halo_set_exchange(s2d_handle h, s2d_exchange_fn fn, void* user) {
+  CART_GUARD_BEGIN
+  Eb->halo_set_exchange(fn, user);
+  CART_GUARD_END
+}
+int s2d_halo_set_peers(s2d_handle h, void*, void*, void*, void*) {
+  CART_GUARD_BEGIN
+  throw StateError("s2d_halo_set_peers: direct peer-memory exchange is not available in this build; use s2d_halo_set_exchange");
+  CART_GUARD_END
+}
 
 }  // extern "C"

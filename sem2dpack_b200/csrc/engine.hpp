@@ -93,6 +93,8 @@ class EngineBase {
   virtual void get_coloring(int32_t* ncolors, int32_t* color) = 0;
   virtual float time_fint(int reps) = 0;
   virtual float time_steps(int nsteps) = 0;
+  virtual void halo_info(int64_t* count, void** send_dev, void** recv_dev) = 0;
+  virtual void halo_set_exchange(s2d_exchange_fn fn, void* user) = 0;
 };
 
 template <typename T>
@@ -152,6 +154,67 @@ class Engine : public EngineBase {
   DevBuf<T> cart_hx, cart_hz;
   std::function<void(const T*, double*)> cart_to_ref;    // lattice (T) -> reference numbering (FP64), device to device
   std::function<void(const double*, T*)> cart_from_ref;  // reference numbering (FP64) -> lattice (T)
+  // x-strip interfaces with neighbour GPUs: partial sums of lattice column 0 / LX-1 are
+  // packed right after the two boundary strips are done, exchanged on a side stream while the
+  // interior strips are still computing, and added as (own + neighbour's) on both sides
+  DevBuf<T> xh_send[2], xh_recv[2];
+  s2d_exchange_fn xh_fn = nullptr;
+  void* xh_user = nullptr;
+  cudaStream_t xstream = nullptr;
+  cudaEvent_t xh_ev_b = nullptr, xh_ev_x = nullptr;
+  bool xhalo() const { return cart_mode && (cart_S.xhalo_left || cart_S.xhalo_right); }
+  void xhalo_setup() {
+    if (!xhalo() || xstream) return;
+    const size_t n = (size_t)cart_S.LZ * ndof;
+    for (int sd = 0; sd < 2; ++sd)
+      if (sd ? cart_S.xhalo_right : cart_S.xhalo_left) {
+        xh_send[sd].alloc(n);
+        xh_recv[sd].alloc(n);
+        xh_send[sd].zero();
+        xh_recv[sd].zero();
+      }
+    S2D_CUDA(cudaStreamCreateWithFlags(&xstream, cudaStreamNonBlocking));
+    S2D_CUDA(cudaEventCreateWithFlags(&xh_ev_b, cudaEventDisableTiming));
+    S2D_CUDA(cudaEventCreateWithFlags(&xh_ev_x, cudaEventDisableTiming));
+  }
+  void launch_fint_xhalo(const T* dd, T* ff) {
+    if (!xh_fn) throw StateError("this x-strip has neighbours: attach a halo exchange (s2d_halo_set_exchange) first");
+    const StripGeom& S0 = cart_S;
+    const int nb = (S0.xhalo_left ? 1 : 0) + ((S0.xhalo_right && (S0.nstrips > 1 || !S0.xhalo_left)) ? 1 : 0);
+    StripGeom B = S0, I = S0;
+    if (S0.xhalo_left) {
+      B.it_strip0 = 0;
+      B.it_step = S0.nstrips - 1;
+    } else {
+      B.it_strip0 = S0.nstrips - 1;
+      B.it_step = 0;
+    }
+    B.it_nstr = nb;
+    B.nitems = (long long)S0.nseg * nb;
+    I.it_strip0 = S0.xhalo_left ? 1 : 0;
+    I.it_nstr = S0.nstrips - nb;
+    I.it_step = 1;
+    I.nitems = (long long)S0.nseg * I.it_nstr;
+    launch_elem_strip_items<T>(B, p_coef.p, dd, ff, cart_hx.p, cart_hz.p, npoin, h_H.data(), stream);
+    S2D_CUDA(cudaEventRecord(xh_ev_b, stream));
+    launches++;
+    if (I.nitems > 0) {
+      launch_elem_strip_items<T>(I, p_coef.p, dd, ff, cart_hx.p, cart_hz.p, npoin, h_H.data(), stream);
+      launches++;
+    }
+    S2D_CUDA(cudaStreamWaitEvent(xstream, xh_ev_b, 0));
+    const int n2 = 2 * S0.LZ * ndof;
+    k_xhalo_pack<T><<<ceil_div(n2, 256), 256, 0, xstream>>>(S0, ff, cart_hz.p, npoin, xh_send[0].p, xh_send[1].p);
+    launches++;
+    const int rc = xh_fn(xh_user, (void*)xstream);
+    if (rc != 0) throw StateError("halo exchange hook failed with code " + std::to_string(rc));
+    S2D_CUDA(cudaEventRecord(xh_ev_x, xstream));
+    launches += launch_strip_fold<T>(S0, ff, cart_hx.p, cart_hz.p, npoin, stream);
+    S2D_CUDA(cudaStreamWaitEvent(stream, xh_ev_x, 0));
+    k_xhalo_unpack<T><<<ceil_div(n2, 256), 256, 0, stream>>>(S0, ff, cart_hz.p, npoin, xh_recv[0].p, xh_recv[1].p);
+    launches++;
+    S2D_CUDA(cudaGetLastError());
+  }
 
   // bare engine for the structured builder (cart.cu fills the tables on the device)
   struct Raw {};
@@ -212,6 +275,9 @@ class Engine : public EngineBase {
     partial.alloc(1024);
   }
   ~Engine() override {
+    if (xh_ev_b) cudaEventDestroy(xh_ev_b);
+    if (xh_ev_x) cudaEventDestroy(xh_ev_x);
+    if (xstream) cudaStreamDestroy(xstream);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -669,7 +735,8 @@ class Engine : public EngineBase {
   // f = -K d  (compute_Fint, solver.f90:273-320); f must be zero on entry unless the patch variant
   void launch_fint(const T* dd, const T* vv, T* ff) {
     if (cart_mode) {
-      launches += launch_elem_strip<T>(cart_S, p_coef.p, dd, ff, cart_hx.p, cart_hz.p, npoin, h_H.data(), stream);
+      if (xhalo()) launch_fint_xhalo(dd, ff);
+      else launches += launch_elem_strip<T>(cart_S, p_coef.p, dd, ff, cart_hx.p, cart_hz.p, npoin, h_H.data(), stream);
       return;
     }
     if (variant == S2D_ASM_PATCH) {
@@ -1017,6 +1084,22 @@ class Engine : public EngineBase {
     S2D_REQUIRE(!cart_mode, "get_coloring: not available for builder-made meshes");
     if (nc) *nc = ncolors;
     if (color) std::copy(h_color.begin(), h_color.end(), color);
+  }
+
+  void halo_info(int64_t* count, void** send_dev, void** recv_dev) override {
+    S2D_REQUIRE(cart_mode, "halo_info: only x-strips made by the structured builder have halos");
+    xhalo_setup();
+    if (count) *count = (int64_t)cart_S.LZ * ndof;
+    for (int sd = 0; sd < 2; ++sd) {
+      if (send_dev) send_dev[sd] = xh_send[sd].p;
+      if (recv_dev) recv_dev[sd] = xh_recv[sd].p;
+    }
+  }
+  void halo_set_exchange(s2d_exchange_fn fn, void* user) override {
+    S2D_REQUIRE(cart_mode, "halo_set_exchange: only x-strips made by the structured builder have halos");
+    xhalo_setup();
+    xh_fn = fn;
+    xh_user = user;
   }
 
   float time_fint(int reps) override {

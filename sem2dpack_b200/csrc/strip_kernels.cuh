@@ -34,7 +34,28 @@ struct StripGeom {
   int nstrips, SEG, nseg_lo, nseg;
   int LX, LZ;              // lattice extent (LZ counts the duplicated fault row)
   long long nitems;
+  // subset of strips handled by one launch: strip = it_strip0 + (k % it_nstr) * it_step, band = k / it_nstr
+  int it_strip0, it_nstr, it_step;
+  // x-strip interfaces with neighbour GPUs: the halo fold leaves lattice column 0 / LX-1 to the exchange
+  int xhalo_left, xhalo_right;
 };
+
+// band below the shared row gz, or -1 when gz is not the bottom row of a band that shares it
+__host__ __device__ inline int strip_shared_row_seg(const StripGeom& G, int gz) {
+  int g = gz, lower = 1;
+  if (G.ezflt > 0 && gz >= G.ezflt * (G.N - 1) + 1) {
+    g = gz - 1;
+    lower = 0;
+  }
+  if (g % (G.N - 1) != 0) return -1;
+  const int ez = g / (G.N - 1);
+  if (G.ezflt > 0 && lower) {
+    if (ez > 0 && ez < G.ezflt && ez % G.SEG == 0) return ez / G.SEG - 1;
+  } else {
+    if (ez > G.ezflt && ez < G.nz && (ez - G.ezflt) % G.SEG == 0) return G.nseg_lo + (ez - G.ezflt) / G.SEG - 1;
+  }
+  return -1;
+}
 
 __host__ __device__ inline void strip_seg_rows(const StripGeom& G, int seg, int& ez0, int& ez1) {
   if (seg < G.nseg_lo) {
@@ -111,7 +132,8 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * WARPS + warp;
   if (item >= G.nitems) return;  // whole warps leave; no CTA barrier is used below
-  const int seg = (int)(item / G.nstrips), strip = (int)(item - (long long)seg * G.nstrips);
+  const int seg = (int)(item / G.it_nstr);
+  const int strip = G.it_strip0 + (int)(item - (long long)seg * G.it_nstr) * G.it_step;
   int ez0, ez1;
   strip_seg_rows(G, seg, ez0, ez1);
   const int ex0 = strip * EPW;
@@ -302,23 +324,7 @@ __global__ void k_strip_halo_sum(StripGeom G, T* __restrict__ f, const T* __rest
   if (w < nA) {  // strip-boundary columns, all rows
     const int b = 1 + (int)(w / G.LZ), gz = (int)(w - (long long)(b - 1) * G.LZ);
     const size_t node = (size_t)gz * G.LX + (size_t)b * G.W;
-    // is gz the bottom row of a band that shares it with the band below?
-    int seg_l = -1;
-    {
-      int g = gz, lower = 1;
-      if (G.ezflt > 0 && gz >= G.ezflt * (G.N - 1) + 1) {
-        g = gz - 1;
-        lower = 0;
-      }
-      if (g % (G.N - 1) == 0) {
-        const int ez = g / (G.N - 1);
-        if (G.ezflt > 0 && lower) {
-          if (ez > 0 && ez < G.ezflt && ez % G.SEG == 0) seg_l = ez / G.SEG - 1;
-        } else {
-          if (ez > G.ezflt && ez < G.nz && (ez - G.ezflt) % G.SEG == 0) seg_l = G.nseg_lo + (ez - G.ezflt) / G.SEG - 1;
-        }
-      }
-    }
+    const int seg_l = strip_shared_row_seg(G, gz);
     for (int c = 0; c < G.ndof; ++c) {
       T acc = f[node + npoin * c] + halo_x[hx_c * c + (size_t)(b - 1) * G.LZ + gz];
       if (seg_l >= 0) {
@@ -340,11 +346,54 @@ __global__ void k_strip_halo_sum(StripGeom G, T* __restrict__ f, const T* __rest
   } else if (lc == 0 && strip > 0) {
     return;  // strip-boundary column: handled above
   }
+  if ((gx == 0 && G.xhalo_left) || (gx == G.LX - 1 && G.xhalo_right)) return;  // folded by k_xhalo_unpack
   int ez0, ez1;
   strip_seg_rows(G, seg_u, ez0, ez1);
   const size_t node = (size_t)strip_lat_row(G, ez0, 0) * G.LX + gx;
   for (int c = 0; c < G.ndof; ++c)
     f[node + npoin * c] += halo_z[hz_c * c + ((size_t)(seg_u - 1) * G.nstrips + strip) * G.WL + lc];
+}
+
+// x-strip interface columns (multi-GPU): this GPU's complete partial sum of lattice column 0 / LX-1,
+// i.e. the stored force plus the band-top partial of the same strip.  buf[c][gz].
+template <typename T>
+__device__ __forceinline__ T xhalo_own(const StripGeom& G, const T* f, const T* halo_z, size_t npoin, int side,
+                                       int c, int gz) {
+  const int strip = side ? G.nstrips - 1 : 0;
+  const int gx = side ? G.LX - 1 : 0;
+  T acc = f[(size_t)gz * G.LX + gx + npoin * c];
+  const int seg_l = strip_shared_row_seg(G, gz);
+  if (seg_l >= 0) {
+    const size_t hz_c = (size_t)G.nseg * G.nstrips * G.WL;
+    const int lc = side ? (G.LX - 1 - strip * G.W) : 0;
+    acc += halo_z[hz_c * c + ((size_t)seg_l * G.nstrips + strip) * G.WL + lc];
+  }
+  return acc;
+}
+template <typename T>
+__global__ void k_xhalo_pack(StripGeom G, const T* __restrict__ f, const T* __restrict__ halo_z, size_t npoin,
+                             T* __restrict__ send_l, T* __restrict__ send_r) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = G.LZ * G.ndof;
+  if (w >= 2 * n) return;
+  const int side = w / n, q = w - side * n;
+  T* dst = side ? send_r : send_l;
+  if (!dst) return;
+  dst[q] = xhalo_own(G, f, halo_z, npoin, side, q / G.LZ, q % G.LZ);
+}
+// f = own + neighbour's; a + b == b + a bit for bit, so both GPUs hold the same value afterwards
+template <typename T>
+__global__ void k_xhalo_unpack(StripGeom G, T* __restrict__ f, const T* __restrict__ halo_z, size_t npoin,
+                               const T* __restrict__ recv_l, const T* __restrict__ recv_r) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = G.LZ * G.ndof;
+  if (w >= 2 * n) return;
+  const int side = w / n, q = w - side * n;
+  const T* src = side ? recv_r : recv_l;
+  if (!src) return;
+  const int c = q / G.LZ, gz = q % G.LZ;
+  const int gx = side ? G.LX - 1 : 0;
+  f[(size_t)gz * G.LX + gx + npoin * c] = xhalo_own(G, f, halo_z, npoin, side, c, gz) + src[q];
 }
 
 template <typename T, int N, int NDOF>
@@ -353,9 +402,9 @@ inline void launch_elem_strip_n(const StripArgs<T, N>& A, cudaStream_t s) {
   k_elem_strip<T, N, NDOF><<<(unsigned)nblk, strip_warps() * 32, 0, s>>>(A);
 }
 
-// f = -K d on the lattice: strip kernel + halo fold (2 launches)
+// element-force launch over the strips selected by G.it_* (no halo fold)
 template <typename T>
-inline int launch_elem_strip(const StripGeom& G, const T* coef, const T* d, T* f, T* halo_x, T* halo_z,
+inline void launch_elem_strip_items(const StripGeom& G, const T* coef, const T* d, T* f, T* halo_x, T* halo_z,
                              size_t npoin, const double* hprime, cudaStream_t s) {
 #define S2D_STRIP_CASE(NN)                                             \
   case NN: {                                                           \
@@ -384,7 +433,11 @@ inline int launch_elem_strip(const StripGeom& G, const T* coef, const T* d, T* f
       throw ArgError("ngll must be in 3..10");
   }
 #undef S2D_STRIP_CASE
-  int n = 1;
+}
+template <typename T>
+inline int launch_strip_fold(const StripGeom& G, T* f, const T* halo_x, const T* halo_z, size_t npoin,
+                             cudaStream_t s) {
+  int n = 0;
   const int nsh = (G.nseg_lo > 0 ? G.nseg_lo - 1 : 0) + (G.nseg - G.nseg_lo - 1);
   const long long nh = (long long)(G.nstrips - 1) * G.LZ + (long long)nsh * G.LX;
   if (nh > 0) {
@@ -393,6 +446,18 @@ inline int launch_elem_strip(const StripGeom& G, const T* coef, const T* d, T* f
   }
   S2D_CUDA(cudaGetLastError());
   return n;
+}
+// f = -K d on the lattice: strip kernel over every strip + halo fold (2 launches)
+template <typename T>
+inline int launch_elem_strip(const StripGeom& G0, const T* coef, const T* d, T* f, T* halo_x, T* halo_z,
+                             size_t npoin, const double* hprime, cudaStream_t s) {
+  StripGeom G = G0;
+  G.it_strip0 = 0;
+  G.it_nstr = G.nstrips;
+  G.it_step = 1;
+  G.nitems = (long long)G.nseg * G.nstrips;
+  launch_elem_strip_items<T>(G, coef, d, f, halo_x, halo_z, npoin, hprime, s);
+  return 1 + launch_strip_fold<T>(G, f, halo_x, halo_z, npoin, s);
 }
 
 }  // namespace s2d

@@ -231,6 +231,11 @@ class CartEngine(Engine):
         self.npoin, self.nelem, self.dt = npoin.value, nelem.value, dtv.value
         self.nx, self.nz = nx, nz
 
+    def set_dt(self, dt):
+        """time%dt shared by every x-strip of one global mesh (min over strips of the Courant step)."""
+        self._ck(self.L.s2d_cart_set_dt(self.h, float(dt)))
+        self.dt = float(dt)
+
     def add_abso_side(self, side, stacey=False):
         self._ck(self.L.s2d_cart_add_abso(self.h, side, int(stacey)))
 
