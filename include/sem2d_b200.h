@@ -188,6 +188,9 @@ int s2d_get_coloring(s2d_handle h, int32_t* ncolors, int32_t* color);
 int s2d_time_fint(s2d_handle h, int32_t reps, float* ms_avg);
 /* Times nsteps full steps on the engine stream with CUDA events (no host traffic inside). */
 int s2d_time_steps(s2d_handle h, int32_t nsteps, float* ms_total);
+/* Average duration (ms per launch, CUDA events on the engine's stream) of the dominant kernel --
+ * the strip kernel of a builder-made engine -- over the launches of the last s2d_time_steps call. */
+int s2d_kernel_ms(s2d_handle h, float* ms);
 /* number of kernels the engine has launched so far */
 int s2d_launch_count(s2d_handle h, int64_t* n);
 /* raw CUDA stream (cudaStream_t) the engine launches on, for external event timing */

@@ -6,6 +6,6 @@ NX=${NX:-2048}; NZ=${NZ:-2048}; TAG=${TAG:-r1}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --nx $NX --nz $NZ --steps 3 --warmup 3 --no-cpu --fint-reps 2 > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_elem_patch -s 4 -c 2 -f -o gpurun_out/prof_${TAG} \
+ncu --set full --clock-control none --import-source on -k regex:k_elem_strip -s 4 -c 2 -f -o gpurun_out/prof_${TAG} \
     python bench.py --nx $NX --nz $NZ --steps 3 --warmup 3 --no-cpu --fint-reps 2 > gpurun_out/bench_under_ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out

@@ -27,6 +27,13 @@ __global__ void k_predict_leapfrog(T* __restrict__ d, const T* __restrict__ v, T
     if (zero_f) f[q] = 0;     // solver.f90:286
   }
 }
+// out-of-place leapfrog predictor of the fused step: dst = src + dt*v
+template <typename T>
+__global__ void k_predict_to(T* __restrict__ dst, const T* __restrict__ src, const T* __restrict__ v, size_t n,
+                             T dt) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) dst[q] = src[q] + dt * v[q];
+}
 template <typename T>
 __global__ void k_predict_newmark(T* __restrict__ d, T* __restrict__ v, T* __restrict__ a, size_t n,
                                   T dt, T c1, T c2, int zero_f) {
@@ -459,15 +466,22 @@ __global__ void k_dynflt(FaultDev F, T* MxA, const T* __restrict__ Vf, const T* 
   }
 }
 
-// BC_DYNFLT_write: one CTA.  Potency sums are ordered tree reductions (deterministic).
+// BC_DYNFLT_write.  Every CTA reduces its slice of the fault in a fixed tree order and copies its
+// share of the output records; the CTA that finishes last (ticket) adds the per-CTA partial sums
+// in ascending CTA order, writes the potency line and advances the output state: deterministic.
+constexpr int DYNW_THREADS = 256;
+constexpr int DYNW_MAX_CTAS = 128;
 template <typename T>
-__global__ void __launch_bounds__(256) k_dynflt_write(FaultDev F, const T* __restrict__ d,
-                                                      const T* __restrict__ v, size_t npoin,
-                                                      const StepCtl* ctl) {
-  __shared__ double red[6][256];
+__global__ void __launch_bounds__(DYNW_THREADS) k_dynflt_write(FaultDev F, const T* __restrict__ d,
+                                                               const T* __restrict__ v, size_t npoin,
+                                                               const StepCtl* ctl, double* __restrict__ part,
+                                                               unsigned* __restrict__ ticket) {
+  __shared__ double red[6][DYNW_THREADS];
+  __shared__ bool last;
   const int t = threadIdx.x, np = F.np, ndof = F.ndof;
+  const int stride = gridDim.x * DYNW_THREADS;
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  for (int k = t; k < np; k += 256) {
+  for (int k = blockIdx.x * DYNW_THREADS + t; k < np; k += stride) {
     const double nx = F.n1[k], nz = F.n1[k + np], B = F.B[k];
     for (int w = 0; w < 2; ++w) {
       const T* fld = w ? v : d;
@@ -493,28 +507,16 @@ __global__ void __launch_bounds__(256) k_dynflt_write(FaultDev F, const T* __res
   }
   for (int q = 0; q < 6; ++q) red[q][t] = acc[q];
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
+  for (int s = DYNW_THREADS / 2; s > 0; s >>= 1) {
     if (t < s)
       for (int q = 0; q < 6; ++q) red[q][t] += red[q][t + s];
     __syncthreads();
   }
-  const int ncall = F.ostate[2];
-  const int npot = 2 * (ndof + 1);
-  if (t == 0 && ncall < F.ncall_max) {
-    double* p = F.potency + (size_t)ncall * npot;
-    if (ndof == 2) {
-      p[0] = red[0][0]; p[1] = red[1][0]; p[2] = 0.5 * red[2][0];
-      p[3] = red[3][0]; p[4] = red[4][0]; p[5] = 0.5 * red[5][0];
-    } else {
-      p[0] = 0.5 * red[0][0]; p[1] = 0.5 * red[1][0];
-      p[2] = 0.5 * red[2][0]; p[3] = 0.5 * red[3][0];
-    }
-  }
-  const int oit = F.ostate[0], nout = F.ostate[1];
+  const int oit = F.ostate[0], nout = F.ostate[1], ncall = F.ostate[2];
   const bool out = (ctl->it >= oit) && nout < F.nrec_max;
   if (out) {
     float* r = F.records + (size_t)nout * 6 * F.onx;
-    for (int m = t; m < F.onx; m += 256) {
+    for (int m = blockIdx.x * DYNW_THREADS + t; m < F.onx; m += stride) {
       const int k = F.oix1 - 1 + m * F.oixd;
       r[m] = (float)F.D[k];
       r[F.onx + m] = (float)F.V[k];
@@ -524,13 +526,34 @@ __global__ void __launch_bounds__(256) k_dynflt_write(FaultDev F, const T* __res
       r[5 * F.onx + m] = (float)F.Tstick[k];
     }
   }
+  if (t < 6) part[blockIdx.x * 6 + t] = red[t][0];
+  __threadfence();
   __syncthreads();
+  if (t == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
   if (t == 0) {
+    double tot[6] = {0, 0, 0, 0, 0, 0};
+    for (unsigned b = 0; b < gridDim.x; ++b)
+      for (int q = 0; q < 6; ++q) tot[q] += __ldcg(&part[b * 6 + q]);
+    const int npot = 2 * (ndof + 1);
+    if (ncall < F.ncall_max) {
+      double* p = F.potency + (size_t)ncall * npot;
+      if (ndof == 2) {
+        p[0] = tot[0]; p[1] = tot[1]; p[2] = 0.5 * tot[2];
+        p[3] = tot[3]; p[4] = tot[4]; p[5] = 0.5 * tot[5];
+      } else {
+        p[0] = 0.5 * tot[0]; p[1] = 0.5 * tot[1];
+        p[2] = 0.5 * tot[2]; p[3] = 0.5 * tot[3];
+      }
+    }
     F.ostate[2] = ncall + 1;
     if (ctl->it >= oit) {
       F.ostate[0] = oit + F.oitd;
       F.ostate[1] = nout + (out ? 1 : 0);
     }
+    *ticket = 0;
   }
 }
 

@@ -390,10 +390,22 @@ static void cart_build(Engine<T>& E, CartState& S) {
   S2D_CUDA(cudaGetLastError());
   // halo arrays of the strip kernel
   E.cart_S = G.S;
-  E.cart_hx.alloc((size_t)G.ndof * std::max(G.S.nstrips - 1, 0) * G.S.LZ + 1);
+  E.cart_hx.alloc((size_t)G.ndof * std::max(G.S.ngroups - 1, 0) * G.S.LZ + 1);
   E.cart_hz.alloc((size_t)G.ndof * G.S.nseg * G.S.nstrips * G.S.WL + 1);
   E.cart_hx.zero(st);
   E.cart_hz.zero(st);
+  // deferred nodes of the fused step that come from the decomposition itself: rows shared by two
+  // bands, columns shared by two groups, GPU interface columns
+  E.h_rowflag.assign(G.S.LZ, 0);
+  E.h_colflag.assign(G.S.LX, 0);
+  for (int gz = 0; gz < G.S.LZ; ++gz)
+    if (strip_shared_row_seg(G.S, gz) >= 0) E.h_rowflag[gz] = 1;
+  for (int hb = 0; hb + 1 < G.S.ngroups; ++hb) {
+    int sr;
+    E.h_colflag[strip_halo_col(G.S, hb, sr)] = 1;
+  }
+  if (G.halo_left) E.h_colflag[0] = 1;
+  if (G.halo_right) E.h_colflag[G.S.LX - 1] = 1;
   const CartGeom Gc = G;
   Engine<T>* Ep = &E;
   E.cart_to_ref = [Ep, Gc, nblk](const T* lat, double* ref) {
@@ -510,12 +522,14 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
       Q.nseg = Q.nseg_lo + (G.nz - G.ezflt + Q.SEG - 1) / Q.SEG;
       Q.LX = G.nx * (G.N - 1) + 1;
       Q.LZ = G.nz * (G.N - 1) + 1 + (G.ezflt > 0 ? 1 : 0);
-      Q.nitems = (long long)Q.nseg * Q.nstrips;
-      Q.it_strip0 = 0;
-      Q.it_nstr = Q.nstrips;
-      Q.it_step = 1;
       Q.xhalo_left = G.halo_left ? 1 : 0;
       Q.xhalo_right = G.halo_right ? 1 : 0;
+      // one CTA = a group of adjacent strips; the strips next to a GPU interface form groups of their own
+      strip_set_groups(Q, strip_warps(), G.halo_left != 0, G.halo_right != 0);
+      Q.it_g0 = 0;
+      Q.it_ng = Q.ngroups;
+      Q.it_step = 1;
+      Q.nitems = (long long)Q.nseg * Q.ngroups;
     }
     const long long npoin = cart_npoin(G);
     const long long nelem = (long long)G.nx * G.nz;
@@ -841,6 +855,12 @@ int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double*
   CART_GUARD_END
 }
 
+int s2d_kernel_ms(s2d_handle h, float* ms) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(ms != nullptr, "s2d_kernel_ms: null pointer");
+  *ms = Eb->kernel_ms();
+  CART_GUARD_END
+}
 int s2d_halo_info(s2d_handle h, int64_t* count, void** send_dev, void** recv_dev) {
   CART_GUARD_BEGIN
   Eb->halo_info(count, send_dev, recv_dev);

@@ -38,7 +38,9 @@ struct FaultBc {
   DevBuf<double> swf_dc, swf_mus, swf_mud, swf_p, swf_alpha, swf_theta;
   DevBuf<double> rsf_dc, rsf_mus, rsf_a, rsf_b, rsf_Vstar, rsf_Vc, rsf_Tc, rsf_coeft, rsf_theta;
   DevBuf<float> records;
-  DevBuf<double> potency;
+  DevBuf<double> potency, wpart;
+  DevBuf<unsigned> wticket;
+  int wctas = 1;
 };
 struct BcRef {
   int kind;
@@ -93,6 +95,8 @@ class EngineBase {
   virtual void get_coloring(int32_t* ncolors, int32_t* color) = 0;
   virtual float time_fint(int reps) = 0;
   virtual float time_steps(int nsteps) = 0;
+  float last_kernel_ms_base = 0.f;
+  virtual float kernel_ms() = 0;
   virtual void halo_info(int64_t* count, void** send_dev, void** recv_dev) = 0;
   virtual void halo_set_exchange(s2d_exchange_fn fn, void* user) = 0;
 };
@@ -154,6 +158,36 @@ class Engine : public EngineBase {
   DevBuf<T> cart_hx, cart_hz;
   std::function<void(const T*, double*)> cart_to_ref;    // lattice (T) -> reference numbering (FP64), device to device
   std::function<void(const double*, T*)> cart_from_ref;  // reference numbering (FP64) -> lattice (T)
+  // fused leapfrog step of the strip kernel: two displacement buffers (the kernel reads d[n] and
+  // writes the predicted d[n+1] of the next step), deferred-node tables (strip_kernels.cuh)
+  DevBuf<T> d2;
+  int dsel = 0;             // which buffer holds the displacement the caller sees
+  bool pred_valid = false;  // the other buffer holds d + dt*v of the next step
+  bool fused = false;
+  bool store_accel = env_int("S2D_STORE_ACCEL", 1) != 0;
+  int strip_prefetch = env_int("S2D_STRIP_PF", 1);
+  std::vector<uint8_t> h_rowflag, h_colflag;
+  std::vector<std::vector<int32_t>> h_bc_nodes;  // node lists of every boundary condition (for the flags)
+  DevBuf<uint8_t> rowflag, colflag;
+  DevBuf<int> drows, dcols;
+  int ndrows = 0, ndcols = 0;
+  T* dn() { return dsel ? d2.p : d.p; }
+  T* dalt() { return dsel ? d.p : d2.p; }
+  DevBuf<T>& dbuf() { return dsel ? d2 : d; }
+  // per-launch timing of the dominant kernel inside s2d_time_steps
+  std::vector<cudaEvent_t> kev;
+  bool kev_on = false;
+  size_t kev_n = 0;
+  float last_kernel_ms = 0.f;
+  void kev_mark() {
+    if (!kev_on) return;
+    if (kev_n >= kev.size()) {
+      cudaEvent_t e;
+      S2D_CUDA(cudaEventCreate(&e));
+      kev.push_back(e);
+    }
+    S2D_CUDA(cudaEventRecord(kev[kev_n++], stream));
+  }
   // x-strip interfaces with neighbour GPUs: partial sums of lattice column 0 / LX-1 are
   // packed right after the two boundary strips are done, exchanged on a side stream while the
   // interior strips are still computing, and added as (own + neighbour's) on both sides
@@ -177,29 +211,49 @@ class Engine : public EngineBase {
     S2D_CUDA(cudaEventCreateWithFlags(&xh_ev_b, cudaEventDisableTiming));
     S2D_CUDA(cudaEventCreateWithFlags(&xh_ev_x, cudaEventDisableTiming));
   }
-  void launch_fint_xhalo(const T* dd, T* ff) {
-    if (!xh_fn) throw StateError("this x-strip has neighbours: attach a halo exchange (s2d_halo_set_exchange) first");
+  StripIO<T> strip_io(const T* dd, T* ff) {
+    StripIO<T> io;
+    io.coef = p_coef.p;
+    io.d = dd;
+    io.f = ff;
+    io.halo_x = cart_hx.p;
+    io.halo_z = cart_hz.p;
+    io.npoin = npoin;
+    io.hprime = h_H.data();
+    io.prefetch = strip_prefetch;
+    return io;
+  }
+  // strip kernel over the whole box (+ halo fold, + interface exchange); io.v_in != null = fused update
+  void launch_strips(const StripIO<T>& io) {
     const StripGeom& S0 = cart_S;
-    const int nb = (S0.xhalo_left ? 1 : 0) + ((S0.xhalo_right && (S0.nstrips > 1 || !S0.xhalo_left)) ? 1 : 0);
-    StripGeom B = S0, I = S0;
-    if (S0.xhalo_left) {
-      B.it_strip0 = 0;
-      B.it_step = S0.nstrips - 1;
-    } else {
-      B.it_strip0 = S0.nstrips - 1;
-      B.it_step = 0;
+    if (!xhalo()) {
+      kev_mark();
+      launch_elem_strip_items<T>(strip_all_groups(S0), io, stream);
+      kev_mark();
+      launches += 1 + launch_strip_fold<T>(S0, io.f, cart_hx.p, cart_hz.p, npoin, stream);
+      return;
     }
-    B.it_nstr = nb;
+    if (!xh_fn) throw StateError("this x-strip has neighbours: attach a halo exchange (s2d_halo_set_exchange) first");
+    // boundary groups = the single-strip groups next to the interfaces
+    const int nb = S0.g_lead + S0.g_tail + ((S0.nstrips == 1) ? 1 : 0);
+    StripGeom B = S0, I = S0;
+    B.it_g0 = S0.g_lead ? 0 : S0.ngroups - 1;
+    B.it_step = S0.ngroups - 1;
+    B.it_ng = nb;
+    if (nb == 1) B.it_step = 0;
     B.nitems = (long long)S0.nseg * nb;
-    I.it_strip0 = S0.xhalo_left ? 1 : 0;
-    I.it_nstr = S0.nstrips - nb;
+    I.it_g0 = S0.g_lead;
+    I.it_ng = S0.ngroups - nb;
     I.it_step = 1;
-    I.nitems = (long long)S0.nseg * I.it_nstr;
-    launch_elem_strip_items<T>(B, p_coef.p, dd, ff, cart_hx.p, cart_hz.p, npoin, h_H.data(), stream);
+    I.nitems = (long long)S0.nseg * I.it_ng;
+    T* ff = io.f;
+    launch_elem_strip_items<T>(B, io, stream);
     S2D_CUDA(cudaEventRecord(xh_ev_b, stream));
     launches++;
     if (I.nitems > 0) {
-      launch_elem_strip_items<T>(I, p_coef.p, dd, ff, cart_hx.p, cart_hz.p, npoin, h_H.data(), stream);
+      kev_mark();
+      launch_elem_strip_items<T>(I, io, stream);
+      kev_mark();
       launches++;
     }
     S2D_CUDA(cudaStreamWaitEvent(xstream, xh_ev_b, 0));
@@ -275,6 +329,7 @@ class Engine : public EngineBase {
     partial.alloc(1024);
   }
   ~Engine() override {
+    for (auto e : kev) cudaEventDestroy(e);
     if (xh_ev_b) cudaEventDestroy(xh_ev_b);
     if (xh_ev_x) cudaEventDestroy(xh_ev_x);
     if (xstream) cudaStreamDestroy(xstream);
@@ -326,6 +381,7 @@ class Engine : public EngineBase {
     S2D_REQUIRE(np > 0 && node && C, "add_abso: empty boundary");
     check_nodes(np, node, "add_abso");
     auto b = std::make_unique<AbsoBc>();
+    h_bc_nodes.emplace_back(node, node + np);
     b->node.upload(node, np);
     b->C.upload(C, (size_t)np * ndof);
     if (!is_flat && ndof == 2) {
@@ -385,6 +441,7 @@ class Engine : public EngineBase {
     S2D_REQUIRE(np > 0 && node, "add_dirneu: empty boundary");
     check_nodes(np, node, "add_dirneu");
     auto b = std::make_unique<DirneuBc>();
+    h_bc_nodes.emplace_back(node, node + np);
     b->np = np;
     b->kind_h = kind_h;
     b->kind_v = kind_v;
@@ -423,6 +480,8 @@ class Engine : public EngineBase {
     };
     b->node1.upload(D.node1, np);
     F.node1 = b->node1.p;
+    h_bc_nodes.emplace_back(D.node1, D.node1 + np);
+    if (D.node2) h_bc_nodes.emplace_back(D.node2, D.node2 + np);
     if (D.node2) {
       b->node2.upload(D.node2, np);
       F.node2 = b->node2.p;
@@ -564,6 +623,11 @@ class Engine : public EngineBase {
     b->records.zero();
     b->potency.alloc((size_t)F.ncall_max * 2 * (ndof + 1));
     b->potency.zero();
+    b->wctas = std::max(1, std::min(DYNW_MAX_CTAS, (np + 4 * DYNW_THREADS - 1) / (4 * DYNW_THREADS)));
+    b->wpart.alloc((size_t)DYNW_MAX_CTAS * 6);
+    b->wpart.zero();
+    b->wticket.alloc(1);
+    b->wticket.zero();
     std::vector<int> ost = {D.oit, 0, 0};
     b->ostate.upload(ost);
     F.ostate = b->ostate.p;
@@ -617,6 +681,41 @@ class Engine : public EngineBase {
   }
 
   // ---- planning ------------------------------------------------------------------------
+  // Deferred nodes of the fused step: halo rows / columns (flagged by the builder) plus every node a
+  // boundary condition or a source touches.  A list that runs along one lattice column flags that
+  // column, anything else flags the rows of its nodes.
+  void build_deferred_tables() {
+    const int LX = cart_S.LX, LZ = cart_S.LZ;
+    h_rowflag.resize(LZ, 0);
+    h_colflag.resize(LX, 0);
+    std::vector<std::vector<int32_t>> lists = h_bc_nodes;
+    lists.push_back(h_src_iglob);
+    for (auto& L : lists) {
+      std::vector<int> colcount(LX, 0), rowcount(LZ, 0);
+      for (int nd : L) {
+        colcount[(nd - 1) % LX]++;
+        rowcount[(nd - 1) / LX]++;
+      }
+      for (int nd : L) {
+        const int gx = (nd - 1) % LX, gz = (nd - 1) / LX;
+        if (colcount[gx] > rowcount[gz]) h_colflag[gx] = 1;
+        else h_rowflag[gz] = 1;
+      }
+    }
+    std::vector<int> rows, cols;
+    for (int r = 0; r < LZ; ++r)
+      if (h_rowflag[r]) rows.push_back(r);
+    for (int c = 0; c < LX; ++c)
+      if (h_colflag[c]) cols.push_back(c);
+    ndrows = (int)rows.size();
+    ndcols = (int)cols.size();
+    rowflag.upload(h_rowflag);
+    colflag.upload(h_colflag);
+    if (ndrows) drows.upload(rows);
+    if (ndcols) dcols.upload(cols);
+    d2.alloc(npoin * ndof);
+    d2.zero();
+  }
   void build_color_plan() {
     const int n2 = ngll * ngll;
     ncolors = greedy_coloring(h_ibool.data(), n2, nelem, npoin, h_color);
@@ -707,8 +806,10 @@ class Engine : public EngineBase {
     S2D_REQUIRE(variant_ >= 0 && variant_ <= 2, "commit: unknown assembly variant");
     variant = variant_;
     if (cart_mode) {
-      S2D_REQUIRE(variant == S2D_ASM_PATCH, "commit: the structured builder only provides the patch plan");
+      S2D_REQUIRE(variant == S2D_ASM_PATCH, "commit: the structured builder only provides the strip kernel");
       k_invert<T><<<grid_for(rmass.n), 256, 0, stream>>>(rmass.p, rmass.n);
+      fused = (scheme.kind == 0) && env_int("S2D_FUSED", 1) != 0;
+      if (fused) build_deferred_tables();
     } else {
       if (nkv == 0) h_elem2kv.assign(nelem, -1);
       build_color_plan();
@@ -735,8 +836,7 @@ class Engine : public EngineBase {
   // f = -K d  (compute_Fint, solver.f90:273-320); f must be zero on entry unless the patch variant
   void launch_fint(const T* dd, const T* vv, T* ff) {
     if (cart_mode) {
-      if (xhalo()) launch_fint_xhalo(dd, ff);
-      else launches += launch_elem_strip<T>(cart_S, p_coef.p, dd, ff, cart_hx.p, cart_hz.p, npoin, h_H.data(), stream);
+      launch_strips(strip_io(dd, ff));
       return;
     }
     if (variant == S2D_ASM_PATCH) {
@@ -830,8 +930,7 @@ class Engine : public EngineBase {
     }
   }
 
-  void launch_bcs() {
-    const T* D = d.p;
+  void launch_bcs(const T* D) {
     const T* V = v.p;
     T* f = a.p;
     // bc_gen.f90:273-281: absorbing boundaries first, then the others in input order
@@ -861,37 +960,82 @@ class Engine : public EngineBase {
 
   void launch_outputs() {
     if (rec.present) {
-      const T* fld = rec.field == 'D' ? d.p : (rec.field == 'V' ? v.p : a.p);
+      const T* fld = rec.field == 'D' ? dn() : (rec.field == 'V' ? v.p : a.p);
       k_rec_store<T><<<ceil_div((long long)rec.dev.nx * ndof, 128), 128, 0, stream>>>(rec.dev, fld, npoin, ctl.p);
       launches++;
     }
     for (auto& b : faults) {
-      k_dynflt_write<T><<<1, 256, 0, stream>>>(b->dev, d.p, v.p, npoin, ctl.p);
+      k_dynflt_write<T><<<b->wctas, DYNW_THREADS, 0, stream>>>(b->dev, dn(), v.p, npoin, ctl.p, b->wpart.p,
+                                                               b->wticket.p);
       launches++;
     }
   }
 
-  void launch_step() {
+  // one leapfrog step with the node update fused into the strip kernel (strip_kernels.cuh)
+  void launch_step_fused() {
     const size_t nd = npoin * ndof;
     const T dt = (T)scheme.dt;
     k_tick<<<1, 1, 0, stream>>>(ctl.p);
     launches++;
-    const int zf = needs_zero_f() ? 1 : 0;
-    if (scheme.kind == 0) {
-      k_predict_leapfrog<T><<<grid_for(nd), 256, 0, stream>>>(d.p, v.p, a.p, nd, dt, zf);
-    } else {
-      const T c1 = (T)((0.5 - scheme.beta) * scheme.dt * scheme.dt), c2 = (T)((1.0 - scheme.gamma) * scheme.dt);
-      k_predict_newmark<T><<<grid_for(nd), 256, 0, stream>>>(d.p, v.p, a.p, nd, dt, c1, c2, zf);
+    if (!pred_valid) {  // first step after the fields were set: d[n] = d[n-1] + dt*v (solver.f90:151)
+      k_predict_to<T><<<grid_for(nd), 256, 0, stream>>>(dalt(), dn(), v.p, nd, dt);
+      launches++;
     }
-    launches++;
-    launch_fint(d.p, v.p, a.p);
+    T* dc = dalt();   // d[n]
+    T* dnx = dn();    // receives the prediction d[n+1]; d[n-1] is dead
+    StripIO<T> io = strip_io(dc, a.p);
+    io.v_in = v.p;
+    io.v_out = v.p;
+    io.rmass = rmass.p;
+    io.d_next = dnx;
+    io.a_out = store_accel ? a.p : nullptr;
+    io.rowflag = rowflag.p;
+    io.colflag = colflag.p;
+    io.dt = scheme.dt;
+    launch_strips(io);
     if (!h_src_iglob.empty()) {
       const int ns = (int)h_src_iglob.size();
       k_sources<T><<<ceil_div(ns, 32), 32, 0, stream>>>(a.p, npoin, ndof, ns, src_iglob.p, src_dir.p,
                                                         src_ampli.p, ctl.p);
       launches++;
     }
-    launch_bcs();
+    launch_bcs(dc);
+    const long long nw = (long long)ndrows * cart_S.LX + (long long)ndcols * cart_S.LZ;
+    if (nw > 0) {
+      k_strip_deferred<T><<<(unsigned)((nw + 255) / 256), 256, 0, stream>>>(
+          cart_S.LX, cart_S.LZ, ndof, npoin, drows.p, ndrows, dcols.p, ndcols, rowflag.p, a.p, v.p, rmass.p, dc, dnx, dt);
+      launches++;
+    }
+    dsel ^= 1;  // the caller now sees d[n]; the other buffer holds the prediction
+    pred_valid = true;
+    launch_outputs();
+  }
+
+  void launch_step() {
+    if (fused) {
+      launch_step_fused();
+      return;
+    }
+    const size_t nd = npoin * ndof;
+    const T dt = (T)scheme.dt;
+    k_tick<<<1, 1, 0, stream>>>(ctl.p);
+    launches++;
+    const int zf = needs_zero_f() ? 1 : 0;
+    if (scheme.kind == 0) {
+      k_predict_leapfrog<T><<<grid_for(nd), 256, 0, stream>>>(dn(), v.p, a.p, nd, dt, zf);
+    } else {
+      const T c1 = (T)((0.5 - scheme.beta) * scheme.dt * scheme.dt), c2 = (T)((1.0 - scheme.gamma) * scheme.dt);
+      k_predict_newmark<T><<<grid_for(nd), 256, 0, stream>>>(dn(), v.p, a.p, nd, dt, c1, c2, zf);
+    }
+    launches++;
+    launch_fint(dn(), v.p, a.p);
+    if (!h_src_iglob.empty()) {
+      const int ns = (int)h_src_iglob.size();
+      k_sources<T><<<ceil_div(ns, 32), 32, 0, stream>>>(a.p, npoin, ndof, ns, src_iglob.p, src_dir.p,
+                                                        src_ampli.p, ctl.p);
+      launches++;
+    }
+    launch_bcs(dn());
     T c3, c4;
     if (scheme.kind == 0) {
       c3 = dt;
@@ -900,7 +1044,7 @@ class Engine : public EngineBase {
       c3 = (T)(scheme.gamma * scheme.dt);
       c4 = (T)(scheme.beta * scheme.dt * scheme.dt);
     }
-    k_correct<T><<<grid_for(nd), 256, 0, stream>>>(d.p, v.p, a.p, rmass.p, nd, c3, c4);
+    k_correct<T><<<grid_for(nd), 256, 0, stream>>>(dn(), v.p, a.p, rmass.p, nd, c3, c4);
     launches++;
     launch_outputs();
   }
@@ -954,7 +1098,7 @@ class Engine : public EngineBase {
     const size_t nd = npoin * ndof;
     if (scratch.n != nd) scratch.alloc(nd);
     scratch.zero(stream);
-    launch_fint(d.p, v.p, scratch.p);
+    launch_fint(dn(), v.p, scratch.p);
     download(scratch, out);
   }
 
@@ -999,12 +1143,14 @@ class Engine : public EngineBase {
     }
   }
   void set_fields(const double* dd, const double* vv, const double* aa) override {
-    upload_field(d, dd);
+    if (dd) pred_valid = false;
+    upload_field(dbuf(), dd);
+    if (vv) pred_valid = false;
     upload_field(v, vv);
     upload_field(a, aa);
   }
   void get_fields(double* dd, double* vv, double* aa) override {
-    download(d, dd);
+    download(dbuf(), dd);
     download(v, vv);
     download(a, aa);
   }
@@ -1065,7 +1211,7 @@ class Engine : public EngineBase {
   }
   void progress(double* vmax, double* dmax) override {
     if (vmax) *vmax = reduce_absmax(v);
-    if (dmax) *dmax = reduce_absmax(d);
+    if (dmax) *dmax = reduce_absmax(dbuf());
   }
   double energy() override {
     S2D_REQUIRE(mass.n == npoin, "energy: s2d_set_mass was not called");
@@ -1086,6 +1232,7 @@ class Engine : public EngineBase {
     if (color) std::copy(h_color.begin(), h_color.end(), color);
   }
 
+  float kernel_ms() override { return last_kernel_ms; }
   void halo_info(int64_t* count, void** send_dev, void** recv_dev) override {
     S2D_REQUIRE(cart_mode, "halo_info: only x-strips made by the structured builder have halos");
     xhalo_setup();
@@ -1110,10 +1257,10 @@ class Engine : public EngineBase {
     cudaEvent_t e0, e1;
     S2D_CUDA(cudaEventCreate(&e0));
     S2D_CUDA(cudaEventCreate(&e1));
-    launch_fint(d.p, v.p, scratch.p);  // warm
+    launch_fint(dn(), v.p, scratch.p);  // warm
     S2D_CUDA(cudaStreamSynchronize(stream));
     S2D_CUDA(cudaEventRecord(e0, stream));
-    for (int r = 0; r < reps; ++r) launch_fint(d.p, v.p, scratch.p);
+    for (int r = 0; r < reps; ++r) launch_fint(dn(), v.p, scratch.p);
     S2D_CUDA(cudaEventRecord(e1, stream));
     S2D_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
@@ -1130,13 +1277,23 @@ class Engine : public EngineBase {
     S2D_CUDA(cudaEventCreate(&e1));
     // the stf tables of the last s2d_step call are replayed cyclically (row = (it-it0) mod nrows)
     S2D_CUDA(cudaStreamSynchronize(stream));
+    kev_on = cart_mode;
+    kev_n = 0;
     S2D_CUDA(cudaEventRecord(e0, stream));
     for (int k = 0; k < nsteps; ++k) launch_step();
     S2D_CUDA(cudaEventRecord(e1, stream));
     S2D_CUDA(cudaEventSynchronize(e1));
+    kev_on = false;
     it += nsteps;
     float ms = 0;
     S2D_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    last_kernel_ms = 0.f;
+    for (size_t q = 0; q + 1 < kev_n; q += 2) {
+      float t = 0;
+      S2D_CUDA(cudaEventElapsedTime(&t, kev[q], kev[q + 1]));
+      last_kernel_ms += t;
+    }
+    if (kev_n >= 2) last_kernel_ms /= (float)(kev_n / 2);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     check_device_error();

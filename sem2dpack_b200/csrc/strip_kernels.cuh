@@ -1,24 +1,33 @@
-// Element-force + assembly kernel for structured (MESH_CART) grids: the z-marching strip kernel.
+// Element-force + assembly (+ node update) kernel for structured (MESH_CART) grids: the z-marching
+// strip kernel.
 //
 // Replaces, for the flat Cartesian box, compute_Fint's element loop (SRC/solver.f90:291-299), the
 // gather/scatter of SRC/fields.f90:173-189,113-129 and ELAST_KD1/KD2_{SH,PSV} with mxm/My_MATMUL
-// folded in (SRC/mat_elastic.f90:464-775, SRC/mxmlib.f90).  Same operator as elem_kernels.cuh:
-//   Uxi = Ht U, Ueta = U H,  f = H (tH) + (tHt) Ht      (H(i,j) = h'_i(x_j))
+// folded in (SRC/mat_elastic.f90:464-775, SRC/mxmlib.f90) and -- in its fused form -- the
+// mass-inverse update of solve_leapfrog (SRC/solver.f90:151,157-158).  Same operator as
+// elem_kernels.cuh:   Uxi = Ht U, Ueta = U H,  f = H (tH) + (tHt) Ht      (H(i,j) = h'_i(x_j))
 //
 // Layout.  Fields live on the GLL LATTICE: node (gx,gz) at gz*LX + gx, LX = nx*(N-1)+1; the row of
 // split fault nodes is stored twice (lower side, then upper side).  The box is cut into vertical
-// strips EPW = floor(32/N) elements wide and horizontal bands of SEG element rows; one WARP owns one
-// (band, strip) item and marches through it upward, one element row per iteration:
+// strips EPW = floor(32/N) elements wide and horizontal bands of SEG element rows.  One WARP owns one
+// (band, strip) and marches through it upward, one element row per iteration; one CTA is a GROUP of
+// GW adjacent strips of the same band:
 //   * lane (el,i) owns lattice column i of element el and keeps that column's N values of the
 //     current element row in registers, so eta-contractions (along z) are register-local with
 //     hprime as constant-bank operands, and xi-contractions go through a warp-private
-//     shared-memory tile read back as 128-bit rows (__syncwarp only, no CTA barrier anywhere);
+//     shared-memory tile read back as 128-bit rows (__syncwarp only);
 //   * the top node of a row is the bottom node of the next: its displacement and its partial
 //     force sum are carried in registers (vertical assembly costs one add, no memory);
-//   * columns shared by two elements of the strip are merged with one warp shuffle;
-//   * every lattice node is written exactly once; only the strip's right edge column and the band's
-//     top row leave partial sums in small halo arrays, folded in by k_strip_halo_sum in a fixed
-//     order (deterministic, no atomics).
+//   * columns shared by two elements of a strip are merged with one warp shuffle, columns shared
+//     by two strips of a group are handed over through shared memory (one CTA barrier per row);
+//   * every lattice node is written exactly once.  Only a group's right edge column and a band's
+//     top row leave partial sums in small halo arrays, folded in by k_strip_fold in a fixed order
+//     (deterministic, no atomics).
+// Fused form: a node whose force is complete when its owner lane holds it -- every node except the
+// "deferred" ones (halo columns / rows, boundary-condition and source rows or columns, flagged in
+// rowflag / colflag) -- is advanced on the spot: a = rmass*f, v += dt*a, d_next = d + dt*v, so the
+// force array is never written or re-read for it.  Deferred nodes get their force stored and are
+// advanced by k_strip_deferred after the fold, the sources and the boundary conditions.
 // Coefficient planes are stored per (band, strip, element row) as [plane pair][j][lane] 16-byte
 // vectors: every warp load is one contiguous run, the whole array is read exactly once per step.
 #pragma once
@@ -33,12 +42,45 @@ struct StripGeom {
   int EPW, W, WL;          // elements per strip, lattice columns per full strip, W+1
   int nstrips, SEG, nseg_lo, nseg;
   int LX, LZ;              // lattice extent (LZ counts the duplicated fault row)
-  long long nitems;
-  // subset of strips handled by one launch: strip = it_strip0 + (k % it_nstr) * it_step, band = k / it_nstr
-  int it_strip0, it_nstr, it_step;
-  // x-strip interfaces with neighbour GPUs: the halo fold leaves lattice column 0 / LX-1 to the exchange
+  // groups of strips (one CTA each): [strip 0 alone if g_lead] [runs of GW strips] [last strip alone if g_tail]
+  int GW, g_lead, g_tail, ngroups;
+  // subset of groups handled by one launch: group = it_g0 + (k % it_ng) * it_step, band = k / it_ng
+  int it_g0, it_ng, it_step;
+  long long nitems;        // CTAs of this launch
+  // x-strip interfaces with neighbour GPUs: the fold leaves lattice column 0 / LX-1 to the exchange
   int xhalo_left, xhalo_right;
 };
+
+__host__ __device__ inline void strip_group(const StripGeom& G, int g, int& first, int& count) {
+  if (G.g_lead && g == 0) {
+    first = 0;
+    count = 1;
+    return;
+  }
+  const int s0 = G.g_lead ? 1 : 0;
+  const int nmid = G.nstrips - s0 - (G.g_tail ? 1 : 0);
+  const int gm = g - s0;
+  if (gm * G.GW < nmid) {
+    first = s0 + gm * G.GW;
+    count = min(G.GW, nmid - gm * G.GW);
+  } else {
+    first = G.nstrips - 1;
+    count = 1;
+  }
+}
+__host__ __device__ inline int strip_group_of(const StripGeom& G, int strip) {
+  if (G.g_lead && strip == 0) return 0;
+  const int s0 = G.g_lead ? 1 : 0;
+  if (G.g_tail && strip == G.nstrips - 1) return G.ngroups - 1;
+  return s0 + (strip - s0) / G.GW;
+}
+inline void strip_set_groups(StripGeom& G, int GW, bool lead, bool tail) {
+  G.GW = GW;
+  G.g_lead = (lead && G.nstrips > 1) ? 1 : 0;
+  G.g_tail = (tail && G.nstrips > 1) ? 1 : 0;
+  const int nmid = G.nstrips - G.g_lead - G.g_tail;
+  G.ngroups = G.g_lead + (nmid + GW - 1) / GW + G.g_tail;
+}
 
 // band below the shared row gz, or -1 when gz is not the bottom row of a band that shares it
 __host__ __device__ inline int strip_shared_row_seg(const StripGeom& G, int gz) {
@@ -56,7 +98,6 @@ __host__ __device__ inline int strip_shared_row_seg(const StripGeom& G, int gz) 
   }
   return -1;
 }
-
 __host__ __device__ inline void strip_seg_rows(const StripGeom& G, int seg, int& ez0, int& ez1) {
   if (seg < G.nseg_lo) {
     ez0 = seg * G.SEG;
@@ -72,9 +113,6 @@ __host__ __device__ inline int strip_seg_of(const StripGeom& G, int ez) {
 }
 __host__ __device__ inline int strip_lat_row(const StripGeom& G, int ez, int j) {
   return ez * (G.N - 1) + j + ((G.ezflt > 0 && ez >= G.ezflt) ? 1 : 0);
-}
-__host__ __device__ inline bool strip_row_detached(const StripGeom& G, int ez) {  // no element below shares nodes
-  return ez == 0 || (G.ezflt > 0 && ez == G.ezflt);
 }
 // first element (in units of elements) of the coefficient block of element row ez of (seg, strip)
 __host__ __device__ inline long long strip_elem_off(const StripGeom& G, int seg, int strip, int ez) {
@@ -105,19 +143,32 @@ struct StripArgs {
   const T* coef;
   const T* d;
   T* f;
-  T* halo_x;   // [c][nstrips-1][LZ]      partial sums of the column shared with the strip to the right
+  T* halo_x;   // [c][ngroups-1][LZ]      partial sums of the column shared with the group to the right
   T* halo_z;   // [c][nseg][nstrips][WL]  partial sums of the row shared with the band above
   size_t npoin;
-  T H[N * N];  // hprime, column-major (constant bank)
+  // fused leapfrog update of the nodes that are not deferred
+  const T* v_in;
+  T* v_out;
+  const T* rmass;
+  T* d_next;
+  T* a_out;                 // accelerations (may be null: not materialised)
+  const uint8_t* rowflag;   // (LZ) != 0: every node of the lattice row is deferred
+  const uint8_t* colflag;   // (LX) != 0: every node of the lattice column is deferred
+  T dt;
+  int prefetch;             // L2 prefetch of the next element row's coefficient block
+  T H[N * N];               // hprime, column-major (constant bank)
 };
 
 template <typename T>
 __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
+__device__ __forceinline__ void l2_prefetch_line(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 constexpr int strip_warps() { return 4; }
 constexpr int strip_min_ctas(int N, int tsize) { return N <= 6 ? 3 : (tsize == 4 ? 2 : 1); }
 
-template <typename T, int N, int NDOF>
+template <typename T, int N, int NDOF, bool FUSED>
 __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T)))
     k_elem_strip(const __grid_constant__ StripArgs<T, N> A) {
   constexpr int WARPS = strip_warps();
@@ -128,40 +179,48 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
   constexpr unsigned FULL = 0xffffffffu;
   using V2 = typename Vec2<T>::type;
   __shared__ __align__(16) T tile[WARPS][NDOF][N][EPW][NP];
+  __shared__ T hand[2][WARPS][NDOF][N];  // right-edge column of a strip, handed to the strip on its right
   const StripGeom& G = A.G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long item = (long long)blockIdx.x * WARPS + warp;
-  if (item >= G.nitems) return;  // whole warps leave; no CTA barrier is used below
-  const int seg = (int)(item / G.it_nstr);
-  const int strip = G.it_strip0 + (int)(item - (long long)seg * G.it_nstr) * G.it_step;
+  const long long cta = blockIdx.x;
+  const int seg = (int)(cta / G.it_ng);
+  const int grp = G.it_g0 + (int)(cta - (long long)seg * G.it_ng) * G.it_step;
+  int gfirst, gcount;
+  strip_group(G, grp, gfirst, gcount);
+  const bool wact = warp < gcount;            // warps beyond the group only keep the barriers company
+  const int strip = gfirst + (wact ? warp : 0);
   int ez0, ez1;
   strip_seg_rows(G, seg, ez0, ez1);
   const int ex0 = strip * EPW;
   const int cx = min(EPW, G.nx - ex0);
   int el = lane / N;
   const int i = lane - el * N;
-  const bool real = el < cx;
-  if (!real) el = cx - 1;  // shadow lanes mirror the last element (same cache lines), never store
+  const bool real = wact && el < cx;
+  if (el >= cx) el = cx - 1;  // shadow lanes mirror the last element (same cache lines), never store
   const int lanep = el * N + i;
-  const bool dup = (i == N - 1) && (el < cx - 1);    // column owned by lane+1 (i = 0 of the next element)
+  const bool dup = (i == N - 1) && (el < cx - 1);     // column owned by lane+1 (i = 0 of the next element)
   const bool redge = (i == N - 1) && (el == cx - 1);  // strip's right edge
   const bool merge = real && (i == 0) && (el > 0);
-  const bool to_halo = redge && (strip < G.nstrips - 1);
-  const bool st_ok = real && !dup;
+  const bool give = real && redge && (warp < gcount - 1);            // handed to the next warp of the group
+  const bool take = real && (lane == 0) && (warp > 0);               // receives the previous warp's edge
+  const bool to_halo = redge && !give && (strip < G.nstrips - 1);    // group's right edge: partial sum to halo_x
+  const bool st_ok = real && !dup && !give;
   const size_t LX = (size_t)G.LX;
   const int gx = (ex0 + el) * (N - 1) + i;
   const T* up = A.d + gx;
   T* sp;
   size_t rstride, cstride;
   if (to_halo) {
-    sp = A.halo_x + (size_t)strip * G.LZ;
+    sp = A.halo_x + (size_t)grp * G.LZ;
     rstride = 1;
-    cstride = (size_t)(G.nstrips - 1) * G.LZ;
+    cstride = (size_t)(G.ngroups - 1) * G.LZ;
   } else {
     sp = A.f + gx;
     rstride = LX;
     cstride = A.npoin;
   }
+  bool coldef = true;
+  if (FUSED) coldef = to_halo || (A.colflag[gx] != 0);
   T(*tl)[N][EPW][NP] = tile[warp];
   T Hi[N], HTi[N];
 #pragma unroll
@@ -182,126 +241,201 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
   const V2* cp = reinterpret_cast<const V2*>(A.coef) +
                  (size_t)strip_elem_off(G, seg, strip, ez0) * (NEL * N * N / 2) + lanep;
   const size_t cp_row = (size_t)cx * (NEL * N * N / 2);
+  const int nlines = (int)((cp_row * sizeof(V2) + 127) / 128);
 
   for (int ez = ez0; ez < ez1; ++ez, cp += cp_row) {
     const size_t grow = (size_t)strip_lat_row(G, ez, 0);
     const size_t rowbase = grow * LX;
-    // ---- loads of this element row: displacement rows j = 1..N-1, coefficient planes
-#pragma unroll
-    for (int c = 0; c < NDOF; ++c)
-#pragma unroll
-      for (int j = 1; j < N; ++j) U[c][j] = up[A.npoin * c + rowbase + (size_t)j * LX];
-    V2 a2[NEL / 2][N];
-#pragma unroll
-    for (int pp = 0; pp < NEL / 2; ++pp)
-#pragma unroll
-      for (int j = 0; j < N; ++j) a2[pp][j] = ld_stream(cp + (size_t)(pp * N + j) * cxN);
-    // ---- gradients: xi through the warp tile, eta in registers
-#pragma unroll
-    for (int c = 0; c < NDOF; ++c)
-#pragma unroll
-      for (int j = 0; j < N; ++j) tl[c][j][el][i] = U[c][j];
-    __syncwarp();
-    T gxi[NDOF][N], get[NDOF][N];
-#pragma unroll
-    for (int c = 0; c < NDOF; ++c)
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        T row[NP];
-        const V2* rp = reinterpret_cast<const V2*>(&tl[c][j][el][0]);
-#pragma unroll
-        for (int m = 0; m < NP / 2; ++m) {
-          const V2 t = rp[m];
-          row[2 * m] = t.x;
-          row[2 * m + 1] = t.y;
-        }
-        T s1 = 0, s2 = 0;
-#pragma unroll
-        for (int m = 0; m < N; ++m) {
-          s1 += Hi[m] * row[m];               // (Ht U)(i,j)
-          s2 += U[c][m] * A.H[m + N * j];     // (U H)(i,j)
-        }
-        gxi[c][j] = s1;
-        get[c][j] = s2;
-      }
-    __syncwarp();
-    // ---- pointwise stage (mat_elastic.f90:600-619 / :484-496 / :751-762)
-    T tH[NDOF][N], tHt[NDOF][N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      T ar[NEL], g1[NDOF], g2[NDOF], o1[NDOF], o2[NDOF];
-#pragma unroll
-      for (int pp = 0; pp < NEL / 2; ++pp) {
-        ar[2 * pp] = a2[pp][j].x;
-        ar[2 * pp + 1] = a2[pp][j].y;
-      }
-#pragma unroll
-      for (int c = 0; c < NDOF; ++c) {
-        g1[c] = gxi[c][j];
-        g2[c] = get[c][j];
-      }
-      pointwise_stage<T, NDOF>(ar, NEL, KD2, g1, g2, o1, o2);
-#pragma unroll
-      for (int c = 0; c < NDOF; ++c) {
-        tH[c][j] = o1[c];
-        tHt[c][j] = o2[c];
-      }
-    }
-    // ---- second contractions: H tH through the tile, tHt Ht in registers
-#pragma unroll
-    for (int c = 0; c < NDOF; ++c)
-#pragma unroll
-      for (int j = 0; j < N; ++j) tl[c][j][el][i] = tH[c][j];
-    __syncwarp();
     T f[NDOF][N];
-#pragma unroll
-    for (int c = 0; c < NDOF; ++c)
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        T row[NP];
-        const V2* rp = reinterpret_cast<const V2*>(&tl[c][j][el][0]);
-#pragma unroll
-        for (int m = 0; m < NP / 2; ++m) {
-          const V2 t = rp[m];
-          row[2 * m] = t.x;
-          row[2 * m + 1] = t.y;
-        }
-        T s1 = 0, s2 = 0;
-#pragma unroll
-        for (int m = 0; m < N; ++m) {
-          s1 += HTi[m] * row[m];               // (H tH)(i,j)
-          s2 += tHt[c][m] * A.H[j + N * m];    // (tHt Ht)(i,j)
-        }
-        f[c][j] = s1 + s2;
-      }
-    __syncwarp();
-    // ---- assembly: merge the column shared with the element to the left, add the carried row
-#pragma unroll
-    for (int c = 0; c < NDOF; ++c)
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        const T t = __shfl_up_sync(FULL, f[c][j], 1);
-        if (merge) f[c][j] += t;
-      }
-#pragma unroll
-    for (int c = 0; c < NDOF; ++c) {
-      f[c][0] += Fc[c];
-      Fc[c] = f[c][N - 1];
-      U[c][0] = U[c][N - 1];
-    }
-    if (st_ok) {
+    unsigned defer = 0;  // bit j: the node of row grow+j is deferred (its force is stored instead)
+    if (wact) {
+      // ---- loads of this element row: displacement rows j = 1..N-1, coefficient planes
 #pragma unroll
       for (int c = 0; c < NDOF; ++c)
 #pragma unroll
-        for (int j = 0; j < N - 1; ++j) sp[cstride * c + (grow + j) * rstride] = f[c][j];
+        for (int j = 1; j < N; ++j) U[c][j] = up[A.npoin * c + rowbase + (size_t)j * LX];
+      V2 a2[NEL / 2][N];
+#pragma unroll
+      for (int pp = 0; pp < NEL / 2; ++pp)
+#pragma unroll
+        for (int j = 0; j < N; ++j) a2[pp][j] = ld_stream(cp + (size_t)(pp * N + j) * cxN);
+      if (A.prefetch && ez + 1 < ez1) {
+        const char* nb = reinterpret_cast<const char*>(cp - lanep + cp_row);
+        for (int l = lane; l < nlines; l += 32) l2_prefetch_line(nb + (size_t)l * 128);
+      }
+      if (FUSED) {
+#pragma unroll
+        for (int j = 0; j < N - 1; ++j)
+          if (coldef || A.rowflag[grow + j]) defer |= 1u << j;
+        // node data of the fused update is read at the end of the row: pull its lines into L2 now
+        if (A.prefetch && st_ok && i == 0) {
+#pragma unroll
+          for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+            for (int j = 0; j < N - 1; ++j) {
+              const size_t q = A.npoin * c + rowbase + (size_t)j * LX + gx;
+              l2_prefetch_line(A.v_in + q);
+              l2_prefetch_line(A.rmass + q);
+            }
+        }
+      }
+      // ---- gradients: xi through the warp tile, eta in registers
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+        for (int j = 0; j < N; ++j) tl[c][j][el][i] = U[c][j];
+      __syncwarp();
+      T gxi[NDOF][N], get[NDOF][N];
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          T row[NP];
+          const V2* rp = reinterpret_cast<const V2*>(&tl[c][j][el][0]);
+#pragma unroll
+          for (int m = 0; m < NP / 2; ++m) {
+            const V2 t = rp[m];
+            row[2 * m] = t.x;
+            row[2 * m + 1] = t.y;
+          }
+          T s1 = 0, s2 = 0;
+#pragma unroll
+          for (int m = 0; m < N; ++m) {
+            s1 += Hi[m] * row[m];               // (Ht U)(i,j)
+            s2 += U[c][m] * A.H[m + N * j];     // (U H)(i,j)
+          }
+          gxi[c][j] = s1;
+          get[c][j] = s2;
+        }
+      __syncwarp();
+      // ---- pointwise stage (mat_elastic.f90:600-619 / :484-496 / :751-762)
+      T tH[NDOF][N], tHt[NDOF][N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        T ar[NEL], g1[NDOF], g2[NDOF], o1[NDOF], o2[NDOF];
+#pragma unroll
+        for (int pp = 0; pp < NEL / 2; ++pp) {
+          ar[2 * pp] = a2[pp][j].x;
+          ar[2 * pp + 1] = a2[pp][j].y;
+        }
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) {
+          g1[c] = gxi[c][j];
+          g2[c] = get[c][j];
+        }
+        pointwise_stage<T, NDOF>(ar, NEL, KD2, g1, g2, o1, o2);
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) {
+          tH[c][j] = o1[c];
+          tHt[c][j] = o2[c];
+        }
+      }
+      // ---- second contractions: H tH through the tile, tHt Ht in registers
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+        for (int j = 0; j < N; ++j) tl[c][j][el][i] = tH[c][j];
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          T row[NP];
+          const V2* rp = reinterpret_cast<const V2*>(&tl[c][j][el][0]);
+#pragma unroll
+          for (int m = 0; m < NP / 2; ++m) {
+            const V2 t = rp[m];
+            row[2 * m] = t.x;
+            row[2 * m + 1] = t.y;
+          }
+          T s1 = 0, s2 = 0;
+#pragma unroll
+          for (int m = 0; m < N; ++m) {
+            s1 += HTi[m] * row[m];               // (H tH)(i,j)
+            s2 += tHt[c][m] * A.H[j + N * m];    // (tHt Ht)(i,j)
+          }
+          f[c][j] = s1 + s2;
+        }
+      __syncwarp();
+      // ---- assembly inside the strip: merge the column shared with the element to the left
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const T t = __shfl_up_sync(FULL, f[c][j], 1);
+          if (merge) f[c][j] += t;
+        }
+      if (give) {
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+          for (int j = 0; j < N; ++j) hand[ez & 1][warp][c][j] = f[c][j];
+      }
+    }
+    if (WARPS > 1) __syncthreads();
+    if (wact) {
+      if (take) {  // column shared with the strip on the left (same group)
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+          for (int j = 0; j < N; ++j) f[c][j] += hand[ez & 1][warp - 1][c][j];
+      }
+      // ---- vertical carry, then every node of rows j = 0..N-2 is final for this strip
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) {
+        f[c][0] += Fc[c];
+        Fc[c] = f[c][N - 1];
+      }
+      if (st_ok) {
+        T vv[NDOF][N - 1], rm[NDOF][N - 1];
+        if (FUSED) {  // unconditional (deferred nodes included): one batch of independent loads
+#pragma unroll
+          for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+            for (int j = 0; j < N - 1; ++j) {
+              const size_t q = A.npoin * c + rowbase + (size_t)j * LX + gx;
+              vv[c][j] = A.v_in[q];
+              rm[c][j] = A.rmass[q];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+          for (int j = 0; j < N - 1; ++j) {
+            if (!FUSED || ((defer >> j) & 1u)) {
+              sp[cstride * c + (grow + j) * rstride] = f[c][j];
+            } else {  // solver.f90:157-158, then :151 of the next step
+              const size_t q = A.npoin * c + rowbase + (size_t)j * LX + gx;
+              const T acc = rm[c][j] * f[c][j];
+              const T vn = vv[c][j] + A.dt * acc;
+              A.v_out[q] = vn;
+              A.d_next[q] = U[c][j] + A.dt * vn;
+              if (A.a_out) A.a_out[q] = acc;
+            }
+          }
+      }
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) U[c][0] = U[c][N - 1];
     }
   }
-  // ---- top row of the band: private when nothing above shares it, else a partial sum for the band above
+  // ---- top row of the band: final when nothing above shares it, else a partial sum for the band above
   if (st_ok) {
     if (ez1 == G.nz || (G.ezflt > 0 && ez1 == G.ezflt)) {
       const size_t gt = (size_t)strip_lat_row(G, ez1 - 1, N - 1);
+      if (!FUSED || coldef || A.rowflag[gt]) {
 #pragma unroll
-      for (int c = 0; c < NDOF; ++c) sp[cstride * c + gt * rstride] = Fc[c];
+        for (int c = 0; c < NDOF; ++c) sp[cstride * c + gt * rstride] = Fc[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) {
+          const size_t q = A.npoin * c + gt * LX + gx;
+          const T acc = A.rmass[q] * Fc[c];
+          const T vn = A.v_in[q] + A.dt * acc;
+          A.v_out[q] = vn;
+          A.d_next[q] = U[c][0] + A.dt * vn;
+          if (A.a_out) A.a_out[q] = acc;
+        }
+      }
     } else {
 #pragma unroll
       for (int c = 0; c < NDOF; ++c)
@@ -310,26 +444,39 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
   }
 }
 
+// lattice column of the boundary between group hb and group hb+1
+__host__ __device__ inline int strip_halo_col(const StripGeom& G, int hb, int& strip_right) {
+  int first, count;
+  strip_group(G, hb + 1, first, count);
+  strip_right = first;
+  return first * G.W;
+}
+
 // Adds the partial sums left in the halo arrays.  One thread per halo node, fixed order of additions
-// ((f + left strip) + band below + band below of the left strip): deterministic.
+// ((f + left group) + band below + band below of the left strip): deterministic.
+//   part A: the ngroups-1 halo columns (threads run across the columns of one lattice row first)
+//   part B: the rows shared by two bands, minus the halo columns
 template <typename T>
-__global__ void k_strip_halo_sum(StripGeom G, T* __restrict__ f, const T* __restrict__ halo_x,
-                                 const T* __restrict__ halo_z, size_t npoin) {
+__global__ void k_strip_fold(StripGeom G, T* __restrict__ f, const T* __restrict__ halo_x,
+                             const T* __restrict__ halo_z, size_t npoin) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nA = (long long)(G.nstrips - 1) * G.LZ;
+  const int nhb = G.ngroups - 1;
+  const long long nA = (long long)nhb * G.LZ;
   const int nsh_lo = G.nseg_lo > 0 ? G.nseg_lo - 1 : 0;
   const int nsh = nsh_lo + (G.nseg - G.nseg_lo - 1);
   const size_t hz_c = (size_t)G.nseg * G.nstrips * G.WL;
-  const size_t hx_c = (size_t)(G.nstrips - 1) * G.LZ;
-  if (w < nA) {  // strip-boundary columns, all rows
-    const int b = 1 + (int)(w / G.LZ), gz = (int)(w - (long long)(b - 1) * G.LZ);
-    const size_t node = (size_t)gz * G.LX + (size_t)b * G.W;
+  const size_t hx_c = (size_t)nhb * G.LZ;
+  if (w < nA) {
+    const int gz = (int)(w / nhb), hb = (int)(w - (long long)gz * nhb);
+    int sr;
+    const int gx = strip_halo_col(G, hb, sr);
+    const size_t node = (size_t)gz * G.LX + gx;
     const int seg_l = strip_shared_row_seg(G, gz);
     for (int c = 0; c < G.ndof; ++c) {
-      T acc = f[node + npoin * c] + halo_x[hx_c * c + (size_t)(b - 1) * G.LZ + gz];
+      T acc = f[node + npoin * c] + halo_x[hx_c * c + (size_t)hb * G.LZ + gz];
       if (seg_l >= 0) {
-        acc += halo_z[hz_c * c + ((size_t)seg_l * G.nstrips + b) * G.WL];
-        acc += halo_z[hz_c * c + ((size_t)seg_l * G.nstrips + (b - 1)) * G.WL + G.W];
+        acc += halo_z[hz_c * c + ((size_t)seg_l * G.nstrips + sr) * G.WL];
+        acc += halo_z[hz_c * c + ((size_t)seg_l * G.nstrips + (sr - 1)) * G.WL + G.W];
       }
       f[node + npoin * c] = acc;
     }
@@ -344,7 +491,7 @@ __global__ void k_strip_halo_sum(StripGeom G, T* __restrict__ f, const T* __rest
     strip = G.nstrips - 1;
     lc = gx - strip * G.W;
   } else if (lc == 0 && strip > 0) {
-    return;  // strip-boundary column: handled above
+    if (strip_group_of(G, strip - 1) != strip_group_of(G, strip)) return;  // halo column: part A
   }
   if ((gx == 0 && G.xhalo_left) || (gx == G.LX - 1 && G.xhalo_right)) return;  // folded by k_xhalo_unpack
   int ez0, ez1;
@@ -352,6 +499,37 @@ __global__ void k_strip_halo_sum(StripGeom G, T* __restrict__ f, const T* __rest
   const size_t node = (size_t)strip_lat_row(G, ez0, 0) * G.LX + gx;
   for (int c = 0; c < G.ndof; ++c)
     f[node + npoin * c] += halo_z[hz_c * c + ((size_t)(seg_u - 1) * G.nstrips + strip) * G.WL + lc];
+}
+
+// Leapfrog update of the deferred nodes once their force is complete (fold, sources, boundary
+// conditions done): a = rmass*f, v += dt*a, d_next = d + dt*v  (solver.f90:157-158,151).
+//   part A: flagged rows (contiguous);  part B: flagged columns, minus the nodes of flagged rows
+template <typename T>
+__global__ void k_strip_deferred(int LX, int LZ, int ndof, size_t npoin, const int* __restrict__ drows, int ndrows,
+                                 const int* __restrict__ dcols, int ndcols, const uint8_t* __restrict__ rowflag,
+                                 T* __restrict__ fa, T* __restrict__ v, const T* __restrict__ rmass,
+                                 const T* __restrict__ d, T* __restrict__ d_next, T dt) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nA = (long long)ndrows * LX;
+  size_t node;
+  if (w < nA) {
+    const int r = (int)(w / LX);
+    node = (size_t)drows[r] * LX + (size_t)(w - (long long)r * LX);
+  } else {
+    const long long w2 = w - nA;
+    if (w2 >= (long long)ndcols * LZ) return;
+    const int gz = (int)(w2 / ndcols), k = (int)(w2 - (long long)gz * ndcols);
+    if (rowflag[gz]) return;
+    node = (size_t)gz * LX + dcols[k];
+  }
+  for (int c = 0; c < ndof; ++c) {
+    const size_t q = node + npoin * c;
+    const T acc = rmass[q] * fa[q];
+    const T vn = v[q] + dt * acc;
+    fa[q] = acc;
+    v[q] = vn;
+    d_next[q] = d[q] + dt * vn;
+  }
 }
 
 // x-strip interface columns (multi-GPU): this GPU's complete partial sum of lattice column 0 / LX-1,
@@ -396,29 +574,61 @@ __global__ void k_xhalo_unpack(StripGeom G, T* __restrict__ f, const T* __restri
   f[(size_t)gz * G.LX + gx + npoin * c] = xhalo_own(G, f, halo_z, npoin, side, c, gz) + src[q];
 }
 
-template <typename T, int N, int NDOF>
-inline void launch_elem_strip_n(const StripArgs<T, N>& A, cudaStream_t s) {
-  const long long nblk = (A.G.nitems + strip_warps() - 1) / strip_warps();
-  k_elem_strip<T, N, NDOF><<<(unsigned)nblk, strip_warps() * 32, 0, s>>>(A);
-}
-
-// element-force launch over the strips selected by G.it_* (no halo fold)
+// everything a strip launch needs besides the geometry
 template <typename T>
-inline void launch_elem_strip_items(const StripGeom& G, const T* coef, const T* d, T* f, T* halo_x, T* halo_z,
-                             size_t npoin, const double* hprime, cudaStream_t s) {
-#define S2D_STRIP_CASE(NN)                                             \
-  case NN: {                                                           \
-    StripArgs<T, NN> A{};                                              \
-    A.G = G;                                                           \
-    A.coef = coef;                                                     \
-    A.d = d;                                                           \
-    A.f = f;                                                           \
-    A.halo_x = halo_x;                                                 \
-    A.halo_z = halo_z;                                                 \
-    A.npoin = npoin;                                                   \
-    for (int k = 0; k < NN * NN; ++k) A.H[k] = (T)hprime[k];           \
-    if (G.ndof == 1) launch_elem_strip_n<T, NN, 1>(A, s);              \
-    else launch_elem_strip_n<T, NN, 2>(A, s);                          \
+struct StripIO {
+  const T* coef;
+  const T* d;
+  T* f;
+  T* halo_x;
+  T* halo_z;
+  size_t npoin;
+  const double* hprime;
+  // fused update (null v_in = plain force evaluation)
+  const T* v_in = nullptr;
+  T* v_out = nullptr;
+  const T* rmass = nullptr;
+  T* d_next = nullptr;
+  T* a_out = nullptr;
+  const uint8_t* rowflag = nullptr;
+  const uint8_t* colflag = nullptr;
+  double dt = 0.0;
+  int prefetch = 1;
+};
+
+// element-force launch over the groups selected by G.it_* (no halo fold)
+template <typename T>
+inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cudaStream_t s) {
+  if (G.nitems <= 0) return;
+  const bool fused = io.v_in != nullptr;
+#define S2D_STRIP_CASE(NN)                                                                        \
+  case NN: {                                                                                      \
+    StripArgs<T, NN> A{};                                                                         \
+    A.G = G;                                                                                      \
+    A.coef = io.coef;                                                                             \
+    A.d = io.d;                                                                                   \
+    A.f = io.f;                                                                                   \
+    A.halo_x = io.halo_x;                                                                         \
+    A.halo_z = io.halo_z;                                                                         \
+    A.npoin = io.npoin;                                                                           \
+    A.v_in = io.v_in;                                                                             \
+    A.v_out = io.v_out;                                                                           \
+    A.rmass = io.rmass;                                                                           \
+    A.d_next = io.d_next;                                                                         \
+    A.a_out = io.a_out;                                                                           \
+    A.rowflag = io.rowflag;                                                                       \
+    A.colflag = io.colflag;                                                                       \
+    A.dt = (T)io.dt;                                                                              \
+    A.prefetch = io.prefetch;                                                                     \
+    for (int k = 0; k < NN * NN; ++k) A.H[k] = (T)io.hprime[k];                                   \
+    const unsigned nb = (unsigned)G.nitems;                                                       \
+    if (G.ndof == 1) {                                                                            \
+      if (fused) k_elem_strip<T, NN, 1, true><<<nb, strip_warps() * 32, 0, s>>>(A);               \
+      else k_elem_strip<T, NN, 1, false><<<nb, strip_warps() * 32, 0, s>>>(A);                    \
+    } else {                                                                                      \
+      if (fused) k_elem_strip<T, NN, 2, true><<<nb, strip_warps() * 32, 0, s>>>(A);               \
+      else k_elem_strip<T, NN, 2, false><<<nb, strip_warps() * 32, 0, s>>>(A);                    \
+    }                                                                                             \
   } break;
   switch (G.N) {
     S2D_STRIP_CASE(3)
@@ -433,31 +643,26 @@ inline void launch_elem_strip_items(const StripGeom& G, const T* coef, const T* 
       throw ArgError("ngll must be in 3..10");
   }
 #undef S2D_STRIP_CASE
+  S2D_CUDA(cudaGetLastError());
 }
 template <typename T>
 inline int launch_strip_fold(const StripGeom& G, T* f, const T* halo_x, const T* halo_z, size_t npoin,
                              cudaStream_t s) {
-  int n = 0;
   const int nsh = (G.nseg_lo > 0 ? G.nseg_lo - 1 : 0) + (G.nseg - G.nseg_lo - 1);
-  const long long nh = (long long)(G.nstrips - 1) * G.LZ + (long long)nsh * G.LX;
-  if (nh > 0) {
-    k_strip_halo_sum<T><<<(unsigned)((nh + 255) / 256), 256, 0, s>>>(G, f, halo_x, halo_z, npoin);
-    n++;
-  }
+  const long long nh = (long long)(G.ngroups - 1) * G.LZ + (long long)nsh * G.LX;
+  if (nh <= 0) return 0;
+  k_strip_fold<T><<<(unsigned)((nh + 255) / 256), 256, 0, s>>>(G, f, halo_x, halo_z, npoin);
   S2D_CUDA(cudaGetLastError());
-  return n;
+  return 1;
 }
-// f = -K d on the lattice: strip kernel over every strip + halo fold (2 launches)
-template <typename T>
-inline int launch_elem_strip(const StripGeom& G0, const T* coef, const T* d, T* f, T* halo_x, T* halo_z,
-                             size_t npoin, const double* hprime, cudaStream_t s) {
+// all groups of the box
+inline StripGeom strip_all_groups(const StripGeom& G0) {
   StripGeom G = G0;
-  G.it_strip0 = 0;
-  G.it_nstr = G.nstrips;
+  G.it_g0 = 0;
+  G.it_ng = G.ngroups;
   G.it_step = 1;
-  G.nitems = (long long)G.nseg * G.nstrips;
-  launch_elem_strip_items<T>(G, coef, d, f, halo_x, halo_z, npoin, hprime, s);
-  return 1 + launch_strip_fold<T>(G, f, halo_x, halo_z, npoin, s);
+  G.nitems = (long long)G.nseg * G.ngroups;
+  return G;
 }
 
 }  // namespace s2d

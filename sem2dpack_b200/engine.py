@@ -190,6 +190,11 @@ class Engine:
         self._ck(self.L.s2d_time_steps(self.h, nsteps, C.byref(ms)))
         return ms.value
 
+    def kernel_ms(self):
+        ms = C.c_float()
+        self._ck(self.L.s2d_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
     def launch_count(self):
         n = C.c_int64()
         self._ck(self.L.s2d_launch_count(self.h, C.byref(n)))
