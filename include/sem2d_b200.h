@@ -216,6 +216,11 @@ typedef struct {
   double courant;
   int32_t device;
   int32_t halo_left, halo_right; /* strip has a neighbour on that side (no physical boundary there) */
+  /* 0: isotropic P-SV boxes keep only (lambda, mu) per GLL point in HBM and the strip kernel forms
+   *    the six planes of MAT_ELAST_init_a (mat_elastic.f90:334-340,355-357) in registers, with the
+   *    same sequence of roundings (a third of the coefficient traffic);
+   * 1: all nelast planes are stored, as matwrk_elast_type%a is (mat_elastic.f90:11-14). */
+  int32_t coef_mode;
 } s2d_cart_desc;
 int s2d_cart_create(s2d_handle* h, const s2d_cart_desc* desc);
 /* BC_ABSO_init on mesh side tag 1 bottom, 2 right, 3 top, 4 left (mesh_structured.f90:86-196);

@@ -58,7 +58,7 @@ class CartDesc(C.Structure):
         ("seed", C.c_uint64), ("ix0", C.c_int64), ("iz0", C.c_int64),
         ("rho", C.c_double), ("cp", C.c_double), ("cs", C.c_double),
         ("precision", C.c_int32), ("scheme", Scheme), ("courant", C.c_double), ("device", C.c_int32),
-        ("halo_left", C.c_int32), ("halo_right", C.c_int32),
+        ("halo_left", C.c_int32), ("halo_right", C.c_int32), ("coef_mode", C.c_int32),
     ]
 
 

@@ -163,7 +163,7 @@ __host__ __device__ inline void cart_planes(const CartGeom& G, double rho, doubl
 // kernels
 // coefficient planes in the strip layout of strip_kernels.cuh; one thread per GLL point of an element
 template <typename T>
-__global__ void k_cart_coef(CartGeom G, T* __restrict__ coef, int nelast) {
+__global__ void k_cart_coef(CartGeom G, T* __restrict__ coef, int nelast, int compact) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int N = G.N, N2 = N * N;
   const long long total = (long long)G.nx * G.nz * N2;
@@ -174,6 +174,11 @@ __global__ void k_cart_coef(CartGeom G, T* __restrict__ coef, int nelast) {
   const int ix = (int)(e % G.nx), iz = (int)(e / G.nx);
   double rho, cp, cs, av[6];
   cart_material(G, ix, iz, i, j, rho, cp, cs);
+  if (compact) {  // (lambda, mu) only: the strip kernel forms the planes (strip_kernels.cuh)
+    coef[strip_coef_index(G.S, 2, ix, iz, i, j, 0)] = (T)(rho * (cp * cp - 2.0 * cs * cs));
+    coef[strip_coef_index(G.S, 2, ix, iz, i, j, 1)] = (T)(rho * cs * cs);
+    return;
+  }
   cart_planes(G, rho, cp, cs, i, j, nelast, av);
   for (int pl = 0; pl < nelast; ++pl) coef[strip_coef_index(G.S, nelast, ix, iz, i, j, pl)] = (T)av[pl];
 }
@@ -355,6 +360,7 @@ struct CartState {
   double H[100];
   bool mass_inverted = false;
   bool bc_added = false;
+  int coef_mode = 0;  // 0 = compact (lambda, mu) where the rheology allows, 1 = all planes stored
   double CoefA2V() const { return scheme.kind == 1 ? scheme.gamma * scheme.dt : scheme.dt; }        // time.f90:443-456
   double CoefA2D() const { return scheme.kind == 1 ? scheme.beta * scheme.dt * scheme.dt : 0.0; }    // time.f90:426-440
   double CoefA2Vrhs() const { return scheme.kind == 1 ? scheme.alpha * CoefA2V() : 0.5 * CoefA2V(); }  // :465-486
@@ -383,8 +389,13 @@ static void cart_build(Engine<T>& E, CartState& S) {
   E.nkv = 0;
   E.ncoefsets = G.seed != 0 ? E.nelem : 1;
   E.p_hetero = true;
-  E.p_coef.alloc((size_t)E.nelem * nelast * N2);
-  k_cart_coef<T><<<nblk, 256, 0, st>>>(G, E.p_coef.p, nelast);
+  E.cart_compact = (G.ndof == 2 && S.coef_mode == 0) ? 1 : 0;
+  E.cart_cdx = 2.0 / G.hx;
+  E.cart_cdz = 2.0 / G.hz;
+  E.cart_cdet = (0.5 * G.hx) * (0.5 * G.hz);
+  E.cart_wgll.assign(G.wgll, G.wgll + N);
+  E.p_coef.alloc((size_t)E.nelem * (E.cart_compact ? 2 : nelast) * N2);
+  k_cart_coef<T><<<nblk, 256, 0, st>>>(G, E.p_coef.p, nelast, E.cart_compact);
   // mass (kept un-inverted in rmass until commit)
   k_cart_mass<T><<<nblk, 256, 0, st>>>(G, E.rmass.p, E.npoin);
   S2D_CUDA(cudaGetLastError());
@@ -394,6 +405,8 @@ static void cart_build(Engine<T>& E, CartState& S) {
   E.cart_hz.alloc((size_t)G.ndof * G.S.nseg * G.S.nstrips * G.S.WL + 1);
   E.cart_hx.zero(st);
   E.cart_hz.zero(st);
+  E.cart_meet.alloc((size_t)G.S.nseg * std::max(G.S.ngroups - 1, 1));
+  E.cart_meet.zero(st);
   // deferred nodes of the fused step that come from the decomposition itself: rows shared by two
   // bands, columns shared by two groups, GPU interface columns
   E.h_rowflag.assign(G.S.LZ, 0);
@@ -402,7 +415,7 @@ static void cart_build(Engine<T>& E, CartState& S) {
     if (strip_shared_row_seg(G.S, gz) >= 0) E.h_rowflag[gz] = 1;
   for (int hb = 0; hb + 1 < G.S.ngroups; ++hb) {
     int sr;
-    E.h_colflag[strip_halo_col(G.S, hb, sr)] = 1;
+    E.h_colflag[strip_halo_col(G.S, hb, sr)] = 2;  // not finished by its owner lane, but inside the strip kernel
   }
   if (G.halo_left) E.h_colflag[0] = 1;
   if (G.halo_right) E.h_colflag[G.S.LX - 1] = 1;
@@ -518,6 +531,7 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
       Q.WL = Q.W + 1;
       Q.nstrips = (G.nx + Q.EPW - 1) / Q.EPW;
       Q.SEG = std::max(1, env_int("S2D_SEG", 32));
+      Q.SEG = std::min(Q.SEG, (32 * STRIP_MASK_WORDS - 2) / (G.N - 1));  // rows of a band fit the kernel's row mask
       Q.nseg_lo = G.ezflt > 0 ? (G.ezflt + Q.SEG - 1) / Q.SEG : 0;
       Q.nseg = Q.nseg_lo + (G.nz - G.ezflt + Q.SEG - 1) / Q.SEG;
       Q.LX = G.nx * (G.N - 1) + 1;
@@ -543,6 +557,7 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
     }
     S->scheme = D->scheme;
     S->courant = D->courant;
+    S->coef_mode = D->coef_mode != 0 ? 1 : (env_int("S2D_COEF_FULL", 0) != 0 ? 1 : 0);
     // dt from the Courant number (init.f90:187-225, time.f90:334-341)
     {
       DevBuf<unsigned long long> mx;
@@ -813,19 +828,37 @@ int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double*
     // reference layout a(ngll,ngll,nelast,nelem) from the strip layout
     const int nelast = (G.ndof == 1) ? 2 : 6;
     std::vector<double> pc;
+    int compact = 0;
     if (Eb->prec == 8) {
       pc = as_engine<double>(Eb)->p_coef.to_host();
+      compact = as_engine<double>(Eb)->cart_compact;
     } else {
       std::vector<float> t = as_engine<float>(Eb)->p_coef.to_host();
       pc.assign(t.begin(), t.end());
+      compact = as_engine<float>(Eb)->cart_compact;
     }
+    const double cdx = 2.0 / G.hx, cdz = 2.0 / G.hz, det = (0.5 * G.hx) * (0.5 * G.hz);
     for (int iz = 0; iz < G.nz; ++iz)
       for (int ix = 0; ix < G.nx; ++ix) {
         const size_t e = (size_t)ix + (size_t)G.nx * iz;
-        for (int pl = 0; pl < nelast; ++pl)
-          for (int j = 0; j < N; ++j)
-            for (int i = 0; i < N; ++i)
-              a[(e * nelast + pl) * N2 + i + N * j] = pc[strip_coef_index(G.S, nelast, ix, iz, i, j, pl)];
+        for (int j = 0; j < N; ++j)
+          for (int i = 0; i < N; ++i) {
+            double av[6];
+            if (compact) {  // the planes as the strip kernel forms them from (lambda, mu)
+              const double la = pc[strip_coef_index(G.S, 2, ix, iz, i, j, 0)];
+              const double mu = pc[strip_coef_index(G.S, 2, ix, iz, i, j, 1)];
+              const double kx = la + 2.0 * mu, nw = -(det * (G.wgll[i] * G.wgll[j]));
+              av[0] = nw * ((kx * cdx) * cdx);
+              av[1] = nw * ((la * cdx) * cdz);
+              av[2] = nw * ((kx * cdz) * cdz);
+              av[3] = nw * ((mu * cdz) * cdz);
+              av[4] = nw * ((mu * cdx) * cdz);
+              av[5] = nw * ((mu * cdx) * cdx);
+            } else {
+              for (int pl = 0; pl < nelast; ++pl) av[pl] = pc[strip_coef_index(G.S, nelast, ix, iz, i, j, pl)];
+            }
+            for (int pl = 0; pl < nelast; ++pl) a[(e * nelast + pl) * N2 + i + N * j] = av[pl];
+          }
       }
   }
   if (rmass) {

@@ -46,10 +46,12 @@ __device__ __forceinline__ void pointwise_stage(const T* __restrict__ a, int nel
   } else {
     const T uxx = gxi[0], uzx = gxi[NDOF - 1], uxe = get[0], uze = get[NDOF - 1];
     if (nelast == 6) {  // P-SV flat (mat_elastic.f90:484-496 KD1, :600-619 KD2)
-      tH[0] = a[0] * uxx + a[1] * uze;
-      tHt[0] = kd2 ? a[3] * (uxe + uzx) : a[3] * uxe + a[4] * uzx;
-      tH[NDOF - 1] = a[4] * uxe + a[5] * uzx;
-      tHt[NDOF - 1] = a[1] * uxx + a[2] * uze;
+      // explicit fused multiply-adds: every kernel (and both coefficient modes of the strip kernel)
+      // rounds these sums the same way, whatever the compiler would have contracted
+      tH[0] = fma(a[0], uxx, a[1] * uze);
+      tHt[0] = kd2 ? a[3] * (uxe + uzx) : fma(a[3], uxe, a[4] * uzx);
+      tH[NDOF - 1] = fma(a[4], uxe, a[5] * uzx);
+      tHt[NDOF - 1] = fma(a[1], uxx, a[2] * uze);
     } else {  // general P-SV, 10 planes (mat_elastic.f90:497-515)
       tH[0] = a[0] * uxx + a[6] * uxe + a[7] * uzx + a[1] * uze;
       tHt[0] = a[6] * uxx + a[3] * uxe + a[4] * uzx + a[8] * uze;

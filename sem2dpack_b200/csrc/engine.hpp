@@ -156,6 +156,11 @@ class Engine : public EngineBase {
   bool cart_mode = false;
   StripGeom cart_S{};
   DevBuf<T> cart_hx, cart_hz;
+  DevBuf<int> cart_meet;  // arrival counters of the group-boundary columns (strip_kernels.cuh)
+  // compact coefficient mode: p_coef holds (lambda, mu) per GLL point, the strip kernel forms the planes
+  int cart_compact = 0;
+  double cart_cdx = 0.0, cart_cdz = 0.0, cart_cdet = 0.0;
+  std::vector<double> cart_wgll;
   std::function<void(const T*, double*)> cart_to_ref;    // lattice (T) -> reference numbering (FP64), device to device
   std::function<void(const double*, T*)> cart_from_ref;  // reference numbering (FP64) -> lattice (T)
   // fused leapfrog step of the strip kernel: two displacement buffers (the kernel reads d[n] and
@@ -164,8 +169,12 @@ class Engine : public EngineBase {
   int dsel = 0;             // which buffer holds the displacement the caller sees
   bool pred_valid = false;  // the other buffer holds d + dt*v of the next step
   bool fused = false;
-  bool store_accel = env_int("S2D_STORE_ACCEL", 1) != 0;
+  // accelerations of the fused step: 1 = written every step, 0 = never, 2 (default) = when somebody can
+  // see them: on the last step of every s2d_step call, and on every step if receivers record 'A'
+  int store_accel = env_int("S2D_STORE_ACCEL", 2);
   int strip_prefetch = env_int("S2D_STRIP_PF", 1);
+  int strip_occ = env_int("S2D_STRIP_OCC", 0);
+  int strip_stage = env_int("S2D_STAGE", 7);
   std::vector<uint8_t> h_rowflag, h_colflag;
   std::vector<std::vector<int32_t>> h_bc_nodes;  // node lists of every boundary condition (for the flags)
   DevBuf<uint8_t> rowflag, colflag;
@@ -218,9 +227,17 @@ class Engine : public EngineBase {
     io.f = ff;
     io.halo_x = cart_hx.p;
     io.halo_z = cart_hz.p;
+    io.meet = cart_meet.p;
     io.npoin = npoin;
     io.hprime = h_H.data();
     io.prefetch = strip_prefetch;
+    io.compact = cart_compact;
+    io.occ = strip_occ;
+    io.stage = strip_stage;
+    io.cdx = cart_cdx;
+    io.cdz = cart_cdz;
+    io.cdet = cart_cdet;
+    io.wgll = cart_wgll.empty() ? nullptr : cart_wgll.data();
     return io;
   }
   // strip kernel over the whole box (+ halo fold, + interface exchange); io.v_in != null = fused update
@@ -698,7 +715,7 @@ class Engine : public EngineBase {
       }
       for (int nd : L) {
         const int gx = (nd - 1) % LX, gz = (nd - 1) / LX;
-        if (colcount[gx] > rowcount[gz]) h_colflag[gx] = 1;
+        if (colcount[gx] > rowcount[gz]) h_colflag[gx] = 1;  // overrides 2 (group-boundary column)
         else h_rowflag[gz] = 1;
       }
     }
@@ -706,7 +723,7 @@ class Engine : public EngineBase {
     for (int r = 0; r < LZ; ++r)
       if (h_rowflag[r]) rows.push_back(r);
     for (int c = 0; c < LX; ++c)
-      if (h_colflag[c]) cols.push_back(c);
+      if (h_colflag[c] == 1) cols.push_back(c);  // 2 = group-boundary column: advanced inside k_elem_strip
     ndrows = (int)rows.size();
     ndcols = (int)cols.size();
     rowflag.upload(h_rowflag);
@@ -972,7 +989,7 @@ class Engine : public EngineBase {
   }
 
   // one leapfrog step with the node update fused into the strip kernel (strip_kernels.cuh)
-  void launch_step_fused() {
+  void launch_step_fused(bool last_of_call) {
     const size_t nd = npoin * ndof;
     const T dt = (T)scheme.dt;
     k_tick<<<1, 1, 0, stream>>>(ctl.p);
@@ -988,7 +1005,8 @@ class Engine : public EngineBase {
     io.v_out = v.p;
     io.rmass = rmass.p;
     io.d_next = dnx;
-    io.a_out = store_accel ? a.p : nullptr;
+    const bool want_a = store_accel == 1 || (store_accel == 2 && (last_of_call || (rec.present && rec.field == 'A')));
+    io.a_out = want_a ? a.p : nullptr;
     io.rowflag = rowflag.p;
     io.colflag = colflag.p;
     io.dt = scheme.dt;
@@ -1011,9 +1029,9 @@ class Engine : public EngineBase {
     launch_outputs();
   }
 
-  void launch_step() {
+  void launch_step(bool last_of_call = true) {
     if (fused) {
-      launch_step_fused();
+      launch_step_fused(last_of_call);
       return;
     }
     const size_t nd = npoin * ndof;
@@ -1087,7 +1105,7 @@ class Engine : public EngineBase {
     const int it0 = it + 1;
     S2D_CUDA(cudaMemcpyAsync(&ctl.p->it0, &it0, sizeof(int), cudaMemcpyHostToDevice, stream));
     S2D_CUDA(cudaMemcpyAsync(&ctl.p->nrows, &nsteps, sizeof(int), cudaMemcpyHostToDevice, stream));
-    for (int k = 0; k < nsteps; ++k) launch_step();
+    for (int k = 0; k < nsteps; ++k) launch_step(k == nsteps - 1);
     it += nsteps;
     S2D_CUDA(cudaGetLastError());
     check_device_error();
@@ -1280,7 +1298,7 @@ class Engine : public EngineBase {
     kev_on = cart_mode;
     kev_n = 0;
     S2D_CUDA(cudaEventRecord(e0, stream));
-    for (int k = 0; k < nsteps; ++k) launch_step();
+    for (int k = 0; k < nsteps; ++k) launch_step(k == nsteps - 1);
     S2D_CUDA(cudaEventRecord(e1, stream));
     S2D_CUDA(cudaEventSynchronize(e1));
     kev_on = false;

@@ -133,6 +133,14 @@ __host__ __device__ inline size_t strip_coef_index(const StripGeom& G, int nelas
   return base + 2 * ((size_t)((pl >> 1) * N + j) * (cx * N) + el * N + i) + (pl & 1);
 }
 
+// lattice column of the boundary between group hb and group hb+1
+__host__ __device__ inline int strip_halo_col(const StripGeom& G, int hb, int& strip_right) {
+  int first, count;
+  strip_group(G, hb + 1, first, count);
+  strip_right = first;
+  return first * G.W;
+}
+
 template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
@@ -153,11 +161,21 @@ struct StripArgs {
   T* d_next;
   T* a_out;                 // accelerations (may be null: not materialised)
   const uint8_t* rowflag;   // (LZ) != 0: every node of the lattice row is deferred
-  const uint8_t* colflag;   // (LX) != 0: every node of the lattice column is deferred
+  const uint8_t* colflag;   // (LX) 1: every node of the lattice column is deferred; 2: group-boundary column
+  int* meet;                // [nseg][ngroups-1] arrival counters of the group-boundary columns (zero between launches)
   T dt;
-  int prefetch;             // L2 prefetch of the next element row's coefficient block
+  int prefetch;             // L2 prefetch of what is not staged
+  int stage;                // what goes through the shared-memory staging area (bits: 1 d, 2 coefficients, 4 v+rmass)
   T H[N * N];               // hprime, column-major (constant bank)
+  // compact coefficient mode (isotropic flat grids): only (lambda, mu) are stored per GLL point and
+  // the six planes of MAT_ELAST_init_a (mat_elastic.f90:334-340,355-357) are formed in registers,
+  // a_k = -weights * ((c * m1) * m2) with the same order of roundings as the stored planes
+  T cdx, cdz, cdet;         // DxiDx = 2/hx, DetaDz = 2/hz, |J| = (hx/2)(hz/2)
+  T wg[N];                  // GLL weights: weights(i,j) = |J| * (wg[i] * wg[j])
 };
+
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 
 template <typename T>
 __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
@@ -165,23 +183,59 @@ __device__ __forceinline__ void l2_prefetch_line(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-constexpr int strip_warps() { return 4; }
-constexpr int strip_min_ctas(int N, int tsize) { return N <= 6 ? 3 : (tsize == 4 ? 2 : 1); }
+// asynchronous global -> shared copies (LDGSTS): the loads of the next element row are in flight
+// while the current one is computed, without holding registers
+template <int BYTES>
+__device__ __forceinline__ void stage_copy(void* smem, const void* g) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sa), "l"(g), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND>
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
-template <typename T, int N, int NDOF, bool FUSED>
-__global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T)))
+constexpr int strip_warps() { return 4; }
+constexpr int STRIP_MASK_WORDS = 128;  // a band has at most 32*128 lattice rows (s2d_cart_create clamps SEG)
+// bytes of the staging area of one warp: coefficient vectors and displacement rows of one element
+// row; in the fused form also the velocities and inverse masses of the nodes it will advance
+constexpr size_t strip_stage_bytes(int N, int NDOF, int tsize, bool fused, bool compact) {
+  const size_t npl = compact ? 2 : (NDOF == 1 ? 2 : 6);
+  const size_t c = (npl / 2) * N * 32 * (2 * tsize), u = (size_t)NDOF * (N - 1) * 32 * tsize, r = (size_t)(N - 1) * 32 * tsize;
+  return c + u + (fused ? u + r : 0);
+}
+constexpr int strip_min_ctas(int N, int tsize, bool compact = false) {
+  return N <= 6 ? (tsize == 4 ? 4 : 3) : (tsize == 4 ? 2 : 1);
+}
+
+template <typename T, int N, int NDOF, bool FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT)>
+__global__ void __launch_bounds__(strip_warps() * 32, MINB)
     k_elem_strip(const __grid_constant__ StripArgs<T, N> A) {
+  static_assert(!COMPACT || NDOF == 2, "compact coefficients: P-SV only");
   constexpr int WARPS = strip_warps();
   constexpr int NEL = NDOF == 1 ? 2 : 6;
+  constexpr int NPL = COMPACT ? 2 : NEL;  // planes stored per GLL point
   constexpr int KD2 = (N == 5) ? 1 : 0;  // OPT_NGLL (constants.f90:6, mat_elastic.f90:412)
   constexpr int EPW = 32 / N;
-  constexpr int NP = (N + 1) & ~1;       // tile rows padded to an even count: 16-byte vector reads
+  constexpr int NP = N;                  // tile rows: N scalars, read back one broadcast LDS per value
   constexpr unsigned FULL = 0xffffffffu;
   using V2 = typename Vec2<T>::type;
-  __shared__ __align__(16) T tile[WARPS][NDOF][N][EPW][NP];
+  __shared__ __align__(16) T tile[WARPS][NDOF][N][EPW * NP];
   __shared__ T hand[2][WARPS][NDOF][N];  // right-edge column of a strip, handed to the strip on its right
+  __shared__ unsigned rowmask[STRIP_MASK_WORDS + 1];  // bit r: lattice row (band's first row + r) is deferred
+  extern __shared__ __align__(16) unsigned char stage_raw[];
+  constexpr int NU = NDOF * (N - 1);
+  constexpr size_t SZ_C = (size_t)(NPL / 2) * N * 32 * sizeof(V2), SZ_U = (size_t)NU * 32 * sizeof(T);
   const StripGeom& G = A.G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // every lane only ever touches its own slots of the staging area: no barrier guards it
+  unsigned char* wstage = stage_raw + (size_t)warp * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT);
+  V2* st_c = reinterpret_cast<V2*>(wstage) + lane;             // [plane pair * N + j][32]
+  T* st_u = reinterpret_cast<T*>(wstage + SZ_C) + lane;        // [c * (N-1) + j-1][32]
+  T* st_v = reinterpret_cast<T*>(wstage + SZ_C + SZ_U) + lane; // [c * (N-1) + j][32]   (fused)
+  T* st_r = st_v + NU * 32;                                    // [j][32]               (fused)
   const long long cta = blockIdx.x;
   const int seg = (int)(cta / G.it_ng);
   const int grp = G.it_g0 + (int)(cta - (long long)seg * G.it_ng) * G.it_step;
@@ -220,8 +274,19 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
     cstride = A.npoin;
   }
   bool coldef = true;
-  if (FUSED) coldef = to_halo || (A.colflag[gx] != 0);
-  T(*tl)[N][EPW][NP] = tile[warp];
+  const int band_row0 = strip_lat_row(G, ez0, 0);
+  if (FUSED) {
+    coldef = to_halo || (A.colflag[gx] != 0);
+    const int nrows_band = strip_lat_row(G, ez1 - 1, N - 1) - band_row0 + 1;
+    for (int w = warp; w <= STRIP_MASK_WORDS; w += WARPS) {
+      const int r = 32 * w + lane;
+      const unsigned m = __ballot_sync(FULL, r < nrows_band && A.rowflag[band_row0 + r] != 0);
+      if (lane == 0) rowmask[w] = m;
+      if (32 * w >= nrows_band) break;  // one word past the band's last one (zeros) is enough
+    }
+    __syncthreads();
+  }
+  T(*tlw)[N][EPW * NP] = tile[warp];
   T Hi[N], HTi[N];
 #pragma unroll
   for (int m = 0; m < N; ++m) {
@@ -239,9 +304,43 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
   }
   const int cxN = cx * N;
   const V2* cp = reinterpret_cast<const V2*>(A.coef) +
-                 (size_t)strip_elem_off(G, seg, strip, ez0) * (NEL * N * N / 2) + lanep;
-  const size_t cp_row = (size_t)cx * (NEL * N * N / 2);
-  const int nlines = (int)((cp_row * sizeof(V2) + 127) / 128);
+                 (size_t)strip_elem_off(G, seg, strip, ez0) * (NPL * N * N / 2) + lanep;
+  const size_t cp_row = (size_t)cx * (NPL * N * N / 2);
+  T nW[COMPACT ? N : 1];  // -weights(i,j) of this lane's column
+  if (COMPACT) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) nW[j] = -mul_rn(A.cdet, mul_rn(A.wg[i], A.wg[j]));
+  }
+
+  // loads of one element row: displacement rows j = 1..N-1 and the coefficient vectors.  A.stage
+  // selects what goes through the staging area (bit 0: displacements, 1: coefficients, 2: v and
+  // rmass of the fused update); the rest is loaded straight into registers when it is needed.
+  const bool stg_u = A.stage & 1, stg_c = A.stage & 2, stg_v = A.stage & 4;
+  auto issue_row = [&](int ezr, const V2* cpr) {
+    const size_t rb = (size_t)strip_lat_row(G, ezr, 0) * LX;
+    if (stg_u) {
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+        for (int j = 1; j < N; ++j)
+          stage_copy<sizeof(T)>(st_u + (c * (N - 1) + j - 1) * 32, up + A.npoin * c + rb + (size_t)j * LX);
+    }
+    if (stg_c) {
+#pragma unroll
+      for (int pp = 0; pp < NPL / 2; ++pp)
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+          stage_copy<sizeof(V2)>(st_c + (pp * N + j) * 32, cpr + (size_t)(pp * N + j) * cxN);
+    } else if (A.prefetch) {  // pull the row's coefficient block into L2
+      const char* nb = reinterpret_cast<const char*>(cpr - lanep);
+      const int nlines = (int)((cp_row * sizeof(V2) + 127) / 128);
+      for (int l = lane; l < nlines; l += 32) l2_prefetch_line(nb + (size_t)l * 128);
+    }
+  };
+  if (wact) {
+    issue_row(ez0, cp);
+    stage_commit();
+  }
 
   for (int ez = ez0; ez < ez1; ++ez, cp += cp_row) {
     const size_t grow = (size_t)strip_lat_row(G, ez, 0);
@@ -249,55 +348,76 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
     T f[NDOF][N];
     unsigned defer = 0;  // bit j: the node of row grow+j is deferred (its force is stored instead)
     if (wact) {
-      // ---- loads of this element row: displacement rows j = 1..N-1, coefficient planes
+      // ---- this element row has landed in the staging area: move it to registers, then start the
+      // copies of what the end of this iteration needs (v, rmass) and of the whole next row
+      stage_wait<0>();
+      V2 a2[NPL / 2][N];
+      if (stg_u) {
 #pragma unroll
-      for (int c = 0; c < NDOF; ++c)
+        for (int c = 0; c < NDOF; ++c)
 #pragma unroll
-        for (int j = 1; j < N; ++j) U[c][j] = up[A.npoin * c + rowbase + (size_t)j * LX];
-      V2 a2[NEL / 2][N];
+          for (int j = 1; j < N; ++j) U[c][j] = st_u[(c * (N - 1) + j - 1) * 32];
+      } else {
 #pragma unroll
-      for (int pp = 0; pp < NEL / 2; ++pp)
+        for (int c = 0; c < NDOF; ++c)
 #pragma unroll
-        for (int j = 0; j < N; ++j) a2[pp][j] = ld_stream(cp + (size_t)(pp * N + j) * cxN);
-      if (A.prefetch && ez + 1 < ez1) {
-        const char* nb = reinterpret_cast<const char*>(cp - lanep + cp_row);
-        for (int l = lane; l < nlines; l += 32) l2_prefetch_line(nb + (size_t)l * 128);
+          for (int j = 1; j < N; ++j) U[c][j] = up[A.npoin * c + rowbase + (size_t)j * LX];
+      }
+      if (stg_c) {
+#pragma unroll
+        for (int pp = 0; pp < NPL / 2; ++pp)
+#pragma unroll
+          for (int j = 0; j < N; ++j) a2[pp][j] = st_c[(pp * N + j) * 32];
+      } else {
+#pragma unroll
+        for (int pp = 0; pp < NPL / 2; ++pp)
+#pragma unroll
+          for (int j = 0; j < N; ++j) a2[pp][j] = ld_stream(cp + (size_t)(pp * N + j) * cxN);
       }
       if (FUSED) {
-#pragma unroll
-        for (int j = 0; j < N - 1; ++j)
-          if (coldef || A.rowflag[grow + j]) defer |= 1u << j;
-        // node data of the fused update is read at the end of the row: pull its lines into L2 now
-        if (A.prefetch && st_ok && i == 0) {
-#pragma unroll
-          for (int c = 0; c < NDOF; ++c)
+        {
+          const int o = (int)grow - band_row0;
+          const unsigned long long two = ((unsigned long long)rowmask[(o >> 5) + 1] << 32) | rowmask[o >> 5];
+          defer = coldef ? ~0u : (unsigned)(two >> (o & 31));
+        }
+        if (st_ok) {
+          if (stg_v) {
 #pragma unroll
             for (int j = 0; j < N - 1; ++j) {
-              const size_t q = A.npoin * c + rowbase + (size_t)j * LX + gx;
-              l2_prefetch_line(A.v_in + q);
-              l2_prefetch_line(A.rmass + q);
+              const size_t q = rowbase + (size_t)j * LX + gx;
+              stage_copy<sizeof(T)>(st_r + j * 32, A.rmass + q);
+#pragma unroll
+              for (int c = 0; c < NDOF; ++c)
+                stage_copy<sizeof(T)>(st_v + (c * (N - 1) + j) * 32, A.v_in + A.npoin * c + q);
             }
+          } else if (A.prefetch && i == 0) {  // read at the end of the row: pull the lines into L2 now
+#pragma unroll
+            for (int j = 0; j < N - 1; ++j) {
+              const size_t q = rowbase + (size_t)j * LX + gx;
+              l2_prefetch_line(A.rmass + q);
+#pragma unroll
+              for (int c = 0; c < NDOF; ++c) l2_prefetch_line(A.v_in + A.npoin * c + q);
+            }
+          }
         }
       }
+      stage_commit();
+      if (ez + 1 < ez1) issue_row(ez + 1, cp + cp_row);
+      stage_commit();
       // ---- gradients: xi through the warp tile, eta in registers
 #pragma unroll
       for (int c = 0; c < NDOF; ++c)
 #pragma unroll
-        for (int j = 0; j < N; ++j) tl[c][j][el][i] = U[c][j];
+        for (int j = 0; j < N; ++j) tlw[c][j][lanep] = U[c][j];
       __syncwarp();
       T gxi[NDOF][N], get[NDOF][N];
 #pragma unroll
       for (int c = 0; c < NDOF; ++c)
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-          T row[NP];
-          const V2* rp = reinterpret_cast<const V2*>(&tl[c][j][el][0]);
+          T row[N];  // the 5 lanes of an element read the same word: one wavefront per value
 #pragma unroll
-          for (int m = 0; m < NP / 2; ++m) {
-            const V2 t = rp[m];
-            row[2 * m] = t.x;
-            row[2 * m + 1] = t.y;
-          }
+          for (int m = 0; m < N; ++m) row[m] = tlw[c][j][el * N + m];
           T s1 = 0, s2 = 0;
 #pragma unroll
           for (int m = 0; m < N; ++m) {
@@ -313,10 +433,23 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         T ar[NEL], g1[NDOF], g2[NDOF], o1[NDOF], o2[NDOF];
+        if constexpr (COMPACT) {
+          const T la = a2[0][j].x, mu = a2[0][j].y;
+          const T kx = la + T(2) * mu;  // 2*mu is exact: one rounding with or without contraction
+          const T kdx = mul_rn(kx, A.cdx), ldx = mul_rn(la, A.cdx), mdx = mul_rn(mu, A.cdx);
+          const T kdz = mul_rn(kx, A.cdz), mdz = mul_rn(mu, A.cdz);
+          ar[0] = mul_rn(nW[j], mul_rn(kdx, A.cdx));
+          ar[1] = mul_rn(nW[j], mul_rn(ldx, A.cdz));
+          ar[2] = mul_rn(nW[j], mul_rn(kdz, A.cdz));
+          ar[3] = mul_rn(nW[j], mul_rn(mdz, A.cdz));
+          ar[4] = mul_rn(nW[j], mul_rn(mdx, A.cdz));
+          ar[5] = mul_rn(nW[j], mul_rn(mdx, A.cdx));
+        } else {
 #pragma unroll
-        for (int pp = 0; pp < NEL / 2; ++pp) {
-          ar[2 * pp] = a2[pp][j].x;
-          ar[2 * pp + 1] = a2[pp][j].y;
+          for (int pp = 0; pp < NPL / 2; ++pp) {
+            ar[2 * pp] = a2[pp][j].x;
+            ar[2 * pp + 1] = a2[pp][j].y;
+          }
         }
 #pragma unroll
         for (int c = 0; c < NDOF; ++c) {
@@ -334,20 +467,15 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
 #pragma unroll
       for (int c = 0; c < NDOF; ++c)
 #pragma unroll
-        for (int j = 0; j < N; ++j) tl[c][j][el][i] = tH[c][j];
+        for (int j = 0; j < N; ++j) tlw[c][j][lanep] = tH[c][j];
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < NDOF; ++c)
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-          T row[NP];
-          const V2* rp = reinterpret_cast<const V2*>(&tl[c][j][el][0]);
+          T row[N];  // the 5 lanes of an element read the same word: one wavefront per value
 #pragma unroll
-          for (int m = 0; m < NP / 2; ++m) {
-            const V2 t = rp[m];
-            row[2 * m] = t.x;
-            row[2 * m + 1] = t.y;
-          }
+          for (int m = 0; m < N; ++m) row[m] = tlw[c][j][el * N + m];
           T s1 = 0, s2 = 0;
 #pragma unroll
           for (int m = 0; m < N; ++m) {
@@ -387,16 +515,28 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
         Fc[c] = f[c][N - 1];
       }
       if (st_ok) {
-        T vv[NDOF][N - 1], rm[NDOF][N - 1];
-        if (FUSED) {  // unconditional (deferred nodes included): one batch of independent loads
-#pragma unroll
-          for (int c = 0; c < NDOF; ++c)
+        // The inverse mass of a node that no boundary condition touches is the same for every
+        // component (mat_mass.f90:56-57; only bc_abso.f90:243 makes the columns differ, on deferred
+        // nodes), so one read of component 1 serves all of them.
+        T vv[NDOF][N - 1], rm[N - 1];
+        if (FUSED) {  // requested at the top of this iteration; the next row's copies may still be in flight
+          if (stg_v) {
+            stage_wait<1>();
 #pragma unroll
             for (int j = 0; j < N - 1; ++j) {
-              const size_t q = A.npoin * c + rowbase + (size_t)j * LX + gx;
-              vv[c][j] = A.v_in[q];
-              rm[c][j] = A.rmass[q];
+              rm[j] = st_r[j * 32];
+#pragma unroll
+              for (int c = 0; c < NDOF; ++c) vv[c][j] = st_v[(c * (N - 1) + j) * 32];
             }
+          } else {  // one batch of independent loads (deferred nodes included)
+#pragma unroll
+            for (int j = 0; j < N - 1; ++j) {
+              const size_t q = rowbase + (size_t)j * LX + gx;
+              rm[j] = A.rmass[q];
+#pragma unroll
+              for (int c = 0; c < NDOF; ++c) vv[c][j] = A.v_in[A.npoin * c + q];
+            }
+          }
         }
 #pragma unroll
         for (int c = 0; c < NDOF; ++c)
@@ -406,7 +546,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
               sp[cstride * c + (grow + j) * rstride] = f[c][j];
             } else {  // solver.f90:157-158, then :151 of the next step
               const size_t q = A.npoin * c + rowbase + (size_t)j * LX + gx;
-              const T acc = rm[c][j] * f[c][j];
+              const T acc = rm[j] * f[c][j];
               const T vn = vv[c][j] + A.dt * acc;
               A.v_out[q] = vn;
               A.d_next[q] = U[c][j] + A.dt * vn;
@@ -429,7 +569,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
 #pragma unroll
         for (int c = 0; c < NDOF; ++c) {
           const size_t q = A.npoin * c + gt * LX + gx;
-          const T acc = A.rmass[q] * Fc[c];
+          const T acc = A.rmass[gt * LX + gx] * Fc[c];
           const T vn = A.v_in[q] + A.dt * acc;
           A.v_out[q] = vn;
           A.d_next[q] = U[c][0] + A.dt * vn;
@@ -442,42 +582,112 @@ __global__ void __launch_bounds__(strip_warps() * 32, strip_min_ctas(N, sizeof(T
         A.halo_z[((size_t)(c * G.nseg + seg) * G.nstrips + strip) * G.WL + el * (N - 1) + i] = Fc[c];
     }
   }
+  // ---- columns shared by two groups: the left group left its partial sums in halo_x, the right
+  // group (the column's owner) in f.  Whichever of the two CTAs gets there second adds them -- the
+  // same two addends either way, so the result does not depend on who it is -- and, in the fused
+  // form, advances the nodes.  No CTA ever waits for another.  Rows shared by two bands stay with
+  // k_strip_fold (they also need the band below).
+  if (G.ngroups > 1) {
+    __shared__ int second[2];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      const int hb = grp - 1 + (int)threadIdx.x;  // boundary with the group on the left / on the right
+      int sec = 0;
+      if (hb >= 0 && hb < G.ngroups - 1) {
+        int* m = A.meet + (size_t)seg * (G.ngroups - 1) + hb;
+        sec = atomicAdd(m, 1);
+        if (sec) *m = 0;  // armed again for the next evaluation
+      }
+      second[threadIdx.x] = sec;
+    }
+    __syncthreads();
+    int ra = strip_lat_row(G, ez0, 0), rb = strip_lat_row(G, ez1 - 1, N - 1);
+    if (strip_shared_row_seg(G, ra) >= 0) ++ra;
+    if (!(ez1 == G.nz || (G.ezflt > 0 && ez1 == G.ezflt))) --rb;
+    const int nrows = rb - ra + 1;
+    const size_t hx_c = (size_t)(G.ngroups - 1) * G.LZ;
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+      if (!second[side]) continue;
+      __threadfence();
+      const int hb = grp - 1 + side;
+      int sr;
+      const int hx = strip_halo_col(G, hb, sr);
+      const bool bcol = FUSED && A.colflag[hx] == 1;
+      // two nodes per thread and pass, every load issued before the first use
+#pragma unroll 1
+      for (int k0 = threadIdx.x; k0 < nrows * NDOF; k0 += 2 * blockDim.x) {
+        size_t q[2];
+        T tot[2], rm[2], vv[2], dd[2];
+        bool on[2], store_f[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int k = k0 + u * blockDim.x;
+          on[u] = k < nrows * NDOF;
+          const int kk = on[u] ? k : k0;
+          const int c = kk / nrows, gz = ra + (kk - c * nrows);
+          q[u] = A.npoin * c + (size_t)gz * LX + hx;
+          tot[u] = __ldcg(A.f + q[u]) + __ldcg(A.halo_x + hx_c * c + (size_t)hb * G.LZ + gz);
+          store_f[u] = !FUSED || bcol || A.rowflag[gz];
+          if (FUSED) {
+            rm[u] = A.rmass[q[u]];
+            vv[u] = A.v_in[q[u]];
+            dd[u] = A.d[q[u]];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (!on[u]) continue;
+          if (store_f[u]) {
+            A.f[q[u]] = tot[u];
+          } else {
+            const T acc = rm[u] * tot[u];
+            const T vn = vv[u] + A.dt * acc;
+            A.v_out[q[u]] = vn;
+            A.d_next[q[u]] = dd[u] + A.dt * vn;
+            if (A.a_out) A.a_out[q[u]] = acc;
+          }
+        }
+      }
+    }
+  }
 }
 
-// lattice column of the boundary between group hb and group hb+1
-__host__ __device__ inline int strip_halo_col(const StripGeom& G, int hb, int& strip_right) {
-  int first, count;
-  strip_group(G, hb + 1, first, count);
-  strip_right = first;
-  return first * G.W;
-}
 
-// Adds the partial sums left in the halo arrays.  One thread per halo node, fixed order of additions
-// ((f + left group) + band below + band below of the left strip): deterministic.
-//   part A: the ngroups-1 halo columns (threads run across the columns of one lattice row first)
-//   part B: the rows shared by two bands, minus the halo columns
+// Adds the partial sums that meet on the rows shared by two bands.  One thread per node, fixed order of
+// additions ((f + left group) + band below + band below of the left strip): deterministic.
+//   part A: the nodes of those rows that also lie on a group-boundary column
+//   part B: the other nodes of those rows
+// (group-boundary columns away from these rows are added inside k_elem_strip)
+__host__ __device__ inline int strip_shared_upper_seg(const StripGeom& G, int r) {
+  const int nsh_lo = G.nseg_lo > 0 ? G.nseg_lo - 1 : 0;
+  return r < nsh_lo ? r + 1 : G.nseg_lo + 1 + (r - nsh_lo);
+}
 template <typename T>
 __global__ void k_strip_fold(StripGeom G, T* __restrict__ f, const T* __restrict__ halo_x,
                              const T* __restrict__ halo_z, size_t npoin) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nhb = G.ngroups - 1;
-  const long long nA = (long long)nhb * G.LZ;
   const int nsh_lo = G.nseg_lo > 0 ? G.nseg_lo - 1 : 0;
   const int nsh = nsh_lo + (G.nseg - G.nseg_lo - 1);
+  const long long nA = (long long)nhb * nsh;
   const size_t hz_c = (size_t)G.nseg * G.nstrips * G.WL;
   const size_t hx_c = (size_t)nhb * G.LZ;
   if (w < nA) {
-    const int gz = (int)(w / nhb), hb = (int)(w - (long long)gz * nhb);
+    const int r = (int)(w / nhb), hb = (int)(w - (long long)r * nhb);
+    const int seg_u = strip_shared_upper_seg(G, r);
+    int ez0, ez1;
+    strip_seg_rows(G, seg_u, ez0, ez1);
+    const int gz = strip_lat_row(G, ez0, 0);
     int sr;
     const int gx = strip_halo_col(G, hb, sr);
     const size_t node = (size_t)gz * G.LX + gx;
-    const int seg_l = strip_shared_row_seg(G, gz);
+    const int seg_l = seg_u - 1;
     for (int c = 0; c < G.ndof; ++c) {
       T acc = f[node + npoin * c] + halo_x[hx_c * c + (size_t)hb * G.LZ + gz];
-      if (seg_l >= 0) {
-        acc += halo_z[hz_c * c + ((size_t)seg_l * G.nstrips + sr) * G.WL];
-        acc += halo_z[hz_c * c + ((size_t)seg_l * G.nstrips + (sr - 1)) * G.WL + G.W];
-      }
+      acc += halo_z[hz_c * c + ((size_t)seg_l * G.nstrips + sr) * G.WL];
+      acc += halo_z[hz_c * c + ((size_t)seg_l * G.nstrips + (sr - 1)) * G.WL + G.W];
       f[node + npoin * c] = acc;
     }
     return;
@@ -485,13 +695,13 @@ __global__ void k_strip_fold(StripGeom G, T* __restrict__ f, const T* __restrict
   const long long w2 = w - nA;
   if (w2 >= (long long)nsh * G.LX) return;
   const int r = (int)(w2 / G.LX), gx = (int)(w2 - (long long)r * G.LX);
-  const int seg_u = r < nsh_lo ? r + 1 : G.nseg_lo + 1 + (r - nsh_lo);
+  const int seg_u = strip_shared_upper_seg(G, r);
   int strip = gx / G.W, lc = gx - strip * G.W;
   if (strip >= G.nstrips) {
     strip = G.nstrips - 1;
     lc = gx - strip * G.W;
   } else if (lc == 0 && strip > 0) {
-    if (strip_group_of(G, strip - 1) != strip_group_of(G, strip)) return;  // halo column: part A
+    if (strip_group_of(G, strip - 1) != strip_group_of(G, strip)) return;  // group-boundary column: part A
   }
   if ((gx == 0 && G.xhalo_left) || (gx == G.LX - 1 && G.xhalo_right)) return;  // folded by k_xhalo_unpack
   int ez0, ez1;
@@ -592,9 +802,25 @@ struct StripIO {
   T* a_out = nullptr;
   const uint8_t* rowflag = nullptr;
   const uint8_t* colflag = nullptr;
+  int* meet = nullptr;
   double dt = 0.0;
   int prefetch = 1;
+  int stage = 7;
+  // compact coefficient mode (coef holds lambda, mu only)
+  int compact = 0;
+  int occ = 0;              // resident CTAs per SM the kernel is compiled for (0 = default)
+  double cdx = 0.0, cdz = 0.0, cdet = 0.0;
+  const double* wgll = nullptr;
 };
+
+template <typename T, int N, int NDOF, bool FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT)>
+inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) {
+  constexpr size_t smem = strip_warps() * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT);
+  if (smem > 48 * 1024 - 16 * 1024)  // per device: set on every launch (static shared memory takes up to 20 KB)
+    S2D_CUDA(cudaFuncSetAttribute(k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB><<<nb, strip_warps() * 32, smem, s>>>(A);
+}
 
 // element-force launch over the groups selected by G.it_* (no halo fold)
 template <typename T>
@@ -618,16 +844,33 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
     A.a_out = io.a_out;                                                                           \
     A.rowflag = io.rowflag;                                                                       \
     A.colflag = io.colflag;                                                                       \
+    A.meet = io.meet;                                                                             \
     A.dt = (T)io.dt;                                                                              \
     A.prefetch = io.prefetch;                                                                     \
+    A.stage = io.stage;                                                                           \
     for (int k = 0; k < NN * NN; ++k) A.H[k] = (T)io.hprime[k];                                   \
+    A.cdx = (T)io.cdx;                                                                            \
+    A.cdz = (T)io.cdz;                                                                            \
+    A.cdet = (T)io.cdet;                                                                          \
+    for (int k = 0; k < NN; ++k) A.wg[k] = io.wgll ? (T)io.wgll[k] : (T)0;                        \
     const unsigned nb = (unsigned)G.nitems;                                                       \
     if (G.ndof == 1) {                                                                            \
-      if (fused) k_elem_strip<T, NN, 1, true><<<nb, strip_warps() * 32, 0, s>>>(A);               \
-      else k_elem_strip<T, NN, 1, false><<<nb, strip_warps() * 32, 0, s>>>(A);                    \
+      if (io.compact) throw ArgError("compact coefficients need ndof = 2");                       \
+      if (fused) strip_launch<T, NN, 1, true, false>(nb, A, s);                                   \
+      else strip_launch<T, NN, 1, false, false>(nb, A, s);                                        \
+    } else if (io.compact) {                                                                      \
+      if constexpr (NN == 5 && sizeof(T) == 8) {  /* measured alternative: 4 CTAs/SM, spills */    \
+        if (io.occ == 4) {                                                                        \
+          if (fused) strip_launch<T, NN, 2, true, true, 4>(nb, A, s);                             \
+          else strip_launch<T, NN, 2, false, true, 4>(nb, A, s);                                  \
+          break;                                                                                  \
+        }                                                                                         \
+      }                                                                                           \
+      if (fused) strip_launch<T, NN, 2, true, true>(nb, A, s);                                    \
+      else strip_launch<T, NN, 2, false, true>(nb, A, s);                                         \
     } else {                                                                                      \
-      if (fused) k_elem_strip<T, NN, 2, true><<<nb, strip_warps() * 32, 0, s>>>(A);               \
-      else k_elem_strip<T, NN, 2, false><<<nb, strip_warps() * 32, 0, s>>>(A);                    \
+      if (fused) strip_launch<T, NN, 2, true, false>(nb, A, s);                                   \
+      else strip_launch<T, NN, 2, false, false>(nb, A, s);                                        \
     }                                                                                             \
   } break;
   switch (G.N) {
@@ -649,7 +892,7 @@ template <typename T>
 inline int launch_strip_fold(const StripGeom& G, T* f, const T* halo_x, const T* halo_z, size_t npoin,
                              cudaStream_t s) {
   const int nsh = (G.nseg_lo > 0 ? G.nseg_lo - 1 : 0) + (G.nseg - G.nseg_lo - 1);
-  const long long nh = (long long)(G.ngroups - 1) * G.LZ + (long long)nsh * G.LX;
+  const long long nh = (long long)(G.ngroups - 1) * nsh + (long long)nsh * G.LX;
   if (nh <= 0) return 0;
   k_strip_fold<T><<<(unsigned)((nh + 255) / 256), 256, 0, s>>>(G, f, halo_x, halo_z, npoin);
   S2D_CUDA(cudaGetLastError());

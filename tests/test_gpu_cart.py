@@ -93,6 +93,58 @@ def test_synthetic_benchmark_family(scheme, stacey, nx, nz, ezflt):
     o.close()
 
 
+@pytest.mark.parametrize("ngll,nx,nz,ezflt", [(5, 19, 13, 6), (6, 11, 9, 4), (9, 7, 8, 0)])
+def test_compact_coefficients_equal_stored_planes(ngll, nx, nz, ezflt):
+    """coef_mode 0 keeps (lambda, mu) per GLL point and forms the six planes of MAT_ELAST_init_a
+    (mat_elastic.f90:334-340,355-357) in registers; coef_mode 1 stores them.  Same sequence of
+    roundings: planes, forces and a whole run are BITWISE equal between the two."""
+    xl, zl = (0.0, nx * 100.0), (0.0, nz * 130.0)   # non-square elements: KD2's a4*(..) shortcut differs from KD1
+    es = [CartEngine(ngll, 2, nx, nz, xl, zl, ezflt=ezflt, seed=SEED, coef_mode=m) for m in (0, 1)]
+    planes = [e.get_tables(ibool=False, a=True, rmass=False)[1] for e in es]
+    assert np.array_equal(planes[0], planes[1])
+    d = np.random.default_rng(11).standard_normal(es[0].npoin * 2)
+    out = []
+    for e in es:
+        for side in (1, 2, 3, 4):
+            e.add_abso_side(side)
+        e.commit()
+        e.set_fields(d * 1e-3, d)
+        f0 = e.compute_fint()
+        e.step(40, None)
+        out.append((f0,) + tuple(e.get_fields()))
+        e.close()
+    for x, y in zip(*out):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("coef_mode", [0, 1])
+def test_accel_policy_and_modes(coef_mode, monkeypatch):
+    """fields%accel is materialised on the last step of every s2d_step call (S2D_STORE_ACCEL=2, the
+    default) -- the same values as when it is written on every step, for either coefficient mode."""
+    nx, nz, nsteps = 24, 16, 60
+    o = orc.Oracle(harness.cart_deck(nx, nz, ezflt=8, nsteps=nsteps), synthetic_seed=SEED, renumber=False)
+    tab = np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)])
+    o.step(nsteps)
+    res = []
+    for policy in ("2", "1"):
+        monkeypatch.setenv("S2D_STORE_ACCEL", policy)
+        e = CartEngine(5, 2, nx, nz, (0.0, nx * 100.0), (0.0, nz * 100.0), ezflt=8, seed=SEED, coef_mode=coef_mode)
+        e.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, nx * 50.0, harness.nuc_radius(nx), nt_max=nsteps)
+        for side in (1, 2, 3, 4):
+            e.add_abso_side(side)
+        e.add_force_at(0.37 * nx * 100, 0.61 * nz * 100, [o.f("src.0.dir1"), o.f("src.0.dir2")])
+        e.commit()
+        e.step(25, tab[:25])
+        e.step(nsteps - 25, tab[25:])
+        res.append(e.get_fields())
+        e.close()
+    for x, y in zip(*res):
+        assert np.array_equal(x, y)
+    for x, k in zip(res[0], ("d", "v", "acc")):
+        assert rel_l2(x, o.arr(k)) <= 1e-10, k
+    o.close()
+
+
 def test_fp32_builder():
     nx, nz, nsteps = 24, 16, 100
     o = orc.Oracle(harness.cart_deck(nx, nz, nsteps=nsteps, abso=(1, 2, 3, 4)), synthetic_seed=SEED, renumber=False)
