@@ -174,7 +174,6 @@ class Engine : public EngineBase {
   int store_accel = env_int("S2D_STORE_ACCEL", 2);
   int strip_prefetch = env_int("S2D_STRIP_PF", 1);
   int strip_occ = env_int("S2D_STRIP_OCC", 0);
-  int strip_stage = env_int("S2D_STAGE", 7);
   std::vector<uint8_t> h_rowflag, h_colflag;
   std::vector<std::vector<int32_t>> h_bc_nodes;  // node lists of every boundary condition (for the flags)
   DevBuf<uint8_t> rowflag, colflag;
@@ -233,7 +232,6 @@ class Engine : public EngineBase {
     io.prefetch = strip_prefetch;
     io.compact = cart_compact;
     io.occ = strip_occ;
-    io.stage = strip_stage;
     io.cdx = cart_cdx;
     io.cdz = cart_cdz;
     io.cdet = cart_cdet;

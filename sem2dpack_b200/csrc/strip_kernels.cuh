@@ -165,7 +165,6 @@ struct StripArgs {
   int* meet;                // [nseg][ngroups-1] arrival counters of the group-boundary columns (zero between launches)
   T dt;
   int prefetch;             // L2 prefetch of what is not staged
-  int stage;                // what goes through the shared-memory staging area (bits: 1 d, 2 coefficients, 4 v+rmass)
   T H[N * N];               // hprime, column-major (constant bank)
   // compact coefficient mode (isotropic flat grids): only (lambda, mu) are stored per GLL point and
   // the six planes of MAT_ELAST_init_a (mat_elastic.f90:334-340,355-357) are formed in registers,
@@ -197,6 +196,9 @@ __device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_g
 template <int NPEND>
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
+#ifndef S2D_STRIP_STAGE
+#define S2D_STRIP_STAGE 7
+#endif
 constexpr int strip_warps() { return 4; }
 constexpr int STRIP_MASK_WORDS = 128;  // a band has at most 32*128 lattice rows (s2d_cart_create clamps SEG)
 // bytes of the staging area of one warp: coefficient vectors and displacement rows of one element
@@ -312,10 +314,12 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     for (int j = 0; j < N; ++j) nW[j] = -mul_rn(A.cdet, mul_rn(A.wg[i], A.wg[j]));
   }
 
-  // loads of one element row: displacement rows j = 1..N-1 and the coefficient vectors.  A.stage
-  // selects what goes through the staging area (bit 0: displacements, 1: coefficients, 2: v and
-  // rmass of the fused update); the rest is loaded straight into registers when it is needed.
-  const bool stg_u = A.stage & 1, stg_c = A.stage & 2, stg_v = A.stage & 4;
+  // loads of one element row: displacement rows j = 1..N-1 and the coefficient vectors.
+  // S2D_STRIP_STAGE (compile time) selects what goes through the staging area (bit 0:
+  // displacements, 1: coefficients, 2: v and rmass of the fused update); the rest is loaded straight
+  // into registers when it is needed.  Measured on B200, 4096^2 FP64 compact: 7 -> 6.45 ms,
+  // 5 -> 6.59, 4 -> 6.83, 1 -> 6.88, 0 -> 7.11 ms per launch.
+  constexpr bool stg_u = S2D_STRIP_STAGE & 1, stg_c = S2D_STRIP_STAGE & 2, stg_v = S2D_STRIP_STAGE & 4;
   auto issue_row = [&](int ezr, const V2* cpr) {
     const size_t rb = (size_t)strip_lat_row(G, ezr, 0) * LX;
     if (stg_u) {
@@ -805,7 +809,6 @@ struct StripIO {
   int* meet = nullptr;
   double dt = 0.0;
   int prefetch = 1;
-  int stage = 7;
   // compact coefficient mode (coef holds lambda, mu only)
   int compact = 0;
   int occ = 0;              // resident CTAs per SM the kernel is compiled for (0 = default)
@@ -847,7 +850,6 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
     A.meet = io.meet;                                                                             \
     A.dt = (T)io.dt;                                                                              \
     A.prefetch = io.prefetch;                                                                     \
-    A.stage = io.stage;                                                                           \
     for (int k = 0; k < NN * NN; ++k) A.H[k] = (T)io.hprime[k];                                   \
     A.cdx = (T)io.cdx;                                                                            \
     A.cdz = (T)io.cdz;                                                                            \
