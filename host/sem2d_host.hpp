@@ -1,0 +1,494 @@
+// C++ host side of the B200 time-stepping path: the reference's module API for this path
+// (problem_type, read_main, init_main, solve, REC_store/REC_write, BC_write, IO_abort), with the same
+// names, argument meaning and error behaviour, over the C-ABI of include/sem2d_b200.h.
+//
+// The reference is a Fortran program (no Fortran compiler exists in the build image, SURVEY.md
+// header), so this layer is what a maintainer's ISO_C_BINDING shim looks like when
+// written in C++.  Scope = what the device-side structured builder provides: &MESH_CART boxes with
+// one ELAST material, ABSORB sides, the split-node DYNFLT of `ezflt` with slip weakening, FORCE
+// sources, REC_LINE stations at nodes, leapfrog and Newmark.  Anything else in a Par.inp is
+// refused with IO_abort, never silently ignored -- except plotting (&SNAP_*), which is not on the path.
+//
+//   reference                                           here
+//   read_main   SRC/input.f90:12-63                     read_main(pb, "Par.inp")
+//   init_main   SRC/init.f90:16-131                     init_main(pb)        (builds the problem in HBM)
+//   solve       SRC/solver.f90:20-35                    solve(pb, nsteps)    (nsteps passes of main.f90:51-99)
+//   REC_store   SRC/receivers.f90:309-344               inside solve (device), REC_fetch copies rec%sis back
+//   REC_write   SRC/receivers.f90:351-392               REC_write(rec)       Ux/Uy/Uz_sem2d.dat (SEP), header
+//   BC_write    SRC/bc_gen.f90:313-337                  inside solve (device), BC_DYNFLT_flush writes the files
+//   IO_abort    SRC/stdio.f90:205-214                   throws io_abort; main prints and stops
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../include/sem2d_b200.h"
+#include "namelist.hpp"
+#include "stf.hpp"
+
+namespace sem2d {
+
+struct io_abort : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+[[noreturn]] inline void IO_abort(const std::string& msg) { throw io_abort(msg); }
+
+// timescheme_type (SRC/time.f90:5-11)
+struct timescheme_type {
+  std::string kind = "leapfrog";
+  double dt = 0.0, courant = 0.5, total = 0.0, time = 0.0;
+  double alpha = 1.0, beta = 0.0, gamma = 0.5;
+  int nt = 0;
+};
+
+// source_type with a so_force_type mechanism (SRC/src_gen.f90:17-27, SRC/src_force.f90:9-12)
+struct source_type {
+  double coord[2] = {0, 0};
+  double tdelay = 0.0;
+  stf_type stf;
+  double dir[2] = {0, 1};
+  int32_t id = -1;
+};
+
+// rec_type (SRC/receivers.f90:9-20)
+struct rec_type {
+  int number = 0, isamp = 1, nx = 0, nt = 0;
+  char SeisField = 'V', irepr = 'D';
+  bool AtNode = true;
+  double first[2] = {0, 0}, last[2] = {0, 0};
+  double tsamp = 0.0;
+  std::vector<double> coord;  // (2,nx)
+  std::vector<float> sis;     // (nt,nx,ndof)
+};
+
+// bc_type (SRC/bc_gen.f90:29-41), the kinds this host hands to the device
+struct bc_type {
+  int tag[2] = {0, 0};
+  std::string kind;
+  bool stacey = false;  // &BC_ABSORB
+  // &BC_DYNFLT / &BC_DYNFLT_SWF (SRC/bc_dynflt.f90:63-229, SRC/bc_dynflt_swf.f90:30-140)
+  double Tn = 0, Tt = 0, Tt_nuc = 0, x_nuc = 0, half_nuc = -1, Dc = 0.5, MuS = 0.6, MuD = 0.5;
+  int oxi[3] = {1, 2147483647, 1};
+  double ot1 = 0.0, otd = 0.0;
+  int32_t fault_id = -1;
+  int np = 0, oitd = 1;
+};
+
+// problem_type (SRC/problem_class.f90:19-46): what the host keeps; fields, operator data and boundary
+// tables live in HBM behind pb.gpu
+struct problem_type {
+  s2d_handle gpu = nullptr;
+  int iexec = 0, ngll = 9, ndof = 2, ItInfo = 100;
+  std::string title;
+  // &MESH_CART
+  double xlim[2] = {0, 0}, zlim[2] = {0, 0};
+  int nelem[2] = {0, 0}, ezflt = 0;
+  // &MAT_ELASTIC
+  double rho = 0, cp = 0, cs = 0;
+  timescheme_type time;
+  std::vector<bc_type> bc;
+  std::vector<source_type> src;
+  std::unique_ptr<rec_type> rec;
+  int64_t npoin = 0, nelem_total = 0;
+  int it = 0;
+  int precision = 8, device = -1;
+  ~problem_type() {
+    if (gpu) s2d_destroy(gpu);
+  }
+};
+
+inline void s2d_check(const problem_type& pb, int rc, const char* where) {
+  if (rc == S2D_OK) return;
+  const char* m = pb.gpu ? s2d_last_error(pb.gpu) : "";
+  IO_abort(std::string(where) + ": " + (m && *m ? m : "device call failed") + " (code " + std::to_string(rc) + ")");
+}
+
+// the list-directed records that follow a distribution block: the first `n` numbers after the
+// closing '/' of the first `group` in the file (SRC/distribution_pwconr.f90:58-66)
+inline std::vector<double> trailing_numbers(const std::string& file, const std::string& group, int n);
+
+// ---------------------------------------------------------------------------------------------
+// read_main (SRC/input.f90:12-63): &GENERAL, MESH_read, MAT_read, BC_read, TIME_read, SO_read, REC_read
+inline void read_main(problem_type& pb, const std::string& file) {
+  namelist_file in(file);
+  long k = in.find("GENERAL");
+  if (k < 0) IO_abort("GENERAL parameters not found");
+  {
+    const nml_group& g = in.at((size_t)k);  // SRC/input.f90:64-100
+    pb.iexec = g.integer("iexec", 0);
+    pb.ndof = g.integer("ndof", 2);
+    pb.ngll = g.integer("ngll", 9);
+    pb.ItInfo = g.integer("itinfo", 100);
+    pb.title = g.text("title", "");
+    if (pb.ndof > 2 || pb.ndof < 1) IO_abort("GENERAL input block: ndof must be 1 or 2 (SH or P-SV)");
+    if (pb.ngll <= 0) IO_abort("GENERAL input block: ngll must be positive");
+    if (pb.ItInfo <= 0) IO_abort("GENERAL input block: itInfo must be positive");
+    if (g.has("w")) IO_abort("GENERAL: finite seismogenic width W (2.5D) is not provided by the B200 path");
+  }
+  // MESH_read (SRC/mesh_gen.f90:61-100), CART_read (SRC/mesh_cartesian.f90:82-170)
+  k = in.find("MESH_DEF");
+  if (k < 0) IO_abort("MESH_read: MESH_DEF input block not found");
+  if (in.at((size_t)k).text("method", "") != "CARTESIAN")
+    IO_abort("MESH_read: only method='CARTESIAN' is provided by the B200 structured builder");
+  k = in.find("MESH_CART", (size_t)k);
+  if (k < 0) IO_abort("CART_read: MESH_CART input block not found");
+  {
+    const nml_group& g = in.at((size_t)k);
+    if (g.count("xlim") < 2 || g.count("zlim") < 2 || g.count("nelem") < 2) IO_abort("CART_read: xlim, zlim and nelem are required");
+    for (int q = 0; q < 2; ++q) {
+      pb.xlim[q] = g.real8("xlim", 0, q);
+      pb.zlim[q] = g.real8("zlim", 0, q);
+      pb.nelem[q] = g.integer("nelem", 0, q);
+    }
+    pb.ezflt = g.integer("ezflt", 0);
+    if (g.has("fztag") || g.has("fznz") || g.has("splitd")) IO_abort("CART_read: fztag / FZnz / splitD are not provided by the B200 path");
+    if (pb.ezflt < 0) IO_abort("CART_read: ezflt = -1 (fault at mid height) needs an even nelem(2)");
+  }
+  // MAT_read (SRC/mat_gen.f90:119-189): one ELAST material
+  k = in.find("MATERIAL");
+  if (k < 0) IO_abort("MAT_read: no MATERIAL block");
+  if (in.find("MATERIAL", (size_t)k + 1) >= 0) IO_abort("MAT_read: a single material is provided by the B200 structured builder");
+  {
+    const nml_group& g = in.at((size_t)k);
+    if (g.count("kind") != 1 || g.text("kind", "") != "ELAST") IO_abort("MAT_read: only kind='ELAST' is provided here");
+    const long m = in.find("MAT_ELASTIC", (size_t)k);
+    if (m < 0) IO_abort("MAT_ELAST_read: MAT_ELASTIC input block not found");
+    const nml_group& e = in.at((size_t)m);  // SRC/mat_elastic.f90:104-129
+    if (e.has("cph") || e.has("csh") || e.has("rhoh") || e.has("c11")) IO_abort("MAT_ELAST_read: distributions / anisotropy are not provided here");
+    pb.rho = e.real8("rho", 0.0);
+    pb.cp = e.real8("cp", 0.0);
+    pb.cs = e.real8("cs", 0.0);
+    if (!(pb.rho > 0 && pb.cp > 0 && pb.cs > 0)) IO_abort("MAT_ELAST_read: rho, cp, cs must be positive");
+  }
+  // BC_read (SRC/bc_gen.f90:98-188): in input order
+  for (long b = in.find("BC_DEF"); b >= 0; b = in.find("BC_DEF", (size_t)b + 1)) {
+    const nml_group& g = in.at((size_t)b);
+    bc_type bc;
+    bc.kind = g.text("kind", "");
+    if (g.has("tags")) {
+      bc.tag[0] = g.integer("tags", 0, 0);
+      bc.tag[1] = g.integer("tags", 0, 1);
+    } else {
+      bc.tag[0] = g.integer("tag", 0);
+    }
+    const long nxt = in.find("BC_DEF", (size_t)b + 1);
+    auto sub = [&](const char* name) -> const nml_group* {
+      const long s = in.find(name, (size_t)b);
+      return (s >= 0 && (nxt < 0 || s < nxt)) ? &in.at((size_t)s) : nullptr;
+    };
+    if (bc.kind == "ABSORB") {  // SRC/bc_abso.f90:62-110
+      if (const nml_group* a = sub("BC_ABSORB")) {
+        bc.stacey = a->logical("stacey", false);
+        if (a->logical("let_wave", true) == false) { /* only matters with an incident wave source */ }
+      }
+      if (bc.tag[0] < 1 || bc.tag[0] > 4) IO_abort("BC_read: ABSORB tag must be a side of the box (1..4)");
+    } else if (bc.kind == "DYNFLT") {
+      if (!(bc.tag[0] == 5 && bc.tag[1] == 6)) IO_abort("BC_read: DYNFLT is provided on the split-node fault tags=5,6 of MESH_CART ezflt");
+      const nml_group* f = sub("BC_DYNFLT");
+      if (!f) IO_abort("BC_DYNFLT_read: BC_DYNFLT input block not found");
+      if (f->text("friction", "SWF") != "SWF" || f->count("friction") > 1) IO_abort("BC_DYNFLT_read: only friction='SWF' is provided here");
+      bc.Tn = f->real8("tn", 0.0);
+      bc.Tt = bc.Tt_nuc = f->real8("tt", 0.0);
+      for (int q = 0; q < 3; ++q) bc.oxi[q] = f->integer("oxi", bc.oxi[q], q);
+      bc.ot1 = f->real8("ot1", 0.0);
+      bc.otd = f->real8("otd", 0.0);
+      if (f->has("tth")) {  // DIST_PWCONR with two zones around ref (SRC/distribution_pwconr.f90:40-85)
+        if (f->text("tth", "") != "PWCONR") IO_abort("BC_DYNFLT_read: TtH: only 'PWCONR' with num=2 is provided here");
+        const nml_group* d = sub("DIST_PWCONR");
+        if (!d || d->integer("num", 0) != 2) IO_abort("DIST_PWCONR: num=2 expected");
+        bc.x_nuc = d->real8("ref", 0.0, 0);
+        // the radius and the two values follow the block as list-directed records
+        std::vector<double> v = trailing_numbers(file, "DIST_PWCONR", 3);
+        bc.half_nuc = v[0];
+        bc.Tt_nuc = v[1];
+        bc.Tt = v[2];
+      }
+      for (const char* key : {"tnh", "sxx", "sxz", "szz", "cohesion", "v", "opening"})
+        if (f->has(key)) IO_abort(std::string("BC_DYNFLT_read: '") + key + "' is not provided here");
+      const nml_group* w = sub("BC_DYNFLT_SWF");
+      if (!w) IO_abort("BC_DYNFLT_SWF input block not found");
+      if (w->integer("kind", 1) != 1 || w->logical("healing", false)) IO_abort("BC_DYNFLT_SWF: only kind=1 without healing is provided here");
+      bc.Dc = w->real8("dc", 0.5);
+      bc.MuS = w->real8("mus", 0.6);
+      bc.MuD = w->real8("mud", 0.5);
+      for (const char* key : {"dch", "mush", "mudh", "alpha", "alphah", "p"})
+        if (w->has(key)) IO_abort(std::string("BC_DYNFLT_SWF: '") + key + "' is not provided here");
+    } else {
+      IO_abort("BC_read: boundary kind '" + bc.kind + "' is not provided by the B200 structured builder (ABSORB, DYNFLT are)");
+    }
+    pb.bc.push_back(bc);
+  }
+  // TIME_read (SRC/time.f90:122-230)
+  k = in.find("TIME");
+  if (k < 0) IO_abort("TIME parameters not found");
+  {
+    const nml_group& g = in.at((size_t)k);
+    timescheme_type& t = pb.time;
+    t.kind = g.text("kind", "leapfrog");
+    int NbSteps = g.integer("nbsteps", 0);
+    t.dt = g.real8("dt", 0.0);
+    t.courant = g.real8("courant", 0.5);
+    double TotalTime = g.real8("totaltime", 0.0);
+    if (NbSteps < 0) IO_abort("TIME: NbSteps must be positive");
+    if (t.dt < 0.0) IO_abort("TIME: Dt must be positive");
+    if (t.courant < 0.0 || t.courant > 0.6) IO_abort("TIME: Courant out of range [0,0.6]");
+    if (TotalTime < 0.0) IO_abort("TIME: TotalTime must be positive");
+    if (NbSteps * TotalTime != 0.0) IO_abort("TIME: bad combination of settings, NbSteps or TotalTime");
+    if (t.dt > 0.0) {
+      if (TotalTime > 0.0) NbSteps = (int)std::ceil(TotalTime / t.dt);
+      TotalTime = t.dt * NbSteps;
+    }
+    t.nt = NbSteps;
+    t.total = TotalTime;
+    if (t.kind == "newmark") {
+      const long m = in.find("TIME_NEWMARK", (size_t)k);
+      if (m >= 0) {
+        t.beta = in.at((size_t)m).real8("beta", 0.0);
+        t.gamma = in.at((size_t)m).real8("gamma", 0.5);
+      }
+      if (t.beta != 0.0) IO_abort("TIME: only the explicit Newmark scheme (beta=0) is on the B200 path");
+    } else if (t.kind != "leapfrog") {
+      IO_abort("TIME: scheme '" + t.kind + "' is not provided by the B200 path (leapfrog, newmark are)");
+    }
+  }
+  // SO_read (SRC/src_gen.f90:126-214)
+  for (long s = in.find("SRC_DEF"); s >= 0; s = in.find("SRC_DEF", (size_t)s + 1)) {
+    const nml_group& g = in.at((size_t)s);
+    source_type so;
+    if (g.has("file")) IO_abort("SO_read: source positions from a file are not provided here");
+    if (g.count("coord") < 2) IO_abort("SO_read: coord is required");
+    so.coord[0] = g.real8("coord", 0, 0);
+    so.coord[1] = g.real8("coord", 0, 1);
+    so.tdelay = g.real8("delay", 0.0);
+    if (g.text("mechanism", "") != "FORCE") IO_abort("SO_read: only mechanism='FORCE' is provided here");
+    so.stf = STF_read(g.text("stf", ""), in, (size_t)s);
+    const long m = in.find("SRC_FORCE", (size_t)s);  // SRC/src_force.f90:40-58
+    const double PI = 3.141592653589793238462643383279502884197;
+    const double angle = (m >= 0 ? in.at((size_t)m).real8("angle", 0.0) : 0.0) * PI / 180.0;
+    so.dir[0] = -std::sin(angle);
+    so.dir[1] = std::cos(angle);
+    pb.src.push_back(so);
+  }
+  // REC_read (SRC/receivers.f90:62-140)
+  k = in.find("REC_LINE");
+  if (k >= 0) {
+    const nml_group& g = in.at((size_t)k);
+    pb.rec.reset(new rec_type());
+    rec_type& r = *pb.rec;
+    r.number = g.integer("number", 0);
+    r.isamp = g.integer("isamp", 1);
+    r.SeisField = g.text("field", "V")[0];
+    r.AtNode = g.logical("atnode", true);
+    r.irepr = g.text("irepr", "D")[0];
+    if (r.number < 0) IO_abort("REC_read: \"number\" must be positive");
+    if (r.SeisField != 'D' && r.SeisField != 'V' && r.SeisField != 'A') IO_abort("REC_read: parameter field has wrong value [D,V,A]");
+    if (g.text("file", "none") != "none") IO_abort("REC_read: station files are not provided here");
+    if (!r.AtNode) IO_abort("REC_read: AtNode=F (interpolated stations) is provided by the generic C-ABI, not by this host");
+    if (g.count("first") < 2 || g.count("last") < 2) IO_abort("REC_read: first and last are required");
+    for (int q = 0; q < 2; ++q) {
+      r.first[q] = g.real8("first", 0, q);
+      r.last[q] = g.real8("last", 0, q);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// init_main (SRC/init.f90:16-131): mesh, numbering, operator data, mass, dt, boundaries, sources and
+// receivers -- built on the device by the structured builder, in the order init_main uses
+inline void init_main(problem_type& pb) {
+  s2d_cart_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.ngll = pb.ngll;
+  d.ndof = pb.ndof;
+  d.nx = pb.nelem[0];
+  d.nz = pb.nelem[1];
+  d.ezflt = pb.ezflt;
+  d.x0 = pb.xlim[0];
+  d.x1 = pb.xlim[1];
+  d.z0 = pb.zlim[0];
+  d.z1 = pb.zlim[1];
+  d.seed = 0;
+  d.rho = pb.rho;
+  d.cp = pb.cp;
+  d.cs = pb.cs;
+  d.precision = pb.precision;
+  d.scheme.kind = pb.time.kind == "newmark" ? 1 : 0;
+  d.scheme.dt = pb.time.dt;
+  d.scheme.beta = pb.time.beta;
+  d.scheme.gamma = pb.time.gamma;
+  d.scheme.alpha = pb.time.alpha;
+  d.courant = pb.time.courant;
+  d.device = pb.device;
+  const int rc = s2d_cart_create(&pb.gpu, &d);
+  if (rc == S2D_ENODEV) IO_abort("init_main: no CUDA device (the B200 path has no CPU fallback)");
+  if (rc != S2D_OK) IO_abort("init_main: s2d_cart_create failed (code " + std::to_string(rc) + ")");
+  double dt = 0;
+  s2d_check(pb, s2d_cart_info(pb.gpu, &pb.npoin, &pb.nelem_total, &dt), "init_main");
+  // TIME_init (SRC/time.f90:323-341)
+  timescheme_type& t = pb.time;
+  if (!(t.dt > 0.0)) {
+    t.dt = dt;
+    if (t.total > 0.0) t.nt = (int)std::ceil(t.total / t.dt);
+    t.total = t.nt * t.dt;
+  }
+  // BC_init (SRC/bc_gen.f90:190-251): input order
+  for (bc_type& bc : pb.bc) {
+    if (bc.kind == "ABSORB") {
+      s2d_check(pb, s2d_cart_add_abso(pb.gpu, bc.tag[0], bc.stacey ? 1 : 0), "BC_ABSO_init");
+    } else {  // DYNFLT
+      bc.oitd = std::max(1, (int)std::lround(bc.otd / t.dt));  // SRC/bc_dynflt.f90:452-456
+      if (std::lround(bc.ot1 / t.dt) != 0) IO_abort("BC_DYNFLT_init: ot1 > 0 is not provided here");
+      const int np = pb.nelem[0] * (pb.ngll - 1) + 1;
+      if (!(bc.oxi[0] <= 1 && bc.oxi[1] >= np)) IO_abort("BC_DYNFLT_init: oxi must span the whole fault here (stride only)");
+      s2d_check(pb, s2d_cart_add_fault_swf(pb.gpu, bc.Dc, bc.MuS, bc.MuD, bc.Tn, bc.Tt, bc.Tt_nuc, bc.x_nuc, bc.half_nuc,
+                                           bc.oxi[2], bc.oitd, t.nt, &bc.fault_id),
+                "BC_DYNFLT_init");
+      bc.np = np;
+    }
+  }
+  // SO_init (SRC/src_gen.f90:216-262): nearest node
+  for (source_type& so : pb.src)
+    s2d_check(pb, s2d_cart_add_force(pb.gpu, so.coord[0], so.coord[1], so.dir, &so.id), "SO_init");
+  // REC_init (SRC/receivers.f90:143-226)
+  if (pb.rec) {
+    rec_type& r = *pb.rec;
+    r.nt = t.nt / r.isamp + 1;  // receivers.f90:172
+    r.tsamp = t.dt * r.isamp;
+    s2d_check(pb, s2d_cart_add_receivers(pb.gpu, r.number, r.first[0], r.first[1], r.last[0], r.last[1], r.SeisField,
+                                         r.isamp, r.nt),
+              "REC_init");
+    int32_t nx = 0;
+    s2d_check(pb, s2d_cart_receiver_info(pb.gpu, &nx, nullptr), "REC_init");
+    r.nx = nx;
+    r.coord.resize(2 * (size_t)nx);
+    s2d_check(pb, s2d_cart_receiver_info(pb.gpu, &nx, r.coord.data()), "REC_init");
+  }
+  s2d_check(pb, s2d_commit(pb.gpu, S2D_ASM_PATCH), "init_main");
+  pb.it = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// solve (SRC/solver.f90:20-35) + the per-step outputs of the main loop (SRC/main.f90:51-99):
+// nsteps passes on the device.  The source amplitudes are evaluated here as SO_add does
+// (SRC/src_gen.f90:300-303): stf(time - tdelay), time = it*dt.
+inline void solve(problem_type& pb, int nsteps = 1) {
+  std::vector<double> ampli;
+  const size_t ns = pb.src.size();
+  if (ns) {
+    ampli.resize(ns * (size_t)nsteps);
+    for (int k = 0; k < nsteps; ++k)
+      for (size_t s = 0; s < ns; ++s)
+        ampli[s + ns * (size_t)k] = STF_get(pb.src[s].stf, (pb.it + k + 1) * pb.time.dt - pb.src[s].tdelay);
+  }
+  s2d_check(pb, s2d_step(pb.gpu, nsteps, ns ? ampli.data() : nullptr, nullptr), "solve");
+  pb.it += nsteps;
+  pb.time.time = pb.it * pb.time.dt;
+}
+
+// rec%sis as REC_store has filled it up to now
+inline void REC_fetch(problem_type& pb) {
+  if (!pb.rec) return;
+  rec_type& r = *pb.rec;
+  r.sis.resize((size_t)r.nt * r.nx * pb.ndof);
+  s2d_check(pb, s2d_get_seis(pb.gpu, r.sis.data()), "REC_store");
+}
+
+// REC_init's header (SRC/receivers.f90:214-221) and REC_write's SEP files (:351-392): one direct-access
+// record of nt float32 per station, Uy for SH, Ux and Uz for P-SV
+inline void REC_write(const rec_type& r, int ndof, const std::string& dir = ".") {
+  auto path = [&](const char* n) { return dir + "/" + n; };
+  if (FILE* f = std::fopen(path("SeisHeader_sem2d.hdr").c_str(), "w")) {
+    std::fprintf(f, " DT NSAMP NSTA\n %.7E %d %d\n XSTA ZSTA\n", (double)(float)r.tsamp, r.nt, r.nx);
+    for (int k = 0; k < r.nx; ++k) std::fprintf(f, " %.16E %.16E\n", r.coord[2 * k], r.coord[2 * k + 1]);
+    std::fclose(f);
+  } else {
+    IO_abort("REC_write: cannot open SeisHeader_sem2d.hdr");
+  }
+  const char* names1[] = {"Uy_sem2d.dat"};
+  const char* names2[] = {"Ux_sem2d.dat", "Uz_sem2d.dat"};
+  for (int c = 0; c < ndof; ++c) {
+    const char* nm = ndof == 1 ? names1[0] : names2[c];
+    FILE* f = std::fopen(path(nm).c_str(), "wb");
+    if (!f) IO_abort(std::string("REC_write: cannot open ") + nm);
+    std::fwrite(r.sis.data() + (size_t)c * r.nt * r.nx, sizeof(float), (size_t)r.nt * r.nx, f);
+    std::fclose(f);
+  }
+}
+
+// The files BC_DYNFLT_init / BC_DYNFLT_write produce (SRC/bc_dynflt.f90:429-520,751-778):
+// FltXX_sem2d.hdr, FltXX_init_sem2d.tab, FltXX_sem2d.dat (sequential unformatted: every record framed
+// by its 4-byte length, as gfortran/ifort write it) and FltXX_potency_sem2d.tab (6D24.16 per call).
+inline void BC_DYNFLT_flush(problem_type& pb, const bc_type& bc, const std::string& dir = ".") {
+  int32_t np = 0;
+  s2d_check(pb, s2d_cart_fault_info(pb.gpu, &np, nullptr, nullptr, nullptr, nullptr), "BC_write");
+  std::vector<double> coord(2 * (size_t)np), T0(2 * (size_t)np), B(np);
+  double mu0 = 0;
+  s2d_check(pb, s2d_cart_fault_info(pb.gpu, &np, coord.data(), T0.data(), B.data(), &mu0), "BC_write");
+  const int oixd = bc.oxi[2], onx = (np - 1) / oixd + 1;
+  int32_t nout = 0, ncalls = 0;
+  s2d_check(pb, s2d_get_fault(pb.gpu, bc.fault_id, nullptr, &nout, nullptr, &ncalls), "BC_write");
+  std::vector<float> rec((size_t)nout * 6 * onx);
+  std::vector<double> pot((size_t)ncalls * 2 * (pb.ndof + 1));
+  s2d_check(pb, s2d_get_fault(pb.gpu, bc.fault_id, rec.data(), &nout, pot.data(), &ncalls), "BC_write");
+  char base[64];
+  std::snprintf(base, sizeof(base), "%s/Flt%02d", dir.c_str(), bc.tag[0]);
+  const std::string b(base);
+  if (FILE* f = std::fopen((b + "_sem2d.hdr").c_str(), "w")) {
+    std::fprintf(f, " NPTS NDAT NSAMP DELT\n %d %d %d %.16E\n", onx, 6, pb.time.nt / bc.oitd + 1, pb.time.dt * bc.oitd);
+    std::fprintf(f, " Slip:Slip_Rate:Shear_Stress:Normal_Stress:Friction:T_stick\n XPTS ZPTS\n");
+    for (int i = 0; i < np; i += oixd) std::fprintf(f, " %.16E %.16E\n", coord[2 * i], coord[2 * i + 1]);
+    std::fclose(f);
+  }
+  if (FILE* f = std::fopen((b + "_init_sem2d.tab").c_str(), "w")) {
+    for (int i = 0; i < np; i += oixd) std::fprintf(f, " %.16E %.16E %.16E %.16E\n", T0[i], T0[i + np], mu0, B[i]);
+    std::fclose(f);
+  }
+  if (FILE* f = std::fopen((b + "_sem2d.dat").c_str(), "wb")) {
+    const int32_t len = (int32_t)(onx * sizeof(float));
+    for (int r = 0; r < nout * 6; ++r) {
+      std::fwrite(&len, 4, 1, f);
+      std::fwrite(rec.data() + (size_t)r * onx, sizeof(float), onx, f);
+      std::fwrite(&len, 4, 1, f);
+    }
+    std::fclose(f);
+  }
+  if (FILE* f = std::fopen((b + "_potency_sem2d.tab").c_str(), "w")) {
+    const int w = 2 * (pb.ndof + 1);
+    for (int c = 0; c < ncalls; ++c) {
+      for (int q = 0; q < w; ++q) std::fprintf(f, "%24.16E", pot[(size_t)c * w + q]);
+      std::fprintf(f, "\n");
+    }
+    std::fclose(f);
+  }
+}
+
+inline std::vector<double> trailing_numbers(const std::string& file, const std::string& group, int n) {
+  std::ifstream f(file);
+  std::string all((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  std::string up = all;
+  for (char& c : up) c = (char)std::toupper((unsigned char)c);
+  size_t p = up.find("&" + group);
+  if (p == std::string::npos) IO_abort(group + ": block not found");
+  p = all.find('/', p);
+  std::vector<double> v;
+  std::stringstream ss(all.substr(p + 1));
+  std::string tok;
+  while ((int)v.size() < n && ss >> tok) {
+    if (tok[0] == '&') break;
+    if (tok[0] == '#') {
+      std::string rest;
+      std::getline(ss, rest);
+      continue;
+    }
+    v.push_back(nml_group::to_double(tok));
+  }
+  if ((int)v.size() < n) IO_abort(group + ": missing list-directed records after the block");
+  return v;
+}
+
+}  // namespace sem2d

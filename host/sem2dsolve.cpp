@@ -1,0 +1,76 @@
+// sem2dsolve_b200 -- the reference's `program main` (SRC/main.f90:1-110) for the B200 path:
+// reads Par.inp from the working directory, builds the problem in HBM, runs the time loop on the
+// device and writes the reference's seismogram and fault files.
+//
+//   sem2dsolve_b200 [Par.inp] [--precision 4|8] [--device N] [--quiet]
+//
+// Exit code 0 on success; on IO_abort the message is printed as stdio.f90:205-214 does
+// ("FATAL ERROR" banner) and the exit code is 1.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "sem2d_host.hpp"
+
+using namespace sem2d;
+
+int main(int argc, char** argv) {
+  std::string file = "Par.inp";
+  bool quiet = false;
+  problem_type pb;
+  for (int a = 1; a < argc; ++a) {
+    const std::string s = argv[a];
+    if (s == "--precision" && a + 1 < argc) pb.precision = std::atoi(argv[++a]);
+    else if (s == "--device" && a + 1 < argc) pb.device = std::atoi(argv[++a]);
+    else if (s == "--quiet") quiet = true;
+    else file = s;
+  }
+  try {
+    const auto t0 = std::chrono::steady_clock::now();
+    read_main(pb, file);   // main.f90:27
+    init_main(pb);         // main.f90:31
+    const auto t1 = std::chrono::steady_clock::now();
+    if (!quiet) {
+      std::printf("\n Program  S P E C F E M : B200 time-stepping path\n %s\n", pb.title.c_str());
+      std::printf("   elements %lld  GLL nodes %lld  ngll %d  ndof %d\n", (long long)pb.nelem_total, (long long)pb.npoin, pb.ngll, pb.ndof);
+      std::printf("   Time step (secs)      = %.6E\n   Number of time steps  = %d\n   Total duration (secs) = %.6E\n",
+                  pb.time.dt, pb.time.nt, pb.time.total);
+      std::printf("   scheme %s\n", pb.time.kind.c_str());
+    }
+    if (pb.iexec == 0) {  // check mode stops after the set-up (main.f90:66)
+      std::printf(" iexec=0: problem checked, not solved\n");
+      return 0;
+    }
+    // main.f90:51-99: the loop body runs on the device in chunks that end on the ItInfo lines
+    while (pb.it < pb.time.nt) {
+      const int n = std::min(pb.ItInfo - pb.it % pb.ItInfo, pb.time.nt - pb.it);
+      solve(pb, n);
+      if (pb.it % pb.ItInfo == 0 && !quiet) {
+        double vmax = 0, dmax = 0;
+        s2d_check(pb, s2d_progress(pb.gpu, &vmax, &dmax), "main");
+        std::printf("Timestep #%8d  t = %11.4E  vmax = %11.4E  dmax = %11.4E\n", pb.it, pb.time.time, vmax, dmax);
+      }
+    }
+    const auto t2 = std::chrono::steady_clock::now();
+    if (pb.rec) {  // main.f90:104
+      REC_fetch(pb);
+      REC_write(*pb.rec, pb.ndof);
+    }
+    for (const bc_type& bc : pb.bc)
+      if (bc.kind == "DYNFLT") BC_DYNFLT_flush(pb, bc);
+    if (!quiet) {
+      const double ti = std::chrono::duration<double>(t1 - t0).count(), ts = std::chrono::duration<double>(t2 - t1).count();
+      std::printf("\n---  TIME (in seconds) :\n  initialization . . %.3E\n  per timestep . . . %.3E\n  total solver . . . %.3E\n",
+                  ti, ts / std::max(pb.time.nt, 1), ts);
+      std::printf("  GLL DOF-updates/s  %.3E\n", (double)pb.npoin * pb.ndof * pb.time.nt / ts);
+    }
+  } catch (const io_abort& e) {  // IO_abort (stdio.f90:205-214)
+    std::printf("\n%s\n FATAL ERROR\n %s\n%s\n", std::string(50, '*').c_str(), e.what(), std::string(50, '*').c_str());
+    return 1;
+  } catch (const std::exception& e) {
+    std::printf("\n FATAL ERROR\n %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

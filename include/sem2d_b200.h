@@ -235,6 +235,13 @@ int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, doub
 int s2d_cart_add_force(s2d_handle h, double x, double z, const double dir[2], int32_t* src_id);
 int s2d_cart_add_receivers(s2d_handle h, int32_t nx, double xa, double za, double xb, double zb,
                            char field, int32_t isamp, int32_t nt_rec);
+/* the split-node fault as BC_DYNFLT_init leaves it (bc_dynflt.f90:392-458): node count, bc%coord(2,np),
+ * bc%T0(np,2), bc%B(np,1) and the initial friction coefficient -- what FltXX_sem2d.hdr and
+ * FltXX_init_sem2d.tab hold.  Any pointer may be NULL. */
+int s2d_cart_fault_info(s2d_handle h, int32_t* np, double* coord, double* T0, double* B, double* mu0);
+/* number of stations kept (duplicates dropped, receivers.f90:255) and their relocated positions
+ * rec%coord(2,nx) (receivers.f90:231-303); coord may be NULL */
+int s2d_cart_receiver_info(s2d_handle h, int32_t* nx, double* coord);
 int s2d_cart_info(s2d_handle h, int64_t* npoin, int64_t* nelem, double* dt);
 /* Overrides the time step (time%dt) before any boundary is added.  x-strips of one global mesh
  * must agree on dt: the host takes the minimum of the per-strip Courant steps (the reference takes

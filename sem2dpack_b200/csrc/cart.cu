@@ -360,6 +360,11 @@ struct CartState {
   double H[100];
   bool mass_inverted = false;
   bool bc_added = false;
+  std::vector<double> fault_coord;  // (2, np) bc%coord of the split-node fault
+  std::vector<double> fault_T0;     // (np, 2), fault_B (np): initial tractions and node weights (FltXX_init_sem2d.tab)
+  std::vector<double> fault_B;
+  double fault_mu0 = 0.0;
+  std::vector<double> rec_coord;  // (2, nx) positions of the relocated stations (rec%coord, receivers.f90:231-303)
   int coef_mode = 0;  // 0 = compact (lambda, mu) where the rheology allows, 1 = all planes stored
   double CoefA2V() const { return scheme.kind == 1 ? scheme.gamma * scheme.dt : scheme.dt; }        // time.f90:443-456
   double CoefA2D() const { return scheme.kind == 1 ? scheme.beta * scheme.dt * scheme.dt : 0.0; }    // time.f90:426-440
@@ -744,6 +749,10 @@ int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, doub
     invM2[q] = 1.0 / m2[q];
     Z[q] = 1.0 / (A2V * B[q] * (invM1[q] + invM2[q]));  // bc_dynflt.f90:349-354
   }
+  S.fault_coord = coord;
+  S.fault_T0 = T0;
+  S.fault_B.assign(B.begin(), B.begin() + np);
+  S.fault_mu0 = MuS;
   s2d_dynflt_desc d;
   std::memset(&d, 0, sizeof(d));
   d.np = np;
@@ -806,9 +815,30 @@ int s2d_cart_add_receivers(s2d_handle h, int32_t nx, double xa, double za, doubl
     bool dup = false;
     if (ig.size() > 1)
       for (int v : ig) dup = dup || (v == id);
-    if (!dup) ig.push_back(id);
+    if (!dup) {
+      ig.push_back(id);
+      S.rec_coord.push_back(gx_of(G, ex, i));
+      S.rec_coord.push_back(gz_of(G, ez, j));
+    }
   }
   Eb->add_receivers((int)ig.size(), field, isamp, nt_rec, 1, ig.data(), nullptr, nullptr);
+  CART_GUARD_END
+}
+
+int s2d_cart_fault_info(s2d_handle h, int32_t* np, double* coord, double* T0, double* B, double* mu0) {
+  CART_GUARD_BEGIN
+  if (np) *np = (int32_t)(S.fault_coord.size() / 2);
+  if (coord) std::copy(S.fault_coord.begin(), S.fault_coord.end(), coord);
+  if (T0) std::copy(S.fault_T0.begin(), S.fault_T0.end(), T0);
+  if (B) std::copy(S.fault_B.begin(), S.fault_B.end(), B);
+  if (mu0) *mu0 = S.fault_mu0;
+  CART_GUARD_END
+}
+
+int s2d_cart_receiver_info(s2d_handle h, int32_t* nx, double* coord) {
+  CART_GUARD_BEGIN
+  if (nx) *nx = (int32_t)(S.rec_coord.size() / 2);
+  if (coord) std::copy(S.rec_coord.begin(), S.rec_coord.end(), coord);
   CART_GUARD_END
 }
 

@@ -1,0 +1,99 @@
+"""sem2dsolve_b200 -- the C++ host of the path (host/: read_main, init_main, solve, REC_write over the
+C-ABI) -- run as the reference's executable is run: a Par.inp in the working directory, output files
+in the reference's formats.  Checked DIRECTLY against the reference's own known-answer artefacts
+(no oracle in between) and, for the fault files, against the oracle.
+
+  TestSH        EXAMPLES/TestSH/uyref.mat + analyze_test.m          analytic, 2 % max-norm
+  LambsProblem  EXAMPLES/LambsProblem/U{x,z}_file_ascii + test.out   0.5 % max-norm, 4 recorded misfits
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import harness
+import orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "sem2dpack_b200", "lib", "sem2dsolve_b200")
+
+
+def run(tmp_path, deck_text, *args):
+    assert os.path.exists(EXE), "host program missing: run __graft_entry__.build()"
+    (tmp_path / "Par.inp").write_text(deck_text)
+    p = subprocess.run([EXE, *args], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    return p
+
+
+def read_sep(tmp_path, name):
+    """POST/sem2d_read_seis.m: header 'DT NSAMP NSTA', then one float32 record of NSAMP per station"""
+    hdr = (tmp_path / "SeisHeader_sem2d.hdr").read_text().split("\n")
+    dt, nsamp, nsta = hdr[1].split()
+    coord = np.array([[float(v) for v in ln.split()] for ln in hdr[3:3 + int(nsta)]])
+    u = np.fromfile(tmp_path / name, dtype=np.float32).reshape(int(nsta), int(nsamp)).T
+    return float(dt), coord, u
+
+
+def test_testsh_against_the_analytic_trace(tmp_path):
+    p = run(tmp_path, harness.deck("testsh"))
+    assert p.returncode == 0, p.stdout + p.stderr
+    dt, coord, u = read_sep(tmp_path, "Uy_sem2d.dat")
+    assert u.shape == (1988, 7) and abs(dt - 1.76209e-2) < 1e-6
+    assert np.allclose(coord[:, 0], np.linspace(0, 30, 7)) and np.allclose(coord[:, 1], 0)
+    uref = harness.refdata()["testsh_uref"]
+    err = np.abs(u[:, 4].astype(np.float64) - uref).max() / np.abs(uref).max()
+    assert err < 0.02, err   # analyze_test.m
+
+
+def test_lamb_against_the_recorded_misfits(tmp_path):
+    p = run(tmp_path, harness.deck("lamb"))
+    assert p.returncode == 0, p.stdout + p.stderr
+    g = harness.refdata()
+    _, _, ux = read_sep(tmp_path, "Ux_sem2d.dat")
+    _, _, uz = read_sep(tmp_path, "Uz_sem2d.dat")
+    uxa = np.vstack([np.zeros((1, 2)), g["lamb_ux"].reshape(2, -1).T])
+    uza = np.vstack([np.zeros((1, 2)), g["lamb_uz"].reshape(2, -1).T])
+    num = np.abs(np.hstack([ux - uxa, uz - uza])).max(axis=0)
+    den = np.abs(np.hstack([uxa, uza])).max(axis=0)
+    err = num / den
+    assert err.max() < 0.005
+    assert np.allclose(err, g["lamb_misfits"], rtol=2e-3), (err, g["lamb_misfits"])
+
+
+def test_fault_files_against_the_oracle(tmp_path):
+    """a MESH_CART ezflt deck with the split-node slip-weakening fault: FltXX_sem2d.dat (sequential
+    unformatted records), the potency table and the seismograms equal the oracle's after the same
+    float32 cast"""
+    nx, nz, nsteps = 24, 16, 200
+    deck = harness.cart_deck(nx, nz, ezflt=8, nsteps=nsteps)
+    p = run(tmp_path, deck)
+    assert p.returncode == 0, p.stdout + p.stderr
+    o = orc.Oracle(deck, renumber=False)
+    o.step(nsteps)
+    _, _, ux = read_sep(tmp_path, "Ux_sem2d.dat")
+    ref = o.seis()
+    assert np.abs(ux - ref[:, :, 0]).max() <= 2e-7 * np.abs(ref).max()
+    hdr = (tmp_path / "Flt05_sem2d.hdr").read_text().split("\n")
+    npts, ndat, nsamp = (int(v) for v in hdr[1].split()[:3])
+    assert (npts, ndat, nsamp) == (o.i("bc.0.onx"), 6, nsteps + 1)
+    raw = np.fromfile(tmp_path / "Flt05_sem2d.dat", dtype=np.int32).reshape(nsamp, ndat, npts + 2)
+    assert (raw[:, :, 0] == 4 * npts).all() and (raw[:, :, -1] == 4 * npts).all()   # record markers
+    rec = raw[:, :, 1:-1].copy().view(np.float32)
+    want = o.arr("bc.0.out").reshape(-1, 6, npts)
+    for c in range(6):
+        assert np.abs(rec[:, c] - want[:, c]).max() <= 2e-7 * max(np.abs(want[:, c]).max(), 1e-30), c
+    assert rec[-1, 0].max() > 1e-3   # the fault did slip
+    pot = np.loadtxt(tmp_path / "Flt05_potency_sem2d.tab")
+    assert pot.shape == (nsteps + 1, 6)
+    o.close()
+
+
+def test_unsupported_input_aborts_like_io_abort(tmp_path):
+    """what the host does not provide is refused the way the reference refuses bad input: message +
+    non-zero exit (IO_abort, stdio.f90:205-214), never ignored"""
+    p = run(tmp_path, harness.deck("tpv3"))
+    assert p.returncode == 1 and "FATAL ERROR" in p.stdout and "MAT_read" in p.stdout
+    p = run(tmp_path, harness.deck("testsh").replace("courant = 0.3d0", "courant = 0.9d0"))
+    assert p.returncode == 1 and "Courant out of range" in p.stdout

@@ -1,0 +1,38 @@
+"""CPU checks of the C++ host program (host/): Par.inp reading and the reference's error behaviour.
+Everything that reaches the device is covered by tests/test_gpu_host_program.py."""
+import os
+import subprocess
+
+import harness
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "sem2dpack_b200", "lib", "sem2dsolve_b200")
+
+
+def run(tmp_path, text):
+    (tmp_path / "Par.inp").write_text(text)
+    return subprocess.run([EXE], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+
+
+def test_refusals_happen_while_reading_the_deck(tmp_path):
+    assert os.path.exists(EXE), "host program missing: run __graft_entry__.build()"
+    cases = [
+        (harness.deck("tpv3"), "MAT_read"),                                                    # ELAST + KV
+        (harness.deck("ratestate"), "CART_read"),                                              # fztag
+        (harness.deck("testsh").replace("courant = 0.3d0", "courant = 0.9d0"), "Courant out of range [0,0.6]"),
+        (harness.deck("testsh").replace("'RICKER'", "'BUTTERWORTH'"), "STF_read"),
+        (harness.deck("testsh").replace("kind = 'ABSORB'", "kind = 'PERIOD'", 1), "BC_read"),
+        (harness.deck("lamb").replace("TotalTime=1.5d0, Dt=0.5d-3", "TotalTime=1.5d0, NbSteps=10"), "bad combination"),
+        ("&GENERAL iexec=1 /\n", "MESH_DEF input block not found"),
+    ]
+    for text, needle in cases:
+        p = run(tmp_path, text)
+        assert p.returncode == 1 and "FATAL ERROR" in p.stdout and needle in p.stdout, (needle, p.stdout)
+
+
+def test_a_good_deck_gets_as_far_as_the_device(tmp_path):
+    """without a GPU the only possible failure of a supported deck is the missing device: there is no
+    CPU fallback behind the host program"""
+    p = run(tmp_path, harness.deck("lamb"))
+    if p.returncode != 0:
+        assert "no CUDA device" in p.stdout, p.stdout
