@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--fint-reps", type=int, default=10)
     ap.add_argument("--coef", choices=["compact", "full"], default="compact",
                     help="coefficient storage: (lambda, mu) per GLL point, or all six planes a(5,5,6) per element")
+    ap.add_argument("--halo", choices=["peer", "nccl"], default="peer",
+                    help="x-strip interface exchange: engine kernels writing into the neighbour's memory, or NCCL")
     ap.add_argument("--accel", choices=["last", "every"], default="last",
                     help="accelerations written on the last step of each s2d_step call, or on every step")
     args = ap.parse_args()
@@ -237,9 +239,25 @@ def main():
             torch.cuda.empty_cache()
     if e is None:
         raise SystemExit("could not build the workload: " + "; ".join(tried))
+    halo = "none (one strip)"
     if world > 1:
-        from sem2dpack_b200.strips import attach_halo_exchange
-        attach_halo_exchange(e, rank, world, precision=args.precision)
+        from sem2dpack_b200.strips import attach_halo_exchange, attach_peer_exchange
+        halo = "nccl send/recv through torch.distributed"
+        ok = 0
+        if args.halo == "peer":
+            try:
+                attach_peer_exchange(e, rank, world)
+                ok = 1
+            except Exception as ex:  # e.g. CUDA IPC not permitted in this container
+                print(f"[bench] rank {rank}: peer-memory halo exchange unavailable ({ex})", file=sys.stderr)
+        t = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 1:
+            halo = "peer memory over NVLink (CUDA IPC slots + device flags, no host call on the step path)"
+        else:
+            if args.halo == "peer":
+                halo += " (peer-memory mapping failed on some rank)"
+            attach_halo_exchange(e, rank, world, precision=args.precision)
     ndofs_rank = e.npoin * NDOF
     ric = Ricker(2.0, 0.6, 1.0e9)
 
@@ -314,7 +332,7 @@ def main():
                                     else "one a(5,5,6) block per element in HBM"),
                    "accel": ("materialised every step" if store_accel else
                              "materialised on the last step of each s2d_step call (every step in the e2e leg)"),
-                   "npoin_per_gpu": e.npoin, "nelem_per_gpu": e.nelem, "dt": e.dt,
+                   "halo_exchange": halo, "npoin_per_gpu": e.npoin, "nelem_per_gpu": e.nelem, "dt": e.dt,
                    "l2_policy": "working set (>=100 GB per GPU at the default size) far exceeds the 126 MB L2",
                    "requested": f"{args.nx}x{args.nz}", "fallbacks_tried": tried},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

@@ -258,10 +258,25 @@ int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double*
 int s2d_halo_info(s2d_handle h, int64_t* count, void** send_dev, void** recv_dev);
 typedef int (*s2d_exchange_fn)(void* user, void* stream);
 int s2d_halo_set_exchange(s2d_handle h, s2d_exchange_fn fn, void* user);
-/* peer-to-peer variant: write partial sums straight into the neighbour's recv buffer (pointer
- * obtained through CUDA IPC by the host) and signal with a flag; no host hook on the step path. */
+/* Peer-memory variant (NVLink, no host hook and no NCCL call on the step path): the engine's pack
+ * kernel writes its partial sums straight into the NEIGHBOUR's receive slot and then raises the
+ * neighbour's flag with the sequence number of the force evaluation; the neighbour's stream waits on
+ * its own flag before it adds them.  The pointers are device pointers valid on this GPU:
+ *   left_recv_dev  = the left neighbour's recv[1],  left_flag_dev  = &(its flags)[1]
+ *   right_recv_dev = the right neighbour's recv[0], right_flag_dev = &(its flags)[0]
+ * as returned by s2d_halo_peer_buffers on the neighbour (same process, peer access enabled), or
+ * mapped through CUDA IPC by s2d_halo_ipc_export / s2d_halo_ipc_open (one process per GPU).
+ * Every strip must run the same sequence of force evaluations. */
 int s2d_halo_set_peers(s2d_handle h, void* left_recv_dev, void* right_recv_dev,
                        void* left_flag_dev, void* right_flag_dev);
+/* recv_dev[2]: receive buffers (2 slots of s2d_halo_info's count each) [0] left, [1] right;
+ * flags_dev: two 64-bit flags, [0] raised by the left neighbour, [1] by the right one */
+int s2d_halo_peer_buffers(s2d_handle h, void** recv_dev, void** flags_dev);
+/* blob: S2D_HALO_IPC_BYTES bytes (three cudaIpcMemHandle_t) to hand to both neighbours */
+#define S2D_HALO_IPC_BYTES 192
+int s2d_halo_ipc_export(s2d_handle h, void* blob);
+/* the neighbours' blobs (NULL where there is no neighbour); calls s2d_halo_set_peers */
+int s2d_halo_ipc_open(s2d_handle h, const void* left_blob, const void* right_blob);
 
 #ifdef __cplusplus
 }

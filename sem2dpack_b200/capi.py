@@ -51,6 +51,9 @@ class DynfltDesc(C.Structure):
     ]
 
 
+HALO_IPC_BYTES = 192  # S2D_HALO_IPC_BYTES
+
+
 class CartDesc(C.Structure):
     _fields_ = [
         ("ngll", C.c_int32), ("ndof", C.c_int32), ("nx", C.c_int32), ("nz", C.c_int32), ("ezflt", C.c_int32),
@@ -110,6 +113,9 @@ _SIGS = {
     "s2d_halo_info": [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p],
     "s2d_halo_set_exchange": [C.c_void_p, C.c_void_p, C.c_void_p],
     "s2d_halo_set_peers": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    "s2d_halo_peer_buffers": [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)],
+    "s2d_halo_ipc_export": [C.c_void_p, C.c_void_p],
+    "s2d_halo_ipc_open": [C.c_void_p, C.c_void_p, C.c_void_p],
 }
 _STR_FUNCS = ("s2d_last_error", "s2d_version")
 

@@ -934,9 +934,51 @@ int s2d_halo_set_exchange(s2d_handle h, s2d_exchange_fn fn, void* user) {
   Eb->halo_set_exchange(fn, user);
   CART_GUARD_END
 }
-int s2d_halo_set_peers(s2d_handle h, void*, void*, void*, void*) {
+int s2d_halo_set_peers(s2d_handle h, void* left_recv_dev, void* right_recv_dev, void* left_flag_dev,
+                       void* right_flag_dev) {
   CART_GUARD_BEGIN
-  throw StateError("s2d_halo_set_peers: direct peer-memory exchange is not available in this build; use s2d_halo_set_exchange");
+  Eb->halo_set_peers(left_recv_dev, right_recv_dev, left_flag_dev, right_flag_dev);
+  CART_GUARD_END
+}
+
+// CUDA IPC plumbing for one process per GPU: blob = handles of {recv[0], recv[1], flags}
+int s2d_halo_ipc_export(s2d_handle h, void* blob) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(blob, "halo_ipc_export: null blob");
+  void* recv[2] = {nullptr, nullptr};
+  void* flags = nullptr;
+  Eb->halo_peer_buffers(recv, &flags);
+  cudaIpcMemHandle_t hd[3];
+  std::memset(hd, 0, sizeof(hd));
+  if (recv[0]) S2D_CUDA(cudaIpcGetMemHandle(&hd[0], recv[0]));
+  if (recv[1]) S2D_CUDA(cudaIpcGetMemHandle(&hd[1], recv[1]));
+  S2D_CUDA(cudaIpcGetMemHandle(&hd[2], flags));
+  std::memcpy(blob, hd, sizeof(hd));
+  CART_GUARD_END
+}
+
+int s2d_halo_ipc_open(s2d_handle h, const void* left_blob, const void* right_blob) {
+  CART_GUARD_BEGIN
+  void *lr = nullptr, *lf = nullptr, *rr = nullptr, *rf = nullptr;
+  cudaIpcMemHandle_t hd[3];
+  if (left_blob) {  // I am the left neighbour's RIGHT side: its recv[1] and flags[1]
+    std::memcpy(hd, left_blob, sizeof(hd));
+    S2D_CUDA(cudaIpcOpenMemHandle(&lr, hd[1], cudaIpcMemLazyEnablePeerAccess));
+    S2D_CUDA(cudaIpcOpenMemHandle(&lf, hd[2], cudaIpcMemLazyEnablePeerAccess));
+    lf = (unsigned long long*)lf + 1;
+  }
+  if (right_blob) {  // I am the right neighbour's LEFT side: its recv[0] and flags[0]
+    std::memcpy(hd, right_blob, sizeof(hd));
+    S2D_CUDA(cudaIpcOpenMemHandle(&rr, hd[0], cudaIpcMemLazyEnablePeerAccess));
+    S2D_CUDA(cudaIpcOpenMemHandle(&rf, hd[2], cudaIpcMemLazyEnablePeerAccess));
+  }
+  Eb->halo_set_peers(lr, rr, lf, rf);
+  CART_GUARD_END
+}
+
+int s2d_halo_peer_buffers(s2d_handle h, void** recv_dev, void** flags_dev) {
+  CART_GUARD_BEGIN
+  Eb->halo_peer_buffers(recv_dev, flags_dev);
   CART_GUARD_END
 }
 

@@ -99,6 +99,8 @@ class EngineBase {
   virtual float kernel_ms() = 0;
   virtual void halo_info(int64_t* count, void** send_dev, void** recv_dev) = 0;
   virtual void halo_set_exchange(s2d_exchange_fn fn, void* user) = 0;
+  virtual void halo_peer_buffers(void** recv_dev, void** flags_dev) = 0;
+  virtual void halo_set_peers(void* left_recv, void* right_recv, void* left_flag, void* right_flag) = 0;
 };
 
 template <typename T>
@@ -202,6 +204,13 @@ class Engine : public EngineBase {
   DevBuf<T> xh_send[2], xh_recv[2];
   s2d_exchange_fn xh_fn = nullptr;
   void* xh_user = nullptr;
+  // direct peer-memory exchange: the neighbours' receive slots and flags (device pointers that are
+  // valid on this GPU: CUDA IPC mappings or peer-enabled allocations), my own flags, the evaluation count
+  bool xh_peer = false;
+  T* xh_peer_recv[2] = {nullptr, nullptr};
+  unsigned long long* xh_peer_flag[2] = {nullptr, nullptr};
+  DevBuf<unsigned long long> xh_flags;
+  unsigned long long xh_seq = 0;
   cudaStream_t xstream = nullptr;
   cudaEvent_t xh_ev_b = nullptr, xh_ev_x = nullptr;
   bool xhalo() const { return cart_mode && (cart_S.xhalo_left || cart_S.xhalo_right); }
@@ -211,10 +220,12 @@ class Engine : public EngineBase {
     for (int sd = 0; sd < 2; ++sd)
       if (sd ? cart_S.xhalo_right : cart_S.xhalo_left) {
         xh_send[sd].alloc(n);
-        xh_recv[sd].alloc(n);
+        xh_recv[sd].alloc(2 * n);  // two slots for the peer-memory exchange; the hook exchange uses the first
         xh_send[sd].zero();
         xh_recv[sd].zero();
       }
+    xh_flags.alloc(2);
+    xh_flags.zero();
     S2D_CUDA(cudaStreamCreateWithFlags(&xstream, cudaStreamNonBlocking));
     S2D_CUDA(cudaEventCreateWithFlags(&xh_ev_b, cudaEventDisableTiming));
     S2D_CUDA(cudaEventCreateWithFlags(&xh_ev_x, cudaEventDisableTiming));
@@ -248,7 +259,8 @@ class Engine : public EngineBase {
       launches += 1 + launch_strip_fold<T>(S0, io.f, cart_hx.p, cart_hz.p, npoin, stream);
       return;
     }
-    if (!xh_fn) throw StateError("this x-strip has neighbours: attach a halo exchange (s2d_halo_set_exchange) first");
+    if (!xh_fn && !xh_peer)
+      throw StateError("this x-strip has neighbours: attach a halo exchange (s2d_halo_set_exchange or s2d_halo_set_peers) first");
     // boundary groups = the single-strip groups next to the interfaces
     const int nb = S0.g_lead + S0.g_tail + ((S0.nstrips == 1) ? 1 : 0);
     StripGeom B = S0, I = S0;
@@ -273,14 +285,32 @@ class Engine : public EngineBase {
     }
     S2D_CUDA(cudaStreamWaitEvent(xstream, xh_ev_b, 0));
     const int n2 = 2 * S0.LZ * ndof;
-    k_xhalo_pack<T><<<ceil_div(n2, 256), 256, 0, xstream>>>(S0, ff, cart_hz.p, npoin, xh_send[0].p, xh_send[1].p);
-    launches++;
-    const int rc = xh_fn(xh_user, (void*)xstream);
-    if (rc != 0) throw StateError("halo exchange hook failed with code " + std::to_string(rc));
+    const size_t nh = (size_t)S0.LZ * ndof;
+    const T *rl = xh_recv[0].p, *rr = xh_recv[1].p;
+    if (xh_peer) {  // write my partial sums into the neighbours' slots over NVLink, then raise their flags
+      ++xh_seq;
+      const size_t slot = (size_t)(xh_seq & 1) * nh;
+      k_xhalo_pack<T><<<ceil_div(n2, 256), 256, 0, xstream>>>(S0, ff, cart_hz.p, npoin,
+                                                             xh_peer_recv[0] ? xh_peer_recv[0] + slot : nullptr,
+                                                             xh_peer_recv[1] ? xh_peer_recv[1] + slot : nullptr);
+      k_xhalo_signal<<<1, 1, 0, xstream>>>(xh_peer_flag[0], xh_peer_flag[1], xh_seq);
+      launches += 2;
+      if (rl) rl += slot;
+      if (rr) rr += slot;
+    } else {
+      k_xhalo_pack<T><<<ceil_div(n2, 256), 256, 0, xstream>>>(S0, ff, cart_hz.p, npoin, xh_send[0].p, xh_send[1].p);
+      launches++;
+      const int rc = xh_fn(xh_user, (void*)xstream);
+      if (rc != 0) throw StateError("halo exchange hook failed with code " + std::to_string(rc));
+    }
     S2D_CUDA(cudaEventRecord(xh_ev_x, xstream));
     launches += launch_strip_fold<T>(S0, ff, cart_hx.p, cart_hz.p, npoin, stream);
     S2D_CUDA(cudaStreamWaitEvent(stream, xh_ev_x, 0));
-    k_xhalo_unpack<T><<<ceil_div(n2, 256), 256, 0, stream>>>(S0, ff, cart_hz.p, npoin, xh_recv[0].p, xh_recv[1].p);
+    if (xh_peer) {
+      k_xhalo_wait<<<1, 1, 0, stream>>>(xh_flags.p, S0.xhalo_left, S0.xhalo_right, xh_seq, ctl.p);
+      launches++;
+    }
+    k_xhalo_unpack<T><<<ceil_div(n2, 256), 256, 0, stream>>>(S0, ff, cart_hz.p, npoin, rl, rr);
     launches++;
     S2D_CUDA(cudaGetLastError());
   }
@@ -1071,6 +1101,7 @@ class Engine : public EngineBase {
     S2D_CUDA(cudaStreamSynchronize(stream));
     if (c.err == 1) throw StateError("NR_Solver has exceeded the maximum iterations (200)");
     if (c.err == 2) throw StateError("NR_Solver could not bracket a root");
+    if (c.err == 3) throw StateError("halo exchange: a neighbour GPU did not signal within 10 s");
   }
 
   void step(int nsteps, const double* srca, const double* bca) override {
@@ -1257,6 +1288,24 @@ class Engine : public EngineBase {
       if (send_dev) send_dev[sd] = xh_send[sd].p;
       if (recv_dev) recv_dev[sd] = xh_recv[sd].p;
     }
+  }
+  void halo_peer_buffers(void** recv_dev, void** flags_dev) override {
+    S2D_REQUIRE(cart_mode, "halo_peer_buffers: only x-strips made by the structured builder have halos");
+    xhalo_setup();
+    for (int sd = 0; sd < 2; ++sd)
+      if (recv_dev) recv_dev[sd] = xh_recv[sd].p;
+    if (flags_dev) *flags_dev = xh_flags.p;
+  }
+  void halo_set_peers(void* left_recv, void* right_recv, void* left_flag, void* right_flag) override {
+    S2D_REQUIRE(cart_mode, "halo_set_peers: only x-strips made by the structured builder have halos");
+    xhalo_setup();
+    S2D_REQUIRE(!cart_S.xhalo_left || (left_recv && left_flag), "halo_set_peers: the left neighbour's buffers are missing");
+    S2D_REQUIRE(!cart_S.xhalo_right || (right_recv && right_flag), "halo_set_peers: the right neighbour's buffers are missing");
+    xh_peer_recv[0] = cart_S.xhalo_left ? (T*)left_recv : nullptr;
+    xh_peer_recv[1] = cart_S.xhalo_right ? (T*)right_recv : nullptr;
+    xh_peer_flag[0] = cart_S.xhalo_left ? (unsigned long long*)left_flag : nullptr;
+    xh_peer_flag[1] = cart_S.xhalo_right ? (unsigned long long*)right_flag : nullptr;
+    xh_peer = true;
   }
   void halo_set_exchange(s2d_exchange_fn fn, void* user) override {
     S2D_REQUIRE(cart_mode, "halo_set_exchange: only x-strips made by the structured builder have halos");

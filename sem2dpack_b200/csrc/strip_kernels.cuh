@@ -773,6 +773,38 @@ __global__ void k_xhalo_pack(StripGeom G, const T* __restrict__ f, const T* __re
   if (!dst) return;
   dst[q] = xhalo_own(G, f, halo_z, npoin, side, q / G.LZ, q % G.LZ);
 }
+// Peer-memory exchange (NVLink): k_xhalo_pack writes straight into the neighbour GPU's receive slot;
+// then one thread publishes the sequence number of this force evaluation in the neighbour's flag,
+// and the neighbour's stream spins on its own flag before it unpacks.  Two receive slots (seq & 1):
+// a GPU sends evaluation seq+1 only after it has unpacked seq, so slot seq & 1 is rewritten (at
+// seq+2) only after its owner has read it.
+static __global__ void k_xhalo_signal(unsigned long long* peer_flag_l, unsigned long long* peer_flag_r, unsigned long long seq) {
+  __threadfence_system();
+  if (peer_flag_l) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag_l), "l"(seq) : "memory");
+  if (peer_flag_r) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag_r), "l"(seq) : "memory");
+}
+// flags[0] is written by the left neighbour, flags[1] by the right one.  Gives up after ~10 s with
+// ctl->err = 3 instead of hanging the GPU (a neighbour that died never signals).
+static __global__ void k_xhalo_wait(const unsigned long long* flags, int wait_l, int wait_r, unsigned long long seq, StepCtl* ctl) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int sd = 0; sd < 2; ++sd) {
+    if (!(sd ? wait_r : wait_l)) continue;
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + sd) : "memory");
+      if (v >= seq) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > 10000000000ull) {
+        ctl->err = 3;
+        return;
+      }
+      __nanosleep(200);
+    } while (true);
+  }
+  __threadfence_system();
+}
+
 // f = own + neighbour's; a + b == b + a bit for bit, so both GPUs hold the same value afterwards
 template <typename T>
 __global__ void k_xhalo_unpack(StripGeom G, T* __restrict__ f, const T* __restrict__ halo_z, size_t npoin,

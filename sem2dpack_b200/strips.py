@@ -90,15 +90,48 @@ def attach_halo_exchange(engine, rank, world, group=None, precision=8):
     engine._ck(engine.L.s2d_halo_set_exchange(engine.h, C.cast(cb, C.c_void_p), None))
 
 
+def attach_peer_exchange(engine, rank, world, group=None):
+    """Direct peer-memory halo exchange over NVLink (s2d_halo_ipc_export / s2d_halo_ipc_open): every
+    rank publishes CUDA IPC handles of its receive slots and flags, the neighbours map them, and from
+    then on the engine's own kernels write the interface partial sums into the neighbour's memory
+    and signal through device flags -- no host hook and no NCCL call on the step path.
+    torch.distributed only carries the 192-byte handles once."""
+    blob = (C.c_ubyte * capi.HALO_IPC_BYTES)()
+    engine._ck(engine.L.s2d_halo_ipc_export(engine.h, blob))
+    blobs = [None] * world
+    dist.all_gather_object(blobs, bytes(blob), group=group)
+
+    def buf(r):
+        return (C.c_ubyte * capi.HALO_IPC_BYTES).from_buffer_copy(blobs[r]) if 0 <= r < world else None
+    left, right = buf(rank - 1), buf(rank + 1)
+    engine._peer_blobs = (left, right)
+    engine._ck(engine.L.s2d_halo_ipc_open(engine.h, left, right))
+
+
 class LocalStrips:
     """Several x-strips of one box on ONE GPU inside one process, stepped by one thread each and
     exchanging through device copies -- the same engine-side halo path as the multi-GPU run, used by
     the single-GPU parity tests (whole box vs strips must agree bit for bit)."""
 
-    def __init__(self, engines, precision=8):
+    def __init__(self, engines, precision=8, peer=False):
         self.engines = engines
         self.n = len(engines)
         self.barrier = threading.Barrier(self.n)
+        if peer:  # the device-side protocol of the multi-GPU run: neighbours' slots and flags, no hook
+            ptrs = []
+            for e in engines:
+                recv = (C.c_void_p * 2)()
+                flags = C.c_void_p()
+                e._ck(e.L.s2d_halo_peer_buffers(e.h, recv, C.byref(flags)))
+                ptrs.append((recv[0], recv[1], flags.value))
+            for r, e in enumerate(engines):
+                lr = lf = rr = rf = None
+                if r > 0:
+                    lr, lf = ptrs[r - 1][1], ptrs[r - 1][2] + 8
+                if r < self.n - 1:
+                    rr, rf = ptrs[r + 1][0], ptrs[r + 1][2]
+                e._ck(e.L.s2d_halo_set_peers(e.h, lr, rr, lf, rf))
+            return
         self.bufs = [halo_tensors(e, precision) for e in engines]
         self._cbs = []
         for r, e in enumerate(engines):

@@ -38,9 +38,13 @@ def _build(nx_glob, nz, lo, hi, ezflt, scheme_kind, nsteps, world_rank, world, s
     return e, fid, nsrc
 
 
-@pytest.mark.parametrize("world,nx,nz,ezflt,seg,scheme", [(2, 20, 12, 5, 4, "leapfrog"), (3, 30, 9, 4, 32, "newmark"),
-                                                         (4, 16, 8, 0, 3, "leapfrog")])
-def test_strips_match_whole_box(world, nx, nz, ezflt, seg, scheme, monkeypatch):
+@pytest.mark.parametrize("world,nx,nz,ezflt,seg,scheme,peer", [
+    (2, 20, 12, 5, 4, "leapfrog", False), (3, 30, 9, 4, 32, "newmark", False), (4, 16, 8, 0, 3, "leapfrog", False),
+    # the device-side peer-memory protocol (slots + flags) of the multi-GPU run, here between two strips
+    # that share one GPU; few streams on purpose: a spinning wait kernel must not share a hardware queue
+    # with the kernel it waits for
+    (2, 20, 12, 5, 4, "leapfrog", True), (2, 26, 10, 4, 32, "newmark", True)])
+def test_strips_match_whole_box(world, nx, nz, ezflt, seg, scheme, peer, monkeypatch):
     monkeypatch.setenv("S2D_SEG", str(seg))
     nsteps = 200
     kind = 0 if scheme == "leapfrog" else 1
@@ -58,7 +62,7 @@ def test_strips_match_whole_box(world, nx, nz, ezflt, seg, scheme, monkeypatch):
     parts = strips.partition(nx, world)
     built = [_build(nx, nz, lo, hi, ezflt, kind, nsteps, r, world, sdir, dt=whole.dt) for r, (lo, hi) in enumerate(parts)]
     engines = [b[0] for b in built]
-    grp = strips.LocalStrips(engines)
+    grp = strips.LocalStrips(engines, peer=peer)
     grp.run(lambda r, e: e.step(nsteps, tab if built[r][2] else None))
     npw = whole.npoin
     fields = []
