@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsem2d_b200.so")
+# S2D_LIB_PATH: a differently tuned build of the same library (kernel experiments only)
+LIB_PATH = os.environ.get("S2D_LIB_PATH") or os.path.join(_HERE, "lib", "libsem2d_b200.so")
 _LIB = None
 
 S2D_ASM_PATCH, S2D_ASM_COLOR, S2D_ASM_ATOMIC = 0, 1, 2
