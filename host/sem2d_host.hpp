@@ -6,7 +6,7 @@
 // header), so this layer is what a maintainer's ISO_C_BINDING shim looks like when
 // written in C++.  Scope = what the device-side structured builder provides: &MESH_CART boxes with
 // one ELAST material, ABSORB sides, the split-node DYNFLT of `ezflt` with slip weakening, FORCE
-// sources, REC_LINE stations at nodes, leapfrog and Newmark.  Anything else in a Par.inp is
+// and moment-tensor sources, REC_LINE stations at nodes, the leapfrog, Newmark, HHT-alpha and symplectic schemes.  Anything else in a Par.inp is
 // refused with IO_abort, never silently ignored -- except plotting (&SNAP_*), which is not on the path.
 //
 //   reference                                           here
@@ -44,6 +44,8 @@ struct timescheme_type {
   double dt = 0.0, courant = 0.5, total = 0.0, time = 0.0;
   double alpha = 1.0, beta = 0.0, gamma = 0.5;
   int nt = 0;
+  int nstages = 0;               // symplectic schemes: time%a(1:nstages+1), time%b(1:nstages)
+  std::vector<double> a, b;
 };
 
 // source_type with a so_force_type mechanism (SRC/src_gen.f90:17-27, SRC/src_force.f90:9-12)
@@ -52,6 +54,8 @@ struct source_type {
   double tdelay = 0.0;
   stf_type stf;
   double dir[2] = {0, 1};
+  bool moment = false;           // so_moment_type (SRC/src_moment.f90:9-14): M(2,ndof) column-major
+  double M[4] = {0, 0, 0, 0};
   int32_t id = -1;
 };
 
@@ -252,8 +256,34 @@ inline void read_main(problem_type& pb, const std::string& file) {
         t.gamma = in.at((size_t)m).real8("gamma", 0.5);
       }
       if (t.beta != 0.0) IO_abort("TIME: only the explicit Newmark scheme (beta=0) is on the B200 path");
+    } else if (t.kind == "HHT-alpha") {  // SRC/time.f90:232-246
+      double alpha = 0.5, rho = 0.5;
+      const long m = in.find("TIME_HHTA", (size_t)k);
+      if (m >= 0) {
+        alpha = in.at((size_t)m).real8("alpha", 0.5);
+        rho = in.at((size_t)m).real8("rho", 0.5);
+      }
+      if (alpha < 0.0 || alpha > 1.0) IO_abort("TIME_HHTA: alpha is out of range [0,1]");
+      if (rho < 0.5 || rho > 1.0) IO_abort("TIME_HHTA: rho is out of range [0.5,1]");
+      t.alpha = alpha;
+      t.gamma = 1.5 - alpha;
+      t.beta = alpha != 1.0 ? 1.0 - alpha - rho * rho * (rho - 1.0) / ((1.0 - alpha) * ((1.0 + rho) * (1.0 + rho) * (1.0 + rho))) : 0.0;
+    } else if (t.kind == "symp_PV") {  // SRC/time.f90:248-255
+      t.nstages = 1;
+      t.a = {0.5, 0.5};
+      t.b = {1.0};
+    } else if (t.kind == "symp_PFR") {  // :257-269
+      const double theta = 1.0 / (2.0 - std::pow(2.0, 1.0 / 3.0));
+      t.nstages = 3;
+      t.a = {theta / 2.0, (1.0 - theta) / 2.0, (1.0 - theta) / 2.0, theta / 2.0};
+      t.b = {theta, 1.0 - 2.0 * theta, theta};
+    } else if (t.kind == "symp_PEFRL") {  // :271-287
+      const double xi = 0.1786178958448091, lambda = -0.2123418310626054, chi = -0.06626458266981849;
+      t.nstages = 4;
+      t.a = {xi, chi, 1.0 - 2.0 * (chi + xi), chi, xi};
+      t.b = {0.5 - lambda, lambda, lambda, 0.5 - lambda};
     } else if (t.kind != "leapfrog") {
-      IO_abort("TIME: scheme '" + t.kind + "' is not provided by the B200 path (leapfrog, newmark are)");
+      IO_abort("TIME: unknown kind");
     }
   }
   // SO_read (SRC/src_gen.f90:126-214)
@@ -265,13 +295,51 @@ inline void read_main(problem_type& pb, const std::string& file) {
     so.coord[0] = g.real8("coord", 0, 0);
     so.coord[1] = g.real8("coord", 0, 1);
     so.tdelay = g.real8("delay", 0.0);
-    if (g.text("mechanism", "") != "FORCE") IO_abort("SO_read: only mechanism='FORCE' is provided here");
+    const std::string mech = g.text("mechanism", "");
     so.stf = STF_read(g.text("stf", ""), in, (size_t)s);
-    const long m = in.find("SRC_FORCE", (size_t)s);  // SRC/src_force.f90:40-58
     const double PI = 3.141592653589793238462643383279502884197;
-    const double angle = (m >= 0 ? in.at((size_t)m).real8("angle", 0.0) : 0.0) * PI / 180.0;
-    so.dir[0] = -std::sin(angle);
-    so.dir[1] = std::cos(angle);
+    if (mech == "FORCE") {
+      const long m = in.find("SRC_FORCE", (size_t)s);  // SRC/src_force.f90:40-58
+      const double angle = (m >= 0 ? in.at((size_t)m).real8("angle", 0.0) : 0.0) * PI / 180.0;
+      so.dir[0] = -std::sin(angle);
+      so.dir[1] = std::cos(angle);
+    } else if (mech == "EXPLOSION" || mech == "DOUBLE_COUPLE" || mech == "MOMENT") {  // SRC/src_moment.f90:26-104
+      so.moment = true;
+      if (mech == "EXPLOSION") {
+        if (pb.ndof != 2) IO_abort("SRC_MOMENT_read: explosion only allowed in PSV (ndof=2)");
+        so.M[0] = so.M[3] = 1.0;
+      } else if (mech == "DOUBLE_COUPLE") {
+        const long m = in.find("SRC_DOUBLE_COUPLE", (size_t)s);
+        if (m < 0) IO_abort("SRC_MOMENT_read: SRC_DOUBLE_COUPLE input block not found");
+        const double dip = in.at((size_t)m).real8("dip", 90.0) * PI / 180.0;
+        const double n1 = std::sin(dip), n2 = std::cos(dip);
+        if (pb.ndof == 2) {
+          const double r1 = -std::cos(dip), r2 = std::sin(dip);
+          so.M[0] = 2.0 * r1 * n1;
+          so.M[2] = r1 * n2 + r2 * n1;
+          so.M[1] = so.M[2];
+          so.M[3] = 2.0 * r2 * n2;
+        } else {
+          so.M[0] = n1;
+          so.M[1] = n2;
+        }
+      } else {
+        const long m = in.find("SRC_MOMENT", (size_t)s);
+        if (m < 0) IO_abort("SRC_MOMENT_read: SRC_MOMENT input block not found");
+        const nml_group& q = in.at((size_t)m);
+        if (pb.ndof == 2) {
+          so.M[0] = q.real8("mxx", 0.0);
+          so.M[2] = q.real8("mxz", 0.0);
+          so.M[1] = q.real8("mzx", 0.0);
+          so.M[3] = q.real8("mzz", 0.0);
+        } else {
+          so.M[0] = q.real8("myx", 0.0);
+          so.M[1] = q.real8("myz", 0.0);
+        }
+      }
+    } else {
+      IO_abort("SO_read: mechanism '" + mech + "' is not provided here (FORCE, EXPLOSION, DOUBLE_COUPLE, MOMENT are)");
+    }
     pb.src.push_back(so);
   }
   // REC_read (SRC/receivers.f90:62-140)
@@ -317,7 +385,10 @@ inline void init_main(problem_type& pb) {
   d.cp = pb.cp;
   d.cs = pb.cs;
   d.precision = pb.precision;
-  d.scheme.kind = pb.time.kind == "newmark" ? 1 : 0;
+  d.scheme.kind = pb.time.kind == "newmark" ? 1 : (pb.time.kind == "HHT-alpha" ? 2 : (pb.time.nstages > 0 ? 3 : 0));
+  d.scheme.nstages = pb.time.nstages;
+  for (size_t q = 0; q < pb.time.a.size(); ++q) d.scheme.coa[q] = pb.time.a[q];
+  for (size_t q = 0; q < pb.time.b.size(); ++q) d.scheme.cob[q] = pb.time.b[q];
   d.scheme.dt = pb.time.dt;
   d.scheme.beta = pb.time.beta;
   d.scheme.gamma = pb.time.gamma;
@@ -352,8 +423,10 @@ inline void init_main(problem_type& pb) {
     }
   }
   // SO_init (SRC/src_gen.f90:216-262): nearest node
-  for (source_type& so : pb.src)
-    s2d_check(pb, s2d_cart_add_force(pb.gpu, so.coord[0], so.coord[1], so.dir, &so.id), "SO_init");
+  for (source_type& so : pb.src) {
+    if (so.moment) s2d_check(pb, s2d_cart_add_moment(pb.gpu, so.coord[0], so.coord[1], so.M, &so.id), "SRC_MOMENT_init");
+    else s2d_check(pb, s2d_cart_add_force(pb.gpu, so.coord[0], so.coord[1], so.dir, &so.id), "SO_init");
+  }
   // REC_init (SRC/receivers.f90:143-226)
   if (pb.rec) {
     rec_type& r = *pb.rec;
@@ -380,10 +453,22 @@ inline void solve(problem_type& pb, int nsteps = 1) {
   std::vector<double> ampli;
   const size_t ns = pb.src.size();
   if (ns) {
-    ampli.resize(ns * (size_t)nsteps);
-    for (int k = 0; k < nsteps; ++k)
-      for (size_t s = 0; s < ns; ++s)
-        ampli[s + ns * (size_t)k] = STF_get(pb.src[s].stf, (pb.it + k + 1) * pb.time.dt - pb.src[s].tdelay);
+    const timescheme_type& t = pb.time;
+    const int nst = t.nstages > 0 ? t.nstages : 1;
+    ampli.resize(ns * (size_t)nsteps * nst);
+    for (int k = 0; k < nsteps; ++k) {
+      const double time = (pb.it + k + 1) * t.dt;
+      if (t.nstages > 0) {  // solve_symplectic (SRC/solver.f90:186-191): one evaluation per stage
+        double ts = time - t.dt;
+        for (int q = 0; q < nst; ++q) {
+          ts = ts + t.dt * t.a[q];
+          for (size_t s = 0; s < ns; ++s) ampli[s + ns * ((size_t)k * nst + q)] = STF_get(pb.src[s].stf, ts - pb.src[s].tdelay);
+        }
+      } else {  // HHT-alpha evaluates at t_alpha = time + (alpha-1)*dt (SRC/solver.f90:116-117)
+        const double te = t.kind == "HHT-alpha" ? time + (t.alpha - 1.0) * t.dt : time;
+        for (size_t s = 0; s < ns; ++s) ampli[s + ns * (size_t)k] = STF_get(pb.src[s].stf, te - pb.src[s].tdelay);
+      }
+    }
   }
   s2d_check(pb, s2d_step(pb.gpu, nsteps, ns ? ampli.data() : nullptr, nullptr), "solve");
   pb.it += nsteps;

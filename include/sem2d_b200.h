@@ -40,11 +40,21 @@ extern "C" {
 
 typedef struct s2d_engine* s2d_handle;
 
-/* timescheme_type (SRC/time.f90:5-11); kind 0 = 'leapfrog' (solver.f90:140-160), 1 = 'newmark'
- * (solver.f90:42-84).  alpha is carried for CoefA2Vrhs but HHT-alpha stepping is not provided. */
+/* timescheme_type (SRC/time.f90:5-11).  kind:
+ *   0 'leapfrog'  (solver.f90:140-160)      1 'newmark' (solver.f90:42-84)
+ *   2 'HHT-alpha' (solver.f90:89-128): beta, gamma, alpha as TIME_read derives them (time.f90:232-246)
+ *   3 symplectic  (solver.f90:169-199; 'symp_PV', 'symp_PFR', 'symp_PEFRL', 'symp_PEFRL4'...):
+ *     nstages and the coefficient tables time%a(1:nstages+1), time%b(1:nstages) (time.f90:248-300);
+ *     as in the reference, boundary conditions are not applied by this scheme.
+ * The source amplitudes s2d_step receives are evaluated by the host at the times the scheme uses:
+ * it*dt for kinds 0/1, it*dt+(alpha-1)*dt for kind 2, and one row per STAGE for kind 3
+ * (t = (it-1)*dt + dt*sum(a(1:k)), solver.f90:186-191). */
+#define S2D_MAX_STAGES 8
 typedef struct {
   int32_t kind;
   double dt, beta, gamma, alpha;
+  int32_t nstages;
+  double coa[S2D_MAX_STAGES + 1], cob[S2D_MAX_STAGES];
 } s2d_scheme;
 
 /* element-force / assembly kernel variants */
@@ -129,6 +139,12 @@ int s2d_add_dynflt(s2d_handle h, const s2d_dynflt_desc* desc, int32_t* fault_id)
 
 /* src_force_type (SRC/src_force.f90:77-90): f(iglob,:) += dir(:)*ampli(t); returns source index. */
 int s2d_add_force(s2d_handle h, int32_t iglob, const double dir[2], int32_t* src_id);
+/* so_moment_type after SRC_MOMENT_init (SRC/src_moment.f90:129-180): the terms of SRC_MOMENT_add
+ * (:183-197) in the order that routine applies them -- for every element k that holds the source node,
+ * iglob_xi(:,k) with coef_xi(:,:,k), then iglob_eta(:,k) with coef_eta(:,:,k):
+ *   f(node[t], c) += ampli(t_step) * coef[t + nterms*c],  t = 0..nterms-1 in sequence.
+ * Shares the source index space (columns of src_ampli) with s2d_add_force. */
+int s2d_add_moment(s2d_handle h, int32_t nterms, const int32_t* node, const double* coef, int32_t* src_id);
 
 /* rec_type (SRC/receivers.f90:9-20): field 'D','V' or 'A'; nt_rec = time%nt/isamp+1 (:188);
  * at_node: iglob(nx); else einterp(nx) + interp(ngll*ngll,nx) (:231-303). */
@@ -233,6 +249,9 @@ int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, doub
                            double Tt_nuc, double x_nuc, double half_nuc, int32_t oixd, int32_t oitd,
                            int32_t nt_max, int32_t* fault_id);
 int s2d_cart_add_force(s2d_handle h, double x, double z, const double dir[2], int32_t* src_id);
+/* SRC_MOMENT_init on the box: moment tensor M(2,ndof) column-major as so%M (src_moment.f90:44-100) at the
+ * GLL node nearest to (x,z) */
+int s2d_cart_add_moment(s2d_handle h, double x, double z, const double* M, int32_t* src_id);
 int s2d_cart_add_receivers(s2d_handle h, int32_t nx, double xa, double za, double xb, double zb,
                            char field, int32_t isamp, int32_t nt_rec);
 /* the split-node fault as BC_DYNFLT_init leaves it (bc_dynflt.f90:392-458): node count, bc%coord(2,np),

@@ -118,7 +118,9 @@ long long orc_get_int(void* hv, const char* name_) {
   if (n == "nbc") return (long long)pb.bc.size();
   if (n == "nbnd") return (long long)pb.grid.bnds.size();
   if (n == "nsrc") return (long long)pb.src.size();
-  if (n == "scheme") return pb.time.kind == "leapfrog" ? 0 : (pb.time.kind == "newmark" ? 1 : -1);
+  if (n == "nstages") return pb.time.nstages;
+  if (n == "scheme")
+    return pb.time.kind == "leapfrog" ? 0 : (pb.time.kind == "newmark" ? 1 : (pb.time.kind == "HHT-alpha" ? 2 : (pb.time.nstages > 0 ? 3 : -1)));
   if (n == "rec.present") return pb.rec.present;
   if (n == "rec.nx") return pb.rec.nx;
   if (n == "rec.nt") return pb.rec.nt;
@@ -184,6 +186,8 @@ long long orc_get_int(void* hv, const char* name_) {
     int i = std::atoi(n.substr(4, p2 - 4).c_str());
     std::string f = n.substr(p2 + 1);
     if (f == "iglob") return pb.src[i].iglob;
+    if (f == "moment") return pb.src[i].moment ? 1 : 0;
+    if (f == "nterms") return (long long)pb.src[i].mnode.size();
   }
   return -999;
 }
@@ -267,6 +271,17 @@ long long orc_array(void* hv, const char* name_, const void** ptr, char* dtype) 
 #define RET_I(v) { *ptr = (v).data(); *dtype = 'i'; return (long long)(v).size(); }
 #define RET_F(v) { *ptr = (v).data(); *dtype = 'f'; return (long long)(v).size(); }
   if (n == "ibool") RET_I(pb.grid.ibool);
+  if (n == "time.a") RET_D(pb.time.a);
+  if (n == "time.b") RET_D(pb.time.b);
+  if (n.rfind("src.", 0) == 0) {
+    size_t p2 = n.find('.', 4);
+    int i = std::atoi(n.substr(4, p2 - 4).c_str());
+    std::string f = n.substr(p2 + 1);
+    if (i >= 0 && i < (int)pb.src.size()) {
+      if (f == "mnode") RET_I(pb.src[i].mnode);
+      if (f == "mcoef") RET_D(pb.src[i].mcoef);
+    }
+  }
   if (n == "coord") RET_D(pb.grid.coord);
   if (n == "coord_fem") RET_D(pb.grid.coord_fem);
   if (n == "knods") RET_I(pb.grid.knods);

@@ -718,6 +718,8 @@ struct TimeScheme {  // timescheme_type (time.f90:5-11)
   std::string kind = "leapfrog";
   double dt = 0, courant = 0.5, time = 0, total = 0, alpha = 1.0, beta = 0.0, gamma = 0.5, Omega_max = 2.0;
   int nt = 0;
+  int nstages = 0;              // symplectic schemes (time.f90:248-300)
+  std::vector<double> a, b;     // time%a(1:nstages+1), time%b(1:nstages)
   double CoefA2D() const {  // time.f90:426-440
     if (kind == "newmark" || kind == "HHT-alpha") return beta * dt * dt;
     return 0.0;
@@ -816,6 +818,11 @@ struct Source {  // source_type (src_gen.f90:20-26) with FORCE mechanism (src_fo
   Ricker stf;
   double dir[2] = {0, 1};
   int iglob = 0;
+  // so_moment_type (src_moment.f90:9-14); moment == false: collocated force
+  bool moment = false;
+  double M[4] = {0, 0, 0, 0};              // M(2,ndof) col-major
+  std::vector<int> mnode;                  // terms of SRC_MOMENT_add in application order
+  std::vector<double> mcoef;               // (nterms, ndof) col-major
 };
 struct Receivers {  // rec_type (receivers.f90:9-20)
   bool present = false;
@@ -2066,11 +2073,68 @@ inline void compute_Fint(Problem& pb, std::vector<double>& f, const std::vector<
   }
 }
 
-// src_gen.f90:290-317 SO_add with FORCE_add (src_force.f90:77-90)
+// src_moment.f90:129-180 SRC_MOMENT_init, with SE_node_belongs_to (spec_grid.f90:385-409: elements in
+// ascending order, each holding the node once)
+inline void SRC_MOMENT_init(Source& so, Problem& pb) {
+  const Grid& g = pb.grid;
+  int n = g.ngll, ndof = pb.ndof;
+  std::vector<int> etab, itab, jtab;
+  for (int e = 1; e <= g.nelem; ++e)
+    for (int j = 1; j <= n; ++j)
+      for (int i = 1; i <= n; ++i)
+        if (g.ib(i, j, e) == so.iglob) {
+          etab.push_back(e);
+          itab.push_back(i);
+          jtab.push_back(j);
+        }
+  int nel = (int)etab.size(), nterms = nel * 2 * n;
+  so.mnode.assign(nterms, 0);
+  so.mcoef.assign((size_t)nterms * ndof, 0.0);
+  int t = 0;
+  for (int k = 0; k < nel; ++k) {
+    int e = etab[k], i = itab[k], j = jtab[k];
+    double jac[4], ji[4], G[4] = {0, 0, 0, 0};
+    SE_Jacobian(g, e, i, j, jac);
+    invert2(jac, ji);  // jac_inv(r,c) at ji[r + 2*c]
+    if (ndof == 2) {   // G = matmul(M, transpose(jac_inv)): G(a,b) = sum_k M(a,k)*jac_inv(b,k)
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) G[a + 2 * b] = so.M[a + 2 * 0] * ji[b + 2 * 0] + so.M[a + 2 * 1] * ji[b + 2 * 1];
+    } else {           // G(:,1) = matmul(jac_inv, M(:,1))
+      for (int a = 0; a < 2; ++a) G[a] = ji[a + 2 * 0] * so.M[0] + ji[a + 2 * 1] * so.M[1];
+    }
+    for (int q = 1; q <= n; ++q, ++t) {  // iglob_xi(:,k) = ibool(:,j,e); coef_xi(:,c,k) = G(c,1)*hprime(:,i)
+      so.mnode[t] = g.ib(q, j, e);
+      if (ndof == 2) {
+        so.mcoef[t] = G[0 + 2 * 0] * g.H[(q - 1) + (size_t)n * (i - 1)];
+        so.mcoef[t + (size_t)nterms] = G[1 + 2 * 0] * g.H[(q - 1) + (size_t)n * (i - 1)];
+      } else {
+        so.mcoef[t] = G[0] * g.H[(q - 1) + (size_t)n * (i - 1)];
+      }
+    }
+    for (int q = 1; q <= n; ++q, ++t) {  // iglob_eta(:,k) = ibool(i,:,e); coef_eta(:,c,k) = G(c,2)*hprime(:,j)
+      so.mnode[t] = g.ib(i, q, e);
+      if (ndof == 2) {
+        so.mcoef[t] = G[0 + 2 * 1] * g.H[(q - 1) + (size_t)n * (j - 1)];
+        so.mcoef[t + (size_t)nterms] = G[1 + 2 * 1] * g.H[(q - 1) + (size_t)n * (j - 1)];
+      } else {
+        so.mcoef[t] = G[1] * g.H[(q - 1) + (size_t)n * (j - 1)];
+      }
+    }
+  }
+}
+
+// src_gen.f90:290-317 SO_add with FORCE_add (src_force.f90:77-90) / SRC_MOMENT_add (src_moment.f90:183-197)
 inline void SO_add(Problem& pb, double t, std::vector<double>& MxA) {
   for (auto& s : pb.src) {
     double ampli = s.stf.eval(t - s.tdelay);
     ampli = ampli * s.ampli;
+    if (s.moment) {
+      size_t nt = s.mnode.size();
+      for (size_t q = 0; q < nt; ++q)
+        for (int c = 0; c < pb.ndof; ++c)
+          MxA[pb.idx(s.mnode[q], c)] = MxA[pb.idx(s.mnode[q], c)] + ampli * s.mcoef[q + nt * c];
+      continue;
+    }
     if (pb.ndof == 1) {
       MxA[pb.idx(s.iglob, 0)] = MxA[pb.idx(s.iglob, 0)] + ampli;
     } else {
@@ -2080,7 +2144,7 @@ inline void SO_add(Problem& pb, double t, std::vector<double>& MxA) {
   }
 }
 
-// solver.f90:42-84 solve_Newmark, :140-160 solve_leapfrog
+// solver.f90:42-84 solve_Newmark, :89-128 solve_HHT_alpha, :140-160 solve_leapfrog, :169-199 solve_symplectic
 inline void solve(Problem& pb) {
   size_t nn = pb.d.size();
   std::vector<double>&d = pb.d, &v = pb.v, &a = pb.a_, &f = pb.a_;
@@ -2104,6 +2168,39 @@ inline void solve(Problem& pb) {
     double c3 = gamma * dt, c4 = beta * dt * dt;
     for (size_t q = 0; q < nn; ++q) v[q] = v[q] + c3 * a[q];
     for (size_t q = 0; q < nn; ++q) d[q] = d[q] + c4 * a[q];
+  } else if (pb.time.kind == "HHT-alpha") {  // solver.f90:89-128
+    double alpha = pb.time.alpha, beta = pb.time.beta, gamma = pb.time.gamma;
+    std::vector<double> d_alpha = d, v_alpha = v;
+    double c1 = (0.5 - beta) * dt * dt, c2 = (1.0 - gamma) * dt;
+    for (size_t q = 0; q < nn; ++q) d[q] = d[q] + dt * v[q] + c1 * a[q];
+    for (size_t q = 0; q < nn; ++q) v[q] = v[q] + c2 * a[q];
+    for (size_t q = 0; q < nn; ++q) d_alpha[q] = alpha * d[q] + (1.0 - alpha) * d_alpha[q];
+    for (size_t q = 0; q < nn; ++q) v_alpha[q] = alpha * v[q] + (1.0 - alpha) * v_alpha[q];
+    compute_Fint(pb, f, d_alpha, v_alpha);
+    double t_alpha = pb.time.time + (alpha - 1.0) * dt;
+    SO_add(pb, t_alpha, f);
+    double tmp = pb.time.time;
+    pb.time.time = t_alpha;
+    BC_apply(pb, f);
+    pb.time.time = tmp;
+    for (size_t q = 0; q < nn; ++q) a[q] = f[q] * pb.rmass[q];
+    double c3 = gamma * dt, c4 = beta * dt * dt;
+    for (size_t q = 0; q < nn; ++q) v[q] = v[q] + c3 * a[q];
+    for (size_t q = 0; q < nn; ++q) d[q] = d[q] + c4 * a[q];
+  } else if (pb.time.nstages > 0) {  // solve_symplectic (solver.f90:169-199): no boundary conditions
+    double t = pb.time.time - dt;
+    for (int k = 0; k < pb.time.nstages; ++k) {
+      double ca = dt * pb.time.a[k];
+      for (size_t q = 0; q < nn; ++q) d[q] = d[q] + ca * v[q];
+      compute_Fint(pb, f, d, v);
+      t = t + dt * pb.time.a[k];
+      SO_add(pb, t, f);
+      for (size_t q = 0; q < nn; ++q) a[q] = pb.rmass[q] * f[q];
+      double cb = dt * pb.time.b[k];
+      for (size_t q = 0; q < nn; ++q) v[q] = v[q] + cb * a[q];
+    }
+    double ca = dt * pb.time.a[pb.time.nstages];
+    for (size_t q = 0; q < nn; ++q) d[q] = d[q] + ca * v[q];
   } else {
     IO_abort("solve: scheme not supported by the oracle: " + pb.time.kind);
   }
@@ -2154,6 +2251,7 @@ inline void init_main(Problem& pb, const CartSpec& cart) {
     s.iglob = SE_find_nearest_node(g, s.coord[0], s.coord[1]);
     s.coord[0] = g.coord[2 * (size_t)(s.iglob - 1)];
     s.coord[1] = g.coord[2 * (size_t)(s.iglob - 1) + 1];
+    if (s.moment) SRC_MOMENT_init(s, pb);
   }
   for (size_t q = 0; q < nn; ++q) pb.rmass[q] = 1.0 / pb.rmass[q];  // init.f90:112-116
   pb.time.time = 0.0;
@@ -2246,6 +2344,33 @@ inline void read_main(Problem& pb, CartSpec& cart, ParInp& in) {
         t.beta = gn->dbl("beta", 0.0);
         t.gamma = gn->dbl("gamma", 0.5);
       }
+    } else if (t.kind == "HHT-alpha") {  // time.f90:232-246
+      double alpha = 0.5, rho = 0.5;
+      const NmlGroup* gh = in.next("TIME_HHTA");
+      if (gh) {
+        alpha = gh->dbl("alpha", 0.5);
+        rho = gh->dbl("rho", 0.5);
+      }
+      if (alpha < 0.0 || alpha > 1.0) IO_abort("TIME_HHTA: alpha is out of range [0,1]");
+      if (rho < 0.5 || rho > 1.0) IO_abort("TIME_HHTA: rho is out of range [0.5,1]");
+      t.alpha = alpha;
+      t.gamma = 1.5 - alpha;
+      if (alpha != 1.0) t.beta = 1.0 - alpha - rho * rho * (rho - 1.0) / ((1.0 - alpha) * ((1.0 + rho) * (1.0 + rho) * (1.0 + rho)));
+      else t.beta = 0.0;
+    } else if (t.kind == "symp_PV") {  // time.f90:248-255
+      t.nstages = 1;
+      t.a = {0.5, 0.5};
+      t.b = {1.0};
+    } else if (t.kind == "symp_PFR") {  // time.f90:257-269
+      t.nstages = 3;
+      double theta = 1.0 / (2.0 - std::pow(2.0, 1.0 / 3.0));
+      t.a = {theta / 2.0, (1.0 - theta) / 2.0, (1.0 - theta) / 2.0, theta / 2.0};
+      t.b = {theta, 1.0 - 2.0 * theta, theta};
+    } else if (t.kind == "symp_PEFRL") {  // time.f90:271-287
+      t.nstages = 4;
+      double xi = 0.1786178958448091, lambda = -0.2123418310626054, chi = -0.06626458266981849;
+      t.a = {xi, chi, 1.0 - 2.0 * (chi + xi), chi, xi};
+      t.b = {0.5 - lambda, lambda, lambda, 0.5 - lambda};
     } else if (t.kind != "leapfrog") {
       IO_abort("oracle: time scheme not supported: " + t.kind);
     }
@@ -2431,7 +2556,9 @@ inline void read_main(Problem& pb, CartSpec& cart, ParInp& in) {
     pb.src.clear();
     if (gs) {
       if (upper(gs->str("stf", " ")) != "RICKER") IO_abort("oracle: only stf='RICKER' supported");
-      if (upper(gs->str("mechanism", " ")) != "FORCE") IO_abort("oracle: only mechanism='FORCE' supported");
+      std::string mech = upper(gs->str("mechanism", " "));
+      if (mech != "FORCE" && mech != "EXPLOSION" && mech != "DOUBLE_COUPLE" && mech != "MOMENT")
+        IO_abort("oracle: mechanism not supported: " + mech);
       Source s;
       s.coord[0] = gs->dbl("coord", HUGE_D, 0);
       s.coord[1] = gs->dbl("coord", HUGE_D, 1);
@@ -2441,11 +2568,47 @@ inline void read_main(Problem& pb, CartSpec& cart, ParInp& in) {
       s.stf.t0 = gr->real_as_dbl("onset", 0.0);
       s.stf.ampli = gr->real_as_dbl("ampli", 1.0);
       in.rewind();
-      const NmlGroup* gfo = in.next("SRC_FORCE");
-      double angle = gfo ? gfo->dbl("angle", 0.0) : 0.0;
-      angle = angle * PI / 180.0;
-      s.dir[0] = -std::sin(angle);
-      s.dir[1] = std::cos(angle);
+      if (mech == "FORCE") {
+        const NmlGroup* gfo = in.next("SRC_FORCE");
+        double angle = gfo ? gfo->dbl("angle", 0.0) : 0.0;
+        angle = angle * PI / 180.0;
+        s.dir[0] = -std::sin(angle);
+        s.dir[1] = std::cos(angle);
+      } else {  // SRC_MOMENT_read (src_moment.f90:26-104); M(2,ndof) col-major
+        s.moment = true;
+        int ndof = pb.ndof;
+        if (mech == "EXPLOSION") {
+          if (ndof != 2) IO_abort("SRC_MOMENT_read: explosion only allowed in PSV (ndof=2)");
+          s.M[0] = 1.0; s.M[1] = 0.0; s.M[2] = 0.0; s.M[3] = 1.0;
+        } else if (mech == "DOUBLE_COUPLE") {
+          const NmlGroup* gd = in.next("SRC_DOUBLE_COUPLE");
+          if (!gd) IO_abort("SRC_MOMENT_read: SRC_DOUBLE_COUPLE input block not found");
+          double dip = gd->dbl("dip", 90.0) * PI / 180.0;
+          double n1 = std::sin(dip), n2 = std::cos(dip);
+          if (ndof == 2) {
+            double r1 = -std::cos(dip), r2 = std::sin(dip);
+            s.M[0] = 2.0 * r1 * n1;           // M(1,1)
+            s.M[2] = r1 * n2 + r2 * n1;       // M(1,2)
+            s.M[1] = s.M[2];                  // M(2,1)
+            s.M[3] = 2.0 * r2 * n2;           // M(2,2)
+          } else {
+            s.M[0] = n1;
+            s.M[1] = n2;
+          }
+        } else {
+          const NmlGroup* gm = in.next("SRC_MOMENT");
+          if (!gm) IO_abort("SRC_MOMENT_read: SRC_MOMENT input block not found");
+          if (ndof == 2) {
+            s.M[0] = gm->dbl("Mxx", 0.0);
+            s.M[2] = gm->dbl("Mxz", 0.0);
+            s.M[1] = gm->dbl("Mzx", 0.0);
+            s.M[3] = gm->dbl("Mzz", 0.0);
+          } else {
+            s.M[0] = gm->dbl("Myx", 0.0);
+            s.M[1] = gm->dbl("Myz", 0.0);
+          }
+        }
+      }
       pb.src.push_back(s);
     }
   }

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("S2D_LIB_PATH") or os.path.join(_HERE, "lib", "libsem2
 _LIB = None
 
 S2D_ASM_PATCH, S2D_ASM_COLOR, S2D_ASM_ATOMIC = 0, 1, 2
-LEAPFROG, NEWMARK = 0, 1
+LEAPFROG, NEWMARK, HHT_ALPHA, SYMPLECTIC = 0, 1, 2, 3
 
 _PD = C.POINTER(C.c_double)
 _PI = C.POINTER(C.c_int32)
@@ -27,9 +27,13 @@ class S2DError(RuntimeError):
         self.code = code
 
 
+MAX_STAGES = 8  # S2D_MAX_STAGES
+
+
 class Scheme(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dt", C.c_double), ("beta", C.c_double), ("gamma", C.c_double),
-                ("alpha", C.c_double)]
+                ("alpha", C.c_double), ("nstages", C.c_int32), ("coa", C.c_double * (MAX_STAGES + 1)),
+                ("cob", C.c_double * MAX_STAGES)]
 
 
 class DynfltDesc(C.Structure):
@@ -79,6 +83,7 @@ _SIGS = {
     "s2d_add_dirneu": [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
     "s2d_add_dynflt": [C.c_void_p, C.POINTER(DynfltDesc), C.POINTER(C.c_int32)],
     "s2d_add_force": [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)],
+    "s2d_add_moment": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)],
     "s2d_add_receivers": [C.c_void_p, C.c_int32, C.c_char, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                           C.c_void_p, C.c_void_p],
     "s2d_commit": [C.c_void_p, C.c_int32],
@@ -107,6 +112,7 @@ _SIGS = {
                                C.c_int32, C.c_int32],
     "s2d_cart_fault_info": [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p,
                             C.POINTER(C.c_double)],
+    "s2d_cart_add_moment": [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_int32)],
     "s2d_cart_receiver_info": [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p],
     "s2d_cart_info": [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)],
     "s2d_cart_set_dt": [C.c_void_p, C.c_double],

@@ -69,17 +69,59 @@ __global__ void k_invert(T* x, size_t n) {
 // point forces: f(iglob,:) += dir*ampli(it)
 template <typename T>
 __global__ void k_sources(T* f, size_t npoin, int ndof, int nsrc, const int* iglob,
-                          const double* dir /*(2,nsrc)*/, const double* ampli /*[steps][nsrc]*/,
-                          const StepCtl* ctl) {
+                          const double* dir /*(2,nsrc)*/, const double* ampli /*[steps*nstages][nsrc]*/,
+                          const StepCtl* ctl, int stage, int nstages) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nsrc) return;
-  const double amp = ampli[(size_t)((ctl->it - ctl->it0) % ctl->nrows) * nsrc + s];
+  if (s >= nsrc || iglob[s] <= 0) return;  // 0: a moment source (k_moments)
+  const double amp = ampli[(size_t)(((ctl->it - ctl->it0) * nstages + stage) % ctl->nrows) * nsrc + s];
   const size_t node = (size_t)(iglob[s] - 1);
   if (ndof == 1) {
     f[node] = (T)((double)f[node] + amp);  // src_force.f90:84
   } else {
     f[node] = (T)((double)f[node] + dir[2 * s] * amp);
     f[node + npoin] = (T)((double)f[node + npoin] + dir[2 * s + 1] * amp);
+  }
+}
+
+// moment-tensor sources (SRC_MOMENT_add, src_moment.f90:183-197): one thread per source walks its
+// terms in the reference's order (a node can appear in several terms)
+template <typename T>
+__global__ void k_moments(T* f, size_t npoin, int ndof, int nmom, const int* src_id, const int* start,
+                          const int* node, const double* coef, int nsrc, const double* ampli, const StepCtl* ctl,
+                          int stage, int nstages) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nmom) return;
+  const double amp = ampli[(size_t)(((ctl->it - ctl->it0) * nstages + stage) % ctl->nrows) * nsrc + src_id[m]];
+  const int t0 = start[m], nt = start[m + 1] - t0;
+  for (int t = 0; t < nt; ++t) {
+    const size_t q = (size_t)(node[t0 + t] - 1);
+    for (int c = 0; c < ndof; ++c) f[q + npoin * c] = (T)((double)f[q + npoin * c] + amp * coef[t0 + t + (size_t)nt * c]);
+  }
+}
+
+// y += c*x  (symplectic stages, solver.f90:185,197)
+template <typename T>
+__global__ void k_axpy(T* __restrict__ y, const T* __restrict__ x, T* __restrict__ f, size_t n, T c, int zero_f) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    y[q] = y[q] + c * x[q];
+    if (zero_f) f[q] = 0;
+  }
+}
+// HHT-alpha predictor (solver.f90:108-113)
+template <typename T>
+__global__ void k_predict_hht(T* __restrict__ d, T* __restrict__ v, T* __restrict__ a, T* __restrict__ d_alpha,
+                              T* __restrict__ v_alpha, size_t n, T dt, T c1, T c2, T alpha, int zero_f) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    const T aq = a[q], v0 = v[q], d0 = d[q];
+    const T d1 = d0 + dt * v0 + c1 * aq;
+    const T v1 = v0 + c2 * aq;
+    d[q] = d1;
+    v[q] = v1;
+    d_alpha[q] = alpha * d1 + ((T)1 - alpha) * d0;
+    v_alpha[q] = alpha * v1 + ((T)1 - alpha) * v0;
+    if (zero_f) a[q] = 0;
   }
 }
 
@@ -161,7 +203,7 @@ __global__ void k_dirneu(T* f, size_t npoin, int ndof, int np, const int* node, 
 // dynamic fault
 struct FaultDev {
   int np, ndof, two_sides, allow_opening;
-  double CoefA2V, CoefA2D, dt;
+  double CoefA2V, CoefA2D, dt, tshift;
   const int *node1, *node2;
   const double *n1, *B, *invM1, *invM2, *Z, *T0, *cohesion, *coord;
   double *T, *Tstick, *V, *D, *MU, *sigma;
@@ -364,7 +406,7 @@ __global__ void k_dynflt(FaultDev F, T* MxA, const T* __restrict__ Vf, const T* 
   const int np = F.np;
   if (k >= np) return;
   const int ndof = F.ndof;
-  const double time = (double)ctl->it * F.dt;
+  const double time = (double)ctl->it * F.dt + F.tshift;  // HHT-alpha: t_alpha (solver.f90:116-121)
   double dD[2] = {0, 0}, dV[2] = {0, 0}, dA[2] = {0, 0}, Tt[2] = {0, 0}, Ts[2] = {0, 0};
   size_t i1[2], i2[2] = {0, 0};
   for (int c = 0; c < ndof; ++c) {

@@ -14,6 +14,8 @@
 // The heterogeneous material is the counter-based hash model of the synthetic benchmark
 // (SURVEY.md 8d): values depend only on the global GLL lattice coordinates, so x-strips of one
 // global mesh built on different GPUs agree bit for bit.
+#include <algorithm>
+#include <array>
 #include <map>
 
 #include "engine.hpp"
@@ -366,9 +368,10 @@ struct CartState {
   double fault_mu0 = 0.0;
   std::vector<double> rec_coord;  // (2, nx) positions of the relocated stations (rec%coord, receivers.f90:231-303)
   int coef_mode = 0;  // 0 = compact (lambda, mu) where the rheology allows, 1 = all planes stored
-  double CoefA2V() const { return scheme.kind == 1 ? scheme.gamma * scheme.dt : scheme.dt; }        // time.f90:443-456
-  double CoefA2D() const { return scheme.kind == 1 ? scheme.beta * scheme.dt * scheme.dt : 0.0; }    // time.f90:426-440
-  double CoefA2Vrhs() const { return scheme.kind == 1 ? scheme.alpha * CoefA2V() : 0.5 * CoefA2V(); }  // :465-486
+  bool nm() const { return scheme.kind == 1 || scheme.kind == 2; }  // 'newmark', 'HHT-alpha'
+  double CoefA2V() const { return nm() ? scheme.gamma * scheme.dt : scheme.dt; }        // time.f90:443-456
+  double CoefA2D() const { return nm() ? scheme.beta * scheme.dt * scheme.dt : 0.0; }    // time.f90:426-440
+  double CoefA2Vrhs() const { return nm() ? scheme.alpha * CoefA2V() : 0.5 * CoefA2V(); }  // :465-486
 };
 
 void cart_free(void* c) { delete (CartState*)c; }
@@ -497,7 +500,7 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
   *out = nullptr;
   if (D->ngll < 3 || D->ngll > 10 || (D->ndof != 1 && D->ndof != 2) || D->nx < 1 || D->nz < 1 || D->ezflt < 0 ||
       D->ezflt >= D->nz || !(D->x1 > D->x0) || !(D->z1 > D->z0) || (D->precision != 8 && D->precision != 4) ||
-      (D->scheme.kind != 0 && D->scheme.kind != 1))
+      D->scheme.kind < 0 || D->scheme.kind > 3)
     return S2D_EINVAL;
   std::string err;
   const int dev = select_device(D->device, err);
@@ -796,6 +799,77 @@ int s2d_cart_add_force(s2d_handle h, double x, double z, const double* dir, int3
   nearest_1d(G, x, G.x0, G.hx, G.nx, ex, i);
   nearest_1d(G, z, G.z0, G.hz, G.nz, ez, j);
   const int id = Eb->add_force((int)cart_lat_id(G, ex, ez, i, j), dir);
+  if (src_id) *src_id = id;
+  CART_GUARD_END
+}
+
+// SRC_MOMENT_init (src_moment.f90:129-180) on the box: for every element that holds the source node, in
+// ascending element order (SE_node_belongs_to), the N nodes of its xi-line and of its eta-line through
+// the node with G = M * transpose(jac_inv) (P-SV) or jac_inv * M (SH); jac_inv = diag(2/hx, 2/hz).
+int s2d_cart_add_moment(s2d_handle h, double x, double z, const double* M, int32_t* src_id) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(M, "cart_add_moment: null M");
+  const CartGeom& G = S.G;
+  const int N = G.N, ndof = G.ndof;
+  int ex, i, ez, j;
+  nearest_1d(G, x, G.x0, G.hx, G.nx, ex, i);
+  nearest_1d(G, z, G.z0, G.hz, G.nz, ez, j);
+  const double dxi = 2.0 / G.hx, deta = 2.0 / G.hz;
+  // elements containing lattice node (ex,i ; ez,j): the node may also be the last point of the element
+  // to the left / below (not across the split fault row)
+  std::vector<std::array<int, 4>> holders;  // ix, iz, i, j
+  for (int dz = -1; dz <= 0; ++dz)
+    for (int dx = -1; dx <= 0; ++dx) {
+      int ix = ex, li = i, iz = ez, lj = j;
+      if (dx == -1) {
+        if (!(i == 0 && ex > 0)) continue;
+        ix = ex - 1;
+        li = N - 1;
+      }
+      if (dz == -1) {
+        if (!(j == 0 && ez > 0 && !row_detached(G, ez))) continue;
+        iz = ez - 1;
+        lj = N - 1;
+      }
+      holders.push_back({ix, iz, li, lj});
+    }
+  // nearest_1d prefers the higher element on ties, so also look right / up
+  if (i == N - 1 && ex + 1 < G.nx) {
+    const size_t n0 = holders.size();
+    for (size_t q = 0; q < n0; ++q) holders.push_back({holders[q][0] + 1, holders[q][1], 0, holders[q][3]});
+  }
+  if (j == N - 1 && ez + 1 < G.nz && !row_detached(G, ez + 1)) {
+    const size_t n0 = holders.size();
+    for (size_t q = 0; q < n0; ++q) holders.push_back({holders[q][0], holders[q][1] + 1, holders[q][2], 0});
+  }
+  std::sort(holders.begin(), holders.end(), [&](const std::array<int, 4>& a, const std::array<int, 4>& b) {
+    return (long long)a[1] * G.nx + a[0] < (long long)b[1] * G.nx + b[0];
+  });
+  const int nt = (int)holders.size() * 2 * N;
+  std::vector<int> node(nt);
+  std::vector<double> coef((size_t)nt * ndof);
+  int t = 0;
+  for (auto& hd : holders) {
+    double gx1[2], ge1[2];  // G(c,1), G(c,2) per component
+    if (ndof == 2) {  // G = M * transpose(jac_inv): G(c,1) = M(c,1)*dxi, G(c,2) = M(c,2)*deta   (M column-major (2,2))
+      for (int c = 0; c < 2; ++c) {
+        gx1[c] = M[c + 2 * 0] * dxi;
+        ge1[c] = M[c + 2 * 1] * deta;
+      }
+    } else {  // G(:,1) = jac_inv * M(:,1)
+      gx1[0] = dxi * M[0];
+      ge1[0] = deta * M[1];
+    }
+    for (int k = 0; k < N; ++k, ++t) {  // iglob_xi(:,k) = ibool(:,j,e), coef_xi = G(c,1)*hprime(:,i)
+      node[t] = (int)cart_lat_id(G, hd[0], hd[1], k, hd[3]);
+      for (int c = 0; c < ndof; ++c) coef[t + (size_t)nt * c] = gx1[c] * S.H[k + N * hd[2]];
+    }
+    for (int k = 0; k < N; ++k, ++t) {  // iglob_eta(:,k) = ibool(i,:,e), coef_eta = G(c,2)*hprime(:,j)
+      node[t] = (int)cart_lat_id(G, hd[0], hd[1], hd[2], k);
+      for (int c = 0; c < ndof; ++c) coef[t + (size_t)nt * c] = ge1[c] * S.H[k + N * hd[3]];
+    }
+  }
+  const int id = Eb->add_moment(nt, node.data(), coef.data());
   if (src_id) *src_id = id;
   CART_GUARD_END
 }

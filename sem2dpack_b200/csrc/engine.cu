@@ -89,7 +89,7 @@ int s2d_create(s2d_handle* out, int32_t ngll, int32_t ndof, int32_t nelem, int32
   if (!out) return S2D_EINVAL;
   *out = nullptr;
   if (!ibool || !hprime || !rmass || !scheme || ngll < 3 || ngll > 10 || (ndof != 1 && ndof != 2) ||
-      nelem < 1 || npoin < 1 || (precision != 8 && precision != 4) || (scheme->kind != 0 && scheme->kind != 1) ||
+      nelem < 1 || npoin < 1 || (precision != 8 && precision != 4) || scheme->kind < 0 || scheme->kind > 3 ||
       !(scheme->dt > 0.0)) {
     g_create_err = "s2d_create: invalid argument";
     return S2D_EINVAL;
@@ -160,6 +160,12 @@ int s2d_add_force(s2d_handle h, int32_t iglob, const double dir[2], int32_t* src
   return guard(h, [&](EngineBase& E) {
     S2D_REQUIRE(dir, "s2d_add_force: null dir");
     int id = E.add_force(iglob, dir);
+    if (src_id) *src_id = id;
+  });
+}
+int s2d_add_moment(s2d_handle h, int32_t nterms, const int32_t* node, const double* coef, int32_t* src_id) {
+  return guard(h, [&](EngineBase& E) {
+    int id = E.add_moment(nterms, node, coef);
     if (src_id) *src_id = id;
   });
 }

@@ -78,6 +78,7 @@ class EngineBase {
                           const double* B_v) = 0;
   virtual int add_dynflt(const s2d_dynflt_desc& d) = 0;
   virtual int add_force(int iglob, const double dir[2]) = 0;
+  virtual int add_moment(int nterms, const int32_t* node, const double* coef) = 0;
   virtual void add_receivers(int nx, char field, int isamp, int nt_rec, int at_node, const int32_t* iglob,
                              const int32_t* einterp, const double* interp) = 0;
   virtual void commit(int variant) = 0;
@@ -131,6 +132,14 @@ class Engine : public EngineBase {
   std::vector<double> h_src_dir;
   DevBuf<int> src_iglob;
   DevBuf<double> src_dir, src_ampli, bc_ampli;
+  // moment-tensor sources (src_moment.f90): terms of SRC_MOMENT_add per source
+  std::vector<int32_t> h_mom_src, h_mom_start{0}, h_mom_node;
+  std::vector<double> h_mom_coef;
+  DevBuf<int> mom_src, mom_start, mom_node;
+  DevBuf<double> mom_coef;
+  // HHT-alpha work fields (fields%displ_alpha, veloc_alpha; fields.f90:10-11)
+  DevBuf<T> d_alpha, v_alpha;
+  int nstages() const { return scheme.kind == 3 ? scheme.nstages : 1; }
   size_t src_ampli_cap = 0, bc_ampli_cap = 0;
   Receivers rec;
   // control
@@ -518,6 +527,7 @@ class Engine : public EngineBase {
     F.CoefA2V = D.CoefA2V;
     F.CoefA2D = D.CoefA2D;
     F.dt = scheme.dt;
+    F.tshift = scheme.kind == 2 ? (scheme.alpha - 1.0) * scheme.dt : 0.0;
     auto up = [&](DevBuf<double>& buf, const double* src, size_t n) -> const double* {
       if (!src) return nullptr;
       buf.upload(src, n);
@@ -692,6 +702,20 @@ class Engine : public EngineBase {
     return (int)h_src_iglob.size() - 1;
   }
 
+  int add_moment(int nterms, const int32_t* node, const double* coef_) override {
+    S2D_REQUIRE(!committed, "add_moment after commit");
+    S2D_REQUIRE(nterms > 0 && node && coef_, "add_moment: empty source");
+    for (int t = 0; t < nterms; ++t) S2D_REQUIRE(node[t] >= 1 && (size_t)node[t] <= npoin, "add_moment: node id out of range");
+    h_src_iglob.push_back(0);  // keeps the source index space of the amplitude table
+    h_src_dir.push_back(0.0);
+    h_src_dir.push_back(0.0);
+    h_mom_src.push_back((int)h_src_iglob.size() - 1);
+    h_mom_node.insert(h_mom_node.end(), node, node + nterms);
+    h_mom_coef.insert(h_mom_coef.end(), coef_, coef_ + (size_t)nterms * ndof);
+    h_mom_start.push_back((int)h_mom_node.size());
+    return (int)h_src_iglob.size() - 1;
+  }
+
   void add_receivers(int nx, char field, int isamp, int nt_rec, int at_node, const int32_t* iglob,
                      const int32_t* einterp, const double* interp) override {
     S2D_REQUIRE(!committed, "add_receivers after commit");
@@ -734,7 +758,12 @@ class Engine : public EngineBase {
     h_rowflag.resize(LZ, 0);
     h_colflag.resize(LX, 0);
     std::vector<std::vector<int32_t>> lists = h_bc_nodes;
-    lists.push_back(h_src_iglob);
+    std::vector<int32_t> forces;
+    for (int nd : h_src_iglob)
+      if (nd > 0) forces.push_back(nd);
+    lists.push_back(forces);
+    for (size_t m = 0; m + 1 < h_mom_start.size(); ++m)  // one list per moment source: a row and a column
+      lists.emplace_back(h_mom_node.begin() + h_mom_start[m], h_mom_node.begin() + h_mom_start[m + 1]);
     for (auto& L : lists) {
       std::vector<int> colcount(LX, 0), rowcount(LZ, 0);
       for (int nd : L) {
@@ -864,6 +893,18 @@ class Engine : public EngineBase {
       src_iglob.upload(h_src_iglob);
       src_dir.upload(h_src_dir);
     }
+    if (!h_mom_src.empty()) {
+      mom_src.upload(h_mom_src);
+      mom_start.upload(h_mom_start);
+      mom_node.upload(h_mom_node);
+      mom_coef.upload(h_mom_coef);
+    }
+    if (scheme.kind == 2) {
+      d_alpha.alloc(npoin * ndof);
+      v_alpha.alloc(npoin * ndof);
+    }
+    if (scheme.kind == 3)
+      S2D_REQUIRE(scheme.nstages >= 1 && scheme.nstages <= S2D_MAX_STAGES, "commit: symplectic scheme needs 1..8 stages");
     committed = true;
     // it = 0 outputs: BC_write(bc,0) at the end of BC_init (bc_gen.f90:249), REC_store(rec,0) (main.f90:35)
     launch_outputs();
@@ -1003,6 +1044,23 @@ class Engine : public EngineBase {
     }
   }
 
+  // SO_add (src_gen.f90:290-317): collocated forces, then moment tensors
+  void launch_sources(T* f, int stage = 0) {
+    if (h_src_iglob.empty()) return;
+    const int ns = (int)h_src_iglob.size(), nst = nstages();
+    if ((size_t)ns > h_mom_src.size()) {
+      k_sources<T><<<ceil_div(ns, 32), 32, 0, stream>>>(f, npoin, ndof, ns, src_iglob.p, src_dir.p, src_ampli.p, ctl.p,
+                                                        stage, nst);
+      launches++;
+    }
+    if (!h_mom_src.empty()) {
+      const int nm = (int)h_mom_src.size();
+      k_moments<T><<<ceil_div(nm, 32), 32, 0, stream>>>(f, npoin, ndof, nm, mom_src.p, mom_start.p, mom_node.p,
+                                                        mom_coef.p, ns, src_ampli.p, ctl.p, stage, nst);
+      launches++;
+    }
+  }
+
   void launch_outputs() {
     if (rec.present) {
       const T* fld = rec.field == 'D' ? dn() : (rec.field == 'V' ? v.p : a.p);
@@ -1039,12 +1097,7 @@ class Engine : public EngineBase {
     io.colflag = colflag.p;
     io.dt = scheme.dt;
     launch_strips(io);
-    if (!h_src_iglob.empty()) {
-      const int ns = (int)h_src_iglob.size();
-      k_sources<T><<<ceil_div(ns, 32), 32, 0, stream>>>(a.p, npoin, ndof, ns, src_iglob.p, src_dir.p,
-                                                        src_ampli.p, ctl.p);
-      launches++;
-    }
+    launch_sources(a.p);
     launch_bcs(dc);
     const long long nw = (long long)ndrows * cart_S.LX + (long long)ndcols * cart_S.LZ;
     if (nw > 0) {
@@ -1067,21 +1120,38 @@ class Engine : public EngineBase {
     k_tick<<<1, 1, 0, stream>>>(ctl.p);
     launches++;
     const int zf = needs_zero_f() ? 1 : 0;
+    if (scheme.kind == 3) {  // solve_symplectic (solver.f90:169-199): no boundary conditions, as in the reference
+      for (int k = 0; k < scheme.nstages; ++k) {
+        k_axpy<T><<<grid_for(nd), 256, 0, stream>>>(dn(), v.p, a.p, nd, (T)(scheme.dt * scheme.coa[k]), zf);
+        launch_fint(dn(), v.p, a.p);
+        launch_sources(a.p, k);
+        k_correct<T><<<grid_for(nd), 256, 0, stream>>>(dn(), v.p, a.p, rmass.p, nd, (T)(scheme.dt * scheme.cob[k]), (T)0);
+        launches += 2;
+      }
+      k_axpy<T><<<grid_for(nd), 256, 0, stream>>>(dn(), v.p, a.p, nd, (T)(scheme.dt * scheme.coa[scheme.nstages]), 0);
+      launches++;
+      launch_outputs();
+      return;
+    }
+    const T* dforce = dn();
+    const T* vforce = v.p;
     if (scheme.kind == 0) {
       k_predict_leapfrog<T><<<grid_for(nd), 256, 0, stream>>>(dn(), v.p, a.p, nd, dt, zf);
     } else {
       const T c1 = (T)((0.5 - scheme.beta) * scheme.dt * scheme.dt), c2 = (T)((1.0 - scheme.gamma) * scheme.dt);
-      k_predict_newmark<T><<<grid_for(nd), 256, 0, stream>>>(dn(), v.p, a.p, nd, dt, c1, c2, zf);
+      if (scheme.kind == 2) {  // solve_HHT_alpha (solver.f90:89-128): forces from the alpha-weighted fields
+        k_predict_hht<T><<<grid_for(nd), 256, 0, stream>>>(dn(), v.p, a.p, d_alpha.p, v_alpha.p, nd, dt, c1, c2,
+                                                           (T)scheme.alpha, zf);
+        dforce = d_alpha.p;
+        vforce = v_alpha.p;
+      } else {
+        k_predict_newmark<T><<<grid_for(nd), 256, 0, stream>>>(dn(), v.p, a.p, nd, dt, c1, c2, zf);
+      }
     }
     launches++;
-    launch_fint(dn(), v.p, a.p);
-    if (!h_src_iglob.empty()) {
-      const int ns = (int)h_src_iglob.size();
-      k_sources<T><<<ceil_div(ns, 32), 32, 0, stream>>>(a.p, npoin, ndof, ns, src_iglob.p, src_dir.p,
-                                                        src_ampli.p, ctl.p);
-      launches++;
-    }
-    launch_bcs(dn());
+    launch_fint(dforce, vforce, a.p);
+    launch_sources(a.p);
+    launch_bcs(dn());  // BC_apply sees fields%displ / veloc (solver.f90:121), not the alpha-weighted copies
     T c3, c4;
     if (scheme.kind == 0) {
       c3 = dt;
@@ -1111,7 +1181,7 @@ class Engine : public EngineBase {
     const size_t ns = h_src_iglob.size();
     if (ns > 0) {
       S2D_REQUIRE(srca != nullptr, "step: src_ampli missing");
-      const size_t need = ns * nsteps;
+      const size_t need = ns * nsteps * nstages();
       if (need > src_ampli_cap) {
         S2D_CUDA(cudaStreamSynchronize(stream));
         src_ampli.alloc(need);
@@ -1133,7 +1203,8 @@ class Engine : public EngineBase {
     }
     const int it0 = it + 1;
     S2D_CUDA(cudaMemcpyAsync(&ctl.p->it0, &it0, sizeof(int), cudaMemcpyHostToDevice, stream));
-    S2D_CUDA(cudaMemcpyAsync(&ctl.p->nrows, &nsteps, sizeof(int), cudaMemcpyHostToDevice, stream));
+    const int nrows = nsteps * nstages();  // one row per stage for the symplectic schemes
+    S2D_CUDA(cudaMemcpyAsync(&ctl.p->nrows, &nrows, sizeof(int), cudaMemcpyHostToDevice, stream));
     for (int k = 0; k < nsteps; ++k) launch_step(k == nsteps - 1);
     it += nsteps;
     S2D_CUDA(cudaGetLastError());

@@ -8,11 +8,36 @@ from . import capi
 from .capi import (S2D_ASM_PATCH, DynfltDesc, S2DError, Scheme, _f64, _i32, _pd, _pi, _ptr)
 
 
+def symplectic_stages(kind):
+    """time%a, time%b of the symplectic schemes (SRC/time.f90:248-300)."""
+    if kind == "symp_PV":
+        return [0.5, 0.5], [1.0]
+    if kind == "symp_PFR":
+        th = 1.0 / (2.0 - 2.0 ** (1.0 / 3.0))
+        return [th / 2, (1 - th) / 2, (1 - th) / 2, th / 2], [th, 1 - 2 * th, th]
+    if kind == "symp_PEFRL":
+        xi, lam, chi = 0.1786178958448091, -0.2123418310626054, -0.06626458266981849
+        return ([xi, chi, 1 - 2 * (chi + xi), chi, xi], [0.5 - lam, lam, lam, 0.5 - lam])
+    raise ValueError(kind)
+
+
+def make_scheme(kind, dt, beta, gamma, alpha, stages=None):
+    s = Scheme(kind, dt, beta, gamma, alpha)
+    if stages is not None:
+        coa, cob = stages
+        s.nstages = len(cob)
+        for k, x in enumerate(coa):
+            s.coa[k] = x
+        for k, x in enumerate(cob):
+            s.cob[k] = x
+    return s
+
+
 class Engine:
     """One device-resident SEM2DPACK problem (problem_type, SRC/problem_class.f90:19-46)."""
 
     def __init__(self, ngll, ndof, ibool, hprime, rmass, scheme_kind, dt, beta=0.0, gamma=0.5, alpha=1.0,
-                 precision=8, device=-1, _handle=None):
+                 precision=8, device=-1, _handle=None, stages=None):
         self.L = capi.lib()
         self._keep = []
         if _handle is not None:
@@ -26,7 +51,7 @@ class Engine:
         npoin = rmass.size // ndof
         self.ngll, self.ndof, self.nelem, self.npoin = ngll, ndof, nelem, npoin
         self.dt = dt
-        sch = Scheme(scheme_kind, dt, beta, gamma, alpha)
+        sch = make_scheme(scheme_kind, dt, beta, gamma, alpha, stages)
         h = C.c_void_p()
         rc = self.L.s2d_create(C.byref(h), ngll, ndof, nelem, npoin, _ptr(ibool), _ptr(hprime), _ptr(rmass),
                                precision, C.byref(sch), device)
@@ -98,6 +123,14 @@ class Engine:
     def add_force(self, iglob, direction):
         sid = C.c_int32(-1)
         self._ck(self.L.s2d_add_force(self.h, int(iglob), _ptr(_f64(direction)), C.byref(sid)))
+        return sid.value
+
+    def add_moment(self, node, coef):
+        """so_moment_type after SRC_MOMENT_init (SRC/src_moment.f90:129-180): node (nterms) and
+        coef (nterms, ndof) column-major, in the order SRC_MOMENT_add applies them."""
+        node = _i32(node)
+        sid = C.c_int32(-1)
+        self._ck(self.L.s2d_add_moment(self.h, node.size, _ptr(node), _ptr(_f64(coef)), C.byref(sid)))
         return sid.value
 
     def add_receivers(self, field, isamp, nt_rec, iglob=None, einterp=None, interp=None):
@@ -212,7 +245,7 @@ class CartEngine(Engine):
 
     def __init__(self, ngll, ndof, nx, nz, xlim, zlim, ezflt=0, seed=0, rho=0.0, cp=0.0, cs=0.0, scheme_kind=0,
                  dt=0.0, courant=0.5, beta=0.0, gamma=0.5, alpha=1.0, precision=8, device=-1, ix0=0, iz0=0,
-                 halo_left=False, halo_right=False, coef_mode=0):
+                 halo_left=False, halo_right=False, coef_mode=0, stages=None):
         L = capi.lib()
         d = capi.CartDesc()
         d.ngll, d.ndof, d.nx, d.nz, d.ezflt = ngll, ndof, nx, nz, ezflt
@@ -221,7 +254,7 @@ class CartEngine(Engine):
         d.seed, d.ix0, d.iz0 = seed, ix0, iz0
         d.rho, d.cp, d.cs = rho, cp, cs
         d.precision = precision
-        d.scheme = Scheme(scheme_kind, dt, beta, gamma, alpha)
+        d.scheme = make_scheme(scheme_kind, dt, beta, gamma, alpha, stages)
         d.courant = courant
         d.device = device
         d.halo_left, d.halo_right = int(halo_left), int(halo_right)
@@ -254,6 +287,12 @@ class CartEngine(Engine):
     def add_force_at(self, x, z, direction):
         sid = C.c_int32(-1)
         self._ck(self.L.s2d_cart_add_force(self.h, x, z, _ptr(_f64(direction)), C.byref(sid)))
+        return sid.value
+
+    def add_moment_at(self, x, z, M):
+        """M(2,ndof) column-major as so%M (SRC/src_moment.f90:44-100)"""
+        sid = C.c_int32(-1)
+        self._ck(self.L.s2d_cart_add_moment(self.h, x, z, _ptr(_f64(M)), C.byref(sid)))
         return sid.value
 
     def add_receiver_line(self, nx, first, last, field, isamp, nt_rec):

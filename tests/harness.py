@@ -66,10 +66,13 @@ class Rig:
         self.ngll, self.ndof = ngll, ndof
         self.dt = o.f("dt")
         self.nt = o.i("nt")
-        kind = o.i("scheme")
-        assert kind in (0, 1)
+        kind = o.i("scheme")   # 0 leapfrog, 1 newmark, 2 HHT-alpha, 3 symplectic
+        assert kind in (0, 1, 2, 3)
+        self.kind = kind
+        self.alpha = o.f("alpha")
+        self.stages = (list(o.arr("time.a")), list(o.arr("time.b"))) if kind == 3 else None
         e = Engine(ngll, ndof, o.arr("ibool"), o.arr("H"), o.arr("rmass"), kind, self.dt, o.f("beta"), o.f("gamma"),
-                   o.f("alpha"), precision=precision, device=device)
+                   o.f("alpha"), precision=precision, device=device, stages=self.stages)
         self.e = e
         if kd2 is None:
             kd2 = (ngll == 5)  # OPT_NGLL (SRC/constants.f90:6, mat_elastic.f90:412)
@@ -114,7 +117,10 @@ class Rig:
                 self.faults.append((fid, i, o.i(p + "np"), o.i(p + "onx")))
         self.nsrc = o.i("nsrc")
         for s in range(self.nsrc):
-            e.add_force(o.i(f"src.{s}.iglob"), [o.f(f"src.{s}.dir1"), o.f(f"src.{s}.dir2")])
+            if o.i(f"src.{s}.moment"):   # what SRC_MOMENT_init built (src_moment.f90:129-180)
+                e.add_moment(o.arr(f"src.{s}.mnode"), o.arr(f"src.{s}.mcoef"))
+            else:
+                e.add_force(o.i(f"src.{s}.iglob"), [o.f(f"src.{s}.dir1"), o.f(f"src.{s}.dir2")])
         if o.i("rec.present"):
             fld = chr(o.i("rec.field"))
             if o.i("rec.atnode"):
@@ -128,9 +134,21 @@ class Rig:
         """STF_get(t-tdelay)*ampli evaluated by the host per step (src_gen.f90:300-303)."""
         if self.nsrc == 0:
             return None
+        if self.kind == 3:   # one row per stage: t = (it-1)*dt + dt*sum(a(1:k)) (solver.f90:186-191)
+            coa, cob = self.stages
+            nst = len(cob)
+            tab = np.empty((nsteps * nst, self.nsrc))
+            for k in range(nsteps):
+                t = (it_first + k) * self.dt - self.dt
+                for q in range(nst):
+                    t = t + self.dt * coa[q]
+                    for s in range(self.nsrc):
+                        tab[k * nst + q, s] = self.o.stf(s, t)
+            return tab
+        shift = (self.alpha - 1.0) * self.dt if self.kind == 2 else 0.0   # t_alpha (solver.f90:116)
         tab = np.empty((nsteps, self.nsrc))
         for k in range(nsteps):
-            t = (it_first + k) * self.dt
+            t = (it_first + k) * self.dt + shift
             for s in range(self.nsrc):
                 tab[k, s] = self.o.stf(s, t)
         return tab
