@@ -33,13 +33,15 @@ B_STEP = B_K1 + 6 * W8
 B_COEF = NELAST * NGLL ** 2 * W8 / (NDOF * (NGLL - 1) ** 2)   # 37.5 B/DOF of coefficient planes
 
 
-def moved_bytes_per_dof(fused, store_accel, compact, w=W8):
+def moved_bytes_per_dof(fused, store_accel, compact, w=W8, newmark=False):
     """bytes the strip kernel must move per DOF.  Coefficients: all six planes, or (lambda, mu) only in
     the compact mode.  Plain force evaluation: d read, f written.  Fused leapfrog update: d, v read,
     the inverse mass read once per node (w/ndof per DOF), v, d_next (, a) written.  ibool is never read."""
     coef = (2 if compact else NELAST) * NGLL ** 2 * w / (NDOF * (NGLL - 1) ** 2)
     if not fused:
         return coef + 2 * w
+    if newmark:   # explicit Newmark also reads a[n-1] and always writes a[n]
+        return coef + 4 * w + w / NDOF + 2 * w
     return coef + 4 * w + w / NDOF + (w if store_accel else 0)
 METRIC = "GLL DOF-updates/sec"
 UNIT = "DOF-updates/s"
@@ -119,11 +121,11 @@ def cpu_oracle_rate(nx, nz, nsteps):
     return ndofs * nsteps / t, t
 
 
-def build_engine(nx, nz, rank, world, device, nt_max, precision=8, sync_dt=None):
+def build_engine(nx, nz, rank, world, device, nt_max, precision=8, sync_dt=None, scheme_kind=0):
     from sem2dpack_b200 import CartEngine
     ez = nz // 2
     e = CartEngine(NGLL, NDOF, nx, nz, (rank * nx * H, (rank + 1) * nx * H), (0.0, nz * H), ezflt=ez, seed=SEED,
-                   scheme_kind=0, courant=0.5, precision=precision, device=device, ix0=rank * nx * (NGLL - 1), iz0=0,
+                   scheme_kind=scheme_kind, courant=0.5, precision=precision, device=device, ix0=rank * nx * (NGLL - 1), iz0=0,
                    halo_left=rank > 0, halo_right=rank < world - 1)
     if sync_dt is not None:
         e.set_dt(sync_dt(e.dt))  # one Courant step for the whole mesh: the minimum over the strips
@@ -183,6 +185,8 @@ def main():
     ap.add_argument("--fint-reps", type=int, default=10)
     ap.add_argument("--coef", choices=["compact", "full"], default="compact",
                     help="coefficient storage: (lambda, mu) per GLL point, or all six planes a(5,5,6) per element")
+    ap.add_argument("--scheme", choices=["leapfrog", "newmark"], default="leapfrog",
+                    help="time scheme of the workload (BASELINE configs[4]: leapfrog/Newmark); newmark = explicit, beta=0")
     ap.add_argument("--halo", choices=["peer", "nccl"], default="peer",
                     help="x-strip interface exchange: engine kernels writing into the neighbour's memory, or NCCL")
     ap.add_argument("--accel", choices=["last", "every"], default="last",
@@ -229,7 +233,7 @@ def main():
     for nzt in [nz, (nz * 3) // 4, nz // 2, nz // 4]:
         try:
             e, nsrc = build_engine(nx, nzt, rank, world, local, nt_max, args.precision,
-                                   sync_dt if world > 1 else None)
+                                   sync_dt if world > 1 else None, 1 if args.scheme == "newmark" else 0)
             e.commit()
             nz = nzt
             break
@@ -288,7 +292,7 @@ def main():
     store_accel = args.accel == "every"
     compact = args.coef == "compact"
     w = W8 if args.precision == 8 else 4
-    b_moved = moved_bytes_per_dof(fused, store_accel, compact, w)
+    b_moved = moved_bytes_per_dof(fused, store_accel, compact, w, args.scheme == "newmark")
     barrier()
     ms_fint = e.time_fint(args.fint_reps)
     barrier()
@@ -327,7 +331,7 @@ def main():
         "dtype": "f64" if args.precision == 8 else "f32", "data": "synthetic",
         "config": {"workload": f"synthetic {nx * world}x{nz} Q4 structured mesh ({nx}x{nz} x-strip per GPU), NGLL=5, "
                                "ndof=2 heterogeneous isotropic elastic (material differs at every GLL point) + planar "
-                               "two-sided SWF fault + ABSORB on 4 sides, leapfrog, Courant 0.5, 128 receivers/GPU",
+                               f"two-sided SWF fault + ABSORB on 4 sides, {args.scheme}, Courant 0.5, 128 receivers/GPU",
                    "coefficients": ("(lambda, mu) per GLL point in HBM, six planes formed in registers" if compact
                                     else "one a(5,5,6) block per element in HBM"),
                    "accel": ("materialised every step" if store_accel else
@@ -337,7 +341,7 @@ def main():
                    "requested": f"{args.nx}x{args.nz}", "fallbacks_tried": tried},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "k_elem_strip<fused leapfrog update>" if fused else "k_elem_strip",
+                     "kernel": f"k_elem_strip<fused {args.scheme} update>" if fused else "k_elem_strip",
                      "algorithmic_bytes_per_dof": b_moved, "dofs_per_launch": ndofs_rank, "ms_per_launch": ms_kernel,
                      "note": "bytes = what this kernel must move per DOF (coefficients, d, v, rmass in; v, d_next(, a) out); "
                              "SURVEY 8d's canonical K1+update figure is %.1f B/DOF (%.1f with a stored)" % (B_STEP, B_STEP + W8),

@@ -27,12 +27,16 @@ __global__ void k_predict_leapfrog(T* __restrict__ d, const T* __restrict__ v, T
     if (zero_f) f[q] = 0;     // solver.f90:286
   }
 }
-// out-of-place leapfrog predictor of the fused step: dst = src + dt*v
+// out-of-place displacement predictor of the fused step: dst = src + dt*v (+ c1*a for Newmark, solver.f90:59)
 template <typename T>
-__global__ void k_predict_to(T* __restrict__ dst, const T* __restrict__ src, const T* __restrict__ v, size_t n,
-                             T dt) {
+__global__ void k_predict_to(T* __restrict__ dst, const T* __restrict__ src, const T* __restrict__ v,
+                             const T* __restrict__ a, size_t n, T dt, T c1) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) dst[q] = src[q] + dt * v[q];
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    T x = src[q] + dt * v[q];
+    if (c1 != (T)0) x = x + c1 * a[q];
+    dst[q] = x;
+  }
 }
 template <typename T>
 __global__ void k_predict_newmark(T* __restrict__ d, T* __restrict__ v, T* __restrict__ a, size_t n,

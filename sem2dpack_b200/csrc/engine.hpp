@@ -882,7 +882,8 @@ class Engine : public EngineBase {
     if (cart_mode) {
       S2D_REQUIRE(variant == S2D_ASM_PATCH, "commit: the structured builder only provides the strip kernel");
       k_invert<T><<<grid_for(rmass.n), 256, 0, stream>>>(rmass.p, rmass.n);
-      fused = (scheme.kind == 0) && env_int("S2D_FUSED", 1) != 0;
+      // the node update rides in the strip kernel for leapfrog and for the explicit Newmark scheme (beta = 0)
+      fused = (scheme.kind == 0 || (scheme.kind == 1 && scheme.beta == 0.0)) && env_int("S2D_FUSED", 1) != 0;
       if (fused) build_deferred_tables();
     } else {
       if (nkv == 0) h_elem2kv.assign(nelem, -1);
@@ -1080,8 +1081,12 @@ class Engine : public EngineBase {
     const T dt = (T)scheme.dt;
     k_tick<<<1, 1, 0, stream>>>(ctl.p);
     launches++;
-    if (!pred_valid) {  // first step after the fields were set: d[n] = d[n-1] + dt*v (solver.f90:151)
-      k_predict_to<T><<<grid_for(nd), 256, 0, stream>>>(dalt(), dn(), v.p, nd, dt);
+    const bool nmk = scheme.kind == 1;
+    const T c1 = nmk ? (T)(0.5 * scheme.dt * scheme.dt) : (T)0;            // (1/2 - beta) dt^2, beta = 0
+    const T c2 = nmk ? (T)((1.0 - scheme.gamma) * scheme.dt) : (T)0;
+    const T c3 = nmk ? (T)(scheme.gamma * scheme.dt) : dt;
+    if (!pred_valid) {  // first step after the fields were set: the predictor (solver.f90:151 / :59)
+      k_predict_to<T><<<grid_for(nd), 256, 0, stream>>>(dalt(), dn(), v.p, a.p, nd, dt, c1);
       launches++;
     }
     T* dc = dalt();   // d[n]
@@ -1091,18 +1096,24 @@ class Engine : public EngineBase {
     io.v_out = v.p;
     io.rmass = rmass.p;
     io.d_next = dnx;
-    const bool want_a = store_accel == 1 || (store_accel == 2 && (last_of_call || (rec.present && rec.field == 'A')));
+    const bool want_a = nmk || store_accel == 1 || (store_accel == 2 && (last_of_call || (rec.present && rec.field == 'A')));
     io.a_out = want_a ? a.p : nullptr;
     io.rowflag = rowflag.p;
     io.colflag = colflag.p;
     io.dt = scheme.dt;
+    io.newmark = nmk ? 1 : 0;
+    io.c1 = c1;
+    io.c2 = c2;
+    io.c3 = c3;
+    io.a_in = a.p;
     launch_strips(io);
     launch_sources(a.p);
     launch_bcs(dc);
     const long long nw = (long long)ndrows * cart_S.LX + (long long)ndcols * cart_S.LZ;
     if (nw > 0) {
       k_strip_deferred<T><<<(unsigned)((nw + 255) / 256), 256, 0, stream>>>(
-          cart_S.LX, cart_S.LZ, ndof, npoin, drows.p, ndrows, dcols.p, ndcols, rowflag.p, a.p, v.p, rmass.p, dc, dnx, dt);
+          cart_S.LX, cart_S.LZ, ndof, npoin, drows.p, ndrows, dcols.p, ndcols, rowflag.p, a.p, v.p, rmass.p, dc, dnx, dt,
+          c1, c3);
       launches++;
     }
     dsel ^= 1;  // the caller now sees d[n]; the other buffer holds the prediction

@@ -164,6 +164,10 @@ struct StripArgs {
   const uint8_t* colflag;   // (LX) 1: every node of the lattice column is deferred; 2: group-boundary column
   int* meet;                // [nseg][ngroups-1] arrival counters of the group-boundary columns (zero between launches)
   T dt;
+  // explicit Newmark (solver.f90:59-60,78-82 with beta = 0): c1 = dt^2/2, c2 = (1-gamma) dt, c3 = gamma dt;
+  // leapfrog is the same update with c1 = c2 = 0, c3 = dt
+  T c1, c2, c3;
+  const T* a_in;            // accelerations of the previous step (Newmark predictor); aliases f / a_out
   int prefetch;             // L2 prefetch of what is not staged
   T H[N * N];               // hprime, column-major (constant bank)
   // compact coefficient mode (isotropic flat grids): only (lambda, mu) are stored per GLL point and
@@ -206,16 +210,17 @@ constexpr int strip_warps() { return 4; }
 constexpr int STRIP_MASK_WORDS = 128;  // a band has at most 32*128 lattice rows (s2d_cart_create clamps SEG)
 // bytes of the staging area of one warp: coefficient vectors and displacement rows of one element
 // row; in the fused form also the velocities and inverse masses of the nodes it will advance
-constexpr size_t strip_stage_bytes(int N, int NDOF, int tsize, bool fused, bool compact) {
+// (fused: 0 plain force evaluation, 1 leapfrog update, 2 explicit Newmark update: also the old accelerations)
+constexpr size_t strip_stage_bytes(int N, int NDOF, int tsize, int fused, bool compact) {
   const size_t npl = compact ? 2 : (NDOF == 1 ? 2 : 6);
   const size_t c = (npl / 2) * N * 32 * (2 * tsize), u = (size_t)NDOF * (N - 1) * 32 * tsize, r = (size_t)(N - 1) * 32 * tsize;
-  return c + u + (fused ? u + r : 0);
+  return c + u + (fused ? u + r : 0) + (fused == 2 ? u : 0);
 }
 constexpr int strip_min_ctas(int N, int tsize, bool compact = false) {
   return N <= 6 ? (tsize == 4 ? 4 : 3) : (tsize == 4 ? 2 : 1);
 }
 
-template <typename T, int N, int NDOF, bool FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT)>
+template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT)>
 __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     k_elem_strip(const __grid_constant__ StripArgs<T, N> A) {
   static_assert(!COMPACT || NDOF == 2, "compact coefficients: P-SV only");
@@ -241,6 +246,8 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   T* st_u = reinterpret_cast<T*>(wstage + SZ_C) + lane;        // [c * (N-1) + j-1][32]
   T* st_v = reinterpret_cast<T*>(wstage + SZ_C + SZ_U) + lane; // [c * (N-1) + j][32]   (fused)
   T* st_r = st_v + NU * 32;                                    // [j][32]               (fused)
+  T* st_a = st_r + (N - 1) * 32;                               // [c * (N-1) + j][32]   (fused Newmark: a[n-1])
+  constexpr bool NM = FUSED == 2;
   const long long cta = blockIdx.x;
   const int seg = (int)(cta / G.it_ng);
   const int grp = G.it_g0 + (int)(cta - (long long)seg * G.it_ng) * G.it_step;
@@ -394,8 +401,10 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
               const size_t q = rowbase + (size_t)j * LX + gx;
               stage_copy<sizeof(T)>(st_r + j * 32, A.rmass + q);
 #pragma unroll
-              for (int c = 0; c < NDOF; ++c)
+              for (int c = 0; c < NDOF; ++c) {
                 stage_copy<sizeof(T)>(st_v + (c * (N - 1) + j) * 32, A.v_in + A.npoin * c + q);
+                if (NM) stage_copy<sizeof(T)>(st_a + (c * (N - 1) + j) * 32, A.a_in + A.npoin * c + q);
+              }
             }
           } else if (A.prefetch && i == 0) {  // read at the end of the row: pull the lines into L2 now
 #pragma unroll
@@ -537,7 +546,10 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
             for (int j = 0; j < N - 1; ++j) {
               rm[j] = st_r[j * 32];
 #pragma unroll
-              for (int c = 0; c < NDOF; ++c) vv[c][j] = st_v[(c * (N - 1) + j) * 32];
+              for (int c = 0; c < NDOF; ++c) {
+                vv[c][j] = st_v[(c * (N - 1) + j) * 32];
+                if (NM) vv[c][j] = vv[c][j] + A.c2 * st_a[(c * (N - 1) + j) * 32];  // predictor, solver.f90:60
+              }
             }
           } else {  // one batch of independent loads (deferred nodes included)
 #pragma unroll
@@ -545,7 +557,10 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
               const size_t q = rowbase + (size_t)j * LX + gx;
               rm[j] = A.rmass[q];
 #pragma unroll
-              for (int c = 0; c < NDOF; ++c) vv[c][j] = A.v_in[A.npoin * c + q];
+              for (int c = 0; c < NDOF; ++c) {
+                vv[c][j] = A.v_in[A.npoin * c + q];
+                if (NM) vv[c][j] = vv[c][j] + A.c2 * A.a_in[A.npoin * c + q];
+              }
             }
           }
         }
@@ -553,14 +568,19 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         for (int c = 0; c < NDOF; ++c)
 #pragma unroll
           for (int j = 0; j < N - 1; ++j) {
+            const size_t q = A.npoin * c + rowbase + (size_t)j * LX + gx;
             if (!FUSED || ((defer >> j) & 1u)) {
               sp[cstride * c + (grow + j) * rstride] = f[c][j];
-            } else {  // solver.f90:157-158, then :151 of the next step
-              const size_t q = A.npoin * c + rowbase + (size_t)j * LX + gx;
+              // Newmark: the lane that stores into f owns the node and leaves the predicted velocity
+              // for the boundary conditions and the deferred update
+              if (NM && !to_halo) A.v_out[q] = vv[c][j];
+            } else {  // solver.f90:157-158 (leapfrog) / :78-81 (Newmark), then the predictor of the next step
               const T acc = rm[j] * f[c][j];
-              const T vn = vv[c][j] + A.dt * acc;
+              const T vn = vv[c][j] + A.c3 * acc;
               A.v_out[q] = vn;
-              A.d_next[q] = U[c][j] + A.dt * vn;
+              T dn = U[c][j] + A.dt * vn;
+              if (NM) dn = dn + A.c1 * acc;
+              A.d_next[q] = dn;
               if (A.a_out) A.a_out[q] = acc;
             }
           }
@@ -575,15 +595,25 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       const size_t gt = (size_t)strip_lat_row(G, ez1 - 1, N - 1);
       if (!FUSED || coldef || A.rowflag[gt]) {
 #pragma unroll
-        for (int c = 0; c < NDOF; ++c) sp[cstride * c + gt * rstride] = Fc[c];
+        for (int c = 0; c < NDOF; ++c) {
+          const size_t q = A.npoin * c + gt * LX + gx;
+          T vp = 0;
+          if (NM && !to_halo) vp = A.v_in[q] + A.c2 * A.a_in[q];  // before f overwrites a
+          sp[cstride * c + gt * rstride] = Fc[c];
+          if (NM && !to_halo) A.v_out[q] = vp;
+        }
       } else {
 #pragma unroll
         for (int c = 0; c < NDOF; ++c) {
           const size_t q = A.npoin * c + gt * LX + gx;
           const T acc = A.rmass[gt * LX + gx] * Fc[c];
-          const T vn = A.v_in[q] + A.dt * acc;
+          T vp = A.v_in[q];
+          if (NM) vp = vp + A.c2 * A.a_in[q];
+          const T vn = vp + A.c3 * acc;
           A.v_out[q] = vn;
-          A.d_next[q] = U[c][0] + A.dt * vn;
+          T dn = U[c][0] + A.dt * vn;
+          if (NM) dn = dn + A.c1 * acc;
+          A.d_next[q] = dn;
           if (A.a_out) A.a_out[q] = acc;
         }
       }
@@ -643,7 +673,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           store_f[u] = !FUSED || bcol || A.rowflag[gz];
           if (FUSED) {
             rm[u] = A.rmass[q[u]];
-            vv[u] = A.v_in[q[u]];
+            vv[u] = __ldcg(A.v_in + q[u]);  // Newmark: already predicted by the column's owner lane
             dd[u] = A.d[q[u]];
           }
         }
@@ -654,9 +684,11 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
             A.f[q[u]] = tot[u];
           } else {
             const T acc = rm[u] * tot[u];
-            const T vn = vv[u] + A.dt * acc;
+            const T vn = vv[u] + A.c3 * acc;
             A.v_out[q[u]] = vn;
-            A.d_next[q[u]] = dd[u] + A.dt * vn;
+            T dn = dd[u] + A.dt * vn;
+            if (NM) dn = dn + A.c1 * acc;
+            A.d_next[q[u]] = dn;
             if (A.a_out) A.a_out[q[u]] = acc;
           }
         }
@@ -729,7 +761,7 @@ template <typename T>
 __global__ void k_strip_deferred(int LX, int LZ, int ndof, size_t npoin, const int* __restrict__ drows, int ndrows,
                                  const int* __restrict__ dcols, int ndcols, const uint8_t* __restrict__ rowflag,
                                  T* __restrict__ fa, T* __restrict__ v, const T* __restrict__ rmass,
-                                 const T* __restrict__ d, T* __restrict__ d_next, T dt) {
+                                 const T* __restrict__ d, T* __restrict__ d_next, T dt, T c1, T c3) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nA = (long long)ndrows * LX;
   size_t node;
@@ -746,10 +778,12 @@ __global__ void k_strip_deferred(int LX, int LZ, int ndof, size_t npoin, const i
   for (int c = 0; c < ndof; ++c) {
     const size_t q = node + npoin * c;
     const T acc = rmass[q] * fa[q];
-    const T vn = v[q] + dt * acc;
+    const T vn = v[q] + c3 * acc;  // Newmark: v already holds the predicted velocity
     fa[q] = acc;
     v[q] = vn;
-    d_next[q] = d[q] + dt * vn;
+    T dn = d[q] + dt * vn;
+    if (c1 != (T)0) dn = dn + c1 * acc;
+    d_next[q] = dn;
   }
 }
 
@@ -847,6 +881,9 @@ struct StripIO {
   const uint8_t* colflag = nullptr;
   int* meet = nullptr;
   double dt = 0.0;
+  int newmark = 0;          // fused explicit Newmark instead of leapfrog
+  double c1 = 0.0, c2 = 0.0, c3 = 0.0;
+  const T* a_in = nullptr;
   int prefetch = 1;
   // compact coefficient mode (coef holds lambda, mu only)
   int compact = 0;
@@ -855,12 +892,20 @@ struct StripIO {
   const double* wgll = nullptr;
 };
 
-template <typename T, int N, int NDOF, bool FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT)>
+template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT)>
 inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) {
   constexpr size_t smem = strip_warps() * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT);
-  if (smem > 48 * 1024 - 16 * 1024)  // per device: set on every launch (static shared memory takes up to 20 KB)
+  // Opt in to the dynamic shared memory once per device and instantiation.  Never on the step path
+  // afterwards: cudaFuncSetAttribute can serialise with running kernels, and a strip that is waiting
+  // on its neighbour's flag must not keep the neighbour's host thread from launching.
+  static bool done[64] = {};
+  int dev = 0;
+  S2D_CUDA(cudaGetDevice(&dev));
+  if (!done[dev & 63]) {
     S2D_CUDA(cudaFuncSetAttribute(k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done[dev & 63] = true;
+  }
   k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB><<<nb, strip_warps() * 32, smem, s>>>(A);
 }
 
@@ -888,6 +933,10 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
     A.colflag = io.colflag;                                                                       \
     A.meet = io.meet;                                                                             \
     A.dt = (T)io.dt;                                                                              \
+    A.c1 = (T)io.c1;                                                                              \
+    A.c2 = (T)io.c2;                                                                              \
+    A.c3 = (T)(fused && !io.newmark ? io.dt : io.c3);                                             \
+    A.a_in = io.a_in;                                                                             \
     A.prefetch = io.prefetch;                                                                     \
     for (int k = 0; k < NN * NN; ++k) A.H[k] = (T)io.hprime[k];                                   \
     A.cdx = (T)io.cdx;                                                                            \
@@ -895,23 +944,27 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
     A.cdet = (T)io.cdet;                                                                          \
     for (int k = 0; k < NN; ++k) A.wg[k] = io.wgll ? (T)io.wgll[k] : (T)0;                        \
     const unsigned nb = (unsigned)G.nitems;                                                       \
+    const int mode = !fused ? 0 : (io.newmark ? 2 : 1);                                           \
     if (G.ndof == 1) {                                                                            \
       if (io.compact) throw ArgError("compact coefficients need ndof = 2");                       \
-      if (fused) strip_launch<T, NN, 1, true, false>(nb, A, s);                                   \
-      else strip_launch<T, NN, 1, false, false>(nb, A, s);                                        \
+      if (mode == 2) strip_launch<T, NN, 1, 2, false>(nb, A, s);                                  \
+      else if (mode == 1) strip_launch<T, NN, 1, 1, false>(nb, A, s);                             \
+      else strip_launch<T, NN, 1, 0, false>(nb, A, s);                                            \
     } else if (io.compact) {                                                                      \
       if constexpr (NN == 5 && sizeof(T) == 8) {  /* measured alternative: 4 CTAs/SM, spills */    \
-        if (io.occ == 4) {                                                                        \
-          if (fused) strip_launch<T, NN, 2, true, true, 4>(nb, A, s);                             \
-          else strip_launch<T, NN, 2, false, true, 4>(nb, A, s);                                  \
+        if (io.occ == 4 && mode < 2) {                                                            \
+          if (mode == 1) strip_launch<T, NN, 2, 1, true, 4>(nb, A, s);                            \
+          else strip_launch<T, NN, 2, 0, true, 4>(nb, A, s);                                      \
           break;                                                                                  \
         }                                                                                         \
       }                                                                                           \
-      if (fused) strip_launch<T, NN, 2, true, true>(nb, A, s);                                    \
-      else strip_launch<T, NN, 2, false, true>(nb, A, s);                                         \
+      if (mode == 2) strip_launch<T, NN, 2, 2, true>(nb, A, s);                                   \
+      else if (mode == 1) strip_launch<T, NN, 2, 1, true>(nb, A, s);                              \
+      else strip_launch<T, NN, 2, 0, true>(nb, A, s);                                             \
     } else {                                                                                      \
-      if (fused) strip_launch<T, NN, 2, true, false>(nb, A, s);                                   \
-      else strip_launch<T, NN, 2, false, false>(nb, A, s);                                        \
+      if (mode == 2) strip_launch<T, NN, 2, 2, false>(nb, A, s);                                  \
+      else if (mode == 1) strip_launch<T, NN, 2, 1, false>(nb, A, s);                             \
+      else strip_launch<T, NN, 2, 0, false>(nb, A, s);                                            \
     }                                                                                             \
   } break;
   switch (G.N) {
