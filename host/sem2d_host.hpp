@@ -5,7 +5,7 @@
 // The reference is a Fortran program (no Fortran compiler exists in the build image, SURVEY.md
 // header), so this layer is what a maintainer's ISO_C_BINDING shim looks like when
 // written in C++.  Scope = what the device-side structured builder provides: &MESH_CART boxes with
-// one ELAST material, ABSORB sides, the split-node DYNFLT of `ezflt` with slip weakening, FORCE
+// one ELAST material, ABSORB and PERIOD sides, the split-node DYNFLT of `ezflt` with slip weakening, FORCE
 // and moment-tensor sources, REC_LINE stations at nodes, the leapfrog, Newmark, HHT-alpha and symplectic schemes.  Anything else in a Par.inp is
 // refused with IO_abort, never silently ignored -- except plotting (&SNAP_*), which is not on the path.
 //
@@ -191,6 +191,8 @@ inline void read_main(problem_type& pb, const std::string& file) {
         if (a->logical("let_wave", true) == false) { /* only matters with an incident wave source */ }
       }
       if (bc.tag[0] < 1 || bc.tag[0] > 4) IO_abort("BC_read: ABSORB tag must be a side of the box (1..4)");
+    } else if (bc.kind == "PERIOD") {  // SRC/bc_periodic.f90:29-40: no parameters
+      if (bc.tag[1] == 0) IO_abort("BC_read: PERIOD needs tags = master, slave");
     } else if (bc.kind == "DYNFLT") {
       if (!(bc.tag[0] == 5 && bc.tag[1] == 6)) IO_abort("BC_read: DYNFLT is provided on the split-node fault tags=5,6 of MESH_CART ezflt");
       const nml_group* f = sub("BC_DYNFLT");
@@ -223,7 +225,7 @@ inline void read_main(problem_type& pb, const std::string& file) {
       for (const char* key : {"dch", "mush", "mudh", "alpha", "alphah", "p"})
         if (w->has(key)) IO_abort(std::string("BC_DYNFLT_SWF: '") + key + "' is not provided here");
     } else {
-      IO_abort("BC_read: boundary kind '" + bc.kind + "' is not provided by the B200 structured builder (ABSORB, DYNFLT are)");
+      IO_abort("BC_read: boundary kind '" + bc.kind + "' is not provided by the B200 structured builder (ABSORB, PERIOD, DYNFLT are)");
     }
     pb.bc.push_back(bc);
   }
@@ -407,8 +409,11 @@ inline void init_main(problem_type& pb) {
     if (t.total > 0.0) t.nt = (int)std::ceil(t.total / t.dt);
     t.total = t.nt * t.dt;
   }
-  // BC_init (SRC/bc_gen.f90:190-251): input order
+  // BC_init (SRC/bc_gen.f90:190-251): periodic boundaries first, then input order
+  for (bc_type& bc : pb.bc)
+    if (bc.kind == "PERIOD") s2d_check(pb, s2d_cart_add_periodic(pb.gpu, bc.tag[0], bc.tag[1]), "BC_PERIO_init");
   for (bc_type& bc : pb.bc) {
+    if (bc.kind == "PERIOD") continue;
     if (bc.kind == "ABSORB") {
       s2d_check(pb, s2d_cart_add_abso(pb.gpu, bc.tag[0], bc.stacey ? 1 : 0), "BC_ABSO_init");
     } else {  // DYNFLT

@@ -103,6 +103,11 @@ int s2d_add_abso(s2d_handle h, int32_t np, const int32_t* node, const double* C,
 int s2d_add_dirneu(s2d_handle h, int32_t np, const int32_t* node, int32_t kind_h, int32_t kind_v,
                    const double* B_h, const double* B_v);
 
+/* bc_periodic_type (SRC/bc_periodic.f90:11-14): f(master) += f(slave); f(slave) = f(master)
+ * (BC_PERIO_set_field, :77-86), applied before every other boundary (bc_gen.f90:271-281).  The mass
+ * handed to s2d_create already carries the same sum (BC_PERIO_init, :73). */
+int s2d_add_periodic(s2d_handle h, int32_t np, const int32_t* master, const int32_t* slave);
+
 /* bc_dynflt_type (SRC/bc_dynflt.f90:18-38) after BC_DYNFLT_init (:231-520). */
 typedef struct {
   int32_t np;
@@ -243,6 +248,10 @@ int s2d_cart_create(s2d_handle* h, const s2d_cart_desc* desc);
  * adds CoefA2Vrhs*C to the mass like bc_abso.f90:243.  Must precede s2d_cart_add_fault when the
  * reference deck lists ABSORB first. */
 int s2d_cart_add_abso(s2d_handle h, int32_t side_tag, int32_t stacey);
+/* BC_PERIO_init between two opposite sides of the box: tags (4,2) / (2,4) or (1,3) / (3,1); sums the
+ * mass of the pairs (bc_periodic.f90:73).  Must precede the other boundaries, as in bc_gen.f90:221-228.
+ * Not available across x-strips (a strip with a neighbour has no left / right physical side). */
+int s2d_cart_add_periodic(s2d_handle h, int32_t master_tag, int32_t slave_tag);
 /* two-sided DYNFLT on tags 5,6 with linear slip weakening: uniform Dc, MuS, MuD, Tn, Tt, and Tt_nuc
  * where |x - x_nuc| <= half_nuc (the PWCONR patch of the TPV3 deck). */
 int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, double Tn, double Tt,

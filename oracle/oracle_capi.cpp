@@ -320,6 +320,10 @@ long long orc_array(void* hv, const char* name_, const void** ptr, char* dtype) 
     int i = std::atoi(n.substr(3, p2 - 3).c_str());
     std::string f = n.substr(p2 + 1);
     Bc& b = pb.bc[i];
+    if (b.kind == IS_PERIOD) {
+      if (f == "master") RET_I(b.perio->master->node);
+      if (f == "slave") RET_I(b.perio->slave->node);
+    }
     if (b.kind == IS_ABSORB) {
       BcAbso& a = *b.abso;
       if (f == "node") RET_I(a.topo->node);

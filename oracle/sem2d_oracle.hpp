@@ -795,9 +795,26 @@ struct BcDynflt {  // bc_dynflt_type (bc_dynflt.f90:18-38)
 };
 
 enum BcKind { IS_EMPTY = 0, IS_DIRNEU = 1, IS_KINFLT = 2, IS_ABSORB = 3, IS_PERIOD = 4, IS_LISFLT = 5, IS_DYNFLT = 6 };
+struct BcPerio {  // bc_periodic_type (bc_periodic.f90:11-14)
+  const Boundary* master = nullptr;
+  const Boundary* slave = nullptr;
+};
+// bc_periodic.f90:107-121 BC_PERIO_intersects
+inline bool BC_PERIO_intersects(const Boundary& bnd, const BcPerio* perio) {
+  if (!perio) return false;
+  auto on = [&](int node) {
+    for (int v : perio->master->node)
+      if (v == node) return true;
+    for (int v : perio->slave->node)
+      if (v == node) return true;
+    return false;
+  };
+  return on(bnd.node[0]) && on(bnd.node[bnd.npoin - 1]);
+}
 struct Bc {  // bc_type (bc_gen.f90:29-41)
   int tag[2] = {0, 0};
   int kind = IS_EMPTY;
+  std::unique_ptr<BcPerio> perio;
   std::unique_ptr<BcAbso> abso;
   std::unique_ptr<BcDirneu> dirneu;
   std::unique_ptr<BcDynflt> dynflt;
@@ -854,6 +871,7 @@ struct Problem {  // problem_type (problem_class.f90:19-46)
   std::vector<double> rmass;      // (npoin,ndof) -- mass until init end, then inverse
   std::vector<double> d, v, a_;   // fields (npoin,ndof) col-major
   std::vector<Bc> bc;
+  const BcPerio* perio = nullptr;  // the periodic boundary the other BC_*_init routines receive (bc_gen.f90:221-246)
   std::vector<Source> src;
   Receivers rec;
   int it = 0;
@@ -1105,7 +1123,7 @@ inline void MAT_MASS_init(Problem& pb) {
 inline void BC_ABSO_init(BcAbso& bc, int tag, Problem& pb) {
   Grid& g = pb.grid;
   bc.topo = g.bc_inquire(tag);
-  bc.periodic = false;
+  bc.periodic = BC_PERIO_intersects(*bc.topo, pb.perio);  // bc_abso.f90:139
   int ndof = pb.ndof, ngll = g.ngll;
   int bc_nelem = bc.topo->nelem, bc_npoin = bc.topo->npoin;
   std::vector<double> B;
@@ -1173,6 +1191,13 @@ inline void BC_ABSO_init(BcAbso& bc, int tag, Problem& pb) {
         bc.K[q] = -bc.K[q];
       }
   }
+  if (bc.periodic && bc.is_flat) {  // bc_abso.f90:226-230
+    if (bc.stacey) IO_abort("oracle: a Stacey boundary that meets a periodic one is not restated (bc_abso.f90:328-331)");
+    for (int c = 0; c < ndof; ++c) {
+      bc.C[0 + (size_t)bc_npoin * c] = bc.C[0 + (size_t)bc_npoin * c] + bc.C[(bc_npoin - 1) + (size_t)bc_npoin * c];
+      bc.C[(bc_npoin - 1) + (size_t)bc_npoin * c] = bc.C[0 + (size_t)bc_npoin * c];
+    }
+  }
   if (bc.is_flat) {
     double coef = pb.time.CoefA2Vrhs();
     for (int c = 0; c < ndof; ++c)
@@ -1230,7 +1255,7 @@ inline void BC_ABSO_apply(const BcAbso& bc, const Problem& pb, const std::vector
 inline void BC_DIRNEU_init(BcDirneu& bc, int tag, Problem& pb) {
   bc.topo = pb.grid.bc_inquire(tag);
   std::vector<double> n, B;
-  BC_get_normal_and_weights(*bc.topo, pb.grid, n, B, false);
+  BC_get_normal_and_weights(*bc.topo, pb.grid, n, B, BC_PERIO_intersects(*bc.topo, pb.perio));
   int np = bc.topo->npoin;
   bool ax = true, az = true;
   for (int k = 0; k < np; ++k) {
@@ -1527,7 +1552,7 @@ inline void BC_DYNFLT_init(BcDynflt& bc, const int tags[2], Problem& pb) {
         IO_abort("bc_dynflt_init: coordinates on boundaries do not match properly");
   {
     std::vector<double> tn, tB;
-    BC_get_normal_and_weights(*bc.bc1, g, tn, tB, false);
+    BC_get_normal_and_weights(*bc.bc1, g, tn, tB, BC_PERIO_intersects(*bc.bc1, pb.perio));
     bc.n1.assign((size_t)2 * npoin, 0.0);
     bc.B.assign((size_t)npoin * ndof, 0.0);
     int j = 0;
@@ -1774,7 +1799,34 @@ inline void BC_DYNFLT_apply(BcDynflt& bc, const Problem& pb, std::vector<double>
 }
 
 // ------------------------------------------------------------------------------------------
-// bc_gen.f90:190-250 bc_init (periodic not supported) and :256-308 bc_apply, :313-337 BC_write
+// bc_periodic.f90:77-86 BC_PERIO_set_field: the vector-subscripted sum, then the copy back
+inline void BC_PERIO_set_field(const BcPerio& bc, const Problem& pb, std::vector<double>& field) {
+  int np = bc.master->npoin;
+  for (int c = 0; c < pb.ndof; ++c) {
+    for (int k = 0; k < np; ++k)
+      field[pb.idx(bc.master->node[k], c)] = field[pb.idx(bc.master->node[k], c)] + field[pb.idx(bc.slave->node[k], c)];
+    for (int k = 0; k < np; ++k) field[pb.idx(bc.slave->node[k], c)] = field[pb.idx(bc.master->node[k], c)];
+  }
+}
+// bc_periodic.f90:44-74 BC_PERIO_init
+inline void BC_PERIO_init(BcPerio& bc, const int tags[2], Problem& pb) {
+  const Grid& g = pb.grid;
+  bc.master = g.bc_inquire(tags[0]);
+  bc.slave = g.bc_inquire(tags[1]);
+  if (bc.master->nelem != bc.slave->nelem) IO_abort("bc_perio_init: number of boundary elements do not match");
+  if (bc.master->npoin != bc.slave->npoin) IO_abort("bc_perio_init: number of nodes on boundaries do not match");
+  const double TINY_XABS = 1e-3;  // constants.f90:36
+  double s1 = g.coord[2 * (size_t)(bc.master->node[0] - 1)] - g.coord[2 * (size_t)(bc.slave->node[0] - 1)];
+  double s2 = g.coord[2 * (size_t)(bc.master->node[0] - 1) + 1] - g.coord[2 * (size_t)(bc.slave->node[0] - 1) + 1];
+  for (int k = 0; k < bc.master->npoin; ++k) {
+    size_t m = (size_t)(bc.master->node[k] - 1), sl = (size_t)(bc.slave->node[k] - 1);
+    if (std::fabs(g.coord[2 * m] - g.coord[2 * sl] - s1) > TINY_XABS || std::fabs(g.coord[2 * m + 1] - g.coord[2 * sl + 1] - s2) > TINY_XABS)
+      IO_abort("bc_perio_init: coordinates on boundaries do not match properly");
+  }
+  BC_PERIO_set_field(bc, pb, pb.rmass);
+}
+
+// bc_gen.f90:190-250 bc_init and :256-308 bc_apply, :313-337 BC_write
 inline void BC_write(Problem& pb, int itime) {
   for (auto& b : pb.bc)
     if (b.kind == IS_DYNFLT) BC_DYNFLT_write(*b.dynflt, pb, itime);
@@ -1783,6 +1835,12 @@ inline void BC_init(Problem& pb) {
   for (auto& b : pb.bc)
     for (int j = 0; j < 2; ++j)
       if (b.tag[j] != 0 && !pb.grid.bc_inquire(b.tag[j])) b.kind = IS_EMPTY;
+  pb.perio = nullptr;  // first the periodic boundaries (bc_gen.f90:221-228)
+  for (auto& b : pb.bc)
+    if (b.kind == IS_PERIOD) {
+      BC_PERIO_init(*b.perio, b.tag, pb);
+      pb.perio = b.perio.get();
+    }
   for (auto& b : pb.bc) {
     switch (b.kind) {
       case IS_DIRNEU: BC_DIRNEU_init(*b.dirneu, b.tag[0], pb); break;
@@ -1794,6 +1852,8 @@ inline void BC_init(Problem& pb) {
   BC_write(pb, 0);
 }
 inline void BC_apply(Problem& pb, std::vector<double>& field) {
+  for (auto& b : pb.bc)  // first periodic, then absorbing, then the rest (bc_gen.f90:271-281)
+    if (b.kind == IS_PERIOD) BC_PERIO_set_field(*b.perio, pb, field);
   for (auto& b : pb.bc)
     if (b.kind == IS_ABSORB) BC_ABSO_apply(*b.abso, pb, pb.d, pb.v, pb.a_);
   for (auto& b : pb.bc) {
@@ -2454,6 +2514,10 @@ inline void read_main(Problem& pb, CartSpec& cart, ParInp& in) {
         const NmlGroup* ga = in.next("BC_ABSORB");
         b.abso->stacey = ga ? ga->logical("stacey", false) : false;
         b.abso->let_wave = ga ? ga->logical("let_wave", true) : true;
+      } else if (kind == "PERIOD") {  // BC_PERIO_read (bc_periodic.f90:29-40): no parameters
+        b.kind = IS_PERIOD;
+        b.perio.reset(new BcPerio());
+        if (b.tag[1] == 0) IO_abort("bc_read: PERIOD needs tags = master, slave");
       } else if (kind == "DIRNEU") {  // bc_DIRNEU_read (bc_dirneu.f90:50-112)
         b.kind = IS_DIRNEU;
         b.dirneu.reset(new BcDirneu());

@@ -83,6 +83,8 @@ _SIGS = {
     "s2d_add_dirneu": [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
     "s2d_add_dynflt": [C.c_void_p, C.POINTER(DynfltDesc), C.POINTER(C.c_int32)],
     "s2d_add_force": [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)],
+    "s2d_add_periodic": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
+    "s2d_cart_add_periodic": [C.c_void_p, C.c_int32, C.c_int32],
     "s2d_add_moment": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)],
     "s2d_add_receivers": [C.c_void_p, C.c_int32, C.c_char, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                           C.c_void_p, C.c_void_p],

@@ -87,6 +87,19 @@ __global__ void k_sources(T* f, size_t npoin, int ndof, int nsrc, const int* igl
   }
 }
 
+// periodic boundary (BC_PERIO_set_field, bc_periodic.f90:77-86)
+template <typename T>
+__global__ void k_periodic(T* f, size_t npoin, int ndof, int np, const int* master, const int* slave) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= np) return;
+  for (int c = 0; c < ndof; ++c) {
+    const size_t m = (size_t)(master[k] - 1) + npoin * c, s = (size_t)(slave[k] - 1) + npoin * c;
+    const T sum = f[m] + f[s];
+    f[m] = sum;
+    f[s] = sum;
+  }
+}
+
 // moment-tensor sources (SRC_MOMENT_add, src_moment.f90:183-197): one thread per source walks its
 // terms in the reference's order (a node can appear in several terms)
 template <typename T>

@@ -362,6 +362,7 @@ struct CartState {
   double H[100];
   bool mass_inverted = false;
   bool bc_added = false;
+  int perio_lr = 0, perio_bt = 0;   // periodic pairs: left-right (tags 4,2), bottom-top (tags 1,3)
   std::vector<double> fault_coord;  // (2, np) bc%coord of the split-node fault
   std::vector<double> fault_T0;     // (np, 2), fault_B (np): initial tractions and node weights (FltXX_init_sem2d.tab)
   std::vector<double> fault_B;
@@ -677,6 +678,14 @@ int s2d_cart_add_abso(s2d_handle h, int32_t side, int32_t stacey) {
       }
     }
   }
+  // the boundary meets a periodic one at both ends (BC_PERIO_intersects): bc_abso.f90:226-230
+  if ((horiz && S.perio_lr) || (!horiz && S.perio_bt)) {
+    S2D_REQUIRE(!st, "cart_add_abso: a Stacey boundary that meets a periodic one is not provided (bc_abso.f90:328-331)");
+    for (int c = 0; c < ndof; ++c) {
+      C[0 + (size_t)np * c] = C[0 + (size_t)np * c] + C[(np - 1) + (size_t)np * c];
+      C[(np - 1) + (size_t)np * c] = C[0 + (size_t)np * c];
+    }
+  }
   Eb->add_abso(np, node.data(), C.data(), 1, nullptr, st ? 1 : 0, ne, bibool.data(), st ? K.data() : nullptr);
   // bc_abso.f90:243: the implicit treatment of C*v augments the mass
   DevBuf<int> dn;
@@ -688,6 +697,48 @@ int s2d_cart_add_abso(s2d_handle h, int32_t side, int32_t stacey) {
   else
     k_add_mass<float><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<float>(Eb)->rmass.p, Eb->npoin, ndof, np, dn.p, dC.p, S.CoefA2Vrhs());
   S2D_CUDA(cudaStreamSynchronize(Eb->stream));
+  CART_GUARD_END
+}
+
+// BC_PERIO_init (bc_periodic.f90:44-74) between two opposite sides of the box
+int s2d_cart_add_periodic(s2d_handle h, int32_t master_tag, int32_t slave_tag) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(!Eb->committed, "cart_add_periodic after commit");
+  S2D_REQUIRE(!S.bc_added, "cart_add_periodic: periodic boundaries are initialised before the others (bc_gen.f90:221-228)");
+  const CartGeom& G = S.G;
+  const bool lr = (master_tag == 4 && slave_tag == 2) || (master_tag == 2 && slave_tag == 4);
+  const bool bt = (master_tag == 1 && slave_tag == 3) || (master_tag == 3 && slave_tag == 1);
+  S2D_REQUIRE(lr || bt, "cart_add_periodic: tags must be two opposite sides of the box");
+  S2D_REQUIRE(!(lr && (G.halo_left || G.halo_right)), "cart_add_periodic: not available across x-strips");
+  const int LX = G.S.LX, LZ = G.S.LZ;
+  const int np = lr ? LZ : LX;
+  std::vector<int> m(np), sl(np);
+  for (int k = 0; k < np; ++k) {
+    int a, b;  // lattice ids (1-based) of the pair, in the order of the sorted boundary node lists
+    if (lr) {
+      a = k * LX + 1;            // tag 4, left
+      b = k * LX + LX;           // tag 2, right
+      if (master_tag == 2) std::swap(a, b);
+    } else {
+      a = k + 1;                 // tag 1, bottom
+      b = (LZ - 1) * LX + k + 1; // tag 3, top
+      if (master_tag == 3) std::swap(a, b);
+    }
+    m[k] = a;
+    sl[k] = b;
+  }
+  Eb->add_periodic(np, m.data(), sl.data());
+  // the mass of the pairs is summed (bc_periodic.f90:73); rmass still holds the mass here
+  DevBuf<int> dm, ds;
+  dm.upload(m);
+  ds.upload(sl);
+  if (Eb->prec == 8)
+    k_periodic<double><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<double>(Eb)->rmass.p, Eb->npoin, G.ndof, np, dm.p, ds.p);
+  else
+    k_periodic<float><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<float>(Eb)->rmass.p, Eb->npoin, G.ndof, np, dm.p, ds.p);
+  S2D_CUDA(cudaStreamSynchronize(Eb->stream));
+  if (lr) S.perio_lr = 1;
+  else S.perio_bt = 1;
   CART_GUARD_END
 }
 
@@ -723,6 +774,10 @@ int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, doub
       T0[pos] = nuc ? Tt_nuc : Tt;                        // bc_dynflt.f90:392-400 with no background stress
       T0[pos + np] = Tn;
     }
+  if (S.perio_lr) {  // BC_get_normal_and_weights(..., periodic) (spec_grid.f90:1000-1005)
+    B[0] = B[0] + B[np - 1];
+    B[np - 1] = B[0];
+  }
   if (ndof == 2)
     for (int k = 0; k < np; ++k) B[k + np] = B[k];
   // invM at the fault nodes from the current mass (bc_dynflt.f90:338-343)

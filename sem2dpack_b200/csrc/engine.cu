@@ -163,6 +163,9 @@ int s2d_add_force(s2d_handle h, int32_t iglob, const double dir[2], int32_t* src
     if (src_id) *src_id = id;
   });
 }
+int s2d_add_periodic(s2d_handle h, int32_t np, const int32_t* master, const int32_t* slave) {
+  return guard(h, [&](EngineBase& E) { E.add_periodic(np, master, slave); });
+}
 int s2d_add_moment(s2d_handle h, int32_t nterms, const int32_t* node, const double* coef, int32_t* src_id) {
   return guard(h, [&](EngineBase& E) {
     int id = E.add_moment(nterms, node, coef);

@@ -77,6 +77,7 @@ class EngineBase {
   virtual void add_dirneu(int np, const int32_t* node, int kind_h, int kind_v, const double* B_h,
                           const double* B_v) = 0;
   virtual int add_dynflt(const s2d_dynflt_desc& d) = 0;
+  virtual void add_periodic(int np, const int32_t* master, const int32_t* slave) = 0;
   virtual int add_force(int iglob, const double dir[2]) = 0;
   virtual int add_moment(int nterms, const int32_t* node, const double* coef) = 0;
   virtual void add_receivers(int nx, char field, int isamp, int nt_rec, int at_node, const int32_t* iglob,
@@ -126,6 +127,12 @@ class Engine : public EngineBase {
   std::vector<std::unique_ptr<DirneuBc>> dirneu;
   std::vector<std::unique_ptr<FaultBc>> faults;
   std::vector<BcRef> bc_order;
+  // periodic boundaries: pairs of nodes whose forces are summed first (bc_gen.f90:271-275)
+  struct PerioBc {
+    int np = 0;
+    DevBuf<int> master, slave;
+  };
+  std::vector<std::unique_ptr<PerioBc>> perio;
   int n_neumann_slots = 0;
   // sources
   std::vector<int32_t> h_src_iglob;
@@ -702,6 +709,22 @@ class Engine : public EngineBase {
     return (int)h_src_iglob.size() - 1;
   }
 
+  void add_periodic(int np, const int32_t* master, const int32_t* slave) override {
+    S2D_REQUIRE(!committed, "add_periodic after commit");
+    S2D_REQUIRE(np > 0 && master && slave, "add_periodic: empty boundary");
+    check_nodes(np, master, "add_periodic");
+    check_nodes(np, slave, "add_periodic");
+    std::unique_ptr<PerioBc> b(new PerioBc());
+    b->np = np;
+    b->master.upload(std::vector<int32_t>(master, master + np));
+    b->slave.upload(std::vector<int32_t>(slave, slave + np));
+    std::vector<int32_t> both(master, master + np);
+    both.insert(both.end(), slave, slave + np);
+    h_bc_nodes.emplace_back(master, master + np);  // two lists: each side flags its own row / column
+    h_bc_nodes.emplace_back(slave, slave + np);
+    perio.push_back(std::move(b));
+  }
+
   int add_moment(int nterms, const int32_t* node, const double* coef_) override {
     S2D_REQUIRE(!committed, "add_moment after commit");
     S2D_REQUIRE(nterms > 0 && node && coef_, "add_moment: empty source");
@@ -1020,7 +1043,11 @@ class Engine : public EngineBase {
   void launch_bcs(const T* D) {
     const T* V = v.p;
     T* f = a.p;
-    // bc_gen.f90:273-281: absorbing boundaries first, then the others in input order
+    // bc_gen.f90:271-281: periodic boundaries first, then absorbing, then the others in input order
+    for (auto& b : perio) {
+      k_periodic<T><<<ceil_div(b->np, 128), 128, 0, stream>>>(f, npoin, ndof, b->np, b->master.p, b->slave.p);
+      launches++;
+    }
     for (auto& r : bc_order)
       if (r.kind == BC_ABSO) {
         AbsoBc& b = *abso[r.index];

@@ -125,6 +125,11 @@ class Engine:
         self._ck(self.L.s2d_add_force(self.h, int(iglob), _ptr(_f64(direction)), C.byref(sid)))
         return sid.value
 
+    def add_periodic(self, master, slave):
+        """bc_periodic_type (SRC/bc_periodic.f90): f(master) += f(slave); f(slave) = f(master)"""
+        master, slave = _i32(master), _i32(slave)
+        self._ck(self.L.s2d_add_periodic(self.h, master.size, _ptr(master), _ptr(slave)))
+
     def add_moment(self, node, coef):
         """so_moment_type after SRC_MOMENT_init (SRC/src_moment.f90:129-180): node (nterms) and
         coef (nterms, ndof) column-major, in the order SRC_MOMENT_add applies them."""
@@ -288,6 +293,9 @@ class CartEngine(Engine):
         sid = C.c_int32(-1)
         self._ck(self.L.s2d_cart_add_force(self.h, x, z, _ptr(_f64(direction)), C.byref(sid)))
         return sid.value
+
+    def add_periodic_sides(self, master_tag, slave_tag):
+        self._ck(self.L.s2d_cart_add_periodic(self.h, master_tag, slave_tag))
 
     def add_moment_at(self, x, z, M):
         """M(2,ndof) column-major as so%M (SRC/src_moment.f90:44-100)"""

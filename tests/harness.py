@@ -11,7 +11,7 @@ from sem2dpack_b200 import Engine
 from sem2dpack_b200.capi import S2D_ASM_PATCH
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-IS_ABSORB, IS_DIRNEU, IS_DYNFLT = 3, 1, 6
+IS_ABSORB, IS_DIRNEU, IS_DYNFLT, IS_PERIOD = 3, 1, 6, 4
 
 
 def deck(name):
@@ -30,13 +30,15 @@ def nuc_radius(nx, h=100.0):
 
 
 def cart_deck(nx, nz, ngll=5, ndof=2, ezflt=0, scheme="leapfrog", courant=0.5, nsteps=50, h=100.0, fault="swf",
-              abso=(1, 2, 3, 4), stacey=False, nrec=8, src=True):
+              abso=(1, 2, 3, 4), stacey=False, nrec=8, src=True, periodic=None):
     """A MESH_CART deck of the synthetic benchmark family at test size."""
     L = [f"&GENERAL iexec=1, ngll={ngll}, fmax=3.d0, ndof={ndof}, title='synthetic', verbose='0000', ItInfo=1000 /",
          "&MESH_DEF method='CARTESIAN' /",
          f"&MESH_CART xlim=0d0,{nx*h}d0, zlim=0d0,{nz*h}d0, nelem={nx},{nz}" + (f", ezflt={ezflt}" if ezflt else "") + " /",
          "&MATERIAL tag=1, kind='ELAST' /",
          "&MAT_ELASTIC rho=2670.d0, cp=6000.d0, cs=3464.d0 /"]
+    if periodic:
+        L += [f"&BC_DEF tags={periodic[0]},{periodic[1]}, kind='PERIOD' /"]
     if ezflt and fault:
         L += ["&BC_DEF tags=5,6, kind='DYNFLT' /"]
         if fault == "swf":
@@ -83,7 +85,9 @@ class Rig:
         for i in range(o.i("nbc")):
             k = o.i(f"bc.{i}.kind")
             p = f"bc.{i}."
-            if k == IS_ABSORB:
+            if k == IS_PERIOD:
+                e.add_periodic(o.arr(p + "master"), o.arr(p + "slave"))
+            elif k == IS_ABSORB:
                 st = bool(o.i(p + "stacey"))
                 e.add_abso(o.arr(p + "node"), o.arr(p + "C"), is_flat=bool(o.i(p + "is_flat")), n=o.arr(p + "n"),
                            stacey=st, bibool=o.arr(p + "bibool") if st else None, K=o.arr(p + "K") if st else None)

@@ -114,6 +114,52 @@ def test_structured_builder_moment_and_fused_step(x, z):
     o.close()
 
 
+def test_periodic_boundary_generic_engine():
+    """bc_periodic.f90: Lamb's deck with the left and right sides tied together instead of absorbing;
+    the bottom absorbing boundary meets the periodic one at both ends (C merged, bc_abso.f90:226-230)"""
+    text = harness.deck("lamb")
+    text = text.replace("&BC_DEF  tag = 2 , kind = 'ABSORB' /\n&BC_ABSORB  stacey=F/\n", "&BC_DEF  tags = 4,2 , kind = 'PERIOD' /\n")
+    text = text.replace("&BC_DEF  tag = 4 , kind = 'ABSORB' /\n&BC_ABSORB  stacey=F/\n", "")
+    assert "PERIOD" in text and text.count("ABSORB") == 2
+    (ed, ev, ea), (s_got, s_ref), r = _run(text, 600)
+    assert r.o.i("bc.1.kind") == harness.IS_PERIOD or r.o.i("bc.0.kind") == harness.IS_PERIOD
+    assert ed <= 1e-10 and ev <= 1e-10 and ea <= 1e-10, (ed, ev, ea)
+    d = r.o.arr("d")
+    m = r.o.arr("bc.1.master") if r.o.i("bc.1.kind") == harness.IS_PERIOD else r.o.arr("bc.0.master")
+    s = r.o.arr("bc.1.slave") if r.o.i("bc.1.kind") == harness.IS_PERIOD else r.o.arr("bc.0.slave")
+    assert np.array_equal(d[m - 1], d[s - 1]) and np.abs(d[m - 1]).max() > 0   # the two sides move together
+    r.close()
+
+
+@pytest.mark.parametrize("scheme", ["leapfrog", "newmark"])
+def test_periodic_boundary_structured_builder(scheme):
+    """s2d_cart_add_periodic + fused step: periodic left/right, absorbing bottom/top, the two-sided fault
+    running into the periodic sides (its end weights merged, spec_grid.f90:1000-1005)"""
+    nx, nz, ezflt, nsteps, h = 24, 16, 8, 300, 100.0
+    o = orc.Oracle(harness.cart_deck(nx, nz, ezflt=ezflt, scheme=scheme, nsteps=nsteps, abso=(1, 3), periodic=(4, 2)),
+                   synthetic_seed=20261017, renumber=False)
+    e = CartEngine(5, 2, nx, nz, (0.0, nx * h), (0.0, nz * h), ezflt=ezflt, seed=20261017,
+                   scheme_kind=0 if scheme == "leapfrog" else 1, courant=0.5)
+    e.add_periodic_sides(4, 2)
+    fid = e.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, nx * h / 2, harness.nuc_radius(nx, h), nt_max=nsteps)
+    for side in (1, 3):
+        e.add_abso_side(side, False)
+    e.add_force_at(0.37 * nx * h, 0.61 * nz * h, [o.f("src.0.dir1"), o.f("src.0.dir2")])
+    e.commit()
+    tab = np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)])
+    e.step(nsteps, tab)
+    o.step(nsteps)
+    d, v, a = e.get_fields()
+    assert rel_l2(d, o.arr("d")) <= 1e-10 and rel_l2(v, o.arr("v")) <= 1e-10 and rel_l2(a, o.arr("acc")) <= 1e-10
+    ibf = [i for i in range(o.i("nbc")) if o.i(f"bc.{i}.kind") == harness.IS_DYNFLT][0]
+    st = e.fault_state(fid, o.i(f"bc.{ibf}.np"))
+    for k in ("D", "V", "T"):
+        assert rel_l2(st[k], o.arr(f"bc.{ibf}.{k}")) <= 1e-10, k
+    assert np.abs(st["D"]).max() > 1e-3
+    e.close()
+    o.close()
+
+
 def test_host_program_takes_the_new_blocks(tmp_path):
     """sem2dsolve_b200 on a TestSH deck with a moment source and the PFR symplectic scheme"""
     text = harness.deck("testsh").replace("mechanism= 'FORCE'", "mechanism= 'MOMENT'")
