@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--fint-reps", type=int, default=10)
     ap.add_argument("--coef", choices=["compact", "full"], default="compact",
                     help="coefficient storage: (lambda, mu) per GLL point, or all six planes a(5,5,6) per element")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: every GPU owns an --nx x --nz strip; strong: the --nx x --nz mesh is split over the GPUs")
     ap.add_argument("--scheme", choices=["leapfrog", "newmark"], default="leapfrog",
                     help="time scheme of the workload (BASELINE configs[4]: leapfrog/Newmark); newmark = explicit, beta=0")
     ap.add_argument("--halo", choices=["peer", "nccl"], default="peer",
@@ -223,6 +225,10 @@ def main():
     nt_max = 2 * (K + W) + 16
     # build, falling back to a shorter mesh if 180 GB cannot hold the requested one
     nx, nz = args.nx, args.nz
+    if args.scaling == "strong":
+        if nx % world:
+            raise SystemExit("--scaling strong needs --nx divisible by the number of GPUs")
+        nx //= world
     e = None
     tried = []
     def sync_dt(dt_local):
@@ -327,7 +333,7 @@ def main():
     vmax, dmax = e.progress()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64" if args.precision == 8 else "f32", "data": "synthetic",
         "config": {"workload": f"synthetic {nx * world}x{nz} Q4 structured mesh ({nx}x{nz} x-strip per GPU), NGLL=5, "
                                "ndof=2 heterogeneous isotropic elastic (material differs at every GLL point) + planar "

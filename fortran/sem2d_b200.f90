@@ -1,0 +1,155 @@
+! sem2d_b200.f90 -- ISO_C_BINDING interface to libsem2d_b200.so (include/sem2d_b200.h).
+!
+! This is the module a SEM2DPACK maintainer adds to SRC/ (INTEGRATION.md has the call sites).  It is
+! delivered as source: no Fortran compiler exists in the build image (SURVEY.md header), so it is not
+! compiled here; the same C entry points are exercised by the C++ host (host/) and by ctypes
+! (sem2dpack_b200/capi.py) in every GPU test.  Arrays are passed as they are in the reference:
+! column-major, 1-based node / element ids, default integers, double precision.
+module sem2d_b200
+  use iso_c_binding
+  implicit none
+  type, bind(C) :: s2d_scheme            ! timescheme_type, time.f90:5-11
+    integer(c_int32_t) :: kind           ! 0 leapfrog (solver.f90:140-160), 1 newmark (:42-84),
+                                         ! 2 HHT-alpha (:89-128), 3 symplectic (:169-199)
+    real(c_double) :: dt, beta, gamma, alpha
+    integer(c_int32_t) :: nstages        ! time%nstages, time%a(1:nstages+1), time%b(1:nstages)
+    real(c_double) :: coa(9), cob(8)
+  end type
+  interface
+    integer(c_int) function s2d_create(h, ngll, ndof, nelem, npoin, ibool, hprime, rmass, precision, scheme, device) &
+        bind(C, name='s2d_create')
+      import
+      type(c_ptr), intent(out) :: h
+      integer(c_int32_t), value :: ngll, ndof, nelem, npoin, precision, device
+      integer(c_int32_t), intent(in) :: ibool(*)        ! grid%ibool(ngll,ngll,nelem)   spec_grid.f90:52
+      real(c_double), intent(in) :: hprime(*), rmass(*) ! grid%hprime, pb%rmass(npoin,ndof)
+      type(s2d_scheme), intent(in) :: scheme
+    end function
+    integer(c_int) function s2d_set_elastic(h, nelast, ncoefsets, a, elem2set, kd2) bind(C, name='s2d_set_elastic')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: nelast, ncoefsets, kd2
+      real(c_double), intent(in) :: a(*)                ! a(ngll,ngll,nelast) blocks   mat_elastic.f90:290-360
+      integer(c_int32_t), intent(in) :: elem2set(*)
+    end function
+    integer(c_int) function s2d_set_kv(h, nkv, elem_ids, eta) bind(C, name='s2d_set_kv')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: nkv
+      integer(c_int32_t), intent(in) :: elem_ids(*)
+      real(c_double), intent(in) :: eta(*)              ! eta(ngll,ngll) per KV element, already *dt
+    end function
+    integer(c_int) function s2d_add_abso(h, np, node, C, is_flat, n, stacey, nbe, bibool, K) bind(C, name='s2d_add_abso')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: np, is_flat, stacey, nbe
+      integer(c_int32_t), intent(in) :: node(*), bibool(*)
+      real(c_double), intent(in) :: C(*), n(*), K(*)    ! bc_abso_type, bc_abso.f90:38-46
+    end function
+    integer(c_int) function s2d_add_periodic(h, np, master, slave) bind(C, name='s2d_add_periodic')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: np
+      integer(c_int32_t), intent(in) :: master(*), slave(*)   ! bc%master%node, bc%slave%node   bc_periodic.f90:11-14
+    end function
+    integer(c_int) function s2d_add_dirneu(h, np, node, kind_h, kind_v, B_h, B_v) bind(C, name='s2d_add_dirneu')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: np, kind_h, kind_v
+      integer(c_int32_t), intent(in) :: node(*)
+      type(c_ptr), value :: B_h, B_v                     ! c_null_ptr = homogeneous Neumann
+    end function
+    integer(c_int) function s2d_add_dynflt(h, desc, fault_id) bind(C, name='s2d_add_dynflt')
+      import
+      type(c_ptr), value :: h
+      type(c_ptr), value :: desc                         ! type(s2d_dynflt_desc), see the header
+      integer(c_int32_t), intent(out) :: fault_id
+    end function
+    integer(c_int) function s2d_add_force(h, iglob, dir, src_id) bind(C, name='s2d_add_force')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: iglob
+      real(c_double), intent(in) :: dir(2)
+      integer(c_int32_t), intent(out) :: src_id
+    end function
+    integer(c_int) function s2d_add_moment(h, nterms, node, coef, src_id) bind(C, name='s2d_add_moment')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: nterms
+      integer(c_int32_t), intent(in) :: node(*)          ! iglob_xi(:,k), iglob_eta(:,k), k = 1..nel   src_moment.f90:150-152
+      real(c_double), intent(in) :: coef(*)              ! coef_xi(:,:,k), coef_eta(:,:,k) as (nterms,ndof)
+      integer(c_int32_t), intent(out) :: src_id
+    end function
+    integer(c_int) function s2d_add_receivers(h, nx, field, isamp, nt_rec, at_node, iglob, einterp, interp) &
+        bind(C, name='s2d_add_receivers')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: nx, isamp, nt_rec, at_node
+      character(kind=c_char), value :: field
+      type(c_ptr), value :: iglob, einterp, interp
+    end function
+    integer(c_int) function s2d_commit(h, variant) bind(C, name='s2d_commit')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: variant               ! 0 patch (default), 1 colour, 2 atomic
+    end function
+    integer(c_int) function s2d_set_fields(h, d, v, a) bind(C, name='s2d_set_fields')
+      import
+      type(c_ptr), value :: h
+      real(c_double), intent(in) :: d(*), v(*), a(*)
+    end function
+    integer(c_int) function s2d_get_fields(h, d, v, a) bind(C, name='s2d_get_fields')
+      import
+      type(c_ptr), value :: h
+      real(c_double), intent(out) :: d(*), v(*), a(*)
+    end function
+    integer(c_int) function s2d_step(h, nsteps, src_ampli, bc_ampli) bind(C, name='s2d_step')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: nsteps
+      type(c_ptr), value :: src_ampli, bc_ampli          ! (nsrc,nsteps), (2*ndirneu,nsteps) or c_null_ptr
+    end function
+    integer(c_int) function s2d_get_seis(h, sis) bind(C, name='s2d_get_seis')
+      import
+      type(c_ptr), value :: h
+      real(c_float), intent(out) :: sis(*)               ! rec%sis(nt,nx,ndof)   receivers.f90:12
+    end function
+    integer(c_int) function s2d_get_fault(h, fault_id, records, nout, potency, ncalls) bind(C, name='s2d_get_fault')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: fault_id
+      type(c_ptr), value :: records, potency
+      integer(c_int32_t), intent(out) :: nout, ncalls
+    end function
+    integer(c_int) function s2d_progress(h, vmax, dmax) bind(C, name='s2d_progress')
+      import
+      type(c_ptr), value :: h
+      real(c_double), intent(out) :: vmax, dmax
+    end function
+    integer(c_int) function s2d_destroy(h) bind(C, name='s2d_destroy')
+      import
+      type(c_ptr), value :: h
+    end function
+    type(c_ptr) function s2d_last_error(h) bind(C, name='s2d_last_error')
+      import
+      type(c_ptr), value :: h
+    end function
+  end interface
+contains
+  subroutine s2d_check(h, rc)             ! error behaviour of the reference: IO_abort (stdio.f90:205-214)
+    use stdio, only : IO_abort
+    type(c_ptr), intent(in) :: h
+    integer(c_int), intent(in) :: rc
+    character(kind=c_char), pointer :: msg(:)
+    character(len=256) :: text
+    integer :: k
+    if (rc == 0) return
+    call c_f_pointer(s2d_last_error(h), msg, [256])
+    text = ' '
+    do k = 1, 256
+      if (msg(k) == c_null_char) exit
+      text(k:k) = msg(k)
+    enddo
+    call IO_abort(trim(text))
+  end subroutine
+end module sem2d_b200
