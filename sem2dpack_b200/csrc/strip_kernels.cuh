@@ -520,6 +520,8 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           for (int j = 0; j < N; ++j) hand[ez & 1][warp][c][j] = f[c][j];
       }
     }
+    // (producer / consumer named barriers between neighbouring warps instead of this CTA barrier were
+    // tried: bar.arrive / bar.sync pairs with two slots deadlocked on partially filled groups -- not pursued)
     if (WARPS > 1) __syncthreads();
     if (wact) {
       if (take) {  // column shared with the strip on the left (same group)
