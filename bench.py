@@ -353,7 +353,9 @@ def main():
                              "SURVEY 8d's canonical K1+update figure is %.1f B/DOF (%.1f with a stored)" % (B_STEP, B_STEP + W8),
                      "k1_alone": {"kernel": "k_elem_strip + k_strip_fold, plain force evaluation", "ms_per_launch": ms_fint,
                                   "algorithmic_bytes_per_dof": b_k1, "achieved": ach_k1, "frac": ach_k1 / peak,
-                                  "canonical_bytes_per_dof": B_K1},
+                                  "canonical_bytes_per_dof": B_K1, "gdof_per_s": ndofs_rank / (ms_fint * 1e-3) / 1e9,
+                                  "note": "BASELINE.md's K1 target (60 % of the roofline at the canonical 56.6 B/DOF) is "
+                                          "69.4 G DOF/s; frac is quoted on the bytes this kernel really moves"},
                      "full_step": {"algorithmic_bytes_per_dof": b_moved, "canonical_bytes_per_dof": B_STEP,
                                    "achieved": b_moved * value / world / 1e9, "frac": b_moved * value / world / 1e9 / peak,
                                    "note": "whole step (strip kernel + fold + boundary + deferred-node kernels) against "
