@@ -98,6 +98,9 @@ struct problem_type {
   std::vector<bc_type> bc;
   std::vector<source_type> src;
   std::unique_ptr<rec_type> rec;
+  // &SNAP_DEF (SRC/plot_gen.f90:58-110): binary snapshots of the node fields only
+  bool snap_bin = false, snap_fields[3] = {false, false, false};  // D, V, A
+  int snap_itd = 100, snap_it1 = 0;
   int64_t npoin = 0, nelem_total = 0;
   int it = 0;
   int precision = 8, device = -1;
@@ -344,6 +347,28 @@ inline void read_main(problem_type& pb, const std::string& file) {
     }
     pb.src.push_back(so);
   }
+  // read_plot_gen (SRC/plot_gen.f90:58-110).  PostScript / AVS / Visual3 / GMT plotting is not on the
+  // path and is skipped; binary snapshots (bin=T, the default) of D, V, A are written as PLOT_FIELD does.
+  k = in.find("SNAP_DEF");
+  {
+    std::string fields = "V";
+    pb.snap_bin = true;
+    if (k >= 0) {
+      const nml_group& g = in.at((size_t)k);
+      pb.snap_bin = g.logical("bin", true);
+      fields = g.text("fields", "V");
+      pb.snap_itd = g.integer("itd", 100);
+      pb.snap_it1 = g.integer("it1", 0);
+    }
+    for (char c : fields) {
+      if (c == 'D') pb.snap_fields[0] = true;
+      else if (c == 'V') pb.snap_fields[1] = true;
+      else if (c == 'A') pb.snap_fields[2] = true;
+      else if (pb.snap_bin && c != ' ')
+        IO_abort(std::string("SNAP_DEF: snapshot field '") + c + "' (strain, stress, divergence, curl) is not provided here");
+    }
+    if (pb.snap_itd <= 0) IO_abort("SNAP_DEF: itd must be positive");
+  }
   // REC_read (SRC/receivers.f90:62-140)
   k = in.find("REC_LINE");
   if (k >= 0) {
@@ -478,6 +503,59 @@ inline void solve(problem_type& pb, int nsteps = 1) {
   s2d_check(pb, s2d_step(pb.gpu, nsteps, ns ? ampli.data() : nullptr, nullptr), "solve");
   pb.it += nsteps;
   pb.time.time = pb.it * pb.time.dt;
+}
+
+// Grid files every reader of the snapshots needs (SE_init, SRC/spec_grid.f90:136-141,296-306,365-371):
+// grid_sem2d.hdr, ibool_sem2d.dat (int32 (ngll,ngll) per element), coord_sem2d.dat (float32 (2) per node).
+// The structured builder numbers the elements row by row (OPT_RENUMBER = .false., constants.f90:10-15).
+inline void SE_write_grid(problem_type& pb, const std::string& dir = ".") {
+  const size_t n2 = (size_t)pb.ngll * pb.ngll;
+  std::vector<int32_t> ibool(n2 * (size_t)pb.nelem_total);
+  std::vector<double> coord(2 * (size_t)pb.npoin);
+  s2d_check(pb, s2d_cart_get(pb.gpu, ibool.data(), nullptr, nullptr, coord.data()), "SE_init");
+  if (FILE* f = std::fopen((dir + "/grid_sem2d.hdr").c_str(), "w")) {
+    std::fprintf(f, " NELEM  NPGEO  NGNOD  NPOIN  NGLL\n %lld %lld 4 %lld %d\n", (long long)pb.nelem_total,
+                 (long long)(pb.nelem[0] + 1) * (pb.nelem[1] + 1) + (pb.ezflt > 0 ? pb.nelem[0] + 1 : 0), (long long)pb.npoin, pb.ngll);
+    std::fclose(f);
+  }
+  if (FILE* f = std::fopen((dir + "/ibool_sem2d.dat").c_str(), "wb")) {
+    std::fwrite(ibool.data(), sizeof(int32_t), ibool.size(), f);
+    std::fclose(f);
+  }
+  if (FILE* f = std::fopen((dir + "/coord_sem2d.dat").c_str(), "wb")) {
+    std::vector<float> c4(coord.begin(), coord.end());
+    std::fwrite(c4.data(), sizeof(float), c4.size(), f);
+    std::fclose(f);
+  }
+}
+
+// PLOT_FIELD's binary branch (SRC/plot_gen.f90:168-215 -> IO_rw_field, SRC/stdio.f90:112-139): one float32
+// per node, files <d|v|a><x|z|y>_NNN_sem2d.dat, NNN = (it-IT1)/ITD
+inline bool snapshot_due(const problem_type& pb, int it) {
+  if (!pb.snap_bin || !(pb.snap_fields[0] || pb.snap_fields[1] || pb.snap_fields[2])) return false;
+  return it >= pb.snap_it1 && (it - pb.snap_it1) % pb.snap_itd == 0;
+}
+inline void PLOT_FIELD(problem_type& pb, int it, const std::string& dir = ".") {
+  if (!snapshot_due(pb, it)) return;
+  const size_t n = (size_t)pb.npoin;
+  std::vector<double> d(n * pb.ndof), v(n * pb.ndof), a(n * pb.ndof);
+  s2d_check(pb, s2d_get_fields(pb.gpu, d.data(), v.data(), a.data()), "PLOT_FIELD");
+  const std::vector<double>* fld[3] = {&d, &v, &a};
+  const char fchar[3] = {'d', 'v', 'a'};
+  std::vector<float> buf(n);
+  for (int i = 0; i < 3; ++i) {
+    if (!pb.snap_fields[i]) continue;
+    for (int c = 0; c < pb.ndof; ++c) {
+      char name[64];
+      std::snprintf(name, sizeof(name), "%c%c_%03d_sem2d.dat", fchar[i], pb.ndof == 1 ? 'y' : (c == 0 ? 'x' : 'z'),
+                    (it - pb.snap_it1) / pb.snap_itd);
+      for (size_t q = 0; q < n; ++q) buf[q] = (float)(*fld[i])[q + n * c];
+      FILE* f = std::fopen((dir + "/" + name).c_str(), "wb");
+      if (!f) IO_abort(std::string("PLOT_FIELD: cannot open ") + name);
+      std::fwrite(buf.data(), sizeof(float), n, f);
+      std::fclose(f);
+    }
+  }
 }
 
 // rec%sis as REC_store has filled it up to now

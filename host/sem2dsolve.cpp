@@ -42,10 +42,20 @@ int main(int argc, char** argv) {
       std::printf(" iexec=0: problem checked, not solved\n");
       return 0;
     }
-    // main.f90:51-99: the loop body runs on the device in chunks that end on the ItInfo lines
+    // the snapshot files need the grid (spec_grid.f90 writes it at init); PLOT_FIELD at it = 0 (main.f90:38)
+    if (snapshot_due(pb, pb.snap_it1) && pb.snap_it1 <= pb.time.nt) SE_write_grid(pb);
+    PLOT_FIELD(pb, 0);
+    // main.f90:51-99: the loop body runs on the device in chunks that end on the ItInfo lines and on
+    // the snapshot steps
     while (pb.it < pb.time.nt) {
-      const int n = std::min(pb.ItInfo - pb.it % pb.ItInfo, pb.time.nt - pb.it);
+      int n = std::min(pb.ItInfo - pb.it % pb.ItInfo, pb.time.nt - pb.it);
+      for (int k = 1; k < n; ++k)
+        if (snapshot_due(pb, pb.it + k)) {
+          n = k;
+          break;
+        }
       solve(pb, n);
+      PLOT_FIELD(pb, pb.it);  // main.f90:82
       if (pb.it % pb.ItInfo == 0 && !quiet) {
         double vmax = 0, dmax = 0;
         s2d_check(pb, s2d_progress(pb.gpu, &vmax, &dmax), "main");

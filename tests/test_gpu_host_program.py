@@ -90,6 +90,32 @@ def test_fault_files_against_the_oracle(tmp_path):
     o.close()
 
 
+def test_binary_snapshots_and_grid_files(tmp_path):
+    """&SNAP_DEF bin=T: PLOT_FIELD's node-wise float32 files and the grid files POST/ reads them with"""
+    deck = harness.deck("lamb").replace("TotalTime=1.5d0, Dt=0.5d-3", "NbSteps=250, Dt=0.5d-3")
+    deck = deck.replace("&SNAP_DEF itd=5000, fields='V'/", "&SNAP_DEF itd=100, fields='DV', ps=F /")
+    p = run(tmp_path, deck, "--quiet")
+    assert p.returncode == 0, p.stdout + p.stderr
+    o = orc.Oracle(deck, renumber=False)
+    npoin, nelem = o.i("npoin"), o.i("nelem")
+    hdr = (tmp_path / "grid_sem2d.hdr").read_text().split("\n")[1].split()
+    assert [int(v) for v in hdr] == [nelem, 41 * 21, 4, npoin, 9]
+    ib = np.fromfile(tmp_path / "ibool_sem2d.dat", dtype=np.int32)
+    assert np.array_equal(ib, o.arr("ibool"))
+    co = np.fromfile(tmp_path / "coord_sem2d.dat", dtype=np.float32).reshape(npoin, 2)
+    assert np.abs(co - o.arr("coord").reshape(npoin, 2)).max() <= 1e-3
+    for snap, it in ((0, 0), (1, 100), (2, 200)):
+        if it:
+            o.step(100)
+        for name, key, c in (("dx", "d", 0), ("dz", "d", 1), ("vx", "v", 0), ("vz", "v", 1)):
+            got = np.fromfile(tmp_path / f"{name}_{snap:03d}_sem2d.dat", dtype=np.float32)
+            ref = o.arr(key)[c * npoin:(c + 1) * npoin]
+            assert got.shape == (npoin,)
+            assert np.abs(got - ref).max() <= 2e-7 * max(np.abs(ref).max(), 1e-30), (name, snap)
+    assert not (tmp_path / "vx_003_sem2d.dat").exists()
+    o.close()
+
+
 def test_unsupported_input_aborts_like_io_abort(tmp_path):
     """what the host does not provide is refused the way the reference refuses bad input: message +
     non-zero exit (IO_abort, stdio.f90:205-214), never ignored"""
