@@ -45,7 +45,7 @@ def moved_bytes_per_dof(fused, store_accel, compact, w=W8, newmark=False):
     return coef + 4 * w + w / NDOF + (w if store_accel else 0)
 METRIC = "GLL DOF-updates/sec"
 UNIT = "DOF-updates/s"
-CPU_SAMPLE_N = 768      # oracle sample mesh (elements per side)
+CPU_SAMPLE_N = int(os.environ.get("BENCH_CPU_SAMPLE_N", "768"))   # oracle sample mesh (elements per side)
 CPU_SAMPLE_STEPS = 20
 
 

@@ -198,3 +198,42 @@ def test_strip_kernel_fint(ngll, ndof, nx, nz, ezflt, seg, monkeypatch):
     assert np.array_equal(e.compute_fint(), got)
     e.close()
     o.close()
+
+
+@pytest.mark.parametrize("ngll,ndof,nx,nz,ezflt,seg,scheme", [
+    (5, 2, 27, 11, 0, 3, "leapfrog"),     # two full groups + a 1-strip remainder, 4 bands, no fault
+    (5, 2, 50, 12, 5, 2, "newmark"),      # three groups (one partial), bands of 2 rows on both sides of the fault
+    (5, 1, 31, 9, 4, 4, "leapfrog"),      # SH
+    (5, 1, 26, 7, 3, 1, "newmark"),       # SH, one element row per band: every row boundary is shared
+    (6, 2, 23, 10, 3, 3, "newmark"),      # 5 elements per strip (the TPV3 order)
+    (9, 2, 14, 6, 2, 2, "leapfrog"),      # 3 elements per strip (the Lamb order)
+    (3, 2, 47, 8, 4, 5, "leapfrog"),      # 10 elements per strip
+    (5, 2, 6, 40, 17, 32, "newmark"),     # a single strip, tall
+    (4, 2, 33, 5, 2, 64, "leapfrog"),     # band taller than the mesh
+])
+def test_fused_step_decompositions(ngll, ndof, nx, nz, ezflt, seg, scheme, monkeypatch):
+    """the fused leapfrog / explicit Newmark step over strip, group and band decompositions that exercise
+    every hand-over: strips of one CTA, columns finished by the second CTA to arrive, rows shared by
+    two bands, their corners, deferred boundary rows and columns, the duplicated fault row"""
+    monkeypatch.setenv("S2D_SEG", str(seg))
+    nsteps, h = 80, 100.0
+    o = orc.Oracle(harness.cart_deck(nx, nz, ngll=ngll, ndof=ndof, ezflt=ezflt, scheme=scheme, nsteps=nsteps, nrec=0,
+                                     fault="swf" if ezflt else None),
+                   synthetic_seed=SEED, renumber=False)
+    e = CartEngine(ngll, ndof, nx, nz, (0.0, nx * h), (0.0, nz * h), ezflt=ezflt, seed=SEED,
+                   scheme_kind=0 if scheme == "leapfrog" else 1, courant=0.5)
+    if ezflt:
+        e.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, nx * h / 2, harness.nuc_radius(nx, h), nt_max=nsteps)
+    for side in (1, 2, 3, 4):
+        e.add_abso_side(side, False)
+    e.add_force_at(0.37 * nx * h, 0.61 * nz * h, [o.f("src.0.dir1"), o.f("src.0.dir2")])
+    e.commit()
+    tab = np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)])
+    e.step(30, tab[:30])
+    e.step(nsteps - 30, tab[30:])
+    o.step(nsteps)
+    d, v, a = e.get_fields()
+    assert rel_l2(d, o.arr("d")) <= 1e-10 and rel_l2(v, o.arr("v")) <= 1e-10 and rel_l2(a, o.arr("acc")) <= 1e-10
+    assert np.abs(d).max() > 0
+    e.close()
+    o.close()
