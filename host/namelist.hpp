@@ -19,6 +19,7 @@ namespace sem2d {
 struct nml_group {
   std::string name;                                         // upper case, without '&'
   std::map<std::string, std::vector<std::string>> items;    // lower-case key -> value tokens
+  size_t end_pos = 0;                                       // offset of the closing '/' in namelist_file::text()
   bool has(const std::string& k) const { return items.count(k) != 0; }
   static double to_double(std::string t) {
     for (char& c : t)
@@ -64,9 +65,25 @@ class namelist_file {
       if (p != std::string::npos && (line[p] == '#' || line[p] == '!')) continue;
       ss << line << '\n';
     }
-    parse(ss.str());
+    text_ = ss.str();
+    parse(text_);
   }
   size_t size() const { return groups_.size(); }
+  const std::string& text() const { return text_; }
+  // The list-directed records (read(iin,*)) that follow group k: the next n numbers, starting on the line
+  // after the one that closes the group (e.g. SRC/distribution_order0.f90:55-69, distribution_pwconr.f90:36-40)
+  std::vector<double> records_after(size_t k, size_t n) const {
+    size_t p = text_.find('\n', groups_[k].end_pos);
+    std::vector<double> v;
+    if (p == std::string::npos) return v;
+    std::stringstream ss(text_.substr(p + 1));
+    std::string tok;
+    while (v.size() < n && ss >> tok) {
+      if (tok[0] == '&') break;
+      v.push_back(nml_group::to_double(tok));
+    }
+    return v;
+  }
   const nml_group& at(size_t k) const { return groups_[k]; }
   // index of the first group called `name` at or after `from`, or -1 (END= branch of the read)
   long find(const std::string& name, size_t from = 0) const {
@@ -77,6 +94,7 @@ class namelist_file {
 
  private:
   std::vector<nml_group> groups_;
+  std::string text_;
   static bool key_char(char c) { return std::isalnum((unsigned char)c) || c == '_'; }
   void parse(const std::string& s) {
     size_t p = 0;
@@ -114,6 +132,7 @@ class namelist_file {
           }
         }
       }
+      g.end_pos = p;
       ++p;  // '/'
       groups_.push_back(g);
     }

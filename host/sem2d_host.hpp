@@ -5,7 +5,8 @@
 // The reference is a Fortran program (no Fortran compiler exists in the build image, SURVEY.md
 // header), so this layer is what a maintainer's ISO_C_BINDING shim looks like when
 // written in C++.  Scope = what the device-side structured builder provides: &MESH_CART boxes with
-// one ELAST material, ABSORB and PERIOD sides, the split-node DYNFLT of `ezflt` with slip weakening, FORCE
+// one ELAST material, ABSORB, PERIOD and DIRNEU sides, DYNFLT (the split-node row of `ezflt`, or the bottom / top
+// side as a one-sided fault) with slip-weakening or rate-and-state friction and ORDER0 / PWCONR distributions, FORCE
 // and moment-tensor sources, REC_LINE stations at nodes, the leapfrog, Newmark, HHT-alpha and symplectic schemes.  Anything else in a Par.inp is
 // refused with IO_abort, never silently ignored -- except plotting (&SNAP_*), which is not on the path.
 //
@@ -70,17 +71,55 @@ struct rec_type {
   std::vector<float> sis;     // (nt,nx,ndof)
 };
 
+// cd_type (SRC/distribution_cd.f90): a constant or a spatial distribution evaluated at node coordinates.
+// Distributions provided: ORDER0 (SRC/distribution_order0.f90: blocks of constant value on an x-z grid of
+// zones) and PWCONR (SRC/distribution_pwconr.f90: constant in concentric rings around a point).
+struct cd_type {
+  double c = 0.0;
+  int dist = 0;  // 0 constant, 1 ORDER0, 2 PWCONR
+  int xn = 1, zn = 1;
+  std::vector<double> xb, zb, val;  // ORDER0: zone boundaries, val(xn,zn) column-major
+  double ref[2] = {0, 0};           // PWCONR: reference point, radii, values
+  std::vector<double> rad;
+  double eval(double x, double z) const {
+    if (dist == 0) return c;
+    if (dist == 1) {  // generate_order0_dist / zone (distribution_order0.f90:73-105)
+      auto zone = [](double q, int nz, const std::vector<double>& b) {
+        if (nz == 1) return 1;
+        int k = 1;
+        for (; k <= nz - 1; ++k)
+          if (q < b[k - 1]) break;
+        return k;
+      };
+      return val[(zone(x, xn, xb) - 1) + (size_t)xn * (zone(z, zn, zb) - 1)];
+    }
+    const double r = std::sqrt((x - ref[0]) * (x - ref[0]) + (z - ref[1]) * (z - ref[1]));  // distribution_pwconr.f90:69-85
+    size_t iz = 0;
+    for (; iz + 1 < val.size(); ++iz)
+      if (r <= rad[iz]) break;
+    return val[iz];
+  }
+};
+
 // bc_type (SRC/bc_gen.f90:29-41), the kinds this host hands to the device
 struct bc_type {
   int tag[2] = {0, 0};
   std::string kind;
   bool stacey = false;  // &BC_ABSORB
-  // &BC_DYNFLT / &BC_DYNFLT_SWF (SRC/bc_dynflt.f90:63-229, SRC/bc_dynflt_swf.f90:30-140)
-  double Tn = 0, Tt = 0, Tt_nuc = 0, x_nuc = 0, half_nuc = -1, Dc = 0.5, MuS = 0.6, MuD = 0.5;
   int oxi[3] = {1, 2147483647, 1};
   double ot1 = 0.0, otd = 0.0;
   int32_t fault_id = -1;
-  int np = 0, oitd = 1;
+  int np = 0, oitd = 1, oit = 0;
+  std::vector<double> MU0;   // initial friction coefficient of the output nodes (FltXX_init_sem2d.tab)
+  // general &BC_DYNFLT (SRC/bc_dynflt.f90:104-229): constants or distributions, one or two friction laws
+  cd_type cd_Tn, cd_Tt, cd_cohesion, cd_V;
+  bool opening = true, has_swf = false, has_rsf = false;
+  int swf_kind = 1, rsf_kind = 1, nor_kind = 1;
+  bool swf_healing = false;
+  cd_type swf_Dc, swf_MuS, swf_MuD, swf_alpha, swf_p;                    // SRC/bc_dynflt_swf.f90:30-100
+  cd_type rsf_Dc, rsf_MuS, rsf_a, rsf_b, rsf_Vstar, rsf_theta, rsf_Vc;   // SRC/bc_dynflt_rsf.f90:30-90
+  double nor_L = 1, nor_V = 1, nor_T = 1;                                // SRC/bc_dynflt_normal.f90:30-60
+  int kind_h = 1, kind_v = 1;                                            // &BC_DIRNEU: 1 Neumann, 2 Dirichlet
 };
 
 // problem_type (SRC/problem_class.f90:19-46): what the host keeps; fields, operator data and boundary
@@ -115,9 +154,42 @@ inline void s2d_check(const problem_type& pb, int rc, const char* where) {
   IO_abort(std::string(where) + ": " + (m && *m ? m : "device call failed") + " (code " + std::to_string(rc) + ")");
 }
 
-// the list-directed records that follow a distribution block: the first `n` numbers after the
-// closing '/' of the first `group` in the file (SRC/distribution_pwconr.f90:58-66)
-inline std::vector<double> trailing_numbers(const std::string& file, const std::string& group, int n);
+// DIST_CD_Read (SRC/distribution_cd.f90:26-61): the constant `key`, or -- when `key`H names a distribution --
+// the next &DIST_<name> block after position `cur` (the reference reads the file forward) and its records
+inline cd_type DIST_CD_Read(const namelist_file& in, const nml_group& g, const std::string& key, double dflt, size_t& cur) {
+  cd_type cd;
+  cd.c = g.real8(key, dflt);
+  const std::string name = g.text(key + "h", "");
+  if (name.empty()) return cd;
+  const long k = in.find("DIST_" + name, cur);
+  if (k < 0) IO_abort("DIST_read: DIST_" + name + " input block not found");
+  cur = (size_t)k + 1;
+  const nml_group& d = in.at((size_t)k);
+  if (name == "ORDER0") {  // read_order0_dist (distribution_order0.f90:40-69)
+    cd.dist = 1;
+    cd.xn = d.integer("xn", 1);
+    cd.zn = d.integer("zn", 1);
+    const size_t nxb = cd.xn > 1 ? cd.xn - 1 : 0, nzb = cd.zn > 1 ? cd.zn - 1 : 0, nv = (size_t)cd.xn * cd.zn;
+    const std::vector<double> r = in.records_after((size_t)k, nxb + nzb + nv);
+    if (r.size() < nxb + nzb + nv) IO_abort("read_order0_dist: missing records after DIST_ORDER0");
+    cd.xb.assign(r.begin(), r.begin() + nxb);
+    cd.zb.assign(r.begin() + nxb, r.begin() + nxb + nzb);
+    cd.val.assign(r.begin() + nxb + nzb, r.end());
+  } else if (name == "PWCONR") {  // read_pwconr_dist (distribution_pwconr.f90:25-41)
+    cd.dist = 2;
+    const int num = d.integer("num", 0);
+    if (num < 2) IO_abort("read_pwconr_dist: needs more than 2 zones (num)");
+    cd.ref[0] = d.real8("ref", 0.0, 0);
+    cd.ref[1] = d.real8("ref", 0.0, 1);
+    const std::vector<double> r = in.records_after((size_t)k, (size_t)(2 * num - 1));
+    if ((int)r.size() < 2 * num - 1) IO_abort("read_pwconr_dist: missing records after DIST_PWCONR");
+    cd.rad.assign(r.begin(), r.begin() + (num - 1));
+    cd.val.assign(r.begin() + (num - 1), r.end());
+  } else {
+    IO_abort("DIST_read: distribution '" + name + "' is not provided here (ORDER0, PWCONR are)");
+  }
+  return cd;
+}
 
 // ---------------------------------------------------------------------------------------------
 // read_main (SRC/input.f90:12-63): &GENERAL, MESH_read, MAT_read, BC_read, TIME_read, SO_read, REC_read
@@ -153,24 +225,29 @@ inline void read_main(problem_type& pb, const std::string& file) {
       pb.nelem[q] = g.integer("nelem", 0, q);
     }
     pb.ezflt = g.integer("ezflt", 0);
-    if (g.has("fztag") || g.has("fznz") || g.has("splitd")) IO_abort("CART_read: fztag / FZnz / splitD are not provided by the B200 path");
+    if (g.has("splitd")) IO_abort("CART_read: splitD is not provided by the B200 path");
+    // fztag / FZnz only re-tag the element rows next to the fault (mesh_cartesian.f90:262-268); accepted when
+    // every material is the same (checked in MAT_read below)
     if (pb.ezflt < 0) IO_abort("CART_read: ezflt = -1 (fault at mid height) needs an even nelem(2)");
   }
-  // MAT_read (SRC/mat_gen.f90:119-189): one ELAST material
+  // MAT_read (SRC/mat_gen.f90:119-189): ELAST materials that all carry the same properties (each MATERIAL
+  // block reads the next MAT_ELASTIC block FORWARD from its own position, so several tags can share one)
   k = in.find("MATERIAL");
   if (k < 0) IO_abort("MAT_read: no MATERIAL block");
-  if (in.find("MATERIAL", (size_t)k + 1) >= 0) IO_abort("MAT_read: a single material is provided by the B200 structured builder");
-  {
-    const nml_group& g = in.at((size_t)k);
+  for (long m0 = k, first = 1; m0 >= 0; m0 = in.find("MATERIAL", (size_t)m0 + 1), first = 0) {
+    const nml_group& g = in.at((size_t)m0);
     if (g.count("kind") != 1 || g.text("kind", "") != "ELAST") IO_abort("MAT_read: only kind='ELAST' is provided here");
-    const long m = in.find("MAT_ELASTIC", (size_t)k);
+    const long m = in.find("MAT_ELASTIC", (size_t)m0);
     if (m < 0) IO_abort("MAT_ELAST_read: MAT_ELASTIC input block not found");
     const nml_group& e = in.at((size_t)m);  // SRC/mat_elastic.f90:104-129
     if (e.has("cph") || e.has("csh") || e.has("rhoh") || e.has("c11")) IO_abort("MAT_ELAST_read: distributions / anisotropy are not provided here");
-    pb.rho = e.real8("rho", 0.0);
-    pb.cp = e.real8("cp", 0.0);
-    pb.cs = e.real8("cs", 0.0);
-    if (!(pb.rho > 0 && pb.cp > 0 && pb.cs > 0)) IO_abort("MAT_ELAST_read: rho, cp, cs must be positive");
+    const double rho = e.real8("rho", 0.0), cp = e.real8("cp", 0.0), cs = e.real8("cs", 0.0);
+    if (!(rho > 0 && cp > 0 && cs > 0)) IO_abort("MAT_ELAST_read: rho, cp, cs must be positive");
+    if (!first && (rho != pb.rho || cp != pb.cp || cs != pb.cs))
+      IO_abort("MAT_read: several different materials are not provided by the B200 structured builder");
+    pb.rho = rho;
+    pb.cp = cp;
+    pb.cs = cs;
   }
   // BC_read (SRC/bc_gen.f90:98-188): in input order
   for (long b = in.find("BC_DEF"); b >= 0; b = in.find("BC_DEF", (size_t)b + 1)) {
@@ -196,39 +273,79 @@ inline void read_main(problem_type& pb, const std::string& file) {
       if (bc.tag[0] < 1 || bc.tag[0] > 4) IO_abort("BC_read: ABSORB tag must be a side of the box (1..4)");
     } else if (bc.kind == "PERIOD") {  // SRC/bc_periodic.f90:29-40: no parameters
       if (bc.tag[1] == 0) IO_abort("BC_read: PERIOD needs tags = master, slave");
-    } else if (bc.kind == "DYNFLT") {
-      if (!(bc.tag[0] == 5 && bc.tag[1] == 6)) IO_abort("BC_read: DYNFLT is provided on the split-node fault tags=5,6 of MESH_CART ezflt");
+    } else if (bc.kind == "DIRNEU") {  // SRC/bc_dirneu.f90:50-112
+      const nml_group* dn = sub("BC_DIRNEU");
+      if (!dn) IO_abort("bc_DIRNEU_read: no BC_DIRNEU block found");
+      if (dn->text("hstf", "none") != "none" || dn->text("vstf", "none") != "none")
+        IO_abort("bc_DIRNEU_read: time-dependent Neumann conditions are provided by the generic C-ABI, not by this host");
+      bc.kind_h = dn->text("h", "N") == "D" ? 2 : 1;
+      bc.kind_v = dn->text("v", "N") == "D" ? 2 : 1;
+      if (bc.tag[0] < 1 || bc.tag[0] > 4) IO_abort("BC_read: DIRNEU tag must be a side of the box (1..4)");
+    } else if (bc.kind == "DYNFLT") {  // BC_DYNFLT_read (SRC/bc_dynflt.f90:104-229)
+      const bool two = bc.tag[0] == 5 && bc.tag[1] == 6, one = (bc.tag[0] == 1 || bc.tag[0] == 3) && bc.tag[1] == 0;
+      if (!two && !one)
+        IO_abort("BC_read: DYNFLT is provided on tags=5,6 (split-node row of MESH_CART ezflt) or on the bottom / top side (tag=1 or 3)");
       const nml_group* f = sub("BC_DYNFLT");
       if (!f) IO_abort("BC_DYNFLT_read: BC_DYNFLT input block not found");
-      if (f->text("friction", "SWF") != "SWF" || f->count("friction") > 1) IO_abort("BC_DYNFLT_read: only friction='SWF' is provided here");
-      bc.Tn = f->real8("tn", 0.0);
-      bc.Tt = bc.Tt_nuc = f->real8("tt", 0.0);
       for (int q = 0; q < 3; ++q) bc.oxi[q] = f->integer("oxi", bc.oxi[q], q);
       bc.ot1 = f->real8("ot1", 0.0);
       bc.otd = f->real8("otd", 0.0);
-      if (f->has("tth")) {  // DIST_PWCONR with two zones around ref (SRC/distribution_pwconr.f90:40-85)
-        if (f->text("tth", "") != "PWCONR") IO_abort("BC_DYNFLT_read: TtH: only 'PWCONR' with num=2 is provided here");
-        const nml_group* d = sub("DIST_PWCONR");
-        if (!d || d->integer("num", 0) != 2) IO_abort("DIST_PWCONR: num=2 expected");
-        bc.x_nuc = d->real8("ref", 0.0, 0);
-        // the radius and the two values follow the block as list-directed records
-        std::vector<double> v = trailing_numbers(file, "DIST_PWCONR", 3);
-        bc.half_nuc = v[0];
-        bc.Tt_nuc = v[1];
-        bc.Tt = v[2];
+      bc.opening = f->logical("opening", true);
+      if (f->logical("osides", false)) IO_abort("BC_DYNFLT_read: osides=T is not provided here");
+      for (const char* key : {"sxx", "sxy", "sxz", "syz", "szz", "sxxh", "sxyh", "sxzh", "syzh", "szzh"})
+        if (f->has(key)) IO_abort(std::string("BC_DYNFLT_read: background stress '") + key + "' is not provided here");
+      size_t cur = (size_t)(f - &in.at(0)) + 1;  // distributions are read forward from the block (bc_dynflt.f90:164-172)
+      bc.cd_cohesion = DIST_CD_Read(in, *f, "cohesion", 0.0, cur);
+      bc.cd_Tn = DIST_CD_Read(in, *f, "tn", 0.0, cur);
+      bc.cd_Tt = DIST_CD_Read(in, *f, "tt", 0.0, cur);
+      bc.cd_V = DIST_CD_Read(in, *f, "v", 1e-12, cur);
+      for (size_t q = 0; q < f->count("friction") || q < 1; ++q) {
+        const std::string law = f->text("friction", "SWF", q);
+        if (law == "SWF") {  // swf_read (SRC/bc_dynflt_swf.f90:30-100)
+          const nml_group* w = sub("BC_DYNFLT_SWF");
+          static const nml_group none;
+          if (!w) w = &none;
+          bc.has_swf = true;
+          bc.swf_kind = w->integer("kind", 1);
+          bc.swf_healing = w->logical("healing", false);
+          if (bc.swf_kind < 1 || bc.swf_kind > 3) IO_abort("BC_DYNFLT_SWF: invalid kind");
+          size_t c2 = w == &none ? cur : (size_t)(w - &in.at(0)) + 1;
+          bc.swf_Dc = DIST_CD_Read(in, *w, "dc", 0.5, c2);
+          bc.swf_MuS = DIST_CD_Read(in, *w, "mus", 0.6, c2);
+          bc.swf_MuD = DIST_CD_Read(in, *w, "mud", 0.5, c2);
+          bc.swf_alpha = DIST_CD_Read(in, *w, "alpha", 0.0, c2);
+          bc.swf_p = DIST_CD_Read(in, *w, "p", 3.0, c2);
+        } else if (law == "RSF") {  // rsf_read (SRC/bc_dynflt_rsf.f90:30-90)
+          const nml_group* w = sub("BC_DYNFLT_RSF");
+          static const nml_group none;
+          if (!w) w = &none;
+          bc.has_rsf = true;
+          bc.rsf_kind = w->integer("kind", 1);
+          if (bc.rsf_kind < 1 || bc.rsf_kind > 4) IO_abort("BC_DYNFLT_RSF: invalid kind");
+          size_t c2 = w == &none ? cur : (size_t)(w - &in.at(0)) + 1;
+          bc.rsf_Dc = DIST_CD_Read(in, *w, "dc", 0.5, c2);
+          bc.rsf_MuS = DIST_CD_Read(in, *w, "mus", 0.6, c2);
+          bc.rsf_a = DIST_CD_Read(in, *w, "a", 0.01, c2);
+          bc.rsf_b = DIST_CD_Read(in, *w, "b", 0.02, c2);
+          bc.rsf_Vstar = DIST_CD_Read(in, *w, "vstar", 1.0, c2);
+          bc.rsf_theta = DIST_CD_Read(in, *w, "theta", 0.0, c2);
+          bc.rsf_Vc = DIST_CD_Read(in, *w, "vc", 1e-6, c2);
+        } else if (law == "TWF") {
+          IO_abort("BC_DYNFLT_read: friction='TWF' is provided by the generic C-ABI, not by this host");
+        } else if (!law.empty()) {
+          IO_abort("BC_DYNFLT: invalid friction");
+        }
       }
-      for (const char* key : {"tnh", "sxx", "sxz", "szz", "cohesion", "v", "opening"})
-        if (f->has(key)) IO_abort(std::string("BC_DYNFLT_read: '") + key + "' is not provided here");
-      const nml_group* w = sub("BC_DYNFLT_SWF");
-      if (!w) IO_abort("BC_DYNFLT_SWF input block not found");
-      if (w->integer("kind", 1) != 1 || w->logical("healing", false)) IO_abort("BC_DYNFLT_SWF: only kind=1 without healing is provided here");
-      bc.Dc = w->real8("dc", 0.5);
-      bc.MuS = w->real8("mus", 0.6);
-      bc.MuD = w->real8("mud", 0.5);
-      for (const char* key : {"dch", "mush", "mudh", "alpha", "alphah", "p"})
-        if (w->has(key)) IO_abort(std::string("BC_DYNFLT_SWF: '") + key + "' is not provided here");
+      if (bc.has_swf && bc.has_rsf) IO_abort("BC_DYNFLT_read: SWF and RSF together are not provided here");
+      if (const nml_group* nr = sub("BC_DYNFLT_NOR")) {  // normal_read (SRC/bc_dynflt_normal.f90:30-60)
+        bc.nor_kind = nr->integer("kind", 1);
+        bc.nor_L = nr->real8("l", 1.0);
+        bc.nor_V = nr->real8("v", 1.0);
+        bc.nor_T = nr->real8("t", 1.0);
+        if (bc.nor_kind > 3 || bc.nor_kind < 0) IO_abort("BC_SWFF_init: invalid kind in BC_DYNFLT_NOR input block");
+      }
     } else {
-      IO_abort("BC_read: boundary kind '" + bc.kind + "' is not provided by the B200 structured builder (ABSORB, PERIOD, DYNFLT are)");
+      IO_abort("BC_read: boundary kind '" + bc.kind + "' is not provided by the B200 structured builder (ABSORB, PERIOD, DIRNEU, DYNFLT are)");
     }
     pb.bc.push_back(bc);
   }
@@ -364,8 +481,8 @@ inline void read_main(problem_type& pb, const std::string& file) {
       if (c == 'D') pb.snap_fields[0] = true;
       else if (c == 'V') pb.snap_fields[1] = true;
       else if (c == 'A') pb.snap_fields[2] = true;
-      else if (pb.snap_bin && c != ' ')
-        IO_abort(std::string("SNAP_DEF: snapshot field '") + c + "' (strain, stress, divergence, curl) is not provided here");
+      else if (pb.snap_bin && c != ' ')  // off the path: skipped with a warning, like the plots
+        std::printf(" *** WARNING: SNAP_DEF: snapshot field '%c' (strain, stress, divergence, curl) is not written by this host ***\n", c);
     }
     if (pb.snap_itd <= 0) IO_abort("SNAP_DEF: itd must be positive");
   }
@@ -441,15 +558,68 @@ inline void init_main(problem_type& pb) {
     if (bc.kind == "PERIOD") continue;
     if (bc.kind == "ABSORB") {
       s2d_check(pb, s2d_cart_add_abso(pb.gpu, bc.tag[0], bc.stacey ? 1 : 0), "BC_ABSO_init");
-    } else {  // DYNFLT
-      bc.oitd = std::max(1, (int)std::lround(bc.otd / t.dt));  // SRC/bc_dynflt.f90:452-456
-      if (std::lround(bc.ot1 / t.dt) != 0) IO_abort("BC_DYNFLT_init: ot1 > 0 is not provided here");
-      const int np = pb.nelem[0] * (pb.ngll - 1) + 1;
-      if (!(bc.oxi[0] <= 1 && bc.oxi[1] >= np)) IO_abort("BC_DYNFLT_init: oxi must span the whole fault here (stride only)");
-      s2d_check(pb, s2d_cart_add_fault_swf(pb.gpu, bc.Dc, bc.MuS, bc.MuD, bc.Tn, bc.Tt, bc.Tt_nuc, bc.x_nuc, bc.half_nuc,
-                                           bc.oxi[2], bc.oitd, t.nt, &bc.fault_id),
-                "BC_DYNFLT_init");
+    } else if (bc.kind == "DIRNEU") {
+      s2d_check(pb, s2d_cart_add_dirneu(pb.gpu, bc.tag[0], bc.kind_h, bc.kind_v), "bc_DIRNEU_init");
+    } else {  // BC_DYNFLT_init (SRC/bc_dynflt.f90:231-520): the host evaluates constants / distributions at the
+              // fault nodes, the builder adds the topology (nodes, normals, weights, impedances)
+      bc.oitd = std::max(1, (int)std::lround(bc.otd / t.dt));  // :452-456
+      const int oit = (int)std::lround(bc.ot1 / t.dt);
+      int32_t np = 0;
+      s2d_check(pb, s2d_cart_fault_nodes(pb.gpu, bc.tag[0], bc.tag[1], &np, nullptr), "BC_DYNFLT_init");
+      std::vector<double> xz(2 * (size_t)np);
+      s2d_check(pb, s2d_cart_fault_nodes(pb.gpu, bc.tag[0], bc.tag[1], &np, xz.data()), "BC_DYNFLT_init");
+      auto gen = [&](const cd_type& cd) {  // DIST_CD_Init (SRC/distribution_cd.f90:65-90)
+        std::vector<double> out(np);
+        for (int k = 0; k < np; ++k) out[k] = cd.eval(xz[2 * k], xz[2 * k + 1]);
+        return out;
+      };
+      const std::vector<double> Tt = gen(bc.cd_Tt), Tn = gen(bc.cd_Tn), coh = gen(bc.cd_cohesion), V = gen(bc.cd_V);
+      for (double c : coh)
+        if (c < 0.0) IO_abort("bc_dynflt_init: cohesion must be positive");
+      std::vector<double> T0(2 * (size_t)np), V0((size_t)np * pb.ndof, 0.0);
+      for (int k = 0; k < np; ++k) {  // no background stress: T0 = (Tt, Tn) (:392-400)
+        T0[k] = Tt[k];
+        T0[k + np] = Tn[k];
+        if (bc.has_rsf) V0[k] = V[k];  // bc%V(:,1) = V for rate-and-state faults (:371-376)
+      }
+      s2d_dynflt_desc d;
+      std::memset(&d, 0, sizeof(d));
+      d.np = np;
+      d.T0 = T0.data();
+      d.cohesion = coh.data();
+      d.V0 = V0.data();
+      d.allow_opening = bc.opening ? 1 : 0;
+      std::vector<double> p1, p2, p3, p4, p5, p6, p7, th;
+      if (bc.has_swf) {
+        p1 = gen(bc.swf_Dc); p2 = gen(bc.swf_MuS); p3 = gen(bc.swf_MuD); p4 = gen(bc.swf_p); p5 = gen(bc.swf_alpha);
+        th.assign(np, 0.0);
+        d.swf_kind = bc.swf_kind;
+        d.swf_healing = bc.swf_healing ? 1 : 0;
+        d.swf_dc = p1.data(); d.swf_mus = p2.data(); d.swf_mud = p3.data(); d.swf_p = p4.data(); d.swf_alpha = p5.data();
+        d.swf_theta = th.data();
+      }
+      if (bc.has_rsf) {
+        p1 = gen(bc.rsf_Dc); p2 = gen(bc.rsf_MuS); p3 = gen(bc.rsf_a); p4 = gen(bc.rsf_b); p5 = gen(bc.rsf_Vstar);
+        p6 = gen(bc.rsf_theta); p7 = gen(bc.rsf_Vc);
+        d.rsf_kind = bc.rsf_kind;
+        d.rsf_dc = p1.data(); d.rsf_mus = p2.data(); d.rsf_a = p3.data(); d.rsf_b = p4.data(); d.rsf_Vstar = p5.data();
+        d.rsf_theta = p6.data(); d.rsf_Vc = p7.data();
+      }
+      d.normal_kind = bc.nor_kind;
+      d.normal_T = bc.nor_T;
+      d.normal_L = bc.nor_L;
+      d.normal_V = bc.nor_V;
+      d.oix1 = bc.oxi[0];
+      d.oixn = bc.oxi[1];
+      d.oixd = bc.oxi[2];
+      d.oit = oit;
+      d.oitd = bc.oitd;
+      d.nt_max = t.nt;
+      s2d_check(pb, s2d_cart_add_dynflt(pb.gpu, bc.tag[0], bc.tag[1], &d, &bc.fault_id), "BC_DYNFLT_init");
       bc.np = np;
+      bc.oxi[0] = std::max(bc.oxi[0], 1);
+      bc.oxi[1] = std::min(bc.oxi[1], (int)np);
+      bc.oit = oit;
     }
   }
   // SO_init (SRC/src_gen.f90:216-262): nearest node
@@ -472,6 +642,12 @@ inline void init_main(problem_type& pb) {
     s2d_check(pb, s2d_cart_receiver_info(pb.gpu, &nx, r.coord.data()), "REC_init");
   }
   s2d_check(pb, s2d_commit(pb.gpu, S2D_ASM_PATCH), "init_main");
+  for (bc_type& bc : pb.bc)
+    if (bc.kind == "DYNFLT") {  // bc%MU as BC_DYNFLT_init leaves it (SRC/bc_dynflt.f90:402-420)
+      bc.MU0.resize(bc.np);
+      s2d_check(pb, s2d_get_fault_state(pb.gpu, bc.fault_id, nullptr, nullptr, nullptr, nullptr, bc.MU0.data(), nullptr, nullptr),
+                "BC_DYNFLT_init");
+    }
   pb.it = 0;
 }
 
@@ -593,11 +769,10 @@ inline void REC_write(const rec_type& r, int ndof, const std::string& dir = ".")
 // by its 4-byte length, as gfortran/ifort write it) and FltXX_potency_sem2d.tab (6D24.16 per call).
 inline void BC_DYNFLT_flush(problem_type& pb, const bc_type& bc, const std::string& dir = ".") {
   int32_t np = 0;
-  s2d_check(pb, s2d_cart_fault_info(pb.gpu, &np, nullptr, nullptr, nullptr, nullptr), "BC_write");
+  s2d_check(pb, s2d_cart_fault_info(pb.gpu, bc.fault_id, &np, nullptr, nullptr, nullptr), "BC_write");
   std::vector<double> coord(2 * (size_t)np), T0(2 * (size_t)np), B(np);
-  double mu0 = 0;
-  s2d_check(pb, s2d_cart_fault_info(pb.gpu, &np, coord.data(), T0.data(), B.data(), &mu0), "BC_write");
-  const int oixd = bc.oxi[2], onx = (np - 1) / oixd + 1;
+  s2d_check(pb, s2d_cart_fault_info(pb.gpu, bc.fault_id, &np, coord.data(), T0.data(), B.data()), "BC_write");
+  const int oix1 = bc.oxi[0], oixn = bc.oxi[1], oixd = bc.oxi[2], onx = (oixn - oix1) / oixd + 1;
   int32_t nout = 0, ncalls = 0;
   s2d_check(pb, s2d_get_fault(pb.gpu, bc.fault_id, nullptr, &nout, nullptr, &ncalls), "BC_write");
   std::vector<float> rec((size_t)nout * 6 * onx);
@@ -607,13 +782,13 @@ inline void BC_DYNFLT_flush(problem_type& pb, const bc_type& bc, const std::stri
   std::snprintf(base, sizeof(base), "%s/Flt%02d", dir.c_str(), bc.tag[0]);
   const std::string b(base);
   if (FILE* f = std::fopen((b + "_sem2d.hdr").c_str(), "w")) {
-    std::fprintf(f, " NPTS NDAT NSAMP DELT\n %d %d %d %.16E\n", onx, 6, pb.time.nt / bc.oitd + 1, pb.time.dt * bc.oitd);
+    std::fprintf(f, " NPTS NDAT NSAMP DELT\n %d %d %d %.16E\n", onx, 6, (pb.time.nt - bc.oit) / bc.oitd + 1, pb.time.dt * bc.oitd);
     std::fprintf(f, " Slip:Slip_Rate:Shear_Stress:Normal_Stress:Friction:T_stick\n XPTS ZPTS\n");
-    for (int i = 0; i < np; i += oixd) std::fprintf(f, " %.16E %.16E\n", coord[2 * i], coord[2 * i + 1]);
+    for (int i = oix1 - 1; i < oixn; i += oixd) std::fprintf(f, " %.16E %.16E\n", coord[2 * i], coord[2 * i + 1]);
     std::fclose(f);
   }
   if (FILE* f = std::fopen((b + "_init_sem2d.tab").c_str(), "w")) {
-    for (int i = 0; i < np; i += oixd) std::fprintf(f, " %.16E %.16E %.16E %.16E\n", T0[i], T0[i + np], mu0, B[i]);
+    for (int i = oix1 - 1; i < oixn; i += oixd) std::fprintf(f, " %.16E %.16E %.16E %.16E\n", T0[i], T0[i + np], bc.MU0[i], B[i]);
     std::fclose(f);
   }
   if (FILE* f = std::fopen((b + "_sem2d.dat").c_str(), "wb")) {
@@ -633,30 +808,6 @@ inline void BC_DYNFLT_flush(problem_type& pb, const bc_type& bc, const std::stri
     }
     std::fclose(f);
   }
-}
-
-inline std::vector<double> trailing_numbers(const std::string& file, const std::string& group, int n) {
-  std::ifstream f(file);
-  std::string all((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-  std::string up = all;
-  for (char& c : up) c = (char)std::toupper((unsigned char)c);
-  size_t p = up.find("&" + group);
-  if (p == std::string::npos) IO_abort(group + ": block not found");
-  p = all.find('/', p);
-  std::vector<double> v;
-  std::stringstream ss(all.substr(p + 1));
-  std::string tok;
-  while ((int)v.size() < n && ss >> tok) {
-    if (tok[0] == '&') break;
-    if (tok[0] == '#') {
-      std::string rest;
-      std::getline(ss, rest);
-      continue;
-    }
-    v.push_back(nml_group::to_double(tok));
-  }
-  if ((int)v.size() < n) IO_abort(group + ": missing list-directed records after the block");
-  return v;
 }
 
 }  // namespace sem2d

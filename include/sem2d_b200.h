@@ -263,10 +263,19 @@ int s2d_cart_add_force(s2d_handle h, double x, double z, const double dir[2], in
 int s2d_cart_add_moment(s2d_handle h, double x, double z, const double* M, int32_t* src_id);
 int s2d_cart_add_receivers(s2d_handle h, int32_t nx, double xa, double za, double xb, double zb,
                            char field, int32_t isamp, int32_t nt_rec);
-/* the split-node fault as BC_DYNFLT_init leaves it (bc_dynflt.f90:392-458): node count, bc%coord(2,np),
- * bc%T0(np,2), bc%B(np,1) and the initial friction coefficient -- what FltXX_sem2d.hdr and
- * FltXX_init_sem2d.tab hold.  Any pointer may be NULL. */
-int s2d_cart_fault_info(s2d_handle h, int32_t* np, double* coord, double* T0, double* B, double* mu0);
+/* General BC_DYNFLT_init on the box (bc_dynflt.f90:231-520).  tags (5,6): the split-node row of ezflt;
+ * (1,0) / (3,0): the bottom / top side as a one-sided fault (symmetry assumption, tags(2)=0, :700-716).
+ * s2d_cart_fault_nodes gives np and bc%coord(2,np) so that the host can evaluate its distributions there;
+ * `law` then carries np, T0(np,2), cohesion, V0, the friction-law arrays (swf_*, rsf_*, twf_*), the
+ * normal-stress law and the output strides.  Its topology members (node1, node2, n1, B, invM1, invM2, Z,
+ * coord, CoefA2V, CoefA2D) are ignored: the builder fills them. */
+int s2d_cart_fault_nodes(s2d_handle h, int32_t tag1, int32_t tag2, int32_t* np, double* coord);
+int s2d_cart_add_dynflt(s2d_handle h, int32_t tag1, int32_t tag2, const s2d_dynflt_desc* law, int32_t* fault_id);
+/* bc_DIRNEU_init on side tag 1..4: kind 1 = Neumann (homogeneous), 2 = Dirichlet, per component */
+int s2d_cart_add_dirneu(s2d_handle h, int32_t side_tag, int32_t kind_h, int32_t kind_v);
+/* a fault as BC_DYNFLT_init left it (bc_dynflt.f90:392-458): node count, bc%coord(2,np), bc%T0(np,2),
+ * bc%B(np,1) -- what FltXX_sem2d.hdr and FltXX_init_sem2d.tab hold.  Any pointer may be NULL. */
+int s2d_cart_fault_info(s2d_handle h, int32_t fault_id, int32_t* np, double* coord, double* T0, double* B);
 /* number of stations kept (duplicates dropped, receivers.f90:255) and their relocated positions
  * rec%coord(2,nx) (receivers.f90:231-303); coord may be NULL */
 int s2d_cart_receiver_info(s2d_handle h, int32_t* nx, double* coord);

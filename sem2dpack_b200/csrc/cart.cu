@@ -363,10 +363,10 @@ struct CartState {
   bool mass_inverted = false;
   bool bc_added = false;
   int perio_lr = 0, perio_bt = 0;   // periodic pairs: left-right (tags 4,2), bottom-top (tags 1,3)
-  std::vector<double> fault_coord;  // (2, np) bc%coord of the split-node fault
-  std::vector<double> fault_T0;     // (np, 2), fault_B (np): initial tractions and node weights (FltXX_init_sem2d.tab)
-  std::vector<double> fault_B;
-  double fault_mu0 = 0.0;
+  struct FaultInfo {                // per fault id: bc%coord (2,np), bc%T0 (np,2), bc%B(:,1) (FltXX_sem2d.hdr, _init.tab)
+    std::vector<double> coord, T0, B;
+  };
+  std::vector<FaultInfo> faults;
   std::vector<double> rec_coord;  // (2, nx) positions of the relocated stations (rec%coord, receivers.f90:231-303)
   int coef_mode = 0;  // 0 = compact (lambda, mu) where the rheology allows, 1 = all planes stored
   bool nm() const { return scheme.kind == 1 || scheme.kind == 2; }  // 'newmark', 'HHT-alpha'
@@ -742,90 +742,170 @@ int s2d_cart_add_periodic(s2d_handle h, int32_t master_tag, int32_t slave_tag) {
   CART_GUARD_END
 }
 
-// BC_DYNFLT_init for the split-node fault of MESH_CART ezflt (tags 5 = lower side, 6 = upper side)
-int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, double Tn, double Tt, double Tt_nuc,
-                           double x_nuc, double half_nuc, int32_t oixd, int32_t oitd, int32_t nt_max,
-                           int32_t* fault_id) {
-  CART_GUARD_BEGIN
+// Topology of a fault on the box, as BC_DYNFLT_init builds it (bc_dynflt.f90:258-354): tags (5,6) = the
+// split-node row of MESH_CART ezflt (5 = lower side, 6 = upper side); tag 1 or 3 alone = the bottom / top
+// side as a one-sided fault with the symmetry assumption (tags(2) = 0, :700-716).  Nodes in ascending x.
+struct FaultTopo {
+  int np = 0;
+  bool two = false;
+  std::vector<int> node1, node2;
+  std::vector<double> n1, B, coord;
+};
+static void cart_fault_topology(const CartState& S, int tag1, int tag2, FaultTopo& F) {
   const CartGeom& G = S.G;
-  S2D_REQUIRE(G.ezflt > 0, "cart_add_fault_swf: the mesh has no fault (ezflt = 0)");
-  S2D_REQUIRE(!Eb->committed, "cart_add_fault_swf after commit");
-  S.bc_added = true;
   const int N = G.N, ndof = G.ndof;
+  F.two = (tag1 == 5 && tag2 == 6);
+  S2D_REQUIRE(F.two || ((tag1 == 1 || tag1 == 3) && tag2 == 0),
+              "cart fault: tags must be (5,6) = the ezflt split-node row, or (1,0) / (3,0) = a one-sided fault on the bottom / top side");
+  if (F.two) S2D_REQUIRE(G.ezflt > 0, "cart fault: the mesh has no split-node row (ezflt = 0)");
   const int np = G.nx * (N - 1) + 1;
-  std::vector<int> node1(np), node2(np);
-  std::vector<double> n1((size_t)np * 2), B((size_t)np * ndof, 0.0), T0((size_t)np * 2), coh(np, 0.0), coord((size_t)np * 2);
-  std::vector<double> dc(np, Dc), mus(np, MuS), mud(np, MuD), pw(np, 3.0), alpha(np, 0.0);
-  const int e_lo = G.halo_left ? -1 : 0, e_hi = G.halo_right ? G.nx : G.nx - 1;
+  F.np = np;
+  F.node1.assign(np, 0);
+  F.node2.assign(F.two ? np : 0, 0);
+  F.n1.assign((size_t)np * 2, 0.0);
+  F.B.assign((size_t)np * ndof, 0.0);
+  F.coord.assign((size_t)np * 2, 0.0);
+  // element row and local row of side 1, outward normal (t_z,-t_x) of that side, fault depth
+  int iz1, j1, iz2 = 0, j2 = 0;
+  double nz, zf;
+  if (F.two) {
+    iz1 = G.ezflt - 1; j1 = N - 1; iz2 = G.ezflt; j2 = 0; nz = 1.0; zf = G.z0 + G.hz * G.ezflt;   // edge_U of the lower side
+  } else if (tag1 == 1) {
+    iz1 = 0; j1 = 0; nz = -1.0; zf = G.z0;                                                         // edge_D
+  } else {
+    iz1 = G.nz - 1; j1 = N - 1; nz = 1.0; zf = G.z0 + G.hz * G.nz;                                 // edge_U
+  }
+  const int e_lo = G.halo_left ? -1 : 0, e_hi = G.halo_right ? G.nx : G.nx - 1;  // virtual elements of neighbour strips
   for (int e = e_lo; e <= e_hi; ++e)
     for (int i = 0; i < N; ++i) {
       const int pos = e * (N - 1) + i;
       if (pos < 0 || pos >= np) continue;
-      B[pos] += G.wgll[i] * (0.5 * G.hx);  // BC_get_normal_and_weights (spec_grid.f90:961-1011)
+      F.B[pos] += G.wgll[i] * (0.5 * G.hx);  // BC_get_normal_and_weights (spec_grid.f90:961-1011)
       if (e < 0 || e >= G.nx) continue;
-      node1[pos] = (int)cart_lat_id(G, e, G.ezflt - 1, i, N - 1);
-      node2[pos] = (int)cart_lat_id(G, e, G.ezflt, i, 0);
-      const double x = gx_of(G, e, i);
-      coord[2 * pos] = x;
-      coord[2 * pos + 1] = G.z0 + G.hz * G.ezflt;
-      n1[pos] = 0.0;       // outward normal of the lower side (edge_U): (t_z,-t_x) with t = (-1,0)
-      n1[pos + np] = 1.0;
-      const bool nuc = std::fabs(x - x_nuc) <= half_nuc;  // DIST_PWCONR with one radius (distribution_pwconr.f90:69-85)
-      T0[pos] = nuc ? Tt_nuc : Tt;                        // bc_dynflt.f90:392-400 with no background stress
-      T0[pos + np] = Tn;
+      F.node1[pos] = (int)cart_lat_id(G, e, iz1, i, j1);
+      if (F.two) F.node2[pos] = (int)cart_lat_id(G, e, iz2, i, j2);
+      F.coord[2 * pos] = gx_of(G, e, i);
+      F.coord[2 * pos + 1] = zf;
+      F.n1[pos] = 0.0;
+      F.n1[pos + np] = nz;
     }
   if (S.perio_lr) {  // BC_get_normal_and_weights(..., periodic) (spec_grid.f90:1000-1005)
-    B[0] = B[0] + B[np - 1];
-    B[np - 1] = B[0];
+    F.B[0] = F.B[0] + F.B[np - 1];
+    F.B[np - 1] = F.B[0];
   }
   if (ndof == 2)
-    for (int k = 0; k < np; ++k) B[k + np] = B[k];
+    for (int k = 0; k < np; ++k) F.B[k + np] = F.B[k];
+}
+
+// BC_DYNFLT_init (bc_dynflt.f90:231-520) on the box.  `law` carries what the host read and evaluated at the
+// fault nodes (T0, cohesion, V0, the friction-law arrays, the normal-stress law, the output strides); the
+// topology members (node1, node2, n1, B, invM1, invM2, Z, coord, CoefA2V, CoefA2D) are filled here.
+static int cart_add_dynflt(EngineBase* Eb, CartState& S, int tag1, int tag2, const s2d_dynflt_desc& law) {
+  const CartGeom& G = S.G;
+  S2D_REQUIRE(!Eb->committed, "cart_add_dynflt after commit");
+  S.bc_added = true;
+  const int ndof = G.ndof;
+  FaultTopo F;
+  cart_fault_topology(S, tag1, tag2, F);
+  const int np = F.np;
+  S2D_REQUIRE(law.np == np, "cart_add_dynflt: np does not match the fault (use s2d_cart_fault_nodes)");
+  S2D_REQUIRE(law.T0, "cart_add_dynflt: T0 missing");
   // invM at the fault nodes from the current mass (bc_dynflt.f90:338-343)
-  std::vector<double> m1((size_t)np * ndof), m2((size_t)np * ndof);
+  std::vector<double> m1((size_t)np * ndof), m2((size_t)np * ndof, 0.0);
   {
     DevBuf<int> dn1, dn2;
     DevBuf<double> o1, o2;
-    dn1.upload(node1);
-    dn2.upload(node2);
+    dn1.upload(F.node1);
     o1.alloc((size_t)np * ndof);
-    o2.alloc((size_t)np * ndof);
+    if (F.two) {
+      dn2.upload(F.node2);
+      o2.alloc((size_t)np * ndof);
+    }
     if (Eb->prec == 8) {
       k_gather_nodes<double><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<double>(Eb)->rmass.p, Eb->npoin, ndof, np, dn1.p, o1.p);
-      k_gather_nodes<double><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<double>(Eb)->rmass.p, Eb->npoin, ndof, np, dn2.p, o2.p);
+      if (F.two) k_gather_nodes<double><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<double>(Eb)->rmass.p, Eb->npoin, ndof, np, dn2.p, o2.p);
     } else {
       k_gather_nodes<float><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<float>(Eb)->rmass.p, Eb->npoin, ndof, np, dn1.p, o1.p);
-      k_gather_nodes<float><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<float>(Eb)->rmass.p, Eb->npoin, ndof, np, dn2.p, o2.p);
+      if (F.two) k_gather_nodes<float><<<ceil_div(np, 128), 128, 0, Eb->stream>>>(as_engine<float>(Eb)->rmass.p, Eb->npoin, ndof, np, dn2.p, o2.p);
     }
     S2D_CUDA(cudaStreamSynchronize(Eb->stream));
     o1.download(m1.data());
-    o2.download(m2.data());
+    if (F.two) o2.download(m2.data());
   }
-  std::vector<double> invM1(m1.size()), invM2(m2.size()), Z(m1.size());
+  std::vector<double> invM1(m1.size()), invM2(m1.size(), 0.0), Z(m1.size());
   const double A2V = S.CoefA2V();
   for (size_t q = 0; q < m1.size(); ++q) {
     invM1[q] = 1.0 / m1[q];
-    invM2[q] = 1.0 / m2[q];
-    Z[q] = 1.0 / (A2V * B[q] * (invM1[q] + invM2[q]));  // bc_dynflt.f90:349-354
+    if (F.two) {
+      invM2[q] = 1.0 / m2[q];
+      Z[q] = 1.0 / (A2V * F.B[q] * (invM1[q] + invM2[q]));  // bc_dynflt.f90:349-354
+    } else {
+      Z[q] = 0.5 / (A2V * F.B[q] * invM1[q]);
+    }
   }
-  S.fault_coord = coord;
-  S.fault_T0 = T0;
-  S.fault_B.assign(B.begin(), B.begin() + np);
-  S.fault_mu0 = MuS;
+  s2d_dynflt_desc d = law;
+  d.node1 = F.node1.data();
+  d.node2 = F.two ? F.node2.data() : nullptr;
+  d.n1 = F.n1.data();
+  d.B = F.B.data();
+  d.invM1 = invM1.data();
+  d.invM2 = F.two ? invM2.data() : nullptr;
+  d.Z = Z.data();
+  d.coord = F.coord.data();
+  std::vector<double> coh;
+  if (!d.cohesion) {
+    coh.assign(np, 0.0);
+    d.cohesion = coh.data();
+  }
+  d.CoefA2V = A2V;
+  d.CoefA2D = S.CoefA2D();
+  d.oix1 = std::max(d.oix1, 1);
+  d.oixn = std::min(d.oixn, np);
+  const int id = Eb->add_dynflt(d);
+  CartState::FaultInfo fi;
+  fi.coord = F.coord;
+  fi.T0.assign(law.T0, law.T0 + (size_t)np * 2);
+  fi.B.assign(F.B.begin(), F.B.begin() + np);
+  if ((int)S.faults.size() <= id) S.faults.resize(id + 1);
+  S.faults[id] = fi;
+  return id;
+}
+
+int s2d_cart_fault_nodes(s2d_handle h, int32_t tag1, int32_t tag2, int32_t* np, double* coord) {
+  CART_GUARD_BEGIN
+  FaultTopo F;
+  cart_fault_topology(S, tag1, tag2, F);
+  if (np) *np = F.np;
+  if (coord) std::copy(F.coord.begin(), F.coord.end(), coord);
+  CART_GUARD_END
+}
+
+int s2d_cart_add_dynflt(s2d_handle h, int32_t tag1, int32_t tag2, const s2d_dynflt_desc* law, int32_t* fault_id) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(law, "cart_add_dynflt: null descriptor");
+  const int id = cart_add_dynflt(Eb, S, tag1, tag2, *law);
+  if (fault_id) *fault_id = id;
+  CART_GUARD_END
+}
+
+// the two-sided fault of ezflt with linear slip weakening, uniform parameters and a nucleation patch
+int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, double Tn, double Tt, double Tt_nuc,
+                           double x_nuc, double half_nuc, int32_t oixd, int32_t oitd, int32_t nt_max,
+                           int32_t* fault_id) {
+  CART_GUARD_BEGIN
+  FaultTopo F;
+  cart_fault_topology(S, 5, 6, F);
+  const int np = F.np;
+  std::vector<double> T0((size_t)np * 2), dc(np, Dc), mus(np, MuS), mud(np, MuD), pw(np, 3.0), alpha(np, 0.0);
+  for (int k = 0; k < np; ++k) {
+    const bool nuc = std::fabs(F.coord[2 * k] - x_nuc) <= half_nuc;  // DIST_PWCONR with one radius (distribution_pwconr.f90:69-85)
+    T0[k] = nuc ? Tt_nuc : Tt;                                       // bc_dynflt.f90:392-400 with no background stress
+    T0[k + np] = Tn;
+  }
   s2d_dynflt_desc d;
   std::memset(&d, 0, sizeof(d));
   d.np = np;
-  d.node1 = node1.data();
-  d.node2 = node2.data();
-  d.n1 = n1.data();
-  d.B = B.data();
-  d.invM1 = invM1.data();
-  d.invM2 = invM2.data();
-  d.Z = Z.data();
   d.T0 = T0.data();
-  d.cohesion = coh.data();
-  d.coord = coord.data();
-  d.CoefA2V = A2V;
-  d.CoefA2D = S.CoefA2D();
   d.allow_opening = 1;
   d.swf_kind = 1;
   d.swf_dc = dc.data();
@@ -841,8 +921,27 @@ int s2d_cart_add_fault_swf(s2d_handle h, double Dc, double MuS, double MuD, doub
   d.oit = 0;
   d.oitd = oitd;
   d.nt_max = nt_max;
-  const int id = Eb->add_dynflt(d);
+  const int id = cart_add_dynflt(Eb, S, 5, 6, d);
   if (fault_id) *fault_id = id;
+  CART_GUARD_END
+}
+
+// bc_DIRNEU_init (bc_dirneu.f90:117-146) on a side of the box: kinds 1 = Neumann, 2 = Dirichlet per component
+int s2d_cart_add_dirneu(s2d_handle h, int32_t side, int32_t kind_h, int32_t kind_v) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(side >= 1 && side <= 4, "cart_add_dirneu: side tag must be 1..4");
+  S2D_REQUIRE(!Eb->committed, "cart_add_dirneu after commit");
+  const CartGeom& G = S.G;
+  S2D_REQUIRE(!(side == 4 && G.halo_left) && !(side == 2 && G.halo_right),
+              "cart_add_dirneu: that side is a strip interface, not a physical boundary");
+  S.bc_added = true;
+  const int LX = G.S.LX, LZ = G.S.LZ;
+  const bool horiz = (side == 1 || side == 3);
+  const int np = horiz ? LX : LZ;
+  std::vector<int> node(np);
+  for (int k = 0; k < np; ++k)
+    node[k] = side == 1 ? k + 1 : side == 3 ? (LZ - 1) * LX + k + 1 : side == 4 ? k * LX + 1 : k * LX + LX;
+  Eb->add_dirneu(np, node.data(), kind_h, kind_v, nullptr, nullptr);
   CART_GUARD_END
 }
 
@@ -954,13 +1053,14 @@ int s2d_cart_add_receivers(s2d_handle h, int32_t nx, double xa, double za, doubl
   CART_GUARD_END
 }
 
-int s2d_cart_fault_info(s2d_handle h, int32_t* np, double* coord, double* T0, double* B, double* mu0) {
+int s2d_cart_fault_info(s2d_handle h, int32_t fault_id, int32_t* np, double* coord, double* T0, double* B) {
   CART_GUARD_BEGIN
-  if (np) *np = (int32_t)(S.fault_coord.size() / 2);
-  if (coord) std::copy(S.fault_coord.begin(), S.fault_coord.end(), coord);
-  if (T0) std::copy(S.fault_T0.begin(), S.fault_T0.end(), T0);
-  if (B) std::copy(S.fault_B.begin(), S.fault_B.end(), B);
-  if (mu0) *mu0 = S.fault_mu0;
+  S2D_REQUIRE(fault_id >= 0 && fault_id < (int)S.faults.size() && !S.faults[fault_id].coord.empty(), "cart_fault_info: unknown fault");
+  const CartState::FaultInfo& fi = S.faults[fault_id];
+  if (np) *np = (int32_t)(fi.coord.size() / 2);
+  if (coord) std::copy(fi.coord.begin(), fi.coord.end(), coord);
+  if (T0) std::copy(fi.T0.begin(), fi.T0.end(), T0);
+  if (B) std::copy(fi.B.begin(), fi.B.end(), B);
   CART_GUARD_END
 }
 
