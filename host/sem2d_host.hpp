@@ -6,7 +6,8 @@
 // header), so this layer is what a maintainer's ISO_C_BINDING shim looks like when
 // written in C++.  Scope = what the device-side structured builder provides: &MESH_CART boxes with
 // one ELAST material, ABSORB, PERIOD and DIRNEU sides, DYNFLT (the split-node row of `ezflt`, or the bottom / top
-// side as a one-sided fault) with slip-weakening or rate-and-state friction and ORDER0 / PWCONR distributions, FORCE
+// side as a one-sided fault) with slip-weakening or rate-and-state friction and ORDER0 / PWCONR / GAUSSIAN
+// distributions, Kelvin-Voigt damping (ELAST + KV), FORCE
 // and moment-tensor sources, REC_LINE stations at nodes, the leapfrog, Newmark, HHT-alpha and symplectic schemes.  Anything else in a Par.inp is
 // refused with IO_abort, never silently ignored -- except plotting (&SNAP_*), which is not on the path.
 //
@@ -76,13 +77,19 @@ struct rec_type {
 // zones) and PWCONR (SRC/distribution_pwconr.f90: constant in concentric rings around a point).
 struct cd_type {
   double c = 0.0;
-  int dist = 0;  // 0 constant, 1 ORDER0, 2 PWCONR
+  int dist = 0;  // 0 constant, 1 ORDER0, 2 PWCONR, 3 GAUSSIAN
+  double gx0 = 0, gz0 = 0, glx = 1, glz = 1, goff = 0, gamp = 1;  // GAUSSIAN (SRC/distribution_gaussian.f90:25-50)
+  int gorder = 1;
   int xn = 1, zn = 1;
   std::vector<double> xb, zb, val;  // ORDER0: zone boundaries, val(xn,zn) column-major
   double ref[2] = {0, 0};           // PWCONR: reference point, radii, values
   std::vector<double> rad;
   double eval(double x, double z) const {
     if (dist == 0) return c;
+    if (dist == 3) {  // generate_gaussian_dist (distribution_gaussian.f90:72-73)
+      const double a = (x - gx0) / glx, b = (z - gz0) / glz;
+      return goff + gamp * std::exp(-std::pow(std::pow(a, 2.0) + std::pow(b, 2.0), (double)gorder));
+    }
     if (dist == 1) {  // generate_order0_dist / zone (distribution_order0.f90:73-105)
       auto zone = [](double q, int nz, const std::vector<double>& b) {
         if (nz == 1) return 1;
@@ -131,8 +138,10 @@ struct problem_type {
   // &MESH_CART
   double xlim[2] = {0, 0}, zlim[2] = {0, 0};
   int nelem[2] = {0, 0}, ezflt = 0;
-  // &MAT_ELASTIC
+  // &MAT_ELASTIC, &MAT_KV (SRC/mat_kelvin_voigt.f90:35-66)
   double rho = 0, cp = 0, cs = 0;
+  bool has_kv = false, ETAxDT = true;
+  cd_type kv_eta;
   timescheme_type time;
   std::vector<bc_type> bc;
   std::vector<source_type> src;
@@ -185,8 +194,17 @@ inline cd_type DIST_CD_Read(const namelist_file& in, const nml_group& g, const s
     if ((int)r.size() < 2 * num - 1) IO_abort("read_pwconr_dist: missing records after DIST_PWCONR");
     cd.rad.assign(r.begin(), r.begin() + (num - 1));
     cd.val.assign(r.begin() + (num - 1), r.end());
+  } else if (name == "GAUSSIAN") {  // read_gaussian_dist (distribution_gaussian.f90:25-50)
+    cd.dist = 3;
+    cd.gx0 = d.real8("centered_at", 0.0, 0);
+    cd.gz0 = d.real8("centered_at", 0.0, 1);
+    cd.glx = d.real8("length", 1.0, 0);
+    cd.glz = d.real8("length", 1.0, 1);
+    cd.goff = d.real8("offset", 0.0);
+    cd.gamp = d.real8("ampli", 1.0);
+    cd.gorder = d.integer("order", 1);
   } else {
-    IO_abort("DIST_read: distribution '" + name + "' is not provided here (ORDER0, PWCONR are)");
+    IO_abort("DIST_read: distribution '" + name + "' is not provided here (ORDER0, PWCONR, GAUSSIAN are)");
   }
   return cd;
 }
@@ -236,9 +254,19 @@ inline void read_main(problem_type& pb, const std::string& file) {
   if (k < 0) IO_abort("MAT_read: no MATERIAL block");
   for (long m0 = k, first = 1; m0 >= 0; m0 = in.find("MATERIAL", (size_t)m0 + 1), first = 0) {
     const nml_group& g = in.at((size_t)m0);
-    if (g.count("kind") != 1 || g.text("kind", "") != "ELAST") IO_abort("MAT_read: only kind='ELAST' is provided here");
+    const bool kv = g.count("kind") == 2 && g.text("kind", "", 1) == "KV";
+    if (g.text("kind", "") != "ELAST" || (g.count("kind") != 1 && !kv))
+      IO_abort("MAT_read: only kind='ELAST' and kind='ELAST','KV' are provided here");
     const long m = in.find("MAT_ELASTIC", (size_t)m0);
-    if (m < 0) IO_abort("MAT_ELAST_read: MAT_ELASTIC input block not found");
+    if (kv) {  // MAT_KV_read (SRC/mat_kelvin_voigt.f90:35-66)
+      if (!first) IO_abort("MAT_read: Kelvin-Voigt damping is provided for a single material");
+      const long q = in.find("MAT_KV", (size_t)m0);
+      if (q < 0) IO_abort("MAT_KV_read: MAT_KV input block not found");
+      size_t cur = (size_t)q + 1;
+      pb.kv_eta = DIST_CD_Read(in, in.at((size_t)q), "eta", 0.0, cur);
+      pb.ETAxDT = in.at((size_t)q).logical("etaxdt", true);
+      pb.has_kv = true;
+    }
     const nml_group& e = in.at((size_t)m);  // SRC/mat_elastic.f90:104-129
     if (e.has("cph") || e.has("csh") || e.has("rhoh") || e.has("c11")) IO_abort("MAT_ELAST_read: distributions / anisotropy are not provided here");
     const double rho = e.real8("rho", 0.0), cp = e.real8("cp", 0.0), cs = e.real8("cs", 0.0);
@@ -500,7 +528,6 @@ inline void read_main(problem_type& pb, const std::string& file) {
     if (r.number < 0) IO_abort("REC_read: \"number\" must be positive");
     if (r.SeisField != 'D' && r.SeisField != 'V' && r.SeisField != 'A') IO_abort("REC_read: parameter field has wrong value [D,V,A]");
     if (g.text("file", "none") != "none") IO_abort("REC_read: station files are not provided here");
-    if (!r.AtNode) IO_abort("REC_read: AtNode=F (interpolated stations) is provided by the generic C-ABI, not by this host");
     if (g.count("first") < 2 || g.count("last") < 2) IO_abort("REC_read: first and last are required");
     for (int q = 0; q < 2; ++q) {
       r.first[q] = g.real8("first", 0, q);
@@ -550,6 +577,15 @@ inline void init_main(problem_type& pb) {
     t.dt = dt;
     if (t.total > 0.0) t.nt = (int)std::ceil(t.total / t.dt);
     t.total = t.nt * t.dt;
+  }
+  if (pb.has_kv) {  // MAT_KV_init_elem_work (SRC/mat_kelvin_voigt.f90:117-133): eta at the GLL nodes, times dt
+    std::vector<double> coord(2 * (size_t)pb.npoin), eta((size_t)pb.npoin);
+    s2d_check(pb, s2d_cart_get(pb.gpu, nullptr, nullptr, nullptr, coord.data()), "MAT_KV_init");
+    for (size_t q = 0; q < eta.size(); ++q) {
+      eta[q] = pb.kv_eta.eval(coord[2 * q], coord[2 * q + 1]);
+      if (pb.ETAxDT) eta[q] = t.dt * eta[q];
+    }
+    s2d_check(pb, s2d_cart_set_kv(pb.gpu, eta.data()), "MAT_KV_init");
   }
   // BC_init (SRC/bc_gen.f90:190-251): periodic boundaries first, then input order
   for (bc_type& bc : pb.bc)
@@ -632,9 +668,14 @@ inline void init_main(problem_type& pb) {
     rec_type& r = *pb.rec;
     r.nt = t.nt / r.isamp + 1;  // receivers.f90:172
     r.tsamp = t.dt * r.isamp;
-    s2d_check(pb, s2d_cart_add_receivers(pb.gpu, r.number, r.first[0], r.first[1], r.last[0], r.last[1], r.SeisField,
-                                         r.isamp, r.nt),
-              "REC_init");
+    if (r.AtNode)
+      s2d_check(pb, s2d_cart_add_receivers(pb.gpu, r.number, r.first[0], r.first[1], r.last[0], r.last[1], r.SeisField,
+                                           r.isamp, r.nt),
+                "REC_init");
+    else
+      s2d_check(pb, s2d_cart_add_receivers_interp(pb.gpu, r.number, r.first[0], r.first[1], r.last[0], r.last[1],
+                                                  r.SeisField, r.isamp, r.nt),
+                "REC_init");
     int32_t nx = 0;
     s2d_check(pb, s2d_cart_receiver_info(pb.gpu, &nx, nullptr), "REC_init");
     r.nx = nx;

@@ -279,6 +279,15 @@ int s2d_cart_fault_info(s2d_handle h, int32_t fault_id, int32_t* np, double* coo
 /* number of stations kept (duplicates dropped, receivers.f90:255) and their relocated positions
  * rec%coord(2,nx) (receivers.f90:231-303); coord may be NULL */
 int s2d_cart_receiver_info(s2d_handle h, int32_t* nx, double* coord);
+/* REC_LINE with AtNode=F: stations stay where they are, sampled with the Lagrange interpolant of the element
+ * their nearest node picks (receivers.f90:262-300) */
+int s2d_cart_add_receivers_interp(s2d_handle h, int32_t nx, double xa, double za, double xb, double zb,
+                                  char field, int32_t isamp, int32_t nt_rec);
+/* Kelvin-Voigt viscosity of the whole box (mat_kelvin_voigt.f90:117-150): eta(npoin) at the GLL nodes in the
+ * caller's numbering, already multiplied by dt when ETAxDT.  eta must be a function of position (a constant
+ * or a distribution evaluated at the node coordinates), which makes the element-wise d + eta*v node-wise.
+ * With it the node update runs in separate passes (no fused step). */
+int s2d_cart_set_kv(s2d_handle h, const double* eta_node);
 int s2d_cart_info(s2d_handle h, int64_t* npoin, int64_t* nelem, double* dt);
 /* Overrides the time step (time%dt) before any boundary is added.  x-strips of one global mesh
  * must agree on dt: the host takes the minimum of the per-strip Courant steps (the reference takes

@@ -116,6 +116,9 @@ _SIGS = {
     "s2d_cart_fault_nodes": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p],
     "s2d_cart_add_dynflt": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(DynfltDesc), C.POINTER(C.c_int32)],
     "s2d_cart_add_dirneu": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32],
+    "s2d_cart_set_kv": [C.c_void_p, C.c_void_p],
+    "s2d_cart_add_receivers_interp": [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_char,
+                                      C.c_int32, C.c_int32],
     "s2d_cart_add_moment": [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_int32)],
     "s2d_cart_receiver_info": [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p],
     "s2d_cart_info": [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)],

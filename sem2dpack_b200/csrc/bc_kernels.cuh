@@ -116,6 +116,15 @@ __global__ void k_moments(T* f, size_t npoin, int ndof, int nmom, const int* src
   }
 }
 
+// out = d + eta*v with a node-wise eta (Kelvin-Voigt on structured boxes)
+template <typename T>
+__global__ void k_kv_combine(T* __restrict__ out, const T* __restrict__ d, const T* __restrict__ v,
+                             const T* __restrict__ eta, size_t npoin, int ndof) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n = npoin * ndof;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) out[q] = d[q] + eta[q % npoin] * v[q];
+}
+
 // y += c*x  (symplectic stages, solver.f90:185,197)
 template <typename T>
 __global__ void k_axpy(T* __restrict__ y, const T* __restrict__ x, T* __restrict__ f, size_t n, T c, int zero_f) {

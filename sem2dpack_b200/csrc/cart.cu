@@ -438,6 +438,10 @@ static void cart_build(Engine<T>& E, CartState& S) {
     k_cart_permute<double, T><<<nblk, 256, 0, Ep->stream>>>(Gc, ref, lat, Ep->npoin, Gc.ndof, 0);
     S2D_CUDA(cudaGetLastError());
   };
+  E.cart_from_ref1 = [Ep, Gc, nblk](const double* ref, T* lat) {
+    k_cart_permute<double, T><<<nblk, 256, 0, Ep->stream>>>(Gc, ref, lat, Ep->npoin, 1, 0);
+    S2D_CUDA(cudaGetLastError());
+  };
   S2D_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -1050,6 +1054,60 @@ int s2d_cart_add_receivers(s2d_handle h, int32_t nx, double xa, double za, doubl
     }
   }
   Eb->add_receivers((int)ig.size(), field, isamp, nt_rec, 1, ig.data(), nullptr, nullptr);
+  CART_GUARD_END
+}
+
+// Kelvin-Voigt viscosity of the box (mat_kelvin_voigt.f90): eta per GLL node in the caller's numbering,
+// already multiplied by dt when ETAxDT (:127)
+int s2d_cart_set_kv(s2d_handle h, const double* eta_node) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(eta_node, "cart_set_kv: null eta");
+  Eb->set_node_kv(eta_node);
+  CART_GUARD_END
+}
+
+// REC_posit with AtNode = F (receivers.f90:262-300): the nearest node picks the element (the first one that
+// holds it, SE_node_belongs_to), the point is located inside it (FE_find_point: affine for a rectangle) and
+// the Lagrange weights of SE_init_interpol (spec_grid.f90:385-409) multiply the N*N nodes of that element
+int s2d_cart_add_receivers_interp(s2d_handle h, int32_t nx, double xa, double za, double xb, double zb, char field,
+                                  int32_t isamp, int32_t nt_rec) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(nx >= 1, "cart_add_receivers: nx < 1");
+  const CartGeom& G = S.G;
+  const int N = G.N, N2 = N * N;
+  std::vector<int> nodes((size_t)N2 * nx);
+  std::vector<double> interp((size_t)N2 * nx);
+  S.rec_coord.clear();
+  auto lagrange = [&](double xi, double* hq) {
+    for (int i = 0; i < N; ++i) {
+      double p = 1.0;
+      for (int m = 0; m < N; ++m)
+        if (m != i) p *= (xi - G.xgll[m]) / (G.xgll[i] - G.xgll[m]);
+      hq[i] = p;
+    }
+  };
+  for (int n = 0; n < nx; ++n) {
+    const double w = nx > 1 ? (double)n / (double)(nx - 1) : 0.0;
+    const double x = xa + w * (xb - xa), z = za + w * (zb - za);
+    int ex, i, ez, j;
+    nearest_1d(G, x, G.x0, G.hx, G.nx, ex, i);
+    nearest_1d(G, z, G.z0, G.hz, G.nz, ez, j);
+    // first element (ascending index) that holds the node
+    if (i == 0 && ex > 0) ex -= 1;
+    if (j == 0 && ez > 0 && !row_detached(G, ez)) ez -= 1;
+    const double xi = 2.0 * (x - (G.x0 + G.hx * ex)) / G.hx - 1.0, eta = 2.0 * (z - (G.z0 + G.hz * ez)) / G.hz - 1.0;
+    std::vector<double> hx(N), hz(N);
+    lagrange(xi, hx.data());
+    lagrange(eta, hz.data());
+    for (int jj = 0; jj < N; ++jj)
+      for (int ii = 0; ii < N; ++ii) {
+        nodes[(size_t)N2 * n + ii + N * jj] = (int)cart_lat_id(G, ex, ez, ii, jj);
+        interp[(size_t)N2 * n + ii + N * jj] = hx[ii] * hz[jj];
+      }
+    S.rec_coord.push_back(x);  // the station keeps its position (rec%coord = newcoord of FE_find_point)
+    S.rec_coord.push_back(z);
+  }
+  Eb->add_receivers_nodes(nx, field, isamp, nt_rec, nodes.data(), interp.data());
   CART_GUARD_END
 }
 

@@ -51,7 +51,7 @@ struct Receivers {
   bool present = false;
   char field = 'V';
   RecDev dev{};
-  DevBuf<int> iglob, einterp;
+  DevBuf<int> iglob, einterp, nodes;
   DevBuf<double> interp;
   DevBuf<float> sis;
 };
@@ -82,6 +82,8 @@ class EngineBase {
   virtual int add_moment(int nterms, const int32_t* node, const double* coef) = 0;
   virtual void add_receivers(int nx, char field, int isamp, int nt_rec, int at_node, const int32_t* iglob,
                              const int32_t* einterp, const double* interp) = 0;
+  virtual void add_receivers_nodes(int nx, char field, int isamp, int nt_rec, const int32_t* nodes, const double* interp) = 0;
+  virtual void set_node_kv(const double* eta_ref) = 0;
   virtual void commit(int variant) = 0;
   virtual void set_fields(const double* d, const double* v, const double* a) = 0;
   virtual void get_fields(double* d, double* v, double* a) = 0;
@@ -175,12 +177,16 @@ class Engine : public EngineBase {
   StripGeom cart_S{};
   DevBuf<T> cart_hx, cart_hz;
   DevBuf<int> cart_meet;  // arrival counters of the group-boundary columns (strip_kernels.cuh)
+  // Kelvin-Voigt damping on a structured box: eta (already * dt) is a function of position, so the
+  // element-wise d_loc + eta*v_loc of MAT_KV_add_etav (mat_kelvin_voigt.f90:137-150) is the node field d + eta*v
+  DevBuf<T> cart_kv_eta, cart_kv_buf;
   // compact coefficient mode: p_coef holds (lambda, mu) per GLL point, the strip kernel forms the planes
   int cart_compact = 0;
   double cart_cdx = 0.0, cart_cdz = 0.0, cart_cdet = 0.0;
   std::vector<double> cart_wgll;
   std::function<void(const T*, double*)> cart_to_ref;    // lattice (T) -> reference numbering (FP64), device to device
   std::function<void(const double*, T*)> cart_from_ref;  // reference numbering (FP64) -> lattice (T)
+  std::function<void(const double*, T*)> cart_from_ref1; // the same for a one-component node array
   // fused leapfrog step of the strip kernel: two displacement buffers (the kernel reads d[n] and
   // writes the predicted d[n+1] of the next step), deferred-node tables (strip_kernels.cuh)
   DevBuf<T> d2;
@@ -725,6 +731,46 @@ class Engine : public EngineBase {
     perio.push_back(std::move(b));
   }
 
+  // interpolated stations given by the N*N nodes of their element (structured builder: there is no ibool table)
+  void add_receivers_nodes(int nx, char field, int isamp, int nt_rec, const int32_t* nodes, const double* interp) override {
+    S2D_REQUIRE(!committed, "add_receivers after commit");
+    S2D_REQUIRE(nx > 0 && isamp > 0 && nt_rec > 0 && nodes && interp, "add_receivers_nodes: bad arguments");
+    S2D_REQUIRE(field == 'D' || field == 'V' || field == 'A', "add_receivers: field must be D, V or A");
+    const size_t n2 = (size_t)ngll * ngll;
+    check_nodes((int)(n2 * nx), nodes, "add_receivers_nodes");
+    std::vector<int32_t> eidx(nx);
+    for (int n = 0; n < nx; ++n) eidx[n] = n + 1;
+    rec.present = true;
+    rec.field = field;
+    RecDev& R = rec.dev;
+    R.nx = nx;
+    R.ndof = ndof;
+    R.isamp = isamp;
+    R.nt = nt_rec;
+    R.at_node = 0;
+    R.ngll = ngll;
+    rec.einterp.upload(eidx.data(), nx);
+    rec.interp.upload(interp, n2 * nx);
+    rec.nodes.upload(nodes, n2 * nx);
+    rec.sis.alloc((size_t)nt_rec * nx * ndof);
+    rec.sis.zero();
+    R.iglob = nullptr;
+    R.einterp = rec.einterp.p;
+    R.interp = rec.interp.p;
+    R.ibool = rec.nodes.p;
+    R.sis = rec.sis.p;
+  }
+  void set_node_kv(const double* eta_ref) override {
+    S2D_REQUIRE(cart_mode, "set_node_kv: structured builder only (the generic engine takes s2d_set_kv)");
+    S2D_REQUIRE(!committed, "set_node_kv after commit");
+    DevBuf<double> tmp;
+    tmp.upload(eta_ref, npoin);
+    cart_kv_eta.alloc(npoin);
+    cart_kv_buf.alloc(npoin * ndof);
+    cart_from_ref1(tmp.p, cart_kv_eta.p);
+    S2D_CUDA(cudaStreamSynchronize(stream));
+  }
+
   int add_moment(int nterms, const int32_t* node, const double* coef_) override {
     S2D_REQUIRE(!committed, "add_moment after commit");
     S2D_REQUIRE(nterms > 0 && node && coef_, "add_moment: empty source");
@@ -906,7 +952,8 @@ class Engine : public EngineBase {
       S2D_REQUIRE(variant == S2D_ASM_PATCH, "commit: the structured builder only provides the strip kernel");
       k_invert<T><<<grid_for(rmass.n), 256, 0, stream>>>(rmass.p, rmass.n);
       // the node update rides in the strip kernel for leapfrog and for the explicit Newmark scheme (beta = 0)
-      fused = (scheme.kind == 0 || (scheme.kind == 1 && scheme.beta == 0.0)) && env_int("S2D_FUSED", 1) != 0;
+      fused = (scheme.kind == 0 || (scheme.kind == 1 && scheme.beta == 0.0)) && env_int("S2D_FUSED", 1) != 0 &&
+              cart_kv_eta.n == 0;  // the fused update reads d only: Kelvin-Voigt boxes take the separate passes
       if (fused) build_deferred_tables();
     } else {
       if (nkv == 0) h_elem2kv.assign(nelem, -1);
@@ -946,6 +993,12 @@ class Engine : public EngineBase {
   // f = -K d  (compute_Fint, solver.f90:273-320); f must be zero on entry unless the patch variant
   void launch_fint(const T* dd, const T* vv, T* ff) {
     if (cart_mode) {
+      if (cart_kv_eta.n) {  // forces from d + eta*v (solver.f90:293-295 with mat_kelvin_voigt.f90:147)
+        const size_t nd = npoin * ndof;
+        k_kv_combine<T><<<grid_for(nd), 256, 0, stream>>>(cart_kv_buf.p, dd, vv, cart_kv_eta.p, npoin, ndof);
+        launches++;
+        dd = cart_kv_buf.p;
+      }
       launch_strips(strip_io(dd, ff));
       return;
     }

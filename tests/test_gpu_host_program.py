@@ -130,6 +130,35 @@ def test_ratestate_deck_against_the_shipped_series_and_the_oracle(tmp_path):
     o.close()
 
 
+def test_tpv3_deck_against_the_oracle(tmp_path):
+    """EXAMPLES/TestFlt2D_SCEC_TPV3_inplane through the host program: NGLL=6 P-SV, ELAST + Kelvin-Voigt with
+    a GAUSSIAN eta, one-sided slip-weakening fault on the bottom side with PWCONR Tt and MuS, absorbing
+    sides 2,3, DIRNEU side 4 (v='D'), Newmark, 10 interpolated stations (AtNode=F, isamp=20), fault
+    output nodes 1:65:4.  No artefact of the reference pins this deck: checked against the
+    oracle (float32 files) and the SCEC TPV3 physics the oracle test uses."""
+    deck = harness.deck("tpv3").replace("TotalTime=16.d0", "TotalTime=7.d0")
+    p = run(tmp_path, deck, "--quiet")
+    assert p.returncode == 0, p.stdout + p.stderr
+    o = orc.Oracle(deck, renumber=False)
+    nt = o.i("nt")
+    o.step(nt)
+    x, rec = read_fault(tmp_path, 1)
+    onx = o.i("bc.0.onx")
+    want = o.arr("bc.0.out").reshape(-1, 6, onx)
+    assert rec.shape == want.shape and onx == 17
+    for c in range(6):
+        assert np.abs(rec[:, c] - want[:, c]).max() <= 5e-6 * max(np.abs(want[:, c]).max(), 1e-30), c
+    assert rec[-1, 0].max() > 0.5 and rec[:, 0].min() > -1e-6      # it ruptured, slip is one-signed
+    _, coord, ux = read_sep(tmp_path, "Ux_sem2d.dat")
+    _, _, uz = read_sep(tmp_path, "Uz_sem2d.dat")
+    ref = o.seis()
+    assert ux.shape == ref[:, :, 0].shape == (nt // 20 + 1, 10)
+    assert np.allclose(coord[:, 0], np.linspace(0, 15e3, 10)) and np.allclose(coord[:, 1], 500.0)
+    for got, c in ((ux, 0), (uz, 1)):
+        assert np.abs(got - ref[:, :, c]).max() <= 5e-6 * np.abs(ref[:, :, c]).max(), c
+    o.close()
+
+
 def test_binary_snapshots_and_grid_files(tmp_path):
     """&SNAP_DEF bin=T: PLOT_FIELD's node-wise float32 files and the grid files POST/ reads them with"""
     deck = harness.deck("lamb").replace("TotalTime=1.5d0, Dt=0.5d-3", "NbSteps=250, Dt=0.5d-3")
@@ -159,7 +188,7 @@ def test_binary_snapshots_and_grid_files(tmp_path):
 def test_unsupported_input_aborts_like_io_abort(tmp_path):
     """what the host does not provide is refused the way the reference refuses bad input: message +
     non-zero exit (IO_abort, stdio.f90:205-214), never ignored"""
-    p = run(tmp_path, harness.deck("tpv3"))   # ELAST + KV: the strip kernel has no Kelvin-Voigt term
+    p = run(tmp_path, harness.deck("tpv3").replace("'ELAST' ,'KV'", "'ELAST' ,'DMG'"))
     assert p.returncode == 1 and "FATAL ERROR" in p.stdout and "MAT_read" in p.stdout
     p = run(tmp_path, harness.deck("testsh").replace("courant = 0.3d0", "courant = 0.9d0"))
     assert p.returncode == 1 and "Courant out of range" in p.stdout

@@ -17,7 +17,8 @@ def run(tmp_path, text):
 def test_refusals_happen_while_reading_the_deck(tmp_path):
     assert os.path.exists(EXE), "host program missing: run __graft_entry__.build()"
     cases = [
-        (harness.deck("tpv3"), "MAT_read"),                                                    # ELAST + KV
+        (harness.deck("tpv3").replace("'ELAST' ,'KV'", "'ELAST' ,'PLAST'"), "MAT_read"),
+        (harness.deck("tpv3").replace("etaH='GAUSSIAN'", "etaH='LINEAR'"), "DIST_read"),
         (harness.deck("ratestate").replace("friction='RSF'", "friction='TWF'"), "friction='TWF'"),
         (harness.deck("ratestate").replace("TtH='ORDER0'", "TtH='SPLINE'"), "DIST_read"),
         (harness.deck("testsh").replace("courant = 0.3d0", "courant = 0.9d0"), "Courant out of range [0,0.6]"),
@@ -34,7 +35,7 @@ def test_refusals_happen_while_reading_the_deck(tmp_path):
 def test_a_good_deck_gets_as_far_as_the_device(tmp_path):
     """without a GPU the only possible failure of a supported deck is the missing device: there is no
     CPU fallback behind the host program"""
-    for name in ("lamb", "testsh", "ratestate"):
+    for name in ("lamb", "testsh", "ratestate", "tpv3"):
         p = run(tmp_path, harness.deck(name))
         if p.returncode != 0:
             assert "no CUDA device" in p.stdout, (name, p.stdout)
