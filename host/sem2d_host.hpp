@@ -152,6 +152,7 @@ struct problem_type {
   int64_t npoin = 0, nelem_total = 0;
   int it = 0;
   int precision = 8, device = -1;
+  unsigned long long hash_seed = 0;  // != 0: the heterogeneous hash medium of the synthetic benchmark family
   ~problem_type() {
     if (gpu) s2d_destroy(gpu);
   }
@@ -551,7 +552,7 @@ inline void init_main(problem_type& pb) {
   d.x1 = pb.xlim[1];
   d.z0 = pb.zlim[0];
   d.z1 = pb.zlim[1];
-  d.seed = 0;
+  d.seed = pb.hash_seed;
   d.rho = pb.rho;
   d.cp = pb.cp;
   d.cs = pb.cs;

@@ -2,7 +2,10 @@
 // reads Par.inp from the working directory, builds the problem in HBM, runs the time loop on the
 // device and writes the reference's seismogram and fault files.
 //
-//   sem2dsolve_b200 [Par.inp] [--precision 4|8] [--device N] [--quiet]
+//   sem2dsolve_b200 [Par.inp] [--precision 4|8] [--device N] [--quiet] [--hash-seed S]
+//
+// --hash-seed S (S != 0) replaces the homogeneous &MAT_ELASTIC values by the heterogeneous hash medium of the
+// synthetic benchmark family (BASELINE.json configs[4]), so that this program can drive it.
 //
 // Exit code 0 on success; on IO_abort the message is printed as stdio.f90:205-214 does
 // ("FATAL ERROR" banner) and the exit code is 1.
@@ -24,6 +27,7 @@ int main(int argc, char** argv) {
     if (s == "--precision" && a + 1 < argc) pb.precision = std::atoi(argv[++a]);
     else if (s == "--device" && a + 1 < argc) pb.device = std::atoi(argv[++a]);
     else if (s == "--quiet") quiet = true;
+    else if (s == "--hash-seed" && a + 1 < argc) pb.hash_seed = std::strtoull(argv[++a], nullptr, 10);
     else file = s;
   }
   try {
