@@ -311,7 +311,7 @@ def main():
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
         key = (f"{nx}x{nz}:f{args.precision * 8}:{'fused' if fused else 'plain'}:{'a' if store_accel else 'noa'}:"
-               f"{args.coef}")
+               f"{args.coef}" + (":newmark" if args.scheme == "newmark" else ""))
         traffic = tj.get(key)
     except Exception:
         pass
