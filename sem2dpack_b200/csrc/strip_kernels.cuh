@@ -521,7 +521,8 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       }
     }
     // (producer / consumer named barriers between neighbouring warps instead of this CTA barrier were
-    // tried: bar.arrive / bar.sync pairs with two slots deadlocked on partially filled groups -- not pursued)
+    // tried with two slots and hung: two bar.arrive of a producer that runs a row ahead complete a 64-thread
+    // phase on their own.  Strict alternation would work but couples the pair as tightly as this barrier.)
     if (WARPS > 1) __syncthreads();
     if (wact) {
       if (take) {  // column shared with the strip on the left (same group)
