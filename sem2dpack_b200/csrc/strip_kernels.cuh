@@ -203,6 +203,16 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group
 #ifndef S2D_STRIP_STAGE
 #define S2D_STRIP_STAGE 7
 #endif
+// The coefficient block of an element row is one contiguous run of the strip layout: with all six planes
+// stored (7200 B per row of a P-SV strip) it is brought in by ONE TMA bulk copy per warp and row
+// (cp.async.bulk + mbarrier, SASS UBLKCP) instead of 15 per-lane LDGSTS.128, which cost 15.5 L1 wavefronts
+// each (ncu).  Measured on B200, 4096^2 FP64, ms per launch, LDGSTS -> TMA: fused full planes 8.26 -> 6.99
+// (73 % -> 86 % of the HBM roofline), plain force evaluation 5.61 -> 5.09 (78 % -> 86 %); with the compact
+// (lambda, mu) block (2400 B per row) 5.80 -> 5.93, so that mode keeps the per-lane copies.
+// 0: never, 1 (default): full planes only, 2: both modes.
+#ifndef S2D_STRIP_TMA
+#define S2D_STRIP_TMA 1
+#endif
 // Strips per CTA.  Measured on B200 (4096^2, FP64, compact, fused; ms per launch): 4 warps at 168
 // registers, 3 CTAs/SM: 5.82;  5 warps (128 registers, 3 CTAs/SM): 6.02;  6 warps (168, 2 CTAs): 6.41;
 // 8 warps (128, 2 CTAs): 6.58 -- registers (instruction-level parallelism) beat resident warps here.
@@ -248,6 +258,11 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   T* st_r = st_v + NU * 32;                                    // [j][32]               (fused)
   T* st_a = st_r + (N - 1) * 32;                               // [c * (N-1) + j][32]   (fused Newmark: a[n-1])
   constexpr bool NM = FUSED == 2;
+  constexpr bool tma_c = (S2D_STRIP_TMA == 2 || (S2D_STRIP_TMA == 1 && !COMPACT)) && ((S2D_STRIP_STAGE & 2) != 0) &&
+                         sizeof(T) == 8;  // 16-byte vectors: block address and size are multiples of 16
+  __shared__ __align__(8) unsigned long long cbar[WARPS];
+  V2* st_cb = reinterpret_cast<V2*>(wstage);                   // TMA: the block as it lies in HBM, [pp*N+j][cx*N]
+  unsigned cphase = 0;
   const long long cta = blockIdx.x;
   const int seg = (int)(cta / G.it_ng);
   const int grp = G.it_g0 + (int)(cta - (long long)seg * G.it_ng) * G.it_step;
@@ -339,7 +354,14 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         for (int j = 1; j < N; ++j)
           stage_copy<sizeof(T)>(st_u + (c * (N - 1) + j - 1) * 32, up + A.npoin * c + rb + (size_t)j * LX);
     }
-    if (stg_c) {
+    if (tma_c) {
+      if (lane == 0) {
+        const unsigned bytes = (unsigned)(cp_row * sizeof(V2));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the warp's reads of the block come first
+        mbar_expect_tx(&cbar[warp], bytes);
+        bulk_g2s(st_cb, cpr - lanep, bytes, &cbar[warp]);
+      }
+    } else if (stg_c) {
 #pragma unroll
       for (int pp = 0; pp < NPL / 2; ++pp)
 #pragma unroll
@@ -351,6 +373,10 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       for (int l = lane; l < nlines; l += 32) l2_prefetch_line(nb + (size_t)l * 128);
     }
   };
+  if (tma_c && wact) {
+    if (lane == 0) mbar_init(&cbar[warp], 1);
+    __syncwarp();
+  }
   if (wact) {
     issue_row(ez0, cp);
     stage_commit();
@@ -377,7 +403,15 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
 #pragma unroll
           for (int j = 1; j < N; ++j) U[c][j] = up[A.npoin * c + rowbase + (size_t)j * LX];
       }
-      if (stg_c) {
+      if (tma_c) {
+        mbar_wait(&cbar[warp], cphase);
+        cphase ^= 1u;
+#pragma unroll
+        for (int pp = 0; pp < NPL / 2; ++pp)
+#pragma unroll
+          for (int j = 0; j < N; ++j) a2[pp][j] = st_cb[(pp * N + j) * cxN + lanep];
+        __syncwarp();  // every lane has its vectors in registers before the next row's copy may land
+      } else if (stg_c) {
 #pragma unroll
         for (int pp = 0; pp < NPL / 2; ++pp)
 #pragma unroll
