@@ -78,3 +78,19 @@ def test_argument_validation_precedes_device_use():
     assert L.s2d_create(C.byref(h), 2, 1, 1, 9, None, None, None, 8, C.byref(sch), -1) == -1  # S2D_EINVAL
     assert L.s2d_destroy(None) == -1
     assert L.s2d_step(None, 1, None, None) == -1
+
+
+def test_header_is_plain_c_and_structs_match_the_bindings(tmp_path):
+    """include/sem2d_b200.h is the C-ABI: it must compile as C99 (no C++ or torch types) and its structs must
+    have the layout the ctypes bindings (and the Fortran bind(C) types of INTEGRATION.md) assume."""
+    import ctypes as C
+    import subprocess
+    from sem2dpack_b200 import capi
+    src = tmp_path / "hdr.c"
+    src.write_text('#include <stdio.h>\n#include "sem2d_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu\\n", sizeof(s2d_scheme), sizeof(s2d_cart_desc), '
+                   'sizeof(s2d_dynflt_desc)); return 0; }\n')
+    exe = tmp_path / "hdr"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    assert sizes == [C.sizeof(capi.Scheme), C.sizeof(capi.CartDesc), C.sizeof(capi.DynfltDesc)]
