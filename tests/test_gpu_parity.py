@@ -223,3 +223,77 @@ def test_progress_and_energy():
     assert abs(vmax - np.abs(o.arr("v")).max()) <= 1e-12 * vmax
     assert abs(dmax - np.abs(o.arr("d")).max()) <= 1e-12 * dmax
     r.close()
+
+
+def _engine_from(o, a, nelast, kd2, variant=0, abso_flat=True):
+    """an Engine fed like harness.Rig, but with the caller's coefficient planes / absorbing-boundary form"""
+    from sem2dpack_b200 import Engine
+    e = Engine(o.i("ngll"), o.i("ndof"), o.arr("ibool"), o.arr("H"), o.arr("rmass"), o.i("scheme"), o.f("dt"),
+               o.f("beta"), o.f("gamma"), o.f("alpha"))
+    e.set_elastic(nelast, a, o.arr("elem2set"), kd2)
+    for i in range(o.i("nbc")):
+        p = f"bc.{i}."
+        if o.i(p + "kind") == harness.IS_ABSORB:
+            e.add_abso(o.arr(p + "node"), o.arr(p + "C"), is_flat=abso_flat, n=o.arr(p + "n"))
+    for s in range(o.i("nsrc")):
+        e.add_force(o.i(f"src.{s}.iglob"), [o.f(f"src.{s}.dir1"), o.f(f"src.{s}.dir2")])
+    e.commit(variant)
+    return e
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("ndof", [1, 2])
+def test_general_planes_reduce_to_the_flat_ones(ndof, variant):
+    """nelast = 3 / 10 (curved meshes, mat_elastic.f90:344-358,497-515,663-676): with the planes of a flat grid
+    embedded (the cross terms DxiDz, DetaDx vanish) the general kernels must give the flat KD1 result"""
+    deck = harness.cart_deck(11, 9, ngll=6, ndof=ndof, nrec=0, src=False).replace("zlim=0d0,900.0d0", "zlim=0d0,700.0d0")
+    o = orc.Oracle(deck, synthetic_seed=20261017)
+    n2, nset = 36, o.i("ncoefsets")
+    af = o.arr("a").reshape(nset, -1, n2)
+    ag = np.zeros((nset, 3 if ndof == 1 else 10, n2))
+    ag[:, :af.shape[1]] = af                       # a1..a2 (SH) / a1..a6 (P-SV); a3 / a7..a10 = 0
+    d, v = _rand_fields(o, seed=7)
+    o.set_fields(d, v)
+    ref = o.compute_fint()
+    e = _engine_from(o, ag, ag.shape[1], False, VARIANTS[variant])
+    e.set_fields(d, v)
+    assert rel_l2(e.compute_fint(), ref) <= 1e-13
+    e.close()
+    o.close()
+
+
+@pytest.mark.parametrize("ndof", [1, 2])
+def test_general_planes_give_a_symmetric_operator(ndof):
+    """with arbitrary cross planes (a3 / a7..a10 != 0) no oracle exists (the oracle meshes are flat), but the
+    operator of MAT_ELAST_f stays symmetric: <w, K u> = <u, K w>"""
+    o = orc.Oracle(harness.cart_deck(9, 7, ngll=5, ndof=ndof, nrec=0, src=False), synthetic_seed=20261017)
+    n2, nset = 25, o.i("ncoefsets")
+    rng = np.random.default_rng(3)
+    ag = rng.standard_normal((nset, 3 if ndof == 1 else 10, n2))
+    e = _engine_from(o, ag, ag.shape[1], False)
+    n = o.i("npoin") * ndof
+    u, w = rng.standard_normal(n), rng.standard_normal(n)
+    e.set_fields(u, np.zeros(n))
+    Ku = e.compute_fint()
+    e.set_fields(w, np.zeros(n))
+    Kw = e.compute_fint()
+    a, b = float(w @ Ku), float(u @ Kw)
+    assert abs(a - b) <= 1e-12 * max(abs(a), abs(b)), (a, b)
+    e.close()
+    o.close()
+
+
+def test_nonflat_absorbing_form_on_axis_aligned_sides():
+    """BC_ABSO_apply's normal / tangential form (bc_abso.f90:311-317) on boundaries whose normals are the axes
+    must reproduce the flat form: Lamb's deck stepped with is_flat = 0"""
+    o = orc.Oracle(harness.deck("lamb"))
+    e = _engine_from(o, o.arr("a"), o.i("nelast"), False, abso_flat=False)
+    nsteps = 400
+    tab = np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)])
+    e.step(nsteps, tab)
+    o.step(nsteps)
+    d, v, _ = e.get_fields()
+    assert rel_l2(d, o.arr("d")) <= 1e-10 and rel_l2(v, o.arr("v")) <= 1e-10
+    assert np.abs(d).max() > 0
+    e.close()
+    o.close()
