@@ -297,3 +297,58 @@ def test_nonflat_absorbing_form_on_axis_aligned_sides():
     assert np.abs(d).max() > 0
     e.close()
     o.close()
+
+
+def _fault_run(deck, nsteps, tol=1e-10, skip_tstick=False):
+    o = orc.Oracle(deck)
+    r = Rig(o)
+    _lockstep(o, r, nsteps, 97, tol, skip_tstick=skip_tstick)
+    slip = np.abs(o.arr("bc.0.D")).max()
+    r.close()
+    return slip
+
+
+@pytest.mark.parametrize("edit", [
+    ("Dc=0.4d0,", "kind=2, Dc=0.4d0,"),                                  # exponential weakening (bc_dynflt_swf.f90:160-163)
+    ("Dc=0.4d0,", "kind=3, p=2.5d0, Dc=0.4d0,"),                         # power law (:164-167)
+    ("Dc=0.4d0,", "healing=T, Dc=0.4d0,"),                               # state heals with the slip rate (:178-190)
+    ("Dc=0.4d0,", "alpha=0.02d0, Dc=0.4d0,"),                            # + alpha*theta
+])
+def test_slip_weakening_variants(edit):
+    """the TPV3 deck (one-sided fault, Kelvin-Voigt layer, Newmark) with every slip-weakening option"""
+    deck = harness.deck("tpv3").replace(*edit)
+    assert deck != harness.deck("tpv3")
+    assert _fault_run(deck, 700) > 1e-2
+
+
+@pytest.mark.parametrize("nor", ["kind=0", "kind=2, T=0.05d0", "kind=3, L=0.2d0, V=1d0"])
+def test_normal_stress_laws(nor):
+    """normal_update / normal_getSigma kinds 0, 2, 3 (bc_dynflt_normal.f90:118-147); kind 1 is the default of
+    every other fault test.  A P-SV two-sided fault in a heterogeneous medium so that the normal stress varies."""
+    deck = harness.cart_deck(24, 16, ezflt=8, scheme="newmark", nsteps=400)
+    deck = deck.replace("&BC_DYNFLT_SWF Dc=0.4d0, MuS=0.677d0, MuD=0.525d0 /",
+                        f"&BC_DYNFLT_SWF Dc=0.4d0, MuS=0.677d0, MuD=0.525d0 /\n&BC_DYNFLT_NOR {nor} /")
+    o = orc.Oracle(deck, synthetic_seed=20261017)
+    r = Rig(o)
+    _lockstep(o, r, 400, 97, 1e-10)
+    assert np.abs(o.arr("bc.0.D")).max() > 1e-3
+    r.close()
+
+
+@pytest.mark.parametrize("kind", [1, 2, 4])
+def test_rate_and_state_kinds(kind):
+    """rsf kinds 1 (strong velocity weakening, closed form), 2 (aging law), 4 (V-shape) on the RateState deck
+    (kind 3, the slip law, is the deck's own: test_ratestate_run); T_stick is undefined for RSF"""
+    deck = harness.deck("ratestate").replace("kind=3,", f"kind={kind},")
+    assert f"kind={kind}," in deck
+    _fault_run(deck, 400, tol=1e-9, skip_tstick=True)
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3])
+def test_time_weakening_nucleation(kind):
+    """friction = 'SWF','TWF': mu = min(mu_swf, mu_twf(t)) with the prescribed front of bc_dynflt_twf.f90:117-184"""
+    deck = harness.deck("tpv3").replace("friction='SWF',", "friction='SWF','TWF',")
+    deck = deck.replace("&BC_DYNFLT_SWF ", f"&BC_DYNFLT_TWF kind={kind}, MuS=0.677d0, MuD=0.525d0, Mu0=0.6d0, X=0d0, Z=0d0, "
+                                           "V=2d3, L=1d3, T=2d0 /\n&BC_DYNFLT_SWF ")
+    assert "BC_DYNFLT_TWF" in deck
+    assert _fault_run(deck, 700) > 1e-2
