@@ -352,3 +352,36 @@ def test_time_weakening_nucleation(kind):
                                            "V=2d3, L=1d3, T=2d0 /\n&BC_DYNFLT_SWF ")
     assert "BC_DYNFLT_TWF" in deck
     assert _fault_run(deck, 700) > 1e-2
+
+
+def test_time_dependent_neumann_traction_equals_point_forces():
+    """bc_DIRNEU_apply with a source time function (bc_dirneu.f90:160-167: f += stf(t)*B on the boundary
+    nodes) has no oracle counterpart; it must equal the same load applied as collocated forces"""
+    o = orc.Oracle(harness.deck("lamb"))
+    top = [i for i in range(o.i("nbnd")) if o.i(f"bnd.{i}.tag") == 3][0]
+    nodes = o.arr(f"bnd.{top}.node")
+    rng = np.random.default_rng(2)
+    Bv = rng.uniform(0.5, 1.5, nodes.size)
+    Bh = rng.uniform(-0.3, 0.3, nodes.size)
+    nsteps = 300
+    amp = np.array([o.stf(0, (k + 1) * o.f("dt")) for k in range(nsteps)])
+    out = []
+    for mode in ("neumann", "forces"):
+        from sem2dpack_b200 import Engine
+        e = Engine(o.i("ngll"), 2, o.arr("ibool"), o.arr("H"), o.arr("rmass"), 0, o.f("dt"))
+        e.set_elastic(o.i("nelast"), o.arr("a"), o.arr("elem2set"), False)
+        if mode == "neumann":
+            e.add_dirneu(nodes, 1, 1, B_h=Bh, B_v=Bv)
+            e.commit()
+            e.step(nsteps, None, np.stack([0.5 * amp, amp], axis=1))       # (nsteps, 2): h and v amplitudes
+        else:
+            for k, nd in enumerate(nodes):
+                e.add_force(int(nd), [0.5 * Bh[k], Bv[k]])
+            e.commit()
+            e.step(nsteps, np.repeat(amp[:, None], nodes.size, axis=1))
+        out.append(e.get_fields())
+        e.close()
+    for x, y in zip(*out):
+        assert np.abs(x).max() > 0
+        assert rel_l2(x, y) <= 1e-13
+    o.close()
