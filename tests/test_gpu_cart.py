@@ -237,3 +237,30 @@ def test_fused_step_decompositions(ngll, ndof, nx, nz, ezflt, seg, scheme, monke
     assert np.abs(d).max() > 0
     e.close()
     o.close()
+
+
+@pytest.mark.parametrize("field", ["A", "D"])
+@pytest.mark.parametrize("scheme", ["leapfrog", "newmark"])
+def test_fused_step_receiver_fields(field, scheme):
+    """stations that record accelerations force the fused step to materialise them on every step (they are
+    otherwise written on the last step of a call only); displacement stations read the buffer that holds
+    d[n] after the two displacement buffers have swapped"""
+    nx, nz, nsteps, h = 24, 16, 120, 100.0
+    deck = harness.cart_deck(nx, nz, ezflt=8, scheme=scheme, nsteps=nsteps).replace("field='V'", f"field='{field}'")
+    o = orc.Oracle(deck, synthetic_seed=SEED, renumber=False)
+    e = CartEngine(5, 2, nx, nz, (0.0, nx * h), (0.0, nz * h), ezflt=8, seed=SEED,
+                   scheme_kind=0 if scheme == "leapfrog" else 1, courant=0.5)
+    e.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, nx * h / 2, harness.nuc_radius(nx, h), nt_max=nsteps)
+    for side in (1, 2, 3, 4):
+        e.add_abso_side(side, False)
+    e.add_force_at(0.37 * nx * h, 0.61 * nz * h, [o.f("src.0.dir1"), o.f("src.0.dir2")])
+    e.add_receiver_line(8, (0.1 * nx * h, 0.3 * nz * h), (0.9 * nx * h, 0.8 * nz * h), field, 1, nsteps + 1)
+    e.commit()
+    tab = np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)])
+    e.step(nsteps, tab)
+    o.step(nsteps)
+    s_ref, s_got = o.seis(), e.seis()
+    assert np.abs(s_ref).max() > 0
+    assert np.abs(s_got - s_ref).max() <= 2e-7 * np.abs(s_ref).max()
+    e.close()
+    o.close()
