@@ -316,7 +316,8 @@ def main():
     except Exception:
         pass
     # --- end to end through the public API with host buffers: one s2d_step per step with that
-    # step's stf row (H2D) and a read-back of the step's seismogram row (D2H)
+    # step's stf row (H2D, through the engine's pinned staging buffer) and a read-back of the step's
+    # seismogram row (D2H, likewise)
     it0 = e.it
     n_e2e = max(5, min(K, 20))
     barrier()

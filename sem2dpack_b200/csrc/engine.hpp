@@ -150,6 +150,23 @@ class Engine : public EngineBase {
   DevBuf<T> d_alpha, v_alpha;
   int nstages() const { return scheme.kind == 3 ? scheme.nstages : 1; }
   size_t src_ampli_cap = 0, bc_ampli_cap = 0;
+  // pinned host staging of the per-call inputs / outputs (the caller's buffers are ordinary host memory)
+  struct Pinned {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void* need(size_t n) {
+      if (n > bytes) {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        if (cudaMallocHost(&p, n) != cudaSuccess) throw StateError("cudaMallocHost failed");
+        bytes = n;
+      }
+      return p;
+    }
+    ~Pinned() {
+      if (p) cudaFreeHost(p);
+    }
+  } pin_src, pin_bc, pin_row;
   Receivers rec;
   // control
   DevBuf<StepCtl> ctl;
@@ -1278,7 +1295,9 @@ class Engine : public EngineBase {
         src_ampli.alloc(need);
         src_ampli_cap = need;
       }
-      S2D_CUDA(cudaMemcpyAsync(src_ampli.p, srca, need * sizeof(double), cudaMemcpyHostToDevice, stream));
+      S2D_CUDA(cudaStreamSynchronize(stream));  // the staging buffer of the previous call is free again
+      std::memcpy(pin_src.need(need * sizeof(double)), srca, need * sizeof(double));
+      S2D_CUDA(cudaMemcpyAsync(src_ampli.p, pin_src.p, need * sizeof(double), cudaMemcpyHostToDevice, stream));
     }
     bool any_stf = false;
     for (auto& b : dirneu) any_stf = any_stf || b->B_h.p || b->B_v.p;
@@ -1290,7 +1309,9 @@ class Engine : public EngineBase {
         bc_ampli.alloc(need);
         bc_ampli_cap = need;
       }
-      S2D_CUDA(cudaMemcpyAsync(bc_ampli.p, bca, need * sizeof(double), cudaMemcpyHostToDevice, stream));
+      S2D_CUDA(cudaStreamSynchronize(stream));
+      std::memcpy(pin_bc.need(need * sizeof(double)), bca, need * sizeof(double));
+      S2D_CUDA(cudaMemcpyAsync(bc_ampli.p, pin_bc.p, need * sizeof(double), cudaMemcpyHostToDevice, stream));
     }
     const int it0 = it + 1;
     S2D_CUDA(cudaMemcpyAsync(&ctl.p->it0, &it0, sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -1373,9 +1394,12 @@ class Engine : public EngineBase {
     S2D_REQUIRE(rec.present, "get_seis_row: no receivers");
     S2D_REQUIRE(it_ >= 0 && it_ % rec.dev.isamp == 0 && it_ / rec.dev.isamp < rec.dev.nt, "get_seis_row: step not sampled");
     const size_t r = (size_t)(it_ / rec.dev.isamp);
-    S2D_CUDA(cudaMemcpy2DAsync(row, sizeof(float), rec.sis.p + r, (size_t)rec.dev.nt * sizeof(float), sizeof(float),
-                               (size_t)rec.dev.nx * ndof, cudaMemcpyDeviceToHost, stream));
+    const size_t nrow = (size_t)rec.dev.nx * ndof;
+    float* stage = (float*)pin_row.need(nrow * sizeof(float));
+    S2D_CUDA(cudaMemcpy2DAsync(stage, sizeof(float), rec.sis.p + r, (size_t)rec.dev.nt * sizeof(float), sizeof(float),
+                               nrow, cudaMemcpyDeviceToHost, stream));
     S2D_CUDA(cudaStreamSynchronize(stream));
+    std::memcpy(row, stage, nrow * sizeof(float));
   }
   void get_fault(int id, float* records, int32_t* nout, double* potency, int32_t* ncalls) override {
     S2D_REQUIRE(id >= 0 && id < (int)faults.size(), "get_fault: bad fault id");
