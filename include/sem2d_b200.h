@@ -293,6 +293,16 @@ int s2d_cart_info(s2d_handle h, int64_t* npoin, int64_t* nelem, double* dt);
  * must agree on dt: the host takes the minimum of the per-strip Courant steps (the reference takes
  * the maximum of c/dx over the whole grid, init.f90:187-225) and sets it on every strip. */
 int s2d_cart_set_dt(s2d_handle h, double dt);
+/* Seeded non-trivial state for measurements and windowed parity checks (no reference counterpart: the
+ * reference starts from rest or from a restart file): displ = amp_d*u, veloc = amp_v*u', accel = 0, with
+ * u, u' in U(-1,1) from the same counter-based hash as the synthetic medium, keyed by the node's global
+ * lattice coordinates (partition-independent; the two sides of a split fault row get equal values). */
+int s2d_cart_fill_fields(s2d_handle h, uint64_t seed, double amp_d, double amp_v);
+/* A rectangular window of the GLL lattice (columns gx0..gx0+nwx-1, rows gz0..gz0+nwz-1; a split fault row is
+ * two lattice rows, lower side first): out[c][row][col] in FP64.  What fields%displ/veloc/accel hold there,
+ * without moving the whole (npoin,ndof) arrays of s2d_get_fields.  Any pointer may be NULL. */
+int s2d_cart_get_window(s2d_handle h, int32_t gx0, int32_t gz0, int32_t nwx, int32_t nwz, double* displ,
+                        double* veloc, double* accel);
 /* copies of builder outputs for parity tests against the oracle (host pointers, may be NULL) */
 int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double* coord);
 

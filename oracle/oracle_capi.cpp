@@ -29,8 +29,8 @@ extern "C" {
 
 // Build a problem from the text of a Par.inp.  synthetic_seed != 0 replaces every material by the
 // hash-defined heterogeneous model of the synthetic benchmark config.
-void* orc_create(const char* parinp_text, unsigned long long synthetic_seed, int renumber, int kd_force_kd1,
-                 char* err, int errlen) {
+void* orc_create_at(const char* parinp_text, unsigned long long synthetic_seed, int renumber, int kd_force_kd1,
+                    long long ix0, long long iz0, char* err, int errlen) {
   try {
     OrcHandle* h = new OrcHandle();
     ParInp in = ParInp::from_string(parinp_text);
@@ -43,6 +43,8 @@ void* orc_create(const char* parinp_text, unsigned long long synthetic_seed, int
         mi.seed = synthetic_seed;
         mi.homogeneous = false;
         mi.has_lambda = false;
+        mi.ix0 = ix0;
+        mi.iz0 = iz0;
       }
     }
     init_main(h->pb, h->cart);
@@ -51,6 +53,11 @@ void* orc_create(const char* parinp_text, unsigned long long synthetic_seed, int
     set_err(err, errlen, e.what());
     return nullptr;
   }
+}
+
+void* orc_create(const char* parinp_text, unsigned long long synthetic_seed, int renumber, int kd_force_kd1,
+                 char* err, int errlen) {
+  return orc_create_at(parinp_text, synthetic_seed, renumber, kd_force_kd1, 0, 0, err, errlen);
 }
 
 void orc_destroy(void* hv) { delete (OrcHandle*)hv; }
@@ -296,6 +303,7 @@ long long orc_array(void* hv, const char* name_, const void** ptr, char* dtype) 
   if (n == "kv_elem") RET_I(pb.kv_elem);
   if (n == "kv_eta") RET_D(pb.kv_eta);
   if (n == "rmass") RET_D(pb.rmass);
+  if (n == "mass") RET_D(pb.mass);
   if (n == "d") RET_D(pb.d);
   if (n == "v") RET_D(pb.v);
   if (n == "acc") RET_D(pb.a_);

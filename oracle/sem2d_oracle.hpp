@@ -679,6 +679,7 @@ struct MatInput {  // matpro_input_type (prop_mat.f90:21-25) for ELAST (+KV)
   bool etaxdt = true;
   bool synthetic = false;  // hash-based heterogeneous model (not in the reference)
   uint64_t seed = 0;
+  int64_t ix0 = 0, iz0 = 0;  // lattice origin of this mesh inside a larger synthetic mesh (window tests)
 };
 
 struct ElemProp {  // prop_elem_type (prop_elem.f90:10-14): homogeneous scalar or ngll x ngll values
@@ -869,6 +870,7 @@ struct Problem {  // problem_type (problem_class.f90:19-46)
   std::vector<int> elem2kv;       // (nelem) 0 or 1-based index into kv list
   std::vector<double> kv_eta;     // (ngll,ngll,nkv) already multiplied by dt if ETAxDT
   std::vector<double> rmass;      // (npoin,ndof) -- mass until init end, then inverse
+  std::vector<double> mass;       // (npoin) assembled mass as MAT_MASS_init leaves it (mat_mass.f90:50-57), before BC_init
   std::vector<double> d, v, a_;   // fields (npoin,ndof) col-major
   std::vector<Bc> bc;
   const BcPerio* perio = nullptr;  // the periodic boundary the other BC_*_init routines receive (bc_gen.f90:221-246)
@@ -925,7 +927,7 @@ inline void MAT_init_prop(Problem& pb, int N_for_lattice /*ngll*/) {
       int ie = (eold - 1) % g.nx, je = (eold - 1) / g.nx;
       for (int j = 0; j < n; ++j)
         for (int i = 0; i < n; ++i) {
-          uint64_t ix = (uint64_t)ie * (N_for_lattice - 1) + i, iz = (uint64_t)je * (N_for_lattice - 1) + j;
+          uint64_t ix = (uint64_t)(in.ix0 + (int64_t)ie * (N_for_lattice - 1) + i), iz = (uint64_t)(in.iz0 + (int64_t)je * (N_for_lattice - 1) + j);
           double u1 = hash_u(in.seed, ix, iz, 1), u2 = hash_u(in.seed, ix, iz, 2), u3 = hash_u(in.seed, ix, iz, 3);
           double csv = 3464.0 * (1.0 + 0.10 * u1);
           double cpv = 1.7321 * csv * (1.0 + 0.02 * u2);
@@ -2305,6 +2307,7 @@ inline void init_main(Problem& pb, const CartSpec& cart) {
   pb.v.assign(nn, 0.0);
   pb.a_.assign(nn, 0.0);
   MAT_MASS_init(pb);
+  pb.mass.assign(pb.rmass.begin(), pb.rmass.begin() + g.npoin);
   BC_init(pb);
   REC_init(pb);
   for (auto& s : pb.src) {  // SO_init (src_gen.f90:216-260)

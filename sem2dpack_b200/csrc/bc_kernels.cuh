@@ -70,20 +70,24 @@ __global__ void k_invert(T* x, size_t n) {
 }
 
 // ------------------------------------------------------------------------------------------
-// point forces: f(iglob,:) += dir*ampli(it)
+// SO_add (src_gen.f90:290-317): point forces f(iglob,:) += dir*ampli (src_force.f90:77-90) and the terms of
+// SRC_MOMENT_add (src_moment.f90:183-197).  The reference adds the sources one after the other; here every
+// target node is owned by ONE thread that walks the terms landing on it in that same order (CSR built at
+// commit), so sources that share a node neither race nor change the order of the additions.
 template <typename T>
-__global__ void k_sources(T* f, size_t npoin, int ndof, int nsrc, const int* iglob,
-                          const double* dir /*(2,nsrc)*/, const double* ampli /*[steps*nstages][nsrc]*/,
-                          const StepCtl* ctl, int stage, int nstages) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nsrc || iglob[s] <= 0) return;  // 0: a moment source (k_moments)
-  const double amp = ampli[(size_t)(((ctl->it - ctl->it0) * nstages + stage) % ctl->nrows) * nsrc + s];
-  const size_t node = (size_t)(iglob[s] - 1);
-  if (ndof == 1) {
-    f[node] = (T)((double)f[node] + amp);  // src_force.f90:84
-  } else {
-    f[node] = (T)((double)f[node] + dir[2 * s] * amp);
-    f[node + npoin] = (T)((double)f[node + npoin] + dir[2 * s + 1] * amp);
+__global__ void k_sources(T* f, size_t npoin, int ndof, int nnodes, const int* __restrict__ tnode,
+                          const int* __restrict__ tstart, const int* __restrict__ tsrc,
+                          const double* __restrict__ tcoef /*(nterms,ndof)*/, int nterms, int nsrc,
+                          const double* __restrict__ ampli /*[steps*nstages][nsrc]*/, const StepCtl* ctl, int stage,
+                          int nstages) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnodes) return;
+  const double* row = ampli + (size_t)(((ctl->it - ctl->it0) * nstages + stage) % ctl->nrows) * nsrc;
+  const size_t node = (size_t)(tnode[k] - 1);
+  for (int c = 0; c < ndof; ++c) {
+    double acc = (double)f[node + npoin * c];
+    for (int t = tstart[k]; t < tstart[k + 1]; ++t) acc = (double)(T)(acc + row[tsrc[t]] * tcoef[t + (size_t)nterms * c]);
+    f[node + npoin * c] = (T)acc;
   }
 }
 
@@ -97,22 +101,6 @@ __global__ void k_periodic(T* f, size_t npoin, int ndof, int np, const int* mast
     const T sum = f[m] + f[s];
     f[m] = sum;
     f[s] = sum;
-  }
-}
-
-// moment-tensor sources (SRC_MOMENT_add, src_moment.f90:183-197): one thread per source walks its
-// terms in the reference's order (a node can appear in several terms)
-template <typename T>
-__global__ void k_moments(T* f, size_t npoin, int ndof, int nmom, const int* src_id, const int* start,
-                          const int* node, const double* coef, int nsrc, const double* ampli, const StepCtl* ctl,
-                          int stage, int nstages) {
-  int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= nmom) return;
-  const double amp = ampli[(size_t)(((ctl->it - ctl->it0) * nstages + stage) % ctl->nrows) * nsrc + src_id[m]];
-  const int t0 = start[m], nt = start[m + 1] - t0;
-  for (int t = 0; t < nt; ++t) {
-    const size_t q = (size_t)(node[t0 + t] - 1);
-    for (int c = 0; c < ndof; ++c) f[q + npoin * c] = (T)((double)f[q + npoin * c] + amp * coef[t0 + t + (size_t)nt * c]);
   }
 }
 
@@ -616,7 +604,7 @@ __global__ void __launch_bounds__(DYNW_THREADS) k_dynflt_write(FaultDev F, const
         p[2] = 0.5 * tot[2]; p[3] = 0.5 * tot[3];
       }
     }
-    F.ostate[2] = ncall + 1;
+    F.ostate[2] = min(ncall + 1, F.ncall_max);  // calls beyond nt_max are not recorded (get_fault copies ostate[2] rows)
     if (ctl->it >= oit) {
       F.ostate[0] = oit + F.oitd;
       F.ostate[1] = nout + (out ? 1 : 0);

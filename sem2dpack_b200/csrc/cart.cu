@@ -118,7 +118,7 @@ __host__ __device__ inline long long cart_node_id(const CartGeom& G, int ix, int
 // Internal (device) numbering: the GLL lattice, row-major, the split fault row stored twice.
 // 1-based like every node id that crosses the engine's add_* calls.  (i,j) 0-based here.
 __host__ __device__ inline long long cart_lat_id(const CartGeom& G, int ix, int iz, int i, int j) {
-  return (long long)strip_lat_row(G.S, iz, j) * G.S.LX + (long long)ix * (G.N - 1) + i + 1;
+  return (long long)strip_lat_row(G.S, iz, j) * G.S.LXP + (long long)ix * (G.N - 1) + i + 1;
 }
 
 // material at GLL point (i,j) (0-based) of element (ix,iz)
@@ -265,6 +265,48 @@ __global__ void k_gather_nodes(const T* src, size_t npoin, int ndof, int np, con
   for (int c = 0; c < ndof; ++c) out[k + (size_t)np * c] = (double)src[(size_t)(node[k] - 1) + npoin * c];
 }
 
+template <typename T>
+__global__ void k_fill(T* x, size_t n, T val) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) x[q] = val;
+}
+template <typename TS, typename TD>
+__global__ void k_cast_copy(const TS* __restrict__ src, TD* __restrict__ dst, size_t n) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) dst[q] = (TD)src[q];
+}
+
+// Seeded, non-trivial initial state: d = amp_d * u, v = amp_v * u' with u, u' in U(-1,1) from the counter-based
+// hash of the node's GLOBAL geometric lattice coordinates (both sides of the split fault row get the same
+// values: no initial slip; x-strips of one global mesh agree on their shared columns).
+template <typename T>
+__global__ void k_cart_fill(CartGeom G, T* __restrict__ d, T* __restrict__ v, size_t nlat, uint64_t seed,
+                            double amp_d, double amp_v) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)G.S.LX * G.S.LZ;
+  if (w >= total) return;
+  const int gz = (int)(w / G.S.LX), gx = (int)(w - (long long)gz * G.S.LX);
+  const int gzg = gz - ((G.ezflt > 0 && gz >= G.ezflt * (G.N - 1) + 1) ? 1 : 0);
+  const uint64_t X = (uint64_t)(G.ix0 + gx), Z = (uint64_t)(G.iz0 + gzg);
+  const size_t q = (size_t)gz * G.S.LXP + gx;
+  for (int c = 0; c < G.ndof; ++c) {
+    d[q + nlat * c] = (T)(amp_d * hash_u(seed, X, Z, 16 + c));
+    v[q + nlat * c] = (T)(amp_v * hash_u(seed, X, Z, 32 + c));
+  }
+}
+// a window of the lattice, out[c][gz - gz0][gx - gx0] in FP64
+template <typename T>
+__global__ void k_cart_window(const T* __restrict__ src, double* __restrict__ out, size_t nlat, int LXP, int ndof,
+                              int gx0, int gz0, int nwx, int nwz) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)nwx * nwz * ndof;
+  if (w >= total) return;
+  const int c = (int)(w / ((long long)nwx * nwz));
+  const long long r = w - (long long)c * nwx * nwz;
+  const int z = (int)(r / nwx), x = (int)(r - (long long)z * nwx);
+  out[w] = (double)src[(size_t)(gz0 + z) * LXP + (gx0 + x) + nlat * c];
+}
+
 // ibool in the reference layout (ngll,ngll,nelem), natural element order
 __global__ void k_cart_ibool(CartGeom G, int* __restrict__ ibool) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,8 +322,8 @@ __global__ void k_cart_ibool(CartGeom G, int* __restrict__ ibool) {
 // to_ref != 0: ref[id] = lat[lattice];  else lat[lattice] = ref[id].  Nodes shared by several
 // elements are written several times with the same value.
 template <typename TS, typename TD>
-__global__ void k_cart_permute(CartGeom G, const TS* __restrict__ src, TD* __restrict__ dst, size_t npoin,
-                               int ncomp, int to_ref) {
+__global__ void k_cart_permute(CartGeom G, const TS* __restrict__ src, TD* __restrict__ dst, size_t np_ref,
+                               size_t np_lat, int ncomp, int to_ref) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int N = G.N, N2 = N * N;
   const long long total = (long long)G.nx * G.nz * N2;
@@ -293,8 +335,8 @@ __global__ void k_cart_permute(CartGeom G, const TS* __restrict__ src, TD* __res
   const size_t r = (size_t)(cart_node_id(G, ix, iz, i + 1, j + 1) - 1);
   const size_t l = (size_t)(cart_lat_id(G, ix, iz, i, j) - 1);
   for (int c = 0; c < ncomp; ++c) {
-    if (to_ref) dst[r + npoin * c] = (TD)src[l + npoin * c];
-    else dst[l + npoin * c] = (TD)src[r + npoin * c];
+    if (to_ref) dst[r + np_ref * c] = (TD)src[l + np_lat * c];
+    else dst[l + np_lat * c] = (TD)src[r + np_ref * c];
   }
 }
 
@@ -405,7 +447,9 @@ static void cart_build(Engine<T>& E, CartState& S) {
   E.cart_wgll.assign(G.wgll, G.wgll + N);
   E.p_coef.alloc((size_t)E.nelem * (E.cart_compact ? 2 : nelast) * N2);
   k_cart_coef<T><<<nblk, 256, 0, st>>>(G, E.p_coef.p, nelast, E.cart_compact);
-  // mass (kept un-inverted in rmass until commit)
+  // mass (kept un-inverted in rmass until commit); the pad columns of the lattice rows get 1 so that 1/M and
+  // every node-wise pass stay finite there (their fields are zero and nothing ever reads them)
+  k_fill<T><<<(unsigned)std::min<size_t>((E.rmass.n + 255) / 256, 148 * 32), 256, 0, st>>>(E.rmass.p, E.rmass.n, (T)1);
   k_cart_mass<T><<<nblk, 256, 0, st>>>(G, E.rmass.p, E.npoin);
   S2D_CUDA(cudaGetLastError());
   // halo arrays of the strip kernel
@@ -431,17 +475,26 @@ static void cart_build(Engine<T>& E, CartState& S) {
   const CartGeom Gc = G;
   Engine<T>* Ep = &E;
   E.cart_to_ref = [Ep, Gc, nblk](const T* lat, double* ref) {
-    k_cart_permute<T, double><<<nblk, 256, 0, Ep->stream>>>(Gc, lat, ref, Ep->npoin, Gc.ndof, 1);
+    k_cart_permute<T, double><<<nblk, 256, 0, Ep->stream>>>(Gc, lat, ref, Ep->npoin_ref, Ep->npoin, Gc.ndof, 1);
     S2D_CUDA(cudaGetLastError());
   };
   E.cart_from_ref = [Ep, Gc, nblk](const double* ref, T* lat) {
-    k_cart_permute<double, T><<<nblk, 256, 0, Ep->stream>>>(Gc, ref, lat, Ep->npoin, Gc.ndof, 0);
+    k_cart_permute<double, T><<<nblk, 256, 0, Ep->stream>>>(Gc, ref, lat, Ep->npoin_ref, Ep->npoin, Gc.ndof, 0);
     S2D_CUDA(cudaGetLastError());
   };
   E.cart_from_ref1 = [Ep, Gc, nblk](const double* ref, T* lat) {
-    k_cart_permute<double, T><<<nblk, 256, 0, Ep->stream>>>(Gc, ref, lat, Ep->npoin, 1, 0);
+    k_cart_permute<double, T><<<nblk, 256, 0, Ep->stream>>>(Gc, ref, lat, Ep->npoin_ref, Ep->npoin, 1, 0);
     S2D_CUDA(cudaGetLastError());
   };
+  E.cart_from_ref1d = [Ep, Gc, nblk](const double* ref, double* lat) {
+    k_cart_permute<double, double><<<nblk, 256, 0, Ep->stream>>>(Gc, ref, lat, Ep->npoin_ref, Ep->npoin, 1, 0);
+    S2D_CUDA(cudaGetLastError());
+  };
+  // the assembled mass as MAT_MASS_init leaves it (mat_mass.f90:50-57), before BC_init augments it: what
+  // energy_compute's sum(w*rho*v2) (energy.f90:49-106) amounts to node by node
+  E.mass.alloc(E.npoin);
+  k_cast_copy<T, double><<<(unsigned)((E.npoin + 255) / 256), 256, 0, st>>>(E.rmass.p, E.mass.p, E.npoin);
+  S2D_CUDA(cudaGetLastError());
   S2D_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -548,6 +601,7 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
       Q.nseg_lo = G.ezflt > 0 ? (G.ezflt + Q.SEG - 1) / Q.SEG : 0;
       Q.nseg = Q.nseg_lo + (G.nz - G.ezflt + Q.SEG - 1) / Q.SEG;
       Q.LX = G.nx * (G.N - 1) + 1;
+      Q.LXP = (Q.LX + 1 + 7) / 8 * 8;  // rows start on 32-byte sectors (FP32: 8 elements), one spare column for 16-byte bulk copies
       Q.LZ = G.nz * (G.N - 1) + 1 + (G.ezflt > 0 ? 1 : 0);
       Q.xhalo_left = G.halo_left ? 1 : 0;
       Q.xhalo_right = G.halo_right ? 1 : 0;
@@ -564,7 +618,8 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
       g_cart_err = "internal error: lattice size does not match the node count";
       return S2D_EINVAL;
     }
-    if (npoin > 2147483647LL || nelem * G.N * G.N > (1LL << 40)) {
+    const long long nlat = (long long)G.S.LXP * G.S.LZ;  // device node count: lattice rows of pitch LXP
+    if (nlat > 2147483647LL || nelem * G.N * G.N > (1LL << 40)) {
       g_cart_err = "mesh too large for 32-bit node ids";
       return S2D_EINVAL;
     }
@@ -588,11 +643,11 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
     S->dt = S->scheme.dt;
     std::unique_ptr<EngineBase> impl;
     if (D->precision == 8) {
-      auto* E = new Engine<double>(Engine<double>::Raw(), G.N, G.ndof, (int)nelem, (size_t)npoin, S->H, S->scheme, dev);
+      auto* E = new Engine<double>(Engine<double>::Raw(), G.N, G.ndof, (int)nelem, (size_t)nlat, (size_t)npoin, S->H, S->scheme, dev);
       impl.reset(E);
       cart_build<double>(*E, *S);
     } else {
-      auto* E = new Engine<float>(Engine<float>::Raw(), G.N, G.ndof, (int)nelem, (size_t)npoin, S->H, S->scheme, dev);
+      auto* E = new Engine<float>(Engine<float>::Raw(), G.N, G.ndof, (int)nelem, (size_t)nlat, (size_t)npoin, S->H, S->scheme, dev);
       impl.reset(E);
       cart_build<float>(*E, *S);
     }
@@ -607,7 +662,7 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
 
 int s2d_cart_info(s2d_handle h, int64_t* npoin, int64_t* nelem, double* dt) {
   CART_GUARD_BEGIN
-  if (npoin) *npoin = (int64_t)Eb->npoin;
+  if (npoin) *npoin = (int64_t)Eb->npoin_ref;
   if (nelem) *nelem = (int64_t)Eb->nelem;
   if (dt) *dt = S.dt;
   CART_GUARD_END
@@ -714,18 +769,18 @@ int s2d_cart_add_periodic(s2d_handle h, int32_t master_tag, int32_t slave_tag) {
   const bool bt = (master_tag == 1 && slave_tag == 3) || (master_tag == 3 && slave_tag == 1);
   S2D_REQUIRE(lr || bt, "cart_add_periodic: tags must be two opposite sides of the box");
   S2D_REQUIRE(!(lr && (G.halo_left || G.halo_right)), "cart_add_periodic: not available across x-strips");
-  const int LX = G.S.LX, LZ = G.S.LZ;
+  const int LX = G.S.LX, LZ = G.S.LZ, LXP = G.S.LXP;
   const int np = lr ? LZ : LX;
   std::vector<int> m(np), sl(np);
   for (int k = 0; k < np; ++k) {
     int a, b;  // lattice ids (1-based) of the pair, in the order of the sorted boundary node lists
     if (lr) {
-      a = k * LX + 1;            // tag 4, left
-      b = k * LX + LX;           // tag 2, right
+      a = k * LXP + 1;           // tag 4, left
+      b = k * LXP + LX;          // tag 2, right
       if (master_tag == 2) std::swap(a, b);
     } else {
-      a = k + 1;                 // tag 1, bottom
-      b = (LZ - 1) * LX + k + 1; // tag 3, top
+      a = k + 1;                  // tag 1, bottom
+      b = (LZ - 1) * LXP + k + 1; // tag 3, top
       if (master_tag == 3) std::swap(a, b);
     }
     m[k] = a;
@@ -939,12 +994,12 @@ int s2d_cart_add_dirneu(s2d_handle h, int32_t side, int32_t kind_h, int32_t kind
   S2D_REQUIRE(!(side == 4 && G.halo_left) && !(side == 2 && G.halo_right),
               "cart_add_dirneu: that side is a strip interface, not a physical boundary");
   S.bc_added = true;
-  const int LX = G.S.LX, LZ = G.S.LZ;
+  const int LX = G.S.LX, LZ = G.S.LZ, LXP = G.S.LXP;
   const bool horiz = (side == 1 || side == 3);
   const int np = horiz ? LX : LZ;
   std::vector<int> node(np);
   for (int k = 0; k < np; ++k)
-    node[k] = side == 1 ? k + 1 : side == 3 ? (LZ - 1) * LX + k + 1 : side == 4 ? k * LX + 1 : k * LX + LX;
+    node[k] = side == 1 ? k + 1 : side == 3 ? (LZ - 1) * LXP + k + 1 : side == 4 ? k * LXP + 1 : k * LXP + LX;
   Eb->add_dirneu(np, node.data(), kind_h, kind_v, nullptr, nullptr);
   CART_GUARD_END
 }
@@ -1179,14 +1234,14 @@ int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double*
       }
   }
   if (rmass) {
-    const size_t nd = Eb->npoin * G.ndof;
+    const size_t nd = Eb->npoin_ref * G.ndof;
     DevBuf<double> tmp;
     tmp.alloc(nd);
     const unsigned nblk = (unsigned)((tot + 255) / 256);
     if (Eb->prec == 8)
-      k_cart_permute<double, double><<<nblk, 256, 0, Eb->stream>>>(G, as_engine<double>(Eb)->rmass.p, tmp.p, Eb->npoin, G.ndof, 1);
+      k_cart_permute<double, double><<<nblk, 256, 0, Eb->stream>>>(G, as_engine<double>(Eb)->rmass.p, tmp.p, Eb->npoin_ref, Eb->npoin, G.ndof, 1);
     else
-      k_cart_permute<float, double><<<nblk, 256, 0, Eb->stream>>>(G, as_engine<float>(Eb)->rmass.p, tmp.p, Eb->npoin, G.ndof, 1);
+      k_cart_permute<float, double><<<nblk, 256, 0, Eb->stream>>>(G, as_engine<float>(Eb)->rmass.p, tmp.p, Eb->npoin_ref, Eb->npoin, G.ndof, 1);
     S2D_CUDA(cudaStreamSynchronize(Eb->stream));
     tmp.download(rmass);
     if (!Eb->committed)
@@ -1202,6 +1257,50 @@ int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double*
             coord[2 * nd + 1] = gz_of(G, iz, j);
           }
   }
+  CART_GUARD_END
+}
+
+}  // extern "C"
+template <typename T>
+static void cart_fill(Engine<T>& E, const CartGeom& G, uint64_t seed, double amp_d, double amp_v) {
+  const long long tot = (long long)G.S.LX * G.S.LZ;
+  E.a.zero(E.stream);
+  k_cart_fill<T><<<(unsigned)((tot + 255) / 256), 256, 0, E.stream>>>(G, E.dbuf().p, E.v.p, E.npoin, seed, amp_d, amp_v);
+  S2D_CUDA(cudaGetLastError());
+  E.pred_valid = false;
+  S2D_CUDA(cudaStreamSynchronize(E.stream));
+}
+extern "C" int s2d_cart_fill_fields(s2d_handle h, uint64_t seed, double amp_d, double amp_v) {
+  CART_GUARD_BEGIN
+  if (Eb->prec == 8) cart_fill<double>(*as_engine<double>(Eb), S.G, seed, amp_d, amp_v);
+  else cart_fill<float>(*as_engine<float>(Eb), S.G, seed, amp_d, amp_v);
+  CART_GUARD_END
+}
+
+template <typename T>
+static void cart_window(Engine<T>& E, const CartGeom& G, int gx0, int gz0, int nwx, int nwz, double* d, double* v,
+                        double* a) {
+  const size_t n = (size_t)nwx * nwz * G.ndof;
+  DevBuf<double> tmp;
+  tmp.alloc(n);
+  const T* src[3] = {E.dbuf().p, E.v.p, E.a.p};
+  double* dst[3] = {d, v, a};
+  for (int k = 0; k < 3; ++k) {
+    if (!dst[k]) continue;
+    k_cart_window<T><<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(src[k], tmp.p, E.npoin, G.S.LXP, G.ndof, gx0, gz0, nwx, nwz);
+    S2D_CUDA(cudaGetLastError());
+    S2D_CUDA(cudaStreamSynchronize(E.stream));
+    tmp.download(dst[k]);
+  }
+}
+extern "C" {
+int s2d_cart_get_window(s2d_handle h, int32_t gx0, int32_t gz0, int32_t nwx, int32_t nwz, double* d, double* v, double* a) {
+  CART_GUARD_BEGIN
+  const CartGeom& G = S.G;
+  S2D_REQUIRE(gx0 >= 0 && gz0 >= 0 && nwx >= 1 && nwz >= 1 && gx0 + nwx <= G.S.LX && gz0 + nwz <= G.S.LZ,
+              "cart_get_window: window outside the lattice");
+  if (Eb->prec == 8) cart_window<double>(*as_engine<double>(Eb), G, gx0, gz0, nwx, nwz, d, v, a);
+  else cart_window<float>(*as_engine<float>(Eb), G, gx0, gz0, nwx, nwz, d, v, a);
   CART_GUARD_END
 }
 

@@ -22,6 +22,9 @@ struct ArgError : std::runtime_error {
 struct StateError : std::runtime_error {
   explicit StateError(const std::string& m) : std::runtime_error(m) {}
 };
+struct SolverError : std::runtime_error {  // device-side abort of the friction solver -> S2D_ESOLVER
+  explicit SolverError(const std::string& m) : std::runtime_error(m) {}
+};
 
 #define S2D_CUDA(call)                                                                          \
   do {                                                                                          \

@@ -25,9 +25,12 @@ static int guard(s2d_handle h, F&& fn) {
   } catch (const ArgError& e) {
     h->err = e.what();
     return S2D_EINVAL;
+  } catch (const SolverError& e) {
+    h->err = e.what();
+    return S2D_ESOLVER;
   } catch (const StateError& e) {
     h->err = e.what();
-    return std::string(e.what()).find("NR_Solver") != std::string::npos ? S2D_ESOLVER : S2D_ESTATE;
+    return S2D_ESTATE;
   } catch (const CudaError& e) {
     h->err = e.what();
     return S2D_ECUDA;

@@ -1,6 +1,7 @@
 // Engine core: device-resident state of one SEM2DPACK problem and the per-step launch sequence
 // of solve_leapfrog / solve_Newmark (SRC/solver.f90:42-84,140-160) + REC_store + BC_write.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <functional>
@@ -60,7 +61,8 @@ class EngineBase {
  public:
   virtual ~EngineBase() {}
   int ngll = 0, ndof = 0, nelem = 0, prec = 8;
-  size_t npoin = 0;
+  size_t npoin = 0;      // device node count = component stride (builder-made engines: lattice rows of pitch LXP)
+  size_t npoin_ref = 0;  // node count of the caller's numbering (what host arrays are sized with)
   s2d_scheme scheme{};
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -139,13 +141,14 @@ class Engine : public EngineBase {
   // sources
   std::vector<int32_t> h_src_iglob;
   std::vector<double> h_src_dir;
-  DevBuf<int> src_iglob;
-  DevBuf<double> src_dir, src_ampli, bc_ampli;
+  DevBuf<double> src_ampli, bc_ampli;
+  // source terms grouped by target node, in the order SO_add applies them (k_sources)
+  DevBuf<int> st_node, st_start, st_src;
+  DevBuf<double> st_coef;
+  int st_nnodes = 0, st_nterms = 0;
   // moment-tensor sources (src_moment.f90): terms of SRC_MOMENT_add per source
   std::vector<int32_t> h_mom_src, h_mom_start{0}, h_mom_node;
   std::vector<double> h_mom_coef;
-  DevBuf<int> mom_src, mom_start, mom_node;
-  DevBuf<double> mom_coef;
   // HHT-alpha work fields (fields%displ_alpha, veloc_alpha; fields.f90:10-11)
   DevBuf<T> d_alpha, v_alpha;
   int nstages() const { return scheme.kind == 3 ? scheme.nstages : 1; }
@@ -204,6 +207,7 @@ class Engine : public EngineBase {
   std::function<void(const T*, double*)> cart_to_ref;    // lattice (T) -> reference numbering (FP64), device to device
   std::function<void(const double*, T*)> cart_from_ref;  // reference numbering (FP64) -> lattice (T)
   std::function<void(const double*, T*)> cart_from_ref1; // the same for a one-component node array
+  std::function<void(const double*, double*)> cart_from_ref1d;  // ... kept in FP64 (the mass of s2d_energy)
   // fused leapfrog step of the strip kernel: two displacement buffers (the kernel reads d[n] and
   // writes the predicted d[n+1] of the next step), deferred-node tables (strip_kernels.cuh)
   DevBuf<T> d2;
@@ -356,12 +360,13 @@ class Engine : public EngineBase {
 
   // bare engine for the structured builder (cart.cu fills the tables on the device)
   struct Raw {};
-  Engine(Raw, int ngll_, int ndof_, int nelem_, size_t npoin_, const double* hprime, const s2d_scheme& sch,
-         int dev) {
+  Engine(Raw, int ngll_, int ndof_, int nelem_, size_t npoin_, size_t npoin_ref_, const double* hprime,
+         const s2d_scheme& sch, int dev) {
     ngll = ngll_;
     ndof = ndof_;
     nelem = nelem_;
     npoin = npoin_;
+    npoin_ref = npoin_ref_;
     prec = (int)sizeof(T);
     scheme = sch;
     device = dev;
@@ -389,6 +394,7 @@ class Engine : public EngineBase {
     ndof = ndof_;
     nelem = nelem_;
     npoin = npoin_;
+    npoin_ref = npoin_;
     prec = (int)sizeof(T);
     scheme = sch;
     device = dev;
@@ -452,7 +458,20 @@ class Engine : public EngineBase {
       upload_as(eta, eta_, (size_t)ngll * ngll * nkv);
     }
   }
-  void set_mass(const double* m) override { mass.upload(m, npoin); }
+  // mass(npoin) in the caller's numbering; builder-made engines keep it on the lattice like every field
+  // (the builder also fills it itself, before the boundary conditions touch the mass: cart.cu)
+  void set_mass(const double* m) override {
+    if (!cart_mode) {
+      mass.upload(m, npoin);
+      return;
+    }
+    DevBuf<double> tmp;
+    tmp.upload(m, npoin_ref);
+    mass.alloc(npoin);
+    mass.zero(stream);
+    cart_from_ref1d(tmp.p, mass.p);
+    S2D_CUDA(cudaStreamSynchronize(stream));
+  }
 
   void check_nodes(int np, const int32_t* node, const char* what) {
     for (int k = 0; k < np; ++k)
@@ -781,8 +800,9 @@ class Engine : public EngineBase {
     S2D_REQUIRE(cart_mode, "set_node_kv: structured builder only (the generic engine takes s2d_set_kv)");
     S2D_REQUIRE(!committed, "set_node_kv after commit");
     DevBuf<double> tmp;
-    tmp.upload(eta_ref, npoin);
+    tmp.upload(eta_ref, npoin_ref);
     cart_kv_eta.alloc(npoin);
+    cart_kv_eta.zero(stream);
     cart_kv_buf.alloc(npoin * ndof);
     cart_from_ref1(tmp.p, cart_kv_eta.p);
     S2D_CUDA(cudaStreamSynchronize(stream));
@@ -840,7 +860,7 @@ class Engine : public EngineBase {
   // boundary condition or a source touches.  A list that runs along one lattice column flags that
   // column, anything else flags the rows of its nodes.
   void build_deferred_tables() {
-    const int LX = cart_S.LX, LZ = cart_S.LZ;
+    const int LX = cart_S.LX, LZ = cart_S.LZ, LXP = cart_S.LXP;
     h_rowflag.resize(LZ, 0);
     h_colflag.resize(LX, 0);
     std::vector<std::vector<int32_t>> lists = h_bc_nodes;
@@ -853,11 +873,11 @@ class Engine : public EngineBase {
     for (auto& L : lists) {
       std::vector<int> colcount(LX, 0), rowcount(LZ, 0);
       for (int nd : L) {
-        colcount[(nd - 1) % LX]++;
-        rowcount[(nd - 1) / LX]++;
+        colcount[(nd - 1) % LXP]++;
+        rowcount[(nd - 1) / LXP]++;
       }
       for (int nd : L) {
-        const int gx = (nd - 1) % LX, gz = (nd - 1) / LX;
+        const int gx = (nd - 1) % LXP, gz = (nd - 1) / LXP;
         if (colcount[gx] > rowcount[gz]) h_colflag[gx] = 1;  // overrides 2 (group-boundary column)
         else h_rowflag[gz] = 1;
       }
@@ -977,16 +997,7 @@ class Engine : public EngineBase {
       build_color_plan();
       if (variant == S2D_ASM_PATCH) build_patch_plan_dev();
     }
-    if (!h_src_iglob.empty()) {
-      src_iglob.upload(h_src_iglob);
-      src_dir.upload(h_src_dir);
-    }
-    if (!h_mom_src.empty()) {
-      mom_src.upload(h_mom_src);
-      mom_start.upload(h_mom_start);
-      mom_node.upload(h_mom_node);
-      mom_coef.upload(h_mom_coef);
-    }
+    build_source_terms();
     if (scheme.kind == 2) {
       d_alpha.alloc(npoin * ndof);
       v_alpha.alloc(npoin * ndof);
@@ -1142,21 +1153,54 @@ class Engine : public EngineBase {
     }
   }
 
-  // SO_add (src_gen.f90:290-317): collocated forces, then moment tensors
+  // SO_add (src_gen.f90:290-317): the terms of every source (one for a point force, src_force.f90:84; those of
+  // SRC_MOMENT_add, src_moment.f90:183-197, for a moment tensor) in source order, grouped by target node
+  void build_source_terms() {
+    const int ns = (int)h_src_iglob.size();
+    if (ns == 0) return;
+    struct Term {
+      int node, src;
+      double c[2];
+    };
+    std::vector<Term> terms;
+    size_t m = 0;
+    for (int s = 0; s < ns; ++s) {
+      if (h_src_iglob[s] > 0) {
+        terms.push_back({h_src_iglob[s], s, {ndof == 1 ? 1.0 : h_src_dir[2 * s], ndof == 1 ? 0.0 : h_src_dir[2 * s + 1]}});
+      } else {  // the m-th moment source
+        const int t0 = h_mom_start[m], nt = h_mom_start[m + 1] - t0;
+        for (int t = 0; t < nt; ++t)
+          terms.push_back({h_mom_node[t0 + t], s,
+                           {h_mom_coef[(size_t)t0 * ndof + t], ndof == 2 ? h_mom_coef[(size_t)t0 * ndof + t + nt] : 0.0}});
+        ++m;
+      }
+    }
+    std::stable_sort(terms.begin(), terms.end(), [](const Term& a, const Term& b) { return a.node < b.node; });
+    const int nt = (int)terms.size();
+    std::vector<int> node, start, src(nt);
+    std::vector<double> coef((size_t)nt * ndof);
+    for (int t = 0; t < nt; ++t) {
+      if (t == 0 || terms[t].node != terms[t - 1].node) {
+        node.push_back(terms[t].node);
+        start.push_back(t);
+      }
+      src[t] = terms[t].src;
+      for (int c = 0; c < ndof; ++c) coef[t + (size_t)nt * c] = terms[t].c[c];
+    }
+    start.push_back(nt);
+    st_nnodes = (int)node.size();
+    st_nterms = nt;
+    st_node.upload(node);
+    st_start.upload(start);
+    st_src.upload(src);
+    st_coef.upload(coef);
+  }
   void launch_sources(T* f, int stage = 0) {
-    if (h_src_iglob.empty()) return;
-    const int ns = (int)h_src_iglob.size(), nst = nstages();
-    if ((size_t)ns > h_mom_src.size()) {
-      k_sources<T><<<ceil_div(ns, 32), 32, 0, stream>>>(f, npoin, ndof, ns, src_iglob.p, src_dir.p, src_ampli.p, ctl.p,
-                                                        stage, nst);
-      launches++;
-    }
-    if (!h_mom_src.empty()) {
-      const int nm = (int)h_mom_src.size();
-      k_moments<T><<<ceil_div(nm, 32), 32, 0, stream>>>(f, npoin, ndof, nm, mom_src.p, mom_start.p, mom_node.p,
-                                                        mom_coef.p, ns, src_ampli.p, ctl.p, stage, nst);
-      launches++;
-    }
+    if (st_nnodes == 0) return;
+    k_sources<T><<<ceil_div(st_nnodes, 64), 64, 0, stream>>>(f, npoin, ndof, st_nnodes, st_node.p, st_start.p, st_src.p,
+                                                            st_coef.p, st_nterms, (int)h_src_iglob.size(), src_ampli.p,
+                                                            ctl.p, stage, nstages());
+    launches++;
   }
 
   void launch_outputs() {
@@ -1209,7 +1253,7 @@ class Engine : public EngineBase {
     const long long nw = (long long)ndrows * cart_S.LX + (long long)ndcols * cart_S.LZ;
     if (nw > 0) {
       k_strip_deferred<T><<<(unsigned)((nw + 255) / 256), 256, 0, stream>>>(
-          cart_S.LX, cart_S.LZ, ndof, npoin, drows.p, ndrows, dcols.p, ndcols, rowflag.p, a.p, v.p, rmass.p, dc, dnx, dt,
+          cart_S.LX, cart_S.LXP, cart_S.LZ, ndof, npoin, drows.p, ndrows, dcols.p, ndcols, rowflag.p, a.p, v.p, rmass.p, dc, dnx, dt,
           c1, c3);
       launches++;
     }
@@ -1273,13 +1317,20 @@ class Engine : public EngineBase {
     launch_outputs();
   }
 
+  // Device-side aborts (ctl.err) are reported once: the flag is cleared, so that the next call is judged on its
+  // own.  After S2D_ESOLVER the engine state is undefined (the reference stops the program, bc_dynflt_rsf.f90:463-466).
   void check_device_error() {
     StepCtl c;
     S2D_CUDA(cudaMemcpyAsync(&c, ctl.p, sizeof(c), cudaMemcpyDeviceToHost, stream));
     S2D_CUDA(cudaStreamSynchronize(stream));
-    if (c.err == 1) throw StateError("NR_Solver has exceeded the maximum iterations (200)");
-    if (c.err == 2) throw StateError("NR_Solver could not bracket a root");
+    if (c.err == 0) return;
+    const int zero = 0;
+    S2D_CUDA(cudaMemcpyAsync(&ctl.p->err, &zero, sizeof(int), cudaMemcpyHostToDevice, stream));
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    if (c.err == 1) throw SolverError("NR_Solver has exceeded the maximum iterations (200)");
+    if (c.err == 2) throw SolverError("NR_Solver could not bracket a root");
     if (c.err == 3) throw StateError("halo exchange: a neighbour GPU did not signal within 10 s");
+    throw StateError("device-side abort, code " + std::to_string(c.err));
   }
 
   void step(int nsteps, const double* srca, const double* bca) override {
@@ -1339,7 +1390,7 @@ class Engine : public EngineBase {
     S2D_CUDA(cudaStreamSynchronize(stream));
     if (cart_mode) {
       DevBuf<double> tmp;
-      tmp.upload(src, nd);
+      tmp.upload(src, npoin_ref * ndof);
       cart_from_ref(tmp.p, dst.p);
       S2D_CUDA(cudaStreamSynchronize(stream));
       return;
@@ -1358,7 +1409,7 @@ class Engine : public EngineBase {
     S2D_CUDA(cudaStreamSynchronize(stream));
     if (cart_mode) {
       DevBuf<double> tmp;
-      tmp.alloc(nd);
+      tmp.alloc(npoin_ref * ndof);
       cart_to_ref(src.p, tmp.p);
       S2D_CUDA(cudaStreamSynchronize(stream));
       tmp.download(dst);
@@ -1373,9 +1424,8 @@ class Engine : public EngineBase {
     }
   }
   void set_fields(const double* dd, const double* vv, const double* aa) override {
-    if (dd) pred_valid = false;
+    if (dd || vv || aa) pred_valid = false;  // the cached prediction d + dt*v (+ dt^2/2 a) is stale
     upload_field(dbuf(), dd);
-    if (vv) pred_valid = false;
     upload_field(v, vv);
     upload_field(a, aa);
   }

@@ -7,8 +7,10 @@
 // mass-inverse update of solve_leapfrog (SRC/solver.f90:151,157-158).  Same operator as
 // elem_kernels.cuh:   Uxi = Ht U, Ueta = U H,  f = H (tH) + (tHt) Ht      (H(i,j) = h'_i(x_j))
 //
-// Layout.  Fields live on the GLL LATTICE: node (gx,gz) at gz*LX + gx, LX = nx*(N-1)+1; the row of
-// split fault nodes is stored twice (lower side, then upper side).  The box is cut into vertical
+// Layout.  Fields live on the GLL LATTICE: node (gx,gz) at gz*LXP + gx, LX = nx*(N-1)+1 columns in rows of
+// pitch LXP >= LX + 1, a multiple of 8 elements (every row, hence every strip boundary, starts on a 32-byte
+// DRAM sector; the pad columns hold zeros and are never written); the row of split fault nodes is stored
+// twice (lower side, then upper side).  The box is cut into vertical
 // strips EPW = floor(32/N) elements wide and horizontal bands of SEG element rows.  One WARP owns one
 // (band, strip) and marches through it upward, one element row per iteration; one CTA is a GROUP of
 // GW adjacent strips of the same band:
@@ -42,6 +44,7 @@ struct StripGeom {
   int EPW, W, WL;          // elements per strip, lattice columns per full strip, W+1
   int nstrips, SEG, nseg_lo, nseg;
   int LX, LZ;              // lattice extent (LZ counts the duplicated fault row)
+  int LXP;                 // row pitch of the lattice arrays (>= LX + 1, multiple of 8)
   // groups of strips (one CTA each): [strip 0 alone if g_lead] [runs of GW strips] [last strip alone if g_tail]
   int GW, g_lead, g_tail, ngroups;
   // subset of groups handled by one launch: group = it_g0 + (k % it_ng) * it_step, band = k / it_ng
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   const bool take = real && (lane == 0) && (warp > 0);               // receives the previous warp's edge
   const bool to_halo = redge && !give && (strip < G.nstrips - 1);    // group's right edge: partial sum to halo_x
   const bool st_ok = real && !dup && !give;
-  const size_t LX = (size_t)G.LX;
+  const size_t LX = (size_t)G.LXP;  // row pitch
   const int gx = (ex0 + el) * (N - 1) + i;
   const T* up = A.d + gx;
   T* sp;
@@ -762,7 +765,7 @@ __global__ void k_strip_fold(StripGeom G, T* __restrict__ f, const T* __restrict
     const int gz = strip_lat_row(G, ez0, 0);
     int sr;
     const int gx = strip_halo_col(G, hb, sr);
-    const size_t node = (size_t)gz * G.LX + gx;
+    const size_t node = (size_t)gz * G.LXP + gx;
     const int seg_l = seg_u - 1;
     for (int c = 0; c < G.ndof; ++c) {
       T acc = f[node + npoin * c] + halo_x[hx_c * c + (size_t)hb * G.LZ + gz];
@@ -786,7 +789,7 @@ __global__ void k_strip_fold(StripGeom G, T* __restrict__ f, const T* __restrict
   if ((gx == 0 && G.xhalo_left) || (gx == G.LX - 1 && G.xhalo_right)) return;  // folded by k_xhalo_unpack
   int ez0, ez1;
   strip_seg_rows(G, seg_u, ez0, ez1);
-  const size_t node = (size_t)strip_lat_row(G, ez0, 0) * G.LX + gx;
+  const size_t node = (size_t)strip_lat_row(G, ez0, 0) * G.LXP + gx;
   for (int c = 0; c < G.ndof; ++c)
     f[node + npoin * c] += halo_z[hz_c * c + ((size_t)(seg_u - 1) * G.nstrips + strip) * G.WL + lc];
 }
@@ -795,7 +798,7 @@ __global__ void k_strip_fold(StripGeom G, T* __restrict__ f, const T* __restrict
 // conditions done): a = rmass*f, v += dt*a, d_next = d + dt*v  (solver.f90:157-158,151).
 //   part A: flagged rows (contiguous);  part B: flagged columns, minus the nodes of flagged rows
 template <typename T>
-__global__ void k_strip_deferred(int LX, int LZ, int ndof, size_t npoin, const int* __restrict__ drows, int ndrows,
+__global__ void k_strip_deferred(int LX, int LXP, int LZ, int ndof, size_t npoin, const int* __restrict__ drows, int ndrows,
                                  const int* __restrict__ dcols, int ndcols, const uint8_t* __restrict__ rowflag,
                                  T* __restrict__ fa, T* __restrict__ v, const T* __restrict__ rmass,
                                  const T* __restrict__ d, T* __restrict__ d_next, T dt, T c1, T c3) {
@@ -804,13 +807,13 @@ __global__ void k_strip_deferred(int LX, int LZ, int ndof, size_t npoin, const i
   size_t node;
   if (w < nA) {
     const int r = (int)(w / LX);
-    node = (size_t)drows[r] * LX + (size_t)(w - (long long)r * LX);
+    node = (size_t)drows[r] * LXP + (size_t)(w - (long long)r * LX);
   } else {
     const long long w2 = w - nA;
     if (w2 >= (long long)ndcols * LZ) return;
     const int gz = (int)(w2 / ndcols), k = (int)(w2 - (long long)gz * ndcols);
     if (rowflag[gz]) return;
-    node = (size_t)gz * LX + dcols[k];
+    node = (size_t)gz * LXP + dcols[k];
   }
   for (int c = 0; c < ndof; ++c) {
     const size_t q = node + npoin * c;
@@ -831,7 +834,7 @@ __device__ __forceinline__ T xhalo_own(const StripGeom& G, const T* f, const T* 
                                        int c, int gz) {
   const int strip = side ? G.nstrips - 1 : 0;
   const int gx = side ? G.LX - 1 : 0;
-  T acc = f[(size_t)gz * G.LX + gx + npoin * c];
+  T acc = f[(size_t)gz * G.LXP + gx + npoin * c];
   const int seg_l = strip_shared_row_seg(G, gz);
   if (seg_l >= 0) {
     const size_t hz_c = (size_t)G.nseg * G.nstrips * G.WL;
@@ -895,7 +898,7 @@ __global__ void k_xhalo_unpack(StripGeom G, T* __restrict__ f, const T* __restri
   if (!src) return;
   const int c = q / G.LZ, gz = q % G.LZ;
   const int gx = side ? G.LX - 1 : 0;
-  f[(size_t)gz * G.LX + gx + npoin * c] = xhalo_own(G, f, halo_z, npoin, side, c, gz) + src[q];
+  f[(size_t)gz * G.LXP + gx + npoin * c] = xhalo_own(G, f, halo_z, npoin, side, c, gz) + src[q];
 }
 
 // everything a strip launch needs besides the geometry

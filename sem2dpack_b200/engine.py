@@ -308,6 +308,18 @@ class CartEngine(Engine):
         self._ck(self.L.s2d_cart_add_receivers(self.h, nx, first[0], first[1], last[0], last[1],
                                                field.encode()[:1], isamp, nt_rec))
 
+    def fill_fields(self, seed, amp_d, amp_v):
+        """seeded non-trivial state (hash noise keyed by global lattice coordinates); accel = 0"""
+        self._ck(self.L.s2d_cart_fill_fields(self.h, int(seed), float(amp_d), float(amp_v)))
+
+    def get_window(self, gx0, gz0, nwx, nwz, a=False):
+        """(d, v[, a]) on a window of the GLL lattice, each (ndof, nwz, nwx); a split fault row is two rows"""
+        shp = (self.ndof, nwz, nwx)
+        d, v = np.empty(shp), np.empty(shp)
+        aa = np.empty(shp) if a else None
+        self._ck(self.L.s2d_cart_get_window(self.h, gx0, gz0, nwx, nwz, _ptr(d), _ptr(v), _ptr(aa)))
+        return (d, v, aa) if a else (d, v)
+
     def get_tables(self, ibool=True, a=False, rmass=True, coord=False, nelast=None):
         n2 = self.ngll * self.ngll
         ib = np.empty(self.nelem * n2, np.int32) if ibool else None

@@ -1,8 +1,9 @@
 """Regenerates tests/golden/ from the read-only reference checkout (run in the build container only;
 /root/reference does not exist on the GPU box).
 
-  * *.par       -- the four CPU-runnable example decks of BASELINE.json (EXAMPLES/*/Par.inp with
-                   comment lines dropped); they are INPUT data, the namelist text the reference reads.
+  * *.par       -- the four CPU-runnable example decks of BASELINE.json and four more MESH_CART examples
+                   (EXAMPLES/*/Par.inp with comment lines dropped); they are INPUT data, the namelist text
+                   the reference reads.
   * refdata.npz -- the reference's own known-answer artefacts for those decks:
                    TestSH/uyref.mat (analytic SH trace used by EXAMPLES/TestSH/analyze_test.m),
                    LambsProblem/U{x,z}_file_ascii (EX2DDIR traces, analyze_test.m) and the misfits
@@ -16,7 +17,9 @@ import scipy.io
 
 REF = "/root/reference/EXAMPLES"
 HERE = os.path.dirname(os.path.abspath(__file__))
-DECKS = {"testsh": "TestSH", "lamb": "LambsProblem", "tpv3": "TestFlt2D_SCEC_TPV3_inplane", "ratestate": "RateState"}
+DECKS = {"testsh": "TestSH", "lamb": "LambsProblem", "tpv3": "TestFlt2D_SCEC_TPV3_inplane", "ratestate": "RateState",
+         # round 2: the time-solver lines of InaBox/info:224-225 pin dt / nt; the others are the decks VERDICT r1 names
+         "inabox": "InaBox", "velweak": "Velocity_weakening", "inplane25d": "2.5D_inplane", "kvfz": "Kelvin_Visco_FZ"}
 
 
 def main():

@@ -31,6 +31,9 @@ def lib():
         L = C.CDLL(build_oracle())
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_char_p, C.c_ulonglong, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.orc_create_at.restype = C.c_void_p
+        L.orc_create_at.argtypes = [C.c_char_p, C.c_ulonglong, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
+                                    C.c_char_p, C.c_int]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_step.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.orc_time_solve.restype = C.c_double
@@ -61,11 +64,13 @@ _DT = {b"i": np.int32, b"d": np.float64, b"f": np.float32}
 class Oracle:
     """One SEM2DPACK problem built from Par.inp text and advanced on the CPU."""
 
-    def __init__(self, parinp_text, synthetic_seed=0, renumber=True, kd_force_kd1=False):
+    def __init__(self, parinp_text, synthetic_seed=0, renumber=True, kd_force_kd1=False, lattice_origin=(0, 0)):
+        """lattice_origin: GLL lattice coordinates of this mesh's corner inside a larger synthetic mesh (the hash
+        medium is a function of global lattice coordinates), for windowed parity checks"""
         self.L = lib()
         err = C.create_string_buffer(512)
-        self.h = self.L.orc_create(parinp_text.encode(), synthetic_seed, int(renumber),
-                                   int(kd_force_kd1), err, 512)
+        self.h = self.L.orc_create_at(parinp_text.encode(), synthetic_seed, int(renumber), int(kd_force_kd1),
+                                      int(lattice_origin[0]), int(lattice_origin[1]), err, 512)
         if not self.h:
             raise RuntimeError(err.value.decode())
 

@@ -200,3 +200,16 @@ def test_synthetic_material_hash_is_partition_independent():
     assert a != L.orc_hash_u(20261017, 12346, 678, 1)
     vals = np.array([L.orc_hash_u(20261017, i, 3 * i + 1, 2) for i in range(4000)])
     assert abs(vals.mean()) < 0.05 and abs(vals.std() - 1 / np.sqrt(3)) < 0.03
+
+
+def test_inabox_time_solver_lines():
+    """EXAMPLES/InaBox/info:191-192,224-227 -- the reference's own log of this deck (NGLL=5 P-SV Newmark box, the
+    KD2 path of the benchmark): 25921 GLL points, `Time step (secs) = 681.605E-06`, `Number of time steps = 2935`,
+    `Total duration = 2.001E+00`.  Pins CHECK_grid's max(c/dx) and TIME_init (init.f90:187-225, time.f90:323-341)."""
+    o = orc.Oracle(harness.deck("inabox"))
+    assert o.i("npoin") == 25921 and o.i("nelem") == 1600
+    assert f"{o.f('dt') * 1e6:.3f}" == "681.605"
+    assert o.i("nt") == 2935
+    assert f"{o.i('nt') * o.f('dt'):.3f}" == "2.001"
+    assert abs(o.f("courant") - 0.3) < 1e-15
+    o.close()
