@@ -7,7 +7,11 @@ Workload (BASELINE.json configs[4]): synthetic Q4 structured mesh,
 heterogeneous elastic medium (one coefficient block per element), planar two-sided slip-weakening
 fault at mid height, absorbing boundaries on the 4 sides, Ricker point force, 128 receivers, leapfrog,
 Courant 0.5, FP64.  One step = one pass of the loop body of SRC/main.f90:51-99.
-At N > 1 each rank owns one x-strip of NX element columns (weak scaling, global mesh N*NX x NZ).
+At N > 1 each rank owns one x-strip of NX element columns (weak scaling, global mesh N*NX x NZ); the same
+line then carries a `strong` sub-record (the ONE NX x NZ mesh of BASELINE.json configs[4] split over the N
+GPUs) and an `xdev` record (a small global mesh stepped as N strips on N GPUs and as one box on rank 0:
+interface copies, fields and fault state compared bit for bit before anything is timed).
+The timed state is not at rest: fields start from a seeded random state (s2d_cart_fill_fields).
 Prints ONE JSON line (rank 0).  --impl reference times the CPU oracle (a port of the reference's
 serial Fortran path: no Fortran compiler exists in this image) on the host cores.
 """
@@ -110,10 +114,12 @@ def synthetic_deck(nx, nz, nsteps):
                              nsteps=nsteps, h=H, nrec=0)
 
 
-def cpu_oracle_rate(nx, nz, nsteps):
-    """DOF-updates/s of the CPU oracle (1 thread; the reference solver is serial) on a bounded sample."""
+def cpu_oracle_rate(nx, nz, nsteps, variant="o3"):
+    """DOF-updates/s of the CPU oracle (1 thread; the reference solver is serial) on a bounded sample.
+    variant "o3": -O3 -march=x86-64-v3 (BASELINE.md section 4's optimisation level; the .so must run on the GPU
+    box's host, so no -march=native); "parity": the -O2 -ffp-contract=off build the parity tests use."""
     import orc
-    o = orc.Oracle(synthetic_deck(nx, nz, nsteps + 2), synthetic_seed=SEED)
+    o = orc.Oracle(synthetic_deck(nx, nz, nsteps + 2), synthetic_seed=SEED, variant=variant)
     ndofs = o.i("npoin") * o.i("ndof")
     o.time_solve(1)
     t = o.time_solve(nsteps)
@@ -121,7 +127,7 @@ def cpu_oracle_rate(nx, nz, nsteps):
     return ndofs * nsteps / t, t
 
 
-def build_engine(nx, nz, rank, world, device, nt_max, precision=8, sync_dt=None, scheme_kind=0):
+def build_engine(nx, nz, rank, world, device, nt_max, precision=8, sync_dt=None, scheme_kind=0, oixd=None):
     from sem2dpack_b200 import CartEngine
     ez = nz // 2
     e = CartEngine(NGLL, NDOF, nx, nz, (rank * nx * H, (rank + 1) * nx * H), (0.0, nz * H), ezflt=ez, seed=SEED,
@@ -130,8 +136,8 @@ def build_engine(nx, nz, rank, world, device, nt_max, precision=8, sync_dt=None,
     if sync_dt is not None:
         e.set_dt(sync_dt(e.dt))  # one Courant step for the whole mesh: the minimum over the strips
     xg = world * nx * H
-    e.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, xg / 2, 1500.0, oixd=max(1, (nx * 4 + 1) // 512),
-                    oitd=10, nt_max=nt_max)
+    e.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, xg / 2, 1500.0,
+                    oixd=oixd or max(1, (nx * 4 + 1) // 512), oitd=10, nt_max=nt_max)
     sides = [1, 3] + ([4] if rank == 0 else []) + ([2] if rank == world - 1 else [])
     for s in sorted(sides):
         e.add_abso_side(s, False)
@@ -145,6 +151,92 @@ def build_engine(nx, nz, rank, world, device, nt_max, precision=8, sync_dt=None,
     return e, nsrc
 
 
+FILL = (SEED + 1, 1.0e-3, 1.0)   # seeded non-trivial state of every timed run: |d| <= 1 mm, |v| <= 1 m/s
+
+
+def attach_halo(e, rank, world, args, torch, dist):
+    """x-strip interface exchange of an engine with neighbours; returns the description for `config`"""
+    from sem2dpack_b200.strips import attach_halo_exchange, attach_peer_exchange
+    halo = "nccl send/recv through torch.distributed"
+    ok = 0
+    if args.halo == "peer":
+        try:
+            attach_peer_exchange(e, rank, world)
+            ok = 1
+        except Exception as ex:  # e.g. CUDA IPC not permitted in this container
+            print(f"[bench] rank {rank}: peer-memory halo exchange unavailable ({ex})", file=sys.stderr)
+    t = torch.tensor([ok], dtype=torch.int32, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t.item()) == 1:
+        return "peer memory over NVLink (CUDA IPC slots + device flags, no host call on the step path)"
+    if args.halo == "peer":
+        halo += " (peer-memory mapping failed on some rank)"
+    attach_halo_exchange(e, rank, world, precision=args.precision)
+    return halo
+
+
+def xdev_check(rank, world, local, args, torch, dist, sync_dt):
+    """Cross-device evidence: a small global mesh stepped as `world` x-strips on `world` GPUs and
+    as ONE box on rank 0, same dt / fault / absorbing sides / source / seeded state.  Rank 0 compares bit for
+    bit: the two copies of every interface column, every strip against the box, and the fault state."""
+    import numpy as np
+    from sem2dpack_b200.stf import Ricker
+    nxs, nzs, k = 48, 40, 30
+    nt = k + 8
+    e, nsrc = build_engine(nxs, nzs, rank, world, local, nt, args.precision, sync_dt, 0, oixd=1)
+    e.commit()
+    attach_halo(e, rank, world, args, torch, dist)
+    e.fill_fields(*FILL)
+    ric = Ricker(2.0, 0.6, 1.0e9)
+    e.step(k, ric.table(1, k, e.dt) if nsrc else None)
+    LXs, LZs = nxs * (NGLL - 1) + 1, nzs * (NGLL - 1) + 2
+    d, v = e.get_window(0, 0, LXs, LZs)
+    st = e.fault_state(0, LXs)
+    mine = {"d": d, "v": v, "D": st["D"].reshape(NDOF, -1), "V": st["V"].reshape(NDOF, -1), "dt": e.dt}
+    e.close()
+    allp = [None] * world
+    dist.all_gather_object(allp, mine)
+    res = None
+    if rank == 0:
+        from sem2dpack_b200 import CartEngine
+        nxg = nxs * world
+        g = CartEngine(NGLL, NDOF, nxg, nzs, (0.0, nxg * H), (0.0, nzs * H), ezflt=nzs // 2, seed=SEED, scheme_kind=0,
+                       courant=0.5, precision=args.precision, device=local)
+        g.set_dt(mine["dt"])
+        g.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, nxg * H / 2, 1500.0, oixd=1, oitd=10, nt_max=nt)
+        for sd in (1, 2, 3, 4):
+            g.add_abso_side(sd, False)
+        g.add_force_at(0.37 * nxg * H, 0.61 * nzs * H, [-0.5, 0.8660254037844386])
+        g.commit()
+        g.fill_fields(*FILL)
+        g.step(k, ric.table(1, k, g.dt))
+        LXg = nxg * (NGLL - 1) + 1
+        gd, gv = g.get_window(0, 0, LXg, LZs)
+        gs = g.fault_state(0, LXg)
+        gD, gV = gs["D"].reshape(NDOF, -1), gs["V"].reshape(NDOF, -1)
+        g.close()
+        iface = all(np.array_equal(allp[r][q][:, :, -1], allp[r + 1][q][:, :, 0]) for r in range(world - 1) for q in "dv")
+        whole, fault, worst = True, True, 0.0
+        for r in range(world):
+            x0 = r * nxs * (NGLL - 1)
+            for q, ref in (("d", gd), ("v", gv)):
+                a, b = allp[r][q], ref[:, :, x0:x0 + LXs]
+                whole = whole and np.array_equal(a, b)
+                worst = max(worst, float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)))
+            for q, ref in (("D", gD), ("V", gV)):
+                fault = fault and np.array_equal(allp[r][q], ref[:, x0:x0 + LXs])
+        res = {"mesh": f"{nxg}x{nzs} elements as {world} x-strips of {nxs}x{nzs} on {world} GPUs vs one box on rank 0",
+               "steps": k, "interface_copies_bitwise_equal": bool(iface), "strips_equal_box_bitwise": bool(whole),
+               "fault_state_bitwise_equal": bool(fault), "max_rel_diff": worst,
+               "vmax": float(np.abs(gv).max()), "slip_max": float(np.abs(gD).max()),
+               "pass": bool(iface and whole and fault)}
+    flag = torch.tensor([1 if (res is None or res["pass"]) else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if res is not None:
+        res["pass_all_reduced"] = bool(int(flag.item()))
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -153,7 +245,7 @@ def run_reference(args):
     rates = []
     t0 = time.time()
     for _ in range(max(1, min(args.steps, 3))):
-        r, _ = cpu_oracle_rate(n, n, CPU_SAMPLE_STEPS)
+        r, _ = cpu_oracle_rate(n, n, CPU_SAMPLE_STEPS, "o3")
         rates.append(r)
         if time.time() - t0 > 150:
             break
@@ -166,7 +258,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"oracle (C++ port of the serial Fortran path; no Fortran compiler in the image), "
                                    f"{n}x{n}-element sample of the same workload, {CPU_SAMPLE_STEPS} solve() steps x "
-                                   f"{len(rates)} repeats, 1 thread (the reference is serial)"},
+                                   f"{len(rates)} repeats, 1 thread (the reference is serial), -O3 -march=x86-64-v3"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -182,6 +274,8 @@ def main():
     ap.add_argument("--nz", type=int, default=8192)
     ap.add_argument("--precision", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-xdev", action="store_true", help="skip the cross-device parity check (N > 1)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (N > 1)")
     ap.add_argument("--fint-reps", type=int, default=10)
     ap.add_argument("--coef", choices=["compact", "full"], default="compact",
                     help="coefficient storage: (lambda, mu) per GLL point, or all six planes a(5,5,6) per element")
@@ -222,74 +316,66 @@ def main():
         torch.cuda.synchronize()
 
     K, W = args.steps, args.warmup
-    nt_max = 2 * (K + W) + 16
-    # build, falling back to a shorter mesh if 180 GB cannot hold the requested one
-    nx, nz = args.nx, args.nz
-    if args.scaling == "strong":
-        if nx % world:
-            raise SystemExit("--scaling strong needs --nx divisible by the number of GPUs")
-        nx //= world
-    e = None
-    tried = []
+    nt_max = 4 * (K + W) + 64
+
     def sync_dt(dt_local):
         t = torch.tensor([dt_local], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return float(t.item())
 
-    for nzt in [nz, (nz * 3) // 4, nz // 2, nz // 4]:
-        try:
-            e, nsrc = build_engine(nx, nzt, rank, world, local, nt_max, args.precision,
-                                   sync_dt if world > 1 else None, 1 if args.scheme == "newmark" else 0)
-            e.commit()
-            nz = nzt
-            break
-        except S2DError as ex:
-            tried.append(f"{nx}x{nzt}: {ex}")
-            e = None
-            torch.cuda.empty_cache()
-    if e is None:
-        raise SystemExit("could not build the workload: " + "; ".join(tried))
-    halo = "none (one strip)"
-    if world > 1:
-        from sem2dpack_b200.strips import attach_halo_exchange, attach_peer_exchange
-        halo = "nccl send/recv through torch.distributed"
-        ok = 0
-        if args.halo == "peer":
-            try:
-                attach_peer_exchange(e, rank, world)
-                ok = 1
-            except Exception as ex:  # e.g. CUDA IPC not permitted in this container
-                print(f"[bench] rank {rank}: peer-memory halo exchange unavailable ({ex})", file=sys.stderr)
-        t = torch.tensor([ok], dtype=torch.int32, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        if int(t.item()) == 1:
-            halo = "peer memory over NVLink (CUDA IPC slots + device flags, no host call on the step path)"
-        else:
-            if args.halo == "peer":
-                halo += " (peer-memory mapping failed on some rank)"
-            attach_halo_exchange(e, rank, world, precision=args.precision)
-    ndofs_rank = e.npoin * NDOF
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # --- cross-device parity on a small global mesh, before anything is timed
+    xdev = None
+    if world > 1 and not args.no_xdev:
+        xdev = xdev_check(rank, world, local, args, torch, dist, sync_dt)
+        barrier()
+
     ric = Ricker(2.0, 0.6, 1.0e9)
+    scheme_kind = 1 if args.scheme == "newmark" else 0
 
-    def table(it_first, n):
-        return ric.table(it_first, n, e.dt) if nsrc else None
+    def build(nx, nz_req):
+        """the workload on this rank's x-strip, falling back to a shorter mesh if 180 GB cannot hold it"""
+        tried = []
+        for nzt in [nz_req, (nz_req * 3) // 4, nz_req // 2, nz_req // 4]:
+            try:
+                e, nsrc = build_engine(nx, nzt, rank, world, local, nt_max, args.precision,
+                                       sync_dt if world > 1 else None, scheme_kind)
+                e.commit()
+                halo = attach_halo(e, rank, world, args, torch, dist) if world > 1 else "none (one strip)"
+                e.fill_fields(*FILL)   # the timed region starts from a non-trivial state on every rank
+                return e, nsrc, nzt, halo, tried
+            except S2DError as ex:
+                tried.append(f"{nx}x{nzt}: {ex}")
+                torch.cuda.empty_cache()
+        raise SystemExit("could not build the workload: " + "; ".join(tried))
 
-    # warm-up (also loads the stf table that the timed replay cycles through)
-    barrier()
-    e.step(W, table(1, W))
-    barrier()
-    # --- device-resident timing: K steps between CUDA events on the engine stream
-    l0 = e.launch_count()
-    clk = ClockSampler(local)
-    barrier()
-    ms = e.time_steps(K)
-    barrier()
-    clocks = clk.stop()
-    launches = e.launch_count() - l0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    def timed_steps(e, nsrc):
+        """W warm-up steps (they also load the stf table the timed replay cycles through), then K steps between
+        CUDA events on the engine stream; max over ranks"""
+        barrier()
+        e.step(W, ric.table(1, W, e.dt) if nsrc else None)
+        barrier()
+        l0 = e.launch_count()
+        clk = ClockSampler(local)
+        barrier()
+        ms = e.time_steps(K)
+        barrier()
+        clocks = clk.stop()
+        return allmax(ms), e.launch_count() - l0, clocks
+
+    nx, nz = args.nx, args.nz
+    if args.scaling == "strong":
+        if nx % world:
+            raise SystemExit("--scaling strong needs --nx divisible by the number of GPUs")
+        nx //= world
+    e, nsrc, nz, halo, tried = build(nx, nz)
+    ndofs_rank = e.npoin * NDOF
+    ms_max, launches, clocks = timed_steps(e, nsrc)
     value = ndofs_rank * world * K / (ms_max * 1e-3)
     # --- dominant kernel: the strip kernel as launched inside the timed steps (CUDA events around every
     # launch on the engine stream), and the plain force stage (strip kernel + halo fold) timed alone
@@ -301,6 +387,9 @@ def main():
     b_moved = moved_bytes_per_dof(fused, store_accel, compact, w, args.scheme == "newmark")
     barrier()
     ms_fint = e.time_fint(args.fint_reps)
+    barrier()
+    # the O(boundary) kernels are launch-latency bound: reported as time per step, not against the roofline
+    phases = e.time_phases(max(3, min(K, 10)))
     barrier()
     peak, peak_src = peaks()
     ach = b_moved * ndofs_rank / (ms_kernel * 1e-3) / 1e9
@@ -323,15 +412,33 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for k in range(n_e2e):
-        e.step(1, table(it0 + 1 + k, 1))
+        e.step(1, ric.table(it0 + 1 + k, 1, e.dt) if nsrc else None)
         row = e.seis_row(it0 + 1 + k)
     barrier()
-    t_e2e = time.perf_counter() - t0
-    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = ndofs_rank * world * n_e2e / float(te.item())
+    t_e2e = allmax(time.perf_counter() - t0)
+    e2e_val = ndofs_rank * world * n_e2e / t_e2e
+    h2d = int(allmax(8 * nsrc))          # the rank that owns the source uploads its stf row; max over ranks
+    d2h = int(allmax(int(row.nbytes)))
     vmax, dmax = e.progress()
+    vmax, dmax = allmax(vmax), allmax(dmax)
+    npoin_rank, nelem_rank, dt_run = e.npoin, e.nelem, e.dt
+    e.close()
+    del e
+    torch.cuda.empty_cache()
+
+    # --- strong scaling of the ONE mesh BASELINE.json configs[4] names, split over the GPUs (same line)
+    strong = None
+    if world > 1 and args.scaling == "weak" and not args.no_strong and args.nx % world == 0:
+        es, nsrc_s, nz_s, _, tried_s = build(args.nx // world, args.nz)
+        ms_s, launches_s, clocks_s = timed_steps(es, nsrc_s)
+        LZg = nz_s * (NGLL - 1) + 2
+        ndof_global = (args.nx * (NGLL - 1) + 1) * LZg * NDOF    # unique nodes of the global mesh (interface columns once)
+        phases_s = es.time_phases(max(3, min(K, 10)))
+        strong = {"workload": f"the ONE {args.nx}x{nz_s} mesh split into {world} x-strips of {args.nx // world}x{nz_s}",
+                  "value": ndof_global * K / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s / K, "steps": K,
+                  "dofs_global": ndof_global, "gpu_launches": int(launches_s), "clocks": clocks_s,
+                  "ms_per_step_by_phase": phases_s, "scaling": "strong"}
+        es.close()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -343,7 +450,9 @@ def main():
                                     else "one a(5,5,6) block per element in HBM"),
                    "accel": ("materialised every step" if store_accel else
                              "materialised on the last step of each s2d_step call (every step in the e2e leg)"),
-                   "halo_exchange": halo, "npoin_per_gpu": e.npoin, "nelem_per_gpu": e.nelem, "dt": e.dt,
+                   "initial_state": "seeded random fields on every rank (s2d_cart_fill_fields: |d| <= 1 mm, |v| <= 1 m/s), "
+                                    "not the rest state",
+                   "halo_exchange": halo, "npoin_per_gpu": npoin_rank, "nelem_per_gpu": nelem_rank, "dt": dt_run,
                    "l2_policy": "working set (>=100 GB per GPU at the default size) far exceeds the 126 MB L2",
                    "requested": f"{args.nx}x{args.nz}", "fallbacks_tried": tried},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -361,20 +470,30 @@ def main():
                                    "achieved": b_moved * value / world / 1e9, "frac": b_moved * value / world / 1e9 / peak,
                                    "note": "whole step (strip kernel + fold + boundary + deferred-node kernels) against "
                                            "the bytes the fused kernel must move"}},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 8 * nsrc, "d2h_bytes_per_step": int(row.nbytes),
+        "ms_per_step_by_phase": dict(phases, note="CUDA events between the phases of a step on the engine stream; sources, "
+                                                  "boundary conditions (4 ABSORB sides + DYNFLT), deferred nodes and outputs "
+                                                  "are O(boundary) and launch-latency bound (SURVEY 8d)"),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": n_e2e},
         "gpu_launches": int(launches), "clocks": clocks,
-        "check": {"vmax": vmax, "dmax": dmax},
+        "check": {"vmax": vmax, "dmax": dmax, "note": "max over all ranks of max|v|, max|d| after the run"},
     }
+    if strong is not None:
+        line["strong"] = strong
+    if xdev is not None:
+        line["xdev"] = xdev
     if rank == 0 and not args.no_cpu:
-        r, tcpu = cpu_oracle_rate(CPU_SAMPLE_N, CPU_SAMPLE_N, CPU_SAMPLE_STEPS)
+        r, tcpu = cpu_oracle_rate(CPU_SAMPLE_N, CPU_SAMPLE_N, CPU_SAMPLE_STEPS, "o3")
+        r2, tcpu2 = cpu_oracle_rate(CPU_SAMPLE_N, CPU_SAMPLE_N, max(2, CPU_SAMPLE_STEPS // 2), "parity")
         line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"oracle (C++ port of the serial Fortran path), {CPU_SAMPLE_N}x{CPU_SAMPLE_N}"
                                           f"-element sample of the same workload, {CPU_SAMPLE_STEPS} solve() steps, "
-                                          f"{tcpu:.1f} s, 1 thread; of {os.cpu_count()} host cores"}
+                                          f"{tcpu:.1f} s, 1 thread; of {os.cpu_count()} host cores",
+                                "build": "-O3 -march=x86-64-v3 (BASELINE.md section 4)",
+                                "parity_build_value": r2,
+                                "parity_build": "-O2 -ffp-contract=off (the build the parity tests compare against)"}
     if rank == 0:
         print(json.dumps(line))
-    e.close()
     if world > 1:
         dist.destroy_process_group()
 

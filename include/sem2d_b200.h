@@ -212,6 +212,13 @@ int s2d_time_steps(s2d_handle h, int32_t nsteps, float* ms_total);
 /* Average duration (ms per launch, CUDA events on the engine's stream) of the dominant kernel --
  * the strip kernel of a builder-made engine -- over the launches of the last s2d_time_steps call. */
 int s2d_kernel_ms(s2d_handle h, float* ms);
+/* Runs nsteps steps with CUDA events between the phases of a step on the engine's stream and returns the average
+ * milliseconds per step of each: ms_phase[S2D_NPHASES] = [0] step counter / predictor, [1] element-force kernel
+ * (fused with the node update where it is), [2] halo folds and x-strip interface exchange, [3] SO_add,
+ * [4] BC_apply (absorbing, Dirichlet / Neumann, dynamic faults), [5] node update (deferred nodes or corrector),
+ * [6] REC_store + BC_write.  SURVEY 8d: the O(boundary) kernels are reported as time per step. */
+#define S2D_NPHASES 7
+int s2d_time_phases(s2d_handle h, int32_t nsteps, float* ms_phase);
 /* number of kernels the engine has launched so far */
 int s2d_launch_count(s2d_handle h, int64_t* n);
 /* raw CUDA stream (cudaStream_t) the engine launches on, for external event timing */

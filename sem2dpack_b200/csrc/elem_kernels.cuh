@@ -148,14 +148,18 @@ inline void launch_elem_node(int ngll, const ElemArgs<T>& A, cudaStream_t s) {
     k_elem_node<T, NN, NDOF, ATOMIC><<<ceil_div(A.ne, EPB), 256, 0, s>>>(A); \
   } break;
   switch (ngll) {
+#ifndef S2D_ONLY_N5  // kernel-experiment builds (make EXTRA=-DS2D_ONLY_N5) instantiate NGLL = 5 only
     S2D_CASE(3)
     S2D_CASE(4)
+#endif
     S2D_CASE(5)
+#ifndef S2D_ONLY_N5
     S2D_CASE(6)
     S2D_CASE(7)
     S2D_CASE(8)
     S2D_CASE(9)
     S2D_CASE(10)
+#endif
     default:
       throw ArgError("ngll must be in 3..10");
   }

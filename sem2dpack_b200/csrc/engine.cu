@@ -245,6 +245,9 @@ int s2d_time_steps(s2d_handle h, int32_t nsteps, float* ms_total) {
     *ms_total = E.time_steps(nsteps);
   });
 }
+int s2d_time_phases(s2d_handle h, int32_t nsteps, float* ms_phase) {
+  return guard(h, [&](EngineBase& E) { E.time_phases(nsteps, ms_phase); });
+}
 int s2d_launch_count(s2d_handle h, int64_t* n) {
   return guard(h, [&](EngineBase& E) {
     if (n) *n = E.launches;

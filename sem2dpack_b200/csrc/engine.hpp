@@ -101,6 +101,7 @@ class EngineBase {
   virtual void get_coloring(int32_t* ncolors, int32_t* color) = 0;
   virtual float time_fint(int reps) = 0;
   virtual float time_steps(int nsteps) = 0;
+  virtual void time_phases(int nsteps, float* ms) = 0;
   float last_kernel_ms_base = 0.f;
   virtual float kernel_ms() = 0;
   virtual void halo_info(int64_t* count, void** send_dev, void** recv_dev) = 0;
@@ -232,6 +233,25 @@ class Engine : public EngineBase {
   bool kev_on = false;
   size_t kev_n = 0;
   float last_kernel_ms = 0.f;
+  // phase marks of s2d_time_phases: the time between two consecutive marks on the engine stream is charged to
+  // the phase of the first one.  0 tick / predictor, 1 element-force kernel, 2 halo folds + interface exchange,
+  // 3 sources, 4 boundary conditions, 5 node update (deferred nodes / corrector), 6 outputs, 7 idle
+  enum { PH_PRED = 0, PH_FORCE, PH_FOLD, PH_SRC, PH_BC, PH_UPDATE, PH_OUT, PH_COUNT };
+  std::vector<cudaEvent_t> pev;
+  std::vector<int> pev_phase;
+  bool pev_on = false;
+  void phase(int ph) {
+    if (!pev_on) return;
+    cudaEvent_t e;
+    if (pev_phase.size() < pev.size()) {
+      e = pev[pev_phase.size()];
+    } else {
+      S2D_CUDA(cudaEventCreate(&e));
+      pev.push_back(e);
+    }
+    S2D_CUDA(cudaEventRecord(e, stream));
+    pev_phase.push_back(ph);
+  }
   void kev_mark() {
     if (!kev_on) return;
     if (kev_n >= kev.size()) {
@@ -297,11 +317,14 @@ class Engine : public EngineBase {
     const StripGeom& S0 = cart_S;
     if (!xhalo()) {
       kev_mark();
+      phase(PH_FORCE);
       launch_elem_strip_items<T>(strip_all_groups(S0), io, stream);
       kev_mark();
+      phase(PH_FOLD);
       launches += 1 + launch_strip_fold<T>(S0, io.f, cart_hx.p, cart_hz.p, npoin, stream);
       return;
     }
+    phase(PH_FORCE);
     if (!xh_fn && !xh_peer)
       throw StateError("this x-strip has neighbours: attach a halo exchange (s2d_halo_set_exchange or s2d_halo_set_peers) first");
     // boundary groups = the single-strip groups next to the interfaces
@@ -326,6 +349,7 @@ class Engine : public EngineBase {
       kev_mark();
       launches++;
     }
+    phase(PH_FOLD);
     S2D_CUDA(cudaStreamWaitEvent(xstream, xh_ev_b, 0));
     const int n2 = 2 * S0.LZ * ndof;
     const size_t nh = (size_t)S0.LZ * ndof;
@@ -420,6 +444,7 @@ class Engine : public EngineBase {
   }
   ~Engine() override {
     for (auto e : kev) cudaEventDestroy(e);
+    for (auto e : pev) cudaEventDestroy(e);
     if (xh_ev_b) cudaEventDestroy(xh_ev_b);
     if (xh_ev_x) cudaEventDestroy(xh_ev_x);
     if (xstream) cudaStreamDestroy(xstream);
@@ -1109,14 +1134,18 @@ class Engine : public EngineBase {
   }
   void launch_patch(const T* dd, const T* vv, T* ff) {
     switch (ngll) {
+#ifndef S2D_ONLY_N5
       case 3: launch_patch_n<3>(dd, vv, ff); break;
       case 4: launch_patch_n<4>(dd, vv, ff); break;
+#endif
       case 5: launch_patch_n<5>(dd, vv, ff); break;
+#ifndef S2D_ONLY_N5
       case 6: launch_patch_n<6>(dd, vv, ff); break;
       case 7: launch_patch_n<7>(dd, vv, ff); break;
       case 8: launch_patch_n<8>(dd, vv, ff); break;
       case 9: launch_patch_n<9>(dd, vv, ff); break;
       case 10: launch_patch_n<10>(dd, vv, ff); break;
+#endif
       default: throw ArgError("ngll must be in 3..10");
     }
   }
@@ -1220,6 +1249,7 @@ class Engine : public EngineBase {
   void launch_step_fused(bool last_of_call) {
     const size_t nd = npoin * ndof;
     const T dt = (T)scheme.dt;
+    phase(PH_PRED);
     k_tick<<<1, 1, 0, stream>>>(ctl.p);
     launches++;
     const bool nmk = scheme.kind == 1;
@@ -1248,8 +1278,11 @@ class Engine : public EngineBase {
     io.c3 = c3;
     io.a_in = a.p;
     launch_strips(io);
+    phase(PH_SRC);
     launch_sources(a.p);
+    phase(PH_BC);
     launch_bcs(dc);
+    phase(PH_UPDATE);
     const long long nw = (long long)ndrows * cart_S.LX + (long long)ndcols * cart_S.LZ;
     if (nw > 0) {
       k_strip_deferred<T><<<(unsigned)((nw + 255) / 256), 256, 0, stream>>>(
@@ -1259,7 +1292,9 @@ class Engine : public EngineBase {
     }
     dsel ^= 1;  // the caller now sees d[n]; the other buffer holds the prediction
     pred_valid = true;
+    phase(PH_OUT);
     launch_outputs();
+    phase(PH_COUNT);
   }
 
   void launch_step(bool last_of_call = true) {
@@ -1269,6 +1304,7 @@ class Engine : public EngineBase {
     }
     const size_t nd = npoin * ndof;
     const T dt = (T)scheme.dt;
+    phase(PH_PRED);
     k_tick<<<1, 1, 0, stream>>>(ctl.p);
     launches++;
     const int zf = needs_zero_f() ? 1 : 0;
@@ -1301,9 +1337,13 @@ class Engine : public EngineBase {
       }
     }
     launches++;
+    if (!cart_mode) phase(PH_FORCE);
     launch_fint(dforce, vforce, a.p);
+    phase(PH_SRC);
     launch_sources(a.p);
+    phase(PH_BC);
     launch_bcs(dn());  // BC_apply sees fields%displ / veloc (solver.f90:121), not the alpha-weighted copies
+    phase(PH_UPDATE);
     T c3, c4;
     if (scheme.kind == 0) {
       c3 = dt;
@@ -1314,7 +1354,9 @@ class Engine : public EngineBase {
     }
     k_correct<T><<<grid_for(nd), 256, 0, stream>>>(dn(), v.p, a.p, rmass.p, nd, c3, c4);
     launches++;
+    phase(PH_OUT);
     launch_outputs();
+    phase(PH_COUNT);
   }
 
   // Device-side aborts (ctl.err) are reported once: the flag is cleared, so that the next call is judged on its
@@ -1569,6 +1611,27 @@ class Engine : public EngineBase {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return ms / reps;
+  }
+  // average milliseconds per step of every phase (see the PH_* list) over nsteps steps
+  void time_phases(int nsteps, float* ms) override {
+    S2D_REQUIRE(committed && nsteps > 0 && ms, "time_phases: not committed, nsteps <= 0 or null pointer");
+    S2D_REQUIRE(h_src_iglob.empty() || src_ampli_cap > 0, "time_phases: call s2d_step once first to load the stf table");
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    pev_phase.clear();
+    pev_on = true;
+    for (int k = 0; k < nsteps; ++k) launch_step(k == nsteps - 1);
+    pev_on = false;
+    it += nsteps;
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    for (int q = 0; q < PH_COUNT; ++q) ms[q] = 0.f;
+    for (size_t q = 0; q + 1 < pev_phase.size(); ++q) {
+      if (pev_phase[q] >= PH_COUNT) continue;
+      float t = 0;
+      S2D_CUDA(cudaEventElapsedTime(&t, pev[q], pev[q + 1]));
+      ms[pev_phase[q]] += t;
+    }
+    for (int q = 0; q < PH_COUNT; ++q) ms[q] /= (float)nsteps;
+    check_device_error();
   }
   float time_steps(int nsteps) override {
     S2D_REQUIRE(committed && nsteps > 0, "time_steps: not committed or nsteps <= 0");

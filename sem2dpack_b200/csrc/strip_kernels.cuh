@@ -206,6 +206,9 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group
 #ifndef S2D_STRIP_STAGE
 #define S2D_STRIP_STAGE 7
 #endif
+#ifndef S2D_STRIP_ROT
+#define S2D_STRIP_ROT 0
+#endif
 // The coefficient block of an element row is one contiguous run of the strip layout: with all six planes
 // stored (7200 B per row of a P-SV strip) it is brought in by ONE TMA bulk copy per warp and row
 // (cp.async.bulk + mbarrier, SASS UBLKCP) instead of 15 per-lane LDGSTS.128, which cost 15.5 L1 wavefronts
@@ -317,11 +320,29 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     __syncthreads();
   }
   T(*tlw)[N][EPW * NP] = tile[warp];
-  T Hi[N], HTi[N];
+  // xi-contractions read the other lanes' columns from the warp tile.  S2D_STRIP_ROT: a lane's own column is
+  // already in its registers, so it reads only the other N-1, in a per-lane rotation m_k = (i + k) mod N
+  // (k = 1..N-1): a fifth fewer shared-memory wavefronts, the contraction's sum starts with the own term.
+  constexpr bool ROT = S2D_STRIP_ROT != 0;
+  constexpr int NR = ROT ? N - 1 : N;
+  T Hi[NR], HTi[NR], Hii = 0, HTii = 0;
+  int mo[ROT ? N - 1 : 1];
+  if (ROT) {
+    Hii = A.H[i + N * i];
+    HTii = Hii;
 #pragma unroll
-  for (int m = 0; m < N; ++m) {
-    Hi[m] = A.H[m + N * i];   // H(m,i)
-    HTi[m] = A.H[i + N * m];  // H(i,m)
+    for (int k = 1; k < N; ++k) {
+      const int m = (i + k) % N;
+      Hi[k - 1] = A.H[m + N * i];   // H(m,i)
+      HTi[k - 1] = A.H[i + N * m];  // H(i,m)
+      mo[k - 1] = el * N + m;
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < NR; ++m) {
+      Hi[m] = A.H[m + N * i];   // H(m,i)
+      HTi[m] = A.H[i + N * m];  // H(i,m)
+    }
   }
   T U[NDOF][N], Fc[NDOF];
   {
@@ -472,15 +493,14 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       for (int c = 0; c < NDOF; ++c)
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-          T row[N];  // the 5 lanes of an element read the same word: one wavefront per value
+          T row[NR];  // the 5 lanes of an element read the same word: one wavefront per value
 #pragma unroll
-          for (int m = 0; m < N; ++m) row[m] = tlw[c][j][el * N + m];
-          T s1 = 0, s2 = 0;
+          for (int m = 0; m < NR; ++m) row[m] = tlw[c][j][ROT ? mo[m] : el * N + m];
+          T s1 = ROT ? Hii * U[c][j] : (T)0, s2 = 0;
 #pragma unroll
-          for (int m = 0; m < N; ++m) {
-            s1 += Hi[m] * row[m];               // (Ht U)(i,j)
-            s2 += U[c][m] * A.H[m + N * j];     // (U H)(i,j)
-          }
+          for (int m = 0; m < NR; ++m) s1 += Hi[m] * row[m];                   // (Ht U)(i,j)
+#pragma unroll
+          for (int m = 0; m < N; ++m) s2 += U[c][m] * A.H[m + N * j];          // (U H)(i,j)
           gxi[c][j] = s1;
           get[c][j] = s2;
         }
@@ -530,15 +550,14 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       for (int c = 0; c < NDOF; ++c)
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-          T row[N];  // the 5 lanes of an element read the same word: one wavefront per value
+          T row[NR];
 #pragma unroll
-          for (int m = 0; m < N; ++m) row[m] = tlw[c][j][el * N + m];
-          T s1 = 0, s2 = 0;
+          for (int m = 0; m < NR; ++m) row[m] = tlw[c][j][ROT ? mo[m] : el * N + m];
+          T s1 = ROT ? HTii * tH[c][j] : (T)0, s2 = 0;
 #pragma unroll
-          for (int m = 0; m < N; ++m) {
-            s1 += HTi[m] * row[m];               // (H tH)(i,j)
-            s2 += tHt[c][m] * A.H[j + N * m];    // (tHt Ht)(i,j)
-          }
+          for (int m = 0; m < NR; ++m) s1 += HTi[m] * row[m];                  // (H tH)(i,j)
+#pragma unroll
+          for (int m = 0; m < N; ++m) s2 += tHt[c][m] * A.H[j + N * m];        // (tHt Ht)(i,j)
           f[c][j] = s1 + s2;
         }
       __syncwarp();
@@ -1008,14 +1027,18 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
     }                                                                                             \
   } break;
   switch (G.N) {
+#ifndef S2D_ONLY_N5
     S2D_STRIP_CASE(3)
     S2D_STRIP_CASE(4)
+#endif
     S2D_STRIP_CASE(5)
+#ifndef S2D_ONLY_N5
     S2D_STRIP_CASE(6)
     S2D_STRIP_CASE(7)
     S2D_STRIP_CASE(8)
     S2D_STRIP_CASE(9)
     S2D_STRIP_CASE(10)
+#endif
     default:
       throw ArgError("ngll must be in 3..10");
   }

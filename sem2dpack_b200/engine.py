@@ -228,6 +228,15 @@ class Engine:
         self._ck(self.L.s2d_time_steps(self.h, nsteps, C.byref(ms)))
         return ms.value
 
+    PHASES = ("predictor", "element_force", "halo_fold_exchange", "sources", "boundary_conditions", "node_update",
+              "outputs")
+
+    def time_phases(self, nsteps):
+        """average ms per step of each phase of a step (s2d_time_phases)"""
+        ms = (C.c_float * len(self.PHASES))()
+        self._ck(self.L.s2d_time_phases(self.h, nsteps, ms))
+        return dict(zip(self.PHASES, [float(x) for x in ms]))
+
     def kernel_ms(self):
         ms = C.c_float()
         self._ck(self.L.s2d_kernel_ms(self.h, C.byref(ms)))

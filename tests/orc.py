@@ -11,11 +11,13 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
-_LIB = None
+_LIB = {}
 
 
-def build_oracle(force=False):
-    so = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+def build_oracle(force=False, variant="parity"):
+    """variant "parity": -O2 -ffp-contract=off (what the parity tests compare against); "o3": -O3 -march=x86-64-v3
+    (bench.py's CPU legs only: BASELINE.md section 4's optimisation level)"""
+    so = os.path.join(ORACLE_DIR, "_build", "liboracle.so" if variant == "parity" else "liboracle_o3.so")
     srcs = [os.path.join(ORACLE_DIR, f) for f in
             ("oracle_capi.cpp", "sem2d_oracle.hpp", "gll.hpp", "rcm.hpp", "parinp.hpp")]
     stale = (not os.path.exists(so)) or any(
@@ -25,10 +27,9 @@ def build_oracle(force=False):
     return so
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        L = C.CDLL(build_oracle())
+def lib(variant="parity"):
+    if variant not in _LIB:
+        L = C.CDLL(build_oracle(variant=variant))
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_char_p, C.c_ulonglong, C.c_int, C.c_int, C.c_char_p, C.c_int]
         L.orc_create_at.restype = C.c_void_p
@@ -54,8 +55,8 @@ def lib():
         L.orc_rcm.argtypes = [C.c_int, C.c_int, C.c_void_p]
         L.orc_hash_u.restype = C.c_double
         L.orc_hash_u.argtypes = [C.c_ulonglong] * 4
-        _LIB = L
-    return _LIB
+        _LIB[variant] = L
+    return _LIB[variant]
 
 
 _DT = {b"i": np.int32, b"d": np.float64, b"f": np.float32}
@@ -64,10 +65,11 @@ _DT = {b"i": np.int32, b"d": np.float64, b"f": np.float32}
 class Oracle:
     """One SEM2DPACK problem built from Par.inp text and advanced on the CPU."""
 
-    def __init__(self, parinp_text, synthetic_seed=0, renumber=True, kd_force_kd1=False, lattice_origin=(0, 0)):
+    def __init__(self, parinp_text, synthetic_seed=0, renumber=True, kd_force_kd1=False, lattice_origin=(0, 0),
+                 variant="parity"):
         """lattice_origin: GLL lattice coordinates of this mesh's corner inside a larger synthetic mesh (the hash
         medium is a function of global lattice coordinates), for windowed parity checks"""
-        self.L = lib()
+        self.L = lib(variant)
         err = C.create_string_buffer(512)
         self.h = self.L.orc_create_at(parinp_text.encode(), synthetic_seed, int(renumber), int(kd_force_kd1),
                                       int(lattice_origin[0]), int(lattice_origin[1]), err, 512)

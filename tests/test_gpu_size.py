@@ -38,7 +38,7 @@ def _bench_engine(nx, nz, nsteps, scheme_kind=0, src=None, coef_mode=0):
 def test_whole_mesh_vs_oracle_at_size(n, nsteps, scheme):
     src = (0.37 * n * H, 0.61 * n * H)
     e = _bench_engine(n, n, nsteps, 0 if scheme == "leapfrog" else 1, src)
-    w = window.Window(0, 0, n, n, n, n, n // 2, e.dt, nsteps, SEED, FILL, scheme=scheme, src=src)
+    w = window.Window(0, 0, n, n, n, n, n // 2, e.dt, nsteps, SEED, FILL, scheme=scheme, src=src, half_nuc=HALF_NUC)
     assert w.o.i("npoin") == e.npoin
     e.step(nsteps, w.stf_table(nsteps))
     ed, ev, nn = w.compare(e)
@@ -59,10 +59,11 @@ def test_benchmark_mesh_windows_vs_oracle():
     src = (N * H / 2 + 330.0, ez * H + 710.0)
     e = _bench_engine(N, N, k, 0, src)
     assert e.npoin * 2 > 2 ** 31
-    wins = [window.Window(ez - 24, ez - 24, 48, 48, N, N, ez, e.dt, k, SEED, FILL, src=src),     # fault + source
-            window.Window(N - 40, N - 40, 40, 40, N, N, ez, e.dt, k, SEED, FILL),                 # top-right corner
-            window.Window(0, 0, 40, 40, N, N, ez, e.dt, k, SEED, FILL),                           # bottom-left corner
-            window.Window(2037, ez - 20, 44, 40, N, N, ez, e.dt, k, SEED, FILL)]                  # fault away from the patch
+    kw = dict(half_nuc=HALF_NUC)
+    wins = [window.Window(ez - 24, ez - 24, 48, 48, N, N, ez, e.dt, k, SEED, FILL, src=src, half_nuc=HALF_NUC),     # fault + source
+            window.Window(N - 40, N - 40, 40, 40, N, N, ez, e.dt, k, SEED, FILL, **kw),                 # top-right corner
+            window.Window(0, 0, 40, 40, N, N, ez, e.dt, k, SEED, FILL, **kw),                           # bottom-left corner
+            window.Window(2037, ez - 20, 44, 40, N, N, ez, e.dt, k, SEED, FILL, **kw)]                  # fault away from the patch
     e.step(k, wins[0].stf_table(k))
     for w in wins:
         ed, ev, nn = w.compare(e)

@@ -76,11 +76,11 @@ class Window:
     """the oracle on one window, its node -> lattice map, and the comparison with an engine"""
 
     def __init__(self, X0, Z0, nxw, nzw, NX, NZ, ezflt_g, dt, nsteps, seed, fill, ngll=5, scheme="leapfrog", src=None,
-                 ix0=0):
+                 ix0=0, half_nuc=1500.0):
         """fill = (seed, amp_d, amp_v) of s2d_cart_fill_fields; ix0 = lattice column of the engine's first column
         inside the global mesh (x-strips)"""
         self.X0, self.Z0, self.nxw, self.nzw, self.N = X0, Z0, nxw, nzw, ngll
-        deck, ez, sides = window_deck(X0, Z0, nxw, nzw, NX, NZ, ezflt_g, dt, nsteps, ngll, scheme, src)
+        deck, ez, sides = window_deck(X0, Z0, nxw, nzw, NX, NZ, ezflt_g, dt, nsteps, ngll, scheme, src, half_nuc)
         self.ez, self.sides, self.nsteps = ez, sides, nsteps
         N1 = ngll - 1
         self.o = o = orc.Oracle(deck, synthetic_seed=seed, renumber=False, lattice_origin=(X0 * N1, Z0 * N1))
