@@ -177,8 +177,8 @@ def attach_halo(e, rank, world, args, torch, dist):
 
 def xdev_check(rank, world, local, args, torch, dist, sync_dt):
     """Cross-device evidence: a small global mesh stepped as `world` x-strips on `world` GPUs and
-    as ONE box on rank 0, same dt / fault / absorbing sides / source / seeded state.  Rank 0 compares bit for
-    bit: the two copies of every interface column, every strip against the box, and the fault state."""
+    as ONE box on rank 0, same dt / fault / absorbing sides / source / seeded state.  Rank 0 compares the two
+    copies of every interface column bit for bit, and every strip and its fault state against the box."""
     import numpy as np
     from sem2dpack_b200.stf import Ricker
     nxs, nzs, k = 48, 40, 30
@@ -216,20 +216,24 @@ def xdev_check(rank, world, local, args, torch, dist, sync_dt):
         gD, gV = gs["D"].reshape(NDOF, -1), gs["V"].reshape(NDOF, -1)
         g.close()
         iface = all(np.array_equal(allp[r][q][:, :, -1], allp[r + 1][q][:, :, 0]) for r in range(world - 1) for q in "dv")
-        whole, fault, worst = True, True, 0.0
+        worst, fworst = 0.0, 0.0
         for r in range(world):
             x0 = r * nxs * (NGLL - 1)
             for q, ref in (("d", gd), ("v", gv)):
                 a, b = allp[r][q], ref[:, :, x0:x0 + LXs]
-                whole = whole and np.array_equal(a, b)
                 worst = max(worst, float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)))
             for q, ref in (("D", gD), ("V", gV)):
-                fault = fault and np.array_equal(allp[r][q], ref[:, x0:x0 + LXs])
+                a, b = allp[r][q], ref[:, x0:x0 + LXs]
+                fworst = max(fworst, float(np.abs(a - b).max() / max(np.abs(ref).max(), 1e-300)))
+        # The two copies of an interface node add the same two addends (own + neighbour's partial sum) and must be
+        # bit-identical.  Strips against the one box agree to rounding only: a node shared by four elements is
+        # summed as (upper-left + lower-left) + (upper-right + lower-right) across a CTA-group / GPU boundary and
+        # as (upper-left + upper-right) + (lower-left + lower-right) inside a group, and the groups fall elsewhere.
         res = {"mesh": f"{nxg}x{nzs} elements as {world} x-strips of {nxs}x{nzs} on {world} GPUs vs one box on rank 0",
-               "steps": k, "interface_copies_bitwise_equal": bool(iface), "strips_equal_box_bitwise": bool(whole),
-               "fault_state_bitwise_equal": bool(fault), "max_rel_diff": worst,
+               "steps": k, "interface_copies_bitwise_equal": bool(iface), "strips_vs_box_max_rel_diff": worst,
+               "fault_state_max_rel_diff": fworst, "tolerance": 1e-11,
                "vmax": float(np.abs(gv).max()), "slip_max": float(np.abs(gD).max()),
-               "pass": bool(iface and whole and fault)}
+               "pass": bool(iface and worst <= 1e-11 and fworst <= 1e-11)}
     flag = torch.tensor([1 if (res is None or res["pass"]) else 0], dtype=torch.int32, device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if res is not None:

@@ -203,6 +203,22 @@ int s2d_energy(s2d_handle h, double* E_k);
  * by S2D_ASM_COLOR; computed on the device side of the library.  color(nelem). */
 int s2d_get_coloring(s2d_handle h, int32_t* ncolors, int32_t* color);
 
+/* ---- kernel routing ---------------------------------------------------------------------- */
+/* s2d_commit looks at the topology of ibool: a MESH_CART box (CART_build, mesh_cartesian.f90:219-314) in ANY
+ * element order -- in particular the RCM order the reference uses by default (OPT_RENUMBER, constants.f90:11;
+ * MESH_STRUCTURED_renumber, mesh_structured.f90:204-269) -- with or without the split-node row of `ezflt`, flat
+ * coefficient planes (nelast 2 | 6) and the OPT_NGLL choice of kd2, is moved onto the GLL lattice and runs on the
+ * z-marching strip kernel, exactly like a builder-made box; everything else keeps the any-mesh kernels.  The API
+ * keeps the caller's node and element numbering either way.  S2D_ROUTE_STRIP=0 (environment) disables the routing.
+ * route: 0 = any-mesh kernel (patch / colour / atomic variant), 1 = strip kernel. */
+int s2d_kernel_route(s2d_handle h, int32_t* route);
+/* The recognition on its own (host only, no device needed): nx = nz = 0 when ibool is not such a box; otherwise the
+ * box, the number of element rows below the split-node row (ezflt, 0 = none), the position (ex, ez)(nelem) of
+ * every element and the GLL lattice position (gx, gz)(npoin) of every node, 0-based; gz counts the duplicated
+ * fault row.  lower_hint: a node of the lower block (node1 of a two-sided fault) or 0.  Pointers may be NULL. */
+int s2d_detect_structured(int32_t ngll, int32_t nelem, int32_t npoin, const int32_t* ibool, int32_t lower_hint,
+                          int32_t* nx, int32_t* nz, int32_t* ezflt, int32_t* ex, int32_t* ez, int32_t* gx, int32_t* gz);
+
 /* ---- measurement hooks ------------------------------------------------------------------- */
 /* Times `reps` launches of the element-force+assembly stage alone (CUDA events on the engine's
  * stream), fields untouched apart from accel; returns average milliseconds per launch. */

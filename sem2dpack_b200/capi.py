@@ -104,6 +104,9 @@ _SIGS = {
     "s2d_time_fint": [C.c_void_p, C.c_int32, C.POINTER(C.c_float)],
     "s2d_time_steps": [C.c_void_p, C.c_int32, C.POINTER(C.c_float)],
     "s2d_kernel_ms": [C.c_void_p, C.POINTER(C.c_float)],
+    "s2d_kernel_route": [C.c_void_p, C.POINTER(C.c_int32)],
+    "s2d_detect_structured": [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
+                              C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "s2d_time_phases": [C.c_void_p, C.c_int32, C.c_void_p],
     "s2d_launch_count": [C.c_void_p, C.POINTER(C.c_int64)],
     "s2d_stream": [C.c_void_p, C.POINTER(C.c_void_p)],

@@ -62,6 +62,31 @@ __global__ void k_correct(T* __restrict__ d, T* __restrict__ v, T* __restrict__ 
   }
 }
 
+template <typename T>
+__global__ void k_fill_n(T* x, size_t n, T val) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) x[q] = val;
+}
+// caller's node numbering <-> GLL lattice through an index table (generic handles routed to the strip kernel):
+// to_ref: ref[k] = lat[lat_of[k]], else lat[lat_of[k]] = ref[k]
+template <typename TS, typename TD>
+__global__ void k_lat_permute(const TS* __restrict__ src, TD* __restrict__ dst, const int* __restrict__ lat_of,
+                              size_t np_ref, size_t np_lat, int ncomp, int to_ref) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < np_ref; k += stride) {
+    const size_t l = (size_t)lat_of[k];
+    for (int c = 0; c < ncomp; ++c) {
+      if (to_ref) dst[k + np_ref * c] = (TD)src[l + np_lat * c];
+      else dst[l + np_lat * c] = (TD)src[k + np_ref * c];
+    }
+  }
+}
+static __global__ void k_remap_ids(int* ids, size_t n, const int* __restrict__ lat_of) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
+    if (ids[q] > 0) ids[q] = lat_of[ids[q] - 1] + 1;
+}
+
 // rmass = 1/M once every boundary condition has had its say on M (init.f90:112-116)
 template <typename T>
 __global__ void k_invert(T* x, size_t n) {

@@ -452,26 +452,7 @@ static void cart_build(Engine<T>& E, CartState& S) {
   k_fill<T><<<(unsigned)std::min<size_t>((E.rmass.n + 255) / 256, 148 * 32), 256, 0, st>>>(E.rmass.p, E.rmass.n, (T)1);
   k_cart_mass<T><<<nblk, 256, 0, st>>>(G, E.rmass.p, E.npoin);
   S2D_CUDA(cudaGetLastError());
-  // halo arrays of the strip kernel
-  E.cart_S = G.S;
-  E.cart_hx.alloc((size_t)G.ndof * std::max(G.S.ngroups - 1, 0) * G.S.LZ + 1);
-  E.cart_hz.alloc((size_t)G.ndof * G.S.nseg * G.S.nstrips * G.S.WL + 1);
-  E.cart_hx.zero(st);
-  E.cart_hz.zero(st);
-  E.cart_meet.alloc((size_t)G.S.nseg * std::max(G.S.ngroups - 1, 1));
-  E.cart_meet.zero(st);
-  // deferred nodes of the fused step that come from the decomposition itself: rows shared by two
-  // bands, columns shared by two groups, GPU interface columns
-  E.h_rowflag.assign(G.S.LZ, 0);
-  E.h_colflag.assign(G.S.LX, 0);
-  for (int gz = 0; gz < G.S.LZ; ++gz)
-    if (strip_shared_row_seg(G.S, gz) >= 0) E.h_rowflag[gz] = 1;
-  for (int hb = 0; hb + 1 < G.S.ngroups; ++hb) {
-    int sr;
-    E.h_colflag[strip_halo_col(G.S, hb, sr)] = 2;  // not finished by its owner lane, but inside the strip kernel
-  }
-  if (G.halo_left) E.h_colflag[0] = 1;
-  if (G.halo_right) E.h_colflag[G.S.LX - 1] = 1;
+  E.init_strip_tables(G.S);  // halo arrays and decomposition flags of the strip kernel
   const CartGeom Gc = G;
   Engine<T>* Ep = &E;
   E.cart_to_ref = [Ep, Gc, nblk](const T* lat, double* ref) {
@@ -585,33 +566,7 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
     G.halo_right = D->halo_right;
     gll_tables(G.N, G.xgll, G.wgll, S->H);
     // strip decomposition of the z-marching kernel (strip_kernels.cuh)
-    {
-      StripGeom& Q = G.S;
-      Q.N = G.N;
-      Q.ndof = G.ndof;
-      Q.nx = G.nx;
-      Q.nz = G.nz;
-      Q.ezflt = G.ezflt;
-      Q.EPW = 32 / G.N;
-      Q.W = Q.EPW * (G.N - 1);
-      Q.WL = Q.W + 1;
-      Q.nstrips = (G.nx + Q.EPW - 1) / Q.EPW;
-      Q.SEG = std::max(1, env_int("S2D_SEG", 32));
-      Q.SEG = std::min(Q.SEG, (32 * STRIP_MASK_WORDS - 2) / (G.N - 1));  // rows of a band fit the kernel's row mask
-      Q.nseg_lo = G.ezflt > 0 ? (G.ezflt + Q.SEG - 1) / Q.SEG : 0;
-      Q.nseg = Q.nseg_lo + (G.nz - G.ezflt + Q.SEG - 1) / Q.SEG;
-      Q.LX = G.nx * (G.N - 1) + 1;
-      Q.LXP = (Q.LX + 1 + 7) / 8 * 8;  // rows start on 32-byte sectors (FP32: 8 elements), one spare column for 16-byte bulk copies
-      Q.LZ = G.nz * (G.N - 1) + 1 + (G.ezflt > 0 ? 1 : 0);
-      Q.xhalo_left = G.halo_left ? 1 : 0;
-      Q.xhalo_right = G.halo_right ? 1 : 0;
-      // one CTA = a group of adjacent strips; the strips next to a GPU interface form groups of their own
-      strip_set_groups(Q, strip_warps(), G.halo_left != 0, G.halo_right != 0);
-      Q.it_g0 = 0;
-      Q.it_ng = Q.ngroups;
-      Q.it_step = 1;
-      Q.nitems = (long long)Q.nseg * Q.ngroups;
-    }
+    G.S = make_strip_geom(G.N, G.ndof, G.nx, G.nz, G.ezflt, env_int("S2D_SEG", 32), G.halo_left != 0, G.halo_right != 0);
     const long long npoin = cart_npoin(G);
     const long long nelem = (long long)G.nx * G.nz;
     if (npoin != (long long)G.S.LX * G.S.LZ) {
@@ -1304,12 +1259,6 @@ int s2d_cart_get_window(s2d_handle h, int32_t gx0, int32_t gz0, int32_t nwx, int
   CART_GUARD_END
 }
 
-int s2d_kernel_ms(s2d_handle h, float* ms) {
-  CART_GUARD_BEGIN
-  S2D_REQUIRE(ms != nullptr, "s2d_kernel_ms: null pointer");
-  *ms = Eb->kernel_ms();
-  CART_GUARD_END
-}
 int s2d_halo_info(s2d_handle h, int64_t* count, void** send_dev, void** recv_dev) {
   CART_GUARD_BEGIN
   Eb->halo_info(count, send_dev, recv_dev);

@@ -245,6 +245,34 @@ int s2d_time_steps(s2d_handle h, int32_t nsteps, float* ms_total) {
     *ms_total = E.time_steps(nsteps);
   });
 }
+int s2d_detect_structured(int32_t ngll, int32_t nelem, int32_t npoin, const int32_t* ibool, int32_t lower_hint,
+                          int32_t* nx, int32_t* nz, int32_t* ezflt, int32_t* ex, int32_t* ez, int32_t* gx, int32_t* gz) {
+  if (!ibool || ngll < 3 || ngll > 10 || nelem < 1 || npoin < 1) return S2D_EINVAL;
+  for (size_t q = 0; q < (size_t)nelem * ngll * ngll; ++q)
+    if (ibool[q] < 1 || ibool[q] > npoin) return S2D_EINVAL;
+  StructuredBox B = detect_structured(ibool, ngll, nelem, (size_t)npoin, lower_hint);
+  if (nx) *nx = B.ok ? B.nx : 0;
+  if (nz) *nz = B.ok ? B.nz : 0;
+  if (ezflt) *ezflt = B.ok ? B.ezflt : 0;
+  if (!B.ok) return S2D_OK;
+  if (ex) std::copy(B.ex.begin(), B.ex.end(), ex);
+  if (ez) std::copy(B.ez.begin(), B.ez.end(), ez);
+  if (gx) std::copy(B.gx.begin(), B.gx.end(), gx);
+  if (gz) std::copy(B.gz.begin(), B.gz.end(), gz);
+  return S2D_OK;
+}
+int s2d_kernel_route(s2d_handle h, int32_t* route) {
+  return guard(h, [&](EngineBase& E) {
+    S2D_REQUIRE(route != nullptr, "s2d_kernel_route: null pointer");
+    *route = E.route();
+  });
+}
+int s2d_kernel_ms(s2d_handle h, float* ms) {
+  return guard(h, [&](EngineBase& E) {
+    S2D_REQUIRE(ms != nullptr, "s2d_kernel_ms: null pointer");
+    *ms = E.kernel_ms();
+  });
+}
 int s2d_time_phases(s2d_handle h, int32_t nsteps, float* ms_phase) {
   return guard(h, [&](EngineBase& E) { E.time_phases(nsteps, ms_phase); });
 }

@@ -12,6 +12,7 @@
 #include "elem_kernels.cuh"
 #include "plan.hpp"
 #include "strip_kernels.cuh"
+#include "structured.hpp"
 
 namespace s2d {
 
@@ -104,6 +105,7 @@ class EngineBase {
   virtual void time_phases(int nsteps, float* ms) = 0;
   float last_kernel_ms_base = 0.f;
   virtual float kernel_ms() = 0;
+  virtual int route() = 0;
   virtual void halo_info(int64_t* count, void** send_dev, void** recv_dev) = 0;
   virtual void halo_set_exchange(s2d_exchange_fn fn, void* user) = 0;
   virtual void halo_peer_buffers(void** recv_dev, void** flags_dev) = 0;
@@ -481,6 +483,7 @@ class Engine : public EngineBase {
     if (nkv > 0) {
       elem2kv.upload(h_elem2kv);
       upload_as(eta, eta_, (size_t)ngll * ngll * nkv);
+      h_eta.assign(eta_, eta_ + (size_t)ngll * ngll * nkv);
     }
   }
   // mass(npoin) in the caller's numbering; builder-made engines keep it on the lattice like every field
@@ -609,6 +612,7 @@ class Engine : public EngineBase {
     };
     b->node1.upload(D.node1, np);
     F.node1 = b->node1.p;
+    h_fault_node1.push_back(D.node1[0]);
     h_bc_nodes.emplace_back(D.node1, D.node1 + np);
     if (D.node2) h_bc_nodes.emplace_back(D.node2, D.node2 + np);
     if (D.node2) {
@@ -880,6 +884,171 @@ class Engine : public EngineBase {
     R.sis = rec.sis.p;
   }
 
+  // ---- strip-kernel tables ---------------------------------------------------------------
+  // halo arrays of the strip kernel and the deferred nodes of the fused step that come from the decomposition
+  // itself: rows shared by two bands, columns shared by two groups, GPU interface columns
+  void init_strip_tables(const StripGeom& S) {
+    cart_S = S;
+    cart_hx.alloc((size_t)ndof * std::max(S.ngroups - 1, 0) * S.LZ + 1);
+    cart_hz.alloc((size_t)ndof * S.nseg * S.nstrips * S.WL + 1);
+    cart_hx.zero(stream);
+    cart_hz.zero(stream);
+    cart_meet.alloc((size_t)S.nseg * std::max(S.ngroups - 1, 1));
+    cart_meet.zero(stream);
+    h_rowflag.assign(S.LZ, 0);
+    h_colflag.assign(S.LX, 0);
+    for (int gz = 0; gz < S.LZ; ++gz)
+      if (strip_shared_row_seg(S, gz) >= 0) h_rowflag[gz] = 1;
+    for (int hb = 0; hb + 1 < S.ngroups; ++hb) {
+      int sr;
+      h_colflag[strip_halo_col(S, hb, sr)] = 2;  // not finished by its owner lane, but inside the strip kernel
+    }
+    if (S.xhalo_left) h_colflag[0] = 1;
+    if (S.xhalo_right) h_colflag[S.LX - 1] = 1;
+  }
+
+  // A structured box handed over through the generic API (s2d_create with the Fortran host's RCM-ordered ibool,
+  // s2d_set_elastic with its coefficient blocks): recognised from the topology (structured.hpp) and moved onto the
+  // GLL lattice, so that it runs on the z-marching strip kernel like a builder-made box.  Everything that was
+  // uploaded in the caller's node numbering -- fields, inverse mass, boundary node lists, sources, receivers -- is
+  // re-indexed once, here; the API keeps the caller's numbering (cart_to_ref / cart_from_ref).
+  bool routed = false;      // generic handle running on the strip kernel
+  bool have_colors = false;
+  DevBuf<int> lat_of;       // (npoin_ref) 0-based lattice index of every caller node
+  std::vector<int32_t> h_lat_of;
+  bool try_route_to_strips() {
+    if (cart_mode || variant != S2D_ASM_PATCH || env_int("S2D_ROUTE_STRIP", 1) == 0) return false;
+    if (!(nelast == 2 || nelast == 6)) return false;          // flat-grid planes only (mat_elastic.f90:255-268)
+    if (ndof == 2 && kd2 != (ngll == 5 ? 1 : 0)) return false;  // the strip kernel follows OPT_NGLL (mat_elastic.f90:412)
+    if (nkv > 0 && !strip_kv_ok()) return false;
+    int32_t hint = 0;
+    for (auto& r : bc_order)
+      if (r.kind == BC_DYNFLT && faults[r.index]->dev.two_sides && !h_fault_node1.empty()) {
+        hint = h_fault_node1[r.index];
+        break;
+      }
+    StructuredBox B = detect_structured(h_ibool.data(), ngll, nelem, npoin, hint);
+    if (!B.ok) return false;
+    const StripGeom S = make_strip_geom(ngll, ndof, B.nx, B.nz, B.ezflt, env_int("S2D_SEG", 32), false, false);
+    const size_t nlat = (size_t)S.LXP * S.LZ, nref = npoin;
+    if (nlat > 2147483647ull) return false;
+    // The fused update reads ONE inverse mass per node for the nodes no boundary condition touches (the reference's
+    // mass has equal columns there, mat_mass.f90:56-57; only BC_ABSO_init / BC_PERIO_init change single columns).
+    // A caller whose rmass differs between components elsewhere keeps the any-mesh kernels.
+    if (ndof == 2) {
+      std::vector<T> hr = rmass.to_host();
+      std::vector<uint8_t> touched(nref, 0);
+      for (auto& L : h_bc_nodes)
+        for (int32_t nd : L) touched[(size_t)nd - 1] = 1;
+      for (size_t k = 0; k < nref; ++k)
+        if (!touched[k] && hr[k] != hr[k + nref]) return false;
+    }
+    h_lat_of.resize(nref);
+    for (size_t k = 0; k < nref; ++k) h_lat_of[k] = (int32_t)((size_t)B.gz[k] * S.LXP + B.gx[k]);
+    lat_of.upload(h_lat_of);
+    // fields and inverse mass onto the lattice (pad columns: zero fields, unit inverse mass)
+    auto relayout = [&](DevBuf<T>& buf, T padval) {
+      DevBuf<T> nb;
+      nb.alloc(nlat * ndof);
+      k_fill_n<T><<<grid_for(nb.n), 256, 0, stream>>>(nb.p, nb.n, padval);
+      k_lat_permute<T, T><<<grid_for(nref), 256, 0, stream>>>(buf.p, nb.p, lat_of.p, nref, nlat, ndof, 0);
+      S2D_CUDA(cudaStreamSynchronize(stream));
+      buf = std::move(nb);
+    };
+    relayout(d, (T)0);
+    relayout(v, (T)0);
+    relayout(a, (T)0);
+    relayout(rmass, (T)1);
+    if (mass.n == nref) {
+      DevBuf<double> nb;
+      nb.alloc(nlat);
+      nb.zero(stream);
+      k_lat_permute<double, double><<<grid_for(nref), 256, 0, stream>>>(mass.p, nb.p, lat_of.p, nref, nlat, 1, 0);
+      S2D_CUDA(cudaStreamSynchronize(stream));
+      mass = std::move(nb);
+    }
+    // coefficient planes in the strip layout, all nelast planes stored (what matwrk_elast_type%a holds)
+    {
+      const int N = ngll, n2 = N * N;
+      std::vector<T> pc((size_t)nelem * nelast * n2);
+      for (int e = 0; e < nelem; ++e) {
+        const double* src = h_coef.data() + (size_t)h_elem2set[e] * nelast * n2;
+        for (int pl = 0; pl < nelast; ++pl)
+          for (int j = 0; j < N; ++j)
+            for (int i = 0; i < N; ++i)
+              pc[strip_coef_index(S, nelast, B.ex[e], B.ez[e], i, j, pl)] = (T)src[(size_t)pl * n2 + i + N * j];
+      }
+      p_coef.upload(pc);
+      if (nkv > 0) {  // eta(ngll,ngll) of the Kelvin-Voigt elements, zero elsewhere (mat_kelvin_voigt.f90:137-150)
+        std::vector<T> pe((size_t)nelem * n2, (T)0);
+        for (int e = 0; e < nelem; ++e) {
+          if (h_elem2kv[e] < 0) continue;
+          for (int j = 0; j < N; ++j)
+            for (int i = 0; i < N; ++i)
+              pe[strip_scalar_index(S, B.ex[e], B.ez[e], i, j)] = (T)h_eta[(size_t)h_elem2kv[e] * n2 + i + N * j];
+        }
+        strip_eta.upload(pe);
+      }
+    }
+    // node ids held by the boundary conditions, sources and receivers
+    auto remap_dev = [&](DevBuf<int>& ids) {
+      if (ids.n == 0) return;
+      k_remap_ids<<<grid_for(ids.n), 256, 0, stream>>>(ids.p, ids.n, lat_of.p);
+    };
+    auto remap_host = [&](std::vector<int32_t>& ids) {
+      for (auto& x : ids)
+        if (x > 0) x = h_lat_of[(size_t)x - 1] + 1;
+    };
+    for (auto& b : abso) remap_dev(b->node);
+    for (auto& b : dirneu) remap_dev(b->node);
+    for (auto& b : faults) {
+      remap_dev(b->node1);
+      remap_dev(b->node2);
+    }
+    for (auto& b : perio) {
+      remap_dev(b->master);
+      remap_dev(b->slave);
+    }
+    remap_dev(rec.iglob);
+    remap_dev(rec.nodes);
+    remap_dev(ibool);  // interpolated receivers read the nodes of their element from it
+    for (auto& L : h_bc_nodes) remap_host(L);
+    remap_host(h_src_iglob);
+    remap_host(h_mom_node);
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    npoin_ref = nref;
+    npoin = nlat;
+    cart_mode = true;
+    routed = true;
+    rmass_is_inverse = true;
+    cart_compact = 0;
+    p_hetero = true;
+    init_strip_tables(S);
+    Engine<T>* Ep = this;
+    cart_to_ref = [Ep](const T* lat, double* ref) {
+      k_lat_permute<T, double><<<Ep->grid_for(Ep->npoin_ref), 256, 0, Ep->stream>>>(lat, ref, Ep->lat_of.p, Ep->npoin_ref, Ep->npoin, Ep->ndof, 1);
+      S2D_CUDA(cudaGetLastError());
+    };
+    cart_from_ref = [Ep](const double* ref, T* lat) {
+      k_lat_permute<double, T><<<Ep->grid_for(Ep->npoin_ref), 256, 0, Ep->stream>>>(ref, lat, Ep->lat_of.p, Ep->npoin_ref, Ep->npoin, Ep->ndof, 0);
+      S2D_CUDA(cudaGetLastError());
+    };
+    cart_from_ref1 = [Ep](const double* ref, T* lat) {
+      k_lat_permute<double, T><<<Ep->grid_for(Ep->npoin_ref), 256, 0, Ep->stream>>>(ref, lat, Ep->lat_of.p, Ep->npoin_ref, Ep->npoin, 1, 0);
+      S2D_CUDA(cudaGetLastError());
+    };
+    cart_from_ref1d = [Ep](const double* ref, double* lat) {
+      k_lat_permute<double, double><<<Ep->grid_for(Ep->npoin_ref), 256, 0, Ep->stream>>>(ref, lat, Ep->lat_of.p, Ep->npoin_ref, Ep->npoin, 1, 0);
+      S2D_CUDA(cudaGetLastError());
+    };
+    return true;
+  }
+  bool rmass_is_inverse = false;
+  std::vector<int32_t> h_fault_node1;  // first node1 of every fault (which side of a split-node row is the lower one)
+  std::vector<double> h_eta;
+  DevBuf<T> strip_eta;                 // Kelvin-Voigt eta per element GLL point in the strip layout (zero off the KV elements)
+  static bool strip_kv_ok() { return false; }  // until the strip kernel carries the element-wise d + eta*v
+
   // ---- planning ------------------------------------------------------------------------
   // Deferred nodes of the fused step: halo rows / columns (flagged by the builder) plus every node a
   // boundary condition or a source touches.  A list that runs along one lattice column flags that
@@ -1010,16 +1179,20 @@ class Engine : public EngineBase {
     S2D_REQUIRE(nelast > 0, "commit: s2d_set_elastic was not called");
     S2D_REQUIRE(variant_ >= 0 && variant_ <= 2, "commit: unknown assembly variant");
     variant = variant_;
+    if (!cart_mode) {
+      if (nkv == 0) h_elem2kv.assign(nelem, -1);
+      build_color_plan();  // s2d_get_coloring (and S2D_ASM_COLOR)
+      have_colors = true;
+      try_route_to_strips();
+    }
     if (cart_mode) {
       S2D_REQUIRE(variant == S2D_ASM_PATCH, "commit: the structured builder only provides the strip kernel");
-      k_invert<T><<<grid_for(rmass.n), 256, 0, stream>>>(rmass.p, rmass.n);
+      if (!rmass_is_inverse) k_invert<T><<<grid_for(rmass.n), 256, 0, stream>>>(rmass.p, rmass.n);
       // the node update rides in the strip kernel for leapfrog and for the explicit Newmark scheme (beta = 0)
       fused = (scheme.kind == 0 || (scheme.kind == 1 && scheme.beta == 0.0)) && env_int("S2D_FUSED", 1) != 0 &&
               cart_kv_eta.n == 0;  // the fused update reads d only: Kelvin-Voigt boxes take the separate passes
       if (fused) build_deferred_tables();
     } else {
-      if (nkv == 0) h_elem2kv.assign(nelem, -1);
-      build_color_plan();
       if (variant == S2D_ASM_PATCH) build_patch_plan_dev();
     }
     build_source_terms();
@@ -1552,12 +1725,13 @@ class Engine : public EngineBase {
   }
   void get_coloring(int32_t* nc, int32_t* color) override {
     S2D_REQUIRE(committed, "get_coloring before commit");
-    S2D_REQUIRE(!cart_mode, "get_coloring: not available for builder-made meshes");
+    S2D_REQUIRE(have_colors, "get_coloring: not available for builder-made meshes");
     if (nc) *nc = ncolors;
     if (color) std::copy(h_color.begin(), h_color.end(), color);
   }
 
   float kernel_ms() override { return last_kernel_ms; }
+  int route() override { return cart_mode ? 1 : 0; }
   void halo_info(int64_t* count, void** send_dev, void** recv_dev) override {
     S2D_REQUIRE(cart_mode, "halo_info: only x-strips made by the structured builder have halos");
     xhalo_setup();

@@ -85,6 +85,38 @@ inline void strip_set_groups(StripGeom& G, int GW, bool lead, bool tail) {
   G.ngroups = G.g_lead + (nmid + GW - 1) / GW + G.g_tail;
 }
 
+constexpr int STRIP_MASK_WORDS = 128;  // a band has at most 32*128 lattice rows (make_strip_geom clamps SEG)
+// lattice / strip decomposition of an nx x nz box (split-node row after element row ezflt); one CTA = a group of
+// adjacent strips, the strips next to a GPU interface form groups of their own
+inline StripGeom make_strip_geom(int N, int ndof, int nx, int nz, int ezflt, int seg, bool halo_left, bool halo_right,
+                                 int warps = 4) {
+  StripGeom Q{};
+  Q.N = N;
+  Q.ndof = ndof;
+  Q.nx = nx;
+  Q.nz = nz;
+  Q.ezflt = ezflt;
+  Q.EPW = 32 / N;
+  Q.W = Q.EPW * (N - 1);
+  Q.WL = Q.W + 1;
+  Q.nstrips = (nx + Q.EPW - 1) / Q.EPW;
+  Q.SEG = seg > 1 ? seg : 1;
+  if (Q.SEG > (32 * STRIP_MASK_WORDS - 2) / (N - 1)) Q.SEG = (32 * STRIP_MASK_WORDS - 2) / (N - 1);  // the kernel's row mask
+  Q.nseg_lo = ezflt > 0 ? (ezflt + Q.SEG - 1) / Q.SEG : 0;
+  Q.nseg = Q.nseg_lo + (nz - ezflt + Q.SEG - 1) / Q.SEG;
+  Q.LX = nx * (N - 1) + 1;
+  Q.LXP = (Q.LX + 1 + 7) / 8 * 8;  // rows start on 32-byte sectors (FP32: 8 elements), one spare column for 16-byte bulk copies
+  Q.LZ = nz * (N - 1) + 1 + (ezflt > 0 ? 1 : 0);
+  Q.xhalo_left = halo_left ? 1 : 0;
+  Q.xhalo_right = halo_right ? 1 : 0;
+  strip_set_groups(Q, warps, halo_left, halo_right);
+  Q.it_g0 = 0;
+  Q.it_ng = Q.ngroups;
+  Q.it_step = 1;
+  Q.nitems = (long long)Q.nseg * Q.ngroups;
+  return Q;
+}
+
 // band below the shared row gz, or -1 when gz is not the bottom row of a band that shares it
 __host__ __device__ inline int strip_shared_row_seg(const StripGeom& G, int gz) {
   int g = gz, lower = 1;
@@ -134,6 +166,15 @@ __host__ __device__ inline size_t strip_coef_index(const StripGeom& G, int nelas
   const int cx = min(G.EPW, G.nx - ex0);
   const size_t base = (size_t)strip_elem_off(G, seg, strip, iz) * nelast * N * N;
   return base + 2 * ((size_t)((pl >> 1) * N + j) * (cx * N) + el * N + i) + (pl & 1);
+}
+
+// position of a per-GLL-point scalar (e.g. the Kelvin-Voigt eta) of element (ix,iz): [j][lane] per element row
+__host__ __device__ inline size_t strip_scalar_index(const StripGeom& G, int ix, int iz, int i, int j) {
+  const int N = G.N;
+  const int seg = strip_seg_of(G, iz), strip = ix / G.EPW;
+  const int ex0 = strip * G.EPW, el = ix - ex0;
+  const int cx = min(G.EPW, G.nx - ex0);
+  return (size_t)strip_elem_off(G, seg, strip, iz) * N * N + (size_t)j * (cx * N) + el * N + i;
 }
 
 // lattice column of the boundary between group hb and group hb+1
@@ -223,7 +264,6 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group
 // registers, 3 CTAs/SM: 5.82;  5 warps (128 registers, 3 CTAs/SM): 6.02;  6 warps (168, 2 CTAs): 6.41;
 // 8 warps (128, 2 CTAs): 6.58 -- registers (instruction-level parallelism) beat resident warps here.
 constexpr int strip_warps() { return 4; }
-constexpr int STRIP_MASK_WORDS = 128;  // a band has at most 32*128 lattice rows (s2d_cart_create clamps SEG)
 // bytes of the staging area of one warp: coefficient vectors and displacement rows of one element
 // row; in the fused form also the velocities and inverse masses of the nodes it will advance
 // (fused: 0 plain force evaluation, 1 leapfrog update, 2 explicit Newmark update: also the old accelerations)

@@ -33,6 +33,23 @@ def make_scheme(kind, dt, beta, gamma, alpha, stages=None):
     return s
 
 
+def detect_structured(ngll, ibool, npoin, lower_hint=0):
+    """s2d_detect_structured: None if ibool is not a MESH_CART box, else dict(nx, nz, ezflt, ex, ez, gx, gz)"""
+    L = capi.lib()
+    ibool = _i32(ibool)
+    nelem = ibool.size // (ngll * ngll)
+    nx, nz, ez = C.c_int32(), C.c_int32(), C.c_int32()
+    ex, ezz = np.empty(nelem, np.int32), np.empty(nelem, np.int32)
+    gx, gz = np.empty(npoin, np.int32), np.empty(npoin, np.int32)
+    rc = L.s2d_detect_structured(ngll, nelem, npoin, _ptr(ibool), lower_hint, C.byref(nx), C.byref(nz), C.byref(ez),
+                                 _ptr(ex), _ptr(ezz), _ptr(gx), _ptr(gz))
+    if rc != 0:
+        raise S2DError(rc, "s2d_detect_structured: invalid argument")
+    if nx.value == 0:
+        return None
+    return dict(nx=nx.value, nz=nz.value, ezflt=ez.value, ex=ex, ez=ezz, gx=gx, gz=gz)
+
+
 class Engine:
     """One device-resident SEM2DPACK problem (problem_type, SRC/problem_class.f90:19-46)."""
 
@@ -227,6 +244,12 @@ class Engine:
         ms = C.c_float()
         self._ck(self.L.s2d_time_steps(self.h, nsteps, C.byref(ms)))
         return ms.value
+
+    def route(self):
+        """0 = any-mesh kernel, 1 = z-marching strip kernel (s2d_kernel_route)"""
+        r = C.c_int32()
+        self._ck(self.L.s2d_kernel_route(self.h, C.byref(r)))
+        return r.value
 
     PHASES = ("predictor", "element_force", "halo_fold_exchange", "sources", "boundary_conditions", "node_update",
               "outputs")

@@ -25,9 +25,17 @@ def _rand_fields(o, seed=1):
     return rng.standard_normal(n), rng.standard_normal(n)
 
 
+@pytest.fixture(params=["strip-routing", "any-mesh"])
+def route(request, monkeypatch):
+    """structured decks handed over through the generic API run on the strip kernel by default
+    (s2d_kernel_route); S2D_ROUTE_STRIP=0 keeps them on the any-mesh kernels, which stay covered this way"""
+    monkeypatch.setenv("S2D_ROUTE_STRIP", "1" if request.param == "strip-routing" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("name", ["testsh", "lamb", "tpv3", "ratestate"])
-def test_fint_matches_oracle(name, variant):
+def test_fint_matches_oracle(name, variant, route):
     """compute_Fint (solver.f90:273-320) on random fields: every kernel variant, NGLL 5/6/9, SH and
     P-SV, shared and KV-carrying elements."""
     o = orc.Oracle(harness.deck(name))
@@ -43,7 +51,7 @@ def test_fint_matches_oracle(name, variant):
 
 @pytest.mark.parametrize("ngll", [3, 4, 5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("ndof", [1, 2])
-def test_fint_all_ngll_hetero(ngll, ndof):
+def test_fint_all_ngll_hetero(ngll, ndof, route):
     """heterogeneous medium (one coefficient block per element -> patch-major plane layout)."""
     o = orc.Oracle(harness.cart_deck(12, 9, ngll=ngll, ndof=ndof, nrec=0, src=False), synthetic_seed=20261017)
     assert o.i("ncoefsets") == o.i("nelem")
@@ -133,7 +141,7 @@ def _lockstep(o, r, nsteps, chunk, tol, check_fault=True, skip_tstick=False):
             assert np.abs(pot - pot_ref).max() <= max(tol, 1e-12) * max(np.abs(pot_ref).max(), 1e-300)
 
 
-def test_testsh_full_run_and_known_answer():
+def test_testsh_full_run_and_known_answer(route):
     """EXAMPLES/TestSH end to end (1987 leapfrog steps, NGLL=6 SH, ABSORB, Ricker force, receivers 'D'),
     in lock step with the oracle AND against the analytic trace of analyze_test.m (< 2 %)."""
     o = orc.Oracle(harness.deck("testsh"))
@@ -145,7 +153,7 @@ def test_testsh_full_run_and_known_answer():
     r.close()
 
 
-def test_lamb_full_run_and_known_answer():
+def test_lamb_full_run_and_known_answer(route):
     """EXAMPLES/LambsProblem (3000 steps, NGLL=9 P-SV, P1 absorbing, free surface): misfits of
     analyze_test.m must reproduce the values recorded in test.out:12."""
     o = orc.Oracle(harness.deck("lamb"))
@@ -174,7 +182,7 @@ def test_tpv3_slip_weakening_run():
     r.close()
 
 
-def test_ratestate_run():
+def test_ratestate_run(route):
     """EXAMPLES/RateState: rate-and-state slip law (kind 3, Newton/bisection per node), 803 steps."""
     o = orc.Oracle(harness.deck("ratestate"))
     r = Rig(o)

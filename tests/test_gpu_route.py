@@ -1,0 +1,118 @@
+"""Kernel routing of the generic C-ABI (VERDICT r1 "what's weak" 1): what a Fortran host hands over through
+s2d_create / s2d_set_elastic -- RCM-ordered ibool, per-element coefficient blocks, boundary tables in its own
+node numbering -- must reach the z-marching strip kernel when the mesh is a MESH_CART box, with the same results
+as the any-mesh patch kernel and the oracle."""
+import numpy as np
+import pytest
+
+import harness
+import orc
+from harness import Rig, rel_l2
+
+pytestmark = pytest.mark.gpu
+SEED = 20261017
+
+
+def _run(deck, nsteps, seed=0, chunk=97):
+    o = orc.Oracle(deck, synthetic_seed=seed)
+    r = Rig(o)
+    done = 0
+    while done < nsteps:
+        n = min(chunk, nsteps - done)
+        o.step(n)
+        r.step(n)
+        done += n
+    return o, r
+
+
+@pytest.mark.parametrize("name,nsteps,tol", [("testsh", 600, 1e-10), ("lamb", 600, 1e-10), ("ratestate", 400, 1e-9),
+                                             ("inabox", 500, 1e-10)])
+def test_reference_decks_take_the_strip_kernel(name, nsteps, tol):
+    o, r = _run(harness.deck(name), nsteps)
+    assert r.e.route() == 1
+    d, v, a = r.e.get_fields()
+    for nm, got in (("d", d), ("v", v), ("acc", a)):
+        assert rel_l2(got, o.arr(nm)) <= tol, (nm, rel_l2(got, o.arr(nm)))
+    if o.i("rec.present"):
+        s_ref, s_got = o.seis(), r.e.seis()
+        assert np.abs(s_got - s_ref).max() <= 2e-7 * np.abs(s_ref).max()
+    for fid, ibc, np_, onx in r.faults:
+        st = r.e.fault_state(fid, np_)
+        for k in ("D", "V", "T", "MU"):
+            assert rel_l2(st[k], o.arr(f"bc.{ibc}.{k}")) <= tol, k
+    r.close()
+
+
+@pytest.mark.parametrize("scheme,stacey,nx,nz,ezflt", [("leapfrog", False, 40, 24, 16), ("newmark", True, 26, 21, 9),
+                                                      ("leapfrog", False, 100, 70, 35)])
+def test_synthetic_family_rcm_order_through_the_generic_api(scheme, stacey, nx, nz, ezflt):
+    """heterogeneous medium (one a(5,5,6) block per element), two-sided fault on the split-node row, RCM element
+    order: the route north_star describes"""
+    nsteps = 300
+    o, r = _run(harness.cart_deck(nx, nz, ezflt=ezflt, scheme=scheme, stacey=stacey, nsteps=nsteps), nsteps, seed=SEED)
+    assert r.e.route() == 1
+    d, v, a = r.e.get_fields()
+    for nm, got in (("d", d), ("v", v), ("acc", a)):
+        assert rel_l2(got, o.arr(nm)) <= 1e-10, nm
+    s_ref, s_got = o.seis(), r.e.seis()
+    assert np.abs(s_got - s_ref).max() <= 2e-7 * np.abs(s_ref).max()
+    fid, ibc, np_, onx = r.faults[0]
+    st = r.e.fault_state(fid, np_)
+    for k, floor in (("D", 1e-3), ("V", 1e-3), ("T", 1.0), ("MU", 1e-3)):   # a locked fault slips at rounding level
+        ref = o.arr(f"bc.{ibc}.{k}")
+        assert np.abs(st[k] - ref).max() <= 1e-10 * max(np.abs(ref).max(), floor), k
+    if nx >= 40:
+        assert np.abs(st["D"]).max() > 1e-3
+    rec, pot = r.e.fault(fid, onx)
+    ref = o.arr(f"bc.{ibc}.out").reshape(-1, 6, onx)
+    for c in range(6):
+        assert np.abs(rec[:, c] - ref[:, c]).max() <= 2e-7 * max(np.abs(ref[:, c]).max(), 1e-30)
+    r.close()
+
+
+def test_routing_can_be_switched_off_and_both_kernels_agree(monkeypatch):
+    deck = harness.cart_deck(30, 20, ezflt=10, nsteps=150)
+    outs = []
+    for flag, route in (("1", 1), ("0", 0)):
+        monkeypatch.setenv("S2D_ROUTE_STRIP", flag)
+        o, r = _run(deck, 150, seed=SEED)
+        assert r.e.route() == route
+        d, v, a = r.e.get_fields()
+        assert rel_l2(d, o.arr("d")) <= 1e-10
+        f = r.e.compute_fint()
+        assert rel_l2(f, o.compute_fint()) <= 1e-12
+        nc, col = r.e.coloring()       # the colouring stays available whatever kernel runs
+        assert nc >= 4 and col.size == o.i("nelem")
+        outs.append((d, v, a))
+        r.close()
+    for x, y in zip(*outs):
+        assert rel_l2(x, y) <= 1e-11
+
+
+def test_kelvin_voigt_and_general_planes_keep_the_any_mesh_kernel():
+    o = orc.Oracle(harness.deck("tpv3"))
+    r = Rig(o)
+    assert r.e.route() == 0     # KV elements: until the strip kernel carries the element-wise d + eta*v
+    r.close()
+
+
+def test_fields_energy_and_set_fields_in_the_callers_numbering():
+    """a routed handle still speaks the caller's node numbering: set_fields / get_fields round trip, s2d_energy
+    with the caller's mass"""
+    o = orc.Oracle(harness.cart_deck(19, 13, ezflt=6, nsteps=50), synthetic_seed=SEED)
+    r = Rig(o)
+    assert r.e.route() == 1
+    rng = np.random.default_rng(5)
+    n = o.i("npoin") * 2
+    d0, v0 = rng.standard_normal(n) * 1e-3, rng.standard_normal(n)
+    r.e.set_fields(d0, v0)
+    o.set_fields(d0, v0)
+    d1, v1, _ = r.e.get_fields()
+    assert np.array_equal(d1, d0) and np.array_equal(v1, v0)
+    r.e.set_mass(o.arr("mass"))
+    assert abs(r.e.energy() - o.L.orc_energy_Ek(o.h)) <= 1e-12 * o.L.orc_energy_Ek(o.h)
+    o.step(50)
+    r.step(50)
+    d, v, _ = r.e.get_fields()
+    assert rel_l2(d, o.arr("d")) <= 1e-10 and rel_l2(v, o.arr("v")) <= 1e-10
+    r.close()
