@@ -39,6 +39,17 @@ struct SolverError : std::runtime_error {  // device-side abort of the friction 
     if (!(cond)) throw s2d::ArgError(msg);    \
   } while (0)
 
+// Host -> device copy that is complete on the DEVICE when it returns.  cudaMemcpy from pageable host memory may
+// return as soon as the data sit in the driver's staging buffer, with the DMA still in flight on the legacy default
+// stream; the engine's kernels run on a NON-BLOCKING stream, which that stream does not order -- a kernel launched
+// right after an upload could read the old contents of the tail of the buffer (seen: the highest-numbered nodes of
+// s2d_set_fields).  Waiting for the default stream closes the window.
+inline void h2d_sync(void* dst, const void* src, size_t bytes) {
+  cudaError_t e_ = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+  if (e_ == cudaSuccess) e_ = cudaStreamSynchronize(0);
+  if (e_ != cudaSuccess) throw std::runtime_error(std::string("host to device copy: ") + cudaGetErrorString(e_));
+}
+
 // Owning device array.
 template <typename T>
 struct DevBuf {
@@ -66,12 +77,16 @@ struct DevBuf {
     n = count;
     if (count) S2D_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
   }
+  // on a given stream: ordered there; without one: complete on the device at return (the legacy default stream
+  // does not order the engine's non-blocking stream)
   void zero(cudaStream_t s = 0) {
-    if (n) S2D_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    if (!n) return;
+    S2D_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    if (s == 0) S2D_CUDA(cudaStreamSynchronize(0));
   }
   void upload(const T* host, size_t count) {
     alloc(count);
-    if (count) S2D_CUDA(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    if (count) h2d_sync(p, host, count * sizeof(T));
   }
   void upload(const std::vector<T>& v) { upload(v.data(), v.size()); }
   void download(T* host) const {

@@ -1,7 +1,9 @@
 // C-ABI of the sem2d_b200 engine (include/sem2d_b200.h).
+#define S2D_INSTANTIATE_F64
 #include "engine.hpp"
 
 using namespace s2d;
+template class s2d::Engine<double>;
 
 struct s2d_engine {
   std::unique_ptr<EngineBase> impl;

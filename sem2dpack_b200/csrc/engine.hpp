@@ -202,7 +202,7 @@ class Engine : public EngineBase {
   DevBuf<int> cart_meet;  // arrival counters of the group-boundary columns (strip_kernels.cuh)
   // Kelvin-Voigt damping on a structured box: eta (already * dt) is a function of position, so the
   // element-wise d_loc + eta*v_loc of MAT_KV_add_etav (mat_kelvin_voigt.f90:137-150) is the node field d + eta*v
-  DevBuf<T> cart_kv_eta, cart_kv_buf;
+  DevBuf<T> cart_kv_eta;  // node-wise eta as s2d_cart_set_kv hands it over, until commit spreads it over the elements
   // compact coefficient mode: p_coef holds (lambda, mu) per GLL point, the strip kernel forms the planes
   int cart_compact = 0;
   double cart_cdx = 0.0, cart_cdz = 0.0, cart_cdet = 0.0;
@@ -832,7 +832,6 @@ class Engine : public EngineBase {
     tmp.upload(eta_ref, npoin_ref);
     cart_kv_eta.alloc(npoin);
     cart_kv_eta.zero(stream);
-    cart_kv_buf.alloc(npoin * ndof);
     cart_from_ref1(tmp.p, cart_kv_eta.p);
     S2D_CUDA(cudaStreamSynchronize(stream));
   }
@@ -1047,7 +1046,7 @@ class Engine : public EngineBase {
   std::vector<int32_t> h_fault_node1;  // first node1 of every fault (which side of a split-node row is the lower one)
   std::vector<double> h_eta;
   DevBuf<T> strip_eta;                 // Kelvin-Voigt eta per element GLL point in the strip layout (zero off the KV elements)
-  static bool strip_kv_ok() { return false; }  // until the strip kernel carries the element-wise d + eta*v
+  static bool strip_kv_ok() { return true; }   // k_elem_strip<KV>: d + eta*v element by element
 
   // ---- planning ------------------------------------------------------------------------
   // Deferred nodes of the fused step: halo rows / columns (flagged by the builder) plus every node a
@@ -1188,9 +1187,16 @@ class Engine : public EngineBase {
     if (cart_mode) {
       S2D_REQUIRE(variant == S2D_ASM_PATCH, "commit: the structured builder only provides the strip kernel");
       if (!rmass_is_inverse) k_invert<T><<<grid_for(rmass.n), 256, 0, stream>>>(rmass.p, rmass.n);
+      if (cart_kv_eta.n) {  // s2d_cart_set_kv: eta at the nodes -> eta(ngll,ngll) of every element
+        const size_t tot = (size_t)nelem * ngll * ngll;
+        strip_eta.alloc(tot);
+        k_strip_eta_from_nodes<T><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(cart_S, cart_kv_eta.p, strip_eta.p);
+        S2D_CUDA(cudaStreamSynchronize(stream));
+        cart_kv_eta.release();
+      }
       // the node update rides in the strip kernel for leapfrog and for the explicit Newmark scheme (beta = 0)
       fused = (scheme.kind == 0 || (scheme.kind == 1 && scheme.beta == 0.0)) && env_int("S2D_FUSED", 1) != 0 &&
-              cart_kv_eta.n == 0;  // the fused update reads d only: Kelvin-Voigt boxes take the separate passes
+              strip_eta.n == 0;  // Kelvin-Voigt elements: the node update takes the separate passes
       if (fused) build_deferred_tables();
     } else {
       if (variant == S2D_ASM_PATCH) build_patch_plan_dev();
@@ -1219,13 +1225,12 @@ class Engine : public EngineBase {
   // f = -K d  (compute_Fint, solver.f90:273-320); f must be zero on entry unless the patch variant
   void launch_fint(const T* dd, const T* vv, T* ff) {
     if (cart_mode) {
-      if (cart_kv_eta.n) {  // forces from d + eta*v (solver.f90:293-295 with mat_kelvin_voigt.f90:147)
-        const size_t nd = npoin * ndof;
-        k_kv_combine<T><<<grid_for(nd), 256, 0, stream>>>(cart_kv_buf.p, dd, vv, cart_kv_eta.p, npoin, ndof);
-        launches++;
-        dd = cart_kv_buf.p;
+      StripIO<T> io = strip_io(dd, ff);
+      if (strip_eta.n) {  // forces from d + eta*v, element by element (solver.f90:293-295, mat_kelvin_voigt.f90:147)
+        io.eta = strip_eta.p;
+        io.v_kv = vv;
       }
-      launch_strips(strip_io(dd, ff));
+      launch_strips(io);
       return;
     }
     if (variant == S2D_ASM_PATCH) {
@@ -1611,11 +1616,11 @@ class Engine : public EngineBase {
       return;
     }
     if (sizeof(T) == 8) {
-      S2D_CUDA(cudaMemcpy(dst.p, src, nd * 8, cudaMemcpyHostToDevice));
+      h2d_sync(dst.p, src, nd * 8);
     } else {
       std::vector<T> tmp(nd);
       for (size_t q = 0; q < nd; ++q) tmp[q] = (T)src[q];
-      S2D_CUDA(cudaMemcpy(dst.p, tmp.data(), nd * sizeof(T), cudaMemcpyHostToDevice));
+      h2d_sync(dst.p, tmp.data(), nd * sizeof(T));
     }
   }
   void download(const DevBuf<T>& src, double* dst) {
@@ -1838,5 +1843,14 @@ class Engine : public EngineBase {
     return ms;
   }
 };
+
+// One translation unit per precision instantiates the engine (engine.cu: FP64, engine_f32.cu: FP32); every
+// other one only refers to it.
+#ifndef S2D_INSTANTIATE_F64
+extern template class Engine<double>;
+#endif
+#ifndef S2D_INSTANTIATE_F32
+extern template class Engine<float>;
+#endif
 
 }  // namespace s2d

@@ -212,6 +212,10 @@ struct StripArgs {
   // leapfrog is the same update with c1 = c2 = 0, c3 = dt
   T c1, c2, c3;
   const T* a_in;            // accelerations of the previous step (Newmark predictor); aliases f / a_out
+  // Kelvin-Voigt elements (MAT_KV_add_etav, mat_kelvin_voigt.f90:137-150): forces from d + eta*v, eta per GLL
+  // point of every element in the strip layout (strip_scalar_index; zero on elements without KV)
+  const T* eta;
+  const T* v_kv;
   int prefetch;             // L2 prefetch of what is not staged
   T H[N * N];               // hprime, column-major (constant bank)
   // compact coefficient mode (isotropic flat grids): only (lambda, mu) are stored per GLL point and
@@ -276,10 +280,11 @@ constexpr int strip_min_ctas(int N, int tsize, bool compact = false) {
   return N <= 6 ? (tsize == 4 ? 4 : 3) : (tsize == 4 ? 2 : 1);
 }
 
-template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT)>
+template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false>
 __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     k_elem_strip(const __grid_constant__ StripArgs<T, N> A) {
   static_assert(!COMPACT || NDOF == 2, "compact coefficients: P-SV only");
+  static_assert(!KV || FUSED == 0, "Kelvin-Voigt elements: plain force evaluation (the node update runs in its own passes)");
   constexpr int WARPS = strip_warps();
   constexpr int NEL = NDOF == 1 ? 2 : 6;
   constexpr int NPL = COMPACT ? 2 : NEL;  // planes stored per GLL point
@@ -385,14 +390,17 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     }
   }
   T U[NDOF][N], Fc[NDOF];
+  T Vc[KV ? NDOF : 1];  // KV: velocity of the row shared with the next element row, carried like U[c][0]
   {
     const size_t r0 = (size_t)strip_lat_row(G, ez0, 0) * LX;
 #pragma unroll
     for (int c = 0; c < NDOF; ++c) {
       U[c][0] = up[A.npoin * c + r0];
       Fc[c] = 0;
+      if (KV) Vc[c] = A.v_kv[gx + A.npoin * c + r0];
     }
   }
+  const T* etap = KV ? A.eta + (size_t)strip_elem_off(G, seg, strip, ez0) * (N * N) + lanep : nullptr;
   const int cxN = cx * N;
   const V2* cp = reinterpret_cast<const V2*>(A.coef) +
                  (size_t)strip_elem_off(G, seg, strip, ez0) * (NPL * N * N / 2) + lanep;
@@ -523,10 +531,33 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       // full): this tile 5.82 / 8.26 / 5.61;  __shfl_sync rotations among the N lanes of an element
       // instead of the tile (no shared memory, no __syncwarp) 6.24 / 7.72 / 6.08.  The tile costs 2
       // L1 wavefronts per broadcast LDS.64 (ncu), the shuffles cost issue slots of the same MIO queue.
+      // Kelvin-Voigt: the element sees d + eta*v (mat_kelvin_voigt.f90:147); eta belongs to the element, so the
+      // row shared with the next element row is combined again there, from the carried d and v
+      T Ue[KV ? NDOF : 1][KV ? N : 1];
+      if constexpr (KV) {
+        T et[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) et[j] = ld_stream(etap + (size_t)j * cxN);
+        etap += (size_t)cx * (N * N);
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) {
+          T vr[N];
+          vr[0] = Vc[c];
+#pragma unroll
+          for (int j = 1; j < N; ++j) vr[j] = A.v_kv[gx + A.npoin * c + rowbase + (size_t)j * LX];
+#pragma unroll
+          for (int j = 0; j < N; ++j) Ue[c][j] = U[c][j] + et[j] * vr[j];
+          Vc[c] = vr[N - 1];
+        }
+      }
+      auto& Ut = [&]() -> T(&)[NDOF][N] {
+        if constexpr (KV) return Ue;
+        else return U;
+      }();
 #pragma unroll
       for (int c = 0; c < NDOF; ++c)
 #pragma unroll
-        for (int j = 0; j < N; ++j) tlw[c][j][lanep] = U[c][j];
+        for (int j = 0; j < N; ++j) tlw[c][j][lanep] = Ut[c][j];
       __syncwarp();
       T gxi[NDOF][N], get[NDOF][N];
 #pragma unroll
@@ -536,11 +567,11 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           T row[NR];  // the 5 lanes of an element read the same word: one wavefront per value
 #pragma unroll
           for (int m = 0; m < NR; ++m) row[m] = tlw[c][j][ROT ? mo[m] : el * N + m];
-          T s1 = ROT ? Hii * U[c][j] : (T)0, s2 = 0;
+          T s1 = ROT ? Hii * Ut[c][j] : (T)0, s2 = 0;
 #pragma unroll
           for (int m = 0; m < NR; ++m) s1 += Hi[m] * row[m];                   // (Ht U)(i,j)
 #pragma unroll
-          for (int m = 0; m < N; ++m) s2 += U[c][m] * A.H[m + N * j];          // (U H)(i,j)
+          for (int m = 0; m < N; ++m) s2 += Ut[c][m] * A.H[m + N * j];         // (U H)(i,j)
           gxi[c][j] = s1;
           get[c][j] = s2;
         }
@@ -960,6 +991,18 @@ __global__ void k_xhalo_unpack(StripGeom G, T* __restrict__ f, const T* __restri
   f[(size_t)gz * G.LXP + gx + npoin * c] = xhalo_own(G, f, halo_z, npoin, side, c, gz) + src[q];
 }
 
+// node-wise eta (a function of position, s2d_cart_set_kv) spread over the elements in the strip layout
+template <typename T>
+__global__ void k_strip_eta_from_nodes(StripGeom G, const T* __restrict__ eta_node, T* __restrict__ eta_strip) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = G.N, N2 = N * N;
+  if (w >= (long long)G.nx * G.nz * N2) return;
+  const long long e = w / N2;
+  const int k = (int)(w - e * N2), i = k % N, j = k / N;
+  const int ix = (int)(e % G.nx), iz = (int)(e / G.nx);
+  eta_strip[strip_scalar_index(G, ix, iz, i, j)] = eta_node[(size_t)strip_lat_row(G, iz, j) * G.LXP + (size_t)ix * (N - 1) + i];
+}
+
 // everything a strip launch needs besides the geometry
 template <typename T>
 struct StripIO {
@@ -983,6 +1026,8 @@ struct StripIO {
   int newmark = 0;          // fused explicit Newmark instead of leapfrog
   double c1 = 0.0, c2 = 0.0, c3 = 0.0;
   const T* a_in = nullptr;
+  const T* eta = nullptr;   // Kelvin-Voigt: eta per element GLL point (strip layout) and the velocity field
+  const T* v_kv = nullptr;
   int prefetch = 1;
   // compact coefficient mode (coef holds lambda, mu only)
   int compact = 0;
@@ -991,7 +1036,7 @@ struct StripIO {
   const double* wgll = nullptr;
 };
 
-template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT)>
+template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false>
 inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) {
   constexpr size_t smem = strip_warps() * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT);
   // Opt in to the dynamic shared memory once per device and instantiation.  Never on the step path
@@ -1001,11 +1046,11 @@ inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) 
   int dev = 0;
   S2D_CUDA(cudaGetDevice(&dev));
   if (!done[dev & 63]) {
-    S2D_CUDA(cudaFuncSetAttribute(k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB>,
+    S2D_CUDA(cudaFuncSetAttribute(k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done[dev & 63] = true;
   }
-  k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB><<<nb, strip_warps() * 32, smem, s>>>(A);
+  k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV><<<nb, strip_warps() * 32, smem, s>>>(A);
 }
 
 // element-force launch over the groups selected by G.it_* (no halo fold)
@@ -1036,6 +1081,8 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
     A.c2 = (T)io.c2;                                                                              \
     A.c3 = (T)(fused && !io.newmark ? io.dt : io.c3);                                             \
     A.a_in = io.a_in;                                                                             \
+    A.eta = io.eta;                                                                               \
+    A.v_kv = io.v_kv;                                                                             \
     A.prefetch = io.prefetch;                                                                     \
     for (int k = 0; k < NN * NN; ++k) A.H[k] = (T)io.hprime[k];                                   \
     A.cdx = (T)io.cdx;                                                                            \
@@ -1044,6 +1091,14 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
     for (int k = 0; k < NN; ++k) A.wg[k] = io.wgll ? (T)io.wgll[k] : (T)0;                        \
     const unsigned nb = (unsigned)G.nitems;                                                       \
     const int mode = !fused ? 0 : (io.newmark ? 2 : 1);                                           \
+    if (io.eta) { /* Kelvin-Voigt elements: plain force evaluation from d + eta*v */               \
+      if (mode != 0) throw ArgError("Kelvin-Voigt elements: the node update is not fused");        \
+      constexpr int MB = strip_min_ctas(NN, sizeof(T));                                           \
+      if (G.ndof == 1) strip_launch<T, NN, 1, 0, false, MB, true>(nb, A, s);                      \
+      else if (io.compact) strip_launch<T, NN, 2, 0, true, MB, true>(nb, A, s);                   \
+      else strip_launch<T, NN, 2, 0, false, MB, true>(nb, A, s);                                  \
+      break;                                                                                      \
+    }                                                                                             \
     if (G.ndof == 1) {                                                                            \
       if (io.compact) throw ArgError("compact coefficients need ndof = 2");                       \
       if (mode == 2) strip_launch<T, NN, 1, 2, false>(nb, A, s);                                  \

@@ -89,11 +89,35 @@ def test_routing_can_be_switched_off_and_both_kernels_agree(monkeypatch):
         assert rel_l2(x, y) <= 1e-11
 
 
-def test_kelvin_voigt_and_general_planes_keep_the_any_mesh_kernel():
-    o = orc.Oracle(harness.deck("tpv3"))
-    r = Rig(o)
-    assert r.e.route() == 0     # KV elements: until the strip kernel carries the element-wise d + eta*v
+def test_kelvin_voigt_elements_take_the_strip_kernel():
+    """EXAMPLES/TestFlt2D_SCEC_TPV3_inplane: ELAST + KV elements (eta(ngll,ngll) per element, mat_kelvin_voigt.f90:137-150),
+    Newmark, one-sided fault: k_elem_strip<KV> forms d + eta*v element by element"""
+    o, r = _run(harness.deck("tpv3"), 500)
+    assert r.e.route() == 1
+    d, v, a = r.e.get_fields()
+    for nm, got in (("d", d), ("v", v), ("acc", a)):
+        assert rel_l2(got, o.arr(nm)) <= 1e-10, nm
+    rng = np.random.default_rng(8)
+    n = o.i("npoin") * 2
+    d0, v0 = rng.standard_normal(n), rng.standard_normal(n)
+    r.e.set_fields(d0, v0)
+    o.set_fields(d0, v0)
+    assert rel_l2(r.e.compute_fint(), o.compute_fint()) <= 1e-13
     r.close()
+
+
+def test_general_planes_keep_the_any_mesh_kernel():
+    """nelast = 10 (curved-mesh planes, mat_elastic.f90:344-358) is not the strip kernel's flat form"""
+    from sem2dpack_b200 import Engine
+    o = orc.Oracle(harness.cart_deck(9, 7, ngll=5, ndof=2, nrec=0, src=False), synthetic_seed=SEED)
+    ag = np.zeros((o.i("ncoefsets"), 10, 25))
+    ag[:, :6] = o.arr("a").reshape(o.i("ncoefsets"), 6, 25)
+    e = Engine(5, 2, o.arr("ibool"), o.arr("H"), o.arr("rmass"), 0, o.f("dt"))
+    e.set_elastic(10, ag, o.arr("elem2set"), False)
+    e.commit()
+    assert e.route() == 0
+    e.close()
+    o.close()
 
 
 def test_fields_energy_and_set_fields_in_the_callers_numbering():
