@@ -138,10 +138,21 @@ struct problem_type {
   // &MESH_CART
   double xlim[2] = {0, 0}, zlim[2] = {0, 0};
   int nelem[2] = {0, 0}, ezflt = 0;
-  // &MAT_ELASTIC, &MAT_KV (SRC/mat_kelvin_voigt.f90:35-66)
-  double rho = 0, cp = 0, cs = 0;
-  bool has_kv = false, ETAxDT = true;
-  cd_type kv_eta;
+  int fztag = 0, fznz = 1;                       // mesh_cartesian.f90:281-290
+  struct domain_type {                           // &MESH_CART_DOMAIN (mesh_cartesian.f90:150-176)
+    int tag = 1, ex[2] = {0, 0}, ez[2] = {0, 0};
+  };
+  std::vector<domain_type> domains;
+  // matpro_input_type per tag (SRC/prop_mat.f90:21-25): &MAT_ELASTIC (SRC/mat_elastic.f90:104-129) with constants
+  // or DIST_* fields, &MAT_KV (SRC/mat_kelvin_voigt.f90:35-66)
+  struct material_type {
+    bool set = false, kv = false, ETAxDT = true;
+    cd_type rho, cp, cs, eta;
+    bool homogeneous() const { return rho.dist == 0 && cp.dist == 0 && cs.dist == 0; }
+  };
+  std::vector<material_type> mat;                // index tag-1
+  double rho = 0, cp = 0, cs = 0;                // material of tag 1 when it is homogeneous (builder default)
+  bool has_kv = false;
   timescheme_type time;
   std::vector<bc_type> bc;
   std::vector<source_type> src;
@@ -244,40 +255,75 @@ inline void read_main(problem_type& pb, const std::string& file) {
       pb.nelem[q] = g.integer("nelem", 0, q);
     }
     pb.ezflt = g.integer("ezflt", 0);
-    if (g.has("splitd")) IO_abort("CART_read: splitD is not provided by the B200 path");
-    // fztag / FZnz only re-tag the element rows next to the fault (mesh_cartesian.f90:262-268); accepted when
-    // every material is the same (checked in MAT_read below)
-    if (pb.ezflt < 0) IO_abort("CART_read: ezflt = -1 (fault at mid height) needs an even nelem(2)");
+    if (g.logical("faultx", false)) pb.ezflt = -1;
+    if (g.has("splitd") || g.logical("split", false)) IO_abort("CART_read: split / splitD is not provided by the B200 path");
+    if (pb.ezflt == -1) pb.ezflt = pb.nelem[1] / 2;   // mesh_cartesian.f90:124
+    if (pb.ezflt < -1) IO_abort("CART_read: ezflt must be >= -1");
+    if (pb.ezflt >= pb.nelem[1]) IO_abort("CART_read: ezflt must be < nelem(2)");
+    pb.fztag = g.integer("fztag", 0);
+    pb.fznz = g.integer("fznz", 1);
+    if (pb.fztag < 0) IO_abort("MESH_LAYERS_read: fztag must be positive");
+    if (pb.fznz < 1) IO_abort("MESH_LAYERS_read: fznz must be strictly positive");
   }
-  // MAT_read (SRC/mat_gen.f90:119-189): ELAST materials that all carry the same properties (each MATERIAL
-  // block reads the next MAT_ELASTIC block FORWARD from its own position, so several tags can share one)
+  for (long q = in.find("MESH_CART_DOMAIN"); q >= 0; q = in.find("MESH_CART_DOMAIN", (size_t)q + 1)) {
+    const nml_group& g = in.at((size_t)q);
+    problem_type::domain_type dm;
+    dm.tag = g.integer("tag", 0);
+    for (int c = 0; c < 2; ++c) {
+      dm.ex[c] = g.integer("ex", 0, c);
+      dm.ez[c] = g.integer("ez", 0, c);
+    }
+    if (dm.tag < 1) IO_abort("CART_read: tag null, negative or missing");
+    if (dm.ex[0] < 1 || dm.ex[0] > pb.nelem[0] || dm.ex[1] < 1 || dm.ex[1] > pb.nelem[0]) IO_abort("CART_read: ex out of bounds or missing");
+    if (dm.ez[0] < 1 || dm.ez[0] > pb.nelem[1] || dm.ez[1] < 1 || dm.ez[1] > pb.nelem[1]) IO_abort("CART_read: ez out of bounds or missing");
+    pb.domains.push_back(dm);
+  }
+  // MAT_read (SRC/mat_gen.f90:101-200): one MATERIAL block per tag; each kind reads ITS input block forward from
+  // the position right after the MATERIAL block (so several tags can share one &MAT_ELASTIC that follows them)
   k = in.find("MATERIAL");
-  if (k < 0) IO_abort("MAT_read: no MATERIAL block");
-  for (long m0 = k, first = 1; m0 >= 0; m0 = in.find("MATERIAL", (size_t)m0 + 1), first = 0) {
+  if (k < 0) IO_abort("MAT_read: MATERIAL block not found");
+  {
+    int numat = 0, ntags = 0;
+    for (long m0 = k; m0 >= 0; m0 = in.find("MATERIAL", (size_t)m0 + 1)) {
+      const int tag = in.at((size_t)m0).integer("tag", 0);
+      if (tag <= 0) IO_abort("MAT_read: tag must be positive");
+      ntags = std::max(ntags, tag);
+      ++numat;
+    }
+    if (numat != ntags) IO_abort("MAT_read: inconsistent or missing tags");
+    pb.mat.assign((size_t)numat, problem_type::material_type());
+  }
+  for (long m0 = k; m0 >= 0; m0 = in.find("MATERIAL", (size_t)m0 + 1)) {
     const nml_group& g = in.at((size_t)m0);
-    const bool kv = g.count("kind") == 2 && g.text("kind", "", 1) == "KV";
-    if (g.text("kind", "") != "ELAST" || (g.count("kind") != 1 && !kv))
-      IO_abort("MAT_read: only kind='ELAST' and kind='ELAST','KV' are provided here");
+    problem_type::material_type& M = pb.mat[(size_t)g.integer("tag", 0) - 1];
+    const std::string k1 = g.text("kind", "ELAST", 0), k2 = g.count("kind") >= 2 ? g.text("kind", "", 1) : std::string();
+    if (k1 != "ELAST" || !(k2.empty() || k2 == "KV"))
+      IO_abort("MAT_read: only kind='ELAST' and kind='ELAST','KV' are on the B200 path (PLAST, DMG, VISCO are stateful rheologies)");
     const long m = in.find("MAT_ELASTIC", (size_t)m0);
-    if (kv) {  // MAT_KV_read (SRC/mat_kelvin_voigt.f90:35-66)
-      if (!first) IO_abort("MAT_read: Kelvin-Voigt damping is provided for a single material");
+    if (m < 0) IO_abort("MAT_ELAST_read: MAT_ELASTIC input block not found");
+    const nml_group& e = in.at((size_t)m);  // SRC/mat_elastic.f90:104-129
+    if (e.has("c11") || e.has("c55") || e.has("c11h") || e.has("c55h"))
+      IO_abort("MAT_ELAST_read: anisotropic materials go through the generic C-ABI (s2d_set_elastic), not this host");
+    size_t cur = (size_t)m + 1;  // MAT_setProp reads each property's DIST_* block forward, in the order rho, cp, cs
+    M.rho = DIST_CD_Read(in, e, "rho", 0.0, cur);
+    M.cp = DIST_CD_Read(in, e, "cp", 0.0, cur);
+    M.cs = DIST_CD_Read(in, e, "cs", 0.0, cur);
+    if (M.rho.dist == 0 && !(M.rho.c > 0)) IO_abort("MAT_ELAST_read: undefined density (rho)");
+    if ((M.cp.dist == 0 && !(M.cp.c > 0)) || (M.cs.dist == 0 && !(M.cs.c > 0))) IO_abort("MAT_ELAST_read: incomplete input");
+    if (k2 == "KV") {  // MAT_KV_read (SRC/mat_kelvin_voigt.f90:35-66)
       const long q = in.find("MAT_KV", (size_t)m0);
       if (q < 0) IO_abort("MAT_KV_read: MAT_KV input block not found");
-      size_t cur = (size_t)q + 1;
-      pb.kv_eta = DIST_CD_Read(in, in.at((size_t)q), "eta", 0.0, cur);
-      pb.ETAxDT = in.at((size_t)q).logical("etaxdt", true);
+      size_t c2 = (size_t)q + 1;
+      M.eta = DIST_CD_Read(in, in.at((size_t)q), "eta", 0.0, c2);
+      M.ETAxDT = in.at((size_t)q).logical("etaxdt", true);
+      M.kv = true;
       pb.has_kv = true;
     }
-    const nml_group& e = in.at((size_t)m);  // SRC/mat_elastic.f90:104-129
-    if (e.has("cph") || e.has("csh") || e.has("rhoh") || e.has("c11")) IO_abort("MAT_ELAST_read: distributions / anisotropy are not provided here");
-    const double rho = e.real8("rho", 0.0), cp = e.real8("cp", 0.0), cs = e.real8("cs", 0.0);
-    if (!(rho > 0 && cp > 0 && cs > 0)) IO_abort("MAT_ELAST_read: rho, cp, cs must be positive");
-    if (!first && (rho != pb.rho || cp != pb.cp || cs != pb.cs))
-      IO_abort("MAT_read: several different materials are not provided by the B200 structured builder");
-    pb.rho = rho;
-    pb.cp = cp;
-    pb.cs = cs;
+    M.set = true;
   }
+  pb.rho = pb.mat[0].rho.c;
+  pb.cp = pb.mat[0].cp.c;
+  pb.cs = pb.mat[0].cs.c;
   // BC_read (SRC/bc_gen.f90:98-188): in input order
   for (long b = in.find("BC_DEF"); b >= 0; b = in.find("BC_DEF", (size_t)b + 1)) {
     const nml_group& g = in.at((size_t)b);
@@ -572,6 +618,50 @@ inline void init_main(problem_type& pb) {
   if (rc != S2D_OK) IO_abort("init_main: s2d_cart_create failed (code " + std::to_string(rc) + ")");
   double dt = 0;
   s2d_check(pb, s2d_cart_info(pb.gpu, &pb.npoin, &pb.nelem_total, &dt), "init_main");
+  // MAT_init_prop (SRC/mat_gen.f90:204-303): the element tags of CART_build (mesh_cartesian.f90:270-290), then every
+  // tag's material evaluated at the GLL points of its elements.  One homogeneous material for the whole box is what
+  // s2d_cart_create already built; anything else is handed over with s2d_cart_set_material.
+  const int nx = pb.nelem[0], nz = pb.nelem[1], N = pb.ngll, n2 = N * N;
+  std::vector<int> tag((size_t)nx * nz, pb.domains.empty() ? 1 : 0);
+  for (const auto& dm : pb.domains)
+    for (int i = dm.ex[0]; i <= dm.ex[1]; ++i)
+      for (int j = dm.ez[0]; j <= dm.ez[1]; ++j) tag[(size_t)(i - 1) + (size_t)nx * (j - 1)] = dm.tag;
+  if (pb.fztag > 0) {  // the element rows next to the fault (at the bottom when ezflt = 0)
+    const int j1 = std::max(pb.ezflt + 1 - pb.fznz, 1), j2 = std::min(pb.ezflt + pb.fznz, nz);
+    for (int j = j1; j <= j2; ++j)
+      for (int i = 1; i <= nx; ++i) tag[(size_t)(i - 1) + (size_t)nx * (j - 1)] = pb.fztag;
+  }
+  bool one_material = pb.mat[0].homogeneous();
+  for (int tg : tag) {
+    if (tg == 0) IO_abort("CART_build: Domain tags not entirely set");
+    if (tg < 1 || tg > (int)pb.mat.size() || !pb.mat[(size_t)tg - 1].set)
+      IO_abort("ELAST_init: element tag does not correspond to a material number");
+    const auto& M = pb.mat[(size_t)tg - 1];
+    one_material = one_material && M.homogeneous() && M.rho.c == pb.rho && M.cp.c == pb.cp && M.cs.c == pb.cs;
+  }
+  std::vector<int32_t> ibool;
+  std::vector<double> coord;
+  if (!one_material || pb.has_kv) {
+    ibool.resize((size_t)pb.nelem_total * n2);
+    coord.resize(2 * (size_t)pb.npoin);
+    s2d_check(pb, s2d_cart_get(pb.gpu, ibool.data(), nullptr, nullptr, coord.data()), "MAT_init_prop");
+  }
+  if (!one_material) {
+    if (pb.hash_seed) IO_abort("init_main: the synthetic hash medium replaces the deck's materials; give one homogeneous material");
+    std::vector<double> rho(ibool.size()), cp(ibool.size()), cs(ibool.size());
+    for (size_t e = 0; e < (size_t)pb.nelem_total; ++e) {
+      const auto& M = pb.mat[(size_t)tag[e] - 1];
+      for (int q = 0; q < n2; ++q) {
+        const size_t nd = (size_t)ibool[e * n2 + q] - 1;
+        const double x = coord[2 * nd], z = coord[2 * nd + 1];
+        rho[e * n2 + q] = M.rho.eval(x, z);
+        cp[e * n2 + q] = M.cp.eval(x, z);
+        cs[e * n2 + q] = M.cs.eval(x, z);
+      }
+    }
+    s2d_check(pb, s2d_cart_set_material(pb.gpu, rho.data(), cp.data(), cs.data()), "MAT_init_prop");
+    s2d_check(pb, s2d_cart_info(pb.gpu, &pb.npoin, &pb.nelem_total, &dt), "init_main");
+  }
   // TIME_init (SRC/time.f90:323-341)
   timescheme_type& t = pb.time;
   if (!(t.dt > 0.0)) {
@@ -579,14 +669,21 @@ inline void init_main(problem_type& pb) {
     if (t.total > 0.0) t.nt = (int)std::ceil(t.total / t.dt);
     t.total = t.nt * t.dt;
   }
-  if (pb.has_kv) {  // MAT_KV_init_elem_work (SRC/mat_kelvin_voigt.f90:117-133): eta at the GLL nodes, times dt
-    std::vector<double> coord(2 * (size_t)pb.npoin), eta((size_t)pb.npoin);
-    s2d_check(pb, s2d_cart_get(pb.gpu, nullptr, nullptr, nullptr, coord.data()), "MAT_KV_init");
-    for (size_t q = 0; q < eta.size(); ++q) {
-      eta[q] = pb.kv_eta.eval(coord[2 * q], coord[2 * q + 1]);
-      if (pb.ETAxDT) eta[q] = t.dt * eta[q];
+  if (pb.has_kv) {  // MAT_KV_init_elem_work (SRC/mat_kelvin_voigt.f90:117-133): eta(ngll,ngll) of every KV element, times dt
+    std::vector<int32_t> ids;
+    std::vector<double> eta;
+    for (size_t e = 0; e < (size_t)pb.nelem_total; ++e) {
+      const auto& M = pb.mat[(size_t)tag[e] - 1];
+      if (!M.kv) continue;
+      ids.push_back((int32_t)e + 1);
+      for (int q = 0; q < n2; ++q) {
+        const size_t nd = (size_t)ibool[e * n2 + q] - 1;
+        double v = M.eta.eval(coord[2 * nd], coord[2 * nd + 1]);
+        if (M.ETAxDT) v = t.dt * v;
+        eta.push_back(v);
+      }
     }
-    s2d_check(pb, s2d_cart_set_kv(pb.gpu, eta.data()), "MAT_KV_init");
+    if (!ids.empty()) s2d_check(pb, s2d_cart_set_kv_elems(pb.gpu, (int32_t)ids.size(), ids.data(), eta.data()), "MAT_KV_init");
   }
   // BC_init (SRC/bc_gen.f90:190-251): periodic boundaries first, then input order
   for (bc_type& bc : pb.bc)

@@ -311,6 +311,17 @@ int s2d_cart_add_receivers_interp(s2d_handle h, int32_t nx, double xa, double za
  * or a distribution evaluated at the node coordinates), which makes the element-wise d + eta*v node-wise.
  * With it the node update runs in separate passes (no fused step). */
 int s2d_cart_set_kv(s2d_handle h, const double* eta_node);
+/* Caller-supplied material on the structured builder: what MAT_getProp returns once MAT_read / MAT_init_prop have
+ * run (SRC/mat_gen.f90:101-303) -- every tag with its own material, every property a constant or a DIST_* field --
+ * evaluated by the host at the GLL points: rho, cp, cs (ngll,ngll,nelem), elements in the box's natural order
+ * (element (ix,iz), 0-based, at ix + nx*iz; the reference's order before MESH_STRUCTURED_renumber).  Rebuilds the
+ * coefficient planes (MAT_ELAST_init_a, mat_elastic.f90:290-360), the mass (mat_mass.f90:29-61) and, unless the
+ * scheme came with a dt, the time step (init.f90:187-225, time.f90:334-341).  Before any boundary condition. */
+int s2d_cart_set_material(s2d_handle h, const double* rho, const double* cp, const double* cs);
+/* matwrk_kv_type%eta (SRC/mat_kelvin_voigt.f90:117-150) of the Kelvin-Voigt elements of the box: eta(ngll,ngll,nkv),
+ * already times dt when ETAxDT, elem_ids(nkv) 1-based in natural element order.  The force kernel then sees
+ * d + eta*v element by element (:137-150).  Replaces a previous s2d_cart_set_kv. */
+int s2d_cart_set_kv_elems(s2d_handle h, int32_t nkv, const int32_t* elem_ids, const double* eta);
 int s2d_cart_info(s2d_handle h, int64_t* npoin, int64_t* nelem, double* dt);
 /* Overrides the time step (time%dt) before any boundary is added.  x-strips of one global mesh
  * must agree on dt: the host takes the minimum of the per-strip Courant steps (the reference takes

@@ -125,6 +125,8 @@ _SIGS = {
                                       C.c_int32, C.c_int32],
     "s2d_cart_add_moment": [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_int32)],
     "s2d_cart_receiver_info": [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p],
+    "s2d_cart_set_material": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    "s2d_cart_set_kv_elems": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
     "s2d_cart_info": [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)],
     "s2d_cart_set_dt": [C.c_void_p, C.c_double],
     "s2d_cart_get": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],

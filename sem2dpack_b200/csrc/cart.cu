@@ -45,6 +45,10 @@ struct CartGeom {
   int halo_left, halo_right;
   StripGeom S;  // lattice / strip decomposition of the z-marching kernel
   double xgll[10], wgll[10];
+  // caller-supplied material (s2d_cart_set_material): rho, cp, cs at every GLL point of every element,
+  // (ngll,ngll,nelem) in natural element order; host pointers in the host copy of this struct, device pointers
+  // in the copy the kernels receive (CartState::dev_geom)
+  const double* mat[3];
 };
 
 __host__ __device__ inline bool row_detached(const CartGeom& G, int iz) {  // no element below shares nodes
@@ -124,6 +128,13 @@ __host__ __device__ inline long long cart_lat_id(const CartGeom& G, int ix, int 
 // material at GLL point (i,j) (0-based) of element (ix,iz)
 __host__ __device__ inline void cart_material(const CartGeom& G, int ix, int iz, int i, int j, double& rho,
                                               double& cp, double& cs) {
+  if (G.mat[0]) {  // what MAT_getProp returns once MAT_init_prop has run (mat_gen.f90:204-303)
+    const size_t q = ((size_t)iz * G.nx + ix) * (G.N * G.N) + (size_t)j * G.N + i;
+    rho = G.mat[0][q];
+    cp = G.mat[1][q];
+    cs = G.mat[2][q];
+    return;
+  }
   if (G.seed == 0) {
     rho = G.rho;
     cp = G.cp;
@@ -411,6 +422,14 @@ struct CartState {
   std::vector<FaultInfo> faults;
   std::vector<double> rec_coord;  // (2, nx) positions of the relocated stations (rec%coord, receivers.f90:231-303)
   int coef_mode = 0;  // 0 = compact (lambda, mu) where the rheology allows, 1 = all planes stored
+  std::vector<double> h_mat[3];   // s2d_cart_set_material: host and device copies of rho, cp, cs
+  DevBuf<double> d_mat[3];
+  bool dt_given = false;
+  CartGeom dev_geom() const {     // the geometry as the kernels see it
+    CartGeom g = G;
+    for (int q = 0; q < 3; ++q) g.mat[q] = d_mat[q].p;
+    return g;
+  }
   bool nm() const { return scheme.kind == 1 || scheme.kind == 2; }  // 'newmark', 'HHT-alpha'
   double CoefA2V() const { return nm() ? scheme.gamma * scheme.dt : scheme.dt; }        // time.f90:443-456
   double CoefA2D() const { return nm() ? scheme.beta * scheme.dt * scheme.dt : 0.0; }    // time.f90:426-440
@@ -425,6 +444,48 @@ void* engine_cart(s2d_handle h);
 EngineBase* engine_impl(s2d_handle h);
 void set_error(s2d_handle h, const std::string& m);
 
+// max over the grid of c / min(dx,dz) (CHECK_grid, init.f90:187-225) with the current material
+static double cart_grid_cfl(const CartState& S) {
+  const CartGeom G = S.dev_geom();
+  DevBuf<unsigned long long> mx;
+  mx.alloc(1);
+  mx.zero();
+  const long long tot = (long long)G.nx * G.nz * G.N * G.N;
+  k_cart_cfl<<<(unsigned)((tot + 255) / 256), 256>>>(G, mx.p);
+  S2D_CUDA(cudaGetLastError());
+  unsigned long long bits = 0;
+  S2D_CUDA(cudaMemcpy(&bits, mx.p, 8, cudaMemcpyDeviceToHost));
+  double v;
+  std::memcpy(&v, &bits, 8);
+  return v;
+}
+
+// operator data of the box from the current material: coefficient planes in the strip layout
+// (MAT_ELAST_init_a, mat_elastic.f90:290-360), assembled mass (MAT_MASS_init, mat_mass.f90:29-61)
+template <typename T>
+static void cart_operator(Engine<T>& E, CartState& S) {
+  const CartGeom G = S.dev_geom();
+  const int N = G.N, N2 = N * N;
+  const int nelast = (G.ndof == 1) ? 2 : 6;
+  cudaStream_t st = E.stream;
+  const long long tot = (long long)E.nelem * N2;
+  const unsigned nblk = (unsigned)((tot + 255) / 256);
+  E.ncoefsets = (G.seed != 0 || G.mat[0]) ? E.nelem : 1;
+  E.p_coef.alloc((size_t)E.nelem * (E.cart_compact ? 2 : nelast) * N2);
+  k_cart_coef<T><<<nblk, 256, 0, st>>>(G, E.p_coef.p, nelast, E.cart_compact);
+  // mass (kept un-inverted in rmass until commit); the pad columns of the lattice rows get 1 so that 1/M and
+  // every node-wise pass stay finite there (their fields are zero and nothing ever reads them)
+  k_fill<T><<<(unsigned)std::min<size_t>((E.rmass.n + 255) / 256, 148 * 32), 256, 0, st>>>(E.rmass.p, E.rmass.n, (T)1);
+  k_cart_mass<T><<<nblk, 256, 0, st>>>(G, E.rmass.p, E.npoin);
+  S2D_CUDA(cudaGetLastError());
+  // the assembled mass as MAT_MASS_init leaves it (mat_mass.f90:50-57), before BC_init augments it: what
+  // energy_compute's sum(w*rho*v2) (energy.f90:49-106) amounts to node by node
+  E.mass.alloc(E.npoin);
+  k_cast_copy<T, double><<<(unsigned)((E.npoin + 255) / 256), 256, 0, st>>>(E.rmass.p, E.mass.p, E.npoin);
+  S2D_CUDA(cudaGetLastError());
+  S2D_CUDA(cudaStreamSynchronize(st));
+}
+
 template <typename T>
 static void cart_build(Engine<T>& E, CartState& S) {
   CartGeom& G = S.G;
@@ -438,22 +499,16 @@ static void cart_build(Engine<T>& E, CartState& S) {
   E.nelast = nelast;
   E.kd2 = (N == 5) ? 1 : 0;  // OPT_NGLL (constants.f90:6, mat_elastic.f90:412)
   E.nkv = 0;
-  E.ncoefsets = G.seed != 0 ? E.nelem : 1;
   E.p_hetero = true;
   E.cart_compact = (G.ndof == 2 && S.coef_mode == 0) ? 1 : 0;
   E.cart_cdx = 2.0 / G.hx;
   E.cart_cdz = 2.0 / G.hz;
   E.cart_cdet = (0.5 * G.hx) * (0.5 * G.hz);
   E.cart_wgll.assign(G.wgll, G.wgll + N);
-  E.p_coef.alloc((size_t)E.nelem * (E.cart_compact ? 2 : nelast) * N2);
-  k_cart_coef<T><<<nblk, 256, 0, st>>>(G, E.p_coef.p, nelast, E.cart_compact);
-  // mass (kept un-inverted in rmass until commit); the pad columns of the lattice rows get 1 so that 1/M and
-  // every node-wise pass stay finite there (their fields are zero and nothing ever reads them)
-  k_fill<T><<<(unsigned)std::min<size_t>((E.rmass.n + 255) / 256, 148 * 32), 256, 0, st>>>(E.rmass.p, E.rmass.n, (T)1);
-  k_cart_mass<T><<<nblk, 256, 0, st>>>(G, E.rmass.p, E.npoin);
-  S2D_CUDA(cudaGetLastError());
+  cart_operator<T>(E, S);
   E.init_strip_tables(G.S);  // halo arrays and decomposition flags of the strip kernel
-  const CartGeom Gc = G;
+  CartGeom Gc = G;
+  Gc.mat[0] = Gc.mat[1] = Gc.mat[2] = nullptr;  // the permutations only use the numbering
   Engine<T>* Ep = &E;
   E.cart_to_ref = [Ep, Gc, nblk](const T* lat, double* ref) {
     k_cart_permute<T, double><<<nblk, 256, 0, Ep->stream>>>(Gc, lat, ref, Ep->npoin_ref, Ep->npoin, Gc.ndof, 1);
@@ -471,11 +526,6 @@ static void cart_build(Engine<T>& E, CartState& S) {
     k_cart_permute<double, double><<<nblk, 256, 0, Ep->stream>>>(Gc, ref, lat, Ep->npoin_ref, Ep->npoin, 1, 0);
     S2D_CUDA(cudaGetLastError());
   };
-  // the assembled mass as MAT_MASS_init leaves it (mat_mass.f90:50-57), before BC_init augments it: what
-  // energy_compute's sum(w*rho*v2) (energy.f90:49-106) amounts to node by node
-  E.mass.alloc(E.npoin);
-  k_cast_copy<T, double><<<(unsigned)((E.npoin + 255) / 256), 256, 0, st>>>(E.rmass.p, E.mass.p, E.npoin);
-  S2D_CUDA(cudaGetLastError());
   S2D_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -582,18 +632,8 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
     S->courant = D->courant;
     S->coef_mode = D->coef_mode != 0 ? 1 : (env_int("S2D_COEF_FULL", 0) != 0 ? 1 : 0);
     // dt from the Courant number (init.f90:187-225, time.f90:334-341)
-    {
-      DevBuf<unsigned long long> mx;
-      mx.alloc(1);
-      mx.zero();
-      const long long tot = nelem * G.N * G.N;
-      k_cart_cfl<<<(unsigned)((tot + 255) / 256), 256>>>(G, mx.p);
-      unsigned long long bits = 0;
-      S2D_CUDA(cudaMemcpy(&bits, mx.p, 8, cudaMemcpyDeviceToHost));
-      double v;
-      std::memcpy(&v, &bits, 8);
-      S->grid_cfl = v;
-    }
+    S->grid_cfl = cart_grid_cfl(*S);
+    S->dt_given = S->scheme.dt > 0.0;
     if (!(S->scheme.dt > 0.0)) S->scheme.dt = D->courant / S->grid_cfl;
     S->dt = S->scheme.dt;
     std::unique_ptr<EngineBase> impl;
@@ -613,6 +653,52 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
     fprintf(stderr, "s2d_cart_create: %s\n", e.what());
     return S2D_ECUDA;
   }
+}
+
+// MAT_init_prop's result for the box (mat_gen.f90:204-303): the caller evaluated its materials (per-tag constants,
+// DIST_* fields) at the GLL points of every element; the operator data are rebuilt from them
+int s2d_cart_set_material(s2d_handle h, const double* rho, const double* cp, const double* cs) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(rho && cp && cs, "cart_set_material: null pointer");
+  S2D_REQUIRE(!Eb->committed && !S.bc_added, "cart_set_material: must precede the boundary conditions (BC_init reads the mass)");
+  S2D_REQUIRE(!S.G.halo_left && !S.G.halo_right, "cart_set_material: not available on an x-strip with neighbours");
+  const size_t n = (size_t)Eb->nelem * S.G.N * S.G.N;
+  const double* src[3] = {rho, cp, cs};
+  for (size_t q = 0; q < n; ++q)
+    S2D_REQUIRE(rho[q] > 0.0 && cp[q] > 0.0 && cs[q] > 0.0, "cart_set_material: rho, cp, cs must be positive");
+  for (int k = 0; k < 3; ++k) {
+    S.h_mat[k].assign(src[k], src[k] + n);
+    S.d_mat[k].upload(S.h_mat[k]);
+    S.G.mat[k] = S.h_mat[k].data();
+  }
+  S.grid_cfl = cart_grid_cfl(S);
+  if (!S.dt_given) {  // time.f90:334-341
+    S.scheme.dt = S.courant / S.grid_cfl;
+    S.dt = S.scheme.dt;
+    Eb->scheme.dt = S.dt;
+  }
+  if (Eb->prec == 8) cart_operator<double>(*as_engine<double>(Eb), S);
+  else cart_operator<float>(*as_engine<float>(Eb), S);
+  CART_GUARD_END
+}
+
+// matwrk_kv_type%eta of the Kelvin-Voigt elements (mat_kelvin_voigt.f90:117-150), elements in natural order
+int s2d_cart_set_kv_elems(s2d_handle h, int32_t nkv, const int32_t* elem_ids, const double* eta) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(nkv >= 1 && elem_ids && eta, "cart_set_kv_elems: bad arguments");
+  S2D_REQUIRE(!Eb->committed, "cart_set_kv_elems after commit");
+  const CartGeom& G = S.G;
+  const int N = G.N, n2 = N * N;
+  std::vector<double> pe((size_t)Eb->nelem * n2, 0.0);
+  for (int k = 0; k < nkv; ++k) {
+    const int e = elem_ids[k] - 1;
+    S2D_REQUIRE(e >= 0 && e < Eb->nelem, "cart_set_kv_elems: element id out of range");
+    const int ix = e % G.nx, iz = e / G.nx;
+    for (int j = 0; j < N; ++j)
+      for (int i = 0; i < N; ++i) pe[strip_scalar_index(G.S, ix, iz, i, j)] = eta[(size_t)k * n2 + i + N * j];
+  }
+  Eb->set_strip_eta(pe.data(), pe.size());
+  CART_GUARD_END
 }
 
 int s2d_cart_info(s2d_handle h, int64_t* npoin, int64_t* nelem, double* dt) {

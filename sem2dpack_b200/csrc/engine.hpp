@@ -87,6 +87,7 @@ class EngineBase {
                              const int32_t* einterp, const double* interp) = 0;
   virtual void add_receivers_nodes(int nx, char field, int isamp, int nt_rec, const int32_t* nodes, const double* interp) = 0;
   virtual void set_node_kv(const double* eta_ref) = 0;
+  virtual void set_strip_eta(const double* eta_strip, size_t n) = 0;
   virtual void commit(int variant) = 0;
   virtual void set_fields(const double* d, const double* v, const double* a) = 0;
   virtual void get_fields(double* d, double* v, double* a) = 0;
@@ -834,6 +835,13 @@ class Engine : public EngineBase {
     cart_kv_eta.zero(stream);
     cart_from_ref1(tmp.p, cart_kv_eta.p);
     S2D_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  // eta per element GLL point, already in the strip layout (s2d_cart_set_kv_elems)
+  void set_strip_eta(const double* eta_strip, size_t n) override {
+    S2D_REQUIRE(cart_mode && !committed, "set_strip_eta: builder-made engines only, before commit");
+    upload_as(strip_eta, eta_strip, n);
+    cart_kv_eta.release();
   }
 
   int add_moment(int nterms, const int32_t* node, const double* coef_) override {

@@ -36,6 +36,11 @@
 #include "common.cuh"
 #include "elem_kernels.cuh"
 
+// strips (warps) per CTA of the strip kernel; 4 is the measured best (see strip_warps())
+#ifndef S2D_STRIP_WARPS
+#define S2D_STRIP_WARPS 4
+#endif
+
 namespace s2d {
 
 struct StripGeom {
@@ -89,7 +94,7 @@ constexpr int STRIP_MASK_WORDS = 128;  // a band has at most 32*128 lattice rows
 // lattice / strip decomposition of an nx x nz box (split-node row after element row ezflt); one CTA = a group of
 // adjacent strips, the strips next to a GPU interface form groups of their own
 inline StripGeom make_strip_geom(int N, int ndof, int nx, int nz, int ezflt, int seg, bool halo_left, bool halo_right,
-                                 int warps = 4) {
+                                 int warps = S2D_STRIP_WARPS) {
   StripGeom Q{};
   Q.N = N;
   Q.ndof = ndof;
@@ -223,6 +228,8 @@ struct StripArgs {
   // a_k = -weights * ((c * m1) * m2) with the same order of roundings as the stored planes
   T cdx, cdz, cdet;         // DxiDx = 2/hx, DetaDz = 2/hz, |J| = (hx/2)(hz/2)
   T wg[N];                  // GLL weights: weights(i,j) = |J| * (wg[i] * wg[j])
+  T Hz[N * N];              // DetaDz * hprime, and DetaDz / DxiDx: the metric folded into the contractions
+  T rzx;
 };
 
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
@@ -254,6 +261,22 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group
 #ifndef S2D_STRIP_ROT
 #define S2D_STRIP_ROT 0
 #endif
+// Measurement only (results are WRONG when non-zero): parts of the kernel switched off to see what each costs.
+// bit 0: no warp-tile traffic (xi-contractions from the lane's own column), 1: no coefficient loads, 2: no
+// displacement loads, 3: no v / rmass loads, 4: no v / d_next stores, 5: no per-row CTA barrier.
+// profiles/r2/ablation.md has the numbers.
+#ifndef S2D_ABLATE
+#define S2D_ABLATE 0
+#endif
+// Compact coefficient mode, how the planes of MAT_ELAST_init_a enter.  0: the six planes are formed per GLL point
+// with the reference's sequence of roundings, a_k = -w*((c*m1)*m2) (mat_elastic.f90:334-340,355-357), then the
+// pointwise stage of ELAST_KD*_PSV: 26 FP64 operations per point, bitwise equal to the stored-plane mode.
+// 1 (default): the constant metric factors of the flat grid (DxiDx, DetaDz) are folded into the derivative
+// matrices of the four contractions, so the point only sees lambda, mu and -w: 14 operations per point (a sixth of
+// the kernel's FP64 instructions less); equal to the stored-plane mode to rounding (a few ulp), not bit for bit.
+#ifndef S2D_COMPACT_FOLD
+#define S2D_COMPACT_FOLD 1
+#endif
 // The coefficient block of an element row is one contiguous run of the strip layout: with all six planes
 // stored (7200 B per row of a P-SV strip) it is brought in by ONE TMA bulk copy per warp and row
 // (cp.async.bulk + mbarrier, SASS UBLKCP) instead of 15 per-lane LDGSTS.128, which cost 15.5 L1 wavefronts
@@ -267,7 +290,7 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group
 // Strips per CTA.  Measured on B200 (4096^2, FP64, compact, fused; ms per launch): 4 warps at 168
 // registers, 3 CTAs/SM: 5.82;  5 warps (128 registers, 3 CTAs/SM): 6.02;  6 warps (168, 2 CTAs): 6.41;
 // 8 warps (128, 2 CTAs): 6.58 -- registers (instruction-level parallelism) beat resident warps here.
-constexpr int strip_warps() { return 4; }
+constexpr int strip_warps() { return S2D_STRIP_WARPS; }
 // bytes of the staging area of one warp: coefficient vectors and displacement rows of one element
 // row; in the fused form also the velocities and inverse masses of the nodes it will advance
 // (fused: 0 plain force evaluation, 1 leapfrog update, 2 explicit Newmark update: also the old accelerations)
@@ -277,7 +300,7 @@ constexpr size_t strip_stage_bytes(int N, int NDOF, int tsize, int fused, bool c
   return c + u + (fused ? u + r : 0) + (fused == 2 ? u : 0);
 }
 constexpr int strip_min_ctas(int N, int tsize, bool compact = false) {
-  return N <= 6 ? (tsize == 4 ? 4 : 3) : (tsize == 4 ? 2 : 1);
+  return (N <= 6 ? (tsize == 4 ? 4 : 3) : (tsize == 4 ? 2 : 1)) * 4 / strip_warps();
 }
 
 template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false>
@@ -370,23 +393,26 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   // (k = 1..N-1): a fifth fewer shared-memory wavefronts, the contraction's sum starts with the own term.
   constexpr bool ROT = S2D_STRIP_ROT != 0;
   constexpr int NR = ROT ? N - 1 : N;
+  constexpr bool FOLD = COMPACT && (S2D_COMPACT_FOLD != 0);
+  const T* const HZ = FOLD ? A.Hz : A.H;   // operand of the eta-contractions (constant bank)
+  const T sx = FOLD ? A.cdx : (T)1;        // xi-contractions: the lane's hprime column / row carries DxiDx
   T Hi[NR], HTi[NR], Hii = 0, HTii = 0;
   int mo[ROT ? N - 1 : 1];
   if (ROT) {
-    Hii = A.H[i + N * i];
+    Hii = A.H[i + N * i] * sx;
     HTii = Hii;
 #pragma unroll
     for (int k = 1; k < N; ++k) {
       const int m = (i + k) % N;
-      Hi[k - 1] = A.H[m + N * i];   // H(m,i)
-      HTi[k - 1] = A.H[i + N * m];  // H(i,m)
+      Hi[k - 1] = A.H[m + N * i] * sx;   // H(m,i)
+      HTi[k - 1] = A.H[i + N * m] * sx;  // H(i,m)
       mo[k - 1] = el * N + m;
     }
   } else {
 #pragma unroll
     for (int m = 0; m < NR; ++m) {
-      Hi[m] = A.H[m + N * i];   // H(m,i)
-      HTi[m] = A.H[i + N * m];  // H(i,m)
+      Hi[m] = A.H[m + N * i] * sx;   // H(m,i)
+      HTi[m] = A.H[i + N * m] * sx;  // H(i,m)
     }
   }
   T U[NDOF][N], Fc[NDOF];
@@ -419,14 +445,15 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   constexpr bool stg_u = S2D_STRIP_STAGE & 1, stg_c = S2D_STRIP_STAGE & 2, stg_v = S2D_STRIP_STAGE & 4;
   auto issue_row = [&](int ezr, const V2* cpr) {
     const size_t rb = (size_t)strip_lat_row(G, ezr, 0) * LX;
-    if (stg_u) {
+    if (stg_u && !(S2D_ABLATE & 4)) {
 #pragma unroll
       for (int c = 0; c < NDOF; ++c)
 #pragma unroll
         for (int j = 1; j < N; ++j)
           stage_copy<sizeof(T)>(st_u + (c * (N - 1) + j - 1) * 32, up + A.npoin * c + rb + (size_t)j * LX);
     }
-    if (tma_c) {
+    if (S2D_ABLATE & 2) {
+    } else if (tma_c) {
       if (lane == 0) {
         const unsigned bytes = (unsigned)(cp_row * sizeof(V2));
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the warp's reads of the block come first
@@ -464,7 +491,12 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       // copies of what the end of this iteration needs (v, rmass) and of the whole next row
       stage_wait<0>();
       V2 a2[NPL / 2][N];
-      if (stg_u) {
+      if (S2D_ABLATE & 4) {
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+          for (int j = 1; j < N; ++j) U[c][j] = U[c][0] + (T)j;
+      } else if (stg_u) {
 #pragma unroll
         for (int c = 0; c < NDOF; ++c)
 #pragma unroll
@@ -475,7 +507,15 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
 #pragma unroll
           for (int j = 1; j < N; ++j) U[c][j] = up[A.npoin * c + rowbase + (size_t)j * LX];
       }
-      if (tma_c) {
+      if (S2D_ABLATE & 2) {
+#pragma unroll
+        for (int pp = 0; pp < NPL / 2; ++pp)
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            a2[pp][j].x = U[0][0] + (T)(pp + j);
+            a2[pp][j].y = (T)3e10 + U[0][0];
+          }
+      } else if (tma_c) {
         mbar_wait(&cbar[warp], cphase);
         cphase ^= 1u;
 #pragma unroll
@@ -500,7 +540,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           const unsigned long long two = ((unsigned long long)rowmask[(o >> 5) + 1] << 32) | rowmask[o >> 5];
           defer = coldef ? ~0u : (unsigned)(two >> (o & 31));
         }
-        if (st_ok) {
+        if (st_ok && !(S2D_ABLATE & 8)) {
           if (stg_v) {
 #pragma unroll
             for (int j = 0; j < N - 1; ++j) {
@@ -554,10 +594,12 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         if constexpr (KV) return Ue;
         else return U;
       }();
+      if (!(S2D_ABLATE & 1)) {
 #pragma unroll
-      for (int c = 0; c < NDOF; ++c)
+        for (int c = 0; c < NDOF; ++c)
 #pragma unroll
-        for (int j = 0; j < N; ++j) tlw[c][j][lanep] = Ut[c][j];
+          for (int j = 0; j < N; ++j) tlw[c][j][lanep] = Ut[c][j];
+      }
       __syncwarp();
       T gxi[NDOF][N], get[NDOF][N];
 #pragma unroll
@@ -566,12 +608,12 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         for (int j = 0; j < N; ++j) {
           T row[NR];  // the 5 lanes of an element read the same word: one wavefront per value
 #pragma unroll
-          for (int m = 0; m < NR; ++m) row[m] = tlw[c][j][ROT ? mo[m] : el * N + m];
+          for (int m = 0; m < NR; ++m) row[m] = (S2D_ABLATE & 1) ? Ut[c][(j + m) % N] : tlw[c][j][ROT ? mo[m] : el * N + m];
           T s1 = ROT ? Hii * Ut[c][j] : (T)0, s2 = 0;
 #pragma unroll
           for (int m = 0; m < NR; ++m) s1 += Hi[m] * row[m];                   // (Ht U)(i,j)
 #pragma unroll
-          for (int m = 0; m < N; ++m) s2 += Ut[c][m] * A.H[m + N * j];         // (U H)(i,j)
+          for (int m = 0; m < N; ++m) s2 += Ut[c][m] * HZ[m + N * j];          // (U H)(i,j)
           gxi[c][j] = s1;
           get[c][j] = s2;
         }
@@ -580,6 +622,20 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       T tH[NDOF][N], tHt[NDOF][N];
 #pragma unroll
       for (int j = 0; j < N; ++j) {
+        if constexpr (FOLD) {
+          // gxi carries DxiDx, get carries DetaDz; the second contractions carry the other factor of each plane:
+          //   fx = (DxiDx H)(-w [Kx px + la qz]) + (-w mu [qx + DetaDz Uz,xi]) (DetaDz Ht)      (KD2: a4*(Ux,eta + Uz,xi),
+          //   fz = (DxiDx H)(-w mu [qx + pz])    + (-w [la px + Kx qz]) (DetaDz Ht)              mat_elastic.f90:612)
+          const T la = a2[0][j].x, mu = a2[0][j].y;
+          const T kx = la + T(2) * mu;
+          const T px = gxi[0][j], pz = gxi[NDOF - 1][j], qx = get[0][j], qz = get[NDOF - 1][j];
+          const T shear = mu * (qx + pz);
+          tH[0][j] = nW[j] * fma(kx, px, la * qz);
+          tHt[0][j] = KD2 ? nW[j] * (mu * fma(A.rzx, pz, qx)) : nW[j] * shear;
+          tH[NDOF - 1][j] = nW[j] * shear;
+          tHt[NDOF - 1][j] = nW[j] * fma(la, px, kx * qz);
+          continue;
+        }
         T ar[NEL], g1[NDOF], g2[NDOF], o1[NDOF], o2[NDOF];
         if constexpr (COMPACT) {
           const T la = a2[0][j].x, mu = a2[0][j].y;
@@ -612,10 +668,12 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         }
       }
       // ---- second contractions: H tH through the tile, tHt Ht in registers
+      if (!(S2D_ABLATE & 1)) {
 #pragma unroll
-      for (int c = 0; c < NDOF; ++c)
+        for (int c = 0; c < NDOF; ++c)
 #pragma unroll
-        for (int j = 0; j < N; ++j) tlw[c][j][lanep] = tH[c][j];
+          for (int j = 0; j < N; ++j) tlw[c][j][lanep] = tH[c][j];
+      }
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < NDOF; ++c)
@@ -623,12 +681,12 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         for (int j = 0; j < N; ++j) {
           T row[NR];
 #pragma unroll
-          for (int m = 0; m < NR; ++m) row[m] = tlw[c][j][ROT ? mo[m] : el * N + m];
+          for (int m = 0; m < NR; ++m) row[m] = (S2D_ABLATE & 1) ? tH[c][(j + m) % N] : tlw[c][j][ROT ? mo[m] : el * N + m];
           T s1 = ROT ? HTii * tH[c][j] : (T)0, s2 = 0;
 #pragma unroll
           for (int m = 0; m < NR; ++m) s1 += HTi[m] * row[m];                  // (H tH)(i,j)
 #pragma unroll
-          for (int m = 0; m < N; ++m) s2 += tHt[c][m] * A.H[j + N * m];        // (tHt Ht)(i,j)
+          for (int m = 0; m < N; ++m) s2 += tHt[c][m] * HZ[j + N * m];         // (tHt Ht)(i,j)
           f[c][j] = s1 + s2;
         }
       __syncwarp();
@@ -650,7 +708,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     // (producer / consumer named barriers between neighbouring warps instead of this CTA barrier were
     // tried with two slots and hung: two bar.arrive of a producer that runs a row ahead complete a 64-thread
     // phase on their own.  Strict alternation would work but couples the pair as tightly as this barrier.)
-    if (WARPS > 1) __syncthreads();
+    if (WARPS > 1 && !(S2D_ABLATE & 32)) __syncthreads();
     if (wact) {
       if (take) {  // column shared with the strip on the left (same group)
 #pragma unroll
@@ -669,7 +727,14 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         // component (mat_mass.f90:56-57; only bc_abso.f90:243 makes the columns differ, on deferred
         // nodes), so one read of component 1 serves all of them.
         T vv[NDOF][N - 1], rm[N - 1];
-        if (FUSED) {  // requested at the top of this iteration; the next row's copies may still be in flight
+        if (FUSED && (S2D_ABLATE & 8)) {
+#pragma unroll
+          for (int j = 0; j < N - 1; ++j) {
+            rm[j] = (T)1e-9;
+#pragma unroll
+            for (int c = 0; c < NDOF; ++c) vv[c][j] = U[c][j];
+          }
+        } else if (FUSED) {  // requested at the top of this iteration; the next row's copies may still be in flight
           if (stg_v) {
             stage_wait<1>();
 #pragma unroll
@@ -707,9 +772,10 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
             } else {  // solver.f90:157-158 (leapfrog) / :78-81 (Newmark), then the predictor of the next step
               const T acc = rm[j] * f[c][j];
               const T vn = vv[c][j] + A.c3 * acc;
-              A.v_out[q] = vn;
               T dn = U[c][j] + A.dt * vn;
               if (NM) dn = dn + A.c1 * acc;
+              if ((S2D_ABLATE & 16) && dn != (T)12345.678) continue;  // keeps the arithmetic alive, never stores
+              A.v_out[q] = vn;
               A.d_next[q] = dn;
               if (A.a_out) A.a_out[q] = acc;
             }
@@ -1089,6 +1155,8 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
     A.cdz = (T)io.cdz;                                                                            \
     A.cdet = (T)io.cdet;                                                                          \
     for (int k = 0; k < NN; ++k) A.wg[k] = io.wgll ? (T)io.wgll[k] : (T)0;                        \
+    for (int k = 0; k < NN * NN; ++k) A.Hz[k] = (T)(io.cdz * io.hprime[k]);                        \
+    A.rzx = (T)(io.cdx != 0.0 ? io.cdz / io.cdx : 0.0);                                           \
     const unsigned nb = (unsigned)G.nitems;                                                       \
     const int mode = !fused ? 0 : (io.newmark ? 2 : 1);                                           \
     if (io.eta) { /* Kelvin-Voigt elements: plain force evaluation from d + eta*v */               \

@@ -340,6 +340,18 @@ class CartEngine(Engine):
         self._ck(self.L.s2d_cart_add_receivers(self.h, nx, first[0], first[1], last[0], last[1],
                                                field.encode()[:1], isamp, nt_rec))
 
+    def set_material(self, rho, cp, cs):
+        """rho, cp, cs (nelem, ngll, ngll) [e][j][i] at the GLL points, natural element order (s2d_cart_set_material)"""
+        self._ck(self.L.s2d_cart_set_material(self.h, _ptr(_f64(rho)), _ptr(_f64(cp)), _ptr(_f64(cs))))
+        npoin, nelem, dtv = C.c_int64(), C.c_int64(), C.c_double()
+        self._ck(self.L.s2d_cart_info(self.h, C.byref(npoin), C.byref(nelem), C.byref(dtv)))
+        self.dt = dtv.value
+
+    def set_kv_elems(self, elem_ids, eta):
+        """eta (nkv, ngll, ngll) of the Kelvin-Voigt elements, ids 1-based in natural order (s2d_cart_set_kv_elems)"""
+        elem_ids = _i32(elem_ids)
+        self._ck(self.L.s2d_cart_set_kv_elems(self.h, elem_ids.size, _ptr(elem_ids), _ptr(_f64(eta))))
+
     def fill_fields(self, seed, amp_d, amp_v):
         """seeded non-trivial state (hash noise keyed by global lattice coordinates); accel = 0"""
         self._ck(self.L.s2d_cart_fill_fields(self.h, int(seed), float(amp_d), float(amp_v)))

@@ -95,9 +95,11 @@ def test_synthetic_benchmark_family(scheme, stacey, nx, nz, ezflt):
 
 @pytest.mark.parametrize("ngll,nx,nz,ezflt", [(5, 19, 13, 6), (6, 11, 9, 4), (9, 7, 8, 0)])
 def test_compact_coefficients_equal_stored_planes(ngll, nx, nz, ezflt):
-    """coef_mode 0 keeps (lambda, mu) per GLL point and forms the six planes of MAT_ELAST_init_a
-    (mat_elastic.f90:334-340,355-357) in registers; coef_mode 1 stores them.  Same sequence of
-    roundings: planes, forces and a whole run are BITWISE equal between the two."""
+    """coef_mode 0 keeps (lambda, mu) per GLL point; coef_mode 1 stores the six planes of MAT_ELAST_init_a
+    (mat_elastic.f90:334-340,355-357).  The planes s2d_cart_get reports for the compact mode are formed with the
+    reference's sequence of roundings and are BITWISE those of the stored mode; the compact kernel itself folds the
+    constant metric factors of the flat grid into its derivative matrices (S2D_COMPACT_FOLD, strip_kernels.cuh), so
+    forces and a whole run agree with the stored-plane mode to rounding (<= 1e-13), not bit for bit."""
     xl, zl = (0.0, nx * 100.0), (0.0, nz * 130.0)   # non-square elements: KD2's a4*(..) shortcut differs from KD1
     es = [CartEngine(ngll, 2, nx, nz, xl, zl, ezflt=ezflt, seed=SEED, coef_mode=m) for m in (0, 1)]
     planes = [e.get_tables(ibool=False, a=True, rmass=False)[1] for e in es]
@@ -114,7 +116,8 @@ def test_compact_coefficients_equal_stored_planes(ngll, nx, nz, ezflt):
         out.append((f0,) + tuple(e.get_fields()))
         e.close()
     for x, y in zip(*out):
-        assert np.array_equal(x, y)
+        assert np.abs(y).max() > 0
+        assert rel_l2(x, y) <= 1e-13
 
 
 @pytest.mark.parametrize("coef_mode", [0, 1])

@@ -192,3 +192,67 @@ def test_unsupported_input_aborts_like_io_abort(tmp_path):
     assert p.returncode == 1 and "FATAL ERROR" in p.stdout and "MAT_read" in p.stdout
     p = run(tmp_path, harness.deck("testsh").replace("courant = 0.3d0", "courant = 0.9d0"))
     assert p.returncode == 1 and "Courant out of range" in p.stdout
+
+
+def test_velocity_weakening_deck_two_materials_and_a_kelvin_voigt_layer(tmp_path):
+    """EXAMPLES/Velocity_weakening unchanged but for the run length: NGLL=6 P-SV, fztag=2 -> tag 1 ELAST, tag 2
+    ELAST+KV (one element row next to the fault), one-sided rate-and-state fault, ABSORB, DIRNEU, leapfrog.  The host
+    evaluates both materials at the GLL points (s2d_cart_set_material) and hands the KV row over element by element
+    (s2d_cart_set_kv_elems); fault records and potency against the oracle after the same float32 cast."""
+    deck = harness.deck("velweak").replace("TotalTime=0.10d0", "NbSteps=400")
+    assert "NbSteps=400" in deck
+    p = run(tmp_path, deck, "--quiet")
+    assert p.returncode == 0, p.stdout + p.stderr
+    o = orc.Oracle(deck, renumber=False)
+    assert o.i("nkv") == 100 and o.i("ncoefsets") == 2
+    o.step(400)
+    x, rec = read_fault(tmp_path, 1)
+    want = o.arr("bc.0.out").reshape(-1, 6, rec.shape[2])
+    assert rec.shape == want.shape
+    for c in range(5):     # T_stick is undefined for rate-and-state faults (SURVEY 7.3)
+        assert np.abs(rec[:, c] - want[:, c]).max() <= 1e-6 * max(np.abs(want[:, c]).max(), 1e-30), c
+    assert np.abs(rec[-1, 1]).max() > 1e-3            # the fault slips (nucleation patch)
+    pot = np.loadtxt(tmp_path / "Flt01_potency_sem2d.tab")
+    ref = o.arr("bc.0.potency").reshape(-1, pot.shape[1])
+    assert np.abs(pot - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300)
+    o.close()
+
+
+def test_material_distributions_per_tag(tmp_path):
+    """MAT_read / MAT_init_prop (mat_gen.f90:101-303): two MESH_CART_DOMAIN tags, the upper one with an ORDER0
+    density and a GAUSSIAN shear velocity -- seismograms against the oracle"""
+    deck = """&GENERAL iexec=1, ngll=5, fmax=3.d0, ndof=2, title='two materials', verbose='0000', ItInfo=1000 /
+&MESH_DEF method='CARTESIAN' /
+&MESH_CART xlim=0d0,2400d0, zlim=0d0,1600d0, nelem=24,16 /
+&MESH_CART_DOMAIN tag=1, ex=1,24, ez=1,7 /
+&MESH_CART_DOMAIN tag=2, ex=1,24, ez=8,16 /
+&MATERIAL tag=1, kind='ELAST' /
+&MAT_ELASTIC rho=2670.d0, cp=6000.d0, cs=3464.d0 /
+&MATERIAL tag=2, kind='ELAST' /
+&MAT_ELASTIC rhoH='ORDER0', cp=5200.d0, csH='GAUSSIAN' /
+&DIST_ORDER0 xn=2, zn=1 /
+1250d0
+2500d0 2300d0
+&DIST_GAUSSIAN centered_at=1200d0,1200d0, length=700d0,500d0, offset=2800d0, ampli=-400d0, order=1 /
+&BC_DEF tag=1, kind='ABSORB' /
+&BC_DEF tag=2, kind='ABSORB' /
+&BC_DEF tag=4, kind='ABSORB' /
+&TIME NbSteps=300, courant=0.5d0, kind='newmark' /
+&SRC_DEF stf='RICKER', coord=900d0,1000d0, mechanism='FORCE' /
+&STF_RICKER f0=4.d0, onset=0.3d0, ampli=1.d9 /
+&SRC_FORCE angle=30d0 /
+&REC_LINE number=9, field='V', first=200d0,300d0, last=2200d0,1400d0, isamp=1 /
+"""
+    p = run(tmp_path, deck, "--quiet")
+    assert p.returncode == 0, p.stdout + p.stderr
+    o = orc.Oracle(deck, renumber=False)
+    assert o.i("ncoefsets") > 2
+    o.step(300)
+    dt, _, ux = read_sep(tmp_path, "Ux_sem2d.dat")
+    _, _, uz = read_sep(tmp_path, "Uz_sem2d.dat")
+    assert abs(dt - o.f("dt")) <= 1e-6 * dt
+    ref = o.seis()
+    assert np.abs(ref).max() > 0
+    assert np.abs(ux - ref[:, :, 0]).max() <= 2e-6 * np.abs(ref).max()
+    assert np.abs(uz - ref[:, :, 1]).max() <= 2e-6 * np.abs(ref).max()
+    o.close()

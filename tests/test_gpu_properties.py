@@ -61,7 +61,10 @@ def test_runs_are_bit_reproducible_and_modes_agree(scheme_kind):
         e.close()
     for x, y, z in zip(*out):
         assert np.array_equal(x, y)      # same mode twice: no dependence on the order CTAs meet
-        assert np.array_equal(x, z)      # (lambda, mu) in HBM vs all six planes in HBM
+        # (lambda, mu) in HBM vs all six planes in HBM: equal to rounding (the compact kernel folds the metric
+        # factors into its derivative matrices, S2D_COMPACT_FOLD in strip_kernels.cuh)
+        scale = max(float(np.abs(z).max()), 1e-300)
+        assert np.abs(x.astype(np.float64) - z).max() <= 1e-11 * scale
     assert np.abs(out[0][1]).max() > 0
 
 
