@@ -241,6 +241,64 @@ def xdev_check(rank, world, local, args, torch, dist, sync_dt):
     return res
 
 
+def generic_route_record(n, K, W, local, precision, torch):
+    """The drop-in route north_star describes, measured next to the builder's: the SAME n x n heterogeneous box
+    (all six planes a(5,5,6) per element -- what matwrk_elast_type%a holds) is stepped (1) as the structured
+    builder made it and (2) after its arrays went through the generic C-ABI the way a Fortran host hands them
+    over -- s2d_create with ibool in a scrambled (anti-diagonal, RCM-like) element order and the node numbering
+    that follows it, s2d_set_elastic with one block per element, rmass in that numbering -- where s2d_commit
+    recognises the box from the topology and routes it to the same strip kernel."""
+    import numpy as np
+    from sem2dpack_b200 import CartEngine, Engine
+    e1 = CartEngine(NGLL, NDOF, n, n, (0.0, n * H), (0.0, n * H), seed=SEED, scheme_kind=0, courant=0.5,
+                    precision=precision, device=local, coef_mode=1)
+    ib, a, rm, _ = e1.get_tables(ibool=True, a=True, rmass=True)
+    _, _, hprime = e1.get_gll()
+    dt = e1.dt
+    e1.commit()
+    e1.fill_fields(*FILL)
+    e1.step(W, None)
+    torch.cuda.synchronize()
+    ms1 = e1.time_steps(K)
+    k1 = e1.kernel_ms()
+    npoin = e1.npoin
+    e1.close()
+    n2 = NGLL * NGLL
+    ib = ib.reshape(n * n, n2)
+    ix, iz = np.meshgrid(np.arange(n), np.arange(n))                      # element (ix,iz) at ix + n*iz
+    order = np.lexsort((ix.ravel(), (ix + iz).ravel())).astype(np.int64)  # anti-diagonal sweeps, like an RCM front
+    ib = ib[order]
+    _, first = np.unique(ib.ravel(), return_index=True)                   # nodes renumbered by first occurrence
+    old_of_new = ib.ravel()[np.sort(first)]
+    new_of_old = np.empty(npoin + 1, np.int32)
+    new_of_old[old_of_new] = np.arange(1, npoin + 1, dtype=np.int32)
+    ib2 = new_of_old[ib]
+    rm2 = rm.reshape(NDOF, npoin)[:, old_of_new - 1]
+    a2 = a.reshape(n * n, NELAST * n2)[order]
+    del a, ib, rm
+    e2 = Engine(NGLL, NDOF, ib2, hprime, rm2, 0, dt, precision=precision, device=local)
+    e2.set_elastic(NELAST, a2, np.arange(1, n * n + 1, dtype=np.int32), True)
+    del a2
+    e2.commit()
+    route = e2.route()
+    rng = np.random.default_rng(SEED)
+    e2.set_fields(FILL[1] * rng.uniform(-1, 1, npoin * NDOF), FILL[2] * rng.uniform(-1, 1, npoin * NDOF))
+    e2.step(W, None)
+    torch.cuda.synchronize()
+    ms2 = e2.time_steps(K)
+    k2 = e2.kernel_ms()
+    e2.close()
+    ndof = npoin * NDOF
+    peak, _ = peaks()
+    b = moved_bytes_per_dof(True, False, False, W8 if precision == 8 else 4)
+    return {"mesh": f"{n}x{n} elements, heterogeneous, a(5,5,6) per element in HBM, leapfrog, no boundary conditions",
+            "builder_value": ndof * K / (ms1 * 1e-3), "generic_value": ndof * K / (ms2 * 1e-3), "unit": UNIT,
+            "generic_over_builder": ms1 / ms2, "kernel_route": "strip kernel" if route == 1 else "any-mesh patch kernel",
+            "builder_kernel_ms": k1, "generic_kernel_ms": k2, "algorithmic_bytes_per_dof": b,
+            "generic_kernel_frac_of_hbm_peak": (b * ndof / (k2 * 1e-3) / 1e9 / peak) if k2 > 0 else None,
+            "element_order": "anti-diagonal sweeps (ix+iz, ix), node numbering by first occurrence in that order"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -280,6 +338,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-xdev", action="store_true", help="skip the cross-device parity check (N > 1)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (N > 1)")
+    ap.add_argument("--generic-n", type=int, default=1536,
+                    help="elements per side of the generic-route comparison (N = 1 only; 0 = skip)")
     ap.add_argument("--fint-reps", type=int, default=10)
     ap.add_argument("--coef", choices=["compact", "full"], default="compact",
                     help="coefficient storage: (lambda, mu) per GLL point, or all six planes a(5,5,6) per element")
@@ -482,6 +542,8 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks,
         "check": {"vmax": vmax, "dmax": dmax, "note": "max over all ranks of max|v|, max|d| after the run"},
     }
+    if world == 1 and args.generic_n > 0:
+        line["generic_route"] = generic_route_record(min(args.generic_n, args.nx), K, W, local, args.precision, torch)
     if strong is not None:
         line["strong"] = strong
     if xdev is not None:

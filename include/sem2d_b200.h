@@ -337,6 +337,9 @@ int s2d_cart_fill_fields(s2d_handle h, uint64_t seed, double amp_d, double amp_v
  * without moving the whole (npoin,ndof) arrays of s2d_get_fields.  Any pointer may be NULL. */
 int s2d_cart_get_window(s2d_handle h, int32_t gx0, int32_t gz0, int32_t nwx, int32_t nwz, double* displ,
                         double* veloc, double* accel);
+/* get_GLL_info (SRC/gll.f90:19-36) as the builder computed it: xgll(ngll), wgll(ngll), hprime(ngll,ngll) column-major
+ * with hprime(i,j) = h'_i(x_j).  Any pointer may be NULL. */
+int s2d_cart_get_gll(s2d_handle h, double* xgll, double* wgll, double* hprime);
 /* copies of builder outputs for parity tests against the oracle (host pointers, may be NULL) */
 int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double* coord);
 

@@ -129,6 +129,7 @@ _SIGS = {
     "s2d_cart_set_kv_elems": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
     "s2d_cart_info": [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)],
     "s2d_cart_set_dt": [C.c_void_p, C.c_double],
+    "s2d_cart_get_gll": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "s2d_cart_get": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "s2d_cart_fill_fields": [C.c_void_p, C.c_uint64, C.c_double, C.c_double],
     "s2d_cart_get_window": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],

@@ -1225,6 +1225,15 @@ int s2d_cart_receiver_info(s2d_handle h, int32_t* nx, double* coord) {
   CART_GUARD_END
 }
 
+int s2d_cart_get_gll(s2d_handle h, double* xgll, double* wgll, double* hprime) {
+  CART_GUARD_BEGIN
+  const int N = S.G.N;
+  if (xgll) std::copy(S.G.xgll, S.G.xgll + N, xgll);
+  if (wgll) std::copy(S.G.wgll, S.G.wgll + N, wgll);
+  if (hprime) std::copy(S.H, S.H + N * N, hprime);
+  CART_GUARD_END
+}
+
 int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double* coord) {
   CART_GUARD_BEGIN
   const CartGeom& G = S.G;

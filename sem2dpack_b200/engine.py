@@ -364,6 +364,13 @@ class CartEngine(Engine):
         self._ck(self.L.s2d_cart_get_window(self.h, gx0, gz0, nwx, nwz, _ptr(d), _ptr(v), _ptr(aa)))
         return (d, v, aa) if a else (d, v)
 
+    def get_gll(self):
+        """(xgll, wgll, hprime[column-major flat]) of the builder (s2d_cart_get_gll)"""
+        n = self.ngll
+        x, w, H = np.empty(n), np.empty(n), np.empty(n * n)
+        self._ck(self.L.s2d_cart_get_gll(self.h, _ptr(x), _ptr(w), _ptr(H)))
+        return x, w, H
+
     def get_tables(self, ibool=True, a=False, rmass=True, coord=False, nelast=None):
         n2 = self.ngll * self.ngll
         ib = np.empty(self.nelem * n2, np.int32) if ibool else None
