@@ -122,6 +122,9 @@ struct bc_type {
   cd_type cd_Tn, cd_Tt, cd_cohesion, cd_V;
   bool opening = true, has_swf = false, has_rsf = false;
   int swf_kind = 1, rsf_kind = 1, nor_kind = 1;
+  bool has_twf = false;                                                  // SRC/bc_dynflt_twf.f90:12-16
+  int twf_kind = 1;
+  double twf[9] = {0, 0, 0.6, 0.5, 0.6, 1.0, 1e3, 1.7976931348623157e308, 1.7976931348623157e308};  // X,Z,MuS,MuD,Mu0,L,V,T,Dc
   bool swf_healing = false;
   cd_type swf_Dc, swf_MuS, swf_MuD, swf_alpha, swf_p;                    // SRC/bc_dynflt_swf.f90:30-100
   cd_type rsf_Dc, rsf_MuS, rsf_a, rsf_b, rsf_Vstar, rsf_theta, rsf_Vc;   // SRC/bc_dynflt_rsf.f90:30-90
@@ -134,6 +137,7 @@ struct bc_type {
 struct problem_type {
   s2d_handle gpu = nullptr;
   int iexec = 0, ngll = 9, ndof = 2, ItInfo = 100;
+  double W = 0.0;   // &GENERAL W when given (finite seismogenic width, 2.5D), else 0
   std::string title;
   // &MESH_CART
   double xlim[2] = {0, 0}, zlim[2] = {0, 0};
@@ -237,7 +241,10 @@ inline void read_main(problem_type& pb, const std::string& file) {
     if (pb.ndof > 2 || pb.ndof < 1) IO_abort("GENERAL input block: ndof must be 1 or 2 (SH or P-SV)");
     if (pb.ngll <= 0) IO_abort("GENERAL input block: ngll must be positive");
     if (pb.ItInfo <= 0) IO_abort("GENERAL input block: itInfo must be positive");
-    if (g.has("w")) IO_abort("GENERAL: finite seismogenic width W (2.5D) is not provided by the B200 path");
+    if (g.has("w")) {  // seismogenic width of a 2.5D run (SRC/input.f90:82,119,130)
+      pb.W = g.real8("w", 0.0);
+      if (pb.W <= 0.0) IO_abort("GENERAL input block: W must be positive");
+    }
   }
   // MESH_read (SRC/mesh_gen.f90:61-100), CART_read (SRC/mesh_cartesian.f90:82-170)
   k = in.find("MESH_DEF");
@@ -405,8 +412,25 @@ inline void read_main(problem_type& pb, const std::string& file) {
           bc.rsf_Vstar = DIST_CD_Read(in, *w, "vstar", 1.0, c2);
           bc.rsf_theta = DIST_CD_Read(in, *w, "theta", 0.0, c2);
           bc.rsf_Vc = DIST_CD_Read(in, *w, "vc", 1e-6, c2);
-        } else if (law == "TWF") {
-          IO_abort("BC_DYNFLT_read: friction='TWF' is provided by the generic C-ABI, not by this host");
+        } else if (law == "TWF") {  // twf_read (SRC/bc_dynflt_twf.f90:56-100)
+          const nml_group* w = sub("BC_DYNFLT_TWF");
+          static const nml_group none;
+          if (!w) w = &none;
+          bc.has_twf = true;
+          bc.twf_kind = w->integer("kind", 1);
+          bc.twf[0] = w->real8("x", 0.0);
+          bc.twf[1] = w->real8("z", 0.0);
+          bc.twf[2] = w->real8("mus", 0.6);
+          bc.twf[3] = w->real8("mud", 0.5);
+          bc.twf[4] = w->real8("mu0", 0.6);
+          bc.twf[5] = w->real8("l", 1.0);
+          bc.twf[6] = w->real8("v", 1e3);
+          bc.twf[7] = w->real8("t", 1.7976931348623157e308);
+          bc.twf[8] = w->real8("dc", 1.7976931348623157e308);
+          if (bc.twf_kind < 1) IO_abort("BC_SWFF_init: kind must be > 0");
+          if (bc.twf_kind > 3) IO_abort("BC_SWFF_init: kind must be < 4");
+          if (bc.twf[2] < 0 || bc.twf[3] < 0 || bc.twf[4] < 0) IO_abort("BC_SWFF_init: MuS, MuD, Mu0 must be positive in BC_DYNFLT_TWF input block");
+          if (bc.twf[5] <= 0 || bc.twf[6] <= 0 || bc.twf[7] <= 0 || bc.twf[8] <= 0) IO_abort("BC_SWFF_init: L, V, T, Dc must be positive in BC_DYNFLT_TWF input block");
         } else if (!law.empty()) {
           IO_abort("BC_DYNFLT: invalid friction");
         }
@@ -662,6 +686,7 @@ inline void init_main(problem_type& pb) {
     s2d_check(pb, s2d_cart_set_material(pb.gpu, rho.data(), cp.data(), cs.data()), "MAT_init_prop");
     s2d_check(pb, s2d_cart_info(pb.gpu, &pb.npoin, &pb.nelem_total, &dt), "init_main");
   }
+  if (pb.W > 0.0) s2d_check(pb, s2d_cart_set_w25d(pb.gpu, pb.W), "MAT_ELAST_init_25D");
   // TIME_init (SRC/time.f90:323-341)
   timescheme_type& t = pb.time;
   if (!(t.dt > 0.0)) {
@@ -738,6 +763,11 @@ inline void init_main(problem_type& pb) {
         d.rsf_kind = bc.rsf_kind;
         d.rsf_dc = p1.data(); d.rsf_mus = p2.data(); d.rsf_a = p3.data(); d.rsf_b = p4.data(); d.rsf_Vstar = p5.data();
         d.rsf_theta = p6.data(); d.rsf_Vc = p7.data();
+      }
+      if (bc.has_twf) {
+        d.twf_kind = bc.twf_kind;
+        d.twf_X = bc.twf[0]; d.twf_Z = bc.twf[1]; d.twf_mus = bc.twf[2]; d.twf_mud = bc.twf[3]; d.twf_mu0 = bc.twf[4];
+        d.twf_L = bc.twf[5]; d.twf_V = bc.twf[6]; d.twf_T = bc.twf[7]; d.twf_Dc = bc.twf[8];
       }
       d.normal_kind = bc.nor_kind;
       d.normal_T = bc.nor_T;

@@ -78,10 +78,14 @@ const char* s2d_version(void);
 /* matwrk_elast_type%a (SRC/mat_elastic.f90:11-14,290-360): ncoefsets blocks a(ngll,ngll,nelast),
  * elem2set(nelem) 1-based block of each element (mat_gen.f90:357-365 shares one block between
  * homogeneous elements).  nelast = 2|3 (SH flat|general), 6|10 (P-SV flat|general).
+ * beta25d: matwrk_elast_type%beta(ngll,ngll) per coefficient block (MAT_ELAST_init_25D, mat_elastic.f90:363-383),
+ * the finite-seismogenic-width term of 2.5D runs (&GENERAL W): every element force gets
+ * - beta * d (MAT_ELAST_add_25D_f, :447-459, called from MAT_Fint, mat_gen.f90:440, on the Kelvin-Voigt-modified
+ * d when the element carries KV); NULL when W is infinite.
  * kd2 != 0 selects the ELAST_KD2_* form the reference uses when ngll == OPT_NGLL
  * (mat_elastic.f90:412-423,612), 0 the ELAST_KD1_* form (:489). */
 int s2d_set_elastic(s2d_handle h, int32_t nelast, int32_t ncoefsets, const double* a,
-                    const int32_t* elem2set, int32_t kd2);
+                    const int32_t* elem2set, const double* beta25d, int32_t kd2);
 
 /* matwrk_kv_type%eta (SRC/mat_kelvin_voigt.f90:117-150): eta(ngll,ngll,nkv), already times dt
  * when ETAxDT; elem_ids(nkv) 1-based elements carrying it. */
@@ -322,6 +326,10 @@ int s2d_cart_set_material(s2d_handle h, const double* rho, const double* cp, con
  * already times dt when ETAxDT, elem_ids(nkv) 1-based in natural element order.  The force kernel then sees
  * d + eta*v element by element (:137-150).  Replaces a previous s2d_cart_set_kv. */
 int s2d_cart_set_kv_elems(s2d_handle h, int32_t nkv, const int32_t* elem_ids, const double* eta);
+/* &GENERAL W (SRC/input.f90:82,119): finite seismogenic width of a 2.5D run.  The builder forms
+ * beta = dvol * mu * (pi (1 - nu) / W)^2, nu = lambda / (lambda + mu) / 2 (P-SV; SH without the (1 - nu) factor)
+ * at every GLL point (MAT_ELAST_init_25D, mat_elastic.f90:363-383) from the current material.  Before commit. */
+int s2d_cart_set_w25d(s2d_handle h, double W);
 int s2d_cart_info(s2d_handle h, int64_t* npoin, int64_t* nelem, double* dt);
 /* Overrides the time step (time%dt) before any boundary is added.  x-strips of one global mesh
  * must agree on dt: the host takes the minimum of the per-strip Courant steps (the reference takes

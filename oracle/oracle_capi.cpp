@@ -299,6 +299,7 @@ long long orc_array(void* hv, const char* name_, const void** ptr, char* dtype) 
   if (n == "H") RET_D(pb.grid.H);
   if (n == "Ht") RET_D(pb.grid.Ht);
   if (n == "a") RET_D(pb.a);
+  if (n == "beta25d") RET_D(pb.beta25d);
   if (n == "elem2set") RET_I(pb.elem2set);
   if (n == "kv_elem") RET_I(pb.kv_elem);
   if (n == "kv_eta") RET_D(pb.kv_eta);

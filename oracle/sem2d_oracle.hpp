@@ -864,6 +864,7 @@ struct Problem {  // problem_type (problem_class.f90:19-46)
   // work arrays: coefficient sets (mat_gen.f90:357-365 shares one set per homogeneous tag)
   int nelast = 0;
   std::vector<double> a;          // (ngll,ngll,nelast,ncoefsets)
+  std::vector<double> beta25d;    // (ngll,ngll,ncoefsets) matwrk_elast_type%beta when W is finite (mat_elastic.f90:280-284), else empty
   std::vector<int> elem2set;      // (nelem) 1-based set id
   int ncoefsets = 0;
   std::vector<int> kv_elem;       // 1-based element ids with KV
@@ -1075,6 +1076,9 @@ inline void MAT_init_work(Problem& pb, bool force_general_nelast = false) {
   pb.elem2set.assign(ne, 0);
   pb.elem2kv.assign(ne, 0);
   pb.a.clear();
+  pb.beta25d.clear();
+  const bool w25d = g.W < HUGE_D;
+  std::vector<double> mu(n2), lambda(n2);
   pb.kv_elem.clear();
   pb.kv_eta.clear();
   pb.ncoefsets = 0;
@@ -1095,6 +1099,18 @@ inline void MAT_init_work(Problem& pb, bool force_general_nelast = false) {
     } else {
       MAT_ELAST_init_a(pb, e, pb.nelast, abuf.data());
       pb.a.insert(pb.a.end(), abuf.begin(), abuf.end());
+      if (w25d) {  // MAT_ELAST_init_25D (mat_elastic.f90:363-383)
+        pb.mat.get(pb.mat.mu, e, mu.data());
+        pb.mat.get(pb.mat.lambda, e, lambda.data());
+        for (int j = 1; j <= n; ++j)
+          for (int i = 1; i <= n; ++i) {
+            const int k = (i - 1) + n * (j - 1);
+            const double dvol = SE_VolumeWeight(g, e, i, j);
+            const double nu = lambda[k] / (lambda[k] + mu[k]) / 2.0;
+            const double t = (pb.ndof == 1) ? 4.0 * std::atan(1.0) / g.W : 4.0 * std::atan(1.0) * (1 - nu) / g.W;
+            pb.beta25d.push_back(dvol * mu[k] * (t * t));
+          }
+      }
       pb.ncoefsets++;
       pb.elem2set[e - 1] = pb.ncoefsets;
     }
@@ -2130,6 +2146,11 @@ inline void compute_Fint(Problem& pb, std::vector<double>& f, const std::vector<
     }
     const double* a = &pb.a[(size_t)n2 * pb.nelast * (pb.elem2set[e - 1] - 1)];
     MAT_ELAST_f(floc.data(), dloc.data(), a, pb.nelast, g.H.data(), g.Ht.data(), n, ndof, s, pb.kd_force_kd1);
+    if (!pb.beta25d.empty()) {  // MAT_ELAST_add_25D_f (mat_gen.f90:440, mat_elastic.f90:447-459): the KV-modified d
+      const double* beta = &pb.beta25d[(size_t)n2 * (pb.elem2set[e - 1] - 1)];
+      for (int c = 0; c < ndof; ++c)
+        for (int k = 0; k < n2; ++k) floc[k + (size_t)n2 * c] = floc[k + (size_t)n2 * c] - beta[k] * dloc[k + (size_t)n2 * c];
+    }
     for (int c = 0; c < ndof; ++c)  // FIELD_add_elem (fields.f90:113-129)
       for (int k = 0; k < n2; ++k) f[(size_t)(ib[k] - 1) + np * c] = f[(size_t)(ib[k] - 1) + np * c] + floc[k + (size_t)n2 * c];
   }
@@ -2341,7 +2362,7 @@ inline void read_main(Problem& pb, CartSpec& cart, ParInp& in) {
   pb.grid.ngll = g->integer("ngll", 9);
   pb.grid.fmax = g->dbl("fmax", 1.0);
   pb.grid.W = g->dbl("W", HUGE_D);
-  if (pb.grid.W < HUGE_D) IO_abort("oracle: 2.5D (finite W) not supported");
+  if (pb.grid.W <= 0.0) IO_abort("GENERAL input block: W must be positive");
   // MESH_DEF / MESH_CART (mesh_gen.f90, mesh_cartesian.f90:88-214)
   in.rewind();
   g = in.next("MESH_DEF");

@@ -75,7 +75,7 @@ _SIGS = {
     "s2d_create": [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                    C.c_void_p, C.c_int32, C.POINTER(Scheme), C.c_int32],
     "s2d_destroy": [C.c_void_p],
-    "s2d_set_elastic": [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32],
+    "s2d_set_elastic": [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32],
     "s2d_set_kv": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
     "s2d_set_mass": [C.c_void_p, C.c_void_p],
     "s2d_add_abso": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
@@ -127,6 +127,7 @@ _SIGS = {
     "s2d_cart_receiver_info": [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p],
     "s2d_cart_set_material": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "s2d_cart_set_kv_elems": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
+    "s2d_cart_set_w25d": [C.c_void_p, C.c_double],
     "s2d_cart_info": [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)],
     "s2d_cart_set_dt": [C.c_void_p, C.c_double],
     "s2d_cart_get_gll": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],

@@ -196,6 +196,26 @@ __global__ void k_cart_coef(CartGeom G, T* __restrict__ coef, int nelast, int co
   for (int pl = 0; pl < nelast; ++pl) coef[strip_coef_index(G.S, nelast, ix, iz, i, j, pl)] = (T)av[pl];
 }
 
+// 2.5D term (MAT_ELAST_init_25D, mat_elastic.f90:363-383): beta = dvol * mu * (pi (1 - nu) / W)^2 per GLL point of
+// every element, in the strip layout; SH: without the (1 - nu) factor
+template <typename T>
+__global__ void k_cart_beta(CartGeom G, T* __restrict__ beta, double W) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = G.N, N2 = N * N;
+  if (w >= (long long)G.nx * G.nz * N2) return;
+  const long long e = w / N2;
+  const int k = (int)(w - e * N2), i = k % N, j = k / N;
+  const int ix = (int)(e % G.nx), iz = (int)(e / G.nx);
+  double rho, cp, cs;
+  cart_material(G, ix, iz, i, j, rho, cp, cs);
+  const double la = rho * (cp * cp - 2.0 * cs * cs), mu = rho * cs * cs;
+  const double dvol = ((0.5 * G.hx) * (0.5 * G.hz)) * (G.wgll[i] * G.wgll[j]);
+  const double nu = la / (la + mu) / 2.0;
+  const double pi = 4.0 * atan(1.0);
+  const double t = (G.ndof == 1) ? pi / W : pi * (1 - nu) / W;
+  beta[strip_scalar_index(G.S, ix, iz, i, j)] = (T)(dvol * mu * (t * t));
+}
+
 // assembled mass (mat_mass.f90:50-57): each node is summed by its first element, over the elements
 // that share it in ascending element order; virtual neighbour columns stand in for the elements of
 // an adjacent x-strip so that interface nodes carry the full mass on both ranks.
@@ -425,6 +445,7 @@ struct CartState {
   std::vector<double> h_mat[3];   // s2d_cart_set_material: host and device copies of rho, cp, cs
   DevBuf<double> d_mat[3];
   bool dt_given = false;
+  double W25d = 0.0;              // &GENERAL W when finite (2.5D), else 0
   CartGeom dev_geom() const {     // the geometry as the kernels see it
     CartGeom g = G;
     for (int q = 0; q < 3; ++q) g.mat[q] = d_mat[q].p;
@@ -483,6 +504,11 @@ static void cart_operator(Engine<T>& E, CartState& S) {
   E.mass.alloc(E.npoin);
   k_cast_copy<T, double><<<(unsigned)((E.npoin + 255) / 256), 256, 0, st>>>(E.rmass.p, E.mass.p, E.npoin);
   S2D_CUDA(cudaGetLastError());
+  if (S.W25d > 0.0) {
+    E.strip_beta.alloc((size_t)E.nelem * N2);
+    k_cart_beta<T><<<nblk, 256, 0, st>>>(G, E.strip_beta.p, S.W25d);
+    S2D_CUDA(cudaGetLastError());
+  }
   S2D_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -698,6 +724,16 @@ int s2d_cart_set_kv_elems(s2d_handle h, int32_t nkv, const int32_t* elem_ids, co
       for (int i = 0; i < N; ++i) pe[strip_scalar_index(G.S, ix, iz, i, j)] = eta[(size_t)k * n2 + i + N * j];
   }
   Eb->set_strip_eta(pe.data(), pe.size());
+  CART_GUARD_END
+}
+
+int s2d_cart_set_w25d(s2d_handle h, double W) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(W > 0.0, "GENERAL input block: W must be positive");
+  S2D_REQUIRE(!Eb->committed, "cart_set_w25d after commit");
+  S.W25d = W;
+  if (Eb->prec == 8) cart_operator<double>(*as_engine<double>(Eb), S);
+  else cart_operator<float>(*as_engine<float>(Eb), S);
   CART_GUARD_END
 }
 

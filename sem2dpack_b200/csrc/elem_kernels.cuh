@@ -20,6 +20,7 @@ struct ElemArgs {
   const int* elem2set;  // (nelem) 0-based
   const int* elem2kv;   // (nelem) -1 | 0-based KV slot, or nullptr
   const T* eta;         // (N*N, nkv)
+  const T* beta;        // (N*N, ncoefsets) 2.5D term of MAT_ELAST_add_25D_f (mat_elastic.f90:447-459), or nullptr
   const T* H;           // (N,N) column-major hprime
   const T* d;
   const T* v;
@@ -129,7 +130,11 @@ __global__ void __launch_bounds__(256) k_elem_node(ElemArgs<T> A) {
         s1 += sH[i + N * m] * sP[slot][c][m + N * j];  // (H tH)(i,j)
         s2 += sQ[slot][c][i + N * m] * sH[j + N * m];  // (tHt Ht)(i,j)
       }
-      const T val = s1 + s2;
+      T val = s1 + s2;
+      if (A.beta) {  // f = f - beta*d with the element's (KV-modified) d (mat_gen.f90:440)
+        const int e = A.elist ? A.elist[eidx] : (int)eidx;
+        val = val - A.beta[(size_t)A.elem2set[e] * N2 + k] * sU[slot][c][k];
+      }
       T* dst = A.f + node + A.npoin * c;
       if (ATOMIC)
         atomicAdd(dst, val);
@@ -210,6 +215,7 @@ struct PatchArgs {
   const int* ekv;             // (nelem patch-major) KV slot | -1, or nullptr
   const T* a;                 // hetero: per patch [nelast][N(i)][cnt*N(t)] ; else (N*N,nelast,nsets)
   const T* eta;               // (N*N, nkv)
+  const T* beta;              // (N*N, ncoefsets) 2.5D term (mat_elastic.f90:447-459) indexed through eset, or nullptr
   const T* d;
   const T* v;
   T* f;
@@ -432,6 +438,16 @@ __global__ void __launch_bounds__(patch_ep(N) * N, patch_min_ctas(N, NDOF, sizeo
         for (int m = 0; m < N; ++m) s1 += A.H[i + N * m] * tH[c][m];  // (H tH)(i,j)
         fcol[c][i] = s1;
       }
+    if (A.beta) {  // MAT_ELAST_add_25D_f: - beta*d with the element's (KV-modified) d (mat_gen.f90:440); the
+      // (tHt Ht) half of the elastic force is added below, the sum per node is the same three terms
+      const T* bp = A.beta + (size_t)A.eset[q] * N2 + N * j;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const T b = bp[i];
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) fcol[c][i] = fcol[c][i] - b * ucol[c][i];
+      }
+    }
   }
   __syncthreads();  // all reads of the displacement tiles are done
   if (active) {

@@ -128,10 +128,10 @@ int s2d_destroy(s2d_handle h) {
 }
 
 int s2d_set_elastic(s2d_handle h, int32_t nelast, int32_t ncoefsets, const double* a, const int32_t* elem2set,
-                    int32_t kd2) {
+                    const double* beta25d, int32_t kd2) {
   return guard(h, [&](EngineBase& E) {
     S2D_REQUIRE(a && elem2set, "s2d_set_elastic: null pointer");
-    E.set_elastic(nelast, ncoefsets, a, elem2set, kd2);
+    E.set_elastic(nelast, ncoefsets, a, elem2set, beta25d, kd2);
   });
 }
 int s2d_set_kv(s2d_handle h, int32_t nkv, const int32_t* elem_ids, const double* eta) {

@@ -72,7 +72,8 @@ class EngineBase {
   int it = 0;  // host mirror of ctl.it
   int64_t launches = 0;
 
-  virtual void set_elastic(int nelast, int ncoefsets, const double* a, const int32_t* elem2set, int kd2) = 0;
+  virtual void set_elastic(int nelast, int ncoefsets, const double* a, const int32_t* elem2set, const double* beta25d,
+                           int kd2) = 0;
   virtual void set_kv(int nkv, const int32_t* elem_ids, const double* eta) = 0;
   virtual void set_mass(const double* mass) = 0;
   virtual void add_abso(int np, const int32_t* node, const double* C, int is_flat, const double* n,
@@ -125,7 +126,9 @@ class Engine : public EngineBase {
   DevBuf<T> d, v, a, rmass, scratch;
   // material
   int nelast = 0, ncoefsets = 0, kd2 = 0, nkv = 0;
-  DevBuf<T> coef, eta;
+  DevBuf<T> coef, eta, beta;      // beta: 2.5D term (N*N, ncoefsets), empty when W is infinite
+  std::vector<double> h_beta;
+  DevBuf<T> strip_beta;           // ... per element GLL point in the strip layout (strip kernel)
   DevBuf<int> elem2set, elem2kv;
   std::vector<int32_t> h_elem2set, h_elem2kv;
   std::vector<double> h_coef;
@@ -313,6 +316,7 @@ class Engine : public EngineBase {
     io.cdz = cart_cdz;
     io.cdet = cart_cdet;
     io.wgll = cart_wgll.empty() ? nullptr : cart_wgll.data();
+    io.beta = strip_beta.p;
     return io;
   }
   // strip kernel over the whole box (+ halo fold, + interface exchange); io.v_in != null = fused update
@@ -455,7 +459,8 @@ class Engine : public EngineBase {
   }
 
   // ---- configuration -------------------------------------------------------------------
-  void set_elastic(int nelast_, int ncoefsets_, const double* a_, const int32_t* e2s, int kd2_) override {
+  void set_elastic(int nelast_, int ncoefsets_, const double* a_, const int32_t* e2s, const double* beta_,
+                   int kd2_) override {
     S2D_REQUIRE(!committed, "set_elastic after commit");
     S2D_REQUIRE((ndof == 1 && (nelast_ == 2 || nelast_ == 3)) || (ndof == 2 && (nelast_ == 6 || nelast_ == 10)),
                 "nelast does not match ndof (mat_elastic.f90:255-268)");
@@ -466,6 +471,12 @@ class Engine : public EngineBase {
     const size_t n2 = (size_t)ngll * ngll;
     h_coef.assign(a_, a_ + n2 * nelast * ncoefsets);
     upload_as(coef, a_, h_coef.size());
+    h_beta.clear();
+    beta.release();
+    if (beta_) {  // matwrk_elast_type%beta (mat_elastic.f90:280-284): finite seismogenic width W
+      h_beta.assign(beta_, beta_ + n2 * ncoefsets);
+      upload_as(beta, beta_, h_beta.size());
+    }
     h_elem2set.resize(nelem);
     for (int e = 0; e < nelem; ++e) {
       S2D_REQUIRE(e2s[e] >= 1 && e2s[e] <= ncoefsets, "elem2set entry out of range");
@@ -986,6 +997,14 @@ class Engine : public EngineBase {
               pc[strip_coef_index(S, nelast, B.ex[e], B.ez[e], i, j, pl)] = (T)src[(size_t)pl * n2 + i + N * j];
       }
       p_coef.upload(pc);
+      if (!h_beta.empty()) {  // 2.5D: beta(ngll,ngll) of every element through its coefficient set
+        std::vector<T> pb((size_t)nelem * n2);
+        for (int e = 0; e < nelem; ++e)
+          for (int j = 0; j < N; ++j)
+            for (int i = 0; i < N; ++i)
+              pb[strip_scalar_index(S, B.ex[e], B.ez[e], i, j)] = (T)h_beta[(size_t)h_elem2set[e] * n2 + i + N * j];
+        strip_beta.upload(pb);
+      }
       if (nkv > 0) {  // eta(ngll,ngll) of the Kelvin-Voigt elements, zero elsewhere (mat_kelvin_voigt.f90:137-150)
         std::vector<T> pe((size_t)nelem * n2, (T)0);
         for (int e = 0; e < nelem; ++e) {
@@ -1251,6 +1270,7 @@ class Engine : public EngineBase {
     A.elem2set = elem2set.p;
     A.elem2kv = nkv > 0 ? elem2kv.p : nullptr;
     A.eta = eta.p;
+    A.beta = beta.p;
     A.H = H.p;
     A.d = dd;
     A.v = vv;
@@ -1295,6 +1315,7 @@ class Engine : public EngineBase {
     A.ekv = nkv > 0 ? p_ekv.p : nullptr;
     A.a = p_hetero ? p_coef.p : coef.p;
     A.eta = eta.p;
+    A.beta = beta.p;
     A.d = dd;
     A.v = vv;
     A.f = ff;

@@ -221,6 +221,9 @@ struct StripArgs {
   // point of every element in the strip layout (strip_scalar_index; zero on elements without KV)
   const T* eta;
   const T* v_kv;
+  // 2.5D term of MAT_ELAST_add_25D_f (mat_elastic.f90:447-459, mat_gen.f90:440): f = f - beta*d element by element,
+  // beta per GLL point of every element in the strip layout (strip_scalar_index), or nullptr
+  const T* beta;
   int prefetch;             // L2 prefetch of what is not staged
   T H[N * N];               // hprime, column-major (constant bank)
   // compact coefficient mode (isotropic flat grids): only (lambda, mu) are stored per GLL point and
@@ -689,6 +692,15 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           for (int m = 0; m < N; ++m) s2 += tHt[c][m] * HZ[j + N * m];         // (tHt Ht)(i,j)
           f[c][j] = s1 + s2;
         }
+      if (A.beta != nullptr) {  // finite seismogenic width: - beta*d with the element's (KV-modified) d
+        const T* bp = A.beta + (size_t)strip_elem_off(G, seg, strip, ez) * (N * N) + lanep;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const T b = ld_stream(bp + (size_t)j * cxN);
+#pragma unroll
+          for (int c = 0; c < NDOF; ++c) f[c][j] = f[c][j] - b * Ut[c][j];
+        }
+      }
       __syncwarp();
       // ---- assembly inside the strip: merge the column shared with the element to the left
 #pragma unroll
@@ -1094,6 +1106,7 @@ struct StripIO {
   const T* a_in = nullptr;
   const T* eta = nullptr;   // Kelvin-Voigt: eta per element GLL point (strip layout) and the velocity field
   const T* v_kv = nullptr;
+  const T* beta = nullptr;  // 2.5D: beta per element GLL point (strip layout)
   int prefetch = 1;
   // compact coefficient mode (coef holds lambda, mu only)
   int compact = 0;
@@ -1149,6 +1162,7 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
     A.a_in = io.a_in;                                                                             \
     A.eta = io.eta;                                                                               \
     A.v_kv = io.v_kv;                                                                             \
+    A.beta = io.beta;                                                                             \
     A.prefetch = io.prefetch;                                                                     \
     for (int k = 0; k < NN * NN; ++k) A.H[k] = (T)io.hprime[k];                                   \
     A.cdx = (T)io.cdx;                                                                            \

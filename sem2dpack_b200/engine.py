@@ -93,10 +93,15 @@ class Engine:
             pass
 
     # -- configuration (what init_main hands over, SRC/init.f90:16-131) ---------------------
-    def set_elastic(self, nelast, a, elem2set, kd2):
+    def set_elastic(self, nelast, a, elem2set, kd2, beta25d=None):
+        """beta25d: matwrk_elast_type%beta (ngll,ngll) per coefficient block of a finite-width 2.5D run, or None"""
         a = _f64(a)
         ncoefsets = a.size // (self.ngll * self.ngll * nelast)
-        self._ck(self.L.s2d_set_elastic(self.h, nelast, ncoefsets, _ptr(a), _ptr(_i32(elem2set)), int(kd2)))
+        beta25d = _f64(beta25d)
+        if beta25d is not None:
+            assert beta25d.size == self.ngll * self.ngll * ncoefsets
+        self._ck(self.L.s2d_set_elastic(self.h, nelast, ncoefsets, _ptr(a), _ptr(_i32(elem2set)), _ptr(beta25d),
+                                        int(kd2)))
 
     def set_kv(self, elem_ids, eta):
         elem_ids = _i32(elem_ids)
@@ -351,6 +356,10 @@ class CartEngine(Engine):
         """eta (nkv, ngll, ngll) of the Kelvin-Voigt elements, ids 1-based in natural order (s2d_cart_set_kv_elems)"""
         elem_ids = _i32(elem_ids)
         self._ck(self.L.s2d_cart_set_kv_elems(self.h, elem_ids.size, _ptr(elem_ids), _ptr(_f64(eta))))
+
+    def set_w25d(self, W):
+        """&GENERAL W: finite seismogenic width (s2d_cart_set_w25d)"""
+        self._ck(self.L.s2d_cart_set_w25d(self.h, float(W)))
 
     def fill_fields(self, seed, amp_d, amp_v):
         """seeded non-trivial state (hash noise keyed by global lattice coordinates); accel = 0"""

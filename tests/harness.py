@@ -78,7 +78,8 @@ class Rig:
         self.e = e
         if kd2 is None:
             kd2 = (ngll == 5)  # OPT_NGLL (SRC/constants.f90:6, mat_elastic.f90:412)
-        e.set_elastic(o.i("nelast"), o.arr("a"), o.arr("elem2set"), kd2)
+        beta = o.arr("beta25d")   # finite seismogenic width W (2.5D): matwrk_elast_type%beta per coefficient block
+        e.set_elastic(o.i("nelast"), o.arr("a"), o.arr("elem2set"), kd2, beta25d=beta if beta.size else None)
         if o.i("nkv") > 0:
             e.set_kv(o.arr("kv_elem"), o.arr("kv_eta"))
         self.faults = []

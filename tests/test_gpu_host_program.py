@@ -256,3 +256,21 @@ def test_material_distributions_per_tag(tmp_path):
     assert np.abs(ux - ref[:, :, 0]).max() <= 2e-6 * np.abs(ref).max()
     assert np.abs(uz - ref[:, :, 1]).max() <= 2e-6 * np.abs(ref).max()
     o.close()
+
+
+def test_2p5d_inplane_deck_through_the_host_program(tmp_path):
+    """EXAMPLES/2.5D_inplane (W = 10 km) shortened: the host hands W to the builder (s2d_cart_set_w25d), which forms
+    beta at every GLL point; fault records against the oracle"""
+    deck = harness.deck("inplane25d").replace("TotalTime=30", "NbSteps=300")
+    assert "NbSteps=300" in deck
+    p = run(tmp_path, deck, "--quiet")
+    assert p.returncode == 0, p.stdout + p.stderr
+    o = orc.Oracle(deck, renumber=False)
+    o.step(300)
+    x, rec = read_fault(tmp_path, 1)
+    want = o.arr("bc.0.out").reshape(-1, 6, rec.shape[2])
+    assert rec.shape == want.shape
+    for c in range(6):
+        assert np.abs(rec[:, c] - want[:, c]).max() <= 1e-6 * max(np.abs(want[:, c]).max(), 1e-30), c
+    assert np.abs(rec[-1, 0]).max() > 0
+    o.close()

@@ -140,3 +140,25 @@ def test_fields_energy_and_set_fields_in_the_callers_numbering():
     d, v, _ = r.e.get_fields()
     assert rel_l2(d, o.arr("d")) <= 1e-10 and rel_l2(v, o.arr("v")) <= 1e-10
     r.close()
+
+
+@pytest.mark.parametrize("name,nsteps,route_flag", [("inplane25d", 300, "1"), ("kvfz", 300, "1"), ("kvfz", 200, "0")])
+def test_finite_seismogenic_width_decks(name, nsteps, route_flag, monkeypatch):
+    """&GENERAL W (2.5D): MAT_ELAST_init_25D / MAT_ELAST_add_25D_f (mat_elastic.f90:363-383,447-459): every element
+    force gets - beta*d, with the Kelvin-Voigt-modified d on KV elements (mat_gen.f90:435-440).  EXAMPLES/2.5D_inplane
+    (P-SV, SWF + TWF fault, leapfrog) and EXAMPLES/Kelvin_Visco_FZ (SH, two tags, KV layer with ETAxDT=F, Newmark),
+    on the strip kernel and on the any-mesh patch kernel.  No reference artefact pins these decks: oracle parity."""
+    monkeypatch.setenv("S2D_ROUTE_STRIP", route_flag)
+    o, r = _run(harness.deck(name), nsteps)
+    assert o.arr("beta25d").size > 0 and r.e.route() == int(route_flag)
+    d, v, a = r.e.get_fields()
+    assert np.abs(o.arr("d")).max() > 0
+    for nm, got in (("d", d), ("v", v), ("acc", a)):
+        assert rel_l2(got, o.arr(nm)) <= 1e-10, (nm, rel_l2(got, o.arr(nm)))
+    rng = np.random.default_rng(12)
+    n = o.i("npoin") * o.i("ndof")
+    d0, v0 = rng.standard_normal(n), rng.standard_normal(n)
+    r.e.set_fields(d0, v0)
+    o.set_fields(d0, v0)
+    assert rel_l2(r.e.compute_fint(), o.compute_fint()) <= 1e-13
+    r.close()
