@@ -180,11 +180,10 @@ struct AbsoDev {
   const double* Ht;     // (ngll,ngll) col-major, Ht(i,k) = H(k,i)
 };
 
+// entry k of one absorbing boundary (bc_abso.f90:286-336): only MxA of its own node is modified
 template <typename T>
-__global__ void k_abso(AbsoDev A, const T* __restrict__ D, const T* __restrict__ V, T* MxA,
-                       size_t npoin) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= A.np) return;
+__device__ __forceinline__ void abso_entry(const AbsoDev& A, int k, const T* __restrict__ D, const T* __restrict__ V,
+                                           T* MxA, size_t npoin) {
   const size_t node = (size_t)(A.node[k] - 1);
   if (A.is_flat || A.ndof == 1) {  // bc_abso.f90:309
     for (int c = 0; c < A.ndof; ++c) {
@@ -213,6 +212,40 @@ __global__ void k_abso(AbsoDev A, const T* __restrict__ D, const T* __restrict__
       }
       const size_t q = node + npoin * c;
       MxA[q] = (T)((double)MxA[q] - kxd);
+    }
+  }
+}
+template <typename T>
+__global__ void k_abso(AbsoDev A, const T* __restrict__ D, const T* __restrict__ V, T* MxA,
+                       size_t npoin) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= A.np) return;
+  abso_entry<T>(A, k, D, V, MxA, npoin);
+}
+
+// SO_add and every BC_ABSO_apply of a step in ONE launch.  The sources and the absorbing sides meet on a few
+// nodes (box corners belong to two sides; a source may sit on a side), where the reference applies them one after
+// the other.  Every touched node is owned by one thread that walks ITS operations in that order: source terms
+// first (solve: SO_add before BC_apply, solver.f90:70-75,156), then the absorbing boundaries in the order of
+// bc(:) (bc_gen.f90:283-290).  op >= 0: entry (op >> 3) of absorbing boundary (op & 7); op < 0: source term -op-1.
+template <typename T>
+__global__ void k_node_ops(int nnodes, const int* __restrict__ onode, const int* __restrict__ ostart,
+                           const int* __restrict__ ops, const AbsoDev* __restrict__ absos, const T* __restrict__ D,
+                           const T* __restrict__ V, T* f, size_t npoin, int ndof, const int* __restrict__ tsrc,
+                           const double* __restrict__ tcoef, int nterms, int nsrc, const double* __restrict__ ampli,
+                           const StepCtl* ctl) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nnodes) return;
+  const size_t node = (size_t)(onode[w] - 1);
+  for (int p = ostart[w]; p < ostart[w + 1]; ++p) {
+    const int op = ops[p];
+    if (op < 0) {
+      const int t = -op - 1;
+      const double amp = ampli[(size_t)((ctl->it - ctl->it0) % ctl->nrows) * nsrc + tsrc[t]];
+      for (int c = 0; c < ndof; ++c)
+        f[node + npoin * c] = (T)((double)f[node + npoin * c] + amp * tcoef[t + (size_t)nterms * c]);
+    } else {
+      abso_entry<T>(absos[op & 7], op >> 3, D, V, f, npoin);
     }
   }
 }
@@ -547,6 +580,41 @@ __global__ void k_dynflt(FaultDev F, T* MxA, const T* __restrict__ Vf, const T* 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// receivers
+struct RecDev {
+  int nx, ndof, isamp, nt, at_node, ngll;
+  const int* iglob;    // (nx) 1-based
+  const int* einterp;  // (nx) 1-based element
+  const double* interp;  // (ngll*ngll, nx)
+  const int* ibool;
+  float* sis;  // (nt,nx,ndof)
+};
+// REC_store (receivers.f90:309-344) for trace q = station + nx * component
+template <typename T>
+__device__ __forceinline__ void rec_store_one(const RecDev& R, const T* __restrict__ field, size_t npoin, int it, int q) {
+  if (it % R.isamp != 0) return;
+  const int itsis = it / R.isamp;  // 0-based row
+  if (itsis >= R.nt || q >= R.nx * R.ndof) return;
+  const int n = q % R.nx, c = q / R.nx;
+  double val;
+  if (R.at_node) {
+    val = (double)field[(size_t)(R.iglob[n] - 1) + npoin * c];
+  } else {
+    const int n2 = R.ngll * R.ngll;
+    const int* ib = R.ibool + (size_t)(R.einterp[n] - 1) * n2;
+    double s = 0.0;
+    for (int k = 0; k < n2; ++k)
+      s += R.interp[k + (size_t)n2 * n] * (double)field[(size_t)(ib[k] - 1) + npoin * c];
+    val = s;
+  }
+  R.sis[(size_t)itsis + (size_t)R.nt * (n + (size_t)R.nx * c)] = (float)val;
+}
+template <typename T>
+__global__ void k_rec_store(RecDev R, const T* __restrict__ field, size_t npoin, const StepCtl* ctl) {
+  rec_store_one<T>(R, field, npoin, ctl->it, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 // BC_DYNFLT_write.  Every CTA reduces its slice of the fault in a fixed tree order and copies its
 // share of the output records; the CTA that finishes last (ticket) adds the per-CTA partial sums
 // in ascending CTA order, writes the potency line and advances the output state: deterministic.
@@ -556,11 +624,17 @@ template <typename T>
 __global__ void __launch_bounds__(DYNW_THREADS) k_dynflt_write(FaultDev F, const T* __restrict__ d,
                                                                const T* __restrict__ v, size_t npoin,
                                                                const StepCtl* ctl, double* __restrict__ part,
-                                                               unsigned* __restrict__ ticket) {
+                                                               unsigned* __restrict__ ticket, int nfb, RecDev R,
+                                                               const T* __restrict__ rec_field) {
   __shared__ double red[6][DYNW_THREADS];
   __shared__ bool last;
+  // REC_store rides in the CTAs beyond the first nfb (one launch for the outputs of a step)
+  if ((int)blockIdx.x >= nfb) {
+    rec_store_one<T>(R, rec_field, npoin, ctl->it, ((int)blockIdx.x - nfb) * DYNW_THREADS + (int)threadIdx.x);
+    return;
+  }
   const int t = threadIdx.x, np = F.np, ndof = F.ndof;
-  const int stride = gridDim.x * DYNW_THREADS;
+  const int stride = nfb * DYNW_THREADS;
   double acc[6] = {0, 0, 0, 0, 0, 0};
   for (int k = blockIdx.x * DYNW_THREADS + t; k < np; k += stride) {
     const double nx = F.n1[k], nz = F.n1[k + np], B = F.B[k];
@@ -610,13 +684,13 @@ __global__ void __launch_bounds__(DYNW_THREADS) k_dynflt_write(FaultDev F, const
   if (t < 6) part[blockIdx.x * 6 + t] = red[t][0];
   __threadfence();
   __syncthreads();
-  if (t == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (t == 0) last = (atomicAdd(ticket, 1u) == (unsigned)nfb - 1);
   __syncthreads();
   if (!last) return;
   __threadfence();
   if (t == 0) {
     double tot[6] = {0, 0, 0, 0, 0, 0};
-    for (unsigned b = 0; b < gridDim.x; ++b)
+    for (int b = 0; b < nfb; ++b)
       for (int q = 0; q < 6; ++q) tot[q] += __ldcg(&part[b * 6 + q]);
     const int npot = 2 * (ndof + 1);
     if (ncall < F.ncall_max) {
@@ -636,39 +710,6 @@ __global__ void __launch_bounds__(DYNW_THREADS) k_dynflt_write(FaultDev F, const
     }
     *ticket = 0;
   }
-}
-
-// ------------------------------------------------------------------------------------------
-// receivers
-struct RecDev {
-  int nx, ndof, isamp, nt, at_node, ngll;
-  const int* iglob;    // (nx) 1-based
-  const int* einterp;  // (nx) 1-based element
-  const double* interp;  // (ngll*ngll, nx)
-  const int* ibool;
-  float* sis;  // (nt,nx,ndof)
-};
-template <typename T>
-__global__ void k_rec_store(RecDev R, const T* __restrict__ field, size_t npoin, const StepCtl* ctl) {
-  const int it = ctl->it;
-  if (it % R.isamp != 0) return;
-  const int itsis = it / R.isamp;  // 0-based row
-  if (itsis >= R.nt) return;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= R.nx * R.ndof) return;
-  const int n = q % R.nx, c = q / R.nx;
-  double val;
-  if (R.at_node) {
-    val = (double)field[(size_t)(R.iglob[n] - 1) + npoin * c];
-  } else {
-    const int n2 = R.ngll * R.ngll;
-    const int* ib = R.ibool + (size_t)(R.einterp[n] - 1) * n2;
-    double s = 0.0;
-    for (int k = 0; k < n2; ++k)
-      s += R.interp[k + (size_t)n2 * n] * (double)field[(size_t)(ib[k] - 1) + npoin * c];
-    val = s;
-  }
-  R.sis[(size_t)itsis + (size_t)R.nt * (n + (size_t)R.nx * c)] = (float)val;
 }
 
 // ------------------------------------------------------------------------------------------

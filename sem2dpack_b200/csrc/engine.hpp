@@ -320,7 +320,8 @@ class Engine : public EngineBase {
     return io;
   }
   // strip kernel over the whole box (+ halo fold, + interface exchange); io.v_in != null = fused update
-  void launch_strips(const StripIO<T>& io) {
+  // tick: the step counter is advanced by the fold kernel (fused step: one launch less)
+  void launch_strips(const StripIO<T>& io, StepCtl* tick = nullptr) {
     const StripGeom& S0 = cart_S;
     if (!xhalo()) {
       kev_mark();
@@ -328,7 +329,7 @@ class Engine : public EngineBase {
       launch_elem_strip_items<T>(strip_all_groups(S0), io, stream);
       kev_mark();
       phase(PH_FOLD);
-      launches += 1 + launch_strip_fold<T>(S0, io.f, cart_hx.p, cart_hz.p, npoin, stream);
+      launches += 1 + launch_strip_fold<T>(S0, io.f, cart_hx.p, cart_hz.p, npoin, stream, tick);
       return;
     }
     phase(PH_FORCE);
@@ -378,7 +379,7 @@ class Engine : public EngineBase {
       if (rc != 0) throw StateError("halo exchange hook failed with code " + std::to_string(rc));
     }
     S2D_CUDA(cudaEventRecord(xh_ev_x, xstream));
-    launches += launch_strip_fold<T>(S0, ff, cart_hx.p, cart_hz.p, npoin, stream);
+    launches += launch_strip_fold<T>(S0, ff, cart_hx.p, cart_hz.p, npoin, stream, tick);
     S2D_CUDA(cudaStreamWaitEvent(stream, xh_ev_x, 0));
     if (xh_peer) {
       k_xhalo_wait<<<1, 1, 0, stream>>>(xh_flags.p, S0.xhalo_left, S0.xhalo_right, xh_seq, ctl.p);
@@ -1229,6 +1230,7 @@ class Engine : public EngineBase {
       if (variant == S2D_ASM_PATCH) build_patch_plan_dev();
     }
     build_source_terms();
+    build_node_ops();
     if (scheme.kind == 2) {
       d_alpha.alloc(npoin * ndof);
       v_alpha.alloc(npoin * ndof);
@@ -1365,12 +1367,19 @@ class Engine : public EngineBase {
       k_periodic<T><<<ceil_div(b->np, 128), 128, 0, stream>>>(f, npoin, ndof, b->np, b->master.p, b->slave.p);
       launches++;
     }
-    for (auto& r : bc_order)
-      if (r.kind == BC_ABSO) {
-        AbsoBc& b = *abso[r.index];
-        k_abso<T><<<ceil_div(b.dev.np, 128), 128, 0, stream>>>(b.dev, D, V, f, npoin);
-        launches++;
-      }
+    if (node_ops_ready) {  // SO_add + every BC_ABSO_apply, one launch (k_node_ops)
+      k_node_ops<T><<<ceil_div(no_nnodes, 128), 128, 0, stream>>>(
+          no_nnodes, no_node.p, no_start.p, no_ops.p, no_absos.p, D, V, f, npoin, ndof, st_src.p, st_coef.p, st_nterms,
+          (int)h_src_iglob.size(), src_ampli.p, ctl.p);
+      launches++;
+    } else {
+      for (auto& r : bc_order)
+        if (r.kind == BC_ABSO) {
+          AbsoBc& b = *abso[r.index];
+          k_abso<T><<<ceil_div(b.dev.np, 128), 128, 0, stream>>>(b.dev, D, V, f, npoin);
+          launches++;
+        }
+    }
     for (auto& r : bc_order) {
       if (r.kind == BC_DIRNEU) {
         DirneuBc& b = *dirneu[r.index];
@@ -1431,6 +1440,53 @@ class Engine : public EngineBase {
     st_src.upload(src);
     st_coef.upload(coef);
   }
+  // Sources and absorbing boundaries of a step as per-node operation lists (k_node_ops).  Not with periodic
+  // boundaries (they go between the two, bc_gen.f90:271-281), not for multi-stage schemes (one source row per stage,
+  // no boundary conditions), at most 8 absorbing boundaries.
+  bool node_ops_ready = false;
+  int no_nnodes = 0;
+  DevBuf<int> no_node, no_start, no_ops;
+  DevBuf<AbsoDev> no_absos;
+  void build_node_ops() {
+    node_ops_ready = false;
+    if (abso.empty() || !perio.empty() || scheme.kind == 3 || abso.size() > 8 || env_int("S2D_NODE_OPS", 1) == 0) return;
+    struct Op {
+      int node, op;
+    };
+    std::vector<Op> all;
+    // source terms first, in source order (the table of build_source_terms is sorted by node, stable)
+    {
+      std::vector<int> tnode = st_node.n ? st_node.to_host() : std::vector<int>();
+      std::vector<int> tstart = st_start.n ? st_start.to_host() : std::vector<int>();
+      for (int k = 0; k < st_nnodes; ++k)
+        for (int t = tstart[k]; t < tstart[k + 1]; ++t) all.push_back({tnode[k], -t - 1});
+    }
+    std::vector<AbsoDev> devs;
+    std::vector<std::vector<int>> nodes;
+    for (auto& r : bc_order)
+      if (r.kind == BC_ABSO) {
+        devs.push_back(abso[r.index]->dev);
+        nodes.push_back(abso[r.index]->node.to_host());
+      }
+    for (size_t b = 0; b < devs.size(); ++b)
+      for (int k = 0; k < devs[b].np; ++k) all.push_back({nodes[b][k], (k << 3) | (int)b});
+    std::stable_sort(all.begin(), all.end(), [](const Op& x, const Op& y) { return x.node < y.node; });
+    std::vector<int> node, start, ops(all.size());
+    for (size_t q = 0; q < all.size(); ++q) {
+      if (q == 0 || all[q].node != all[q - 1].node) {
+        node.push_back(all[q].node);
+        start.push_back((int)q);
+      }
+      ops[q] = all[q].op;
+    }
+    start.push_back((int)all.size());
+    no_nnodes = (int)node.size();
+    no_node.upload(node);
+    no_start.upload(start);
+    no_ops.upload(ops);
+    no_absos.upload(devs);
+    node_ops_ready = true;
+  }
   void launch_sources(T* f, int stage = 0) {
     if (st_nnodes == 0) return;
     k_sources<T><<<ceil_div(st_nnodes, 64), 64, 0, stream>>>(f, npoin, ndof, st_nnodes, st_node.p, st_start.p, st_src.p,
@@ -1440,14 +1496,18 @@ class Engine : public EngineBase {
   }
 
   void launch_outputs() {
-    if (rec.present) {
-      const T* fld = rec.field == 'D' ? dn() : (rec.field == 'V' ? v.p : a.p);
-      k_rec_store<T><<<ceil_div((long long)rec.dev.nx * ndof, 128), 128, 0, stream>>>(rec.dev, fld, npoin, ctl.p);
+    const T* fld = rec.field == 'D' ? dn() : (rec.field == 'V' ? v.p : a.p);
+    const int nrb = rec.present ? ceil_div((long long)rec.dev.nx * ndof, DYNW_THREADS) : 0;
+    bool rec_done = !rec.present;
+    for (auto& b : faults) {  // REC_store rides with the first fault's BC_DYNFLT_write: one launch for the outputs
+      const int extra = rec_done ? 0 : nrb;
+      k_dynflt_write<T><<<b->wctas + extra, DYNW_THREADS, 0, stream>>>(b->dev, dn(), v.p, npoin, ctl.p, b->wpart.p,
+                                                                       b->wticket.p, b->wctas, rec.dev, fld);
+      rec_done = true;
       launches++;
     }
-    for (auto& b : faults) {
-      k_dynflt_write<T><<<b->wctas, DYNW_THREADS, 0, stream>>>(b->dev, dn(), v.p, npoin, ctl.p, b->wpart.p,
-                                                               b->wticket.p);
+    if (!rec_done) {
+      k_rec_store<T><<<ceil_div((long long)rec.dev.nx * ndof, 128), 128, 0, stream>>>(rec.dev, fld, npoin, ctl.p);
       launches++;
     }
   }
@@ -1457,8 +1517,6 @@ class Engine : public EngineBase {
     const size_t nd = npoin * ndof;
     const T dt = (T)scheme.dt;
     phase(PH_PRED);
-    k_tick<<<1, 1, 0, stream>>>(ctl.p);
-    launches++;
     const bool nmk = scheme.kind == 1;
     const T c1 = nmk ? (T)(0.5 * scheme.dt * scheme.dt) : (T)0;            // (1/2 - beta) dt^2, beta = 0
     const T c2 = nmk ? (T)((1.0 - scheme.gamma) * scheme.dt) : (T)0;
@@ -1484,9 +1542,9 @@ class Engine : public EngineBase {
     io.c2 = c2;
     io.c3 = c3;
     io.a_in = a.p;
-    launch_strips(io);
+    launch_strips(io, ctl.p);  // ... and the step counter (k_strip_fold)
     phase(PH_SRC);
-    launch_sources(a.p);
+    if (!node_ops_ready) launch_sources(a.p);
     phase(PH_BC);
     launch_bcs(dc);
     phase(PH_UPDATE);
@@ -1547,7 +1605,7 @@ class Engine : public EngineBase {
     if (!cart_mode) phase(PH_FORCE);
     launch_fint(dforce, vforce, a.p);
     phase(PH_SRC);
-    launch_sources(a.p);
+    if (!node_ops_ready) launch_sources(a.p);
     phase(PH_BC);
     launch_bcs(dn());  // BC_apply sees fields%displ / veloc (solver.f90:121), not the alpha-weighted copies
     phase(PH_UPDATE);

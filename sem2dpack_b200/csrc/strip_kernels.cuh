@@ -917,8 +917,9 @@ __host__ __device__ inline int strip_shared_upper_seg(const StripGeom& G, int r)
 }
 template <typename T>
 __global__ void k_strip_fold(StripGeom G, T* __restrict__ f, const T* __restrict__ halo_x,
-                             const T* __restrict__ halo_z, size_t npoin) {
+                             const T* __restrict__ halo_z, size_t npoin, StepCtl* tick) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tick && w == 0) tick->it += 1;  // the step counter rides here (the strip kernel before does not read it)
   const int nhb = G.ngroups - 1;
   const int nsh_lo = G.nseg_lo > 0 ? G.nseg_lo - 1 : 0;
   const int nsh = nsh_lo + (G.nseg - G.nseg_lo - 1);
@@ -1224,11 +1225,11 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
 }
 template <typename T>
 inline int launch_strip_fold(const StripGeom& G, T* f, const T* halo_x, const T* halo_z, size_t npoin,
-                             cudaStream_t s) {
+                             cudaStream_t s, StepCtl* tick = nullptr) {
   const int nsh = (G.nseg_lo > 0 ? G.nseg_lo - 1 : 0) + (G.nseg - G.nseg_lo - 1);
   const long long nh = (long long)(G.ngroups - 1) * nsh + (long long)nsh * G.LX;
-  if (nh <= 0) return 0;
-  k_strip_fold<T><<<(unsigned)((nh + 255) / 256), 256, 0, s>>>(G, f, halo_x, halo_z, npoin);
+  if (nh <= 0 && !tick) return 0;
+  k_strip_fold<T><<<(unsigned)((std::max(nh, 1LL) + 255) / 256), 256, 0, s>>>(G, f, halo_x, halo_z, npoin, tick);
   S2D_CUDA(cudaGetLastError());
   return 1;
 }
