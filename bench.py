@@ -299,6 +299,70 @@ def generic_route_record(n, K, W, local, precision, torch):
             "element_order": "anti-diagonal sweeps (ix+iz, ix), node numbering by first occurrence in that order"}
 
 
+# BASELINE.json configs[0..3]: the reference's own example decks, scaled up so that the device is busy.  Same deck
+# text (tests/golden/*.par, copied from EXAMPLES/*/Par.inp), only `nelem` multiplied and the run length replaced.
+REF_CONFIGS = {
+    "testsh": {"scale": 32, "nelem": (60, 60), "time": ("TotalTime=35.d0", "NbSteps={nt}"),
+               "what": "EXAMPLES/TestSH: SH, NGLL=6, homogeneous, ABSORB x2, Ricker force, leapfrog"},
+    "lamb": {"scale": 24, "nelem": (40, 20), "time": ("TotalTime=1.5d0, Dt=0.5d-3", "NbSteps={nt}, courant=0.3d0"),
+             "what": "EXAMPLES/LambsProblem: P-SV, NGLL=9, free surface + ABSORB x3, Ricker force, leapfrog"},
+    "tpv3": {"scale": 24, "nelem": (70, 40), "time": ("TotalTime=16.d0", "NbSteps={nt}"),
+             "what": "EXAMPLES/TestFlt2D_SCEC_TPV3_inplane: P-SV, NGLL=6, Kelvin-Voigt layer, one-sided SWF fault, "
+                     "ABSORB x2 + DIRNEU, explicit Newmark"},
+    "ratestate": {"scale": 12, "nelem": (270, 90), "time": ("TotalTime=4d0", "NbSteps={nt}"),
+                  "what": "EXAMPLES/RateState: SH, NGLL=5, one-sided rate-and-state fault (slip law), ABSORB + DIRNEU, "
+                          "explicit Newmark"},
+}
+
+
+def config_bytes_per_dof(ngll, ndof, scheme, kv, w=W8):
+    """bytes the engine must move per DOF and step for a builder-made box of that kind: coefficient planes as
+    stored (two per GLL point: SH flat planes, or (lambda, mu) of an isotropic P-SV box), fields and inverse mass.
+    Fused step (leapfrog / explicit Newmark without KV): d, v in, rmass once per node, v, d_next out (+ a in / out
+    for Newmark).  Kelvin-Voigt: predictor pass (d, v, a in; d, v out), force kernel (planes, eta, d, v in; f out),
+    corrector pass (f, rmass, v in; a, v out)."""
+    n1 = (ngll - 1) ** 2
+    coef = 2 * ngll ** 2 * w / (ndof * n1)
+    if kv:
+        return coef + ngll ** 2 * w / (ndof * n1) + 13 * w
+    return coef + 4 * w + w / ndof + (2 * w if scheme == "newmark" else 0)
+
+
+def run_ref_config(name, steps, device, scale=None):
+    """one of BASELINE.json configs[0..3], scaled, through the host program (sem2dsolve_b200 --bench)"""
+    import tempfile
+    import harness
+    cfg = REF_CONFIGS[name]
+    S = scale or cfg["scale"]
+    deck = harness.deck(name)
+    nx, nz = cfg["nelem"]
+    old = f"nelem={nx},{nz}"
+    assert old in deck and cfg["time"][0] in deck, name
+    deck = deck.replace(old, f"nelem={nx * S},{nz * S}").replace(cfg["time"][0], cfg["time"][1].format(nt=steps + 40))
+    exe = os.path.join(ROOT, "sem2dpack_b200", "lib", "sem2dsolve_b200")
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(tmp, "Par.inp"), "w") as f:
+            f.write(deck)
+        p = subprocess.run([exe, "--quiet", "--device", str(device), "--bench", str(steps)], cwd=tmp, capture_output=True,
+                           text=True, timeout=900)
+    if p.returncode != 0:
+        return {"config": name, "error": (p.stdout + p.stderr)[-400:]}
+    r = json.loads(p.stdout.strip().splitlines()[-1])
+    ndofs = r["npoin"] * r["ndof"]
+    peak, _ = peaks()
+    b = config_bytes_per_dof(r["ngll"], r["ndof"], r["scheme"], r["kv"])
+    val = ndofs / (r["ms_per_step"] * 1e-3)
+    names = ("predictor", "element_force", "halo_fold_exchange", "sources", "boundary_conditions", "node_update", "outputs")
+    return {"config": name, "what": cfg["what"], "mesh": f"{nx * S}x{nz * S} elements (x{S} per side)", "npoin": r["npoin"],
+            "ngll": r["ngll"], "ndof": r["ndof"], "scheme": r["scheme"], "kelvin_voigt": r["kv"], "steps": r["steps"],
+            "value": val, "unit": UNIT, "ms_per_step": r["ms_per_step"], "launches_per_step": r["launches_per_step"],
+            "force_kernel_ms": r["kernel_ms"], "ms_per_step_by_phase": dict(zip(names, r["phases_ms"])),
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_dof": b, "achieved": b * val / 1e9, "peak": peak,
+                         "frac": b * val / 1e9 / peak, "unit": "GB/s",
+                         "note": "whole step against the bytes the step must move (config_bytes_per_dof)"},
+            "vmax": r["vmax"]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -338,6 +402,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-xdev", action="store_true", help="skip the cross-device parity check (N > 1)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (N > 1)")
+    ap.add_argument("--config", choices=sorted(REF_CONFIGS), default=None,
+                    help="time ONE of the reference's example decks (BASELINE.json configs[0..3]) scaled up, through the "
+                         "host program, and print its record instead of the benchmark line")
+    ap.add_argument("--config-scale", type=int, default=None, help="elements multiplier per side for --config")
+    ap.add_argument("--no-configs", action="store_true", help="skip the reference_configs sub-records (N = 1)")
     ap.add_argument("--generic-n", type=int, default=1536,
                     help="elements per side of the generic-route comparison (N = 1 only; 0 = skip)")
     ap.add_argument("--fint-reps", type=int, default=10)
@@ -356,6 +425,9 @@ def main():
     os.environ["S2D_STORE_ACCEL"] = "1" if args.accel == "every" else "2"
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.config:
+        print(json.dumps(run_ref_config(args.config, max(args.steps, 5), int(os.environ.get("LOCAL_RANK", "0")), args.config_scale)))
         return
     args.warmup = max(args.warmup, 3)
 
@@ -544,6 +616,8 @@ def main():
     }
     if world == 1 and args.generic_n > 0:
         line["generic_route"] = generic_route_record(min(args.generic_n, args.nx), K, W, local, args.precision, torch)
+    if world == 1 and not args.no_configs:   # BASELINE.json configs[0..3] at scale, same run (records, not the headline)
+        line["reference_configs"] = [run_ref_config(c, max(10, min(K, 30)), local) for c in ("testsh", "lamb", "tpv3", "ratestate")]
     if strong is not None:
         line["strong"] = strong
     if xdev is not None:

@@ -2,7 +2,11 @@
 // reads Par.inp from the working directory, builds the problem in HBM, runs the time loop on the
 // device and writes the reference's seismogram and fault files.
 //
-//   sem2dsolve_b200 [Par.inp] [--precision 4|8] [--device N] [--quiet] [--hash-seed S]
+//   sem2dsolve_b200 [Par.inp] [--precision 4|8] [--device N] [--quiet] [--hash-seed S] [--bench K]
+//
+// --bench K: after init, 5 warm-up steps, then K steps timed on the device (CUDA events, no host traffic); prints
+// one JSON line (steps, ms per step, the force kernel's ms per launch, ms per step of every phase) and exits
+// without writing files.  Used by bench.py --config for the reference's example decks at scale.
 //
 // --hash-seed S (S != 0) replaces the homogeneous &MAT_ELASTIC values by the heterogeneous hash medium of the
 // synthetic benchmark family (BASELINE.json configs[4]), so that this program can drive it.
@@ -21,12 +25,14 @@ using namespace sem2d;
 int main(int argc, char** argv) {
   std::string file = "Par.inp";
   bool quiet = false;
+  int bench_steps = 0;
   problem_type pb;
   for (int a = 1; a < argc; ++a) {
     const std::string s = argv[a];
     if (s == "--precision" && a + 1 < argc) pb.precision = std::atoi(argv[++a]);
     else if (s == "--device" && a + 1 < argc) pb.device = std::atoi(argv[++a]);
     else if (s == "--quiet") quiet = true;
+    else if (s == "--bench" && a + 1 < argc) bench_steps = std::atoi(argv[++a]);
     else if (s == "--hash-seed" && a + 1 < argc) pb.hash_seed = std::strtoull(argv[++a], nullptr, 10);
     else file = s;
   }
@@ -44,6 +50,27 @@ int main(int argc, char** argv) {
     }
     if (pb.iexec == 0) {  // check mode stops after the set-up (main.f90:66)
       std::printf(" iexec=0: problem checked, not solved\n");
+      return 0;
+    }
+    if (bench_steps > 0) {
+      solve(pb, 5);
+      float ms = 0.f, kms = 0.f, ph[S2D_NPHASES];
+      int64_t l0 = 0, l1 = 0;
+      int32_t route = 0;
+      s2d_check(pb, s2d_launch_count(pb.gpu, &l0), "bench");
+      s2d_check(pb, s2d_time_steps(pb.gpu, bench_steps, &ms), "bench");
+      s2d_check(pb, s2d_launch_count(pb.gpu, &l1), "bench");
+      s2d_check(pb, s2d_kernel_ms(pb.gpu, &kms), "bench");
+      s2d_check(pb, s2d_time_phases(pb.gpu, std::min(bench_steps, 10), ph), "bench");
+      s2d_check(pb, s2d_kernel_route(pb.gpu, &route), "bench");
+      double vmax = 0, dmax = 0;
+      s2d_check(pb, s2d_progress(pb.gpu, &vmax, &dmax), "bench");
+      std::printf("{\"npoin\": %lld, \"nelem\": %lld, \"ngll\": %d, \"ndof\": %d, \"scheme\": \"%s\", \"dt\": %.9e, \"steps\": %d, "
+                  "\"ms_per_step\": %.6f, \"kernel_ms\": %.6f, \"launches_per_step\": %.2f, \"kv\": %s, \"vmax\": %.6e, "
+                  "\"phases_ms\": [%.6f, %.6f, %.6f, %.6f, %.6f, %.6f, %.6f]}\n",
+                  (long long)pb.npoin, (long long)pb.nelem_total, pb.ngll, pb.ndof, pb.time.kind.c_str(), pb.time.dt, bench_steps,
+                  ms / bench_steps, kms, (double)(l1 - l0) / bench_steps, pb.has_kv ? "true" : "false", vmax, ph[0], ph[1], ph[2],
+                  ph[3], ph[4], ph[5], ph[6]);
       return 0;
     }
     // the snapshot files need the grid (spec_grid.f90 writes it at init); PLOT_FIELD at it = 0 (main.f90:38)

@@ -5,7 +5,7 @@ for v in "$@"; do
   set -- $v
   lib=$1; shift
   echo "== $lib $*"
-  env S2D_LIB_PATH=$PWD/sem2dpack_b200/$lib/libsem2d_b200.so "$@" python bench.py --nx ${NX:-4096} --nz ${NZ:-4096} --steps ${STEPS:-10} --no-cpu $ARGS 2>&1 | tail -1 | python -c "
+  env S2D_LIB_PATH=$PWD/sem2dpack_b200/$lib/libsem2d_b200.so "$@" python bench.py --nx ${NX:-4096} --nz ${NZ:-4096} --steps ${STEPS:-10} --no-cpu --no-configs --generic-n 0 $ARGS 2>&1 | tail -1 | python -c "
 import json,sys
 try:
     j=json.loads(sys.stdin.read()); r=j['roofline']

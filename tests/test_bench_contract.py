@@ -32,7 +32,8 @@ def test_reference_arm_line():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    j = _run(["--nx", "512", "--nz", "512", "--steps", "5", "--warmup", "3"], {"BENCH_CPU_SAMPLE_N": "96"})
+    j = _run(["--nx", "512", "--nz", "512", "--steps", "5", "--warmup", "3", "--generic-n", "256", "--no-configs"],
+             {"BENCH_CPU_SAMPLE_N": "96"})
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in j, k
@@ -46,3 +47,19 @@ def test_gpu_arm_line():
     assert j["e2e"]["h2d_bytes_per_step"] > 0 and j["e2e"]["d2h_bytes_per_step"] > 0 and j["e2e"]["value"] > 0
     assert j["gpu_launches"] >= 5 and j["cpu_baseline"]["cores"] == 1
     assert set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert j["gpu_launches"] == 6 * 5          # six launches per fused step
+    g = j["generic_route"]
+    assert g["kernel_route"] == "strip kernel" and 0.8 < g["generic_over_builder"] < 1.25
+    assert set(j["ms_per_step_by_phase"]) >= {"element_force", "boundary_conditions", "outputs"}
+    assert j["cpu_baseline"]["parity_build_value"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,scale", [("testsh", 2), ("lamb", 2), ("tpv3", 2), ("ratestate", 1)])
+def test_reference_config_records(name, scale):
+    """bench.py --config: BASELINE.json configs[0..3] through the host program (small scale here)"""
+    j = _run(["--config", name, "--config-scale", str(scale), "--steps", "20"])
+    assert "error" not in j, j
+    assert j["config"] == name and j["value"] > 0 and j["roofline"]["frac"] > 0
+    assert j["kelvin_voigt"] == (name == "tpv3")
+    assert abs(j["value"] - j["npoin"] * j["ndof"] / (j["ms_per_step"] * 1e-3)) <= 1e-6 * j["value"]
