@@ -167,6 +167,7 @@ struct problem_type {
   int64_t npoin = 0, nelem_total = 0;
   int it = 0;
   int precision = 8, device = -1;
+  bool renumber = true;   // RCM element order and the node numbering of a stock reference build (--natural-order: off)
   unsigned long long hash_seed = 0;  // != 0: the heterogeneous hash medium of the synthetic benchmark family
   ~problem_type() {
     if (gpu) s2d_destroy(gpu);
@@ -637,6 +638,7 @@ inline void init_main(problem_type& pb) {
   d.scheme.alpha = pb.time.alpha;
   d.courant = pb.time.courant;
   d.device = pb.device;
+  d.renumber = pb.renumber ? 1 : 0;  // OPT_RENUMBER (SRC/constants.f90:10-15): the reference's default
   const int rc = s2d_cart_create(&pb.gpu, &d);
   if (rc == S2D_ENODEV) IO_abort("init_main: no CUDA device (the B200 path has no CPU fallback)");
   if (rc != S2D_OK) IO_abort("init_main: s2d_cart_create failed (code " + std::to_string(rc) + ")");
@@ -663,21 +665,25 @@ inline void init_main(problem_type& pb) {
     const auto& M = pb.mat[(size_t)tg - 1];
     one_material = one_material && M.homogeneous() && M.rho.c == pb.rho && M.cp.c == pb.cp && M.cs.c == pb.cs;
   }
-  std::vector<int32_t> ibool;
-  std::vector<double> coord;
-  if (!one_material || pb.has_kv) {
-    ibool.resize((size_t)pb.nelem_total * n2);
-    coord.resize(2 * (size_t)pb.npoin);
-    s2d_check(pb, s2d_cart_get(pb.gpu, ibool.data(), nullptr, nullptr, coord.data()), "MAT_init_prop");
-  }
+  // coordinates of the GLL points of element e = ix + nx*iz (natural order: the order s2d_cart_set_material and
+  // s2d_cart_set_kv_elems expect whatever the numbering of the outputs), as the builder computes them
+  std::vector<double> xgll((size_t)N);
+  s2d_check(pb, s2d_cart_get_gll(pb.gpu, xgll.data(), nullptr, nullptr), "MAT_init_prop");
+  const double hx = (pb.xlim[1] - pb.xlim[0]) / nx, hz = (pb.zlim[1] - pb.zlim[0]) / nz;
+  auto gll_xz = [&](size_t e, int q, double& x, double& z) {
+    const int ix = (int)(e % (size_t)nx), iz = (int)(e / (size_t)nx), i = q % N, j = q / N;
+    x = pb.xlim[0] + hx * (ix + 0.5 * (xgll[(size_t)i] + 1.0));
+    z = pb.zlim[0] + hz * (iz + 0.5 * (xgll[(size_t)j] + 1.0));
+  };
   if (!one_material) {
     if (pb.hash_seed) IO_abort("init_main: the synthetic hash medium replaces the deck's materials; give one homogeneous material");
-    std::vector<double> rho(ibool.size()), cp(ibool.size()), cs(ibool.size());
+    const size_t nn = (size_t)pb.nelem_total * n2;
+    std::vector<double> rho(nn), cp(nn), cs(nn);
     for (size_t e = 0; e < (size_t)pb.nelem_total; ++e) {
       const auto& M = pb.mat[(size_t)tag[e] - 1];
       for (int q = 0; q < n2; ++q) {
-        const size_t nd = (size_t)ibool[e * n2 + q] - 1;
-        const double x = coord[2 * nd], z = coord[2 * nd + 1];
+        double x, z;
+        gll_xz(e, q, x, z);
         rho[e * n2 + q] = M.rho.eval(x, z);
         cp[e * n2 + q] = M.cp.eval(x, z);
         cs[e * n2 + q] = M.cs.eval(x, z);
@@ -702,8 +708,9 @@ inline void init_main(problem_type& pb) {
       if (!M.kv) continue;
       ids.push_back((int32_t)e + 1);
       for (int q = 0; q < n2; ++q) {
-        const size_t nd = (size_t)ibool[e * n2 + q] - 1;
-        double v = M.eta.eval(coord[2 * nd], coord[2 * nd + 1]);
+        double x, z;
+        gll_xz(e, q, x, z);
+        double v = M.eta.eval(x, z);
         if (M.ETAxDT) v = t.dt * v;
         eta.push_back(v);
       }
@@ -852,7 +859,8 @@ inline void solve(problem_type& pb, int nsteps = 1) {
 
 // Grid files every reader of the snapshots needs (SE_init, SRC/spec_grid.f90:136-141,296-306,365-371):
 // grid_sem2d.hdr, ibool_sem2d.dat (int32 (ngll,ngll) per element), coord_sem2d.dat (float32 (2) per node).
-// The structured builder numbers the elements row by row (OPT_RENUMBER = .false., constants.f90:10-15).
+// Element order and node numbering are those of the reference's default OPT_RENUMBER = .true. (constants.f90:10-15)
+// unless the program was started with --natural-order.
 inline void SE_write_grid(problem_type& pb, const std::string& dir = ".") {
   const size_t n2 = (size_t)pb.ngll * pb.ngll;
   std::vector<int32_t> ibool(n2 * (size_t)pb.nelem_total);

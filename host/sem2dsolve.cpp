@@ -2,7 +2,10 @@
 // reads Par.inp from the working directory, builds the problem in HBM, runs the time loop on the
 // device and writes the reference's seismogram and fault files.
 //
-//   sem2dsolve_b200 [Par.inp] [--precision 4|8] [--device N] [--quiet] [--hash-seed S] [--bench K]
+//   sem2dsolve_b200 [Par.inp] [--precision 4|8] [--device N] [--quiet] [--hash-seed S] [--bench K] [--natural-order]
+//
+// --natural-order: row-by-row element order (OPT_RENUMBER = .false.) instead of the reference's default reverse
+// Cuthill-McKee order; only the element / node numbering of the grid files and snapshots changes.
 //
 // --bench K: after init, 5 warm-up steps, then K steps timed on the device (CUDA events, no host traffic); prints
 // one JSON line (steps, ms per step, the force kernel's ms per launch, ms per step of every phase) and exits
@@ -32,6 +35,7 @@ int main(int argc, char** argv) {
     if (s == "--precision" && a + 1 < argc) pb.precision = std::atoi(argv[++a]);
     else if (s == "--device" && a + 1 < argc) pb.device = std::atoi(argv[++a]);
     else if (s == "--quiet") quiet = true;
+    else if (s == "--natural-order") pb.renumber = false;
     else if (s == "--bench" && a + 1 < argc) bench_steps = std::atoi(argv[++a]);
     else if (s == "--hash-seed" && a + 1 < argc) pb.hash_seed = std::strtoull(argv[++a], nullptr, 10);
     else file = s;

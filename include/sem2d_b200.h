@@ -223,6 +223,11 @@ int s2d_kernel_route(s2d_handle h, int32_t* route);
 int s2d_detect_structured(int32_t ngll, int32_t nelem, int32_t npoin, const int32_t* ibool, int32_t lower_hint,
                           int32_t* nx, int32_t* nz, int32_t* ezflt, int32_t* ex, int32_t* ez, int32_t* gx, int32_t* gz);
 
+/* MESH_STRUCTURED_renumber (SRC/mesh_structured.f90:204-269) + genrcm (SRC/rcm.f90): the reverse Cuthill-McKee
+ * order the reference gives the elements of every structured mesh by default (OPT_RENUMBER, constants.f90:10-15).
+ * perm(nx*nz), 1-based: perm(new) = old, old = i + nx*(j-1) for element (i,j) of CART_build.  Host only. */
+int s2d_rcm_box(int32_t nx, int32_t nz, int32_t* perm);
+
 /* ---- measurement hooks ------------------------------------------------------------------- */
 /* Times `reps` launches of the element-force+assembly stage alone (CUDA events on the engine's
  * stream), fields untouched apart from accel; returns average milliseconds per launch. */
@@ -269,6 +274,12 @@ typedef struct {
    *    same sequence of roundings (a third of the coefficient traffic);
    * 1: all nelast planes are stored, as matwrk_elast_type%a is (mat_elastic.f90:11-14). */
   int32_t coef_mode;
+  /* != 0: OPT_RENUMBER = .true., the reference's default (SRC/constants.f90:10-15): the elements are put in reverse
+   * Cuthill-McKee order (MESH_STRUCTURED_renumber, mesh_structured.f90:204-269; genrcm, rcm.f90) and the GLL nodes are
+   * numbered by SE_init_numbering in that order, so that s2d_cart_get's ibool, s2d_get_fields / s2d_set_fields and
+   * every node-ordered output are those of a stock reference build.  0: natural (row by row) element order.
+   * s2d_cart_set_material / s2d_cart_set_kv_elems keep the natural element order either way.  Not on x-strips. */
+  int32_t renumber;
 } s2d_cart_desc;
 int s2d_cart_create(s2d_handle* h, const s2d_cart_desc* desc);
 /* BC_ABSO_init on mesh side tag 1 bottom, 2 right, 3 top, 4 left (mesh_structured.f90:86-196);

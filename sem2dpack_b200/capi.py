@@ -66,7 +66,7 @@ class CartDesc(C.Structure):
         ("seed", C.c_uint64), ("ix0", C.c_int64), ("iz0", C.c_int64),
         ("rho", C.c_double), ("cp", C.c_double), ("cs", C.c_double),
         ("precision", C.c_int32), ("scheme", Scheme), ("courant", C.c_double), ("device", C.c_int32),
-        ("halo_left", C.c_int32), ("halo_right", C.c_int32), ("coef_mode", C.c_int32),
+        ("halo_left", C.c_int32), ("halo_right", C.c_int32), ("coef_mode", C.c_int32), ("renumber", C.c_int32),
     ]
 
 
@@ -104,6 +104,7 @@ _SIGS = {
     "s2d_time_fint": [C.c_void_p, C.c_int32, C.POINTER(C.c_float)],
     "s2d_time_steps": [C.c_void_p, C.c_int32, C.POINTER(C.c_float)],
     "s2d_kernel_ms": [C.c_void_p, C.POINTER(C.c_float)],
+    "s2d_rcm_box": [C.c_int32, C.c_int32, C.c_void_p],
     "s2d_kernel_route": [C.c_void_p, C.POINTER(C.c_int32)],
     "s2d_detect_structured": [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
                               C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],

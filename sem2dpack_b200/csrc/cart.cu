@@ -19,6 +19,7 @@
 #include <map>
 
 #include "engine.hpp"
+#include "rcm_box.hpp"
 
 namespace s2d {
 
@@ -446,6 +447,11 @@ struct CartState {
   DevBuf<double> d_mat[3];
   bool dt_given = false;
   double W25d = 0.0;              // &GENERAL W when finite (2.5D), else 0
+  // OPT_RENUMBER (s2d_cart_desc.renumber): elements in reverse Cuthill-McKee order and the GLL numbering that
+  // SE_init_numbering gives in that order (spec_grid.f90:198-314)
+  bool renumber = false;
+  std::vector<int32_t> perm;        // perm[new] = old element (0-based, natural order)
+  std::vector<int32_t> id_of_lat;   // (LXP*LZ) 1-based node id of every lattice point (0 on the pad columns)
   CartGeom dev_geom() const {     // the geometry as the kernels see it
     CartGeom g = G;
     for (int q = 0; q < 3; ++q) g.mat[q] = d_mat[q].p;
@@ -552,6 +558,12 @@ static void cart_build(Engine<T>& E, CartState& S) {
     k_cart_permute<double, double><<<nblk, 256, 0, Ep->stream>>>(Gc, ref, lat, Ep->npoin_ref, Ep->npoin, 1, 0);
     S2D_CUDA(cudaGetLastError());
   };
+  if (S.renumber) {  // RCM element order: the caller's node ids come from a table, like a routed generic handle
+    std::vector<int32_t> lat_of(E.npoin_ref);
+    for (size_t l = 0; l < S.id_of_lat.size(); ++l)
+      if (S.id_of_lat[l] > 0) lat_of[(size_t)S.id_of_lat[l] - 1] = (int32_t)l;
+    E.install_lat_table(lat_of);
+  }
   S2D_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -563,6 +575,49 @@ static Engine<T>* as_engine(EngineBase* b) {
 // coordinates of GLL point (i,j) (0-based) of element (ix,iz)
 static inline double gx_of(const CartGeom& G, int ix, int i) { return G.x0 + G.hx * (ix + 0.5 * (G.xgll[i] + 1.0)); }
 static inline double gz_of(const CartGeom& G, int iz, int j) { return G.z0 + G.hz * (iz + 0.5 * (G.xgll[j] + 1.0)); }
+
+// node id (1-based, the caller's numbering) of GLL point (i,j) (0-based) of element (ix,iz)
+static inline long long cart_ref_id(const CartState& S, int ix, int iz, int i, int j) {
+  if (S.renumber) return S.id_of_lat[(size_t)(cart_lat_id(S.G, ix, iz, i, j) - 1)];
+  return cart_node_id(S.G, ix, iz, i + 1, j + 1);
+}
+
+// SE_init_numbering (spec_grid.f90:249-287) over the elements in the order perm: interior points (i fastest),
+// then the edges D, R, U, L whose points are still unnumbered (counter-clockwise interior points), then the
+// vertices SW, SE, NE, NW that are still unnumbered.  A GLL point is identified by its lattice position, which is
+// what the reference's neighbour / vertex lists establish (split fault rows are two lattice rows).
+static void cart_number_nodes(CartState& S) {
+  const CartGeom& G = S.G;
+  const int N = G.N;
+  S.id_of_lat.assign((size_t)G.S.LXP * G.S.LZ, 0);
+  int32_t npoin = 0;
+  auto at = [&](int ix, int iz, int i, int j) -> int32_t& { return S.id_of_lat[(size_t)(cart_lat_id(G, ix, iz, i, j) - 1)]; };
+  for (size_t en = 0; en < S.perm.size(); ++en) {
+    const int ix = S.perm[en] % G.nx, iz = S.perm[en] / G.nx;
+    for (int j = 1; j < N - 1; ++j)
+      for (int i = 1; i < N - 1; ++i) at(ix, iz, i, j) = ++npoin;
+    for (int n = 0; n < 4; ++n) {  // edge tables (spec_grid.f90:876-883): D, R, U, L
+      auto pt = [&](int k, int& i, int& j) {
+        switch (n) {
+          case 0: i = k; j = 0; break;
+          case 1: i = N - 1; j = k; break;
+          case 2: i = N - 1 - k; j = N - 1; break;
+          default: i = 0; j = N - 1 - k; break;
+        }
+      };
+      int i, j;
+      pt(1, i, j);
+      if (at(ix, iz, i, j) != 0) continue;
+      for (int k = 1; k < N - 1; ++k) {
+        pt(k, i, j);
+        at(ix, iz, i, j) = ++npoin;
+      }
+    }
+    const int vi[4] = {0, N - 1, N - 1, 0}, vj[4] = {0, 0, N - 1, N - 1};
+    for (int n = 0; n < 4; ++n)
+      if (at(ix, iz, vi[n], vj[n]) == 0) at(ix, iz, vi[n], vj[n]) = ++npoin;
+  }
+}
 
 // nearest GLL lattice position along one axis: element index and local index
 static void nearest_1d(const CartGeom& G, double x, double x0, double h, int n, int& e, int& i) {
@@ -653,6 +708,15 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
     if (nlat > 2147483647LL || nelem * G.N * G.N > (1LL << 40)) {
       g_cart_err = "mesh too large for 32-bit node ids";
       return S2D_EINVAL;
+    }
+    S->renumber = D->renumber != 0;
+    if (S->renumber) {
+      if (G.halo_left || G.halo_right) {
+        g_cart_err = "renumber: an x-strip with neighbours keeps the natural element order";
+        return S2D_EINVAL;
+      }
+      S->perm = rcm_box_perm(G.nx, G.nz);
+      cart_number_nodes(*S);
     }
     S->scheme = D->scheme;
     S->courant = D->courant;
@@ -1275,7 +1339,20 @@ int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double*
   const CartGeom& G = S.G;
   const int N = G.N, N2 = N * N;
   const long long tot = (long long)Eb->nelem * N2;
-  if (ibool) {
+  // element e of the caller's order sits at (ix,iz) of the box
+  auto elem_pos = [&](size_t e, int& ix, int& iz) {
+    const size_t old = S.renumber ? (size_t)S.perm[e] : e;
+    ix = (int)(old % G.nx);
+    iz = (int)(old / G.nx);
+  };
+  if (ibool && S.renumber) {
+    for (size_t e = 0; e < (size_t)Eb->nelem; ++e) {
+      int ix, iz;
+      elem_pos(e, ix, iz);
+      for (int j = 0; j < N; ++j)
+        for (int i = 0; i < N; ++i) ibool[e * N2 + i + N * j] = (int32_t)cart_ref_id(S, ix, iz, i, j);
+    }
+  } else if (ibool) {
     DevBuf<int> ib;
     ib.alloc((size_t)tot);
     k_cart_ibool<<<(unsigned)((tot + 255) / 256), 256, 0, Eb->stream>>>(G, ib.p);
@@ -1296,9 +1373,10 @@ int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double*
       compact = as_engine<float>(Eb)->cart_compact;
     }
     const double cdx = 2.0 / G.hx, cdz = 2.0 / G.hz, det = (0.5 * G.hx) * (0.5 * G.hz);
-    for (int iz = 0; iz < G.nz; ++iz)
-      for (int ix = 0; ix < G.nx; ++ix) {
-        const size_t e = (size_t)ix + (size_t)G.nx * iz;
+    for (size_t e = 0; e < (size_t)Eb->nelem; ++e) {
+      {
+        int ix, iz;
+        elem_pos(e, ix, iz);
         for (int j = 0; j < N; ++j)
           for (int i = 0; i < N; ++i) {
             double av[6];
@@ -1318,16 +1396,14 @@ int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double*
             for (int pl = 0; pl < nelast; ++pl) a[(e * nelast + pl) * N2 + i + N * j] = av[pl];
           }
       }
+    }
   }
   if (rmass) {
     const size_t nd = Eb->npoin_ref * G.ndof;
     DevBuf<double> tmp;
     tmp.alloc(nd);
-    const unsigned nblk = (unsigned)((tot + 255) / 256);
-    if (Eb->prec == 8)
-      k_cart_permute<double, double><<<nblk, 256, 0, Eb->stream>>>(G, as_engine<double>(Eb)->rmass.p, tmp.p, Eb->npoin_ref, Eb->npoin, G.ndof, 1);
-    else
-      k_cart_permute<float, double><<<nblk, 256, 0, Eb->stream>>>(G, as_engine<float>(Eb)->rmass.p, tmp.p, Eb->npoin_ref, Eb->npoin, G.ndof, 1);
+    if (Eb->prec == 8) as_engine<double>(Eb)->cart_to_ref(as_engine<double>(Eb)->rmass.p, tmp.p);
+    else as_engine<float>(Eb)->cart_to_ref(as_engine<float>(Eb)->rmass.p, tmp.p);
     S2D_CUDA(cudaStreamSynchronize(Eb->stream));
     tmp.download(rmass);
     if (!Eb->committed)
@@ -1338,7 +1414,7 @@ int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double*
       for (int ix = 0; ix < G.nx; ++ix)
         for (int j = 0; j < N; ++j)
           for (int i = 0; i < N; ++i) {
-            const size_t nd = (size_t)(cart_node_id(G, ix, iz, i + 1, j + 1) - 1);
+            const size_t nd = (size_t)(cart_ref_id(S, ix, iz, i, j) - 1);
             coord[2 * nd] = gx_of(G, ix, i);
             coord[2 * nd + 1] = gz_of(G, iz, j);
           }

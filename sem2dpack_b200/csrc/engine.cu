@@ -1,6 +1,7 @@
 // C-ABI of the sem2d_b200 engine (include/sem2d_b200.h).
 #define S2D_INSTANTIATE_F64
 #include "engine.hpp"
+#include "rcm_box.hpp"
 
 using namespace s2d;
 template class s2d::Engine<double>;
@@ -261,6 +262,12 @@ int s2d_detect_structured(int32_t ngll, int32_t nelem, int32_t npoin, const int3
   if (ez) std::copy(B.ez.begin(), B.ez.end(), ez);
   if (gx) std::copy(B.gx.begin(), B.gx.end(), gx);
   if (gz) std::copy(B.gz.begin(), B.gz.end(), gz);
+  return S2D_OK;
+}
+int s2d_rcm_box(int32_t nx, int32_t nz, int32_t* perm) {
+  if (nx < 1 || nz < 1 || !perm || (long long)nx * nz > 2147483647LL) return S2D_EINVAL;
+  const std::vector<int32_t> p = rcm_box_perm(nx, nz);
+  for (size_t k = 0; k < p.size(); ++k) perm[k] = p[k] + 1;
   return S2D_OK;
 }
 int s2d_kernel_route(s2d_handle h, int32_t* route) {

@@ -1051,6 +1051,13 @@ class Engine : public EngineBase {
     cart_compact = 0;
     p_hetero = true;
     init_strip_tables(S);
+    install_lat_table(h_lat_of);
+    return true;
+  }
+  // the caller's node numbering as a table: lat_of[k] = 0-based lattice index of the caller's node k + 1
+  void install_lat_table(const std::vector<int32_t>& table) {
+    h_lat_of = table;
+    lat_of.upload(h_lat_of);
     Engine<T>* Ep = this;
     cart_to_ref = [Ep](const T* lat, double* ref) {
       k_lat_permute<T, double><<<Ep->grid_for(Ep->npoin_ref), 256, 0, Ep->stream>>>(lat, ref, Ep->lat_of.p, Ep->npoin_ref, Ep->npoin, Ep->ndof, 1);
@@ -1068,7 +1075,6 @@ class Engine : public EngineBase {
       k_lat_permute<double, double><<<Ep->grid_for(Ep->npoin_ref), 256, 0, Ep->stream>>>(ref, lat, Ep->lat_of.p, Ep->npoin_ref, Ep->npoin, 1, 0);
       S2D_CUDA(cudaGetLastError());
     };
-    return true;
   }
   bool rmass_is_inverse = false;
   std::vector<int32_t> h_fault_node1;  // first node1 of every fault (which side of a split-node row is the lower one)

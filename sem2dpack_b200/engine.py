@@ -287,7 +287,7 @@ class CartEngine(Engine):
 
     def __init__(self, ngll, ndof, nx, nz, xlim, zlim, ezflt=0, seed=0, rho=0.0, cp=0.0, cs=0.0, scheme_kind=0,
                  dt=0.0, courant=0.5, beta=0.0, gamma=0.5, alpha=1.0, precision=8, device=-1, ix0=0, iz0=0,
-                 halo_left=False, halo_right=False, coef_mode=0, stages=None):
+                 halo_left=False, halo_right=False, coef_mode=0, stages=None, renumber=False):
         L = capi.lib()
         d = capi.CartDesc()
         d.ngll, d.ndof, d.nx, d.nz, d.ezflt = ngll, ndof, nx, nz, ezflt
@@ -301,6 +301,7 @@ class CartEngine(Engine):
         d.device = device
         d.halo_left, d.halo_right = int(halo_left), int(halo_right)
         d.coef_mode = int(coef_mode)  # 0: (lambda, mu) only where the rheology allows, 1: all planes in HBM
+        d.renumber = int(renumber)    # OPT_RENUMBER: RCM element order and the node numbering that follows from it
         h = C.c_void_p()
         rc = L.s2d_cart_create(C.byref(h), C.byref(d))
         if rc != 0:

@@ -267,3 +267,36 @@ def test_fused_step_receiver_fields(field, scheme):
     assert np.abs(s_got - s_ref).max() <= 2e-7 * np.abs(s_ref).max()
     e.close()
     o.close()
+
+
+@pytest.mark.parametrize("ngll,nx,nz,ezflt", [(5, 19, 13, 6), (6, 11, 9, 0), (3, 30, 7, 3), (9, 7, 8, 4), (5, 64, 40, 20)])
+def test_rcm_order_ibool_bit_exact_and_fields_in_that_numbering(ngll, nx, nz, ezflt):
+    """s2d_cart_desc.renumber = 1: OPT_RENUMBER = .true., the reference's DEFAULT (SRC/constants.f90:10-15).  Elements in
+    the reverse Cuthill-McKee order of MESH_STRUCTURED_renumber (mesh_structured.f90:204-269, rcm.f90) and GLL nodes
+    numbered by SE_init_numbering in that order: ibool bit for bit against the oracle's restatement, coordinates, and
+    a run whose fields come back in that numbering."""
+    deck = harness.cart_deck(nx, nz, ngll=ngll, ezflt=ezflt, nsteps=60, fault=None, nrec=0)
+    o = orc.Oracle(deck, synthetic_seed=SEED, renumber=True)
+    e = CartEngine(ngll, 2, nx, nz, (0.0, nx * 100.0), (0.0, nz * 100.0), ezflt=ezflt, seed=SEED, scheme_kind=0,
+                   courant=0.5, renumber=True)
+    assert e.npoin == o.i("npoin")
+    ib, a, rm, co = e.get_tables(ibool=True, a=True, rmass=True, coord=True)
+    assert np.array_equal(ib, o.arr("ibool"))
+    assert np.abs(co - o.arr("coord")).max() <= 1e-9
+    assert rel_l2(a, o.arr("a")) <= 1e-13          # per-element planes in RCM element order
+    for side in (1, 2, 3, 4):
+        e.add_abso_side(side, False)
+    e.add_force_at(0.37 * nx * 100.0, 0.61 * nz * 100.0, [o.f("src.0.dir1"), o.f("src.0.dir2")])
+    e.commit()
+    rng = np.random.default_rng(2)
+    n = e.npoin * 2
+    d0, v0 = rng.standard_normal(n) * 1e-3, rng.standard_normal(n)
+    e.set_fields(d0, v0)
+    o.set_fields(d0, v0)
+    nsteps = 60
+    e.step(nsteps, np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)]))
+    o.step(nsteps)
+    d, v, _ = e.get_fields()
+    assert rel_l2(d, o.arr("d")) <= 1e-10 and rel_l2(v, o.arr("v")) <= 1e-10
+    e.close()
+    o.close()

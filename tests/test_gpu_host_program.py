@@ -159,13 +159,16 @@ def test_tpv3_deck_against_the_oracle(tmp_path):
     o.close()
 
 
-def test_binary_snapshots_and_grid_files(tmp_path):
-    """&SNAP_DEF bin=T: PLOT_FIELD's node-wise float32 files and the grid files POST/ reads them with"""
+@pytest.mark.parametrize("renumber", [True, False])
+def test_binary_snapshots_and_grid_files(tmp_path, renumber):
+    """&SNAP_DEF bin=T: PLOT_FIELD's node-wise float32 files and the grid files POST/ reads them with.  By default in
+    the element order and node numbering of a stock reference build (OPT_RENUMBER = .true., constants.f90:10-15):
+    ibool_sem2d.dat is bit for bit the oracle's RCM-ordered table; --natural-order gives the row-by-row order."""
     deck = harness.deck("lamb").replace("TotalTime=1.5d0, Dt=0.5d-3", "NbSteps=250, Dt=0.5d-3")
     deck = deck.replace("&SNAP_DEF itd=5000, fields='V'/", "&SNAP_DEF itd=100, fields='DV', ps=F /")
-    p = run(tmp_path, deck, "--quiet")
+    p = run(tmp_path, deck, "--quiet", *([] if renumber else ["--natural-order"]))
     assert p.returncode == 0, p.stdout + p.stderr
-    o = orc.Oracle(deck, renumber=False)
+    o = orc.Oracle(deck, renumber=renumber)
     npoin, nelem = o.i("npoin"), o.i("nelem")
     hdr = (tmp_path / "grid_sem2d.hdr").read_text().split("\n")[1].split()
     assert [int(v) for v in hdr] == [nelem, 41 * 21, 4, npoin, 9]
@@ -274,3 +277,35 @@ def test_2p5d_inplane_deck_through_the_host_program(tmp_path):
         assert np.abs(rec[:, c] - want[:, c]).max() <= 1e-6 * max(np.abs(want[:, c]).max(), 1e-30), c
     assert np.abs(rec[-1, 0]).max() > 0
     o.close()
+
+
+@pytest.mark.parametrize("kind", ["USER", "TAB"])
+def test_user_and_tabulated_source_time_functions(tmp_path, kind):
+    """STF_USER_fun (stf_user.f90:66-79) and STF_TAB_fun (stf_tabulated.f90:76-93: cubic spline with zero end slopes,
+    clamped to the table) through the host program, against the same deck driven through the generic C-ABI with the
+    amplitude table evaluated here (scipy's clamped CubicSpline for TAB)"""
+    from scipy.interpolate import CubicSpline
+    nsteps = 300
+    base = harness.deck("testsh").replace("TotalTime=35.d0", f"NbSteps={nsteps}")
+    o = orc.Oracle(base)
+    dt = o.f("dt")
+    t = (np.arange(nsteps) + 1) * dt
+    if kind == "USER":
+        deck = base.replace("'RICKER'", "'USER'") + "&STF_USER ampli=2.0, onset=0.25, par1=0.05 /\n"
+        arg = t - np.float64(np.float32(0.25))
+        amp = np.float64(np.float32(2.0)) * np.sin(arg) + np.float64(np.float32(0.05)) * arg ** 2
+    else:
+        tt = np.linspace(0.5, 4.0, 36)
+        vv = np.exp(-((tt - 2.0) / 0.6) ** 2) * np.cos(3.0 * tt)
+        (tmp_path / "stf.tab").write_text("".join(f"{a:.16e} {b:.16e}\n" for a, b in zip(tt, vv)))
+        deck = base.replace("'RICKER'", "'TAB'") + "&STF_TAB file='stf.tab' /\n"
+        amp = CubicSpline(tt, vv, bc_type=((1, 0.0), (1, 0.0)))(np.clip(t, tt[0], tt[-1]))
+    p = run(tmp_path, deck, "--quiet")
+    assert p.returncode == 0, p.stdout + p.stderr
+    _, _, u = read_sep(tmp_path, "Uy_sem2d.dat")
+    r = harness.Rig(o)
+    r.e.step(nsteps, amp.reshape(-1, 1))
+    ref = r.e.seis()[:, :, 0]
+    assert np.abs(ref).max() > 0
+    assert np.abs(u - ref).max() <= 1e-6 * np.abs(ref).max()
+    r.close()

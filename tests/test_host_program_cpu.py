@@ -19,10 +19,12 @@ def test_refusals_happen_while_reading_the_deck(tmp_path):
     cases = [
         (harness.deck("tpv3").replace("'ELAST' ,'KV'", "'ELAST' ,'PLAST'"), "MAT_read"),
         (harness.deck("tpv3").replace("etaH='GAUSSIAN'", "etaH='LINEAR'"), "DIST_read"),
-        (harness.deck("ratestate").replace("friction='RSF'", "friction='TWF'"), "friction='TWF'"),
+        (harness.deck("ratestate").replace("friction='RSF'", "friction='XYZ'"), "invalid friction"),
         (harness.deck("ratestate").replace("TtH='ORDER0'", "TtH='SPLINE'"), "DIST_read"),
         (harness.deck("testsh").replace("courant = 0.3d0", "courant = 0.9d0"), "Courant out of range [0,0.6]"),
-        (harness.deck("testsh").replace("'RICKER'", "'BUTTERWORTH'"), "STF_read"),
+        (harness.deck("testsh").replace("'RICKER'", "'BUTTERWORTH'"), "BUTTER_read: not implemented"),   # as the reference
+        (harness.deck("testsh").replace("'RICKER'", "'SPIKE'"), "STF_read"),
+        (harness.deck("testsh").replace("'RICKER'", "'TAB'"), "STF_TAB_read"),                              # no stf.tab here
         (harness.deck("testsh").replace("kind = 'ABSORB'", "kind = 'PERIOD'", 1), "BC_read"),
         (harness.deck("lamb").replace("TotalTime=1.5d0, Dt=0.5d-3", "TotalTime=1.5d0, NbSteps=10"), "bad combination"),
         ("&GENERAL iexec=1 /\n", "MESH_DEF input block not found"),

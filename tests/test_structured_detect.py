@@ -67,3 +67,15 @@ def test_not_a_box():
     assert detect_structured(5, (inv + 1).astype(np.int32), int(inv.max()) + 1) is None
     o.close()
     natural.close()
+
+
+@pytest.mark.parametrize("nx,nz", [(1, 1), (1, 7), (9, 1), (2, 2), (19, 13), (40, 24), (270, 90), (7, 64), (60, 60), (100, 3)])
+def test_rcm_order_equals_the_oracles_restatement_of_genrcm(nx, nz):
+    """s2d_rcm_box (csrc/rcm_box.hpp) against oracle/rcm.hpp, two independent restatements of SRC/rcm.f90 +
+    mesh_structured.f90:204-269; integer data, bit-exact"""
+    import ctypes as C
+    from sem2dpack_b200 import capi
+    perm = np.empty(nx * nz, np.int32)
+    assert capi.lib().s2d_rcm_box(nx, nz, perm.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(perm, orc.rcm(nx, nz))
+    assert np.array_equal(np.sort(perm), np.arange(1, nx * nz + 1))
