@@ -161,12 +161,13 @@ struct problem_type {
   std::vector<bc_type> bc;
   std::vector<source_type> src;
   std::unique_ptr<rec_type> rec;
-  // &SNAP_DEF (SRC/plot_gen.f90:58-110): binary snapshots of the node fields only
-  bool snap_bin = false, snap_fields[3] = {false, false, false};  // D, V, A
+  // &SNAP_DEF (SRC/plot_gen.f90:58-110): binary snapshots; field_names = 'DVAESdc' (plot_gen.f90:13)
+  bool snap_bin = false, snap_fields[7] = {false, false, false, false, false, false, false};
   int snap_itd = 100, snap_it1 = 0;
   int64_t npoin = 0, nelem_total = 0;
   int it = 0;
   int precision = 8, device = -1;
+  bool compute_energies = false;   // COMPUTE_ENERGIES (SRC/constants.f90:22): energy_sem2d.tab, one line per step
   bool renumber = true;   // RCM element order and the node numbering of a stock reference build (--natural-order: off)
   unsigned long long hash_seed = 0;  // != 0: the heterogeneous hash medium of the synthetic benchmark family
   ~problem_type() {
@@ -577,13 +578,9 @@ inline void read_main(problem_type& pb, const std::string& file) {
       pb.snap_itd = g.integer("itd", 100);
       pb.snap_it1 = g.integer("it1", 0);
     }
-    for (char c : fields) {
-      if (c == 'D') pb.snap_fields[0] = true;
-      else if (c == 'V') pb.snap_fields[1] = true;
-      else if (c == 'A') pb.snap_fields[2] = true;
-      else if (pb.snap_bin && c != ' ')  // off the path: skipped with a warning, like the plots
-        std::printf(" *** WARNING: SNAP_DEF: snapshot field '%c' (strain, stress, divergence, curl) is not written by this host ***\n", c);
-    }
+    static const char field_names[] = "DVAESdc";
+    for (int i = 0; i < 7; ++i) pb.snap_fields[i] = fields.find(field_names[i]) != std::string::npos;  // scan(fields, ...) > 0
+    if (pb.ndof == 1) pb.snap_fields[5] = pb.snap_fields[6] = false;  // no div / curl for SH (plot_gen.f90:100)
     if (pb.snap_itd <= 0) IO_abort("SNAP_DEF: itd must be positive");
   }
   // REC_read (SRC/receivers.f90:62-140)
@@ -885,14 +882,20 @@ inline void SE_write_grid(problem_type& pb, const std::string& dir = ".") {
 // PLOT_FIELD's binary branch (SRC/plot_gen.f90:168-215 -> IO_rw_field, SRC/stdio.f90:112-139): one float32
 // per node, files <d|v|a><x|z|y>_NNN_sem2d.dat, NNN = (it-IT1)/ITD
 inline bool snapshot_due(const problem_type& pb, int it) {
-  if (!pb.snap_bin || !(pb.snap_fields[0] || pb.snap_fields[1] || pb.snap_fields[2])) return false;
+  bool any = false;
+  for (bool f : pb.snap_fields) any = any || f;
+  if (!pb.snap_bin || !any) return false;
   return it >= pb.snap_it1 && (it - pb.snap_it1) % pb.snap_itd == 0;
 }
 inline void PLOT_FIELD(problem_type& pb, int it, const std::string& dir = ".") {
   if (!snapshot_due(pb, it)) return;
   const size_t n = (size_t)pb.npoin;
-  std::vector<double> d(n * pb.ndof), v(n * pb.ndof), a(n * pb.ndof);
-  s2d_check(pb, s2d_get_fields(pb.gpu, d.data(), v.data(), a.data()), "PLOT_FIELD");
+  std::vector<double> d, v, a;
+  if (pb.snap_fields[0]) d.resize(n * pb.ndof);
+  if (pb.snap_fields[1]) v.resize(n * pb.ndof);
+  if (pb.snap_fields[2]) a.resize(n * pb.ndof);
+  s2d_check(pb, s2d_get_fields(pb.gpu, d.empty() ? nullptr : d.data(), v.empty() ? nullptr : v.data(), a.empty() ? nullptr : a.data()),
+            "PLOT_FIELD");
   const std::vector<double>* fld[3] = {&d, &v, &a};
   const char fchar[3] = {'d', 'v', 'a'};
   std::vector<float> buf(n);
@@ -909,6 +912,25 @@ inline void PLOT_FIELD(problem_type& pb, int it, const std::string& dir = ".") {
       std::fclose(f);
     }
   }
+  // element-wise fields (plot_gen.f90:222-305): direct-access files, record e = real(field(:,:,k)) of element e
+  const size_t ne = (size_t)pb.nelem_total, n2 = (size_t)pb.ngll * pb.ngll;
+  const int tagn = (it - pb.snap_it1) / pb.snap_itd;
+  auto dump = [&](char what, const std::vector<std::string>& names) {
+    std::vector<float> out(names.size() * ne * n2);
+    s2d_check(pb, s2d_cart_snapshot_elem(pb.gpu, what, out.data()), "PLOT_FIELD");
+    for (size_t k = 0; k < names.size(); ++k) {
+      char name[64];
+      std::snprintf(name, sizeof(name), "%s_%03d_sem2d.dat", names[k].c_str(), tagn);
+      FILE* f = std::fopen((dir + "/" + name).c_str(), "wb");
+      if (!f) IO_abort(std::string("PLOT_FIELD: cannot open ") + name);
+      std::fwrite(out.data() + k * ne * n2, sizeof(float), ne * n2, f);
+      std::fclose(f);
+    }
+  };
+  if (pb.snap_fields[3]) dump('E', pb.ndof == 1 ? std::vector<std::string>{"e13", "e23"} : std::vector<std::string>{"e11", "e22", "e12"});
+  if (pb.snap_fields[4]) dump('S', pb.ndof == 1 ? std::vector<std::string>{"s13", "s23"} : std::vector<std::string>{"s11", "s22", "s12"});
+  if (pb.snap_fields[5]) dump('d', {"div"});
+  if (pb.snap_fields[6]) dump('c', {"curl"});
 }
 
 // rec%sis as REC_store has filled it up to now

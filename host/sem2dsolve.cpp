@@ -4,6 +4,9 @@
 //
 //   sem2dsolve_b200 [Par.inp] [--precision 4|8] [--device N] [--quiet] [--hash-seed S] [--bench K] [--natural-order]
 //
+// --energies: what a reference build with COMPUTE_ENERGIES = .true. (SRC/constants.f90:22-27) does: every step, one
+// line `time, E_ep, E_k, E_el, E_W` (5D24.16) in energy_sem2d.tab (main.f90:90-93, energy.f90:109-116); E_ep = E_el
+// = 0 for the elastic materials of this path (mat_gen.f90:442-445).  Costs one device synchronisation per step.
 // --natural-order: row-by-row element order (OPT_RENUMBER = .false.) instead of the reference's default reverse
 // Cuthill-McKee order; only the element / node numbering of the grid files and snapshots changes.
 //
@@ -36,6 +39,7 @@ int main(int argc, char** argv) {
     else if (s == "--device" && a + 1 < argc) pb.device = std::atoi(argv[++a]);
     else if (s == "--quiet") quiet = true;
     else if (s == "--natural-order") pb.renumber = false;
+    else if (s == "--energies") pb.compute_energies = true;
     else if (s == "--bench" && a + 1 < argc) bench_steps = std::atoi(argv[++a]);
     else if (s == "--hash-seed" && a + 1 < argc) pb.hash_seed = std::strtoull(argv[++a], nullptr, 10);
     else file = s;
@@ -82,14 +86,22 @@ int main(int argc, char** argv) {
     PLOT_FIELD(pb, 0);
     // main.f90:51-99: the loop body runs on the device in chunks that end on the ItInfo lines and on
     // the snapshot steps
+    FILE* fen = pb.compute_energies ? std::fopen("energy_sem2d.tab", "w") : nullptr;
     while (pb.it < pb.time.nt) {
       int n = std::min(pb.ItInfo - pb.it % pb.ItInfo, pb.time.nt - pb.it);
+      if (fen) n = 1;
       for (int k = 1; k < n; ++k)
         if (snapshot_due(pb, pb.it + k)) {
           n = k;
           break;
         }
       solve(pb, n);
+      if (fen) {  // energy_compute + energy_write (main.f90:90-93)
+        double Ek = 0, Ew = 0;
+        s2d_check(pb, s2d_energy(pb.gpu, &Ek), "energy_compute");
+        s2d_check(pb, s2d_energy_w25d(pb.gpu, &Ew), "energy_compute");
+        std::fprintf(fen, "%24.16E%24.16E%24.16E%24.16E%24.16E\n", pb.time.time, 0.0, Ek, 0.0, Ew);
+      }
       PLOT_FIELD(pb, pb.it);  // main.f90:82
       if (pb.it % pb.ItInfo == 0 && !quiet) {
         double vmax = 0, dmax = 0;
@@ -97,6 +109,7 @@ int main(int argc, char** argv) {
         std::printf("Timestep #%8d  t = %11.4E  vmax = %11.4E  dmax = %11.4E\n", pb.it, pb.time.time, vmax, dmax);
       }
     }
+    if (fen) std::fclose(fen);
     const auto t2 = std::chrono::steady_clock::now();
     if (pb.rec) {  // main.f90:104
       REC_fetch(pb);

@@ -201,6 +201,8 @@ int s2d_get_fault_state(s2d_handle h, int32_t fault_id, double* D, double* V, do
 int s2d_progress(s2d_handle h, double* vmax, double* dmax);
 /* energy.f90:49-106 kinetic energy 0.5*sum(M v.v) (needs s2d_set_mass). */
 int s2d_energy(s2d_handle h, double* E_k);
+/* energy.f90:84-104: E_W = 1/2 sum(beta * d.d), the additional elastic energy of a 2.5D run (0 when W is infinite). */
+int s2d_energy_w25d(s2d_handle h, double* E_W);
 
 /* ---- plan introspection (parity of the colouring) ------------------------------ */
 /* greedy first-fit colours (ascending element id, conflict = shares a GLL node), 0-based, as used
@@ -359,6 +361,13 @@ int s2d_cart_get_window(s2d_handle h, int32_t gx0, int32_t gz0, int32_t nwx, int
 /* get_GLL_info (SRC/gll.f90:19-36) as the builder computed it: xgll(ngll), wgll(ngll), hprime(ngll,ngll) column-major
  * with hprime(i,j) = h'_i(x_j).  Any pointer may be NULL. */
 int s2d_cart_get_gll(s2d_handle h, double* xgll, double* wgll, double* hprime);
+/* PLOT_FIELD's element-wise snapshot fields (SRC/plot_gen.f90:239-300), computed on the device from the resident
+ * fields: what = 'E' strain (e11, e22, e12 | e13, e23; FIELD_strain_elem, fields.f90:192-237), 'S' stress (s11, s22,
+ * s12 | s13, s23; MAT_stress_dv, mat_gen.f90:626-641, with the Kelvin-Voigt d + eta*v; isotropic MAT_ELAST_stress,
+ * mat_elastic.f90:822-839), 'd' divergence and 'c' curl of the velocity (P-SV only; fields.f90:242-285).
+ * out[ncomp][nelem][ngll*ngll] float32 -- one record of ngll*ngll reals per element and component, the layout of
+ * e11_NNN_sem2d.dat etc. -- elements in the caller's order (natural, or RCM with `renumber`). */
+int s2d_cart_snapshot_elem(s2d_handle h, char what, float* out);
 /* copies of builder outputs for parity tests against the oracle (host pointers, may be NULL) */
 int s2d_cart_get(s2d_handle h, int32_t* ibool, double* a, double* rmass, double* coord);
 

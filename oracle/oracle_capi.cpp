@@ -104,6 +104,14 @@ int orc_set_fields(void* hv, const double* d, const double* v, const double* a) 
 }
 
 double orc_energy_Ek(void* hv) { return energy_Ek(((OrcHandle*)hv)->pb); }
+double orc_energy_EW(void* hv) { return energy_EW(((OrcHandle*)hv)->pb); }
+
+// element-wise snapshot fields of PLOT_FIELD: fills the scratch array exposed as "snap"
+int orc_snapshot(void* hv, int what) {
+  OrcHandle* h = (OrcHandle*)hv;
+  snapshot_elem(h->pb, (char)what, h->scratch_f);
+  return 0;
+}
 
 long long orc_get_int(void* hv, const char* name_) {
   OrcHandle* h = (OrcHandle*)hv;
@@ -309,6 +317,7 @@ long long orc_array(void* hv, const char* name_, const void** ptr, char* dtype) 
   if (n == "v") RET_D(pb.v);
   if (n == "acc") RET_D(pb.a_);
   if (n == "fint") RET_D(h->scratch_d);
+  if (n == "snap") RET_F(h->scratch_f);
   if (n == "rec.coord") RET_D(pb.rec.coord);
   if (n == "rec.iglob") RET_I(pb.rec.iglob);
   if (n == "rec.interp") RET_D(pb.rec.interp);

@@ -2310,6 +2310,92 @@ inline double energy_Ek(const Problem& pb) {
   return 0.5 * Ek;
 }
 
+// energy.f90:84-104: E_W = 1/2 sum over elements of sum(beta * d2), the additional elastic energy of a 2.5D run
+inline double energy_EW(const Problem& pb) {
+  if (pb.beta25d.empty()) return 0.0;
+  const Grid& g = pb.grid;
+  int n = g.ngll, n2 = n * n;
+  double EW = 0;
+  for (int e = 1; e <= g.nelem; ++e) {
+    const double* beta = &pb.beta25d[(size_t)n2 * (pb.elem2set[e - 1] - 1)];
+    double s = 0;
+    for (int k = 0; k < n2; ++k) {
+      int ip = g.ibool[(size_t)n2 * (e - 1) + k];
+      double d2 = 0;
+      for (int c = 0; c < pb.ndof; ++c) d2 += pb.d[pb.idx(ip, c)] * pb.d[pb.idx(ip, c)];
+      s += beta[k] * d2;
+    }
+    EW += s;
+  }
+  return 0.5 * EW;
+}
+
+// PLOT_FIELD's element-wise snapshot fields (plot_gen.f90:239-300): 'E' strain (FIELD_strain_elem,
+// fields.f90:192-237), 'S' stress (MAT_stress_dv, mat_gen.f90:626-641: Kelvin-Voigt d + eta*v, then MAT_ELAST_stress,
+// mat_elastic.f90:804-839, isotropic), 'd' / 'c' divergence and curl of the velocity (FIELD_divcurl_elem,
+// fields.f90:242-285).  out[(c*nelem + e-1)*n2 + k] as real (float32), c = 0..ndof for E/S, one component for d/c.
+inline void snapshot_elem(const Problem& pb, char what, std::vector<float>& out) {
+  const Grid& g = pb.grid;
+  const int n = g.ngll, n2 = n * n, ndof = pb.ndof;
+  const int ncomp = (what == 'E' || what == 'S') ? ndof + 1 : 1;
+  out.assign((size_t)ncomp * g.nelem * n2, 0.f);
+  std::vector<double> U((size_t)n2 * ndof), dxi((size_t)n2 * ndof), deta((size_t)n2 * ndof), la(n2), mu(n2);
+  const std::vector<double>& fld = (what == 'd' || what == 'c') ? pb.v : pb.d;
+  for (int e = 1; e <= g.nelem; ++e) {
+    const int* ib = &g.ibool[(size_t)n2 * (e - 1)];
+    for (int c = 0; c < ndof; ++c)
+      for (int k = 0; k < n2; ++k) U[k + (size_t)n2 * c] = fld[pb.idx(ib[k], c)];
+    if (what == 'S' && pb.elem2kv[e - 1] > 0) {
+      const double* eta = &pb.kv_eta[(size_t)n2 * (pb.elem2kv[e - 1] - 1)];
+      for (int c = 0; c < ndof; ++c)
+        for (int k = 0; k < n2; ++k) U[k + (size_t)n2 * c] = U[k + (size_t)n2 * c] + eta[k] * pb.v[pb.idx(ib[k], c)];
+    }
+    for (int c = 0; c < ndof; ++c) {  // mxm(hTprime, U), mxm(U, hprime)
+      mxm(g.Ht.data(), &U[(size_t)n2 * c], &dxi[(size_t)n2 * c], n);
+      mxm(&U[(size_t)n2 * c], g.H.data(), &deta[(size_t)n2 * c], n);
+    }
+    if (what == 'S') {
+      pb.mat.get(pb.mat.lambda, e, la.data());
+      pb.mat.get(pb.mat.mu, e, mu.data());
+    }
+    for (int j = 1; j <= n; ++j)
+      for (int i = 1; i <= n; ++i) {
+        const int k = (i - 1) + n * (j - 1);
+        double jac[4], xi[4];
+        SE_Jacobian(g, e, i, j, jac);
+        invert2(jac, xi);  // xjaci(1,1)=dxi_dx, (1,2)=dxi_dz, (2,1)=deta_dx, (2,2)=deta_dz, column-major
+        const double dxi_dx = xi[0], deta_dx = xi[1], dxi_dz = xi[2], deta_dz = xi[3];
+        double ev[3] = {0, 0, 0};
+        if (what == 'E' || what == 'S') {
+          if (ndof == 1) {
+            ev[0] = 0.5 * (dxi[k] * dxi_dx + deta[k] * deta_dx);
+            ev[1] = 0.5 * (dxi[k] * dxi_dz + deta[k] * deta_dz);
+          } else {
+            ev[0] = dxi[k] * dxi_dx + deta[k] * deta_dx;
+            ev[1] = dxi[k + n2] * dxi_dz + deta[k + n2] * deta_dz;
+            ev[2] = 0.5 * (dxi[k] * dxi_dz + deta[k] * deta_dz + dxi[k + n2] * dxi_dx + deta[k + n2] * deta_dx);
+          }
+          if (what == 'S') {
+            if (ndof == 1) {
+              ev[0] = 2.0 * mu[k] * ev[0];
+              ev[1] = 2.0 * mu[k] * ev[1];
+            } else {
+              const double e1 = ev[0], e2 = ev[1];
+              ev[0] = (la[k] + 2.0 * mu[k]) * e1 + la[k] * e2;
+              ev[1] = la[k] * e1 + (la[k] + 2.0 * mu[k]) * e2;
+              ev[2] = 2.0 * mu[k] * ev[2];
+            }
+          }
+          for (int c = 0; c <= ndof; ++c) out[((size_t)c * g.nelem + (e - 1)) * n2 + k] = (float)ev[c];
+        } else {
+          const double dv = dxi[k] * dxi_dx + deta[k] * deta_dx + dxi[k + n2] * dxi_dz + deta[k + n2] * deta_dz;
+          const double cu = dxi[k] * dxi_dz + deta[k] * deta_dz - dxi[k + n2] * dxi_dx - deta[k + n2] * deta_dx;
+          out[(size_t)(e - 1) * n2 + k] = (float)(what == 'd' ? dv : cu);
+        }
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // main.f90:27-99: init_main (init.f90:16-131) then the time loop
 inline void init_main(Problem& pb, const CartSpec& cart) {

@@ -100,6 +100,7 @@ _SIGS = {
     "s2d_get_fault_state": [C.c_void_p, C.c_int32] + [C.c_void_p] * 7,
     "s2d_progress": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "s2d_energy": [C.c_void_p, C.POINTER(C.c_double)],
+    "s2d_energy_w25d": [C.c_void_p, C.POINTER(C.c_double)],
     "s2d_get_coloring": [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p],
     "s2d_time_fint": [C.c_void_p, C.c_int32, C.POINTER(C.c_float)],
     "s2d_time_steps": [C.c_void_p, C.c_int32, C.POINTER(C.c_float)],
@@ -131,6 +132,7 @@ _SIGS = {
     "s2d_cart_set_w25d": [C.c_void_p, C.c_double],
     "s2d_cart_info": [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)],
     "s2d_cart_set_dt": [C.c_void_p, C.c_double],
+    "s2d_cart_snapshot_elem": [C.c_void_p, C.c_char, C.c_void_p],
     "s2d_cart_get_gll": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "s2d_cart_get": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "s2d_cart_fill_fields": [C.c_void_p, C.c_uint64, C.c_double, C.c_double],

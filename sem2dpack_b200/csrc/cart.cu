@@ -339,6 +339,75 @@ __global__ void k_cart_window(const T* __restrict__ src, double* __restrict__ ou
   out[w] = (double)src[(size_t)(gz0 + z) * LXP + (gx0 + x) + nlat * c];
 }
 
+// PLOT_FIELD's element-wise snapshot fields on the flat box (plot_gen.f90:239-300): strain of d (FIELD_strain_elem,
+// fields.f90:192-237), stress of the Kelvin-Voigt-modified d (MAT_stress_dv, mat_gen.f90:626-641; isotropic
+// MAT_ELAST_stress, mat_elastic.f90:822-839), divergence / curl of v (FIELD_divcurl_elem, fields.f90:242-285).
+// One thread per GLL point of an element; out[(c*nelem + e)*N2 + k] float32, e in the caller's element order.
+struct SnapH {
+  double H[100];
+};
+template <typename T>
+__global__ void k_cart_snap(CartGeom G, SnapH Hm, const T* __restrict__ d, const T* __restrict__ v,
+                            const T* __restrict__ eta_strip, size_t nlat, int what, const int* __restrict__ perm,
+                            float* __restrict__ out) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = G.N, N2 = N * N, ndof = G.ndof;
+  const long long nelem = (long long)G.nx * G.nz;
+  if (w >= nelem * N2) return;
+  const long long e = w / N2;
+  const int k = (int)(w - e * N2), i = k % N, j = k / N;
+  const long long old = perm ? perm[e] : e;
+  const int ix = (int)(old % G.nx), iz = (int)(old / G.nx);
+  const bool of_v = what == 'd' || what == 'c';
+  const T* F = of_v ? v : d;
+  const bool kv = what == 'S' && eta_strip != nullptr;
+  auto val = [&](int c, int ii, int jj) {
+    const size_t q = (size_t)(cart_lat_id(G, ix, iz, ii, jj) - 1) + nlat * c;
+    double u = (double)F[q];
+    if (kv) u = u + (double)eta_strip[strip_scalar_index(G.S, ix, iz, ii, jj)] * (double)v[q];
+    return u;
+  };
+  double dxi[2] = {0, 0}, deta[2] = {0, 0};
+  for (int c = 0; c < ndof; ++c)
+    for (int m = 0; m < N; ++m) {
+      dxi[c] += Hm.H[m + N * i] * val(c, m, j);   // (Ht U)(i,j)
+      deta[c] += val(c, i, m) * Hm.H[m + N * j];  // (U H)(i,j)
+    }
+  const double dxi_dx = 2.0 / G.hx, deta_dz = 2.0 / G.hz;
+  double ev[3] = {0, 0, 0};
+  int ncomp = 1;
+  if (what == 'E' || what == 'S') {
+    ncomp = ndof + 1;
+    if (ndof == 1) {
+      ev[0] = 0.5 * (dxi[0] * dxi_dx);
+      ev[1] = 0.5 * (deta[0] * deta_dz);
+    } else {
+      ev[0] = dxi[0] * dxi_dx;
+      ev[1] = deta[1] * deta_dz;
+      ev[2] = 0.5 * (deta[0] * deta_dz + dxi[1] * dxi_dx);
+    }
+    if (what == 'S') {
+      double rho, cp, cs;
+      cart_material(G, ix, iz, i, j, rho, cp, cs);
+      const double la = rho * (cp * cp - 2.0 * cs * cs), mu = rho * cs * cs;
+      if (ndof == 1) {
+        ev[0] = 2.0 * mu * ev[0];
+        ev[1] = 2.0 * mu * ev[1];
+      } else {
+        const double e1 = ev[0], e2 = ev[1];
+        ev[0] = (la + 2.0 * mu) * e1 + la * e2;
+        ev[1] = la * e1 + (la + 2.0 * mu) * e2;
+        ev[2] = 2.0 * mu * ev[2];
+      }
+    }
+  } else if (what == 'd') {
+    ev[0] = dxi[0] * dxi_dx + deta[1] * deta_dz;
+  } else {
+    ev[0] = deta[0] * deta_dz - dxi[1] * dxi_dx;
+  }
+  for (int c = 0; c < ncomp; ++c) out[((size_t)c * nelem + e) * N2 + k] = (float)ev[c];
+}
+
 // ibool in the reference layout (ngll,ngll,nelem), natural element order
 __global__ void k_cart_ibool(CartGeom G, int* __restrict__ ibool) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1454,6 +1523,35 @@ static void cart_window(Engine<T>& E, const CartGeom& G, int gx0, int gz0, int n
     S2D_CUDA(cudaStreamSynchronize(E.stream));
     tmp.download(dst[k]);
   }
+}
+template <typename T>
+static void cart_snapshot(Engine<T>& E, CartState& S, char what, float* out) {
+  const CartGeom G = S.dev_geom();
+  const int N2 = G.N * G.N, ncomp = (what == 'E' || what == 'S') ? G.ndof + 1 : 1;
+  const size_t n = (size_t)ncomp * E.nelem * N2;
+  DevBuf<float> buf;
+  buf.alloc(n);
+  DevBuf<int> dperm;
+  if (S.renumber) dperm.upload(S.perm);
+  SnapH Hm;
+  std::memcpy(Hm.H, S.H, sizeof(Hm.H));
+  const long long tot = (long long)E.nelem * N2;
+  S2D_CUDA(cudaStreamSynchronize(E.stream));
+  k_cart_snap<T><<<(unsigned)((tot + 127) / 128), 128, 0, E.stream>>>(G, Hm, E.dbuf().p, E.v.p, E.strip_eta.n ? E.strip_eta.p : nullptr,
+                                                                       E.npoin, (int)what, S.renumber ? dperm.p : nullptr, buf.p);
+  S2D_CUDA(cudaGetLastError());
+  S2D_CUDA(cudaStreamSynchronize(E.stream));
+  buf.download(out);
+}
+extern "C" int s2d_cart_snapshot_elem(s2d_handle h, char what, float* out) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(out != nullptr, "cart_snapshot_elem: null pointer");
+  S2D_REQUIRE(what == 'E' || what == 'S' || what == 'd' || what == 'c', "cart_snapshot_elem: field must be E, S, d or c");
+  S2D_REQUIRE(!((what == 'd' || what == 'c') && S.G.ndof != 2), "mat_gen:MAT_divcurl_gen: only for P-SV");
+  S2D_REQUIRE(Eb->committed, "cart_snapshot_elem before commit");
+  if (Eb->prec == 8) cart_snapshot<double>(*as_engine<double>(Eb), S, what, out);
+  else cart_snapshot<float>(*as_engine<float>(Eb), S, what, out);
+  CART_GUARD_END
 }
 extern "C" {
 int s2d_cart_get_window(s2d_handle h, int32_t gx0, int32_t gz0, int32_t nwx, int32_t nwz, double* d, double* v, double* a) {

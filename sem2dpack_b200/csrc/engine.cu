@@ -233,6 +233,12 @@ int s2d_energy(s2d_handle h, double* E_k) {
     *E_k = E.energy();
   });
 }
+int s2d_energy_w25d(s2d_handle h, double* E_W) {
+  return guard(h, [&](EngineBase& E) {
+    S2D_REQUIRE(E_W, "s2d_energy_w25d: null pointer");
+    *E_W = E.energy_w25d();
+  });
+}
 int s2d_get_coloring(s2d_handle h, int32_t* ncolors, int32_t* color) {
   return guard(h, [&](EngineBase& E) { E.get_coloring(ncolors, color); });
 }

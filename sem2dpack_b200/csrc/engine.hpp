@@ -101,6 +101,7 @@ class EngineBase {
                                double* theta, double* sigma) = 0;
   virtual void progress(double* vmax, double* dmax) = 0;
   virtual double energy() = 0;
+  virtual double energy_w25d() = 0;
   virtual void get_coloring(int32_t* ncolors, int32_t* color) = 0;
   virtual float time_fint(int reps) = 0;
   virtual float time_steps(int nsteps) = 0;
@@ -1813,6 +1814,22 @@ class Engine : public EngineBase {
     S2D_REQUIRE(mass.n == npoin, "energy: s2d_set_mass was not called");
     const int g = std::min<int>(1024, grid_for(npoin));
     k_kinetic<T><<<g, 256, 0, stream>>>(v.p, mass.p, npoin, ndof, partial.p);
+    launches++;
+    std::vector<double> h(g);
+    S2D_CUDA(cudaMemcpyAsync(h.data(), partial.p, g * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    double s = 0;
+    for (double x_ : h) s += x_;
+    return 0.5 * s;
+  }
+  // E_W = 1/2 sum(beta * d.d) (energy.f90:84-104), the elastic energy of the 2.5D term; 0 when W is infinite
+  double energy_w25d() override {
+    if (!strip_beta.n) {
+      S2D_REQUIRE(h_beta.empty(), "energy_w25d: available on the strip-kernel route (structured boxes)");
+      return 0.0;
+    }
+    const int g = 512;
+    k_strip_energy_w<T><<<g, 256, 0, stream>>>(cart_S, strip_beta.p, dbuf().p, npoin, partial.p);
     launches++;
     std::vector<double> h(g);
     S2D_CUDA(cudaMemcpyAsync(h.data(), partial.p, g * sizeof(double), cudaMemcpyDeviceToHost, stream));

@@ -1082,6 +1082,32 @@ __global__ void k_strip_eta_from_nodes(StripGeom G, const T* __restrict__ eta_no
   eta_strip[strip_scalar_index(G, ix, iz, i, j)] = eta_node[(size_t)strip_lat_row(G, iz, j) * G.LXP + (size_t)ix * (N - 1) + i];
 }
 
+// E_W of energy_compute (energy.f90:84-104): sum over the elements of beta * |d|^2 (2.5D term), per-CTA partial sums
+template <typename T>
+__global__ void __launch_bounds__(256) k_strip_energy_w(StripGeom G, const T* __restrict__ beta, const T* __restrict__ d,
+                                                        size_t nlat, double* __restrict__ partial) {
+  __shared__ double red[256];
+  const int N = G.N, N2 = N * N;
+  const long long total = (long long)G.nx * G.nz * N2;
+  double acc = 0.0;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+    const long long e = w / N2;
+    const int k = (int)(w - e * N2), i = k % N, j = k / N;
+    const int ix = (int)(e % G.nx), iz = (int)(e / G.nx);
+    const size_t q = (size_t)strip_lat_row(G, iz, j) * G.LXP + (size_t)ix * (N - 1) + i;
+    double d2 = 0.0;
+    for (int c = 0; c < G.ndof; ++c) d2 += (double)d[q + nlat * c] * (double)d[q + nlat * c];
+    acc += (double)beta[strip_scalar_index(G, ix, iz, i, j)] * d2;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) {
+    if ((int)threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
 // everything a strip launch needs besides the geometry
 template <typename T>
 struct StripIO {

@@ -234,6 +234,11 @@ class Engine:
         self._ck(self.L.s2d_energy(self.h, C.byref(e)))
         return e.value
 
+    def energy_w25d(self):
+        e = C.c_double()
+        self._ck(self.L.s2d_energy_w25d(self.h, C.byref(e)))
+        return e.value
+
     def coloring(self):
         nc = C.c_int32()
         col = np.empty(self.nelem, np.int32)
@@ -373,6 +378,13 @@ class CartEngine(Engine):
         aa = np.empty(shp) if a else None
         self._ck(self.L.s2d_cart_get_window(self.h, gx0, gz0, nwx, nwz, _ptr(d), _ptr(v), _ptr(aa)))
         return (d, v, aa) if a else (d, v)
+
+    def snapshot_elem(self, what):
+        """PLOT_FIELD's element-wise field 'E' | 'S' | 'd' | 'c': float32 (ncomp, nelem, ngll, ngll)"""
+        ncomp = self.ndof + 1 if what in "ES" else 1
+        out = np.empty((ncomp, self.nelem, self.ngll, self.ngll), np.float32)
+        self._ck(self.L.s2d_cart_snapshot_elem(self.h, what.encode()[:1], _ptr(out)))
+        return out
 
     def get_gll(self):
         """(xgll, wgll, hprime[column-major flat]) of the builder (s2d_cart_get_gll)"""

@@ -41,6 +41,9 @@ def lib(variant="parity"):
         L.orc_time_solve.argtypes = [C.c_void_p, C.c_int]
         L.orc_compute_fint.argtypes = [C.c_void_p]
         L.orc_set_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_snapshot.argtypes = [C.c_void_p, C.c_int]
+        L.orc_energy_EW.restype = C.c_double
+        L.orc_energy_EW.argtypes = [C.c_void_p]
         L.orc_energy_Ek.restype = C.c_double
         L.orc_energy_Ek.argtypes = [C.c_void_p]
         L.orc_get_int.restype = C.c_longlong
@@ -128,6 +131,12 @@ class Oracle:
     def compute_fint(self):
         self.L.orc_compute_fint(self.h)
         return self.arr("fint")
+
+    def snapshot(self, what):
+        """PLOT_FIELD's element-wise field 'E' | 'S' | 'd' | 'c': float32 (ncomp, nelem, ngll, ngll)"""
+        self.L.orc_snapshot(self.h, ord(what))
+        n = self.i("ngll")
+        return self.arr("snap").reshape(-1, self.i("nelem"), n, n)
 
     def set_fields(self, d=None, v=None, a=None):
         def p(x):

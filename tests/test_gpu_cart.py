@@ -300,3 +300,24 @@ def test_rcm_order_ibool_bit_exact_and_fields_in_that_numbering(ngll, nx, nz, ez
     assert rel_l2(d, o.arr("d")) <= 1e-10 and rel_l2(v, o.arr("v")) <= 1e-10
     e.close()
     o.close()
+
+
+@pytest.mark.parametrize("ndof", [1, 2])
+def test_snapshot_elem_fields(ndof):
+    """s2d_cart_snapshot_elem on random fields, heterogeneous medium, natural element order, split-node row"""
+    nx, nz, ez = 13, 9, 4
+    o = orc.Oracle(harness.cart_deck(nx, nz, ndof=ndof, ezflt=ez, nrec=0, src=False, abso=(), fault=None), synthetic_seed=SEED,
+                   renumber=False)
+    e = CartEngine(5, ndof, nx, nz, (0.0, nx * 100.0), (0.0, nz * 100.0), ezflt=ez, seed=SEED)
+    e.commit()
+    rng = np.random.default_rng(4)
+    n = e.npoin * ndof
+    d0, v0 = rng.standard_normal(n), rng.standard_normal(n)
+    e.set_fields(d0, v0)
+    o.set_fields(d0, v0)
+    for what in ("E", "S") + (("d", "c") if ndof == 2 else ()):
+        got, ref = e.snapshot_elem(what), o.snapshot(what)
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max(), what
+    e.close()
+    o.close()

@@ -309,3 +309,47 @@ def test_user_and_tabulated_source_time_functions(tmp_path, kind):
     assert np.abs(ref).max() > 0
     assert np.abs(u - ref).max() <= 1e-6 * np.abs(ref).max()
     r.close()
+
+
+def test_strain_stress_divcurl_snapshots(tmp_path):
+    """&SNAP_DEF fields='ESdc' (plot_gen.f90:222-305): e11/e22/e12, s11/s22/s12, div, curl -- one record of
+    ngll*ngll reals per element, RCM element order -- computed on the device (s2d_cart_snapshot_elem) against the
+    oracle's restatement of FIELD_strain_elem / MAT_stress_dv / FIELD_divcurl_elem; the TPV3 deck so that the stress
+    carries the Kelvin-Voigt d + eta*v"""
+    deck = harness.deck("tpv3").replace("TotalTime=16.d0", "NbSteps=300")
+    deck = deck.replace("&SNAP_DEF itd=200, fields ='V',bin=F,ps=T /", "&SNAP_DEF itd=300, fields='ESdc', bin=T, ps=F /")
+    assert "fields='ESdc'" in deck
+    p = run(tmp_path, deck, "--quiet")
+    assert p.returncode == 0, p.stdout + p.stderr
+    o = orc.Oracle(deck, renumber=True)
+    o.step(300)
+    ne, n2 = o.i("nelem"), o.i("ngll") ** 2
+    for what, names in (("E", ("e11", "e22", "e12")), ("S", ("s11", "s22", "s12")), ("d", ("div",)), ("c", ("curl",))):
+        ref = o.snapshot(what).reshape(len(names), ne * n2)
+        for k, nm in enumerate(names):
+            got = np.fromfile(tmp_path / f"{nm}_001_sem2d.dat", dtype=np.float32)
+            assert got.shape == (ne * n2,)
+            assert np.abs(ref[k]).max() > 0
+            assert np.abs(got - ref[k]).max() <= 2e-6 * np.abs(ref[k]).max(), nm
+    o.close()
+
+
+def test_energy_table(tmp_path):
+    """--energies = a reference build with COMPUTE_ENERGIES (constants.f90:22-27): energy_sem2d.tab, one line
+    `time, E_ep, E_k, E_el, E_W` per step (main.f90:90-93, energy.f90:49-116); 2.5D deck so that E_W is non-zero"""
+    nsteps = 60
+    deck = harness.deck("inplane25d").replace("TotalTime=30", f"NbSteps={nsteps}")
+    p = run(tmp_path, deck, "--quiet", "--energies")
+    assert p.returncode == 0, p.stdout + p.stderr
+    tab = np.loadtxt(tmp_path / "energy_sem2d.tab")
+    assert tab.shape == (nsteps, 5)
+    o = orc.Oracle(deck)
+    for k in range(nsteps):
+        o.step(1)
+        ek, ew = o.L.orc_energy_Ek(o.h), o.L.orc_energy_EW(o.h)
+        assert abs(tab[k, 0] - (k + 1) * o.f("dt")) <= 1e-12 * tab[k, 0]
+        assert tab[k, 1] == 0.0 and tab[k, 3] == 0.0
+        assert abs(tab[k, 2] - ek) <= 1e-9 * max(ek, 1e-300), (k, tab[k, 2], ek)
+        assert abs(tab[k, 4] - ew) <= 1e-9 * max(ew, 1e-300), (k, tab[k, 4], ew)
+    assert tab[-1, 2] > 0 and tab[-1, 4] > 0
+    o.close()
