@@ -25,12 +25,19 @@ module sem2d_b200
       real(c_double), intent(in) :: hprime(*), rmass(*) ! grid%hprime, pb%rmass(npoin,ndof)
       type(s2d_scheme), intent(in) :: scheme
     end function
-    integer(c_int) function s2d_set_elastic(h, nelast, ncoefsets, a, elem2set, kd2) bind(C, name='s2d_set_elastic')
+    integer(c_int) function s2d_set_elastic(h, nelast, ncoefsets, a, elem2set, beta25d, kd2) bind(C, name='s2d_set_elastic')
       import
       type(c_ptr), value :: h
       integer(c_int32_t), value :: nelast, ncoefsets, kd2
       real(c_double), intent(in) :: a(*)                ! a(ngll,ngll,nelast) blocks   mat_elastic.f90:290-360
-      integer(c_int32_t), intent(in) :: elem2set(*)
+      integer(c_int32_t), intent(in) :: elem2set(*)     ! 1-based block of each element
+      type(c_ptr), value :: beta25d                     ! c_loc(beta(ngll,ngll,ncoefsets)) when grid%W is finite
+                                                        ! (mat_elastic.f90:280-284,363-383), else c_null_ptr
+    end function
+    integer(c_int) function s2d_kernel_route(h, route) bind(C, name='s2d_kernel_route')
+      import
+      type(c_ptr), value :: h
+      integer(c_int32_t), intent(out) :: route          ! 1: the box was recognised in ibool, strip kernel; 0: any-mesh kernel
     end function
     integer(c_int) function s2d_set_kv(h, nkv, elem_ids, eta) bind(C, name='s2d_set_kv')
       import

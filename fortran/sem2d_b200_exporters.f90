@@ -19,7 +19,7 @@
     type(matwrk_elem_type), intent(in), target :: matwrk(:)
     type(sem_grid_type), intent(in) :: grid
     double precision, pointer :: a(:,:,:), eta(:,:)
-    double precision, allocatable, target :: abuf(:,:,:,:), etabuf(:,:,:)
+    double precision, allocatable, target :: abuf(:,:,:,:), etabuf(:,:,:), betabuf(:,:,:)
     integer(c_int32_t), allocatable, target :: elem2set(:), kv_elem(:)
     integer :: e, nelast, nsets, nkv, ngll
 
@@ -31,8 +31,8 @@
       if (e > 1 .and. associated(matwrk(e)%elast, matwrk(1)%elast)) then
         elem2set(e) = elem2set(1)
       else
-        elem2set(e) = nsets          ! 0-based set index
         nsets = nsets + 1
+        elem2set(e) = nsets          ! 1-based block index
       endif
     enddo
     call MAT_ELAST_export_a(matwrk(1)%elast, a)
@@ -40,9 +40,17 @@
     allocate(abuf(ngll, ngll, nelast, nsets))
     do e = 1, grid%nelem
       call MAT_ELAST_export_a(matwrk(e)%elast, a)
-      abuf(:,:,:,elem2set(e)+1) = a
+      abuf(:,:,:,elem2set(e)) = a
     enddo
-    call s2d_check(h, s2d_set_elastic(h, nelast, nsets, abuf, elem2set, merge(1, 0, ngll == OPT_NGLL)))
+    if (grid%W < huge(1d0)) then     ! 2.5D: matwrk%elast%beta (mat_elastic.f90:280-284), one block per coefficient set
+      allocate(betabuf(ngll, ngll, nsets))
+      do e = 1, grid%nelem
+        call MAT_ELAST_get_beta(matwrk(e)%elast, betabuf(:,:,elem2set(e)))
+      enddo
+      call s2d_check(h, s2d_set_elastic(h, nelast, nsets, abuf, elem2set, c_loc(betabuf), merge(1, 0, ngll == OPT_NGLL)))
+    else
+      call s2d_check(h, s2d_set_elastic(h, nelast, nsets, abuf, elem2set, c_null_ptr, merge(1, 0, ngll == OPT_NGLL)))
+    endif
 
     nkv = count( (/ (associated(matwrk(e)%kv), e = 1, grid%nelem) /) )
     if (nkv > 0) then

@@ -227,6 +227,10 @@ class Engine : public EngineBase {
   int store_accel = env_int("S2D_STORE_ACCEL", 2);
   int strip_prefetch = env_int("S2D_STRIP_PF", 1);
   int strip_occ = env_int("S2D_STRIP_OCC", 0);
+  // tensor-map staging of the compact fused leapfrog kernel (S2D_STRIP_TENSOR=0 in the environment: per-lane copies)
+  int strip_tensor = env_int("S2D_STRIP_TENSOR", S2D_STRIP_TENSOR);
+  bool tm_ready = false;
+  CUtensorMap tm_d[2], tm_v, tm_r, tm_a;   // d[n] is in either displacement buffer
   std::vector<uint8_t> h_rowflag, h_colflag;
   std::vector<std::vector<int32_t>> h_bc_nodes;  // node lists of every boundary condition (for the flags)
   DevBuf<uint8_t> rowflag, colflag;
@@ -1123,6 +1127,25 @@ class Engine : public EngineBase {
     if (ndcols) dcols.upload(cols);
     d2.alloc(npoin * ndof);
     d2.zero();
+    tm_ready = false;
+    // measured on B200 (4096^2 FP64, ms per launch, per-lane copies -> boxes): compact leapfrog 5.96 -> 5.74, compact
+    // Newmark 7.32 -> 6.81, six stored planes 7.39 -> 7.43 (its coefficient block already comes by TMA): not there
+    if (strip_tensor && ngll <= 6 && (cart_compact || ndof == 1)) {
+      const int bw = strip_box_width(ngll, (int)sizeof(T));
+      // the TENS variant keeps its CTAs per SM only while the shared memory fits (static part: tile, hand-over, masks)
+      const int fusedk = scheme.kind == 1 ? 2 : 1;
+      const size_t smem = strip_tens_smem(ngll, ndof, (int)sizeof(T), cart_compact != 0, fusedk) +
+                          (size_t)strip_warps() * ndof * ngll * (32 / ngll) * ngll * sizeof(T) + 2048;
+      if (smem * strip_min_ctas(ngll, (int)sizeof(T)) <= 227 * 1024) {
+        const StripGeom& S = cart_S;
+        tm_d[0] = lattice_tmap(d.p, (int)sizeof(T), S.LXP, S.LZ, ndof, npoin, bw, ngll - 1);
+        tm_d[1] = lattice_tmap(d2.p, (int)sizeof(T), S.LXP, S.LZ, ndof, npoin, bw, ngll - 1);
+        tm_v = lattice_tmap(v.p, (int)sizeof(T), S.LXP, S.LZ, ndof, npoin, bw, ngll - 1);
+        tm_a = lattice_tmap(a.p, (int)sizeof(T), S.LXP, S.LZ, ndof, npoin, bw, ngll - 1);
+        tm_r = lattice_tmap(rmass.p, (int)sizeof(T), S.LXP, S.LZ, 0, npoin, bw, ngll - 1);
+        tm_ready = true;
+      }
+    }
   }
   void build_color_plan() {
     const int n2 = ngll * ngll;
@@ -1549,6 +1572,12 @@ class Engine : public EngineBase {
     io.c2 = c2;
     io.c3 = c3;
     io.a_in = a.p;
+    if (tm_ready) {  // d[n] lives in the buffer the caller does not see at this point
+      io.tm_d = &tm_d[dc == d.p ? 0 : 1];
+      io.tm_v = &tm_v;
+      io.tm_r = &tm_r;
+      io.tm_a = &tm_a;
+    }
     launch_strips(io, ctl.p);  // ... and the step counter (k_strip_fold)
     phase(PH_SRC);
     if (!node_ops_ready) launch_sources(a.p);

@@ -35,6 +35,7 @@
 #pragma once
 #include "common.cuh"
 #include "elem_kernels.cuh"
+#include "tensor_map.hpp"
 
 // strips (warps) per CTA of the strip kernel; 4 is the measured best (see strip_warps())
 #ifndef S2D_STRIP_WARPS
@@ -154,13 +155,21 @@ __host__ __device__ inline int strip_seg_of(const StripGeom& G, int ez) {
 __host__ __device__ inline int strip_lat_row(const StripGeom& G, int ez, int j) {
   return ez * (G.N - 1) + j + ((G.ezflt > 0 && ez >= G.ezflt) ? 1 : 0);
 }
-// first element (in units of elements) of the coefficient block of element row ez of (seg, strip)
+// element columns [gex0, gex0 + gcx) of the group (CTA) that holds `strip`
+__host__ __device__ inline void strip_group_cols(const StripGeom& G, int strip, int& gex0, int& gcx) {
+  int gfirst, gcount;
+  strip_group(G, strip_group_of(G, strip), gfirst, gcount);
+  gex0 = gfirst * G.EPW;
+  gcx = min((gfirst + gcount) * G.EPW, G.nx) - gex0;
+}
+// first element (in units of elements) of the coefficient block of element row ez of (seg, strip).  Per band the
+// groups follow one another, per group the element rows, per row the strips of the group: the blocks one CTA needs
+// for one element row are ONE contiguous run (one bulk copy), each strip's block inside it is contiguous too.
 __host__ __device__ inline long long strip_elem_off(const StripGeom& G, int seg, int strip, int ez) {
-  int ez0, ez1;
+  int ez0, ez1, gex0, gcx;
   strip_seg_rows(G, seg, ez0, ez1);
-  const int ex0 = strip * G.EPW;
-  const int cx = min(G.EPW, G.nx - ex0);
-  return (long long)ez0 * G.nx + (long long)ex0 * (ez1 - ez0) + (long long)(ez - ez0) * cx;
+  strip_group_cols(G, strip, gex0, gcx);
+  return (long long)ez0 * G.nx + (long long)gex0 * (ez1 - ez0) + (long long)(ez - ez0) * gcx + (strip * G.EPW - gex0);
 }
 // position (in scalars) of a(i,j,plane) of element (ix,iz) inside the strip layout
 __host__ __device__ inline size_t strip_coef_index(const StripGeom& G, int nelast, int ix, int iz, int i, int j,
@@ -196,6 +205,12 @@ template <> struct Vec2<float> { using type = float2; };
 
 template <typename T, int N>
 struct StripArgs {
+  // TMA tensor maps of the lattice fields (TENS variant of the kernel): d[n] (LXP, LZ, ndof), v likewise, rmass
+  // (LXP, LZ); boxes of strip_box_width() columns x (N-1) rows (x ndof)
+  alignas(64) CUtensorMap tm_d;
+  alignas(64) CUtensorMap tm_v;
+  alignas(64) CUtensorMap tm_r;
+  alignas(64) CUtensorMap tm_a;   // a[n-1] (explicit Newmark)
   StripGeom G;
   const T* coef;
   const T* d;
@@ -249,7 +264,10 @@ __device__ __forceinline__ void l2_prefetch_line(const void* p) {
 template <int BYTES>
 __device__ __forceinline__ void stage_copy(void* smem, const void* g) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  if constexpr (BYTES == 16)
+#ifndef S2D_STAGE16_CA
+#define S2D_STAGE16_CA 0
+#endif
+  if constexpr (BYTES == 16 && !S2D_STAGE16_CA)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
   else
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sa), "l"(g), "n"(BYTES) : "memory");
@@ -302,13 +320,82 @@ constexpr size_t strip_stage_bytes(int N, int NDOF, int tsize, int fused, bool c
   const size_t c = (npl / 2) * N * 32 * (2 * tsize), u = (size_t)NDOF * (N - 1) * 32 * tsize, r = (size_t)(N - 1) * 32 * tsize;
   return c + u + (fused ? u + r : 0) + (fused == 2 ? u : 0);
 }
+// TENS variant (S2D_STRIP_TENSOR): the displacement rows, velocities and inverse masses of an element row arrive
+// CTA-wide by THREE tensor-map TMA copies (cp.async.bulk.tensor, SASS UTMALDG) instead of 20 per-lane LDGSTS per
+// warp: a box of strip_box_width() lattice columns (the GW strips of the group + the shared column, rounded up to
+// a 16-byte multiple) by N-1 rows by ndof components.  Two stages; only the coefficient vectors keep the per-lane
+// copies (their block is per strip).
+#ifndef S2D_STRIP_TENSOR
+#define S2D_STRIP_TENSOR 1
+#endif
+// 1: the coefficient blocks of the group's strips (one contiguous run per element row, 9.6 kB in the compact mode)
+// also arrive CTA-wide, by one bulk copy on the displacement box's mbarrier.  Measured on B200, 4096^2 FP64 compact
+// fused, ms per launch: per-lane LDGSTS everywhere 5.84-5.94, boxes for d / v / rmass + per-lane coefficients 5.70-5.75,
+// boxes + CTA-wide coefficient copy 6.18 -- so 0 is the default.
+#ifndef S2D_STRIP_TENSOR_COEF
+#define S2D_STRIP_TENSOR_COEF 0
+#endif
+constexpr int strip_box_width(int N, int tsize) {
+  const int w = strip_warps() * (32 / N) * (N - 1) + 1, q = 16 / tsize;
+  return (w + q - 1) / q * q;
+}
+constexpr size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
+constexpr size_t strip_tens_a_bytes(int N, int NDOF, int tsize) { return align128((size_t)NDOF * (N - 1) * strip_box_width(N, tsize) * tsize); }
+constexpr size_t strip_tens_r_bytes(int N, int tsize) { return align128((size_t)(N - 1) * strip_box_width(N, tsize) * tsize); }
+constexpr size_t strip_tens_c_bytes(int N, int NDOF, int tsize, bool compact) {  // the group's coefficient blocks of one row
+  const size_t npl = compact ? 2 : (NDOF == 1 ? 2 : 6);
+  return S2D_STRIP_TENSOR_COEF ? align128((size_t)strip_warps() * (32 / N) * (npl / 2) * N * N * (2 * tsize)) : 0;
+}
+// dynamic shared memory of the TENS variant: [per-warp coefficient staging unless they come CTA-wide], then
+// 2 x (d box | v box | rmass box [| coefficient blocks of the group])
+constexpr size_t strip_tens_smem(int N, int NDOF, int tsize, bool compact, int fused = 1) {
+  const size_t npl = compact ? 2 : (NDOF == 1 ? 2 : 6);
+  const size_t c = S2D_STRIP_TENSOR_COEF ? 0 : align128((size_t)strip_warps() * (npl / 2) * N * 32 * (2 * tsize));
+  return c + 2 * ((fused == 2 ? 3 : 2) * strip_tens_a_bytes(N, NDOF, tsize) + strip_tens_r_bytes(N, tsize) +
+                  strip_tens_c_bytes(N, NDOF, tsize, compact));
+}
+// cp.async.bulk.tensor global -> shared (tile mode), completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int x, int y, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// mbarrier wait that gives up (trap -> launch failure reported to the host) instead of spinning for ever if a copy
+// never lands, e.g. a malformed tensor map: a hung GPU is worse than a failed call
+__device__ __forceinline__ void mbar_wait_or_trap(unsigned long long* bar, unsigned parity) {
+#ifndef S2D_MBAR_HINT_NS
+#define S2D_MBAR_HINT_NS 20000
+#endif
+  unsigned ok;
+  for (unsigned spins = 0;; ++spins) {
+    // the suspend-time hint lets the warp sleep in hardware until the phase completes instead of polling
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.b32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((unsigned)S2D_MBAR_HINT_NS)
+        : "memory");
+    if (ok) return;
+    if (spins > (1u << 22)) __trap();
+  }
+}
+
 constexpr int strip_min_ctas(int N, int tsize, bool compact = false) {
   return (N <= 6 ? (tsize == 4 ? 4 : 3) : (tsize == 4 ? 2 : 1)) * 4 / strip_warps();
 }
 
-template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false>
+template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false,
+          bool TENS = false>
 __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     k_elem_strip(const __grid_constant__ StripArgs<T, N> A) {
+  static_assert(!TENS || (FUSED >= 1 && !KV), "tensor-map staging: fused leapfrog / explicit Newmark step");
   static_assert(!COMPACT || NDOF == 2, "compact coefficients: P-SV only");
   static_assert(!KV || FUSED == 0, "Kelvin-Voigt elements: plain force evaluation (the node update runs in its own passes)");
   constexpr int WARPS = strip_warps();
@@ -322,13 +409,23 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   __shared__ __align__(16) T tile[WARPS][NDOF][N][EPW * NP];
   __shared__ T hand[2][WARPS][NDOF][N];  // right-edge column of a strip, handed to the strip on its right
   __shared__ unsigned rowmask[STRIP_MASK_WORDS + 1];  // bit r: lattice row (band's first row + r) is deferred
-  extern __shared__ __align__(16) unsigned char stage_raw[];
+  extern __shared__ __align__(128) unsigned char stage_raw[];
   constexpr int NU = NDOF * (N - 1);
   constexpr size_t SZ_C = (size_t)(NPL / 2) * N * 32 * sizeof(V2), SZ_U = (size_t)NU * 32 * sizeof(T);
   const StripGeom& G = A.G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // every lane only ever touches its own slots of the staging area: no barrier guards it
-  unsigned char* wstage = stage_raw + (size_t)warp * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT);
+  unsigned char* wstage = stage_raw + (size_t)warp * (TENS ? SZ_C : strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT));
+  // TENS: CTA-wide boxes behind the per-warp coefficient staging: stage s at tbase + s * TSZ =
+  // [d box | v box | (Newmark: a box) | rmass box | (coefficient blocks)]
+  constexpr int BW = strip_box_width(N, sizeof(T));
+  constexpr size_t TSZ_A = strip_tens_a_bytes(N, NDOF, sizeof(T)), TSZ_R = strip_tens_r_bytes(N, sizeof(T));
+  constexpr size_t TSZ_C = strip_tens_c_bytes(N, NDOF, sizeof(T), COMPACT);
+  constexpr size_t TOFF_R = (FUSED == 2 ? 3 : 2) * TSZ_A;   // rmass box behind d, v (, a)
+  constexpr size_t TSZ = TOFF_R + TSZ_R + TSZ_C;
+  constexpr bool TCOEF = TENS && S2D_STRIP_TENSOR_COEF != 0;
+  unsigned char* tbase = stage_raw + (TCOEF ? 0 : align128((size_t)WARPS * SZ_C));
+  __shared__ __align__(8) unsigned long long tbarA[2], tbarB[2];
   V2* st_c = reinterpret_cast<V2*>(wstage) + lane;             // [plane pair * N + j][32]
   T* st_u = reinterpret_cast<T*>(wstage + SZ_C) + lane;        // [c * (N-1) + j-1][32]
   T* st_v = reinterpret_cast<T*>(wstage + SZ_C + SZ_U) + lane; // [c * (N-1) + j][32]   (fused)
@@ -433,7 +530,10 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   const int cxN = cx * N;
   const V2* cp = reinterpret_cast<const V2*>(A.coef) +
                  (size_t)strip_elem_off(G, seg, strip, ez0) * (NPL * N * N / 2) + lanep;
-  const size_t cp_row = (size_t)cx * (NPL * N * N / 2);
+  int gex0, gcx;
+  strip_group_cols(G, strip, gex0, gcx);
+  const size_t cp_blk = (size_t)cx * (NPL * N * N / 2);    // this strip's block of one element row
+  const size_t cp_row = (size_t)gcx * (NPL * N * N / 2);   // from one element row to the next (the group's blocks)
   T nW[COMPACT ? N : 1];  // -weights(i,j) of this lane's column
   if (COMPACT) {
 #pragma unroll
@@ -448,17 +548,18 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   constexpr bool stg_u = S2D_STRIP_STAGE & 1, stg_c = S2D_STRIP_STAGE & 2, stg_v = S2D_STRIP_STAGE & 4;
   auto issue_row = [&](int ezr, const V2* cpr) {
     const size_t rb = (size_t)strip_lat_row(G, ezr, 0) * LX;
-    if (stg_u && !(S2D_ABLATE & 4)) {
+    if (stg_u && !TENS && !(S2D_ABLATE & 4)) {
 #pragma unroll
       for (int c = 0; c < NDOF; ++c)
 #pragma unroll
         for (int j = 1; j < N; ++j)
           stage_copy<sizeof(T)>(st_u + (c * (N - 1) + j - 1) * 32, up + A.npoin * c + rb + (size_t)j * LX);
     }
-    if (S2D_ABLATE & 2) {
+    (void)rb;
+    if (TCOEF || (S2D_ABLATE & 2)) {
     } else if (tma_c) {
       if (lane == 0) {
-        const unsigned bytes = (unsigned)(cp_row * sizeof(V2));
+        const unsigned bytes = (unsigned)(cp_blk * sizeof(V2));
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the warp's reads of the block come first
         mbar_expect_tx(&cbar[warp], bytes);
         bulk_g2s(st_cb, cpr - lanep, bytes, &cbar[warp]);
@@ -471,13 +572,51 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           stage_copy<sizeof(V2)>(st_c + (pp * N + j) * 32, cpr + (size_t)(pp * N + j) * cxN);
     } else if (A.prefetch) {  // pull the row's coefficient block into L2
       const char* nb = reinterpret_cast<const char*>(cpr - lanep);
-      const int nlines = (int)((cp_row * sizeof(V2) + 127) / 128);
+      const int nlines = (int)((cp_blk * sizeof(V2) + 127) / 128);
       for (int l = lane; l < nlines; l += 32) l2_prefetch_line(nb + (size_t)l * 128);
     }
   };
   if (tma_c && wact) {
     if (lane == 0) mbar_init(&cbar[warp], 1);
     __syncwarp();
+  }
+  // TENS: box origin of this group and the two issue helpers (one elected thread of the CTA)
+  const int bx0 = gfirst * G.W;                 // first lattice column of the group
+  const int bx = gx - bx0;                      // this lane's column inside the boxes
+  auto tens_issue_A = [&](int ezr) {            // displacement rows 1..N-1 of element row ezr -> stage (ezr - ez0) & 1
+    const int sg = (ezr - ez0) & 1;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // ... and (S2D_STRIP_TENSOR_COEF) the coefficient blocks of the group's strips for that row: one contiguous run
+    int g0, gc;
+    strip_group_cols(G, gfirst, g0, gc);
+    const unsigned cbytes = TCOEF ? (unsigned)((size_t)gc * (NPL * N * N / 2) * sizeof(V2)) : 0u;
+    mbar_expect_tx(&tbarA[sg], (unsigned)((size_t)NDOF * (N - 1) * BW * sizeof(T)) + cbytes);
+    tma_load_3d(tbase + sg * TSZ, &A.tm_d, bx0, strip_lat_row(G, ezr, 0) + 1, 0, &tbarA[sg]);
+    if (TCOEF)
+      bulk_g2s(tbase + sg * TSZ + TOFF_R + TSZ_R,
+               reinterpret_cast<const V2*>(A.coef) + (size_t)strip_elem_off(G, seg, gfirst, ezr) * (NPL * N * N / 2), cbytes,
+               &tbarA[sg]);
+  };
+  auto tens_issue_B = [&](int ezr) {            // v and rmass of rows 0..N-2 of element row ezr
+    const int sg = (ezr - ez0) & 1;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&tbarB[sg], (unsigned)((size_t)((FUSED == 2 ? 2 : 1) * NDOF + 1) * (N - 1) * BW * sizeof(T)));
+    tma_load_3d(tbase + sg * TSZ + TSZ_A, &A.tm_v, bx0, strip_lat_row(G, ezr, 0), 0, &tbarB[sg]);
+    if (FUSED == 2) tma_load_3d(tbase + sg * TSZ + 2 * TSZ_A, &A.tm_a, bx0, strip_lat_row(G, ezr, 0), 0, &tbarB[sg]);
+    tma_load_2d(tbase + sg * TSZ + TOFF_R, &A.tm_r, bx0, strip_lat_row(G, ezr, 0), &tbarB[sg]);
+  };
+  if constexpr (TENS) {
+    if (threadIdx.x == 0) {
+      mbar_init(&tbarA[0], 1);
+      mbar_init(&tbarA[1], 1);
+      mbar_init(&tbarB[0], 1);
+      mbar_init(&tbarB[1], 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tens_issue_A(ez0);
+      if (ez0 + 1 < ez1) tens_issue_A(ez0 + 1);
+      tens_issue_B(ez0);
+    }
+    __syncthreads();  // the barriers exist before anybody waits on them
   }
   if (wact) {
     issue_row(ez0, cp);
@@ -494,7 +633,15 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       // copies of what the end of this iteration needs (v, rmass) and of the whole next row
       stage_wait<0>();
       V2 a2[NPL / 2][N];
-      if (S2D_ABLATE & 4) {
+      if constexpr (TENS) {
+        const int kk = ez - ez0;
+        mbar_wait_or_trap(&tbarA[kk & 1], (unsigned)((kk >> 1) & 1));
+        const T* bA = reinterpret_cast<const T*>(tbase + (kk & 1) * TSZ) + bx;
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+          for (int j = 1; j < N; ++j) U[c][j] = bA[(c * (N - 1) + j - 1) * BW];
+      } else if (S2D_ABLATE & 4) {
 #pragma unroll
         for (int c = 0; c < NDOF; ++c)
 #pragma unroll
@@ -510,7 +657,14 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
 #pragma unroll
           for (int j = 1; j < N; ++j) U[c][j] = up[A.npoin * c + rowbase + (size_t)j * LX];
       }
-      if (S2D_ABLATE & 2) {
+      if constexpr (TCOEF) {  // landed with the displacement box (same mbarrier, waited for above)
+        const V2* cb = reinterpret_cast<const V2*>(tbase + ((ez - ez0) & 1) * TSZ + TOFF_R + TSZ_R) +
+                       (size_t)(ex0 - gex0) * (NPL * N * N / 2) + lanep;
+#pragma unroll
+        for (int pp = 0; pp < NPL / 2; ++pp)
+#pragma unroll
+          for (int j = 0; j < N; ++j) a2[pp][j] = cb[(pp * N + j) * cxN];
+      } else if (S2D_ABLATE & 2) {
 #pragma unroll
         for (int pp = 0; pp < NPL / 2; ++pp)
 #pragma unroll
@@ -543,7 +697,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           const unsigned long long two = ((unsigned long long)rowmask[(o >> 5) + 1] << 32) | rowmask[o >> 5];
           defer = coldef ? ~0u : (unsigned)(two >> (o & 31));
         }
-        if (st_ok && !(S2D_ABLATE & 8)) {
+        if (st_ok && !TENS && !(S2D_ABLATE & 8)) {
           if (stg_v) {
 #pragma unroll
             for (int j = 0; j < N - 1; ++j) {
@@ -581,7 +735,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         T et[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) et[j] = ld_stream(etap + (size_t)j * cxN);
-        etap += (size_t)cx * (N * N);
+        etap += (size_t)gcx * (N * N);
 #pragma unroll
         for (int c = 0; c < NDOF; ++c) {
           T vr[N];
@@ -720,7 +874,15 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     // (producer / consumer named barriers between neighbouring warps instead of this CTA barrier were
     // tried with two slots and hung: two bar.arrive of a producer that runs a row ahead complete a 64-thread
     // phase on their own.  Strict alternation would work but couples the pair as tightly as this barrier.)
-    if (WARPS > 1 && !(S2D_ABLATE & 32)) __syncthreads();
+    if ((WARPS > 1 && !(S2D_ABLATE & 32)) || TENS) __syncthreads();
+    if constexpr (TENS) {
+      // every warp has read the displacement box of this row (top of the iteration) and the v / rmass boxes of the
+      // previous row (end of the previous iteration): both stages are free for rows ez + 2 and ez + 1
+      if (threadIdx.x == 0) {
+        if (ez + 2 < ez1) tens_issue_A(ez + 2);
+        if (ez + 1 < ez1) tens_issue_B(ez + 1);
+      }
+    }
     if (wact) {
       if (take) {  // column shared with the strip on the left (same group)
 #pragma unroll
@@ -739,7 +901,21 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         // component (mat_mass.f90:56-57; only bc_abso.f90:243 makes the columns differ, on deferred
         // nodes), so one read of component 1 serves all of them.
         T vv[NDOF][N - 1], rm[N - 1];
-        if (FUSED && (S2D_ABLATE & 8)) {
+        if constexpr (TENS) {
+          const int kk = ez - ez0;
+          mbar_wait_or_trap(&tbarB[kk & 1], (unsigned)((kk >> 1) & 1));
+          const T* bV = reinterpret_cast<const T*>(tbase + (kk & 1) * TSZ + TSZ_A) + bx;
+          const T* bR = reinterpret_cast<const T*>(tbase + (kk & 1) * TSZ + TOFF_R) + bx;
+#pragma unroll
+          for (int j = 0; j < N - 1; ++j) {
+            rm[j] = bR[j * BW];
+#pragma unroll
+            for (int c = 0; c < NDOF; ++c) {
+              vv[c][j] = bV[(c * (N - 1) + j) * BW];
+              if (NM) vv[c][j] = vv[c][j] + A.c2 * bV[TSZ_A / sizeof(T) + (c * (N - 1) + j) * BW];  // predictor, solver.f90:60
+            }
+          }
+        } else if (FUSED && (S2D_ABLATE & 8)) {
 #pragma unroll
           for (int j = 0; j < N - 1; ++j) {
             rm[j] = (T)1e-9;
@@ -1134,6 +1310,11 @@ struct StripIO {
   const T* eta = nullptr;   // Kelvin-Voigt: eta per element GLL point (strip layout) and the velocity field
   const T* v_kv = nullptr;
   const T* beta = nullptr;  // 2.5D: beta per element GLL point (strip layout)
+  // tensor-map staging of the fused leapfrog kernel (null: per-lane copies)
+  const CUtensorMap* tm_d = nullptr;
+  const CUtensorMap* tm_v = nullptr;
+  const CUtensorMap* tm_r = nullptr;
+  const CUtensorMap* tm_a = nullptr;
   int prefetch = 1;
   // compact coefficient mode (coef holds lambda, mu only)
   int compact = 0;
@@ -1142,9 +1323,11 @@ struct StripIO {
   const double* wgll = nullptr;
 };
 
-template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false>
+template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false,
+          bool TENS = false>
 inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) {
-  constexpr size_t smem = strip_warps() * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT);
+  constexpr size_t smem = TENS ? strip_tens_smem(N, NDOF, sizeof(T), COMPACT, FUSED)
+                               : strip_warps() * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT);
   // Opt in to the dynamic shared memory once per device and instantiation.  Never on the step path
   // afterwards: cudaFuncSetAttribute can serialise with running kernels, and a strip that is waiting
   // on its neighbour's flag must not keep the neighbour's host thread from launching.
@@ -1152,11 +1335,11 @@ inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) 
   int dev = 0;
   S2D_CUDA(cudaGetDevice(&dev));
   if (!done[dev & 63]) {
-    S2D_CUDA(cudaFuncSetAttribute(k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV>,
+    S2D_CUDA(cudaFuncSetAttribute(k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV, TENS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done[dev & 63] = true;
   }
-  k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV><<<nb, strip_warps() * 32, smem, s>>>(A);
+  k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV, TENS><<<nb, strip_warps() * 32, smem, s>>>(A);
 }
 
 // element-force launch over the groups selected by G.it_* (no halo fold)
@@ -1200,6 +1383,26 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
     A.rzx = (T)(io.cdx != 0.0 ? io.cdz / io.cdx : 0.0);                                           \
     const unsigned nb = (unsigned)G.nitems;                                                       \
     const int mode = !fused ? 0 : (io.newmark ? 2 : 1);                                           \
+    if constexpr (NN <= 6) { /* CTA-wide tensor-map staging of the fused step (S2D_STRIP_TENSOR) */ \
+      if (mode >= 1 && io.tm_d && !io.eta) {                                                      \
+        constexpr int MB = strip_min_ctas(NN, sizeof(T));                                         \
+        A.tm_d = *io.tm_d;                                                                        \
+        A.tm_v = *io.tm_v;                                                                        \
+        A.tm_r = *io.tm_r;                                                                        \
+        if (mode == 2) A.tm_a = *io.tm_a;                                                         \
+        if (G.ndof == 1) {                                                                        \
+          if (mode == 2) strip_launch<T, NN, 1, 2, false, MB, false, true>(nb, A, s);             \
+          else strip_launch<T, NN, 1, 1, false, MB, false, true>(nb, A, s);                       \
+        } else if (io.compact) {                                                                  \
+          if (mode == 2) strip_launch<T, NN, 2, 2, true, MB, false, true>(nb, A, s);              \
+          else strip_launch<T, NN, 2, 1, true, MB, false, true>(nb, A, s);                        \
+        } else {                                                                                  \
+          if (mode == 2) strip_launch<T, NN, 2, 2, false, MB, false, true>(nb, A, s);             \
+          else strip_launch<T, NN, 2, 1, false, MB, false, true>(nb, A, s);                       \
+        }                                                                                         \
+        break;                                                                                    \
+      }                                                                                           \
+    }                                                                                             \
     if (io.eta) { /* Kelvin-Voigt elements: plain force evaluation from d + eta*v */               \
       if (mode != 0) throw ArgError("Kelvin-Voigt elements: the node update is not fused");        \
       constexpr int MB = strip_min_ctas(NN, sizeof(T));                                           \
