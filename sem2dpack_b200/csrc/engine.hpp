@@ -1085,6 +1085,7 @@ class Engine : public EngineBase {
   std::vector<int32_t> h_fault_node1;  // first node1 of every fault (which side of a split-node row is the lower one)
   std::vector<double> h_eta;
   DevBuf<T> strip_eta;                 // Kelvin-Voigt eta per element GLL point in the strip layout (zero off the KV elements)
+  DevBuf<T> v_alt, a_alt;              // second velocity / acceleration buffers of the fused Kelvin-Voigt step
   static bool strip_kv_ok() { return true; }   // k_elem_strip<KV>: d + eta*v element by element
 
   // ---- planning ------------------------------------------------------------------------
@@ -1253,8 +1254,18 @@ class Engine : public EngineBase {
         cart_kv_eta.release();
       }
       // the node update rides in the strip kernel for leapfrog and for the explicit Newmark scheme (beta = 0)
-      fused = (scheme.kind == 0 || (scheme.kind == 1 && scheme.beta == 0.0)) && env_int("S2D_FUSED", 1) != 0 &&
-              strip_eta.n == 0;  // Kelvin-Voigt elements: the node update takes the separate passes
+      fused = (scheme.kind == 0 || (scheme.kind == 1 && scheme.beta == 0.0)) && env_int("S2D_FUSED", 1) != 0;
+      // Kelvin-Voigt elements read their neighbours' velocities: the fused update then writes v (Newmark: and a)
+      // into a second buffer (S2D_KV_FUSED=0: the separate predictor / corrector passes of round 1)
+      if (strip_eta.n && (ngll > STRIP_KV_FUSED_MAXN || env_int("S2D_KV_FUSED", 1) == 0)) fused = false;
+      if (fused && strip_eta.n) {
+        v_alt.alloc(npoin * ndof);
+        v_alt.zero(stream);
+        if (scheme.kind == 1) {
+          a_alt.alloc(npoin * ndof);
+          a_alt.zero(stream);
+        }
+      }
       if (fused) build_deferred_tables();
     } else {
       if (variant == S2D_ASM_PATCH) build_patch_plan_dev();
@@ -1557,13 +1568,15 @@ class Engine : public EngineBase {
     }
     T* dc = dalt();   // d[n]
     T* dnx = dn();    // receives the prediction d[n+1]; d[n-1] is dead
-    StripIO<T> io = strip_io(dc, a.p);
+    const bool kvf = strip_eta.n != 0;  // Kelvin-Voigt: v (Newmark: and a) go to the second buffer, swapped below
+    StripIO<T> io = strip_io(dc, kvf && nmk ? a_alt.p : a.p);
     io.v_in = v.p;
-    io.v_out = v.p;
+    io.v_out = kvf ? v_alt.p : v.p;
+    if (kvf) io.eta = strip_eta.p;
     io.rmass = rmass.p;
     io.d_next = dnx;
     const bool want_a = nmk || store_accel == 1 || (store_accel == 2 && (last_of_call || (rec.present && rec.field == 'A')));
-    io.a_out = want_a ? a.p : nullptr;
+    io.a_out = want_a ? io.f : nullptr;
     io.rowflag = rowflag.p;
     io.colflag = colflag.p;
     io.dt = scheme.dt;
@@ -1572,13 +1585,17 @@ class Engine : public EngineBase {
     io.c2 = c2;
     io.c3 = c3;
     io.a_in = a.p;
-    if (tm_ready) {  // d[n] lives in the buffer the caller does not see at this point
+    if (tm_ready && !kvf) {  // d[n] lives in the buffer the caller does not see at this point
       io.tm_d = &tm_d[dc == d.p ? 0 : 1];
       io.tm_v = &tm_v;
       io.tm_r = &tm_r;
       io.tm_a = &tm_a;
     }
     launch_strips(io, ctl.p);  // ... and the step counter (k_strip_fold)
+    if (kvf) {  // from here on v / a name the buffers this step wrote
+      std::swap(v, v_alt);
+      if (nmk) std::swap(a, a_alt);
+    }
     phase(PH_SRC);
     if (!node_ops_ready) launch_sources(a.p);
     phase(PH_BC);

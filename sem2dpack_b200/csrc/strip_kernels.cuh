@@ -391,13 +391,22 @@ constexpr int strip_min_ctas(int N, int tsize, bool compact = false) {
   return (N <= 6 ? (tsize == 4 ? 4 : 3) : (tsize == 4 ? 2 : 1)) * 4 / strip_warps();
 }
 
+// Kelvin-Voigt instantiations carry the velocities of the element as well: the FP64 P-SV ones spill at 168 registers
+// (100-320 B), so they run 2 CTAs per SM with the full register file (S2D_KV_MINB to measure the other choice)
+#ifndef S2D_KV_MINB
+#define S2D_KV_MINB 2
+#endif
+constexpr int strip_min_ctas_kv(int N, int tsize, int ndof) {
+  return (tsize == 8 && ndof == 2 && N >= 5 && N <= 6) ? S2D_KV_MINB : strip_min_ctas(N, tsize);
+}
+
 template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false,
           bool TENS = false>
 __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     k_elem_strip(const __grid_constant__ StripArgs<T, N> A) {
   static_assert(!TENS || (FUSED >= 1 && !KV), "tensor-map staging: fused leapfrog / explicit Newmark step");
   static_assert(!COMPACT || NDOF == 2, "compact coefficients: P-SV only");
-  static_assert(!KV || FUSED == 0, "Kelvin-Voigt elements: plain force evaluation (the node update runs in its own passes)");
+  static_assert(!KV || !TENS, "Kelvin-Voigt elements: per-lane staging only");
   constexpr int WARPS = strip_warps();
   constexpr int NEL = NDOF == 1 ? 2 : 6;
   constexpr int NPL = COMPACT ? 2 : NEL;  // planes stored per GLL point
@@ -432,6 +441,19 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   T* st_r = st_v + NU * 32;                                    // [j][32]               (fused)
   T* st_a = st_r + (N - 1) * 32;                               // [c * (N-1) + j][32]   (fused Newmark: a[n-1])
   constexpr bool NM = FUSED == 2;
+  // Kelvin-Voigt inside the fused step: every lane reads the velocities of its element's nodes for d + eta*v, so the
+  // update must not overwrite them in place -- v (and, for Newmark, a) are double-buffered (v_in != v_out) and the
+  // lane that stores a deferred node's force always leaves that node's (predicted) velocity in v_out
+  constexpr bool VDB = KV && FUSED != 0;
+  auto kv_vel = [&](size_t q) -> T {  // the velocity MAT_KV_add_etav sees (solver.f90:293-295)
+    if constexpr (FUSED != 0) {
+      T x = A.v_in[q];
+      if (NM) x = x + A.c2 * A.a_in[q];
+      return x;
+    } else {
+      return A.v_kv[q];
+    }
+  };
   constexpr bool tma_c = (S2D_STRIP_TMA == 2 || (S2D_STRIP_TMA == 1 && !COMPACT)) && ((S2D_STRIP_STAGE & 2) != 0) &&
                          sizeof(T) == 8;  // 16-byte vectors: block address and size are multiples of 16
   __shared__ __align__(8) unsigned long long cbar[WARPS];
@@ -523,7 +545,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     for (int c = 0; c < NDOF; ++c) {
       U[c][0] = up[A.npoin * c + r0];
       Fc[c] = 0;
-      if (KV) Vc[c] = A.v_kv[gx + A.npoin * c + r0];
+      if (KV) Vc[c] = kv_vel(gx + A.npoin * c + r0);
     }
   }
   const T* etap = KV ? A.eta + (size_t)strip_elem_off(G, seg, strip, ez0) * (N * N) + lanep : nullptr;
@@ -554,6 +576,18 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
 #pragma unroll
         for (int j = 1; j < N; ++j)
           stage_copy<sizeof(T)>(st_u + (c * (N - 1) + j - 1) * 32, up + A.npoin * c + rb + (size_t)j * LX);
+    }
+    if constexpr (VDB) {  // the row's velocities (Newmark: and accelerations) travel with its displacements
+      if (stg_u && stg_v) {
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+          for (int j = 1; j < N; ++j) {
+            const size_t q = gx + A.npoin * c + rb + (size_t)j * LX;
+            stage_copy<sizeof(T)>(st_v + (c * (N - 1) + j - 1) * 32, A.v_in + q);
+            if (NM) stage_copy<sizeof(T)>(st_a + (c * (N - 1) + j - 1) * 32, A.a_in + q);
+          }
+      }
     }
     (void)rb;
     if (TCOEF || (S2D_ABLATE & 2)) {
@@ -628,6 +662,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     const size_t rowbase = grow * LX;
     T f[NDOF][N];
     unsigned defer = 0;  // bit j: the node of row grow+j is deferred (its force is stored instead)
+    T vk[VDB ? NDOF : 1][VDB ? N - 1 : 1];  // fused Kelvin-Voigt: velocities of rows 0..N-2, reused by the node update
     if (wact) {
       // ---- this element row has landed in the staging area: move it to registers, then start the
       // copies of what the end of this iteration needs (v, rmass) and of the whole next row
@@ -656,6 +691,20 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         for (int c = 0; c < NDOF; ++c)
 #pragma unroll
           for (int j = 1; j < N; ++j) U[c][j] = up[A.npoin * c + rowbase + (size_t)j * LX];
+      }
+      T Vn[VDB ? NDOF : 1][VDB ? N - 1 : 1];  // fused Kelvin-Voigt: (predicted) velocities of rows 1..N-1
+      if constexpr (VDB) {
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+          for (int j = 1; j < N; ++j) {
+            if (stg_u && stg_v) {
+              Vn[c][j - 1] = st_v[(c * (N - 1) + j - 1) * 32];
+              if (NM) Vn[c][j - 1] = Vn[c][j - 1] + A.c2 * st_a[(c * (N - 1) + j - 1) * 32];
+            } else {
+              Vn[c][j - 1] = kv_vel(gx + A.npoin * c + rowbase + (size_t)j * LX);
+            }
+          }
       }
       if constexpr (TCOEF) {  // landed with the displacement box (same mbarrier, waited for above)
         const V2* cb = reinterpret_cast<const V2*>(tbase + ((ez - ez0) & 1) * TSZ + TOFF_R + TSZ_R) +
@@ -704,9 +753,12 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
               const size_t q = rowbase + (size_t)j * LX + gx;
               stage_copy<sizeof(T)>(st_r + j * 32, A.rmass + q);
 #pragma unroll
-              for (int c = 0; c < NDOF; ++c) {
-                stage_copy<sizeof(T)>(st_v + (c * (N - 1) + j) * 32, A.v_in + A.npoin * c + q);
-                if (NM) stage_copy<sizeof(T)>(st_a + (c * (N - 1) + j) * 32, A.a_in + A.npoin * c + q);
+              if (!VDB) {  // Kelvin-Voigt: the (predicted) velocities are already in registers (vk)
+#pragma unroll
+                for (int c = 0; c < NDOF; ++c) {
+                  stage_copy<sizeof(T)>(st_v + (c * (N - 1) + j) * 32, A.v_in + A.npoin * c + q);
+                  if (NM) stage_copy<sizeof(T)>(st_a + (c * (N - 1) + j) * 32, A.a_in + A.npoin * c + q);
+                }
               }
             }
           } else if (A.prefetch && i == 0) {  // read at the end of the row: pull the lines into L2 now
@@ -741,9 +793,16 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           T vr[N];
           vr[0] = Vc[c];
 #pragma unroll
-          for (int j = 1; j < N; ++j) vr[j] = A.v_kv[gx + A.npoin * c + rowbase + (size_t)j * LX];
+          for (int j = 1; j < N; ++j) {
+            if constexpr (VDB) vr[j] = Vn[c][j - 1];
+            else vr[j] = kv_vel(gx + A.npoin * c + rowbase + (size_t)j * LX);
+          }
 #pragma unroll
           for (int j = 0; j < N; ++j) Ue[c][j] = U[c][j] + et[j] * vr[j];
+          if constexpr (VDB) {
+#pragma unroll
+            for (int j = 0; j < N - 1; ++j) vk[c][j] = vr[j];
+          }
           Vc[c] = vr[N - 1];
         }
       }
@@ -930,8 +989,12 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
               rm[j] = st_r[j * 32];
 #pragma unroll
               for (int c = 0; c < NDOF; ++c) {
-                vv[c][j] = st_v[(c * (N - 1) + j) * 32];
-                if (NM) vv[c][j] = vv[c][j] + A.c2 * st_a[(c * (N - 1) + j) * 32];  // predictor, solver.f90:60
+                if constexpr (VDB) {
+                  vv[c][j] = vk[c][j];
+                } else {
+                  vv[c][j] = st_v[(c * (N - 1) + j) * 32];
+                  if (NM) vv[c][j] = vv[c][j] + A.c2 * st_a[(c * (N - 1) + j) * 32];  // predictor, solver.f90:60
+                }
               }
             }
           } else {  // one batch of independent loads (deferred nodes included)
@@ -941,8 +1004,12 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
               rm[j] = A.rmass[q];
 #pragma unroll
               for (int c = 0; c < NDOF; ++c) {
-                vv[c][j] = A.v_in[A.npoin * c + q];
-                if (NM) vv[c][j] = vv[c][j] + A.c2 * A.a_in[A.npoin * c + q];
+                if constexpr (VDB) {
+                  vv[c][j] = vk[c][j];
+                } else {
+                  vv[c][j] = A.v_in[A.npoin * c + q];
+                  if (NM) vv[c][j] = vv[c][j] + A.c2 * A.a_in[A.npoin * c + q];
+                }
               }
             }
           }
@@ -956,7 +1023,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
               sp[cstride * c + (grow + j) * rstride] = f[c][j];
               // Newmark: the lane that stores into f owns the node and leaves the predicted velocity
               // for the boundary conditions and the deferred update
-              if (NM && !to_halo) A.v_out[q] = vv[c][j];
+              if ((NM || VDB) && !to_halo) A.v_out[q] = vv[c][j];
             } else {  // solver.f90:157-158 (leapfrog) / :78-81 (Newmark), then the predictor of the next step
               const T acc = rm[j] * f[c][j];
               const T vn = vv[c][j] + A.c3 * acc;
@@ -983,8 +1050,9 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           const size_t q = A.npoin * c + gt * LX + gx;
           T vp = 0;
           if (NM && !to_halo) vp = A.v_in[q] + A.c2 * A.a_in[q];  // before f overwrites a
+          else if (VDB && !to_halo) vp = A.v_in[q];
           sp[cstride * c + gt * rstride] = Fc[c];
-          if (NM && !to_halo) A.v_out[q] = vp;
+          if ((NM || VDB) && !to_halo) A.v_out[q] = vp;
         }
       } else {
 #pragma unroll
@@ -1057,7 +1125,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           store_f[u] = !FUSED || bcol || A.rowflag[gz];
           if (FUSED) {
             rm[u] = A.rmass[q[u]];
-            vv[u] = __ldcg(A.v_in + q[u]);  // Newmark: already predicted by the column's owner lane
+            vv[u] = __ldcg((NM && VDB ? A.v_out : A.v_in) + q[u]);  // Newmark: already predicted by the column's owner lane
             dd[u] = A.d[q[u]];
           }
         }
@@ -1323,6 +1391,8 @@ struct StripIO {
   const double* wgll = nullptr;
 };
 
+// largest ngll whose Kelvin-Voigt instantiation also carries the fused node update (compile time of the library)
+constexpr int STRIP_KV_FUSED_MAXN = 6;
 template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false,
           bool TENS = false>
 inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) {
@@ -1404,11 +1474,28 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
       }                                                                                           \
     }                                                                                             \
     if (io.eta) { /* Kelvin-Voigt elements: plain force evaluation from d + eta*v */               \
-      if (mode != 0) throw ArgError("Kelvin-Voigt elements: the node update is not fused");        \
-      constexpr int MB = strip_min_ctas(NN, sizeof(T));                                           \
+      constexpr int MB = strip_min_ctas_kv(NN, sizeof(T), 1), M2 = strip_min_ctas_kv(NN, sizeof(T), 2);  \
+      if (mode != 0) { /* fused with the node update: v (and a) double-buffered by the caller */   \
+        if constexpr (NN <= STRIP_KV_FUSED_MAXN) {                                                \
+          if (io.v_in == io.v_out || (mode == 2 && (const T*)io.f == io.a_in))                    \
+            throw ArgError("Kelvin-Voigt elements: the fused update needs separate output buffers"); \
+          if (G.ndof == 1) {                                                                      \
+            if (mode == 2) strip_launch<T, NN, 1, 2, false, MB, true>(nb, A, s);                  \
+            else strip_launch<T, NN, 1, 1, false, MB, true>(nb, A, s);                            \
+          } else if (io.compact) {                                                                \
+            if (mode == 2) strip_launch<T, NN, 2, 2, true, M2, true>(nb, A, s);                   \
+            else strip_launch<T, NN, 2, 1, true, M2, true>(nb, A, s);                             \
+          } else {                                                                                \
+            if (mode == 2) strip_launch<T, NN, 2, 2, false, M2, true>(nb, A, s);                  \
+            else strip_launch<T, NN, 2, 1, false, M2, true>(nb, A, s);                            \
+          }                                                                                       \
+          break;                                                                                  \
+        }                                                                                         \
+        throw ArgError("Kelvin-Voigt elements: the node update is fused for ngll <= 6 only");      \
+      }                                                                                           \
       if (G.ndof == 1) strip_launch<T, NN, 1, 0, false, MB, true>(nb, A, s);                      \
-      else if (io.compact) strip_launch<T, NN, 2, 0, true, MB, true>(nb, A, s);                   \
-      else strip_launch<T, NN, 2, 0, false, MB, true>(nb, A, s);                                  \
+      else if (io.compact) strip_launch<T, NN, 2, 0, true, M2, true>(nb, A, s);                   \
+      else strip_launch<T, NN, 2, 0, false, M2, true>(nb, A, s);                                  \
       break;                                                                                      \
     }                                                                                             \
     if (G.ndof == 1) {                                                                            \

@@ -162,3 +162,41 @@ def test_finite_seismogenic_width_decks(name, nsteps, route_flag, monkeypatch):
     o.set_fields(d0, v0)
     assert rel_l2(r.e.compute_fint(), o.compute_fint()) <= 1e-13
     r.close()
+
+
+@pytest.mark.parametrize("scheme", ["newmark", "leapfrog"])
+@pytest.mark.parametrize("kv_fused", ["1", "0"])
+def test_kelvin_voigt_inside_the_fused_step(scheme, kv_fused, monkeypatch):
+    """MAT_KV_add_etav (mat_kelvin_voigt.f90:137-150; solver.f90:293-295): the element force is taken from
+    d + eta*v with the PREDICTED velocity.  On the strip kernel the node update rides in the same launch (v and,
+    for Newmark, a are double-buffered because neighbours read them); S2D_KV_FUSED=0 keeps the separate
+    predictor / corrector passes.  TPV3 deck (P-SV, NGLL 6, KV layer, one-sided SWF fault, ABSORB + DIRNEU)."""
+    monkeypatch.setenv("S2D_KV_FUSED", kv_fused)
+    deck = harness.deck("tpv3")
+    if scheme == "leapfrog":
+        deck = deck.replace("kind='newmark'", "kind='leapfrog'")
+        assert "kind='leapfrog'" in deck
+
+    def check():
+        d, v, a = r.e.get_fields()
+        assert np.abs(o.arr("d")).max() > 0
+        for nm, got in (("d", d), ("v", v), ("acc", a)):
+            assert rel_l2(got, o.arr(nm)) <= 1e-10, (nm, rel_l2(got, o.arr(nm)))
+        for fid, ibc, np_, onx in r.faults:
+            st = r.e.fault_state(fid, np_)
+            for k in ("D", "V", "T"):
+                ref = o.arr(f"bc.{ibc}.{k}")
+                assert np.abs(st[k] - ref).max() <= 1e-10 * max(np.abs(ref).max(), 1e-12), k
+
+    o, r = _run(deck, 650)
+    assert r.e.route() == 1 and o.i("nkv") > 0 and r.faults
+    check()
+    n_launch = r.e.launch_count()
+    o.step(40)   # a second call continues from the swapped buffers
+    r.step(40)
+    check()
+    if kv_fused == "1":
+        assert (r.e.launch_count() - n_launch) <= 7 * 40  # no separate predictor / corrector passes
+    else:
+        assert (r.e.launch_count() - n_launch) > 7 * 40
+    r.close()
