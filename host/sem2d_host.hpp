@@ -151,12 +151,15 @@ struct problem_type {
   // or DIST_* fields, &MAT_KV (SRC/mat_kelvin_voigt.f90:35-66)
   struct material_type {
     bool set = false, kv = false, ETAxDT = true;
+    bool plastic = false;                        // kind='PLAST' (&MAT_PLASTIC, SRC/mat_plastic.f90:46-118)
+    double phi = 0, coh = 0, Tv = 0, e0[3] = {0, 0, 0};
     cd_type rho, cp, cs, eta;
     bool homogeneous() const { return rho.dist == 0 && cp.dist == 0 && cs.dist == 0; }
   };
   std::vector<material_type> mat;                // index tag-1
   double rho = 0, cp = 0, cs = 0;                // material of tag 1 when it is homogeneous (builder default)
   bool has_kv = false;
+  bool has_plastic = false;
   timescheme_type time;
   std::vector<bc_type> bc;
   std::vector<source_type> src;
@@ -306,8 +309,26 @@ inline void read_main(problem_type& pb, const std::string& file) {
     const nml_group& g = in.at((size_t)m0);
     problem_type::material_type& M = pb.mat[(size_t)g.integer("tag", 0) - 1];
     const std::string k1 = g.text("kind", "ELAST", 0), k2 = g.count("kind") >= 2 ? g.text("kind", "", 1) : std::string();
+    if (k1 == "PLAST") {  // MAT_PLAST_read (SRC/mat_plastic.f90:66-118): constants only
+      if (!k2.empty()) IO_abort("MAT_read: kind='PLAST' combined with '" + k2 + "' is not on the B200 path");
+      const long m = in.find("MAT_PLASTIC", (size_t)m0);
+      if (m < 0) IO_abort("MAT_PLAST_read: MAT_PLASTIC input block not found");
+      const nml_group& e = in.at((size_t)m);
+      M.rho.c = e.real8("rho", 0.0);
+      M.cp.c = e.real8("cp", 0.0);
+      M.cs.c = e.real8("cs", 0.0);
+      if (!(M.rho.c > 0) || !(M.cp.c > 0) || !(M.cs.c > 0)) IO_abort("MAT_PLAST_read: incomplete input (rho, cp, cs)");
+      M.phi = e.real8("phi", 0.0);
+      M.coh = e.real8("coh", 0.0);
+      M.Tv = e.real8("tv", 0.0);
+      for (int q = 0; q < 3; ++q) M.e0[q] = e.real8("e0", 0.0, (size_t)q);
+      M.plastic = true;
+      M.set = true;
+      pb.has_plastic = true;
+      continue;
+    }
     if (k1 != "ELAST" || !(k2.empty() || k2 == "KV"))
-      IO_abort("MAT_read: only kind='ELAST' and kind='ELAST','KV' are on the B200 path (PLAST, DMG, VISCO are stateful rheologies)");
+      IO_abort("MAT_read: only kind='ELAST', kind='ELAST','KV' and kind='PLAST' are on the B200 path (DMG, VISCO are not)");
     const long m = in.find("MAT_ELASTIC", (size_t)m0);
     if (m < 0) IO_abort("MAT_ELAST_read: MAT_ELASTIC input block not found");
     const nml_group& e = in.at((size_t)m);  // SRC/mat_elastic.f90:104-129
@@ -690,6 +711,22 @@ inline void init_main(problem_type& pb) {
     s2d_check(pb, s2d_cart_info(pb.gpu, &pb.npoin, &pb.nelem_total, &dt), "init_main");
   }
   if (pb.W > 0.0) s2d_check(pb, s2d_cart_set_w25d(pb.gpu, pb.W), "MAT_ELAST_init_25D");
+  if (pb.has_plastic) {  // MAT_init_work (SRC/mat_gen.f90:367-372): one plastic material set per PLAST tag
+    if (pb.ndof != 2) IO_abort("MAT_init_work: plasticity requires ndof=2 (P-SV) ");
+    std::vector<int> set_of_tag(pb.mat.size(), 0);
+    std::vector<double> par;
+    int nsets = 0;
+    for (size_t tg = 0; tg < pb.mat.size(); ++tg) {
+      const auto& M = pb.mat[tg];
+      if (!M.plastic) continue;
+      set_of_tag[tg] = ++nsets;
+      const double six[6] = {M.coh, M.phi, M.Tv, M.e0[0], M.e0[1], M.e0[2]};
+      par.insert(par.end(), six, six + 6);
+    }
+    std::vector<int32_t> eset((size_t)pb.nelem_total);
+    for (size_t e = 0; e < eset.size(); ++e) eset[e] = set_of_tag[(size_t)tag[e] - 1];
+    s2d_check(pb, s2d_cart_set_plastic(pb.gpu, nsets, par.data(), eset.data()), "MAT_PLAST_init_elem_work");
+  }
   // TIME_init (SRC/time.f90:323-341)
   timescheme_type& t = pb.time;
   if (!(t.dt > 0.0)) {

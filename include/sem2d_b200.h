@@ -251,6 +251,17 @@ int s2d_launch_count(s2d_handle h, int64_t* n);
 /* raw CUDA stream (cudaStream_t) the engine launches on, for external event timing */
 int s2d_stream(s2d_handle h, void** stream);
 
+/* Coulomb plasticity (kind='PLAST': MAT_PLAST_read / MAT_PLAST_init_elem_work / MAT_PLAST_stress, mat_plastic.f90:66-118,
+ * 148-218,281-387; MAT_Fint's strain -> stress -> force branch, mat_gen.f90:445-449, with MAT_strain_PSV :752-775 and
+ * MAT_forces :834-866).  par(6,nsets) = coh, phi [degrees], Tv, e0(3) of every plastic material as &MAT_PLASTIC gives
+ * them; elem_set(nelem), natural element order: 0 = elastic element, k = plastic material k (1-based).  lambda, mu come
+ * from s2d_cart_set_material's rho, cp, cs (uniform inside a plastic element, as in the reference).  The plastic strain
+ * ep(ngll,ngll,3) of every element lives on the device and is advanced by every force evaluation (update = .true.);
+ * s2d_cart_get_plastic_strain returns it as (ngll,ngll,3,nelem), natural element order (MAT_PLAST_export).
+ * P-SV, ngll <= 6, at most 7 plastic materials, no Kelvin-Voigt elements in the same problem. */
+int s2d_cart_set_plastic(s2d_handle h, int32_t nsets, const double* par, const int32_t* elem_set);
+int s2d_cart_get_plastic_strain(s2d_handle h, double* ep);
+
 /* ---- device-side structured builder (mesh_cartesian.f90:219-314 + init on the GPU) --------- */
 /* Builds, directly in HBM, a MESH_CART problem: nx*nz Q4 elements on [x0,x1]x[z0,z1], optional
  * horizontal split-node fault after element row ezflt (0 = none), natural (row-major) element

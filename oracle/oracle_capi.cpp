@@ -128,6 +128,7 @@ long long orc_get_int(void* hv, const char* name_) {
   if (n == "nelast") return pb.nelast;
   if (n == "ncoefsets") return pb.ncoefsets;
   if (n == "nkv") return (long long)pb.kv_elem.size();
+  if (n == "npl") return (long long)pb.pl_elem.size();
   if (n == "nt") return pb.time.nt;
   if (n == "it") return pb.it;
   if (n == "nbc") return (long long)pb.bc.size();
@@ -311,6 +312,9 @@ long long orc_array(void* hv, const char* name_, const void** ptr, char* dtype) 
   if (n == "elem2set") RET_I(pb.elem2set);
   if (n == "kv_elem") RET_I(pb.kv_elem);
   if (n == "kv_eta") RET_D(pb.kv_eta);
+  if (n == "pl_elem") RET_I(pb.pl_elem);
+  if (n == "pl_ep") RET_D(pb.pl_ep);
+  if (n == "pl_par") RET_D(pb.pl_par);
   if (n == "rmass") RET_D(pb.rmass);
   if (n == "mass") RET_D(pb.mass);
   if (n == "d") RET_D(pb.d);

@@ -673,6 +673,8 @@ inline int SE_find_nearest_node(const Grid& g, double x, double z, double* dist 
 // materials
 struct MatInput {  // matpro_input_type (prop_mat.f90:21-25) for ELAST (+KV)
   bool elastic = false, isotropic = false, homogeneous = false, kv = false;
+  bool plastic = false;                    // kind='PLAST' (mat_plastic.f90)
+  double phi = 0, coh = 0, Tv = 0, e0[3] = {0, 0, 0};
   Dist rho, cp, cs, eta;
   double lambda = 0, mu = 0;  // set if homogeneous (mat_elastic.f90:118-125)
   bool has_lambda = false;
@@ -870,6 +872,13 @@ struct Problem {  // problem_type (problem_class.f90:19-46)
   std::vector<int> kv_elem;       // 1-based element ids with KV
   std::vector<int> elem2kv;       // (nelem) 0 or 1-based index into kv list
   std::vector<double> kv_eta;     // (ngll,ngll,nkv) already multiplied by dt if ETAxDT
+  // Coulomb plasticity (matwrk_plast_type, mat_plastic.f90:10-19) + derint (mat_gen.f90:46-49), per plastic element
+  std::vector<int> elem2pl;       // (nelem) 0 or 1-based index into the plastic element list
+  std::vector<int> pl_elem;       // 1-based element ids
+  std::vector<double> pl_par;     // (10,npl): lambda, mu, yield_co, yield_mu, vp_factor, e0(3), (unused 2)
+  std::vector<double> pl_ep;      // (ngll,ngll,3,npl) plastic strain
+  std::vector<double> pl_derint;  // (ngll,ngll,5,npl): dxi_dx, dxi_dy, deta_dx, deta_dy, weights
+  std::vector<double> pl_beta;    // (ngll,ngll,npl) when W is finite
   std::vector<double> rmass;      // (npoin,ndof) -- mass until init end, then inverse
   std::vector<double> mass;       // (npoin) assembled mass as MAT_MASS_init leaves it (mat_mass.f90:50-57), before BC_init
   std::vector<double> d, v, a_;   // fields (npoin,ndof) col-major
@@ -962,6 +971,13 @@ inline void MAT_init_prop(Problem& pb, int N_for_lattice /*ngll*/) {
         for (int k = 0; k < n2; ++k) tmp[k] = rho[k] * cs[k] * cs[k];
         m.mu[e - 1] = m.set_vals(tmp.data());
       }
+    }
+    if (in.plastic) {  // MAT_PLAST_init_elem_prop (mat_plastic.f90:121-145): scalar properties
+      m.cp[e - 1] = set_from_input(in.cp);
+      m.cs[e - 1] = set_from_input(in.cs);
+      const double rho1 = in.rho.c, cp1 = in.cp.c, cs1 = in.cs.c;
+      m.lambda[e - 1].homo = rho1 * (cp1 * cp1 - 2.0 * cs1 * cs1);
+      m.mu[e - 1].homo = rho1 * cs1 * cs1;
     }
     if (in.kv) m.eta[e - 1] = set_from_input(in.eta);
   }
@@ -1083,8 +1099,50 @@ inline void MAT_init_work(Problem& pb, bool force_general_nelast = false) {
   pb.kv_eta.clear();
   pb.ncoefsets = 0;
   std::vector<double> abuf((size_t)n2 * pb.nelast), eta(n2);
+  pb.elem2pl.assign(ne, 0);
+  pb.pl_elem.clear();
+  pb.pl_par.clear();
+  pb.pl_ep.clear();
+  pb.pl_derint.clear();
+  pb.pl_beta.clear();
   for (int e = 1; e <= ne; ++e) {
     const MatInput& in = pb.mat.inputs[g.tag[e - 1] - 1];
+    if (in.plastic) {  // mat_gen.f90:367-372: MAT_set_derint (:645-681) + MAT_PLAST_init_elem_work (mat_plastic.f90:148-218)
+      if (pb.ndof != 2) IO_abort("MAT_init_work: plasticity requires ndof=2 (P-SV) ");
+      if (in.kv) IO_abort("oracle: PLAST with KV not supported");
+      pb.pl_elem.push_back(e);
+      pb.elem2pl[e - 1] = (int)pb.pl_elem.size();
+      const size_t o = pb.pl_derint.size();
+      pb.pl_derint.resize(o + (size_t)5 * n2);
+      for (int j = 1; j <= n; ++j)
+        for (int i = 1; i <= n; ++i) {
+          const int k = (i - 1) + n * (j - 1);
+          double jac[4], inv[4];
+          SE_Jacobian(g, e, i, j, jac);
+          invert2(jac, inv);  // SE_InverseJacobian: xjaci(1,1)=dxi_dx, (1,2)=dxi_dy, (2,1)=deta_dx, (2,2)=deta_dy
+          pb.pl_derint[o + k] = inv[0];
+          pb.pl_derint[o + n2 + k] = inv[2];
+          pb.pl_derint[o + 2 * (size_t)n2 + k] = inv[1];
+          pb.pl_derint[o + 3 * (size_t)n2 + k] = inv[3];
+          pb.pl_derint[o + 4 * (size_t)n2 + k] = SE_VolumeWeight(g, e, i, j);
+        }
+      const double lam = pb.mat.lambda[e - 1].homo, mu1 = pb.mat.mu[e - 1].homo;
+      const double phi = PI / 180.0 * in.phi;
+      double par[10] = {lam, mu1, in.coh * std::cos(phi), std::sin(phi), in.Tv > 0.0 ? 1.0 - std::exp(-pb.time.dt / in.Tv) : 1.0,
+                        in.e0[0], in.e0[1], in.e0[2], 0.0, 0.0};
+      pb.pl_par.insert(pb.pl_par.end(), par, par + 10);
+      pb.pl_ep.resize(pb.pl_ep.size() + (size_t)3 * n2, 0.0);
+      if (w25d) {  // MAT_PLAST_init_25D (mat_plastic.f90:221-241)
+        for (int j = 1; j <= n; ++j)
+          for (int i = 1; i <= n; ++i) {
+            const double dvol = SE_VolumeWeight(g, e, i, j);
+            const double nu = lam / (lam + mu1) / 2.0;
+            const double t = 4.0 * std::atan(1.0) * (1 - nu) / g.W;
+            pb.pl_beta.push_back(dvol * mu1 * (t * t));
+          }
+      }
+      continue;
+    }
     if (in.kv) {  // mat_kelvin_voigt.f90:117-135
       pb.mat.get(pb.mat.eta, e, eta.data());
       if (in.etaxdt)
@@ -2138,6 +2196,71 @@ inline void compute_Fint(Problem& pb, std::vector<double>& f, const std::vector<
         dloc[k + (size_t)n2 * c] = d[(size_t)(ib[k] - 1) + np * c];
         vloc[k + (size_t)n2 * c] = v[(size_t)(ib[k] - 1) + np * c];
       }
+    if (!pb.elem2pl.empty() && pb.elem2pl[e - 1] > 0) {
+      // mat_gen.f90:445-449: e = MAT_strain(d), MAT_PLAST_stress(update = true), f = MAT_forces(s) (, 2.5D term)
+      const int ip = pb.elem2pl[e - 1] - 1;
+      const double* D = &pb.pl_derint[(size_t)5 * n2 * ip];
+      const double *dxi_dx = D, *dxi_dy = D + n2, *deta_dx = D + 2 * n2, *deta_dy = D + 3 * n2, *wts = D + 4 * n2;
+      const double* par = &pb.pl_par[(size_t)10 * ip];
+      double* ep = &pb.pl_ep[(size_t)3 * n2 * ip];
+      std::vector<double> gx1(n2), gx2(n2), ge1(n2), ge2(n2), st((size_t)3 * n2), t1(n2), t2(n2), m1(n2), m2(n2);
+      // MAT_strain_PSV (mat_gen.f90:752-775)
+      mxm(g.Ht.data(), dloc.data(), gx1.data(), n);
+      mxm(g.Ht.data(), dloc.data() + n2, gx2.data(), n);
+      mxm(dloc.data(), g.H.data(), ge1.data(), n);
+      mxm(dloc.data() + n2, g.H.data(), ge2.data(), n);
+      const double lambda = par[0], two_mu = 2.0 * par[1];
+      const double s0[3] = {(lambda + two_mu) * par[5] + lambda * par[6], lambda * par[5] + (lambda + two_mu) * par[6],
+                            two_mu * par[7]};  // mat_plastic.f90:199-204
+      for (int k = 0; k < n2; ++k) {
+        const double et1 = gx1[k] * dxi_dx[k] + ge1[k] * deta_dx[k];
+        const double et2 = gx2[k] * dxi_dy[k] + ge2[k] * deta_dy[k];
+        const double et3 = 0.5 * (gx1[k] * dxi_dy[k] + ge1[k] * deta_dy[k] + gx2[k] * dxi_dx[k] + ge2[k] * deta_dx[k]);
+        // MAT_PLAST_stress (mat_plastic.f90:281-387), update = .true.
+        double e1 = et1 - ep[k], e2 = et2 - ep[n2 + k], e3 = et3 - ep[2 * n2 + k];
+        e1 = e1 + par[5];
+        e2 = e2 + par[6];
+        e3 = e3 + par[7];
+        double s1 = (lambda + two_mu) * e1 + lambda * e2;
+        double s2 = lambda * e1 + (lambda + two_mu) * e2;
+        double s3 = two_mu * e3;
+        const double tau = std::sqrt(0.25 * ((s1 - s2) * (s1 - s2)) + s3 * s3);
+        const double sm = 0.5 * (s1 + s2);
+        const double Y = par[2] - par[3] * sm;
+        const double sdt1 = s1 - sm, sdt2 = s2 - sm, sdt3 = s3;
+        const double factor = 1.0 - std::max(1.0 - Y / tau, 0.0) * par[4];
+        const double sd1 = factor * sdt1, sd2 = factor * sdt2, sd3 = factor * sdt3;
+        ep[k] = ep[k] + (sdt1 - sd1) / two_mu;
+        ep[n2 + k] = ep[n2 + k] + (sdt2 - sd2) / two_mu;
+        ep[2 * n2 + k] = ep[2 * n2 + k] + (sdt3 - sd3) / two_mu;
+        s1 = sd1 + sm;
+        s2 = sd2 + sm;
+        s3 = sd3;
+        st[k] = s1 - s0[0];
+        st[n2 + k] = s2 - s0[1];
+        st[2 * n2 + k] = s3 - s0[2];
+      }
+      // MAT_forces (mat_gen.f90:834-866)
+      for (int c = 0; c < 2; ++c) {
+        const double* sa = c == 0 ? &st[0] : &st[2 * n2];
+        const double* sb = c == 0 ? &st[2 * n2] : &st[n2];
+        for (int k = 0; k < n2; ++k) {
+          t1[k] = -wts[k] * (dxi_dx[k] * sa[k] + dxi_dy[k] * sb[k]);
+          t2[k] = -wts[k] * (deta_dx[k] * sa[k] + deta_dy[k] * sb[k]);
+        }
+        mxm(g.H.data(), t1.data(), m1.data(), n);
+        mxm(t2.data(), g.Ht.data(), m2.data(), n);
+        for (int k = 0; k < n2; ++k) floc[k + (size_t)n2 * c] = m1[k] + m2[k];
+      }
+      if (!pb.pl_beta.empty()) {  // MAT_PLAST_add_25D_f (mat_plastic.f90:262-274)
+        const double* beta = &pb.pl_beta[(size_t)n2 * ip];
+        for (int c = 0; c < ndof; ++c)
+          for (int k = 0; k < n2; ++k) floc[k + (size_t)n2 * c] = floc[k + (size_t)n2 * c] - beta[k] * dloc[k + (size_t)n2 * c];
+      }
+      for (int c = 0; c < ndof; ++c)
+        for (int k = 0; k < n2; ++k) f[(size_t)(ib[k] - 1) + np * c] = f[(size_t)(ib[k] - 1) + np * c] + floc[k + (size_t)n2 * c];
+      continue;
+    }
     int ikv = pb.elem2kv[e - 1];
     if (ikv > 0) {  // MAT_KV_add_etav (mat_kelvin_voigt.f90:137-150)
       const double* eta = &pb.kv_eta[(size_t)n2 * (ikv - 1)];
@@ -2375,6 +2498,10 @@ inline void snapshot_elem(const Problem& pb, char what, std::vector<float>& out)
             ev[1] = dxi[k + n2] * dxi_dz + deta[k + n2] * deta_dz;
             ev[2] = 0.5 * (dxi[k] * dxi_dz + deta[k] * deta_dz + dxi[k + n2] * dxi_dx + deta[k + n2] * deta_dx);
           }
+          if (what == 'S' && !pb.elem2pl.empty() && pb.elem2pl[e - 1] > 0) {  // MAT_PLAST_stress, update = .false. (mat_plastic.f90:294,379-383)
+            const double* ep = &pb.pl_ep[(size_t)3 * n2 * (pb.elem2pl[e - 1] - 1)];
+            for (int c = 0; c < 3; ++c) ev[c] = ev[c] - ep[(size_t)c * n2 + k];
+          }
           if (what == 'S') {
             if (ndof == 1) {
               ev[0] = 2.0 * mu[k] * ev[0];
@@ -2587,6 +2714,18 @@ inline void read_main(Problem& pb, CartSpec& cart, ParInp& in) {
           mi.kv = true;
           mi.eta = read_cd(in, gk->dbl("eta", 0.0), gk->str("etaH", ""));
           mi.etaxdt = gk->logical("ETAxDT", true);
+        } else if (kinds[k] == "PLAST") {  // MAT_PLAST_read (mat_plastic.f90:66-118)
+          const NmlGroup* gp = in.next("MAT_PLASTIC");
+          if (!gp) IO_abort("MAT_PLAST_read: MAT_PLASTIC input block not found");
+          mi.plastic = true;
+          mi.isotropic = true;
+          mi.rho = read_cd(in, gp->dbl("rho", 0.0), "");
+          mi.cp = read_cd(in, gp->dbl("cp", 0.0), "");
+          mi.cs = read_cd(in, gp->dbl("cs", 0.0), "");
+          mi.phi = gp->dbl("phi", 0.0);
+          mi.coh = gp->dbl("coh", 0.0);
+          mi.Tv = gp->dbl("Tv", 0.0);
+          for (int q = 0; q < 3; ++q) mi.e0[q] = gp->dbl("e0", 0.0, q);
         } else if (kinds[k] == "") {
         } else {
           IO_abort("oracle: material kind not supported: " + kinds[k]);

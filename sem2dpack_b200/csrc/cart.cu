@@ -348,8 +348,8 @@ struct SnapH {
 };
 template <typename T>
 __global__ void k_cart_snap(CartGeom G, SnapH Hm, const T* __restrict__ d, const T* __restrict__ v,
-                            const T* __restrict__ eta_strip, size_t nlat, int what, const int* __restrict__ perm,
-                            float* __restrict__ out) {
+                            const T* __restrict__ eta_strip, const T* __restrict__ ep_strip, size_t nlat, int what,
+                            const int* __restrict__ perm, float* __restrict__ out) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int N = G.N, N2 = N * N, ndof = G.ndof;
   const long long nelem = (long long)G.nx * G.nz;
@@ -385,6 +385,9 @@ __global__ void k_cart_snap(CartGeom G, SnapH Hm, const T* __restrict__ d, const
       ev[0] = dxi[0] * dxi_dx;
       ev[1] = deta[1] * deta_dz;
       ev[2] = 0.5 * (deta[0] * deta_dz + dxi[1] * dxi_dx);
+    }
+    if (what == 'S' && ep_strip != nullptr) {  // MAT_PLAST_stress without update: the relative elastic strain e - ep
+      for (int c = 0; c < 3; ++c) ev[c] = ev[c] - (double)ep_strip[strip_ep_index(G.S, ix, iz, i, j, c)];
     }
     if (what == 'S') {
       double rho, cp, cs;
@@ -857,6 +860,36 @@ int s2d_cart_set_kv_elems(s2d_handle h, int32_t nkv, const int32_t* elem_ids, co
       for (int i = 0; i < N; ++i) pe[strip_scalar_index(G.S, ix, iz, i, j)] = eta[(size_t)k * n2 + i + N * j];
   }
   Eb->set_strip_eta(pe.data(), pe.size());
+  CART_GUARD_END
+}
+
+int s2d_cart_set_plastic(s2d_handle h, int32_t nsets, const double* par, const int32_t* elem_set) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(nsets >= 1 && par && elem_set, "cart_set_plastic: bad arguments");
+  S2D_REQUIRE(!Eb->committed, "cart_set_plastic after commit");
+  const CartGeom& G = S.G;
+  std::vector<unsigned char> ps((size_t)Eb->nelem, 0);
+  for (int e = 0; e < Eb->nelem; ++e) {
+    S2D_REQUIRE(elem_set[e] >= 0 && elem_set[e] <= nsets, "cart_set_plastic: material set out of range");
+    ps[strip_elem_slot(G.S, e % G.nx, e / G.nx)] = (unsigned char)elem_set[e];
+  }
+  Eb->set_strip_plastic(ps.data(), ps.size(), nsets, par);
+  CART_GUARD_END
+}
+
+int s2d_cart_get_plastic_strain(s2d_handle h, double* ep) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(ep, "cart_get_plastic_strain: null output");
+  const CartGeom& G = S.G;
+  const int N = G.N, n2 = N * N;
+  std::vector<double> st((size_t)Eb->nelem * 3 * n2);
+  Eb->get_strip_plastic_strain(st.data());
+  for (int e = 0; e < Eb->nelem; ++e) {
+    const int ix = e % G.nx, iz = e / G.nx;
+    for (int k = 0; k < 3; ++k)
+      for (int j = 0; j < N; ++j)
+        for (int i = 0; i < N; ++i) ep[(size_t)e * 3 * n2 + (size_t)k * n2 + i + N * j] = st[strip_ep_index(G.S, ix, iz, i, j, k)];
+  }
   CART_GUARD_END
 }
 
@@ -1538,7 +1571,7 @@ static void cart_snapshot(Engine<T>& E, CartState& S, char what, float* out) {
   const long long tot = (long long)E.nelem * N2;
   S2D_CUDA(cudaStreamSynchronize(E.stream));
   k_cart_snap<T><<<(unsigned)((tot + 127) / 128), 128, 0, E.stream>>>(G, Hm, E.dbuf().p, E.v.p, E.strip_eta.n ? E.strip_eta.p : nullptr,
-                                                                       E.npoin, (int)what, S.renumber ? dperm.p : nullptr, buf.p);
+                                                                       E.pl_ep.n ? E.pl_ep.p : nullptr, E.npoin, (int)what, S.renumber ? dperm.p : nullptr, buf.p);
   S2D_CUDA(cudaGetLastError());
   S2D_CUDA(cudaStreamSynchronize(E.stream));
   buf.download(out);

@@ -89,6 +89,8 @@ class EngineBase {
   virtual void add_receivers_nodes(int nx, char field, int isamp, int nt_rec, const int32_t* nodes, const double* interp) = 0;
   virtual void set_node_kv(const double* eta_ref) = 0;
   virtual void set_strip_eta(const double* eta_strip, size_t n) = 0;
+  virtual void set_strip_plastic(const unsigned char* set_strip, size_t n, int nsets, const double* raw) = 0;
+  virtual void get_strip_plastic_strain(double* ep_strip) = 0;
   virtual void commit(int variant) = 0;
   virtual void set_fields(const double* d, const double* v, const double* a) = 0;
   virtual void get_fields(double* d, double* v, double* a) = 0;
@@ -322,6 +324,12 @@ class Engine : public EngineBase {
     io.cdet = cart_cdet;
     io.wgll = cart_wgll.empty() ? nullptr : cart_wgll.data();
     io.beta = strip_beta.p;
+    if (pl_set.n) {
+      io.pl_set = pl_set.p;
+      io.pl_ep = pl_ep.p;
+      for (int k = 0; k < STRIP_PL_SETS; ++k)
+        for (int q = 0; q < 6; ++q) io.pl_par[k][q] = pl_par[k][q];
+    }
     return io;
   }
   // strip kernel over the whole box (+ halo fold, + interface exchange); io.v_in != null = fused update
@@ -855,6 +863,25 @@ class Engine : public EngineBase {
   }
 
   // eta per element GLL point, already in the strip layout (s2d_cart_set_kv_elems)
+  void set_strip_plastic(const unsigned char* set_strip, size_t n, int nsets, const double* raw) override {
+    S2D_REQUIRE(cart_mode && !committed, "set_strip_plastic: builder-made engines only, before commit");
+    S2D_REQUIRE(n == (size_t)nelem && nsets >= 1 && nsets < STRIP_PL_SETS, "set_strip_plastic: 1..7 plastic material sets");
+    S2D_REQUIRE(ndof == 2 && cart_compact && ngll <= STRIP_PLAST_MAXN,
+                "MAT_init_work: plasticity requires ndof=2 (P-SV), an isotropic box and ngll <= 6");
+    pl_set.alloc(n);
+    h2d_sync(pl_set.p, set_strip, n);
+    pl_ep.alloc((size_t)nelem * 3 * ngll * ngll);
+    pl_ep.zero();
+    for (int k = 0; k < nsets; ++k)
+      for (int q = 0; q < 6; ++q) pl_raw[k + 1][q] = raw[(size_t)6 * k + q];
+  }
+  void get_strip_plastic_strain(double* ep_strip) override {
+    S2D_REQUIRE(pl_ep.n > 0, "no plastic elements");
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    std::vector<T> tmp = pl_ep.to_host();
+    for (size_t q = 0; q < tmp.size(); ++q) ep_strip[q] = (double)tmp[q];
+  }
+
   void set_strip_eta(const double* eta_strip, size_t n) override {
     S2D_REQUIRE(cart_mode && !committed, "set_strip_eta: builder-made engines only, before commit");
     upload_as(strip_eta, eta_strip, n);
@@ -1086,6 +1113,11 @@ class Engine : public EngineBase {
   std::vector<double> h_eta;
   DevBuf<T> strip_eta;                 // Kelvin-Voigt eta per element GLL point in the strip layout (zero off the KV elements)
   DevBuf<T> v_alt, a_alt;              // second velocity / acceleration buffers of the fused Kelvin-Voigt step
+  // Coulomb plasticity (mat_plastic.f90): material set per element (strip order), plastic strain per element GLL
+  // point, per set (coh, phi [deg], Tv, e0(3)) as read and (yield_co, yield_mu, vp_factor, e0(3)) as the kernel uses them
+  DevBuf<unsigned char> pl_set;
+  DevBuf<T> pl_ep;
+  double pl_raw[STRIP_PL_SETS][6] = {}, pl_par[STRIP_PL_SETS][6] = {};
   static bool strip_kv_ok() { return true; }   // k_elem_strip<KV>: d + eta*v element by element
 
   // ---- planning ------------------------------------------------------------------------
@@ -1252,6 +1284,16 @@ class Engine : public EngineBase {
         k_strip_eta_from_nodes<T><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(cart_S, cart_kv_eta.p, strip_eta.p);
         S2D_CUDA(cudaStreamSynchronize(stream));
         cart_kv_eta.release();
+      }
+      if (pl_set.n) {  // MAT_PLAST_init_elem_work (mat_plastic.f90:165-184); set 0 (elastic elements) never yields
+        S2D_REQUIRE(strip_eta.n == 0, "plastic elements together with Kelvin-Voigt elements: not provided");
+        for (int k = 1; k < STRIP_PL_SETS; ++k) {
+          const double phi = 3.141592653589793 / 180.0 * pl_raw[k][1];
+          pl_par[k][0] = pl_raw[k][0] * std::cos(phi);
+          pl_par[k][1] = std::sin(phi);
+          pl_par[k][2] = pl_raw[k][2] > 0.0 ? 1.0 - std::exp(-scheme.dt / pl_raw[k][2]) : 1.0;
+          for (int q = 3; q < 6; ++q) pl_par[k][q] = pl_raw[k][q];
+        }
       }
       // the node update rides in the strip kernel for leapfrog and for the explicit Newmark scheme (beta = 0)
       fused = (scheme.kind == 0 || (scheme.kind == 1 && scheme.beta == 0.0)) && env_int("S2D_FUSED", 1) != 0;

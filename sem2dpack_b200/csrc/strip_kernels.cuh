@@ -203,6 +203,20 @@ template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 
+constexpr int STRIP_PL_SETS = 8;  // plastic material sets per problem (set 0 = elastic elements)
+// position of plastic-strain component k at GLL point (i,j) of element (ix,iz)
+__host__ __device__ inline size_t strip_ep_index(const StripGeom& G, int ix, int iz, int i, int j, int k) {
+  const int N = G.N;
+  const int seg = strip_seg_of(G, iz), strip = ix / G.EPW;
+  const int ex0 = strip * G.EPW, el = ix - ex0;
+  const int cx = min(G.EPW, G.nx - ex0);
+  return (size_t)strip_elem_off(G, seg, strip, iz) * 3 * N * N + (size_t)(k * N + j) * (cx * N) + el * N + i;
+}
+__host__ __device__ inline size_t strip_elem_slot(const StripGeom& G, int ix, int iz) {
+  const int strip = ix / G.EPW;
+  return (size_t)strip_elem_off(G, strip_seg_of(G, iz), strip, iz) + (ix - strip * G.EPW);
+}
+
 template <typename T, int N>
 struct StripArgs {
   // TMA tensor maps of the lattice fields (TENS variant of the kernel): d[n] (LXP, LZ, ndof), v likewise, rmass
@@ -239,6 +253,12 @@ struct StripArgs {
   // 2.5D term of MAT_ELAST_add_25D_f (mat_elastic.f90:447-459, mat_gen.f90:440): f = f - beta*d element by element,
   // beta per GLL point of every element in the strip layout (strip_scalar_index), or nullptr
   const T* beta;
+  // Coulomb plasticity (MAT_PLAST_stress, mat_plastic.f90:281-387; PLAST instantiation): material set of every
+  // element in strip order (strip_elem_off + el; 0 = elastic), plastic strain per element GLL point
+  // ([strain component][j][lane] per element row of a strip), per-set yield_co, yield_mu, vp_factor, e0(3)
+  const unsigned char* pl_set;
+  T* pl_ep;
+  T pl_par[STRIP_PL_SETS][6];
   int prefetch;             // L2 prefetch of what is not staged
   T H[N * N];               // hprime, column-major (constant bank)
   // compact coefficient mode (isotropic flat grids): only (lambda, mu) are stored per GLL point and
@@ -401,9 +421,11 @@ constexpr int strip_min_ctas_kv(int N, int tsize, int ndof) {
 }
 
 template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false,
-          bool TENS = false>
+          bool TENS = false, bool PLAST = false>
 __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     k_elem_strip(const __grid_constant__ StripArgs<T, N> A) {
+  static_assert(!PLAST || (COMPACT && NDOF == 2 && !KV && !TENS && S2D_COMPACT_FOLD != 0),
+                "plasticity: P-SV, (lambda, mu) coefficient stream, folded metric");
   static_assert(!TENS || (FUSED >= 1 && !KV), "tensor-map staging: fused leapfrog / explicit Newmark step");
   static_assert(!COMPACT || NDOF == 2, "compact coefficients: P-SV only");
   static_assert(!KV || !TENS, "Kelvin-Voigt elements: per-lane staging only");
@@ -549,6 +571,8 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     }
   }
   const T* etap = KV ? A.eta + (size_t)strip_elem_off(G, seg, strip, ez0) * (N * N) + lanep : nullptr;
+  T* epp = PLAST ? A.pl_ep + (size_t)strip_elem_off(G, seg, strip, ez0) * (3 * N * N) + lanep : nullptr;
+  const unsigned char* plp = PLAST ? A.pl_set + strip_elem_off(G, seg, strip, ez0) + el : nullptr;
   const int cxN = cx * N;
   const V2* cp = reinterpret_cast<const V2*>(A.coef) +
                  (size_t)strip_elem_off(G, seg, strip, ez0) * (NPL * N * N / 2) + lanep;
@@ -668,6 +692,20 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       // copies of what the end of this iteration needs (v, rmass) and of the whole next row
       stage_wait<0>();
       V2 a2[NPL / 2][N];
+      // plasticity: the element's plastic strain and material set, requested before anything else of this row
+      T epr[PLAST ? 3 : 1][PLAST ? N : 1], ppar[PLAST ? 6 : 1];
+      if constexpr (PLAST) {
+        // shadow lanes (el >= cx) mirror the last element -- they write the same tile slots, so they must see
+        // the same state; only real lanes store it back
+        const int pset = (int)*plp;
+        plp += gcx;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int j = 0; j < N; ++j) epr[k][j] = __ldcs(epp + (size_t)(k * N + j) * cxN);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ppar[q] = A.pl_par[pset][q];
+      }
       if constexpr (TENS) {
         const int kk = ez - ez0;
         mbar_wait_or_trap(&tbarA[kk & 1], (unsigned)((kk >> 1) & 1));
@@ -838,6 +876,38 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       T tH[NDOF][N], tHt[NDOF][N];
 #pragma unroll
       for (int j = 0; j < N; ++j) {
+        if constexpr (PLAST) {
+          // MAT_strain_PSV (mat_gen.f90:752-775) on the flat box: e11 = Ux,x  e22 = Uz,z  e12 = (Ux,z + Uz,x)/2;
+          // MAT_PLAST_stress with update (mat_plastic.f90:297-377): trial stress from the absolute elastic strain,
+          // visco-plastic return of the deviatoric part towards the Coulomb yield stress (Andrews 2005), plastic
+          // strain advanced, stress relative to the initial one; MAT_forces (mat_gen.f90:851-860) with the metric
+          // factors carried by the second contractions
+          const T la = a2[0][j].x, two_mu = T(2) * a2[0][j].y;
+          const T px = gxi[0][j], pz = gxi[1][j], qx = get[0][j], qz = get[1][j];
+          const T e1 = (px - epr[0][j]) + ppar[3];
+          const T e2 = (qz - epr[1][j]) + ppar[4];
+          const T e3 = (T(0.5) * (qx + pz) - epr[2][j]) + ppar[5];
+          T s1 = (la + two_mu) * e1 + la * e2;
+          T s2 = la * e1 + (la + two_mu) * e2;
+          T s3 = two_mu * e3;
+          const T tau = sqrt(T(0.25) * ((s1 - s2) * (s1 - s2)) + s3 * s3);
+          const T sm = T(0.5) * (s1 + s2);
+          const T Y = ppar[0] - ppar[1] * sm;
+          const T t1 = s1 - sm, t2 = s2 - sm, t3 = s3;
+          const T factor = T(1) - fmax(T(1) - Y / tau, T(0)) * ppar[2];
+          const T d1 = factor * t1, d2 = factor * t2, d3 = factor * t3;
+          epr[0][j] = epr[0][j] + (t1 - d1) / two_mu;
+          epr[1][j] = epr[1][j] + (t2 - d2) / two_mu;
+          epr[2][j] = epr[2][j] + (t3 - d3) / two_mu;
+          s1 = (d1 + sm) - ((la + two_mu) * ppar[3] + la * ppar[4]);
+          s2 = (d2 + sm) - (la * ppar[3] + (la + two_mu) * ppar[4]);
+          s3 = d3 - two_mu * ppar[5];
+          tH[0][j] = nW[j] * s1;
+          tHt[0][j] = nW[j] * s3;
+          tH[1][j] = nW[j] * s3;
+          tHt[1][j] = nW[j] * s2;
+          continue;
+        }
         if constexpr (FOLD) {
           // gxi carries DxiDx, get carries DetaDz; the second contractions carry the other factor of each plane:
           //   fx = (DxiDx H)(-w [Kx px + la qz]) + (-w mu [qx + DetaDz Uz,xi]) (DetaDz Ht)      (KD2: a4*(Ux,eta + Uz,xi),
@@ -882,6 +952,15 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           tH[c][j] = o1[c];
           tHt[c][j] = o2[c];
         }
+      }
+      if constexpr (PLAST) {
+        if (real) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int j = 0; j < N; ++j) epp[(size_t)(k * N + j) * cxN] = epr[k][j];
+        }
+        epp += (size_t)gcx * (3 * N * N);
       }
       // ---- second contractions: H tH through the tile, tHt Ht in registers
       if (!(S2D_ABLATE & 1)) {
@@ -1377,6 +1456,9 @@ struct StripIO {
   const T* a_in = nullptr;
   const T* eta = nullptr;   // Kelvin-Voigt: eta per element GLL point (strip layout) and the velocity field
   const T* v_kv = nullptr;
+  const unsigned char* pl_set = nullptr;  // Coulomb plasticity (see StripArgs)
+  T* pl_ep = nullptr;
+  double pl_par[STRIP_PL_SETS][6] = {};
   const T* beta = nullptr;  // 2.5D: beta per element GLL point (strip layout)
   // tensor-map staging of the fused leapfrog kernel (null: per-lane copies)
   const CUtensorMap* tm_d = nullptr;
@@ -1393,8 +1475,9 @@ struct StripIO {
 
 // largest ngll whose Kelvin-Voigt instantiation also carries the fused node update (compile time of the library)
 constexpr int STRIP_KV_FUSED_MAXN = 6;
+constexpr int STRIP_PLAST_MAXN = 6;  // plasticity instantiations
 template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false,
-          bool TENS = false>
+          bool TENS = false, bool PLAST = false>
 inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) {
   constexpr size_t smem = TENS ? strip_tens_smem(N, NDOF, sizeof(T), COMPACT, FUSED)
                                : strip_warps() * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT);
@@ -1405,11 +1488,11 @@ inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) 
   int dev = 0;
   S2D_CUDA(cudaGetDevice(&dev));
   if (!done[dev & 63]) {
-    S2D_CUDA(cudaFuncSetAttribute(k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV, TENS>,
+    S2D_CUDA(cudaFuncSetAttribute(k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV, TENS, PLAST>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done[dev & 63] = true;
   }
-  k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV, TENS><<<nb, strip_warps() * 32, smem, s>>>(A);
+  k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV, TENS, PLAST><<<nb, strip_warps() * 32, smem, s>>>(A);
 }
 
 // element-force launch over the groups selected by G.it_* (no halo fold)
@@ -1454,7 +1537,7 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
     const unsigned nb = (unsigned)G.nitems;                                                       \
     const int mode = !fused ? 0 : (io.newmark ? 2 : 1);                                           \
     if constexpr (NN <= 6) { /* CTA-wide tensor-map staging of the fused step (S2D_STRIP_TENSOR) */ \
-      if (mode >= 1 && io.tm_d && !io.eta) {                                                      \
+      if (mode >= 1 && io.tm_d && !io.eta && !io.pl_set) {                                                      \
         constexpr int MB = strip_min_ctas(NN, sizeof(T));                                         \
         A.tm_d = *io.tm_d;                                                                        \
         A.tm_v = *io.tm_v;                                                                        \
@@ -1472,6 +1555,21 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
         }                                                                                         \
         break;                                                                                    \
       }                                                                                           \
+    }                                                                                             \
+    if (io.pl_set) { /* Coulomb plasticity: state per element GLL point, 2 CTAs / SM */             \
+      if constexpr (NN <= STRIP_PLAST_MAXN) {                                                     \
+        if (!io.compact || G.ndof != 2 || io.eta) throw ArgError("plasticity: isotropic P-SV boxes without Kelvin-Voigt elements"); \
+        A.pl_set = io.pl_set;                                                                     \
+        A.pl_ep = io.pl_ep;                                                                       \
+        for (int k = 0; k < STRIP_PL_SETS; ++k)                                                   \
+          for (int q = 0; q < 6; ++q) A.pl_par[k][q] = (T)io.pl_par[k][q];                        \
+        constexpr int MP = sizeof(T) == 8 ? 2 : 3;                                                \
+        if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, true>(nb, A, s);         \
+        else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, true>(nb, A, s);    \
+        else strip_launch<T, NN, 2, 0, true, MP, false, false, true>(nb, A, s);                   \
+        break;                                                                                    \
+      }                                                                                           \
+      throw ArgError("plasticity: ngll <= 6 only");                                               \
     }                                                                                             \
     if (io.eta) { /* Kelvin-Voigt elements: plain force evaluation from d + eta*v */               \
       constexpr int MB = strip_min_ctas_kv(NN, sizeof(T), 1), M2 = strip_min_ctas_kv(NN, sizeof(T), 2);  \

@@ -363,6 +363,19 @@ class CartEngine(Engine):
         elem_ids = _i32(elem_ids)
         self._ck(self.L.s2d_cart_set_kv_elems(self.h, elem_ids.size, _ptr(elem_ids), _ptr(_f64(eta))))
 
+    def set_plastic(self, par, elem_set):
+        """par (nsets, 6) = coh, phi [deg], Tv, e0(3) per plastic material; elem_set (nelem) natural order, 0 = elastic
+        (s2d_cart_set_plastic)"""
+        par = _f64(par).reshape(-1, 6)
+        elem_set = _i32(elem_set)
+        self._ck(self.L.s2d_cart_set_plastic(self.h, par.shape[0], _ptr(par), _ptr(elem_set)))
+
+    def plastic_strain(self):
+        """ep (nelem, 3, ngll, ngll), natural element order (s2d_cart_get_plastic_strain)"""
+        out = np.empty((self.nelem, 3, self.ngll, self.ngll))
+        self._ck(self.L.s2d_cart_get_plastic_strain(self.h, _ptr(out)))
+        return out
+
     def set_w25d(self, W):
         """&GENERAL W: finite seismogenic width (s2d_cart_set_w25d)"""
         self._ck(self.L.s2d_cart_set_w25d(self.h, float(W)))

@@ -321,3 +321,43 @@ def test_snapshot_elem_fields(ndof):
         assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max(), what
     e.close()
     o.close()
+
+
+@pytest.mark.parametrize("ngll,nx,nz,ezflt,seg", [(5, 27, 11, 0, 3), (5, 50, 12, 5, 2), (6, 23, 10, 3, 3), (4, 9, 7, 0, 32),
+                                                  (3, 47, 8, 4, 5)])
+def test_plastic_force_evaluations_and_plastic_strain(ngll, nx, nz, ezflt, seg, monkeypatch):
+    """Coulomb plasticity in the strip kernel (s2d_cart_set_plastic): MAT_strain_PSV -> MAT_PLAST_stress(update) ->
+    MAT_forces (mat_gen.f90:445-449,752-775,834-866; mat_plastic.f90:281-387).  Three successive force evaluations on
+    growing random displacements -- each advances the plastic strain of every element GLL point -- against the
+    oracle: forces after each, the plastic strain at the end, over strip / band decompositions with every halo case."""
+    monkeypatch.setenv("S2D_SEG", str(seg))
+    h = 100.0
+    coh, phi, Tv, e0 = 2.0e6, 30.0, 0.02, (-4.0e-4, -3.0e-4, 2.5e-4)
+    L = [f"&GENERAL iexec=1, ngll={ngll}, fmax=3.d0, ndof=2, title='plastic', verbose='0000', ItInfo=1000 /",
+         "&MESH_DEF method='CARTESIAN' /",
+         f"&MESH_CART xlim=0d0,{nx*h}d0, zlim=0d0,{nz*h}d0, nelem={nx},{nz}" + (f", ezflt={ezflt}" if ezflt else "") + " /",
+         "&MATERIAL tag=1, kind='PLAST' /",
+         f"&MAT_PLASTIC rho=2670.d0, cp=6000.d0, cs=3464.d0, phi={phi}d0, coh={coh}d0, Tv={Tv}d0, e0={e0[0]}d0,{e0[1]}d0,{e0[2]}d0 /",
+         "&TIME NbSteps=10, courant=0.5d0, kind='leapfrog' /"]
+    o = orc.Oracle("\n".join(L) + "\n", renumber=False)
+    assert o.i("npl") == nx * nz
+    e = CartEngine(ngll, 2, nx, nz, (0.0, nx * h), (0.0, nz * h), ezflt=ezflt, seed=0, rho=2670.0, cp=6000.0, cs=3464.0)
+    assert e.npoin == o.i("npoin") and abs(e.dt - o.f("dt")) <= 1e-12 * e.dt
+    e.set_dt(o.f("dt"))     # vp_factor = 1 - exp(-dt/Tv) from the same dt
+    e.set_plastic([[coh, phi, Tv, *e0]], np.ones(nx * nz, np.int32))
+    e.commit()
+    rng = np.random.default_rng(ngll * 100 + nx)
+    base = rng.standard_normal(e.npoin * 2)
+    for amp in (1e-3, 3e-2, 1e-1):   # metres over 100 m elements: from barely yielding to deep in the plastic range
+        d = amp * base
+        e.set_fields(d, d)
+        o.set_fields(d, d)
+        ref = o.compute_fint()
+        got = e.compute_fint()
+        assert rel_l2(got, ref) <= 1e-12, (amp, rel_l2(got, ref))
+    ep_ref = o.arr("pl_ep").reshape(nx * nz, 3, ngll, ngll)
+    ep = e.plastic_strain()
+    assert np.abs(ep_ref).max() > 1e-5
+    assert np.abs(ep - ep_ref).max() <= 1e-12 * np.abs(ep_ref).max()
+    e.close()
+    o.close()

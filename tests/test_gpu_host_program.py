@@ -353,3 +353,46 @@ def test_energy_table(tmp_path):
         assert abs(tab[k, 4] - ew) <= 1e-9 * max(ew, 1e-300), (k, tab[k, 4], ew)
     assert tab[-1, 2] > 0 and tab[-1, 4] > 0
     o.close()
+
+
+def read_snapshot(tmp_path, name, it, nelem, ngll):
+    f = tmp_path / f"{name}_{it:03d}_sem2d.dat"
+    return np.fromfile(f, dtype=np.float32)
+
+
+@pytest.mark.parametrize("nsteps,coh", [(400, "9.669501d6"), (250, "4.0d6")])
+def test_plastic_deck_coulomb_yielding_off_the_fault(tmp_path, nsteps, coh):
+    """EXAMPLES/2.5D_plastic (kind='PLAST', W = 10 km, SWF + TWF fault, ABSORB x3 + DIRNEU, leapfrog), coarsened
+    to 48 x 48 elements: MAT_Fint's strain -> MAT_PLAST_stress(update) -> MAT_forces branch (mat_gen.f90:445-449,
+    mat_plastic.f90:281-387) runs inside the strip kernel with the plastic strain of every element GLL point resident
+    in HBM.  Fields (snapshots D, V), the stress snapshot (relative stress from e - ep) and the fault records against
+    the oracle; the second case lowers the cohesion so that the medium yields from the first steps.
+    No reference artefact pins this deck (none ships): oracle parity."""
+    deck = harness.deck("plastic25d").replace("nelem=160,160", "nelem=48,48").replace("TotalTime=80", f"NbSteps={nsteps}")
+    deck = deck.replace("coh = 9.669501d6", f"coh = {coh}").replace("itd=1000", f"itd={nsteps}").replace("fields ='DVSE'", "fields ='DVS'")
+    assert f"NbSteps={nsteps}" in deck and f"coh = {coh}" in deck and f"itd={nsteps}" in deck
+    p = run(tmp_path, deck, "--quiet", "--natural-order")
+    assert p.returncode == 0, p.stdout + p.stderr
+    o = orc.Oracle(deck, renumber=False)
+    assert o.i("npl") == 48 * 48
+    o.step(nsteps)
+    ep = o.arr("pl_ep")
+    assert np.abs(ep).max() > 1e-6          # the medium has yielded
+    n = o.i("npoin")
+    for nm, key in (("d", "d"), ("v", "v")):
+        ref = o.arr(key).reshape(2, n)
+        for c, ax in enumerate("xz"):
+            got = np.fromfile(tmp_path / f"{nm}{ax}_001_sem2d.dat", dtype=np.float32)
+            assert got.size == n
+            assert np.abs(got - ref[c].astype(np.float32)).max() <= 2e-6 * np.abs(ref[c]).max(), (nm, ax)
+    sref = o.snapshot("S")                   # (3, nelem, ngll, ngll) float32, relative stress C:(e - ep)
+    for c, nm in enumerate(("s11", "s22", "s12")):
+        got = np.fromfile(tmp_path / f"{nm}_001_sem2d.dat", dtype=np.float32)
+        assert got.size == sref[c].size
+        assert np.abs(got - sref[c].ravel()).max() <= 5e-6 * np.abs(sref).max(), nm
+    x, rec = read_fault(tmp_path, 5)
+    want = o.arr("bc.0.out").reshape(-1, 6, rec.shape[2])
+    assert rec.shape == want.shape
+    for c in range(6):
+        assert np.abs(rec[:, c] - want[:, c]).max() <= 1e-6 * max(np.abs(want[:, c]).max(), 1e-30), c
+    o.close()
