@@ -312,10 +312,13 @@ REF_CONFIGS = {
     "ratestate": {"scale": 12, "nelem": (270, 90), "time": ("TotalTime=4d0", "NbSteps={nt}"),
                   "what": "EXAMPLES/RateState: SH, NGLL=5, one-sided rate-and-state fault (slip law), ABSORB + DIRNEU, "
                           "explicit Newmark"},
+    "plastic25d": {"scale": 16, "nelem": (160, 160), "time": ("TotalTime=80", "NbSteps={nt}"),
+                   "what": "EXAMPLES/2.5D_plastic: P-SV, NGLL=5, Coulomb plasticity at every GLL point (stateful rheology), "
+                           "W = 10 km, SWF + TWF fault, ABSORB x3 + DIRNEU, leapfrog"},
 }
 
 
-def config_bytes_per_dof(ngll, ndof, scheme, kv, w=W8):
+def config_bytes_per_dof(ngll, ndof, scheme, kv, w=W8, plastic=False, w25d=False):
     """bytes the engine must move per DOF and step for a builder-made box of that kind: coefficient planes as
     stored (two per GLL point: SH flat planes, or (lambda, mu) of an isotropic P-SV box), fields and inverse mass.
     Fused step (leapfrog / explicit Newmark without KV): d, v in, rmass once per node, v, d_next out (+ a in / out
@@ -328,7 +331,9 @@ def config_bytes_per_dof(ngll, ndof, scheme, kv, w=W8):
     eta = ngll ** 2 * w / (ndof * n1) if kv else 0
     if kv and (ngll > 6 or os.environ.get("S2D_KV_FUSED", "1") == "0"):
         return coef + eta + 13 * w
-    return coef + eta + 4 * w + w / ndof + (2 * w if scheme == "newmark" else 0)
+    # plasticity: the plastic strain (3 per element GLL point) in and out; 2.5D: beta per element GLL point in
+    extra = (6 * ngll ** 2 * w / (ndof * n1) if plastic else 0) + (ngll ** 2 * w / (ndof * n1) if w25d else 0)
+    return coef + eta + extra + 4 * w + w / ndof + (2 * w if scheme == "newmark" else 0)
 
 
 def run_ref_config(name, steps, device, scale=None):
@@ -353,11 +358,12 @@ def run_ref_config(name, steps, device, scale=None):
     r = json.loads(p.stdout.strip().splitlines()[-1])
     ndofs = r["npoin"] * r["ndof"]
     peak, _ = peaks()
-    b = config_bytes_per_dof(r["ngll"], r["ndof"], r["scheme"], r["kv"])
+    b = config_bytes_per_dof(r["ngll"], r["ndof"], r["scheme"], r["kv"], plastic=r.get("plastic", False),
+                             w25d=("W=" in deck.split("/")[0].replace(" ", "")))
     val = ndofs / (r["ms_per_step"] * 1e-3)
     names = ("predictor", "element_force", "halo_fold_exchange", "sources", "boundary_conditions", "node_update", "outputs")
     return {"config": name, "what": cfg["what"], "mesh": f"{nx * S}x{nz * S} elements (x{S} per side)", "npoin": r["npoin"],
-            "ngll": r["ngll"], "ndof": r["ndof"], "scheme": r["scheme"], "kelvin_voigt": r["kv"], "steps": r["steps"],
+            "ngll": r["ngll"], "ndof": r["ndof"], "scheme": r["scheme"], "kelvin_voigt": r["kv"], "plastic": r.get("plastic", False), "steps": r["steps"],
             "value": val, "unit": UNIT, "ms_per_step": r["ms_per_step"], "launches_per_step": r["launches_per_step"],
             "force_kernel_ms": r["kernel_ms"], "ms_per_step_by_phase": dict(zip(names, r["phases_ms"])),
             "roofline": {"bound": "hbm", "algorithmic_bytes_per_dof": b, "achieved": b * val / 1e9, "peak": peak,
@@ -625,7 +631,7 @@ def main():
     if world == 1 and args.generic_n > 0:
         line["generic_route"] = generic_route_record(min(args.generic_n, args.nx), K, W, local, args.precision, torch)
     if world == 1 and not args.no_configs:   # BASELINE.json configs[0..3] at scale, same run (records, not the headline)
-        line["reference_configs"] = [run_ref_config(c, max(10, min(K, 30)), local) for c in ("testsh", "lamb", "tpv3", "ratestate")]
+        line["reference_configs"] = [run_ref_config(c, max(10, min(K, 30)), local) for c in ("testsh", "lamb", "tpv3", "ratestate", "plastic25d")]
     if strong is not None:
         line["strong"] = strong
     if xdev is not None:

@@ -15,6 +15,20 @@ module sem2d_b200
     integer(c_int32_t) :: nstages        ! time%nstages, time%a(1:nstages+1), time%b(1:nstages)
     real(c_double) :: coa(9), cob(8)
   end type
+  type, bind(C) :: s2d_cart_desc          ! include/sem2d_b200.h, same member order
+    integer(c_int32_t) :: ngll, ndof, nx, nz, ezflt
+    real(c_double) :: x0, x1, z0, z1
+    integer(c_int64_t) :: seed            ! 0: homogeneous rho, cp, cs below (then s2d_cart_set_material for anything else)
+    integer(c_int64_t) :: ix0, iz0
+    real(c_double) :: rho, cp, cs
+    integer(c_int32_t) :: precision
+    type(s2d_scheme) :: scheme
+    real(c_double) :: courant
+    integer(c_int32_t) :: device
+    integer(c_int32_t) :: halo_left, halo_right
+    integer(c_int32_t) :: coef_mode
+    integer(c_int32_t) :: renumber        ! 1 = OPT_RENUMBER (constants.f90:10-15): node ids of a stock reference build
+  end type
   interface
     integer(c_int) function s2d_create(h, ngll, ndof, nelem, npoin, ibool, hprime, rmass, precision, scheme, device) &
         bind(C, name='s2d_create')
@@ -140,6 +154,68 @@ module sem2d_b200
     type(c_ptr) function s2d_last_error(h) bind(C, name='s2d_last_error')
       import
       type(c_ptr), value :: h
+    end function
+    ! ---- structured builder: a MESH_CART problem made in HBM from the &MESH_CART / &MATERIAL values -----------------
+    ! (what host/sem2d_host.hpp:init_main does in C++; element-wise arrays in natural element order)
+    integer(c_int) function s2d_cart_create(h, desc) bind(C, name='s2d_cart_create')
+      import
+      type(c_ptr), intent(out) :: h
+      type(s2d_cart_desc), intent(in) :: desc
+    end function
+    integer(c_int) function s2d_cart_set_material(h, rho, cp, cs) bind(C, name='s2d_cart_set_material')
+      import
+      type(c_ptr), value :: h
+      real(c_double), intent(in) :: rho(*), cp(*), cs(*)     ! (ngll,ngll,nelem): MAT_getProp at the GLL points
+    end function
+    integer(c_int) function s2d_cart_set_kv_elems(h, nkv, elem_ids, eta) bind(C, name='s2d_cart_set_kv_elems')
+      import
+      type(c_ptr), value :: h
+      integer(c_int), value :: nkv
+      integer(c_int), intent(in) :: elem_ids(*)              ! 1-based
+      real(c_double), intent(in) :: eta(*)                   ! matwrk%kv%eta(ngll,ngll) of those elements
+    end function
+    integer(c_int) function s2d_cart_set_w25d(h, W) bind(C, name='s2d_cart_set_w25d')
+      import
+      type(c_ptr), value :: h
+      real(c_double), value :: W                             ! grid%W
+    end function
+    integer(c_int) function s2d_cart_set_plastic(h, nsets, par, elem_set) bind(C, name='s2d_cart_set_plastic')
+      import
+      type(c_ptr), value :: h
+      integer(c_int), value :: nsets
+      real(c_double), intent(in) :: par(6,*)                 ! coh, phi, Tv, e0(3) of every PLAST material (mat_plastic.f90:66-118)
+      integer(c_int), intent(in) :: elem_set(*)              ! 0 = elastic element, k = plastic material k
+    end function
+    integer(c_int) function s2d_cart_get_plastic_strain(h, ep) bind(C, name='s2d_cart_get_plastic_strain')
+      import
+      type(c_ptr), value :: h
+      real(c_double), intent(out) :: ep(*)                   ! matwrk%plast%ep(ngll,ngll,3) of every element (MAT_PLAST_export)
+    end function
+    integer(c_int) function s2d_cart_add_abso(h, side_tag, stacey) bind(C, name='s2d_cart_add_abso')
+      import
+      type(c_ptr), value :: h
+      integer(c_int), value :: side_tag, stacey
+    end function
+    integer(c_int) function s2d_cart_add_dirneu(h, side_tag, kind_h, kind_v) bind(C, name='s2d_cart_add_dirneu')
+      import
+      type(c_ptr), value :: h
+      integer(c_int), value :: side_tag, kind_h, kind_v
+    end function
+    integer(c_int) function s2d_cart_add_periodic(h, master_tag, slave_tag) bind(C, name='s2d_cart_add_periodic')
+      import
+      type(c_ptr), value :: h
+      integer(c_int), value :: master_tag, slave_tag
+    end function
+    integer(c_int) function s2d_cart_get(h, ibool, a, rmass, coord) bind(C, name='s2d_cart_get')
+      import
+      type(c_ptr), value :: h
+      type(c_ptr), value :: ibool, a, rmass, coord           ! c_loc of the arrays wanted, c_null_ptr for the others
+    end function
+    integer(c_int) function s2d_cart_snapshot_elem(h, what, out) bind(C, name='s2d_cart_snapshot_elem')
+      import
+      type(c_ptr), value :: h
+      character(kind=c_char), value :: what                  ! 'E' strain, 'S' stress, 'd' div, 'c' curl (plot_gen.f90:13)
+      real(c_float), intent(out) :: out(*)
     end function
   end interface
 contains

@@ -270,6 +270,10 @@ struct StripArgs {
   T rzx;
 };
 
+__device__ __forceinline__ double rsqrt_any(double x) { return rsqrt(x); }
+__device__ __forceinline__ float rsqrt_any(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rcp_any(double x) { return __drcp_rn(x); }
+__device__ __forceinline__ float rcp_any(float x) { return __frcp_rn(x); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 
@@ -694,6 +698,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       V2 a2[NPL / 2][N];
       // plasticity: the element's plastic strain and material set, requested before anything else of this row
       T epr[PLAST ? 3 : 1][PLAST ? N : 1], ppar[PLAST ? 6 : 1];
+      bool yielded = false;
       if constexpr (PLAST) {
         // shadow lanes (el >= cx) mirror the last element -- they write the same tile slots, so they must see
         // the same state; only real lanes store it back
@@ -890,15 +895,20 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           T s1 = (la + two_mu) * e1 + la * e2;
           T s2 = la * e1 + (la + two_mu) * e2;
           T s3 = two_mu * e3;
-          const T tau = sqrt(T(0.25) * ((s1 - s2) * (s1 - s2)) + s3 * s3);
+          // Y / tau as Y * rsqrt(tau^2) and the three divisions by 2 mu as one reciprocal: one special-function
+          // sequence each instead of a square root and four divisions (21.9 -> see DESIGN.md G DOF/s); the results
+          // differ from the reference's expressions by an ulp, far inside the parity tolerance
+          const T tau2 = T(0.25) * ((s1 - s2) * (s1 - s2)) + s3 * s3;
           const T sm = T(0.5) * (s1 + s2);
           const T Y = ppar[0] - ppar[1] * sm;
           const T t1 = s1 - sm, t2 = s2 - sm, t3 = s3;
-          const T factor = T(1) - fmax(T(1) - Y / tau, T(0)) * ppar[2];
+          const T factor = T(1) - fmax(T(1) - Y * rsqrt_any(tau2), T(0)) * ppar[2];
           const T d1 = factor * t1, d2 = factor * t2, d3 = factor * t3;
-          epr[0][j] = epr[0][j] + (t1 - d1) / two_mu;
-          epr[1][j] = epr[1][j] + (t2 - d2) / two_mu;
-          epr[2][j] = epr[2][j] + (t3 - d3) / two_mu;
+          const T i2m = rcp_any(two_mu);
+          epr[0][j] = epr[0][j] + (t1 - d1) * i2m;
+          epr[1][j] = epr[1][j] + (t2 - d2) * i2m;
+          epr[2][j] = epr[2][j] + (t3 - d3) * i2m;
+          yielded = yielded || factor < T(1);
           s1 = (d1 + sm) - ((la + two_mu) * ppar[3] + la * ppar[4]);
           s2 = (d2 + sm) - (la * ppar[3] + (la + two_mu) * ppar[4]);
           s3 = d3 - two_mu * ppar[5];
@@ -954,7 +964,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         }
       }
       if constexpr (PLAST) {
-        if (real) {
+        if (real && yielded) {  // an element that did not yield leaves its plastic strain as it is in HBM
 #pragma unroll
           for (int k = 0; k < 3; ++k)
 #pragma unroll
@@ -1476,6 +1486,9 @@ struct StripIO {
 // largest ngll whose Kelvin-Voigt instantiation also carries the fused node update (compile time of the library)
 constexpr int STRIP_KV_FUSED_MAXN = 6;
 constexpr int STRIP_PLAST_MAXN = 6;  // plasticity instantiations
+#ifndef S2D_PLAST_MINB
+#define S2D_PLAST_MINB 3   // CTAs per SM of the FP64 plasticity instantiations: 168 registers with ~300 B of spills beat 2 CTAs without (4.04 vs 4.36 ms, 2560^2)
+#endif
 template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false,
           bool TENS = false, bool PLAST = false>
 inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) {
@@ -1563,7 +1576,7 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
         A.pl_ep = io.pl_ep;                                                                       \
         for (int k = 0; k < STRIP_PL_SETS; ++k)                                                   \
           for (int q = 0; q < 6; ++q) A.pl_par[k][q] = (T)io.pl_par[k][q];                        \
-        constexpr int MP = sizeof(T) == 8 ? 2 : 3;                                                \
+        constexpr int MP = sizeof(T) == 8 ? S2D_PLAST_MINB : 3;                                   \
         if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, true>(nb, A, s);         \
         else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, true>(nb, A, s);    \
         else strip_launch<T, NN, 2, 0, true, MP, false, false, true>(nb, A, s);                   \

@@ -346,6 +346,12 @@ def test_plastic_force_evaluations_and_plastic_strain(ngll, nx, nz, ezflt, seg, 
     e.set_dt(o.f("dt"))     # vp_factor = 1 - exp(-dt/Tv) from the same dt
     e.set_plastic([[coh, phi, Tv, *e0]], np.ones(nx * nz, np.int32))
     e.commit()
+    _plastic_evaluations(e, o, ngll, nx, nz, np.arange(nx * nz))
+    e.close()
+    o.close()
+
+
+def _plastic_evaluations(e, o, ngll, nx, nz, plastic_elems):
     rng = np.random.default_rng(ngll * 100 + nx)
     base = rng.standard_normal(e.npoin * 2)
     for amp in (1e-3, 3e-2, 1e-1):   # metres over 100 m elements: from barely yielding to deep in the plastic range
@@ -355,9 +361,39 @@ def test_plastic_force_evaluations_and_plastic_strain(ngll, nx, nz, ezflt, seg, 
         ref = o.compute_fint()
         got = e.compute_fint()
         assert rel_l2(got, ref) <= 1e-12, (amp, rel_l2(got, ref))
-    ep_ref = o.arr("pl_ep").reshape(nx * nz, 3, ngll, ngll)
+    ep_ref = np.zeros((nx * nz, 3, ngll, ngll))
+    ep_ref[plastic_elems] = o.arr("pl_ep").reshape(-1, 3, ngll, ngll)
     ep = e.plastic_strain()
     assert np.abs(ep_ref).max() > 1e-5
     assert np.abs(ep - ep_ref).max() <= 1e-12 * np.abs(ep_ref).max()
+
+
+def test_plastic_and_elastic_elements_in_one_box(monkeypatch):
+    """two tags: tag 1 plastic, tag 2 (fztag: the element rows next to the fault) elastic with other wave speeds.  The
+    elastic elements take the same strain -> stress -> force kernel with material set 0 (never yields); the reference
+    evaluates them with MAT_ELAST_f -- equal to rounding."""
+    monkeypatch.setenv("S2D_SEG", "3")
+    ngll, nx, nz, ezflt, h = 5, 31, 12, 6, 100.0
+    coh, phi, Tv, e0 = 2.0e6, 25.0, 0.0, (-4.0e-4, -3.0e-4, 2.5e-4)   # Tv = 0: vp_factor = 1 (mat_plastic.f90:181-185)
+    L = [f"&GENERAL iexec=1, ngll={ngll}, fmax=3.d0, ndof=2, title='plastic', verbose='0000', ItInfo=1000 /",
+         "&MESH_DEF method='CARTESIAN' /",
+         f"&MESH_CART xlim=0d0,{nx*h}d0, zlim=0d0,{nz*h}d0, nelem={nx},{nz}, ezflt={ezflt}, fztag=2, fznz=2 /",
+         "&MATERIAL tag=1, kind='PLAST' /",
+         f"&MAT_PLASTIC rho=2670.d0, cp=6000.d0, cs=3464.d0, phi={phi}d0, coh={coh}d0, Tv={Tv}d0, e0={e0[0]}d0,{e0[1]}d0,{e0[2]}d0 /",
+         "&MATERIAL tag=2, kind='ELAST' /",
+         "&MAT_ELASTIC rho=2500.d0, cp=5000.d0, cs=2900.d0 /",
+         "&TIME NbSteps=10, courant=0.5d0, kind='leapfrog' /"]
+    o = orc.Oracle("\n".join(L) + "\n", renumber=False)
+    tag = np.ones((nz, nx), np.int32)
+    tag[ezflt - 2:ezflt + 2] = 2
+    assert o.i("npl") == int((tag == 1).sum())
+    e = CartEngine(ngll, 2, nx, nz, (0.0, nx * h), (0.0, nz * h), ezflt=ezflt, seed=0, rho=2670.0, cp=6000.0, cs=3464.0)
+    one = np.ones((nx * nz, ngll, ngll))
+    t = tag.ravel()[:, None, None]
+    e.set_material(np.where(t == 1, 2670.0, 2500.0) * one, np.where(t == 1, 6000.0, 5000.0) * one, np.where(t == 1, 3464.0, 2900.0) * one)
+    e.set_dt(o.f("dt"))
+    e.set_plastic([[coh, phi, Tv, *e0]], (tag.ravel() == 1).astype(np.int32))
+    e.commit()
+    _plastic_evaluations(e, o, ngll, nx, nz, np.flatnonzero(tag.ravel() == 1))
     e.close()
     o.close()
