@@ -1,5 +1,8 @@
+"""Plastic box for the ncu capture of the PLAST instantiation (profiles/run_ncu_r2_variants.sh): n x n elements, NGLL 5,
+the 2.5D_plastic material, absorbing sides, seeded state.  usage: bench_plastic.py n amp_d amp_v"""
+import os
 import sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from sem2dpack_b200 import CartEngine
 n = int(sys.argv[1]); h = 100.0

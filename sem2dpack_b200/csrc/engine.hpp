@@ -327,8 +327,7 @@ class Engine : public EngineBase {
     if (pl_set.n) {
       io.pl_set = pl_set.p;
       io.pl_ep = pl_ep.p;
-      for (int k = 0; k < STRIP_PL_SETS; ++k)
-        for (int q = 0; q < 6; ++q) io.pl_par[k][q] = pl_par[k][q];
+      io.pl_tab = pl_tab.p;
     }
     return io;
   }
@@ -1116,7 +1115,7 @@ class Engine : public EngineBase {
   // Coulomb plasticity (mat_plastic.f90): material set per element (strip order), plastic strain per element GLL
   // point, per set (coh, phi [deg], Tv, e0(3)) as read and (yield_co, yield_mu, vp_factor, e0(3)) as the kernel uses them
   DevBuf<unsigned char> pl_set;
-  DevBuf<T> pl_ep;
+  DevBuf<T> pl_ep, pl_tab;
   double pl_raw[STRIP_PL_SETS][6] = {}, pl_par[STRIP_PL_SETS][6] = {};
   static bool strip_kv_ok() { return true; }   // k_elem_strip<KV>: d + eta*v element by element
 
@@ -1294,6 +1293,7 @@ class Engine : public EngineBase {
           pl_par[k][2] = pl_raw[k][2] > 0.0 ? 1.0 - std::exp(-scheme.dt / pl_raw[k][2]) : 1.0;
           for (int q = 3; q < 6; ++q) pl_par[k][q] = pl_raw[k][q];
         }
+        upload_as(pl_tab, &pl_par[0][0], (size_t)STRIP_PL_SETS * 6);
       }
       // the node update rides in the strip kernel for leapfrog and for the explicit Newmark scheme (beta = 0)
       fused = (scheme.kind == 0 || (scheme.kind == 1 && scheme.beta == 0.0)) && env_int("S2D_FUSED", 1) != 0;

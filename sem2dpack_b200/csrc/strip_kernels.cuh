@@ -258,7 +258,7 @@ struct StripArgs {
   // ([strain component][j][lane] per element row of a strip), per-set yield_co, yield_mu, vp_factor, e0(3)
   const unsigned char* pl_set;
   T* pl_ep;
-  T pl_par[STRIP_PL_SETS][6];
+  const T* pl_tab;          // [STRIP_PL_SETS][6] on the device
   int prefetch;             // L2 prefetch of what is not staged
   T H[N * N];               // hprime, column-major (constant bank)
   // compact coefficient mode (isotropic flat grids): only (lambda, mu) are stored per GLL point and
@@ -339,10 +339,14 @@ constexpr int strip_warps() { return S2D_STRIP_WARPS; }
 // bytes of the staging area of one warp: coefficient vectors and displacement rows of one element
 // row; in the fused form also the velocities and inverse masses of the nodes it will advance
 // (fused: 0 plain force evaluation, 1 leapfrog update, 2 explicit Newmark update: also the old accelerations)
-constexpr size_t strip_stage_bytes(int N, int NDOF, int tsize, int fused, bool compact) {
+// plast: also the plastic strain of the row's elements (3 N values per lane) when S2D_PLAST_STAGE
+#ifndef S2D_PLAST_STAGE
+#define S2D_PLAST_STAGE 1
+#endif
+constexpr size_t strip_stage_bytes(int N, int NDOF, int tsize, int fused, bool compact, bool plast = false) {
   const size_t npl = compact ? 2 : (NDOF == 1 ? 2 : 6);
   const size_t c = (npl / 2) * N * 32 * (2 * tsize), u = (size_t)NDOF * (N - 1) * 32 * tsize, r = (size_t)(N - 1) * 32 * tsize;
-  return c + u + (fused ? u + r : 0) + (fused == 2 ? u : 0);
+  return c + u + (fused ? u + r : 0) + (fused == 2 ? u : 0) + (plast && S2D_PLAST_STAGE ? (size_t)3 * N * 32 * tsize : 0);
 }
 // TENS variant (S2D_STRIP_TENSOR): the displacement rows, velocities and inverse masses of an element row arrive
 // CTA-wide by THREE tensor-map TMA copies (cp.async.bulk.tensor, SASS UTMALDG) instead of 20 per-lane LDGSTS per
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   const StripGeom& G = A.G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // every lane only ever touches its own slots of the staging area: no barrier guards it
-  unsigned char* wstage = stage_raw + (size_t)warp * (TENS ? SZ_C : strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT));
+  unsigned char* wstage = stage_raw + (size_t)warp * (TENS ? SZ_C : strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT, PLAST));
   // TENS: CTA-wide boxes behind the per-warp coefficient staging: stage s at tbase + s * TSZ =
   // [d box | v box | (Newmark: a box) | rmass box | (coefficient blocks)]
   constexpr int BW = strip_box_width(N, sizeof(T));
@@ -466,6 +470,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   T* st_v = reinterpret_cast<T*>(wstage + SZ_C + SZ_U) + lane; // [c * (N-1) + j][32]   (fused)
   T* st_r = st_v + NU * 32;                                    // [j][32]               (fused)
   T* st_a = st_r + (N - 1) * 32;                               // [c * (N-1) + j][32]   (fused Newmark: a[n-1])
+  T* st_e = reinterpret_cast<T*>(wstage + strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT, false)) + lane;  // [k * N + j][32] (plasticity)
   constexpr bool NM = FUSED == 2;
   // Kelvin-Voigt inside the fused step: every lane reads the velocities of its element's nodes for d + eta*v, so the
   // update must not overwrite them in place -- v (and, for Newmark, a) are double-buffered (v_in != v_out) and the
@@ -577,6 +582,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   const T* etap = KV ? A.eta + (size_t)strip_elem_off(G, seg, strip, ez0) * (N * N) + lanep : nullptr;
   T* epp = PLAST ? A.pl_ep + (size_t)strip_elem_off(G, seg, strip, ez0) * (3 * N * N) + lanep : nullptr;
   const unsigned char* plp = PLAST ? A.pl_set + strip_elem_off(G, seg, strip, ez0) + el : nullptr;
+  int pset_next = (PLAST && wact) ? (int)*plp : 0;
   const int cxN = cx * N;
   const V2* cp = reinterpret_cast<const V2*>(A.coef) +
                  (size_t)strip_elem_off(G, seg, strip, ez0) * (NPL * N * N / 2) + lanep;
@@ -616,6 +622,11 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
             if (NM) stage_copy<sizeof(T)>(st_a + (c * (N - 1) + j - 1) * 32, A.a_in + q);
           }
       }
+    }
+    if constexpr (PLAST && S2D_PLAST_STAGE != 0) {  // the plastic strain of the row's elements travels with its displacements
+      const T* en = A.pl_ep + (size_t)strip_elem_off(G, seg, strip, ezr) * (3 * N * N) + lanep;
+#pragma unroll
+      for (int k = 0; k < 3 * N; ++k) stage_copy<sizeof(T)>(st_e + k * 32, en + (size_t)k * cxN);
     }
     (void)rb;
     if (TCOEF || (S2D_ABLATE & 2)) {
@@ -702,14 +713,15 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       if constexpr (PLAST) {
         // shadow lanes (el >= cx) mirror the last element -- they write the same tile slots, so they must see
         // the same state; only real lanes store it back
-        const int pset = (int)*plp;
+        const int pset = pset_next;           // read one row ahead: the parameter loads below depend on it
         plp += gcx;
+        if (ez + 1 < ez1) pset_next = (int)*plp;
 #pragma unroll
         for (int k = 0; k < 3; ++k)
 #pragma unroll
-          for (int j = 0; j < N; ++j) epr[k][j] = __ldcs(epp + (size_t)(k * N + j) * cxN);
+          for (int j = 0; j < N; ++j) epr[k][j] = S2D_PLAST_STAGE ? st_e[(k * N + j) * 32] : __ldcs(epp + (size_t)(k * N + j) * cxN);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) ppar[q] = A.pl_par[pset][q];
+        for (int q = 0; q < 6; ++q) ppar[q] = __ldg(A.pl_tab + pset * 6 + q);
       }
       if constexpr (TENS) {
         const int kk = ez - ez0;
@@ -1468,7 +1480,7 @@ struct StripIO {
   const T* v_kv = nullptr;
   const unsigned char* pl_set = nullptr;  // Coulomb plasticity (see StripArgs)
   T* pl_ep = nullptr;
-  double pl_par[STRIP_PL_SETS][6] = {};
+  const T* pl_tab = nullptr;
   const T* beta = nullptr;  // 2.5D: beta per element GLL point (strip layout)
   // tensor-map staging of the fused leapfrog kernel (null: per-lane copies)
   const CUtensorMap* tm_d = nullptr;
@@ -1493,7 +1505,7 @@ template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip
           bool TENS = false, bool PLAST = false>
 inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) {
   constexpr size_t smem = TENS ? strip_tens_smem(N, NDOF, sizeof(T), COMPACT, FUSED)
-                               : strip_warps() * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT);
+                               : strip_warps() * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT, PLAST);
   // Opt in to the dynamic shared memory once per device and instantiation.  Never on the step path
   // afterwards: cudaFuncSetAttribute can serialise with running kernels, and a strip that is waiting
   // on its neighbour's flag must not keep the neighbour's host thread from launching.
@@ -1574,8 +1586,7 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
         if (!io.compact || G.ndof != 2 || io.eta) throw ArgError("plasticity: isotropic P-SV boxes without Kelvin-Voigt elements"); \
         A.pl_set = io.pl_set;                                                                     \
         A.pl_ep = io.pl_ep;                                                                       \
-        for (int k = 0; k < STRIP_PL_SETS; ++k)                                                   \
-          for (int q = 0; q < 6; ++q) A.pl_par[k][q] = (T)io.pl_par[k][q];                        \
+        A.pl_tab = io.pl_tab;                                                                     \
         constexpr int MP = sizeof(T) == 8 ? S2D_PLAST_MINB : 3;                                   \
         if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, true>(nb, A, s);         \
         else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, true>(nb, A, s);    \
