@@ -598,7 +598,10 @@ def main():
                    "coefficients": ("(lambda, mu) per GLL point in HBM, six planes formed in registers" if compact
                                     else "one a(5,5,6) block per element in HBM"),
                    "accel": ("materialised every step" if store_accel else
-                             "materialised on the last step of each s2d_step call (every step in the e2e leg)"),
+                             ("written every step (Newmark needs a[n-1])" if args.scheme == "newmark" else
+                              "not written by the leapfrog step: formed on demand at s2d_get_fields from one force "
+                              "evaluation of d[n] (deferred boundary nodes always keep theirs); round 1 wrote them on "
+                              "the last step of every s2d_step call, i.e. every step of the e2e leg")),
                    "initial_state": "seeded random fields on every rank (s2d_cart_fill_fields: |d| <= 1 mm, |v| <= 1 m/s), "
                                     "not the rest state",
                    "halo_exchange": halo, "npoin_per_gpu": npoin_rank, "nelem_per_gpu": nelem_rank, "dt": dt_run,

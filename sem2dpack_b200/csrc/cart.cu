@@ -1547,6 +1547,7 @@ static void cart_window(Engine<T>& E, const CartGeom& G, int gx0, int gz0, int n
   const size_t n = (size_t)nwx * nwz * G.ndof;
   DevBuf<double> tmp;
   tmp.alloc(n);
+  if (a) E.ensure_accel();
   const T* src[3] = {E.dbuf().p, E.v.p, E.a.p};
   double* dst[3] = {d, v, a};
   for (int k = 0; k < 3; ++k) {

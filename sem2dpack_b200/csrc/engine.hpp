@@ -1116,6 +1116,8 @@ class Engine : public EngineBase {
   // point, per set (coh, phi [deg], Tv, e0(3)) as read and (yield_co, yield_mu, vp_factor, e0(3)) as the kernel uses them
   DevBuf<unsigned char> pl_set;
   DevBuf<T> pl_ep, pl_tab;
+  bool a_stale = false;                // the fused leapfrog step left the accelerations of the nodes it advanced unwritten
+  bool accel_lazy = env_int("S2D_ACCEL_LAZY", 1) != 0;
   double pl_raw[STRIP_PL_SETS][6] = {}, pl_par[STRIP_PL_SETS][6] = {};
   static bool strip_kv_ok() { return true; }   // k_elem_strip<KV>: d + eta*v element by element
 
@@ -1617,7 +1619,16 @@ class Engine : public EngineBase {
     if (kvf) io.eta = strip_eta.p;
     io.rmass = rmass.p;
     io.d_next = dnx;
-    const bool want_a = nmk || store_accel == 1 || (store_accel == 2 && (last_of_call || (rec.present && rec.field == 'A')));
+    // accelerations are written when somebody will read them: the explicit Newmark scheme (next step), receivers
+    // recording 'A', S2D_STORE_ACCEL=1.  Otherwise (leapfrog) they are formed on demand -- ensure_accel(), at
+    // s2d_get_fields / s2d_cart_get_window -- from one plain force evaluation of the displacement the step used: no
+    // 8 B/DOF of stores per s2d_step call.  Where that evaluation is not repeatable (state advanced by every
+    // evaluation: plasticity; Kelvin-Voigt: v already updated) or needs the neighbours (x-strips), the last step of
+    // every call stores them as before.
+    const bool lazy_ok = store_accel == 2 && accel_lazy && !nmk && !xhalo() && strip_eta.n == 0 && pl_set.n == 0;
+    const bool want_a = nmk || store_accel == 1 ||
+                        (store_accel == 2 && ((last_of_call && !lazy_ok) || (rec.present && rec.field == 'A')));
+    a_stale = !want_a;
     io.a_out = want_a ? io.f : nullptr;
     io.rowflag = rowflag.p;
     io.colflag = colflag.p;
@@ -1827,11 +1838,32 @@ class Engine : public EngineBase {
   }
   void set_fields(const double* dd, const double* vv, const double* aa) override {
     if (dd || vv || aa) pred_valid = false;  // the cached prediction d + dt*v (+ dt^2/2 a) is stale
+    if (aa) a_stale = false;
+    else if (dd) ensure_accel();  // a new displacement: form the accelerations of the last step while they still can be
     upload_field(dbuf(), dd);
     upload_field(v, vv);
     upload_field(a, aa);
   }
+  // accelerations of the nodes the fused leapfrog kernel advanced without storing them: a = rmass * Fint(d[n])
+  // (deferred nodes -- boundary conditions, sources, band rows -- always have theirs stored by k_strip_deferred)
+  void ensure_accel() {
+    if (!a_stale) return;
+    S2D_REQUIRE(cart_mode && fused, "ensure_accel: fused structured engines only");
+    const size_t nd = npoin * ndof;
+    if (scratch.n != nd) scratch.alloc(nd);
+    StripIO<T> io = strip_io(dbuf().p, scratch.p);
+    launch_strips(io);
+    const long long tot = (long long)cart_S.LX * cart_S.LZ;
+    k_strip_accel_fill<T><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(cart_S.LX, cart_S.LXP, cart_S.LZ, ndof, npoin, rowflag.p,
+                                                                        colflag.p, scratch.p, rmass.p, a.p);
+    launches++;
+    S2D_CUDA(cudaGetLastError());
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    a_stale = false;
+  }
+
   void get_fields(double* dd, double* vv, double* aa) override {
+    if (aa) ensure_accel();
     download(dbuf(), dd);
     download(v, vv);
     download(a, aa);

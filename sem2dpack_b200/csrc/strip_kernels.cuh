@@ -1341,6 +1341,19 @@ __global__ void k_strip_deferred(int LX, int LXP, int LZ, int ndof, size_t npoin
   }
 }
 
+// a = rmass * f on the nodes the fused kernel advanced itself (everything that is not a deferred row / column)
+template <typename T>
+__global__ void k_strip_accel_fill(int LX, int LXP, int LZ, int ndof, size_t npoin, const uint8_t* __restrict__ rowflag,
+                                   const uint8_t* __restrict__ colflag, const T* __restrict__ f, const T* __restrict__ rmass,
+                                   T* __restrict__ a) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= (long long)LX * LZ) return;
+  const int gz = (int)(w / LX), gx = (int)(w - (long long)gz * LX);
+  if (rowflag[gz] || colflag[gx] == 1) return;
+  const size_t node = (size_t)gz * LXP + gx;
+  for (int c = 0; c < ndof; ++c) a[node + npoin * c] = rmass[node + npoin * c] * f[node + npoin * c];
+}
+
 // x-strip interface columns (multi-GPU): this GPU's complete partial sum of lattice column 0 / LX-1,
 // i.e. the stored force plus the band-top partial of the same strip.  buf[c][gz].
 template <typename T>

@@ -323,6 +323,47 @@ def test_snapshot_elem_fields(ndof):
     o.close()
 
 
+def test_accelerations_on_demand(monkeypatch):
+    """The fused leapfrog step does not write the accelerations of the nodes it advances (8 B/DOF per s2d_step call
+    saved): s2d_get_fields / s2d_cart_get_window form them from one force evaluation of d[n] (Engine::ensure_accel),
+    also when the caller replaces the displacement first.  Same values as with S2D_ACCEL_LAZY=0 (stored by the last
+    step of the call) and as the oracle's; one s2d_step call per step, as the e2e leg of bench.py does it."""
+    nx, nz, nsteps = 43, 14, 40
+    monkeypatch.setenv("S2D_SEG", "3")
+    res = {}
+    for lazy in ("1", "0"):
+        monkeypatch.setenv("S2D_ACCEL_LAZY", lazy)
+        o = orc.Oracle(harness.cart_deck(nx, nz, ezflt=6, nsteps=nsteps + 1), synthetic_seed=SEED, renumber=False)
+        tab = np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps + 1)])
+        e = CartEngine(5, 2, nx, nz, (0.0, nx * 100.0), (0.0, nz * 100.0), ezflt=6, seed=SEED)
+        e.add_fault_swf(0.4, 0.677, 0.525, -120e6, 70e6, 81.6e6, nx * 50.0, harness.nuc_radius(nx), nt_max=nsteps + 1)
+        for side in (1, 2, 3, 4):
+            e.add_abso_side(side)
+        e.add_force_at(0.37 * nx * 100, 0.61 * nz * 100, [o.f("src.0.dir1"), o.f("src.0.dir2")])
+        e.commit()
+        n0 = e.launch_count()
+        for k in range(nsteps):
+            e.step(1, tab[k:k + 1])
+        per_step = (e.launch_count() - n0) / nsteps
+        o.step(nsteps)
+        win = e.get_window(3, 2, 150, 40, a=True)[2]          # accelerations of a lattice window, formed on demand
+        d, v, a = e.get_fields()
+        for nm, got in (("d", d), ("v", v), ("acc", a)):
+            assert rel_l2(got, o.arr(nm)) <= 1e-10, (lazy, nm, rel_l2(got, o.arr(nm)))
+        # a new displacement does not lose the accelerations of the step before it
+        e.step(1, tab[nsteps:])
+        o.step(1)
+        e.set_fields(np.zeros_like(d), None)
+        assert rel_l2(e.get_fields()[2], o.arr("acc")) <= 1e-10
+        res[lazy] = (a, win, per_step)
+        e.close()
+        o.close()
+    scale = np.abs(res["0"][0]).max()
+    assert np.abs(res["1"][0] - res["0"][0]).max() <= 1e-13 * scale
+    assert np.abs(res["1"][1] - res["0"][1]).max() <= 1e-13 * scale
+    assert res["1"][2] <= 6.1 and res["0"][2] <= 6.1   # 6 per step + the predictor of the very first one
+
+
 @pytest.mark.parametrize("ngll,nx,nz,ezflt,seg", [(5, 27, 11, 0, 3), (5, 50, 12, 5, 2), (6, 23, 10, 3, 3), (4, 9, 7, 0, 32),
                                                   (3, 47, 8, 4, 5)])
 def test_plastic_force_evaluations_and_plastic_strain(ngll, nx, nz, ezflt, seg, monkeypatch):
