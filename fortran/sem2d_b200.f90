@@ -186,6 +186,15 @@ module sem2d_b200
       real(c_double), intent(in) :: par(6,*)                 ! coh, phi, Tv, e0(3) of every PLAST material (mat_plastic.f90:66-118)
       integer(c_int), intent(in) :: elem_set(*)              ! 0 = elastic element, k = plastic material k
     end function
+    integer(c_int) function s2d_cart_set_visco(h, nsets, nbody, moduli, wbody, theta, elem_set) bind(C, name='s2d_cart_set_visco')
+      import
+      type(c_ptr), value :: h
+      integer(c_int), value :: nsets
+      integer(c_int), intent(in) :: nbody(*)                 ! matwrk%visco%Nbody of every VISCO material
+      real(c_double), intent(in) :: moduli(2,*)              ! lambda_inf, mu_inf (get_attenuation, mat_visco.f90:251-340)
+      real(c_double), intent(in) :: wbody(8,*), theta(8,3,*) ! m%wbody(1:Nbody), m%theta(1:Nbody,1:3)
+      integer(c_int), intent(in) :: elem_set(*)              ! 0 = elastic element, k = visco material k
+    end function
     integer(c_int) function s2d_cart_get_plastic_strain(h, ep) bind(C, name='s2d_cart_get_plastic_strain')
       import
       type(c_ptr), value :: h

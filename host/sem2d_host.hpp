@@ -75,6 +75,86 @@ struct rec_type {
 // cd_type (SRC/distribution_cd.f90): a constant or a spatial distribution evaluated at node coordinates.
 // Distributions provided: ORDER0 (SRC/distribution_order0.f90: blocks of constant value on an x-z grid of
 // zones) and PWCONR (SRC/distribution_pwconr.f90: constant in concentric rings around a point).
+// get_attenuation (SRC/mat_visco.f90:251-340): relaxation frequencies log-spaced over [fmin, fmax], the anelastic
+// coefficients Y_alpha, Y_beta that make 1/Q constant at 2 Nbody - 1 frequencies in the least-squares sense, the
+// unrelaxed moduli and theta(Nbody,3).  The reference solves the two small least-squares problems with Numerical
+// Recipes' SVD; the minimiser is unique, here it comes from Householder QR.
+struct attenuation_type {
+  std::vector<double> theta, wbody;  // theta[c * Nbody + b]
+  double mu_inf = 0, lambda_inf = 0;
+};
+inline std::vector<double> lsq_qr(std::vector<double> A, int m, int n, std::vector<double> b) {  // A(m,n) column-major
+  for (int k = 0; k < n; ++k) {
+    double nrm = 0;
+    for (int i = k; i < m; ++i) nrm += A[i + (size_t)m * k] * A[i + (size_t)m * k];
+    nrm = std::sqrt(nrm);
+    if (nrm == 0.0) continue;
+    const double alpha = A[k + (size_t)m * k] > 0 ? -nrm : nrm;
+    std::vector<double> v((size_t)m, 0.0);
+    for (int i = k; i < m; ++i) v[(size_t)i] = A[i + (size_t)m * k];
+    v[(size_t)k] -= alpha;
+    double vv = 0;
+    for (int i = k; i < m; ++i) vv += v[(size_t)i] * v[(size_t)i];
+    if (vv == 0.0) continue;
+    for (int j = k; j < n; ++j) {
+      double s = 0;
+      for (int i = k; i < m; ++i) s += v[(size_t)i] * A[i + (size_t)m * j];
+      s = 2.0 * s / vv;
+      for (int i = k; i < m; ++i) A[i + (size_t)m * j] -= s * v[(size_t)i];
+    }
+    double s = 0;
+    for (int i = k; i < m; ++i) s += v[(size_t)i] * b[(size_t)i];
+    s = 2.0 * s / vv;
+    for (int i = k; i < m; ++i) b[(size_t)i] -= s * v[(size_t)i];
+  }
+  std::vector<double> x((size_t)n, 0.0);
+  for (int k = n - 1; k >= 0; --k) {
+    double s = b[(size_t)k];
+    for (int j = k + 1; j < n; ++j) s -= A[k + (size_t)m * j] * x[(size_t)j];
+    x[(size_t)k] = s / A[k + (size_t)m * k];
+  }
+  return x;
+}
+inline attenuation_type get_attenuation(double cp, double cs, double rho, double QP, double QS, int Nbody, double fmin, double fmax) {
+  const double PI_ = 3.141592653589793;
+  const int Nf = 2 * Nbody - 1;
+  const double w0 = 2.0 * PI_ * std::pow(fmin * fmax, 0.5), wmin = 2.0 * PI_ * fmin, wmax = 2.0 * PI_ * fmax;
+  std::vector<double> w((size_t)Nf, w0);
+  if (Nbody > 1)
+    for (int i = 1; i <= Nf; ++i) w[(size_t)i - 1] = std::exp(std::log(wmin) + (i - 1) * (std::log(wmax) - std::log(wmin)) / (Nf - 1));
+  attenuation_type at;
+  at.wbody.resize((size_t)Nbody);
+  for (int j = 1; j <= Nbody; ++j) at.wbody[(size_t)j - 1] = w[(size_t)(2 * j - 2)];
+  std::vector<double> AP((size_t)Nf * Nbody), AS((size_t)Nf * Nbody);
+  for (int i = 0; i < Nf; ++i)
+    for (int j = 0; j < Nbody; ++j) {
+      const double wb = at.wbody[(size_t)j], wi = w[(size_t)i];
+      AP[i + (size_t)Nf * j] = (wb * wi + wb * wb / QP) / (wb * wb + wi * wi);
+      AS[i + (size_t)Nf * j] = (wb * wi + wb * wb / QS) / (wb * wb + wi * wi);
+    }
+  const std::vector<double> Ya = lsq_qr(AP, Nf, Nbody, std::vector<double>((size_t)Nf, 1.0 / QP));
+  const std::vector<double> Yb = lsq_qr(AS, Nf, Nbody, std::vector<double>((size_t)Nf, 1.0 / QS));
+  double RP1 = 1, RP2 = 0, RS1 = 1, RS2 = 0;
+  for (int j = 0; j < Nbody; ++j) {
+    const double r = w0 / at.wbody[(size_t)j], den = 1.0 + r * r;
+    RP1 -= Ya[(size_t)j] / den;
+    RP2 += Ya[(size_t)j] * r / den;
+    RS1 -= Yb[(size_t)j] / den;
+    RS2 += Yb[(size_t)j] * r / den;
+  }
+  const double RP = std::sqrt(RP1 * RP1 + RP2 * RP2), RS = std::sqrt(RS1 * RS1 + RS2 * RS2);
+  const double mu = rho * cs * cs, lambda = rho * (cp * cp - 2.0 * cs * cs);
+  at.mu_inf = mu * (RS + RS1) / (2 * RS * RS);
+  at.lambda_inf = (lambda + 2.0 * mu) * (RP + RP1) / (2 * RP * RP) - 2.0 * at.mu_inf;
+  at.theta.assign((size_t)Nbody * 3, 0.0);
+  for (int j = 0; j < Nbody; ++j) {
+    at.theta[(size_t)j] = (at.lambda_inf + 2.0 * at.mu_inf) * Ya[(size_t)j];
+    at.theta[(size_t)(j + Nbody)] = (at.lambda_inf + 2.0 * at.mu_inf) * Ya[(size_t)j] - 2.0 * at.mu_inf * Yb[(size_t)j];
+    at.theta[(size_t)(j + 2 * Nbody)] = 2.0 * at.mu_inf * Yb[(size_t)j];
+  }
+  return at;
+}
+
 struct cd_type {
   double c = 0.0;
   int dist = 0;  // 0 constant, 1 ORDER0, 2 PWCONR, 3 GAUSSIAN
@@ -153,6 +233,9 @@ struct problem_type {
     bool set = false, kv = false, ETAxDT = true;
     bool plastic = false;                        // kind='PLAST' (&MAT_PLASTIC, SRC/mat_plastic.f90:46-118)
     double phi = 0, coh = 0, Tv = 0, e0[3] = {0, 0, 0};
+    bool visco = false;                          // kind='VISCO' (&MAT_VISCO, SRC/mat_visco.f90:42-113)
+    double QP = 0, QS = 0, fmin = 0, fmax = 0;
+    int Nbody = 0;
     cd_type rho, cp, cs, eta;
     bool homogeneous() const { return rho.dist == 0 && cp.dist == 0 && cs.dist == 0; }
   };
@@ -160,6 +243,7 @@ struct problem_type {
   double rho = 0, cp = 0, cs = 0;                // material of tag 1 when it is homogeneous (builder default)
   bool has_kv = false;
   bool has_plastic = false;
+  bool has_visco = false;
   timescheme_type time;
   std::vector<bc_type> bc;
   std::vector<source_type> src;
@@ -327,8 +411,29 @@ inline void read_main(problem_type& pb, const std::string& file) {
       pb.has_plastic = true;
       continue;
     }
+    if (k1 == "VISCO") {  // MAT_VISCO_read (SRC/mat_visco.f90:65-113): constants only
+      if (!k2.empty()) IO_abort("MAT_read: kind='VISCO' combined with '" + k2 + "' is not on the B200 path");
+      const long m = in.find("MAT_VISCO", (size_t)m0);
+      if (m < 0) IO_abort("MAT_VISCO_read: MAT_VISCO input block not found");
+      const nml_group& e = in.at((size_t)m);
+      M.rho.c = e.real8("rho", 0.0);
+      M.cp.c = e.real8("cp", 0.0);
+      M.cs.c = e.real8("cs", 0.0);
+      M.QP = e.real8("qp", 0.0);
+      M.QS = e.real8("qs", 0.0);
+      M.Nbody = (int)e.real8("nbody", 0.0);
+      M.fmin = e.real8("fmin", 0.0);
+      M.fmax = e.real8("fmax", 0.0);
+      if (!(M.rho.c > 0) || !(M.cp.c > 0) || !(M.cs.c > 0) || !(M.QP > 0) || !(M.QS > 0) || !(M.fmin > 0) || !(M.fmax > M.fmin))
+        IO_abort("MAT_VISCO_read: incomplete input (rho, cp, cs, QP, QS, fmin < fmax)");
+      if (M.Nbody < 1 || M.Nbody > 8) IO_abort("MAT_VISCO_read: Nbody must be in 1..8 on the B200 path");
+      M.visco = true;
+      M.set = true;
+      pb.has_visco = true;
+      continue;
+    }
     if (k1 != "ELAST" || !(k2.empty() || k2 == "KV"))
-      IO_abort("MAT_read: only kind='ELAST', kind='ELAST','KV' and kind='PLAST' are on the B200 path (DMG, VISCO are not)");
+      IO_abort("MAT_read: only kind='ELAST', kind='ELAST','KV', kind='PLAST' and kind='VISCO' are on the B200 path (DMG is not)");
     const long m = in.find("MAT_ELASTIC", (size_t)m0);
     if (m < 0) IO_abort("MAT_ELAST_read: MAT_ELASTIC input block not found");
     const nml_group& e = in.at((size_t)m);  // SRC/mat_elastic.f90:104-129
@@ -711,6 +816,30 @@ inline void init_main(problem_type& pb) {
     s2d_check(pb, s2d_cart_info(pb.gpu, &pb.npoin, &pb.nelem_total, &dt), "init_main");
   }
   if (pb.W > 0.0) s2d_check(pb, s2d_cart_set_w25d(pb.gpu, pb.W), "MAT_ELAST_init_25D");
+  if (pb.has_visco) {  // MAT_VISCO_init_elem_prop (SRC/mat_visco.f90:116-161): get_attenuation per VISCO tag
+    if (pb.ndof != 2) IO_abort("MAT_init_work: visco-elasticity requires ndof=2 (P-SV) ");
+    if (pb.has_plastic || pb.has_kv) IO_abort("MAT_read: VISCO together with PLAST or KV materials is not on the B200 path");
+    std::vector<int> set_of_tag(pb.mat.size(), 0);
+    std::vector<int32_t> nbody;
+    std::vector<double> moduli, wbody, theta;
+    int nsets = 0;
+    for (size_t tg = 0; tg < pb.mat.size(); ++tg) {
+      const auto& M = pb.mat[tg];
+      if (!M.visco) continue;
+      set_of_tag[tg] = ++nsets;
+      attenuation_type at = get_attenuation(M.cp.c, M.cs.c, M.rho.c, M.QP, M.QS, M.Nbody, M.fmin, M.fmax);
+      nbody.push_back(M.Nbody);
+      moduli.push_back(at.lambda_inf);
+      moduli.push_back(at.mu_inf);
+      for (int b = 0; b < 8; ++b) wbody.push_back(b < M.Nbody ? at.wbody[(size_t)b] : 0.0);
+      for (int c = 0; c < 3; ++c)
+        for (int b = 0; b < 8; ++b) theta.push_back(b < M.Nbody ? at.theta[(size_t)c * M.Nbody + b] : 0.0);
+    }
+    std::vector<int32_t> eset((size_t)pb.nelem_total);
+    for (size_t e = 0; e < eset.size(); ++e) eset[e] = set_of_tag[(size_t)tag[e] - 1];
+    s2d_check(pb, s2d_cart_set_visco(pb.gpu, nsets, nbody.data(), moduli.data(), wbody.data(), theta.data(), eset.data()),
+              "MAT_VISCO_init_elem_work");
+  }
   if (pb.has_plastic) {  // MAT_init_work (SRC/mat_gen.f90:367-372): one plastic material set per PLAST tag
     if (pb.ndof != 2) IO_abort("MAT_init_work: plasticity requires ndof=2 (P-SV) ");
     std::vector<int> set_of_tag(pb.mat.size(), 0);

@@ -262,6 +262,17 @@ int s2d_stream(s2d_handle h, void** stream);
 int s2d_cart_set_plastic(s2d_handle h, int32_t nsets, const double* par, const int32_t* elem_set);
 int s2d_cart_get_plastic_strain(s2d_handle h, double* ep);
 
+/* Visco-elasticity (kind='VISCO': generalized Maxwell body, MAT_VISCO_stress mat_visco.f90:206-248, through the same
+ * strain -> stress -> force branch of MAT_Fint, mat_gen.f90:451-457).  Per material k: nbody(k) <= 8 mechanisms,
+ * moduli(2,k) = lambda_inf, mu_inf (the unrelaxed moduli), wbody(8,k) relaxation frequencies, theta(8,3,k) as
+ * get_attenuation (mat_visco.f90:251-340) returns them -- the host evaluates that routine (a least-squares fit per
+ * material), the device keeps the memory variables el(ngll,ngll,Nbody,3) and the previous strain of every element and
+ * advances them in every force evaluation.  elem_set(nelem), natural element order: 0 = elastic element.
+ * s2d_cart_set_material still gives rho, cp, cs (mass, absorbing boundaries, Courant step use the input speeds, as the
+ * reference does).  P-SV, ngll <= 6, no Kelvin-Voigt or plastic elements in the same problem. */
+int s2d_cart_set_visco(s2d_handle h, int32_t nsets, const int32_t* nbody, const double* moduli, const double* wbody,
+                       const double* theta, const int32_t* elem_set);
+
 /* ---- device-side structured builder (mesh_cartesian.f90:219-314 + init on the GPU) --------- */
 /* Builds, directly in HBM, a MESH_CART problem: nx*nz Q4 elements on [x0,x1]x[z0,z1], optional
  * horizontal split-node fault after element row ezflt (0 = none), natural (row-major) element

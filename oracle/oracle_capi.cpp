@@ -129,6 +129,7 @@ long long orc_get_int(void* hv, const char* name_) {
   if (n == "ncoefsets") return pb.ncoefsets;
   if (n == "nkv") return (long long)pb.kv_elem.size();
   if (n == "npl") return (long long)pb.pl_elem.size();
+  if (n == "nvs") return (long long)pb.vs_elem.size();
   if (n == "nt") return pb.time.nt;
   if (n == "it") return pb.it;
   if (n == "nbc") return (long long)pb.bc.size();
@@ -315,6 +316,23 @@ long long orc_array(void* hv, const char* name_, const void** ptr, char* dtype) 
   if (n == "pl_elem") RET_I(pb.pl_elem);
   if (n == "pl_ep") RET_D(pb.pl_ep);
   if (n == "pl_par") RET_D(pb.pl_par);
+  if (n == "vs_el") RET_D(pb.vs_el);
+  if (n.rfind("mat.", 0) == 0) {  // mat.<tag>.theta | wbody | moduli (lambda_inf, mu_inf) of a VISCO material
+    const size_t dot = n.find('.', 4);
+    const int tag = std::atoi(n.substr(4, dot - 4).c_str());
+    if (tag >= 1 && tag <= (int)pb.mat.inputs.size()) {
+      const auto& mi = pb.mat.inputs[tag - 1];
+      const std::string what = n.substr(dot + 1);
+      if (what == "theta") RET_D(mi.theta);
+      if (what == "wbody") RET_D(mi.wbody);
+      if (what == "moduli") {
+        static thread_local std::vector<double> mm;
+        mm = {mi.lambda, mi.mu};
+        RET_D(mm);
+      }
+    }
+  }
+  if (n == "vs_etot") RET_D(pb.vs_etot);
   if (n == "rmass") RET_D(pb.rmass);
   if (n == "mass") RET_D(pb.mass);
   if (n == "d") RET_D(pb.d);

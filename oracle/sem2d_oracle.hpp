@@ -675,6 +675,10 @@ struct MatInput {  // matpro_input_type (prop_mat.f90:21-25) for ELAST (+KV)
   bool elastic = false, isotropic = false, homogeneous = false, kv = false;
   bool plastic = false;                    // kind='PLAST' (mat_plastic.f90)
   double phi = 0, coh = 0, Tv = 0, e0[3] = {0, 0, 0};
+  bool visco = false;                      // kind='VISCO' (mat_visco.f90): generalized Maxwell body, Nbody mechanisms
+  double QP = 0, QS = 0, fmin = 0, fmax = 0;
+  int Nbody = 0;
+  std::vector<double> theta, wbody;        // theta(Nbody,3) column-major, wbody(Nbody): get_attenuation (mat_visco.f90:251-340)
   Dist rho, cp, cs, eta;
   double lambda = 0, mu = 0;  // set if homogeneous (mat_elastic.f90:118-125)
   bool has_lambda = false;
@@ -879,6 +883,13 @@ struct Problem {  // problem_type (problem_class.f90:19-46)
   std::vector<double> pl_ep;      // (ngll,ngll,3,npl) plastic strain
   std::vector<double> pl_derint;  // (ngll,ngll,5,npl): dxi_dx, dxi_dy, deta_dx, deta_dy, weights
   std::vector<double> pl_beta;    // (ngll,ngll,npl) when W is finite
+  // visco-elasticity (matwrk_visco_type, mat_visco.f90:11-19), per visco element; derint shares pl_derint's layout
+  std::vector<int> elem2vs;       // (nelem) 0 or 1-based index into the visco element list
+  std::vector<int> vs_elem;       // 1-based element ids
+  std::vector<double> vs_derint;  // (ngll,ngll,5,nvs)
+  std::vector<double> vs_el;      // (ngll,ngll,Nbody,3) per element, concatenated (offsets vs_off)
+  std::vector<size_t> vs_off;
+  std::vector<double> vs_etot;    // (ngll,ngll,3,nvs) strain of the previous evaluation
   std::vector<double> rmass;      // (npoin,ndof) -- mass until init end, then inverse
   std::vector<double> mass;       // (npoin) assembled mass as MAT_MASS_init leaves it (mat_mass.f90:50-57), before BC_init
   std::vector<double> d, v, a_;   // fields (npoin,ndof) col-major
@@ -894,6 +905,95 @@ struct Problem {  // problem_type (problem_class.f90:19-46)
 
   size_t idx(int ip, int c) const { return (size_t)(ip - 1) + (size_t)grid.npoin * c; }
 };
+
+// ------------------------------------------------------------------------------------------
+// Least squares x = argmin |A x - b|, A (m,n) column-major, m >= n, full column rank.  The reference solves it with
+// Numerical Recipes' svdcmp / svbksb (mat_visco.f90:343-607), i.e. x = V diag(1/w) U^T b; the solution is unique, and
+// here it comes from a one-sided Jacobi SVD (Hestenes) -- same x to rounding (cond(A) ~ 1e2), not the same code.
+inline void lsq_svd(std::vector<double> A, int m, int n, const std::vector<double>& b, std::vector<double>& x) {
+  std::vector<double> V((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) V[i + (size_t)n * i] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        double app = 0, aqq = 0, apq = 0;
+        for (int k = 0; k < m; ++k) {
+          app += A[k + (size_t)m * p] * A[k + (size_t)m * p];
+          aqq += A[k + (size_t)m * q] * A[k + (size_t)m * q];
+          apq += A[k + (size_t)m * p] * A[k + (size_t)m * q];
+        }
+        if (std::abs(apq) <= 1e-300 || std::abs(apq) <= 1e-17 * std::sqrt(app * aqq)) continue;
+        off = std::max(off, std::abs(apq) / std::sqrt(app * aqq));
+        const double zeta = (aqq - app) / (2.0 * apq);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::abs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
+        for (int k = 0; k < m; ++k) {
+          const double ap = A[k + (size_t)m * p], aq = A[k + (size_t)m * q];
+          A[k + (size_t)m * p] = c * ap - sn * aq;
+          A[k + (size_t)m * q] = sn * ap + c * aq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vp = V[k + (size_t)n * p], vq = V[k + (size_t)n * q];
+          V[k + (size_t)n * p] = c * vp - sn * vq;
+          V[k + (size_t)n * q] = sn * vp + c * vq;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  // columns of A are now U diag(w): x = V diag(1/w) U^T b = sum_j V(:,j) (A(:,j)^T b) / w_j^2
+  x.assign(n, 0.0);
+  for (int j = 0; j < n; ++j) {
+    double w2 = 0, ub = 0;
+    for (int k = 0; k < m; ++k) {
+      w2 += A[k + (size_t)m * j] * A[k + (size_t)m * j];
+      ub += A[k + (size_t)m * j] * b[k];
+    }
+    if (w2 == 0.0) continue;  // svbksb skips zero singular values
+    for (int i = 0; i < n; ++i) x[i] += V[i + (size_t)n * j] * (ub / w2);
+  }
+}
+
+// mat_visco.f90:251-340 get_attenuation: relaxation frequencies log-spaced in [fmin, fmax], anelastic coefficients
+// Y_alpha, Y_beta fitted to constant 1/QP, 1/QS at 2 Nbody - 1 frequencies, unrelaxed moduli, theta(Nbody,3)
+inline void get_attenuation(std::vector<double>& theta, std::vector<double>& wbody, double& mu_inf, double& lambda_inf,
+                            double cp, double cs, double rho, double QP, double QS, int Nbody, double fmin, double fmax) {
+  const int Nf = 2 * Nbody - 1;
+  const double w0 = 2.0 * PI * std::pow(fmin * fmax, 0.5), wmin = 2.0 * PI * fmin, wmax = 2.0 * PI * fmax;
+  std::vector<double> w(Nf);
+  if (Nbody > 1)
+    for (int i = 1; i <= Nf; ++i) w[i - 1] = std::exp(std::log(wmin) + (i - 1) * (std::log(wmax) - std::log(wmin)) / (Nf - 1));
+  else
+    for (int i = 0; i < Nf; ++i) w[i] = w0;
+  wbody.assign(Nbody, 0.0);
+  for (int j = 1; j <= Nbody; ++j) wbody[j - 1] = w[2 * j - 2];
+  std::vector<double> AP((size_t)Nf * Nbody), AS((size_t)Nf * Nbody), qpi(Nf, 1.0 / QP), qsi(Nf, 1.0 / QS), Ya, Yb;
+  for (int i = 0; i < Nf; ++i)
+    for (int j = 0; j < Nbody; ++j) {
+      AP[i + (size_t)Nf * j] = (wbody[j] * w[i] + wbody[j] * wbody[j] / QP) / (wbody[j] * wbody[j] + w[i] * w[i]);
+      AS[i + (size_t)Nf * j] = (wbody[j] * w[i] + wbody[j] * wbody[j] / QS) / (wbody[j] * wbody[j] + w[i] * w[i]);
+    }
+  lsq_svd(AP, Nf, Nbody, qpi, Ya);
+  lsq_svd(AS, Nf, Nbody, qsi, Yb);
+  double RP1 = 1, RP2 = 0, RS1 = 1, RS2 = 0;
+  for (int j = 0; j < Nbody; ++j) {
+    const double r = w0 / wbody[j], den = 1.0 + r * r;
+    RP1 = RP1 - Ya[j] / den;
+    RP2 = RP2 + Ya[j] * r / den;
+    RS1 = RS1 - Yb[j] / den;
+    RS2 = RS2 + Yb[j] * r / den;
+  }
+  const double RP = std::sqrt(RP1 * RP1 + RP2 * RP2), RS = std::sqrt(RS1 * RS1 + RS2 * RS2);
+  const double mu = rho * cs * cs, lambda = rho * (cp * cp - 2.0 * cs * cs);
+  mu_inf = mu * (RS + RS1) / (2 * RS * RS);
+  lambda_inf = (lambda + 2.0 * mu) * (RP + RP1) / (2 * RP * RP) - 2.0 * mu_inf;
+  theta.assign((size_t)Nbody * 3, 0.0);
+  for (int j = 0; j < Nbody; ++j) {
+    theta[j] = (lambda_inf + 2.0 * mu_inf) * Ya[j];
+    theta[j + Nbody] = (lambda_inf + 2.0 * mu_inf) * Ya[j] - 2.0 * mu_inf * Yb[j];
+    theta[j + 2 * Nbody] = 2.0 * mu_inf * Yb[j];
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // material init
@@ -971,6 +1071,19 @@ inline void MAT_init_prop(Problem& pb, int N_for_lattice /*ngll*/) {
         for (int k = 0; k < n2; ++k) tmp[k] = rho[k] * cs[k] * cs[k];
         m.mu[e - 1] = m.set_vals(tmp.data());
       }
+    }
+    if (in.visco) {  // MAT_VISCO_init_elem_prop (mat_visco.f90:116-161): unrelaxed moduli from get_attenuation
+      m.cp[e - 1] = set_from_input(in.cp);
+      m.cs[e - 1] = set_from_input(in.cs);
+      MatInput& iw = m.inputs[tag - 1];
+      if (iw.theta.empty()) {
+        double mu_inf, la_inf;
+        get_attenuation(iw.theta, iw.wbody, mu_inf, la_inf, in.cp.c, in.cs.c, in.rho.c, in.QP, in.QS, in.Nbody, in.fmin, in.fmax);
+        iw.lambda = la_inf;
+        iw.mu = mu_inf;
+      }
+      m.lambda[e - 1].homo = iw.lambda;
+      m.mu[e - 1].homo = iw.mu;
     }
     if (in.plastic) {  // MAT_PLAST_init_elem_prop (mat_plastic.f90:121-145): scalar properties
       m.cp[e - 1] = set_from_input(in.cp);
@@ -1099,6 +1212,12 @@ inline void MAT_init_work(Problem& pb, bool force_general_nelast = false) {
   pb.kv_eta.clear();
   pb.ncoefsets = 0;
   std::vector<double> abuf((size_t)n2 * pb.nelast), eta(n2);
+  pb.elem2vs.assign(ne, 0);
+  pb.vs_elem.clear();
+  pb.vs_derint.clear();
+  pb.vs_el.clear();
+  pb.vs_off.clear();
+  pb.vs_etot.clear();
   pb.elem2pl.assign(ne, 0);
   pb.pl_elem.clear();
   pb.pl_par.clear();
@@ -1107,6 +1226,30 @@ inline void MAT_init_work(Problem& pb, bool force_general_nelast = false) {
   pb.pl_beta.clear();
   for (int e = 1; e <= ne; ++e) {
     const MatInput& in = pb.mat.inputs[g.tag[e - 1] - 1];
+    if (in.visco) {  // mat_gen.f90:380-385: MAT_set_derint + MAT_VISCO_init_elem_work (mat_visco.f90:164-200)
+      if (pb.ndof != 2) IO_abort("MAT_init_work: visco-elasticity requires ndof=2 (P-SV) ");
+      if (in.kv) IO_abort("oracle: VISCO with KV not supported");
+      pb.vs_elem.push_back(e);
+      pb.elem2vs[e - 1] = (int)pb.vs_elem.size();
+      const size_t o = pb.vs_derint.size();
+      pb.vs_derint.resize(o + (size_t)5 * n2);
+      for (int j = 1; j <= n; ++j)
+        for (int i = 1; i <= n; ++i) {
+          const int k = (i - 1) + n * (j - 1);
+          double jac[4], inv[4];
+          SE_Jacobian(g, e, i, j, jac);
+          invert2(jac, inv);
+          pb.vs_derint[o + k] = inv[0];
+          pb.vs_derint[o + n2 + k] = inv[2];
+          pb.vs_derint[o + 2 * (size_t)n2 + k] = inv[1];
+          pb.vs_derint[o + 3 * (size_t)n2 + k] = inv[3];
+          pb.vs_derint[o + 4 * (size_t)n2 + k] = SE_VolumeWeight(g, e, i, j);
+        }
+      pb.vs_off.push_back(pb.vs_el.size());
+      pb.vs_el.resize(pb.vs_el.size() + (size_t)n2 * in.Nbody * 3, 0.0);
+      pb.vs_etot.resize(pb.vs_etot.size() + (size_t)3 * n2, 0.0);
+      continue;
+    }
     if (in.plastic) {  // mat_gen.f90:367-372: MAT_set_derint (:645-681) + MAT_PLAST_init_elem_work (mat_plastic.f90:148-218)
       if (pb.ndof != 2) IO_abort("MAT_init_work: plasticity requires ndof=2 (P-SV) ");
       if (in.kv) IO_abort("oracle: PLAST with KV not supported");
@@ -2196,6 +2339,65 @@ inline void compute_Fint(Problem& pb, std::vector<double>& f, const std::vector<
         dloc[k + (size_t)n2 * c] = d[(size_t)(ib[k] - 1) + np * c];
         vloc[k + (size_t)n2 * c] = v[(size_t)(ib[k] - 1) + np * c];
       }
+    if (!pb.elem2vs.empty() && pb.elem2vs[e - 1] > 0) {
+      // mat_gen.f90:451-457: e = MAT_strain(d), MAT_VISCO_stress (mat_visco.f90:206-248), f = MAT_forces(s); no 2.5D term
+      const int iv = pb.elem2vs[e - 1] - 1;
+      const MatInput& in = pb.mat.inputs[g.tag[e - 1] - 1];
+      const int NB = in.Nbody;
+      const double dt = pb.time.dt;
+      const double* D = &pb.vs_derint[(size_t)5 * n2 * iv];
+      const double *dxi_dx = D, *dxi_dy = D + n2, *deta_dx = D + 2 * n2, *deta_dy = D + 3 * n2, *wts = D + 4 * n2;
+      double* el = &pb.vs_el[pb.vs_off[iv]];          // el(ngll,ngll,Nbody,3)
+      double* eo = &pb.vs_etot[(size_t)3 * n2 * iv];  // etot_old(ngll,ngll,3)
+      std::vector<double> gx1(n2), gx2(n2), ge1(n2), ge2(n2), st((size_t)3 * n2), t1(n2), t2(n2), m1(n2), m2(n2);
+      mxm(g.Ht.data(), dloc.data(), gx1.data(), n);
+      mxm(g.Ht.data(), dloc.data() + n2, gx2.data(), n);
+      mxm(dloc.data(), g.H.data(), ge1.data(), n);
+      mxm(dloc.data() + n2, g.H.data(), ge2.data(), n);
+      const double lambda = in.lambda, two_mu = 2.0 * in.mu;
+      for (int b = 0; b < NB; ++b) {  // memory variables advanced with the strain of the previous evaluation
+        const double x = in.wbody[b] * dt;
+        const double RK = x - (x * x) / 2.0 + (x * x * x) / 6.0 - (x * x * x * x) / 24.0;
+        for (int c = 0; c < 3; ++c)
+          for (int k = 0; k < n2; ++k) {
+            double& q = el[k + (size_t)n2 * (b + (size_t)NB * c)];
+            q = q + RK * (eo[k + (size_t)n2 * c] - q);
+          }
+      }
+      for (int k = 0; k < n2; ++k) {
+        const double et1 = gx1[k] * dxi_dx[k] + ge1[k] * deta_dx[k];
+        const double et2 = gx2[k] * dxi_dy[k] + ge2[k] * deta_dy[k];
+        const double et3 = 0.5 * (gx1[k] * dxi_dy[k] + ge1[k] * deta_dy[k] + gx2[k] * dxi_dx[k] + ge2[k] * deta_dx[k]);
+        eo[k] = et1;
+        eo[n2 + k] = et2;
+        eo[2 * n2 + k] = et3;
+        double sa1 = 0, sa2 = 0, sa3 = 0;
+        for (int b = 0; b < NB; ++b) {
+          const double e1 = el[k + (size_t)n2 * (b + (size_t)NB * 0)], e2 = el[k + (size_t)n2 * (b + (size_t)NB * 1)],
+                       e3 = el[k + (size_t)n2 * (b + (size_t)NB * 2)];
+          sa1 = sa1 + in.theta[b] * e1 + in.theta[b + NB] * e2;
+          sa2 = sa2 + in.theta[b + NB] * e1 + in.theta[b] * e2;
+          sa3 = sa3 + in.theta[b + 2 * NB] * e3;
+        }
+        st[k] = (lambda + two_mu) * et1 + lambda * et2 - sa1;
+        st[n2 + k] = lambda * et1 + (lambda + two_mu) * et2 - sa2;
+        st[2 * n2 + k] = two_mu * et3 - sa3;
+      }
+      for (int c = 0; c < 2; ++c) {  // MAT_forces (mat_gen.f90:834-866)
+        const double* sa = c == 0 ? &st[0] : &st[2 * n2];
+        const double* sb = c == 0 ? &st[2 * n2] : &st[n2];
+        for (int k = 0; k < n2; ++k) {
+          t1[k] = -wts[k] * (dxi_dx[k] * sa[k] + dxi_dy[k] * sb[k]);
+          t2[k] = -wts[k] * (deta_dx[k] * sa[k] + deta_dy[k] * sb[k]);
+        }
+        mxm(g.H.data(), t1.data(), m1.data(), n);
+        mxm(t2.data(), g.Ht.data(), m2.data(), n);
+        for (int k = 0; k < n2; ++k) floc[k + (size_t)n2 * c] = m1[k] + m2[k];
+      }
+      for (int c = 0; c < ndof; ++c)
+        for (int k = 0; k < n2; ++k) f[(size_t)(ib[k] - 1) + np * c] = f[(size_t)(ib[k] - 1) + np * c] + floc[k + (size_t)n2 * c];
+      continue;
+    }
     if (!pb.elem2pl.empty() && pb.elem2pl[e - 1] > 0) {
       // mat_gen.f90:445-449: e = MAT_strain(d), MAT_PLAST_stress(update = true), f = MAT_forces(s) (, 2.5D term)
       const int ip = pb.elem2pl[e - 1] - 1;
@@ -2726,6 +2928,20 @@ inline void read_main(Problem& pb, CartSpec& cart, ParInp& in) {
           mi.coh = gp->dbl("coh", 0.0);
           mi.Tv = gp->dbl("Tv", 0.0);
           for (int q = 0; q < 3; ++q) mi.e0[q] = gp->dbl("e0", 0.0, q);
+        } else if (kinds[k] == "VISCO") {  // MAT_VISCO_read (mat_visco.f90:65-113)
+          const NmlGroup* gv = in.next("MAT_VISCO");
+          if (!gv) IO_abort("MAT_VISCO_read: MAT_VISCO input block not found");
+          mi.visco = true;
+          mi.isotropic = true;
+          mi.rho = read_cd(in, gv->dbl("rho", 0.0), "");
+          mi.cp = read_cd(in, gv->dbl("cp", 0.0), "");
+          mi.cs = read_cd(in, gv->dbl("cs", 0.0), "");
+          mi.QP = gv->dbl("QP", 0.0);
+          mi.QS = gv->dbl("QS", 0.0);
+          mi.Nbody = (int)gv->dbl("Nbody", 0.0);
+          mi.fmin = gv->dbl("fmin", 0.0);
+          mi.fmax = gv->dbl("fmax", 0.0);
+          if (mi.Nbody < 1 || mi.Nbody > 8) IO_abort("oracle: MAT_VISCO Nbody must be in 1..8");
         } else if (kinds[k] == "") {
         } else {
           IO_abort("oracle: material kind not supported: " + kinds[k]);

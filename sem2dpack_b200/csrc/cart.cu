@@ -769,7 +769,7 @@ int s2d_cart_create(s2d_handle* out, const s2d_cart_desc* D) {
     G.halo_right = D->halo_right;
     gll_tables(G.N, G.xgll, G.wgll, S->H);
     // strip decomposition of the z-marching kernel (strip_kernels.cuh)
-    G.S = make_strip_geom(G.N, G.ndof, G.nx, G.nz, G.ezflt, env_int("S2D_SEG", 32), G.halo_left != 0, G.halo_right != 0);
+    G.S = make_strip_geom(G.N, G.ndof, G.nx, G.nz, G.ezflt, strip_default_seg(G.N, G.nx, G.nz), G.halo_left != 0, G.halo_right != 0);
     const long long npoin = cart_npoin(G);
     const long long nelem = (long long)G.nx * G.nz;
     if (npoin != (long long)G.S.LX * G.S.LZ) {
@@ -874,6 +874,21 @@ int s2d_cart_set_plastic(s2d_handle h, int32_t nsets, const double* par, const i
     ps[strip_elem_slot(G.S, e % G.nx, e / G.nx)] = (unsigned char)elem_set[e];
   }
   Eb->set_strip_plastic(ps.data(), ps.size(), nsets, par);
+  CART_GUARD_END
+}
+
+int s2d_cart_set_visco(s2d_handle h, int32_t nsets, const int32_t* nbody, const double* moduli, const double* wbody,
+                       const double* theta, const int32_t* elem_set) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(nsets >= 1 && nbody && moduli && wbody && theta && elem_set, "cart_set_visco: bad arguments");
+  S2D_REQUIRE(!Eb->committed, "cart_set_visco after commit");
+  const CartGeom& G = S.G;
+  std::vector<unsigned char> ps((size_t)Eb->nelem, 0);
+  for (int e = 0; e < Eb->nelem; ++e) {
+    S2D_REQUIRE(elem_set[e] >= 0 && elem_set[e] <= nsets, "cart_set_visco: material set out of range");
+    ps[strip_elem_slot(G.S, e % G.nx, e / G.nx)] = (unsigned char)elem_set[e];
+  }
+  Eb->set_strip_visco(ps.data(), ps.size(), nsets, nbody, moduli, wbody, theta);
   CART_GUARD_END
 }
 

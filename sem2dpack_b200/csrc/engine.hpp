@@ -91,6 +91,8 @@ class EngineBase {
   virtual void set_strip_eta(const double* eta_strip, size_t n) = 0;
   virtual void set_strip_plastic(const unsigned char* set_strip, size_t n, int nsets, const double* raw) = 0;
   virtual void get_strip_plastic_strain(double* ep_strip) = 0;
+  virtual void set_strip_visco(const unsigned char* set_strip, size_t n, int nsets, const int32_t* nbody, const double* moduli,
+                               const double* wbody, const double* theta) = 0;
   virtual void commit(int variant) = 0;
   virtual void set_fields(const double* d, const double* v, const double* a) = 0;
   virtual void get_fields(double* d, double* v, double* a) = 0;
@@ -328,6 +330,9 @@ class Engine : public EngineBase {
       io.pl_set = pl_set.p;
       io.pl_ep = pl_ep.p;
       io.pl_tab = pl_tab.p;
+      io.vs_state = vs_state.n ? vs_state.p : nullptr;
+      io.vs_tab = vs_tab.p;
+      io.vs_nb = vs_nb;
     }
     return io;
   }
@@ -874,6 +879,31 @@ class Engine : public EngineBase {
     for (int k = 0; k < nsets; ++k)
       for (int q = 0; q < 6; ++q) pl_raw[k + 1][q] = raw[(size_t)6 * k + q];
   }
+  void set_strip_visco(const unsigned char* set_strip, size_t n, int nsets, const int32_t* nbody, const double* moduli,
+                       const double* wbody, const double* theta) override {
+    S2D_REQUIRE(cart_mode && !committed, "set_strip_visco: builder-made engines only, before commit");
+    S2D_REQUIRE(n == (size_t)nelem && nsets >= 1 && nsets < STRIP_PL_SETS, "set_strip_visco: 1..7 visco-elastic material sets");
+    S2D_REQUIRE(ndof == 2 && cart_compact && ngll <= STRIP_PLAST_MAXN,
+                "MAT_init_work: visco-elasticity requires ndof=2 (P-SV), an isotropic box and ngll <= 6");
+    S2D_REQUIRE(pl_ep.n == 0, "plastic and visco-elastic elements in one problem: not provided");
+    vs_nb = 0;
+    for (int k = 0; k < nsets; ++k) {
+      S2D_REQUIRE(nbody[k] >= 1 && nbody[k] <= STRIP_VS_MAXB, "set_strip_visco: Nbody must be in 1..8");
+      vs_nb = std::max(vs_nb, (int)nbody[k]);
+      double* r = vs_raw[k + 1];
+      r[0] = moduli[2 * k];
+      r[1] = moduli[2 * k + 1];
+      r[2] = (double)nbody[k];
+      for (int b = 0; b < nbody[k]; ++b) {
+        r[3 + b] = wbody[(size_t)STRIP_VS_MAXB * k + b];
+        for (int c = 0; c < 3; ++c) r[3 + (c + 1) * STRIP_VS_MAXB + b] = theta[((size_t)k * 3 + c) * STRIP_VS_MAXB + b];
+      }
+    }
+    pl_set.alloc(n);
+    h2d_sync(pl_set.p, set_strip, n);
+    vs_state.alloc((size_t)nelem * 3 * (vs_nb + 1) * ngll * ngll);
+    vs_state.zero();
+  }
   void get_strip_plastic_strain(double* ep_strip) override {
     S2D_REQUIRE(pl_ep.n > 0, "no plastic elements");
     S2D_CUDA(cudaStreamSynchronize(stream));
@@ -979,7 +1009,7 @@ class Engine : public EngineBase {
       }
     StructuredBox B = detect_structured(h_ibool.data(), ngll, nelem, npoin, hint);
     if (!B.ok) return false;
-    const StripGeom S = make_strip_geom(ngll, ndof, B.nx, B.nz, B.ezflt, env_int("S2D_SEG", 32), false, false);
+    const StripGeom S = make_strip_geom(ngll, ndof, B.nx, B.nz, B.ezflt, strip_default_seg(ngll, B.nx, B.nz), false, false);
     const size_t nlat = (size_t)S.LXP * S.LZ, nref = npoin;
     if (nlat > 2147483647ull) return false;
     // The fused update reads ONE inverse mass per node for the nodes no boundary condition touches (the reference's
@@ -1116,6 +1146,11 @@ class Engine : public EngineBase {
   // point, per set (coh, phi [deg], Tv, e0(3)) as read and (yield_co, yield_mu, vp_factor, e0(3)) as the kernel uses them
   DevBuf<unsigned char> pl_set;
   DevBuf<T> pl_ep, pl_tab;
+  // visco-elasticity (mat_visco.f90): the element sets share pl_set; memory variables + previous strain per element
+  // GLL point; per set lambda_inf, mu_inf, Nbody, wbody(8) [RK factors once dt is known], theta(8,3)
+  DevBuf<T> vs_state, vs_tab;
+  int vs_nb = 0;
+  double vs_raw[STRIP_PL_SETS][STRIP_VS_TAB] = {};
   bool a_stale = false;                // the fused leapfrog step left the accelerations of the nodes it advanced unwritten
   bool accel_lazy = env_int("S2D_ACCEL_LAZY", 1) != 0;
   double pl_raw[STRIP_PL_SETS][6] = {}, pl_par[STRIP_PL_SETS][6] = {};
@@ -1286,7 +1321,18 @@ class Engine : public EngineBase {
         S2D_CUDA(cudaStreamSynchronize(stream));
         cart_kv_eta.release();
       }
-      if (pl_set.n) {  // MAT_PLAST_init_elem_work (mat_plastic.f90:165-184); set 0 (elastic elements) never yields
+      if (vs_state.n) {  // RK_factor of MAT_VISCO_stress (mat_visco.f90:222-224), now that dt is known
+        S2D_REQUIRE(strip_eta.n == 0, "visco-elastic elements together with Kelvin-Voigt elements: not provided");
+        double tab[STRIP_PL_SETS][STRIP_VS_TAB];
+        std::memcpy(tab, vs_raw, sizeof(tab));
+        for (int k = 1; k < STRIP_PL_SETS; ++k)
+          for (int b = 0; b < (int)vs_raw[k][2]; ++b) {
+            const double x = vs_raw[k][3 + b] * scheme.dt;
+            tab[k][3 + b] = x - (x * x) / 2.0 + (x * x * x) / 6.0 - (x * x * x * x) / 24.0;
+          }
+        upload_as(vs_tab, &tab[0][0], (size_t)STRIP_PL_SETS * STRIP_VS_TAB);
+      }
+      if (pl_set.n && !vs_state.n) {  // MAT_PLAST_init_elem_work (mat_plastic.f90:165-184); set 0 (elastic elements) never yields
         S2D_REQUIRE(strip_eta.n == 0, "plastic elements together with Kelvin-Voigt elements: not provided");
         for (int k = 1; k < STRIP_PL_SETS; ++k) {
           const double phi = 3.141592653589793 / 180.0 * pl_raw[k][1];
@@ -1625,7 +1671,7 @@ class Engine : public EngineBase {
     // 8 B/DOF of stores per s2d_step call.  Where that evaluation is not repeatable (state advanced by every
     // evaluation: plasticity; Kelvin-Voigt: v already updated) or needs the neighbours (x-strips), the last step of
     // every call stores them as before.
-    const bool lazy_ok = store_accel == 2 && accel_lazy && !nmk && !xhalo() && strip_eta.n == 0 && pl_set.n == 0;
+    const bool lazy_ok = store_accel == 2 && accel_lazy && !nmk && !xhalo() && strip_eta.n == 0 && pl_set.n == 0;  // pl_set: plastic or visco
     const bool want_a = nmk || store_accel == 1 ||
                         (store_accel == 2 && ((last_of_call && !lazy_ok) || (rec.present && rec.field == 'A')));
     a_stale = !want_a;

@@ -33,6 +33,7 @@
 // Coefficient planes are stored per (band, strip, element row) as [plane pair][j][lane] 16-byte
 // vectors: every warp load is one contiguous run, the whole array is read exactly once per step.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "elem_kernels.cuh"
 #include "tensor_map.hpp"
@@ -203,6 +204,7 @@ template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 
+constexpr int STRIP_VS_MAXB = 8, STRIP_VS_TAB = 3 + 4 * STRIP_VS_MAXB;  // visco: mechanisms per material, table row
 constexpr int STRIP_PL_SETS = 8;  // plastic material sets per problem (set 0 = elastic elements)
 // position of plastic-strain component k at GLL point (i,j) of element (ix,iz)
 __host__ __device__ inline size_t strip_ep_index(const StripGeom& G, int ix, int iz, int i, int j, int k) {
@@ -259,6 +261,12 @@ struct StripArgs {
   const unsigned char* pl_set;
   T* pl_ep;
   const T* pl_tab;          // [STRIP_PL_SETS][6] on the device
+  // visco-elasticity (MAT_VISCO_stress, mat_visco.f90:206-248; the same instantiation, vs_state != null): memory
+  // variables el(Nbody,3) and the strain of the previous evaluation per element GLL point, planes
+  // [3 b + c | 3 vs_nb + c][j][lane] per element row of a strip; per set lambda_inf, mu_inf, Nbody, RK(8), theta(8,3)
+  T* vs_state;
+  const T* vs_tab;          // [STRIP_PL_SETS][STRIP_VS_TAB]
+  int vs_nb;                // memory-variable planes per component in the state layout (max Nbody over the sets)
   int prefetch;             // L2 prefetch of what is not staged
   T H[N * N];               // hprime, column-major (constant bank)
   // compact coefficient mode (isotropic flat grids): only (lambda, mu) are stored per GLL point and
@@ -336,6 +344,15 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group
 // registers, 3 CTAs/SM: 5.82;  5 warps (128 registers, 3 CTAs/SM): 6.02;  6 warps (168, 2 CTAs): 6.41;
 // 8 warps (128, 2 CTAs): 6.58 -- registers (instruction-level parallelism) beat resident warps here.
 constexpr int strip_warps() { return S2D_STRIP_WARPS; }
+// element rows per band: S2D_SEG if set, else 64 when that still leaves every SM a dozen waves of CTAs, else 32.
+// Measured with the tensor-map kernel (FP64 compact fused, ms per step): 4096^2 5.92 (32) / 5.80 (48) / 5.78 (64) /
+// 5.98 (128); 8192^2 24.74-24.95 (32) / 24.37-24.40 (64) / 24.27 (96) / 24.33 (128).
+inline int strip_default_seg(int N, int nx, int nz) {
+  const char* v = std::getenv("S2D_SEG");
+  if (v && *v) return std::atoi(v);
+  const long long groups = ((long long)nx + (32 / N) * strip_warps() - 1) / ((32 / N) * strip_warps());
+  return ((long long)((nz + 63) / 64) * groups >= 12LL * 148 * 3) ? 64 : 32;
+}
 // bytes of the staging area of one warp: coefficient vectors and displacement rows of one element
 // row; in the fused form also the velocities and inverse masses of the nodes it will advance
 // (fused: 0 plain force evaluation, 1 leapfrog update, 2 explicit Newmark update: also the old accelerations)
@@ -583,6 +600,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   T* epp = PLAST ? A.pl_ep + (size_t)strip_elem_off(G, seg, strip, ez0) * (3 * N * N) + lanep : nullptr;
   const unsigned char* plp = PLAST ? A.pl_set + strip_elem_off(G, seg, strip, ez0) + el : nullptr;
   int pset_next = (PLAST && wact) ? (int)*plp : 0;
+  T* vsp = (PLAST && A.vs_state) ? A.vs_state + (size_t)strip_elem_off(G, seg, strip, ez0) * (3 * (A.vs_nb + 1)) * (N * N) + lanep : nullptr;
   const int cxN = cx * N;
   const V2* cp = reinterpret_cast<const V2*>(A.coef) +
                  (size_t)strip_elem_off(G, seg, strip, ez0) * (NPL * N * N / 2) + lanep;
@@ -623,7 +641,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           }
       }
     }
-    if constexpr (PLAST && S2D_PLAST_STAGE != 0) {  // the plastic strain of the row's elements travels with its displacements
+    if (PLAST && S2D_PLAST_STAGE != 0 && A.vs_state == nullptr) {  // the plastic strain of the row's elements travels with its displacements
       const T* en = A.pl_ep + (size_t)strip_elem_off(G, seg, strip, ezr) * (3 * N * N) + lanep;
 #pragma unroll
       for (int k = 0; k < 3 * N; ++k) stage_copy<sizeof(T)>(st_e + k * 32, en + (size_t)k * cxN);
@@ -710,6 +728,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       // plasticity: the element's plastic strain and material set, requested before anything else of this row
       T epr[PLAST ? 3 : 1][PLAST ? N : 1], ppar[PLAST ? 6 : 1];
       bool yielded = false;
+      int vset = 0;
       if constexpr (PLAST) {
         // shadow lanes (el >= cx) mirror the last element -- they write the same tile slots, so they must see
         // the same state; only real lanes store it back
@@ -721,7 +740,8 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
 #pragma unroll
           for (int j = 0; j < N; ++j) epr[k][j] = S2D_PLAST_STAGE ? st_e[(k * N + j) * 32] : __ldcs(epp + (size_t)(k * N + j) * cxN);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) ppar[q] = __ldg(A.pl_tab + pset * 6 + q);
+        for (int q = 0; q < 6; ++q) ppar[q] = A.vs_state ? (T)0 : __ldg(A.pl_tab + pset * 6 + q);
+        vset = pset;
       }
       if constexpr (TENS) {
         const int kk = ez - ez0;
@@ -893,6 +913,50 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       T tH[NDOF][N], tHt[NDOF][N];
 #pragma unroll
       for (int j = 0; j < N; ++j) {
+        if (PLAST && A.vs_state != nullptr) {
+          // generalized Maxwell body: the memory variables of every mechanism relax towards the strain of the
+          // PREVIOUS evaluation (4th-order expansion of 1 - exp(-w dt), mat_visco.f90:221-229), the strain is kept
+          // for the next one, the anelastic stress is taken off the unrelaxed elastic one (:236-246)
+          const T* tb = A.vs_tab + vset * STRIP_VS_TAB;
+          const T la = vset ? __ldg(tb) : a2[0][j].x, two_mu = T(2) * (vset ? __ldg(tb + 1) : a2[0][j].y);
+          const int nb = vset ? (int)__ldg(tb + 2) : 0;
+          const T e1 = gxi[0][j], e2 = get[1][j], e3 = T(0.5) * (get[0][j] + gxi[1][j]);
+          const size_t pstr = (size_t)N * cxN;   // one plane of the element row's block
+          T* sp = vsp + (size_t)j * cxN;
+          T* so = sp + (size_t)(3 * A.vs_nb) * pstr;
+          const T o1 = so[0], o2 = so[pstr], o3 = so[2 * pstr];
+          T sa1 = 0, sa2 = 0, sa3 = 0;
+          for (int b = 0; b < nb; ++b) {
+            const T rk = __ldg(tb + 3 + b), th1 = __ldg(tb + 3 + STRIP_VS_MAXB + b), th2 = __ldg(tb + 3 + 2 * STRIP_VS_MAXB + b),
+                    th3 = __ldg(tb + 3 + 3 * STRIP_VS_MAXB + b);
+            T* sb = sp + (size_t)(3 * b) * pstr;
+            T q1 = sb[0], q2 = sb[pstr], q3 = sb[2 * pstr];
+            q1 = q1 + rk * (o1 - q1);
+            q2 = q2 + rk * (o2 - q2);
+            q3 = q3 + rk * (o3 - q3);
+            if (real) {
+              sb[0] = q1;
+              sb[pstr] = q2;
+              sb[2 * pstr] = q3;
+            }
+            sa1 = sa1 + th1 * q1 + th2 * q2;
+            sa2 = sa2 + th2 * q1 + th1 * q2;
+            sa3 = sa3 + th3 * q3;
+          }
+          if (real && vset) {
+            so[0] = e1;
+            so[pstr] = e2;
+            so[2 * pstr] = e3;
+          }
+          const T s1 = (la + two_mu) * e1 + la * e2 - sa1;
+          const T s2 = la * e1 + (la + two_mu) * e2 - sa2;
+          const T s3 = two_mu * e3 - sa3;
+          tH[0][j] = nW[j] * s1;
+          tHt[0][j] = nW[j] * s3;
+          tH[1][j] = nW[j] * s3;
+          tHt[1][j] = nW[j] * s2;
+          continue;
+        }
         if constexpr (PLAST) {
           // MAT_strain_PSV (mat_gen.f90:752-775) on the flat box: e11 = Ux,x  e22 = Uz,z  e12 = (Ux,z + Uz,x)/2;
           // MAT_PLAST_stress with update (mat_plastic.f90:297-377): trial stress from the absolute elastic strain,
@@ -976,6 +1040,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         }
       }
       if constexpr (PLAST) {
+        if (A.vs_state != nullptr) vsp += (size_t)gcx * (3 * (A.vs_nb + 1)) * (N * N);
         if (real && yielded) {  // an element that did not yield leaves its plastic strain as it is in HBM
 #pragma unroll
           for (int k = 0; k < 3; ++k)
@@ -1494,6 +1559,9 @@ struct StripIO {
   const unsigned char* pl_set = nullptr;  // Coulomb plasticity (see StripArgs)
   T* pl_ep = nullptr;
   const T* pl_tab = nullptr;
+  T* vs_state = nullptr;                  // visco-elasticity (see StripArgs)
+  const T* vs_tab = nullptr;
+  int vs_nb = 0;
   const T* beta = nullptr;  // 2.5D: beta per element GLL point (strip layout)
   // tensor-map staging of the fused leapfrog kernel (null: per-lane copies)
   const CUtensorMap* tm_d = nullptr;
@@ -1600,6 +1668,9 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
         A.pl_set = io.pl_set;                                                                     \
         A.pl_ep = io.pl_ep;                                                                       \
         A.pl_tab = io.pl_tab;                                                                     \
+        A.vs_state = io.vs_state;                                                                 \
+        A.vs_tab = io.vs_tab;                                                                     \
+        A.vs_nb = io.vs_nb;                                                                       \
         constexpr int MP = sizeof(T) == 8 ? S2D_PLAST_MINB : 3;                                   \
         if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, true>(nb, A, s);         \
         else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, true>(nb, A, s);    \

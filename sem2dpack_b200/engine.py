@@ -370,6 +370,21 @@ class CartEngine(Engine):
         elem_set = _i32(elem_set)
         self._ck(self.L.s2d_cart_set_plastic(self.h, par.shape[0], _ptr(par), _ptr(elem_set)))
 
+    def set_visco(self, nbody, moduli, wbody, theta, elem_set):
+        """per visco-elastic material: Nbody, (lambda_inf, mu_inf), wbody (<= 8), theta (Nbody, 3) as get_attenuation
+        returns them; elem_set (nelem) natural order, 0 = elastic (s2d_cart_set_visco)"""
+        nbody = _i32(nbody)
+        ns = nbody.size
+        wb = np.zeros((ns, 8))
+        th = np.zeros((ns, 3, 8))
+        for k in range(ns):
+            nb = int(nbody[k])
+            wb[k, :nb] = np.asarray(wbody[k])[:nb]
+            th[k, :, :nb] = np.asarray(theta[k]).reshape(nb, 3).T
+        mod = _f64(moduli).reshape(ns, 2)
+        elem_set = _i32(elem_set)
+        self._ck(self.L.s2d_cart_set_visco(self.h, ns, _ptr(nbody), _ptr(mod), _ptr(wb), _ptr(th), _ptr(elem_set)))
+
     def plastic_strain(self):
         """ep (nelem, 3, ngll, ngll), natural element order (s2d_cart_get_plastic_strain)"""
         out = np.empty((self.nelem, 3, self.ngll, self.ngll))

@@ -438,3 +438,38 @@ def test_plastic_and_elastic_elements_in_one_box(monkeypatch):
     _plastic_evaluations(e, o, ngll, nx, nz, np.flatnonzero(tag.ravel() == 1))
     e.close()
     o.close()
+
+
+@pytest.mark.parametrize("ngll,nx,nz,ezflt,seg,nbody", [(5, 27, 11, 0, 3, 3), (6, 23, 10, 3, 3, 5), (4, 9, 7, 0, 32, 1), (3, 47, 8, 4, 5, 8)])
+def test_visco_elastic_force_evaluations(ngll, nx, nz, ezflt, seg, nbody, monkeypatch):
+    """Visco-elasticity in the strip kernel (s2d_cart_set_visco): MAT_strain_PSV -> MAT_VISCO_stress -> MAT_forces
+    (mat_gen.f90:451-457, mat_visco.f90:206-248).  Every force evaluation relaxes the Nbody memory variables of each
+    element GLL point towards the strain of the previous evaluation and keeps the new strain, so four successive
+    evaluations on different displacements test the whole state; theta, wbody and the unrelaxed moduli come from the
+    oracle's get_attenuation (mat_visco.f90:251-340), as a Fortran host would hand them over."""
+    monkeypatch.setenv("S2D_SEG", str(seg))
+    h = 100.0
+    L = [f"&GENERAL iexec=1, ngll={ngll}, fmax=3.d0, ndof=2, title='visco', verbose='0000', ItInfo=1000 /",
+         "&MESH_DEF method='CARTESIAN' /",
+         f"&MESH_CART xlim=0d0,{nx*h}d0, zlim=0d0,{nz*h}d0, nelem={nx},{nz}" + (f", ezflt={ezflt}" if ezflt else "") + " /",
+         "&MATERIAL tag=1, kind='VISCO' /",
+         f"&MAT_VISCO rho=2000d0, cp=3000d0, cs=2000d0, QP=30d0, QS=20d0, Nbody={nbody}, fmin=1.8d0, fmax=180d0 /",
+         "&TIME NbSteps=10, courant=0.5d0, kind='leapfrog' /"]
+    o = orc.Oracle("\n".join(L) + "\n", renumber=False)
+    assert o.i("nvs") == nx * nz
+    e = CartEngine(ngll, 2, nx, nz, (0.0, nx * h), (0.0, nz * h), ezflt=ezflt, seed=0, rho=2000.0, cp=3000.0, cs=2000.0)
+    e.set_dt(o.f("dt"))
+    e.set_visco([nbody], o.arr("mat.1.moduli"), [o.arr("mat.1.wbody")], [o.arr("mat.1.theta").reshape(3, nbody).T],
+                np.ones(nx * nz, np.int32))
+    e.commit()
+    rng = np.random.default_rng(ngll * 100 + nx)
+    for k in range(4):
+        d = rng.standard_normal(e.npoin * 2) * 1e-3
+        e.set_fields(d, d)
+        o.set_fields(d, d)
+        ref = o.compute_fint()
+        got = e.compute_fint()
+        assert rel_l2(got, ref) <= 1e-12, (k, rel_l2(got, ref))
+    assert np.abs(o.arr("vs_el")).max() > 0
+    e.close()
+    o.close()

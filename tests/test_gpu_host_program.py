@@ -396,3 +396,37 @@ def test_plastic_deck_coulomb_yielding_off_the_fault(tmp_path, nsteps, coh):
     for c in range(6):
         assert np.abs(rec[:, c] - want[:, c]).max() <= 1e-6 * max(np.abs(want[:, c]).max(), 1e-30), c
     o.close()
+
+
+def test_attenuation_deck_visco_elastic_medium(tmp_path):
+    """EXAMPLES/Attenuation (kind='VISCO': Nbody = 5 mechanisms fitted to QP = 30, QS = 20 over 1.8-180 Hz, NGLL 6,
+    Ricker force, four absorbing sides), first 500 of 1004 steps: the host evaluates get_attenuation (its own
+    least-squares solver) and hands theta / wbody / unrelaxed moduli to s2d_cart_set_visco; the seismogram and the
+    velocity snapshot against the oracle, and against an elastic run of the same deck (the pulse must be damped).
+    No reference artefact pins this deck (benchmark_attenuation.m needs an external analytical code): oracle parity."""
+    nsteps = 500
+    deck = harness.deck("attenuation").replace("TotalTime=0.75d0", f"NbSteps={nsteps}").replace("itd=10000", f"itd={nsteps}")
+    assert f"NbSteps={nsteps}" in deck and f"itd={nsteps}" in deck
+    p = run(tmp_path, deck, "--quiet", "--natural-order")
+    assert p.returncode == 0, p.stdout + p.stderr
+    o = orc.Oracle(deck, renumber=False)
+    assert o.i("nvs") == 44 * 44
+    o.step(nsteps)
+    dt, coord, ux = read_sep(tmp_path, "Ux_sem2d.dat")
+    ref = o.seis()[:, 0, 0]
+    assert ux.shape[0] == ref.shape[0]
+    assert np.abs(ux[:, 0] - ref).max() <= 2e-6 * np.abs(ref).max()
+    n = o.i("npoin")
+    vref = o.arr("v").reshape(2, n)
+    got = np.fromfile(tmp_path / "vx_001_sem2d.dat", dtype=np.float32)
+    assert np.abs(got - vref[0].astype(np.float32)).max() <= 2e-6 * np.abs(vref[0]).max()
+    # the same deck without attenuation: larger peak at the receiver
+    el = deck.replace("kind='VISCO'", "kind='ELAST'").replace(
+        "&MAT_VISCO rho=2000d0, cp=3000d0, cs=2000d0, QP=30d0, QS=20d0, Nbody=5,fmin=1.8d0,fmax=180d0 /",
+        "&MAT_ELASTIC rho=2000d0, cp=3000d0, cs=2000d0 /")
+    assert "MAT_ELASTIC" in el
+    oe = orc.Oracle(el, renumber=False)
+    oe.step(nsteps)
+    assert np.abs(oe.seis()[:, 0, 0]).max() > 1.1 * np.abs(ref).max()
+    oe.close()
+    o.close()
