@@ -186,6 +186,18 @@ module sem2d_b200
       real(c_double), intent(in) :: par(6,*)                 ! coh, phi, Tv, e0(3) of every PLAST material (mat_plastic.f90:66-118)
       integer(c_int), intent(in) :: elem_set(*)              ! 0 = elastic element, k = plastic material k
     end function
+    integer(c_int) function s2d_cart_set_damage(h, nsets, par, elem_set) bind(C, name='s2d_cart_set_damage')
+      import
+      type(c_ptr), value :: h
+      integer(c_int), value :: nsets
+      real(c_double), intent(in) :: par(13,*)                ! lambda, mu, phi, alpha, Cd, beta, R, e0(3), ep(3) (mat_damage.f90:108-173)
+      integer(c_int), intent(in) :: elem_set(*)              ! 0 = elastic element, k = damage material k
+    end function
+    integer(c_int) function s2d_cart_get_damage_state(h, state) bind(C, name='s2d_cart_get_damage_state')
+      import
+      type(c_ptr), value :: h
+      real(c_double), intent(out) :: state(*)                ! (ngll,ngll,4,nelem): matwrk%dmg%alpha, %ep(:,:,1:3)
+    end function
     integer(c_int) function s2d_cart_set_visco(h, nsets, nbody, moduli, wbody, theta, elem_set) bind(C, name='s2d_cart_set_visco')
       import
       type(c_ptr), value :: h

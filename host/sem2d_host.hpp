@@ -200,6 +200,7 @@ struct bc_type {
   std::vector<double> MU0;   // initial friction coefficient of the output nodes (FltXX_init_sem2d.tab)
   // general &BC_DYNFLT (SRC/bc_dynflt.f90:104-229): constants or distributions, one or two friction laws
   cd_type cd_Tn, cd_Tt, cd_cohesion, cd_V;
+  cd_type cd_S[5];   // background stress Sxx, Sxy, Sxz, Syz, Szz (SRC/bc_dynflt.f90:165-169,376-400)
   bool opening = true, has_swf = false, has_rsf = false;
   int swf_kind = 1, rsf_kind = 1, nor_kind = 1;
   bool has_twf = false;                                                  // SRC/bc_dynflt_twf.f90:12-16
@@ -233,6 +234,8 @@ struct problem_type {
     bool set = false, kv = false, ETAxDT = true;
     bool plastic = false;                        // kind='PLAST' (&MAT_PLASTIC, SRC/mat_plastic.f90:46-118)
     double phi = 0, coh = 0, Tv = 0, e0[3] = {0, 0, 0};
+    bool damage = false;                         // kind='DMG' (&MAT_DAMAGE, SRC/mat_damage.f90:80-173): phi, e0 above
+    double Cd = 0, Rdmg = 0, beta = 0, alpha0 = 0, ep0[3] = {0, 0, 0};
     bool visco = false;                          // kind='VISCO' (&MAT_VISCO, SRC/mat_visco.f90:42-113)
     double QP = 0, QS = 0, fmin = 0, fmax = 0;
     int Nbody = 0;
@@ -244,6 +247,7 @@ struct problem_type {
   bool has_kv = false;
   bool has_plastic = false;
   bool has_visco = false;
+  bool has_damage = false;
   timescheme_type time;
   std::vector<bc_type> bc;
   std::vector<source_type> src;
@@ -411,6 +415,27 @@ inline void read_main(problem_type& pb, const std::string& file) {
       pb.has_plastic = true;
       continue;
     }
+    if (k1 == "DMG") {  // MAT_DMG_read (SRC/mat_damage.f90:108-173): constants only
+      if (!k2.empty()) IO_abort("MAT_read: kind='DMG' combined with '" + k2 + "' is not on the B200 path");
+      const long m = in.find("MAT_DAMAGE", (size_t)m0);
+      if (m < 0) IO_abort("MAT_DMG_read: MAT_DAMAGE input block not found");
+      const nml_group& e = in.at((size_t)m);
+      M.rho.c = e.real8("rho", 0.0);
+      M.cp.c = e.real8("cp", 0.0);
+      M.cs.c = e.real8("cs", 0.0);
+      if (!(M.rho.c > 0) || !(M.cp.c > 0) || !(M.cs.c > 0)) IO_abort("MAT_DMG_read: incomplete input (rho, cp, cs)");
+      M.phi = e.real8("phi", 0.0);
+      M.alpha0 = e.real8("alpha", 0.0);
+      M.Cd = e.real8("cd", 0.0);
+      M.beta = e.real8("beta", 0.0);
+      M.Rdmg = e.real8("r", 0.0);
+      for (int q = 0; q < 3; ++q) M.e0[q] = e.real8("e0", 0.0, (size_t)q);
+      for (int q = 0; q < 3; ++q) M.ep0[q] = e.real8("ep", 0.0, (size_t)q);
+      M.damage = true;
+      M.set = true;
+      pb.has_damage = true;
+      continue;
+    }
     if (k1 == "VISCO") {  // MAT_VISCO_read (SRC/mat_visco.f90:65-113): constants only
       if (!k2.empty()) IO_abort("MAT_read: kind='VISCO' combined with '" + k2 + "' is not on the B200 path");
       const long m = in.find("MAT_VISCO", (size_t)m0);
@@ -433,7 +458,7 @@ inline void read_main(problem_type& pb, const std::string& file) {
       continue;
     }
     if (k1 != "ELAST" || !(k2.empty() || k2 == "KV"))
-      IO_abort("MAT_read: only kind='ELAST', kind='ELAST','KV', kind='PLAST' and kind='VISCO' are on the B200 path (DMG is not)");
+      IO_abort("MAT_read: only kind='ELAST', kind='ELAST','KV', kind='PLAST', kind='VISCO' and kind='DMG' are on the B200 path");
     const long m = in.find("MAT_ELASTIC", (size_t)m0);
     if (m < 0) IO_abort("MAT_ELAST_read: MAT_ELASTIC input block not found");
     const nml_group& e = in.at((size_t)m);  // SRC/mat_elastic.f90:104-129
@@ -502,12 +527,14 @@ inline void read_main(problem_type& pb, const std::string& file) {
       bc.otd = f->real8("otd", 0.0);
       bc.opening = f->logical("opening", true);
       if (f->logical("osides", false)) IO_abort("BC_DYNFLT_read: osides=T is not provided here");
-      for (const char* key : {"sxx", "sxy", "sxz", "syz", "szz", "sxxh", "sxyh", "sxzh", "syzh", "szzh"})
-        if (f->has(key)) IO_abort(std::string("BC_DYNFLT_read: background stress '") + key + "' is not provided here");
       size_t cur = (size_t)(f - &in.at(0)) + 1;  // distributions are read forward from the block (bc_dynflt.f90:164-172)
       bc.cd_cohesion = DIST_CD_Read(in, *f, "cohesion", 0.0, cur);
       bc.cd_Tn = DIST_CD_Read(in, *f, "tn", 0.0, cur);
       bc.cd_Tt = DIST_CD_Read(in, *f, "tt", 0.0, cur);
+      {
+        static const char* skey[5] = {"sxx", "sxy", "sxz", "syz", "szz"};
+        for (int q = 0; q < 5; ++q) bc.cd_S[q] = DIST_CD_Read(in, *f, skey[q], 0.0, cur);
+      }
       bc.cd_V = DIST_CD_Read(in, *f, "v", 1e-12, cur);
       for (size_t q = 0; q < f->count("friction") || q < 1; ++q) {
         const std::string law = f->text("friction", "SWF", q);
@@ -816,9 +843,27 @@ inline void init_main(problem_type& pb) {
     s2d_check(pb, s2d_cart_info(pb.gpu, &pb.npoin, &pb.nelem_total, &dt), "init_main");
   }
   if (pb.W > 0.0) s2d_check(pb, s2d_cart_set_w25d(pb.gpu, pb.W), "MAT_ELAST_init_25D");
+  if (pb.has_damage) {  // MAT_DMG_init_elem_prop / _work (SRC/mat_damage.f90:176-279): one set per DMG tag
+    if (pb.ndof != 2) IO_abort("MAT_init_work: the damage rheology requires ndof=2 (P-SV) ");
+    if (pb.has_plastic || pb.has_kv || pb.has_visco) IO_abort("MAT_read: DMG together with PLAST, VISCO or KV materials is not on the B200 path");
+    std::vector<int> set_of_tag(pb.mat.size(), 0);
+    std::vector<double> par;
+    int nsets = 0;
+    for (size_t tg = 0; tg < pb.mat.size(); ++tg) {
+      const auto& M = pb.mat[tg];
+      if (!M.damage) continue;
+      set_of_tag[tg] = ++nsets;
+      const double lam = M.rho.c * (M.cp.c * M.cp.c - 2.0 * M.cs.c * M.cs.c), mu = M.rho.c * M.cs.c * M.cs.c;
+      const double row[13] = {lam, mu, M.phi, M.alpha0, M.Cd, M.beta, M.Rdmg, M.e0[0], M.e0[1], M.e0[2], M.ep0[0], M.ep0[1], M.ep0[2]};
+      par.insert(par.end(), row, row + 13);
+    }
+    std::vector<int32_t> eset((size_t)pb.nelem_total);
+    for (size_t e = 0; e < eset.size(); ++e) eset[e] = set_of_tag[(size_t)tag[e] - 1];
+    s2d_check(pb, s2d_cart_set_damage(pb.gpu, nsets, par.data(), eset.data()), "MAT_DMG_init_elem_work");
+  }
   if (pb.has_visco) {  // MAT_VISCO_init_elem_prop (SRC/mat_visco.f90:116-161): get_attenuation per VISCO tag
     if (pb.ndof != 2) IO_abort("MAT_init_work: visco-elasticity requires ndof=2 (P-SV) ");
-    if (pb.has_plastic || pb.has_kv) IO_abort("MAT_read: VISCO together with PLAST or KV materials is not on the B200 path");
+    if (pb.has_plastic || pb.has_kv || pb.has_damage) IO_abort("MAT_read: VISCO together with PLAST, DMG or KV materials is not on the B200 path");
     std::vector<int> set_of_tag(pb.mat.size(), 0);
     std::vector<int32_t> nbody;
     std::vector<double> moduli, wbody, theta;
@@ -906,9 +951,15 @@ inline void init_main(problem_type& pb) {
       for (double c : coh)
         if (c < 0.0) IO_abort("bc_dynflt_init: cohesion must be positive");
       std::vector<double> T0(2 * (size_t)np), V0((size_t)np * pb.ndof, 0.0);
-      for (int k = 0; k < np; ++k) {  // no background stress: T0 = (Tt, Tn) (:392-400)
-        T0[k] = Tt[k];
-        T0[k + np] = Tn[k];
+      // background stress resolved on the fault (:376-400); the faults of the builder are horizontal: the normal of
+      // side 1 is +z on the split-node row and on the top side, -z on the bottom side
+      const double fnx = 0.0, fnz = (bc.tag[1] == 0 && bc.tag[0] == 1) ? -1.0 : 1.0;
+      const std::vector<double> Sxx = gen(bc.cd_S[0]), Sxy = gen(bc.cd_S[1]), Sxz = gen(bc.cd_S[2]), Syz = gen(bc.cd_S[3]),
+                                Szz = gen(bc.cd_S[4]);
+      for (int k = 0; k < np; ++k) {
+        const double Tx = Sxx[k] * fnx + Sxz[k] * fnz, Ty = Sxy[k] * fnx + Syz[k] * fnz, Tz = Sxz[k] * fnx + Szz[k] * fnz;
+        T0[k] = pb.ndof == 1 ? Tt[k] + Ty : Tt[k] + Tx * fnz - Tz * fnx;
+        T0[k + np] = Tn[k] + Tx * fnx + Tz * fnz;
         if (bc.has_rsf) V0[k] = V[k];  // bc%V(:,1) = V for rate-and-state faults (:371-376)
       }
       s2d_dynflt_desc d;

@@ -77,7 +77,7 @@ int main(int argc, char** argv) {
                   "\"ms_per_step\": %.6f, \"kernel_ms\": %.6f, \"launches_per_step\": %.2f, \"kv\": %s, \"plastic\": %s, \"vmax\": %.6e, "
                   "\"phases_ms\": [%.6f, %.6f, %.6f, %.6f, %.6f, %.6f, %.6f]}\n",
                   (long long)pb.npoin, (long long)pb.nelem_total, pb.ngll, pb.ndof, pb.time.kind.c_str(), pb.time.dt, bench_steps,
-                  ms / bench_steps, kms, (double)(l1 - l0) / bench_steps, pb.has_kv ? "true" : "false", (pb.has_plastic || pb.has_visco) ? "true" : "false", vmax, ph[0], ph[1], ph[2],
+                  ms / bench_steps, kms, (double)(l1 - l0) / bench_steps, pb.has_kv ? "true" : "false", (pb.has_plastic || pb.has_visco || pb.has_damage) ? "true" : "false", vmax, ph[0], ph[1], ph[2],
                   ph[3], ph[4], ph[5], ph[6]);
       return 0;
     }

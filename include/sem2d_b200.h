@@ -270,6 +270,15 @@ int s2d_cart_get_plastic_strain(s2d_handle h, double* ep);
  * advances them in every force evaluation.  elem_set(nelem), natural element order: 0 = elastic element.
  * s2d_cart_set_material still gives rho, cp, cs (mass, absorbing boundaries, Courant step use the input speeds, as the
  * reference does).  P-SV, ngll <= 6, no Kelvin-Voigt or plastic elements in the same problem. */
+/* Damage rheology (kind='DMG': Lyakhovsky et al. 1997 / Hamiel et al. 2004 as in mat_damage.f90; MAT_DMG_stress :337-445,
+ * compute_stress :453-491, MAT_DMG_init_elem_work :209-279).  par(13,nsets) = lambda, mu (intact), phi [degrees], alpha
+ * (initial damage), Cd, beta, R, e0(3), ep(3) of every DMG material; elem_set(nelem), natural element order, 0 = elastic
+ * element.  The device keeps alpha and the plastic strain ep of every element GLL point (s2d_cart_get_damage_state:
+ * (ngll,ngll,4,nelem) = alpha, ep11, ep22, ep12) and advances them in every force evaluation; when compute_stress's
+ * loss-of-convexity checks fail the run stops with "MAT_DMG: damage exceeded critical value", as the reference does.
+ * P-SV, ngll <= 6, no Kelvin-Voigt, plastic or visco-elastic elements in the same problem. */
+int s2d_cart_set_damage(s2d_handle h, int32_t nsets, const double* par, const int32_t* elem_set);
+int s2d_cart_get_damage_state(s2d_handle h, double* state);
 int s2d_cart_set_visco(s2d_handle h, int32_t nsets, const int32_t* nbody, const double* moduli, const double* wbody,
                        const double* theta, const int32_t* elem_set);
 

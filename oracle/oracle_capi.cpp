@@ -130,6 +130,7 @@ long long orc_get_int(void* hv, const char* name_) {
   if (n == "nkv") return (long long)pb.kv_elem.size();
   if (n == "npl") return (long long)pb.pl_elem.size();
   if (n == "nvs") return (long long)pb.vs_elem.size();
+  if (n == "ndm") return (long long)pb.dm_elem.size();
   if (n == "nt") return pb.time.nt;
   if (n == "it") return pb.it;
   if (n == "nbc") return (long long)pb.bc.size();
@@ -333,6 +334,8 @@ long long orc_array(void* hv, const char* name_, const void** ptr, char* dtype) 
     }
   }
   if (n == "vs_etot") RET_D(pb.vs_etot);
+  if (n == "dm_state") RET_D(pb.dm_state);
+  if (n == "dm_par") RET_D(pb.dm_par);
   if (n == "rmass") RET_D(pb.rmass);
   if (n == "mass") RET_D(pb.mass);
   if (n == "d") RET_D(pb.d);

@@ -675,6 +675,8 @@ struct MatInput {  // matpro_input_type (prop_mat.f90:21-25) for ELAST (+KV)
   bool elastic = false, isotropic = false, homogeneous = false, kv = false;
   bool plastic = false;                    // kind='PLAST' (mat_plastic.f90)
   double phi = 0, coh = 0, Tv = 0, e0[3] = {0, 0, 0};
+  bool damage = false;                     // kind='DMG' (mat_damage.f90): phi, e0 as above; Cd, R, beta, alpha, ep
+  double Cd = 0, Rdmg = 0, beta_dmg = 0, alpha0 = 0, ep0[3] = {0, 0, 0};
   bool visco = false;                      // kind='VISCO' (mat_visco.f90): generalized Maxwell body, Nbody mechanisms
   double QP = 0, QS = 0, fmin = 0, fmax = 0;
   int Nbody = 0;
@@ -883,6 +885,12 @@ struct Problem {  // problem_type (problem_class.f90:19-46)
   std::vector<double> pl_ep;      // (ngll,ngll,3,npl) plastic strain
   std::vector<double> pl_derint;  // (ngll,ngll,5,npl): dxi_dx, dxi_dy, deta_dx, deta_dy, weights
   std::vector<double> pl_beta;    // (ngll,ngll,npl) when W is finite
+  // damage rheology (matwrk_dmg_type, mat_damage.f90:44-52), per damage element
+  std::vector<int> elem2dm;       // (nelem) 0 or 1-based index into the damage element list
+  std::vector<int> dm_elem;
+  std::vector<double> dm_derint;  // (ngll,ngll,5,ndm)
+  std::vector<double> dm_par;     // (16,ndm): lambda, mu, xi_0, gamma_r, beta, Cd, Cv, e0(3), s0(3)
+  std::vector<double> dm_state;   // (ngll,ngll,4,ndm): alpha, ep(3)
   // visco-elasticity (matwrk_visco_type, mat_visco.f90:11-19), per visco element; derint shares pl_derint's layout
   std::vector<int> elem2vs;       // (nelem) 0 or 1-based index into the visco element list
   std::vector<int> vs_elem;       // 1-based element ids
@@ -905,6 +913,25 @@ struct Problem {  // problem_type (problem_class.f90:19-46)
 
   size_t idx(int ip, int c) const { return (size_t)(ip - 1) + (size_t)grid.npoin * c; }
 };
+
+// mat_damage.f90:453-491 compute_stress: sigma = (lambda i1 - gamma sqrt(i2)) delta + (2 mu - gamma i1 / sqrt(i2)) e,
+// with the loss-of-convexity checks of the reference (they abort the run)
+inline void DMG_compute_stress(double s[3], const double e[3], double rl, double rm, double rg, double& i1, double& i2, double& xi) {
+  i1 = e[0] + e[1];
+  i2 = e[0] * e[0] + e[1] * e[1] + 2.0 * e[2] * e[2];
+  const double si2 = std::sqrt(i2);
+  xi = si2 < 1e-10 ? 0.0 : i1 / si2;
+  const double two_mue = 2.0 * rm - rg * xi;
+  s[0] = rl * i1 - rg * si2 + two_mue * e[0];
+  s[1] = rl * i1 - rg * si2 + two_mue * e[1];
+  s[2] = two_mue * e[2];
+  const double p = -(4.0 * rm + 2.0 * rl - 3.0 * rg * xi);
+  const double q = two_mue * two_mue + two_mue * (2.0 * rl - rg * xi) + rg * (rl * xi - rg) * (2.0 - xi * xi);
+  const double d = p * p / 4.0 - q;
+  if (d <= 0.0) IO_abort("mat_damage:elastic: discriminant < 0");
+  if (p / 2.0 + std::sqrt(d) >= 0.0) IO_abort("MAT_DMG: damage exceeded critical value (1st type)");
+  if (two_mue <= 0.0) IO_abort("MAT_DMG: damage exceeded critical value (2nd type)");
+}
 
 // ------------------------------------------------------------------------------------------
 // Least squares x = argmin |A x - b|, A (m,n) column-major, m >= n, full column rank.  The reference solves it with
@@ -1085,7 +1112,7 @@ inline void MAT_init_prop(Problem& pb, int N_for_lattice /*ngll*/) {
       m.lambda[e - 1].homo = iw.lambda;
       m.mu[e - 1].homo = iw.mu;
     }
-    if (in.plastic) {  // MAT_PLAST_init_elem_prop (mat_plastic.f90:121-145): scalar properties
+    if (in.plastic || in.damage) {  // MAT_PLAST_init_elem_prop (mat_plastic.f90:121-145) / MAT_DMG_init_elem_prop (mat_damage.f90:176-206): scalar properties
       m.cp[e - 1] = set_from_input(in.cp);
       m.cs[e - 1] = set_from_input(in.cs);
       const double rho1 = in.rho.c, cp1 = in.cp.c, cs1 = in.cs.c;
@@ -1212,6 +1239,11 @@ inline void MAT_init_work(Problem& pb, bool force_general_nelast = false) {
   pb.kv_eta.clear();
   pb.ncoefsets = 0;
   std::vector<double> abuf((size_t)n2 * pb.nelast), eta(n2);
+  pb.elem2dm.assign(ne, 0);
+  pb.dm_elem.clear();
+  pb.dm_derint.clear();
+  pb.dm_par.clear();
+  pb.dm_state.clear();
   pb.elem2vs.assign(ne, 0);
   pb.vs_elem.clear();
   pb.vs_derint.clear();
@@ -1226,6 +1258,48 @@ inline void MAT_init_work(Problem& pb, bool force_general_nelast = false) {
   pb.pl_beta.clear();
   for (int e = 1; e <= ne; ++e) {
     const MatInput& in = pb.mat.inputs[g.tag[e - 1] - 1];
+    if (in.damage) {  // mat_gen.f90:374-378: MAT_set_derint + MAT_DMG_init_elem_work (mat_damage.f90:209-279)
+      if (pb.ndof != 2) IO_abort("oracle: damage rheology requires ndof=2 (P-SV)");
+      if (in.kv) IO_abort("oracle: DMG with KV not supported");
+      pb.dm_elem.push_back(e);
+      pb.elem2dm[e - 1] = (int)pb.dm_elem.size();
+      const size_t o = pb.dm_derint.size();
+      pb.dm_derint.resize(o + (size_t)5 * n2);
+      for (int j = 1; j <= n; ++j)
+        for (int i = 1; i <= n; ++i) {
+          const int k = (i - 1) + n * (j - 1);
+          double jac[4], inv[4];
+          SE_Jacobian(g, e, i, j, jac);
+          invert2(jac, inv);
+          pb.dm_derint[o + k] = inv[0];
+          pb.dm_derint[o + n2 + k] = inv[2];
+          pb.dm_derint[o + 2 * (size_t)n2 + k] = inv[1];
+          pb.dm_derint[o + 3 * (size_t)n2 + k] = inv[3];
+          pb.dm_derint[o + 4 * (size_t)n2 + k] = SE_VolumeWeight(g, e, i, j);
+        }
+      const double lam = pb.mat.lambda[e - 1].homo, mu1 = pb.mat.mu[e - 1].homo;
+      double q = std::sin(in.phi * PI / 180.0);                                       // xi_zero_2d (:295-305)
+      const double xi0 = -std::sqrt(2.0) / std::sqrt(q * q * ((lam / mu1 + 1.0) * (lam / mu1 + 1.0)) + 1.0);
+      const double qq = 2.0 * (mu1 + lam) / (2.0 - xi0 * xi0);                        // gamma_r_2d (:308-317)
+      const double pp = 0.5 * xi0 * (qq + lam);
+      const double gr = pp + std::sqrt(pp * pp + 2.0 * mu1 * qq);
+      double par[16] = {lam, mu1, xi0, gr, in.beta_dmg, in.Cd, in.Rdmg / mu1, in.e0[0], in.e0[1], in.e0[2], 0, 0, 0, 0, 0, 0};
+      {  // initial stress (:262-265)
+        const double mud = mu1 + xi0 * gr * in.alpha0;
+        const double rg = gr * std::pow(in.alpha0, 1.0 + in.beta_dmg) / (1.0 + in.beta_dmg);
+        const double ee[3] = {in.e0[0] - in.ep0[0], in.e0[1] - in.ep0[1], in.e0[2] - in.ep0[2]};
+        double i1, i2, xi;
+        DMG_compute_stress(&par[10], ee, lam, mud, rg, i1, i2, xi);
+      }
+      pb.dm_par.insert(pb.dm_par.end(), par, par + 16);
+      const size_t so = pb.dm_state.size();
+      pb.dm_state.resize(so + (size_t)4 * n2);
+      for (int k = 0; k < n2; ++k) {
+        pb.dm_state[so + k] = in.alpha0;
+        for (int c = 0; c < 3; ++c) pb.dm_state[so + (size_t)(c + 1) * n2 + k] = in.ep0[c];
+      }
+      continue;
+    }
     if (in.visco) {  // mat_gen.f90:380-385: MAT_set_derint + MAT_VISCO_init_elem_work (mat_visco.f90:164-200)
       if (pb.ndof != 2) IO_abort("MAT_init_work: visco-elasticity requires ndof=2 (P-SV) ");
       if (in.kv) IO_abort("oracle: VISCO with KV not supported");
@@ -2339,6 +2413,59 @@ inline void compute_Fint(Problem& pb, std::vector<double>& f, const std::vector<
         dloc[k + (size_t)n2 * c] = d[(size_t)(ib[k] - 1) + np * c];
         vloc[k + (size_t)n2 * c] = v[(size_t)(ib[k] - 1) + np * c];
       }
+    if (!pb.elem2dm.empty() && pb.elem2dm[e - 1] > 0) {
+      // mat_gen.f90:451-457: e = MAT_strain(d), MAT_DMG_stress(update = true, dt) (mat_damage.f90:337-445), f = MAT_forces(s)
+      const int id = pb.elem2dm[e - 1] - 1;
+      const double dt = pb.time.dt;
+      const double* D = &pb.dm_derint[(size_t)5 * n2 * id];
+      const double *dxi_dx = D, *dxi_dy = D + n2, *deta_dx = D + 2 * n2, *deta_dy = D + 3 * n2, *wts = D + 4 * n2;
+      const double* par = &pb.dm_par[(size_t)16 * id];
+      double* al = &pb.dm_state[(size_t)4 * n2 * id];
+      double* ep = al + n2;
+      std::vector<double> gx1(n2), gx2(n2), ge1(n2), ge2(n2), st((size_t)3 * n2), t1(n2), t2(n2), m1(n2), m2(n2);
+      mxm(g.Ht.data(), dloc.data(), gx1.data(), n);
+      mxm(g.Ht.data(), dloc.data() + n2, gx2.data(), n);
+      mxm(dloc.data(), g.H.data(), ge1.data(), n);
+      mxm(dloc.data() + n2, g.H.data(), ge2.data(), n);
+      const double lam = par[0], mu0 = par[1], xi0 = par[2], gr = par[3], beta = par[4], Cd = par[5], Cv = par[6];
+      for (int k = 0; k < n2; ++k) {
+        const double et1 = gx1[k] * dxi_dx[k] + ge1[k] * deta_dx[k];
+        const double et2 = gx2[k] * dxi_dy[k] + ge2[k] * deta_dy[k];
+        const double et3 = 0.5 * (gx1[k] * dxi_dy[k] + ge1[k] * deta_dy[k] + gx2[k] * dxi_dx[k] + ge2[k] * deta_dx[k]);
+        double ee[3] = {et1 + par[7], et2 + par[8], et3 + par[9]};
+        for (int c = 0; c < 3; ++c) ee[c] = ee[c] - ep[(size_t)c * n2 + k];
+        const double rm = mu0 + xi0 * gr * al[k];
+        const double rg = gr * std::pow(al[k], 1.0 + beta) / (1.0 + beta);
+        double sij[3], i1, i2, xi;
+        DMG_compute_stress(sij, ee, lam, rm, rg, i1, i2, xi);
+        double dalpha;
+        if (beta == 0.0) dalpha = dt * Cd * i2 * std::max(xi - xi0, 0.0);
+        else dalpha = dt * Cd * i2 * std::max(xi * std::pow(al[k], beta) - xi0, 0.0);
+        al[k] = al[k] + dalpha;
+        const double sm = 0.5 * (sij[0] + sij[1]);
+        dalpha = Cv * std::max(dalpha, 0.0);
+        ep[k] = ep[k] + (sij[0] - sm) * dalpha;
+        ep[n2 + k] = ep[n2 + k] + (sij[1] - sm) * dalpha;
+        ep[2 * n2 + k] = ep[2 * n2 + k] + sij[2] * dalpha;
+        st[k] = sij[0] - par[10];
+        st[n2 + k] = sij[1] - par[11];
+        st[2 * n2 + k] = sij[2] - par[12];
+      }
+      for (int c = 0; c < 2; ++c) {  // MAT_forces (mat_gen.f90:834-866)
+        const double* sa = c == 0 ? &st[0] : &st[2 * n2];
+        const double* sb = c == 0 ? &st[2 * n2] : &st[n2];
+        for (int k = 0; k < n2; ++k) {
+          t1[k] = -wts[k] * (dxi_dx[k] * sa[k] + dxi_dy[k] * sb[k]);
+          t2[k] = -wts[k] * (deta_dx[k] * sa[k] + deta_dy[k] * sb[k]);
+        }
+        mxm(g.H.data(), t1.data(), m1.data(), n);
+        mxm(t2.data(), g.Ht.data(), m2.data(), n);
+        for (int k = 0; k < n2; ++k) floc[k + (size_t)n2 * c] = m1[k] + m2[k];
+      }
+      for (int c = 0; c < ndof; ++c)
+        for (int k = 0; k < n2; ++k) f[(size_t)(ib[k] - 1) + np * c] = f[(size_t)(ib[k] - 1) + np * c] + floc[k + (size_t)n2 * c];
+      continue;
+    }
     if (!pb.elem2vs.empty() && pb.elem2vs[e - 1] > 0) {
       // mat_gen.f90:451-457: e = MAT_strain(d), MAT_VISCO_stress (mat_visco.f90:206-248), f = MAT_forces(s); no 2.5D term
       const int iv = pb.elem2vs[e - 1] - 1;
@@ -2928,6 +3055,21 @@ inline void read_main(Problem& pb, CartSpec& cart, ParInp& in) {
           mi.coh = gp->dbl("coh", 0.0);
           mi.Tv = gp->dbl("Tv", 0.0);
           for (int q = 0; q < 3; ++q) mi.e0[q] = gp->dbl("e0", 0.0, q);
+        } else if (kinds[k] == "DMG") {  // MAT_DMG_read (mat_damage.f90:108-173)
+          const NmlGroup* gd = in.next("MAT_DAMAGE");
+          if (!gd) IO_abort("MAT_DMG_read: MAT_DAMAGE input block not found");
+          mi.damage = true;
+          mi.isotropic = true;
+          mi.rho = read_cd(in, gd->dbl("rho", 0.0), "");
+          mi.cp = read_cd(in, gd->dbl("cp", 0.0), "");
+          mi.cs = read_cd(in, gd->dbl("cs", 0.0), "");
+          mi.phi = gd->dbl("phi", 0.0);
+          mi.alpha0 = gd->dbl("alpha", 0.0);
+          mi.Cd = gd->dbl("Cd", 0.0);
+          mi.beta_dmg = gd->dbl("beta", 0.0);
+          mi.Rdmg = gd->dbl("R", 0.0);
+          for (int q = 0; q < 3; ++q) mi.e0[q] = gd->dbl("e0", 0.0, q);
+          for (int q = 0; q < 3; ++q) mi.ep0[q] = gd->dbl("ep", 0.0, q);
         } else if (kinds[k] == "VISCO") {  // MAT_VISCO_read (mat_visco.f90:65-113)
           const NmlGroup* gv = in.next("MAT_VISCO");
           if (!gv) IO_abort("MAT_VISCO_read: MAT_VISCO input block not found");

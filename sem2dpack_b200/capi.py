@@ -132,6 +132,8 @@ _SIGS = {
     "s2d_cart_set_w25d": [C.c_void_p, C.c_double],
     "s2d_cart_set_plastic": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
     "s2d_cart_get_plastic_strain": [C.c_void_p, C.c_void_p],
+    "s2d_cart_set_damage": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
+    "s2d_cart_get_damage_state": [C.c_void_p, C.c_void_p],
     "s2d_cart_set_visco": [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "s2d_cart_info": [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)],
     "s2d_cart_set_dt": [C.c_void_p, C.c_double],

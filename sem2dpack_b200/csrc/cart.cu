@@ -892,6 +892,51 @@ int s2d_cart_set_visco(s2d_handle h, int32_t nsets, const int32_t* nbody, const 
   CART_GUARD_END
 }
 
+int s2d_cart_set_damage(s2d_handle h, int32_t nsets, const double* par, const int32_t* elem_set) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(nsets >= 1 && par && elem_set, "cart_set_damage: bad arguments");
+  S2D_REQUIRE(!Eb->committed, "cart_set_damage after commit");
+  const CartGeom& G = S.G;
+  const int N = G.N, n2 = N * N;
+  std::vector<unsigned char> ps((size_t)Eb->nelem, 0);
+  bool nonzero = false;
+  for (int k = 0; k < nsets; ++k)
+    for (int q : {3, 10, 11, 12}) nonzero = nonzero || par[(size_t)13 * k + q] != 0.0;
+  std::vector<double> st;
+  if (nonzero) st.assign((size_t)Eb->nelem * 4 * n2, 0.0);
+  for (int e = 0; e < Eb->nelem; ++e) {
+    S2D_REQUIRE(elem_set[e] >= 0 && elem_set[e] <= nsets, "cart_set_damage: material set out of range");
+    const int ix = e % G.nx, iz = e / G.nx;
+    ps[strip_elem_slot(G.S, ix, iz)] = (unsigned char)elem_set[e];
+    if (nonzero && elem_set[e] > 0) {
+      const double* p = par + (size_t)13 * (elem_set[e] - 1);
+      for (int j = 0; j < N; ++j)
+        for (int i = 0; i < N; ++i) {
+          st[strip_plane_index(G.S, ix, iz, i, j, 0, 4)] = p[3];
+          for (int c = 0; c < 3; ++c) st[strip_plane_index(G.S, ix, iz, i, j, 1 + c, 4)] = p[10 + c];
+        }
+    }
+  }
+  Eb->set_strip_damage(ps.data(), ps.size(), nsets, par, nonzero ? st.data() : nullptr);
+  CART_GUARD_END
+}
+
+int s2d_cart_get_damage_state(s2d_handle h, double* state) {
+  CART_GUARD_BEGIN
+  S2D_REQUIRE(state, "cart_get_damage_state: null output");
+  const CartGeom& G = S.G;
+  const int N = G.N, n2 = N * N;
+  std::vector<double> st((size_t)Eb->nelem * 4 * n2);
+  Eb->get_strip_damage_state(st.data());
+  for (int e = 0; e < Eb->nelem; ++e) {
+    const int ix = e % G.nx, iz = e / G.nx;
+    for (int k = 0; k < 4; ++k)
+      for (int j = 0; j < N; ++j)
+        for (int i = 0; i < N; ++i) state[(size_t)e * 4 * n2 + (size_t)k * n2 + i + N * j] = st[strip_plane_index(G.S, ix, iz, i, j, k, 4)];
+  }
+  CART_GUARD_END
+}
+
 int s2d_cart_get_plastic_strain(s2d_handle h, double* ep) {
   CART_GUARD_BEGIN
   S2D_REQUIRE(ep, "cart_get_plastic_strain: null output");

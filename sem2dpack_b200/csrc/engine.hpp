@@ -91,6 +91,8 @@ class EngineBase {
   virtual void set_strip_eta(const double* eta_strip, size_t n) = 0;
   virtual void set_strip_plastic(const unsigned char* set_strip, size_t n, int nsets, const double* raw) = 0;
   virtual void get_strip_plastic_strain(double* ep_strip) = 0;
+  virtual void set_strip_damage(const unsigned char* set_strip, size_t n, int nsets, const double* par, const double* state_strip) = 0;
+  virtual void get_strip_damage_state(double* state_strip) = 0;
   virtual void set_strip_visco(const unsigned char* set_strip, size_t n, int nsets, const int32_t* nbody, const double* moduli,
                                const double* wbody, const double* theta) = 0;
   virtual void commit(int variant) = 0;
@@ -333,6 +335,9 @@ class Engine : public EngineBase {
       io.vs_state = vs_state.n ? vs_state.p : nullptr;
       io.vs_tab = vs_tab.p;
       io.vs_nb = vs_nb;
+      io.dm_state = dm_state.n ? dm_state.p : nullptr;
+      io.dm_tab = dm_tab.p;
+      io.dm_err = &ctl.p->err;
     }
     return io;
   }
@@ -904,6 +909,50 @@ class Engine : public EngineBase {
     vs_state.alloc((size_t)nelem * 3 * (vs_nb + 1) * ngll * ngll);
     vs_state.zero();
   }
+  // par(13,nsets): lambda, mu, phi [deg], alpha0, Cd, beta, R, e0(3), ep0(3); state_strip: initial alpha, ep(3) of every
+  // element GLL point in the strip layout, or null when every set starts from alpha = 0, ep = 0
+  void set_strip_damage(const unsigned char* set_strip, size_t n, int nsets, const double* par, const double* state_strip) override {
+    S2D_REQUIRE(cart_mode && !committed, "set_strip_damage: builder-made engines only, before commit");
+    S2D_REQUIRE(n == (size_t)nelem && nsets >= 1 && nsets < STRIP_PL_SETS, "set_strip_damage: 1..7 damage material sets");
+    S2D_REQUIRE(ndof == 2 && cart_compact && ngll <= STRIP_PLAST_MAXN,
+                "MAT_init_work: the damage rheology requires ndof=2 (P-SV), an isotropic box and ngll <= 6");
+    S2D_REQUIRE(pl_ep.n == 0 && vs_state.n == 0, "damage together with plastic or visco-elastic elements: not provided");
+    for (int k = 0; k < nsets; ++k) {
+      const double* p = par + (size_t)13 * k;
+      const double lam = p[0], mu1 = p[1], phi = p[2], alpha0 = p[3], Cd = p[4], beta = p[5], R = p[6];
+      S2D_REQUIRE(mu1 > 0.0 && beta >= 0.0, "set_strip_damage: mu must be positive, beta non-negative");
+      const double q = std::sin(phi * 3.141592653589793 / 180.0);                      // xi_zero_2d (mat_damage.f90:295-305)
+      const double xi0 = -std::sqrt(2.0) / std::sqrt(q * q * ((lam / mu1 + 1.0) * (lam / mu1 + 1.0)) + 1.0);
+      const double qq = 2.0 * (mu1 + lam) / (2.0 - xi0 * xi0);                         // gamma_r_2d (:308-317)
+      const double pp = 0.5 * xi0 * (qq + lam);
+      const double gr = pp + std::sqrt(pp * pp + 2.0 * mu1 * qq);
+      double* r = dm_raw[k + 1];
+      r[0] = lam; r[1] = mu1; r[2] = xi0; r[3] = gr; r[4] = beta; r[5] = Cd; r[6] = R / mu1;
+      for (int c = 0; c < 3; ++c) r[7 + c] = p[7 + c];
+      // initial stress (:262-265): compute_stress of e0 - ep0 with the moduli damaged by alpha0
+      const double mud = mu1 + xi0 * gr * alpha0, rg = gr * std::pow(alpha0, 1.0 + beta) / (1.0 + beta);
+      const double e[3] = {p[7] - p[10], p[8] - p[11], p[9] - p[12]};
+      const double i1 = e[0] + e[1], i2 = e[0] * e[0] + e[1] * e[1] + 2.0 * e[2] * e[2], si2 = std::sqrt(i2);
+      const double xi = si2 < 1e-10 ? 0.0 : i1 / si2, two_mue = 2.0 * mud - rg * xi;
+      r[10] = lam * i1 - rg * si2 + two_mue * e[0];
+      r[11] = lam * i1 - rg * si2 + two_mue * e[1];
+      r[12] = two_mue * e[2];
+    }
+    pl_set.alloc(n);
+    h2d_sync(pl_set.p, set_strip, n);
+    const size_t ns = (size_t)nelem * 4 * ngll * ngll;
+    if (state_strip) upload_as(dm_state, state_strip, ns);
+    else {
+      dm_state.alloc(ns);
+      dm_state.zero();
+    }
+  }
+  void get_strip_damage_state(double* state_strip) override {
+    S2D_REQUIRE(dm_state.n > 0, "no damage elements");
+    S2D_CUDA(cudaStreamSynchronize(stream));
+    std::vector<T> tmp = dm_state.to_host();
+    for (size_t q = 0; q < tmp.size(); ++q) state_strip[q] = (double)tmp[q];
+  }
   void get_strip_plastic_strain(double* ep_strip) override {
     S2D_REQUIRE(pl_ep.n > 0, "no plastic elements");
     S2D_CUDA(cudaStreamSynchronize(stream));
@@ -1148,6 +1197,9 @@ class Engine : public EngineBase {
   DevBuf<T> pl_ep, pl_tab;
   // visco-elasticity (mat_visco.f90): the element sets share pl_set; memory variables + previous strain per element
   // GLL point; per set lambda_inf, mu_inf, Nbody, wbody(8) [RK factors once dt is known], theta(8,3)
+  // damage rheology (mat_damage.f90): alpha + ep(3) per element GLL point; per set the 16-entry row of StripArgs::dm_tab
+  DevBuf<T> dm_state, dm_tab;
+  double dm_raw[STRIP_PL_SETS][STRIP_DM_TAB] = {};
   DevBuf<T> vs_state, vs_tab;
   int vs_nb = 0;
   double vs_raw[STRIP_PL_SETS][STRIP_VS_TAB] = {};
@@ -1321,6 +1373,11 @@ class Engine : public EngineBase {
         S2D_CUDA(cudaStreamSynchronize(stream));
         cart_kv_eta.release();
       }
+      if (dm_state.n) {
+        S2D_REQUIRE(strip_eta.n == 0, "damage elements together with Kelvin-Voigt elements: not provided");
+        for (int k = 1; k < STRIP_PL_SETS; ++k) dm_raw[k][13] = scheme.dt;
+        upload_as(dm_tab, &dm_raw[0][0], (size_t)STRIP_PL_SETS * STRIP_DM_TAB);
+      }
       if (vs_state.n) {  // RK_factor of MAT_VISCO_stress (mat_visco.f90:222-224), now that dt is known
         S2D_REQUIRE(strip_eta.n == 0, "visco-elastic elements together with Kelvin-Voigt elements: not provided");
         double tab[STRIP_PL_SETS][STRIP_VS_TAB];
@@ -1332,7 +1389,7 @@ class Engine : public EngineBase {
           }
         upload_as(vs_tab, &tab[0][0], (size_t)STRIP_PL_SETS * STRIP_VS_TAB);
       }
-      if (pl_set.n && !vs_state.n) {  // MAT_PLAST_init_elem_work (mat_plastic.f90:165-184); set 0 (elastic elements) never yields
+      if (pl_set.n && !vs_state.n && !dm_state.n) {  // MAT_PLAST_init_elem_work (mat_plastic.f90:165-184); set 0 (elastic elements) never yields
         S2D_REQUIRE(strip_eta.n == 0, "plastic elements together with Kelvin-Voigt elements: not provided");
         for (int k = 1; k < STRIP_PL_SETS; ++k) {
           const double phi = 3.141592653589793 / 180.0 * pl_raw[k][1];
@@ -1789,6 +1846,7 @@ class Engine : public EngineBase {
     if (c.err == 1) throw SolverError("NR_Solver has exceeded the maximum iterations (200)");
     if (c.err == 2) throw SolverError("NR_Solver could not bracket a root");
     if (c.err == 3) throw StateError("halo exchange: a neighbour GPU did not signal within 10 s");
+    if (c.err == 4) throw SolverError("MAT_DMG: damage exceeded critical value");
     throw StateError("device-side abort, code " + std::to_string(c.err));
   }
 

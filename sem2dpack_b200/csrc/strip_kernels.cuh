@@ -205,6 +205,7 @@ template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 
 constexpr int STRIP_VS_MAXB = 8, STRIP_VS_TAB = 3 + 4 * STRIP_VS_MAXB;  // visco: mechanisms per material, table row
+constexpr int STRIP_DM_TAB = 16;
 constexpr int STRIP_PL_SETS = 8;  // plastic material sets per problem (set 0 = elastic elements)
 // position of plastic-strain component k at GLL point (i,j) of element (ix,iz)
 __host__ __device__ inline size_t strip_ep_index(const StripGeom& G, int ix, int iz, int i, int j, int k) {
@@ -213,6 +214,14 @@ __host__ __device__ inline size_t strip_ep_index(const StripGeom& G, int ix, int
   const int ex0 = strip * G.EPW, el = ix - ex0;
   const int cx = min(G.EPW, G.nx - ex0);
   return (size_t)strip_elem_off(G, seg, strip, iz) * 3 * N * N + (size_t)(k * N + j) * (cx * N) + el * N + i;
+}
+// position of plane k (of nplanes per element) at GLL point (i,j) of element (ix,iz): per-point state of the rheologies
+__host__ __device__ inline size_t strip_plane_index(const StripGeom& G, int ix, int iz, int i, int j, int k, int nplanes) {
+  const int N = G.N;
+  const int seg = strip_seg_of(G, iz), strip = ix / G.EPW;
+  const int ex0 = strip * G.EPW, el = ix - ex0;
+  const int cx = min(G.EPW, G.nx - ex0);
+  return (size_t)strip_elem_off(G, seg, strip, iz) * nplanes * N * N + (size_t)(k * N + j) * (cx * N) + el * N + i;
 }
 __host__ __device__ inline size_t strip_elem_slot(const StripGeom& G, int ix, int iz) {
   const int strip = ix / G.EPW;
@@ -267,6 +276,13 @@ struct StripArgs {
   T* vs_state;
   const T* vs_tab;          // [STRIP_PL_SETS][STRIP_VS_TAB]
   int vs_nb;                // memory-variable planes per component in the state layout (max Nbody over the sets)
+  // damage rheology (MAT_DMG_stress, mat_damage.f90:337-491; the same instantiation, dm_state != null): damage
+  // variable alpha and plastic strain ep(3) per element GLL point, planes [alpha | ep11 | ep22 | ep12][j][lane];
+  // per set lambda, mu, xi_0, gamma_r, beta, Cd, Cv, e0(3), s0(3), dt; *dm_err is set when the loss-of-convexity
+  // checks of compute_stress (:478-489) fail (the reference aborts)
+  T* dm_state;
+  const T* dm_tab;          // [STRIP_PL_SETS][STRIP_DM_TAB]
+  int* dm_err;
   int prefetch;             // L2 prefetch of what is not staged
   T H[N * N];               // hprime, column-major (constant bank)
   // compact coefficient mode (isotropic flat grids): only (lambda, mu) are stored per GLL point and
@@ -600,6 +616,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   T* epp = PLAST ? A.pl_ep + (size_t)strip_elem_off(G, seg, strip, ez0) * (3 * N * N) + lanep : nullptr;
   const unsigned char* plp = PLAST ? A.pl_set + strip_elem_off(G, seg, strip, ez0) + el : nullptr;
   int pset_next = (PLAST && wact) ? (int)*plp : 0;
+  T* dmp = (PLAST && A.dm_state) ? A.dm_state + (size_t)strip_elem_off(G, seg, strip, ez0) * 4 * (N * N) + lanep : nullptr;
   T* vsp = (PLAST && A.vs_state) ? A.vs_state + (size_t)strip_elem_off(G, seg, strip, ez0) * (3 * (A.vs_nb + 1)) * (N * N) + lanep : nullptr;
   const int cxN = cx * N;
   const V2* cp = reinterpret_cast<const V2*>(A.coef) +
@@ -641,7 +658,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           }
       }
     }
-    if (PLAST && S2D_PLAST_STAGE != 0 && A.vs_state == nullptr) {  // the plastic strain of the row's elements travels with its displacements
+    if (PLAST && S2D_PLAST_STAGE != 0 && A.vs_state == nullptr && A.dm_state == nullptr) {  // the plastic strain of the row's elements travels with its displacements
       const T* en = A.pl_ep + (size_t)strip_elem_off(G, seg, strip, ezr) * (3 * N * N) + lanep;
 #pragma unroll
       for (int k = 0; k < 3 * N; ++k) stage_copy<sizeof(T)>(st_e + k * 32, en + (size_t)k * cxN);
@@ -740,7 +757,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
 #pragma unroll
           for (int j = 0; j < N; ++j) epr[k][j] = S2D_PLAST_STAGE ? st_e[(k * N + j) * 32] : __ldcs(epp + (size_t)(k * N + j) * cxN);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) ppar[q] = A.vs_state ? (T)0 : __ldg(A.pl_tab + pset * 6 + q);
+        for (int q = 0; q < 6; ++q) ppar[q] = (A.vs_state || A.dm_state) ? (T)0 : __ldg(A.pl_tab + pset * 6 + q);
         vset = pset;
       }
       if constexpr (TENS) {
@@ -913,6 +930,60 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       T tH[NDOF][N], tHt[NDOF][N];
 #pragma unroll
       for (int j = 0; j < N; ++j) {
+        if (PLAST && A.dm_state != nullptr) {
+          // damage rheology: moduli degraded by alpha (mat_damage.f90:372-378), stress and strain invariants of the
+          // elastic strain e0 + e - ep (compute_stress), damage growth dalpha = dt Cd i2 [xi alpha^beta - xi_0]+ and
+          // the damage-related plastic strain increment Cv dalpha (s - s_mean) (:393-412), relative stress out
+          const T* tb = A.dm_tab + vset * STRIP_DM_TAB;
+          const T e1t = gxi[0][j], e2t = get[1][j], e3t = T(0.5) * (get[0][j] + gxi[1][j]);
+          if (vset == 0) {  // elastic element of a damage problem
+            const T la = a2[0][j].x, two_mu = T(2) * a2[0][j].y;
+            const T s1 = (la + two_mu) * e1t + la * e2t, s2 = la * e1t + (la + two_mu) * e2t, s3 = two_mu * e3t;
+            tH[0][j] = nW[j] * s1;
+            tHt[0][j] = nW[j] * s3;
+            tH[1][j] = nW[j] * s3;
+            tHt[1][j] = nW[j] * s2;
+            continue;
+          }
+          const T rl = __ldg(tb), mu0 = __ldg(tb + 1), xi0 = __ldg(tb + 2), gr = __ldg(tb + 3), beta = __ldg(tb + 4),
+                  Cd = __ldg(tb + 5), Cv = __ldg(tb + 6), dtl = __ldg(tb + 13);
+          const size_t pstr = (size_t)N * cxN;
+          T* sp = dmp + (size_t)j * cxN;
+          T al = sp[0], p1 = sp[pstr], p2 = sp[2 * pstr], p3 = sp[3 * pstr];
+          const T e1 = (e1t + __ldg(tb + 7)) - p1, e2 = (e2t + __ldg(tb + 8)) - p2, e3 = (e3t + __ldg(tb + 9)) - p3;
+          const T rm = mu0 + xi0 * gr * al;
+          const T rg = beta == T(0) ? gr * al : gr * pow(al, T(1) + beta) / (T(1) + beta);
+          const T i1 = e1 + e2, i2 = e1 * e1 + e2 * e2 + T(2) * e3 * e3;
+          const T si2 = sqrt(i2);
+          const T xi = si2 < T(1e-10) ? T(0) : i1 / si2;
+          const T two_mue = T(2) * rm - rg * xi;
+          T s1 = rl * i1 - rg * si2 + two_mue * e1;
+          T s2 = rl * i1 - rg * si2 + two_mue * e2;
+          T s3 = two_mue * e3;
+          {
+            const T pp = -(T(4) * rm + T(2) * rl - T(3) * rg * xi);
+            const T qq = two_mue * two_mue + two_mue * (T(2) * rl - rg * xi) + rg * (rl * xi - rg) * (T(2) - xi * xi);
+            const T dd = pp * pp / T(4) - qq;
+            if (real && (dd <= T(0) || pp / T(2) + sqrt(dd) >= T(0) || two_mue <= T(0))) *A.dm_err = 4;
+          }
+          T dal = dtl * Cd * i2 * fmax((beta == T(0) ? xi : xi * pow(al, beta)) - xi0, T(0));
+          if (real && dal > T(0)) {
+            const T sm = T(0.5) * (s1 + s2);
+            const T da = Cv * dal;
+            sp[0] = al + dal;
+            sp[pstr] = p1 + (s1 - sm) * da;
+            sp[2 * pstr] = p2 + (s2 - sm) * da;
+            sp[3 * pstr] = p3 + s3 * da;
+          }
+          s1 = s1 - __ldg(tb + 10);
+          s2 = s2 - __ldg(tb + 11);
+          s3 = s3 - __ldg(tb + 12);
+          tH[0][j] = nW[j] * s1;
+          tHt[0][j] = nW[j] * s3;
+          tH[1][j] = nW[j] * s3;
+          tHt[1][j] = nW[j] * s2;
+          continue;
+        }
         if (PLAST && A.vs_state != nullptr) {
           // generalized Maxwell body: the memory variables of every mechanism relax towards the strain of the
           // PREVIOUS evaluation (4th-order expansion of 1 - exp(-w dt), mat_visco.f90:221-229), the strain is kept
@@ -1041,6 +1112,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       }
       if constexpr (PLAST) {
         if (A.vs_state != nullptr) vsp += (size_t)gcx * (3 * (A.vs_nb + 1)) * (N * N);
+        if (A.dm_state != nullptr) dmp += (size_t)gcx * 4 * (N * N);
         if (real && yielded) {  // an element that did not yield leaves its plastic strain as it is in HBM
 #pragma unroll
           for (int k = 0; k < 3; ++k)
@@ -1562,6 +1634,9 @@ struct StripIO {
   T* vs_state = nullptr;                  // visco-elasticity (see StripArgs)
   const T* vs_tab = nullptr;
   int vs_nb = 0;
+  T* dm_state = nullptr;                  // damage rheology (see StripArgs)
+  const T* dm_tab = nullptr;
+  int* dm_err = nullptr;
   const T* beta = nullptr;  // 2.5D: beta per element GLL point (strip layout)
   // tensor-map staging of the fused leapfrog kernel (null: per-lane copies)
   const CUtensorMap* tm_d = nullptr;
@@ -1671,6 +1746,9 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
         A.vs_state = io.vs_state;                                                                 \
         A.vs_tab = io.vs_tab;                                                                     \
         A.vs_nb = io.vs_nb;                                                                       \
+        A.dm_state = io.dm_state;                                                                 \
+        A.dm_tab = io.dm_tab;                                                                     \
+        A.dm_err = io.dm_err;                                                                     \
         constexpr int MP = sizeof(T) == 8 ? S2D_PLAST_MINB : 3;                                   \
         if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, true>(nb, A, s);         \
         else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, true>(nb, A, s);    \

@@ -385,6 +385,19 @@ class CartEngine(Engine):
         elem_set = _i32(elem_set)
         self._ck(self.L.s2d_cart_set_visco(self.h, ns, _ptr(nbody), _ptr(mod), _ptr(wb), _ptr(th), _ptr(elem_set)))
 
+    def set_damage(self, par, elem_set):
+        """par (nsets, 13) = lambda, mu, phi [deg], alpha0, Cd, beta, R, e0(3), ep0(3) per damage material; elem_set
+        (nelem) natural order, 0 = elastic (s2d_cart_set_damage)"""
+        par = _f64(par).reshape(-1, 13)
+        elem_set = _i32(elem_set)
+        self._ck(self.L.s2d_cart_set_damage(self.h, par.shape[0], _ptr(par), _ptr(elem_set)))
+
+    def damage_state(self):
+        """(nelem, 4, ngll, ngll): alpha, ep11, ep22, ep12, natural element order (s2d_cart_get_damage_state)"""
+        out = np.empty((self.nelem, 4, self.ngll, self.ngll))
+        self._ck(self.L.s2d_cart_get_damage_state(self.h, _ptr(out)))
+        return out
+
     def plastic_strain(self):
         """ep (nelem, 3, ngll, ngll), natural element order (s2d_cart_get_plastic_strain)"""
         out = np.empty((self.nelem, 3, self.ngll, self.ngll))

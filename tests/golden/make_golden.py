@@ -21,7 +21,7 @@ DECKS = {"testsh": "TestSH", "lamb": "LambsProblem", "tpv3": "TestFlt2D_SCEC_TPV
          # round 2: the time-solver lines of InaBox/info:224-225 pin dt / nt; the others are the decks VERDICT r1 names
          "inabox": "InaBox", "velweak": "Velocity_weakening", "inplane25d": "2.5D_inplane", "kvfz": "Kelvin_Visco_FZ",
          # SURVEY 8f(4), first stateful rheology: Coulomb plasticity
-         "plastic25d": "2.5D_plastic/psi_45_S_0.56_CF_0.63_W_10", "attenuation": "Attenuation"}
+         "plastic25d": "2.5D_plastic/psi_45_S_0.56_CF_0.63_W_10", "attenuation": "Attenuation", "damage": "Damage"}
 
 
 def main():

@@ -473,3 +473,44 @@ def test_visco_elastic_force_evaluations(ngll, nx, nz, ezflt, seg, nbody, monkey
     assert np.abs(o.arr("vs_el")).max() > 0
     e.close()
     o.close()
+
+
+@pytest.mark.parametrize("ngll,nx,nz,ezflt,seg,beta,alpha0", [(5, 27, 11, 0, 3, 0.0, 0.0), (6, 23, 10, 3, 3, 0.0, 0.1),
+                                                            (4, 9, 7, 0, 32, 0.5, 0.05), (3, 47, 8, 4, 5, 0.0, 0.0)])
+def test_damage_rheology_force_evaluations_and_state(ngll, nx, nz, ezflt, seg, beta, alpha0, monkeypatch):
+    """Damage rheology in the strip kernel (s2d_cart_set_damage): MAT_strain_PSV -> MAT_DMG_stress(update, dt) ->
+    MAT_forces (mat_gen.f90:451-457, mat_damage.f90:337-491).  Successive force evaluations on growing random
+    displacements over the deck's prestrain: forces after each, damage variable and plastic strain at the end."""
+    monkeypatch.setenv("S2D_SEG", str(seg))
+    h = 100.0
+    e0, ep0 = (-1.487381e-3, -1.708729e-4, 3.5e-4), (1e-5, -2e-5, 3e-5) if alpha0 else (0.0, 0.0, 0.0)
+    L = [f"&GENERAL iexec=1, ngll={ngll}, fmax=3.d0, ndof=2, title='damage', verbose='0000', ItInfo=1000 /",
+         "&MESH_DEF method='CARTESIAN' /",
+         f"&MESH_CART xlim=0d0,{nx*h}d0, zlim=0d0,{nz*h}d0, nelem={nx},{nz}" + (f", ezflt={ezflt}" if ezflt else "") + " /",
+         "&MATERIAL tag=1, kind='DMG' /",
+         f"&MAT_DAMAGE rho=2670.d0, cp=6000.d0, cs=3464.d0, beta={beta}d0, R=1.d0, Cd=2.5d5, phi=30.9638d0, alpha={alpha0}d0,",
+         f"   e0={e0[0]}d0,{e0[1]}d0,{e0[2]}d0, ep={ep0[0]}d0,{ep0[1]}d0,{ep0[2]}d0 /",
+         "&TIME NbSteps=10, courant=0.5d0, kind='leapfrog' /"]
+    o = orc.Oracle("\n".join(L) + "\n", renumber=False)
+    assert o.i("ndm") == nx * nz
+    rho, cp, cs = 2670.0, 6000.0, 3464.0
+    e = CartEngine(ngll, 2, nx, nz, (0.0, nx * h), (0.0, nz * h), ezflt=ezflt, seed=0, rho=rho, cp=cp, cs=cs)
+    e.set_dt(o.f("dt"))
+    e.set_damage([[rho * (cp * cp - 2 * cs * cs), rho * cs * cs, 30.9638, alpha0, 2.5e5, beta, 1.0, *e0, *ep0]],
+                 np.ones(nx * nz, np.int32))
+    e.commit()
+    rng = np.random.default_rng(ngll * 100 + nx)
+    base = rng.standard_normal(e.npoin * 2)
+    for amp in (1e-3, 1e-2, 3e-2):
+        d = amp * base
+        e.set_fields(d, d)
+        o.set_fields(d, d)
+        ref = o.compute_fint()
+        got = e.compute_fint()
+        assert rel_l2(got, ref) <= 1e-12, (amp, rel_l2(got, ref))
+    st_ref = o.arr("dm_state").reshape(nx * nz, 4, ngll, ngll)
+    st = e.damage_state()
+    assert st_ref[:, 0].max() > alpha0 + 1e-4          # damage has grown
+    assert np.abs(st - st_ref).max() <= 1e-12 * np.abs(st_ref).max()
+    e.close()
+    o.close()

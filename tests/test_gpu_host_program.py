@@ -430,3 +430,31 @@ def test_attenuation_deck_visco_elastic_medium(tmp_path):
     assert np.abs(oe.seis()[:, 0, 0]).max() > 1.1 * np.abs(ref).max()
     oe.close()
     o.close()
+
+
+def test_damage_deck_off_fault_damage(tmp_path):
+    """EXAMPLES/Damage (kind='DMG' on both tags, SWF + TWF fault, four absorbing sides, leapfrog; nondimensional units),
+    coarsened to 60 x 24 elements and without the Kelvin-Voigt layer of tag 2 (DMG with KV is not on the B200 path):
+    rupture nucleates, the off-fault medium accumulates damage and damage-related plastic strain.  Velocity and stress
+    snapshots and the fault records against the oracle.  No reference artefact pins this deck: oracle parity."""
+    nsteps = 500
+    deck = harness.deck("damage").replace("kind='DMG','KV'", "kind='DMG'").replace("nelem=240,100", "nelem=60,24")
+    deck = deck.replace("TotalTime=30d0", f"NbSteps={nsteps}").replace("itd=200", f"itd={nsteps}").replace("iexec=0", "iexec=1")
+    assert f"NbSteps={nsteps}" in deck and "nelem=60,24" in deck and "'KV'" not in deck
+    p = run(tmp_path, deck, "--quiet", "--natural-order")
+    assert p.returncode == 0, p.stdout + p.stderr
+    o = orc.Oracle(deck, renumber=False)
+    assert o.i("ndm") == 60 * 24
+    o.step(nsteps)
+    st = o.arr("dm_state").reshape(-1, 4, 25)
+    assert st[:, 0].max() > 0.05 and np.abs(st[:, 1:]).max() > 1e-3      # damage and plastic strain have grown
+    n = o.i("npoin")
+    vref = o.arr("v").reshape(2, n)
+    got = np.fromfile(tmp_path / "vx_001_sem2d.dat", dtype=np.float32)
+    assert np.abs(got - vref[0].astype(np.float32)).max() <= 5e-6 * np.abs(vref[0]).max()
+    x, rec = read_fault(tmp_path, 5)
+    want = o.arr("bc.0.out").reshape(-1, 6, rec.shape[2])
+    assert rec.shape == want.shape
+    for c in range(6):
+        assert np.abs(rec[:, c] - want[:, c]).max() <= 5e-6 * max(np.abs(want[:, c]).max(), 1e-30), c
+    o.close()

@@ -213,3 +213,18 @@ def test_inabox_time_solver_lines():
     assert f"{o.i('nt') * o.f('dt'):.3f}" == "2.001"
     assert abs(o.f("courant") - 0.3) < 1e-15
     o.close()
+
+
+def test_damage_deck_prestrain_reproduces_the_fault_stresses():
+    """EXAMPLES/Damage gives the medium an initial strain e0 = (-1.487381, -0.1708729, 0.35) and the fault the initial
+    tractions Szz = -2, Sxz = 0.7: they are the same stress state only if xi_zero_2d, gamma_r_2d and compute_stress
+    (mat_damage.f90:295-317,453-491) are restated right -- a consistency pin the reference deck itself holds."""
+    deck = harness.deck("damage").replace("kind='DMG','KV'", "kind='DMG'").replace("nelem=240,100", "nelem=12,4")
+    o = orc.Oracle(deck, renumber=False)
+    par = o.arr("dm_par")[:16]
+    lam, mu, xi0, gr = par[:4]
+    assert abs(lam - 1.0) < 1e-6 and abs(mu - 1.0) < 1e-12      # cp = sqrt(3) cs
+    assert -np.sqrt(2) < xi0 < 0 and gr > 0
+    s0 = par[10:13]
+    assert abs(s0[1] + 2.0) <= 1e-6 and abs(s0[2] - 0.7) <= 1e-6, s0
+    o.close()
