@@ -416,7 +416,16 @@ inline void read_main(problem_type& pb, const std::string& file) {
       continue;
     }
     if (k1 == "DMG") {  // MAT_DMG_read (SRC/mat_damage.f90:108-173): constants only
-      if (!k2.empty()) IO_abort("MAT_read: kind='DMG' combined with '" + k2 + "' is not on the B200 path");
+      if (!(k2.empty() || k2 == "KV")) IO_abort("MAT_read: kind='DMG' combined with '" + k2 + "' is not on the B200 path");
+      if (k2 == "KV") {  // MAT_KV_read (SRC/mat_kelvin_voigt.f90:35-66): the one non-exclusive material (mat_gen.f90:350-354)
+        const long q = in.find("MAT_KV", (size_t)m0);
+        if (q < 0) IO_abort("MAT_KV_read: MAT_KV input block not found");
+        size_t c2 = (size_t)q + 1;
+        M.eta = DIST_CD_Read(in, in.at((size_t)q), "eta", 0.0, c2);
+        M.ETAxDT = in.at((size_t)q).logical("etaxdt", true);
+        M.kv = true;
+        pb.has_kv = true;
+      }
       const long m = in.find("MAT_DAMAGE", (size_t)m0);
       if (m < 0) IO_abort("MAT_DMG_read: MAT_DAMAGE input block not found");
       const nml_group& e = in.at((size_t)m);
@@ -845,7 +854,7 @@ inline void init_main(problem_type& pb) {
   if (pb.W > 0.0) s2d_check(pb, s2d_cart_set_w25d(pb.gpu, pb.W), "MAT_ELAST_init_25D");
   if (pb.has_damage) {  // MAT_DMG_init_elem_prop / _work (SRC/mat_damage.f90:176-279): one set per DMG tag
     if (pb.ndof != 2) IO_abort("MAT_init_work: the damage rheology requires ndof=2 (P-SV) ");
-    if (pb.has_plastic || pb.has_kv || pb.has_visco) IO_abort("MAT_read: DMG together with PLAST, VISCO or KV materials is not on the B200 path");
+    if (pb.has_plastic || pb.has_visco) IO_abort("MAT_read: DMG together with PLAST or VISCO materials is not on the B200 path");
     std::vector<int> set_of_tag(pb.mat.size(), 0);
     std::vector<double> par;
     int nsets = 0;

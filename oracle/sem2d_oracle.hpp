@@ -1258,9 +1258,16 @@ inline void MAT_init_work(Problem& pb, bool force_general_nelast = false) {
   pb.pl_beta.clear();
   for (int e = 1; e <= ne; ++e) {
     const MatInput& in = pb.mat.inputs[g.tag[e - 1] - 1];
+    if (in.kv) {  // mat_kelvin_voigt.f90:117-135
+      pb.mat.get(pb.mat.eta, e, eta.data());
+      if (in.etaxdt)
+        for (int k = 0; k < n2; ++k) eta[k] = pb.time.dt * eta[k];
+      pb.kv_elem.push_back(e);
+      pb.elem2kv[e - 1] = (int)pb.kv_elem.size();
+      pb.kv_eta.insert(pb.kv_eta.end(), eta.begin(), eta.end());
+    }
     if (in.damage) {  // mat_gen.f90:374-378: MAT_set_derint + MAT_DMG_init_elem_work (mat_damage.f90:209-279)
       if (pb.ndof != 2) IO_abort("oracle: damage rheology requires ndof=2 (P-SV)");
-      if (in.kv) IO_abort("oracle: DMG with KV not supported");
       pb.dm_elem.push_back(e);
       pb.elem2dm[e - 1] = (int)pb.dm_elem.size();
       const size_t o = pb.dm_derint.size();
@@ -1302,7 +1309,6 @@ inline void MAT_init_work(Problem& pb, bool force_general_nelast = false) {
     }
     if (in.visco) {  // mat_gen.f90:380-385: MAT_set_derint + MAT_VISCO_init_elem_work (mat_visco.f90:164-200)
       if (pb.ndof != 2) IO_abort("MAT_init_work: visco-elasticity requires ndof=2 (P-SV) ");
-      if (in.kv) IO_abort("oracle: VISCO with KV not supported");
       pb.vs_elem.push_back(e);
       pb.elem2vs[e - 1] = (int)pb.vs_elem.size();
       const size_t o = pb.vs_derint.size();
@@ -1326,7 +1332,6 @@ inline void MAT_init_work(Problem& pb, bool force_general_nelast = false) {
     }
     if (in.plastic) {  // mat_gen.f90:367-372: MAT_set_derint (:645-681) + MAT_PLAST_init_elem_work (mat_plastic.f90:148-218)
       if (pb.ndof != 2) IO_abort("MAT_init_work: plasticity requires ndof=2 (P-SV) ");
-      if (in.kv) IO_abort("oracle: PLAST with KV not supported");
       pb.pl_elem.push_back(e);
       pb.elem2pl[e - 1] = (int)pb.pl_elem.size();
       const size_t o = pb.pl_derint.size();
@@ -1359,14 +1364,6 @@ inline void MAT_init_work(Problem& pb, bool force_general_nelast = false) {
           }
       }
       continue;
-    }
-    if (in.kv) {  // mat_kelvin_voigt.f90:117-135
-      pb.mat.get(pb.mat.eta, e, eta.data());
-      if (in.etaxdt)
-        for (int k = 0; k < n2; ++k) eta[k] = pb.time.dt * eta[k];
-      pb.kv_elem.push_back(e);
-      pb.elem2kv[e - 1] = (int)pb.kv_elem.size();
-      pb.kv_eta.insert(pb.kv_eta.end(), eta.begin(), eta.end());
     }
     int e1 = first[g.tag[e - 1]];
     if (g.flat && !force_general_nelast && in.homogeneous && e > e1) {
@@ -2413,6 +2410,13 @@ inline void compute_Fint(Problem& pb, std::vector<double>& f, const std::vector<
         dloc[k + (size_t)n2 * c] = d[(size_t)(ib[k] - 1) + np * c];
         vloc[k + (size_t)n2 * c] = v[(size_t)(ib[k] - 1) + np * c];
       }
+    // Kelvin-Voigt is the one non-exclusive material: d + eta*v before ANY constitutive law (mat_gen.f90:435)
+    int ikv = pb.elem2kv[e - 1];
+    if (ikv > 0) {  // MAT_KV_add_etav (mat_kelvin_voigt.f90:137-150)
+      const double* eta = &pb.kv_eta[(size_t)n2 * (ikv - 1)];
+      for (int c = 0; c < ndof; ++c)
+        for (int k = 0; k < n2; ++k) dloc[k + (size_t)n2 * c] = dloc[k + (size_t)n2 * c] + eta[k] * vloc[k + (size_t)n2 * c];
+    }
     if (!pb.elem2dm.empty() && pb.elem2dm[e - 1] > 0) {
       // mat_gen.f90:451-457: e = MAT_strain(d), MAT_DMG_stress(update = true, dt) (mat_damage.f90:337-445), f = MAT_forces(s)
       const int id = pb.elem2dm[e - 1] - 1;
@@ -2589,12 +2593,6 @@ inline void compute_Fint(Problem& pb, std::vector<double>& f, const std::vector<
       for (int c = 0; c < ndof; ++c)
         for (int k = 0; k < n2; ++k) f[(size_t)(ib[k] - 1) + np * c] = f[(size_t)(ib[k] - 1) + np * c] + floc[k + (size_t)n2 * c];
       continue;
-    }
-    int ikv = pb.elem2kv[e - 1];
-    if (ikv > 0) {  // MAT_KV_add_etav (mat_kelvin_voigt.f90:137-150)
-      const double* eta = &pb.kv_eta[(size_t)n2 * (ikv - 1)];
-      for (int c = 0; c < ndof; ++c)
-        for (int k = 0; k < n2; ++k) dloc[k + (size_t)n2 * c] = dloc[k + (size_t)n2 * c] + eta[k] * vloc[k + (size_t)n2 * c];
     }
     const double* a = &pb.a[(size_t)n2 * pb.nelast * (pb.elem2set[e - 1] - 1)];
     MAT_ELAST_f(floc.data(), dloc.data(), a, pb.nelast, g.H.data(), g.Ht.data(), n, ndof, s, pb.kd_force_kd1);

@@ -1374,7 +1374,6 @@ class Engine : public EngineBase {
         cart_kv_eta.release();
       }
       if (dm_state.n) {
-        S2D_REQUIRE(strip_eta.n == 0, "damage elements together with Kelvin-Voigt elements: not provided");
         for (int k = 1; k < STRIP_PL_SETS; ++k) dm_raw[k][13] = scheme.dt;
         upload_as(dm_tab, &dm_raw[0][0], (size_t)STRIP_PL_SETS * STRIP_DM_TAB);
       }

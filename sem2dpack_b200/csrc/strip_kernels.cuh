@@ -462,11 +462,15 @@ constexpr int strip_min_ctas_kv(int N, int tsize, int ndof) {
 }
 
 template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false,
-          bool TENS = false, bool PLAST = false>
+          bool TENS = false, int RHEO = 0>
 __global__ void __launch_bounds__(strip_warps() * 32, MINB)
     k_elem_strip(const __grid_constant__ StripArgs<T, N> A) {
-  static_assert(!PLAST || (COMPACT && NDOF == 2 && !KV && !TENS && S2D_COMPACT_FOLD != 0),
-                "plasticity: P-SV, (lambda, mu) coefficient stream, folded metric");
+  // RHEO: stateful rheology of MAT_Fint's strain -> stress -> force branch: 1 Coulomb plasticity, 2 visco-elasticity,
+  // 3 damage (one instantiation each: a run-time switch between them cost the plastic kernel 200 B of spills and 20 %)
+  constexpr bool PLAST = RHEO != 0;
+  static_assert(!PLAST || (COMPACT && NDOF == 2 && !TENS && S2D_COMPACT_FOLD != 0),
+                "stateful rheologies: P-SV, (lambda, mu) coefficient stream, folded metric");
+  static_assert(!(PLAST && KV) || RHEO == 3, "Kelvin-Voigt on top of a stateful rheology: damage only");
   static_assert(!TENS || (FUSED >= 1 && !KV), "tensor-map staging: fused leapfrog / explicit Newmark step");
   static_assert(!COMPACT || NDOF == 2, "compact coefficients: P-SV only");
   static_assert(!KV || !TENS, "Kelvin-Voigt elements: per-lane staging only");
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   const StripGeom& G = A.G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // every lane only ever touches its own slots of the staging area: no barrier guards it
-  unsigned char* wstage = stage_raw + (size_t)warp * (TENS ? SZ_C : strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT, PLAST));
+  unsigned char* wstage = stage_raw + (size_t)warp * (TENS ? SZ_C : strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT, RHEO == 1));
   // TENS: CTA-wide boxes behind the per-warp coefficient staging: stage s at tbase + s * TSZ =
   // [d box | v box | (Newmark: a box) | rmass box | (coefficient blocks)]
   constexpr int BW = strip_box_width(N, sizeof(T));
@@ -616,8 +620,8 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   T* epp = PLAST ? A.pl_ep + (size_t)strip_elem_off(G, seg, strip, ez0) * (3 * N * N) + lanep : nullptr;
   const unsigned char* plp = PLAST ? A.pl_set + strip_elem_off(G, seg, strip, ez0) + el : nullptr;
   int pset_next = (PLAST && wact) ? (int)*plp : 0;
-  T* dmp = (PLAST && A.dm_state) ? A.dm_state + (size_t)strip_elem_off(G, seg, strip, ez0) * 4 * (N * N) + lanep : nullptr;
-  T* vsp = (PLAST && A.vs_state) ? A.vs_state + (size_t)strip_elem_off(G, seg, strip, ez0) * (3 * (A.vs_nb + 1)) * (N * N) + lanep : nullptr;
+  T* dmp = (RHEO == 3) ? A.dm_state + (size_t)strip_elem_off(G, seg, strip, ez0) * 4 * (N * N) + lanep : nullptr;
+  T* vsp = (RHEO == 2) ? A.vs_state + (size_t)strip_elem_off(G, seg, strip, ez0) * (3 * (A.vs_nb + 1)) * (N * N) + lanep : nullptr;
   const int cxN = cx * N;
   const V2* cp = reinterpret_cast<const V2*>(A.coef) +
                  (size_t)strip_elem_off(G, seg, strip, ez0) * (NPL * N * N / 2) + lanep;
@@ -658,7 +662,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           }
       }
     }
-    if (PLAST && S2D_PLAST_STAGE != 0 && A.vs_state == nullptr && A.dm_state == nullptr) {  // the plastic strain of the row's elements travels with its displacements
+    if constexpr (RHEO == 1 && S2D_PLAST_STAGE != 0) {  // the plastic strain of the row's elements travels with its displacements
       const T* en = A.pl_ep + (size_t)strip_elem_off(G, seg, strip, ezr) * (3 * N * N) + lanep;
 #pragma unroll
       for (int k = 0; k < 3 * N; ++k) stage_copy<sizeof(T)>(st_e + k * 32, en + (size_t)k * cxN);
@@ -755,9 +759,10 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
 #pragma unroll
         for (int k = 0; k < 3; ++k)
 #pragma unroll
-          for (int j = 0; j < N; ++j) epr[k][j] = S2D_PLAST_STAGE ? st_e[(k * N + j) * 32] : __ldcs(epp + (size_t)(k * N + j) * cxN);
+          for (int j = 0; j < N; ++j)
+            epr[k][j] = RHEO != 1 ? (T)0 : (S2D_PLAST_STAGE ? st_e[(k * N + j) * 32] : __ldcs(epp + (size_t)(k * N + j) * cxN));
 #pragma unroll
-        for (int q = 0; q < 6; ++q) ppar[q] = (A.vs_state || A.dm_state) ? (T)0 : __ldg(A.pl_tab + pset * 6 + q);
+        for (int q = 0; q < 6; ++q) ppar[q] = RHEO != 1 ? (T)0 : __ldg(A.pl_tab + pset * 6 + q);
         vset = pset;
       }
       if constexpr (TENS) {
@@ -930,7 +935,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       T tH[NDOF][N], tHt[NDOF][N];
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        if (PLAST && A.dm_state != nullptr) {
+        if constexpr (RHEO == 3) {
           // damage rheology: moduli degraded by alpha (mat_damage.f90:372-378), stress and strain invariants of the
           // elastic strain e0 + e - ep (compute_stress), damage growth dalpha = dt Cd i2 [xi alpha^beta - xi_0]+ and
           // the damage-related plastic strain increment Cv dalpha (s - s_mean) (:393-412), relative stress out
@@ -984,7 +989,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           tHt[1][j] = nW[j] * s2;
           continue;
         }
-        if (PLAST && A.vs_state != nullptr) {
+        if constexpr (RHEO == 2) {
           // generalized Maxwell body: the memory variables of every mechanism relax towards the strain of the
           // PREVIOUS evaluation (4th-order expansion of 1 - exp(-w dt), mat_visco.f90:221-229), the strain is kept
           // for the next one, the anelastic stress is taken off the unrelaxed elastic one (:236-246)
@@ -1028,7 +1033,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
           tHt[1][j] = nW[j] * s2;
           continue;
         }
-        if constexpr (PLAST) {
+        if constexpr (RHEO == 1) {
           // MAT_strain_PSV (mat_gen.f90:752-775) on the flat box: e11 = Ux,x  e22 = Uz,z  e12 = (Ux,z + Uz,x)/2;
           // MAT_PLAST_stress with update (mat_plastic.f90:297-377): trial stress from the absolute elastic strain,
           // visco-plastic return of the deviatoric part towards the Coulomb yield stress (Andrews 2005), plastic
@@ -1111,8 +1116,8 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         }
       }
       if constexpr (PLAST) {
-        if (A.vs_state != nullptr) vsp += (size_t)gcx * (3 * (A.vs_nb + 1)) * (N * N);
-        if (A.dm_state != nullptr) dmp += (size_t)gcx * 4 * (N * N);
+        if constexpr (RHEO == 2) vsp += (size_t)gcx * (3 * (A.vs_nb + 1)) * (N * N);
+        if constexpr (RHEO == 3) dmp += (size_t)gcx * 4 * (N * N);
         if (real && yielded) {  // an element that did not yield leaves its plastic strain as it is in HBM
 #pragma unroll
           for (int k = 0; k < 3; ++k)
@@ -1658,10 +1663,10 @@ constexpr int STRIP_PLAST_MAXN = 6;  // plasticity instantiations
 #define S2D_PLAST_MINB 3   // CTAs per SM of the FP64 plasticity instantiations: 168 registers with ~300 B of spills beat 2 CTAs without (4.04 vs 4.36 ms, 2560^2)
 #endif
 template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false,
-          bool TENS = false, bool PLAST = false>
+          bool TENS = false, int RHEO = 0>
 inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) {
   constexpr size_t smem = TENS ? strip_tens_smem(N, NDOF, sizeof(T), COMPACT, FUSED)
-                               : strip_warps() * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT, PLAST);
+                               : strip_warps() * strip_stage_bytes(N, NDOF, sizeof(T), FUSED, COMPACT, RHEO == 1);
   // Opt in to the dynamic shared memory once per device and instantiation.  Never on the step path
   // afterwards: cudaFuncSetAttribute can serialise with running kernels, and a strip that is waiting
   // on its neighbour's flag must not keep the neighbour's host thread from launching.
@@ -1669,11 +1674,11 @@ inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) 
   int dev = 0;
   S2D_CUDA(cudaGetDevice(&dev));
   if (!done[dev & 63]) {
-    S2D_CUDA(cudaFuncSetAttribute(k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV, TENS, PLAST>,
+    S2D_CUDA(cudaFuncSetAttribute(k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV, TENS, RHEO>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done[dev & 63] = true;
   }
-  k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV, TENS, PLAST><<<nb, strip_warps() * 32, smem, s>>>(A);
+  k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV, TENS, RHEO><<<nb, strip_warps() * 32, smem, s>>>(A);
 }
 
 // element-force launch over the groups selected by G.it_* (no halo fold)
@@ -1737,9 +1742,9 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
         break;                                                                                    \
       }                                                                                           \
     }                                                                                             \
-    if (io.pl_set) { /* Coulomb plasticity: state per element GLL point, 2 CTAs / SM */             \
+    if (io.pl_set) { /* stateful rheologies: plasticity / visco-elasticity / damage, state per element GLL point */ \
       if constexpr (NN <= STRIP_PLAST_MAXN) {                                                     \
-        if (!io.compact || G.ndof != 2 || io.eta) throw ArgError("plasticity: isotropic P-SV boxes without Kelvin-Voigt elements"); \
+        if (!io.compact || G.ndof != 2) throw ArgError("stateful rheologies: isotropic P-SV boxes");  \
         A.pl_set = io.pl_set;                                                                     \
         A.pl_ep = io.pl_ep;                                                                       \
         A.pl_tab = io.pl_tab;                                                                     \
@@ -1750,12 +1755,30 @@ inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cu
         A.dm_tab = io.dm_tab;                                                                     \
         A.dm_err = io.dm_err;                                                                     \
         constexpr int MP = sizeof(T) == 8 ? S2D_PLAST_MINB : 3;                                   \
-        if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, true>(nb, A, s);         \
-        else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, true>(nb, A, s);    \
-        else strip_launch<T, NN, 2, 0, true, MP, false, false, true>(nb, A, s);                   \
+        constexpr int MK = sizeof(T) == 8 ? 2 : 3;                                                \
+        if (io.eta) { /* a Kelvin-Voigt layer on top (EXAMPLES/Damage: kind='DMG','KV') */          \
+          if (!io.dm_state) throw ArgError("Kelvin-Voigt elements together with plastic or visco-elastic ones: not provided"); \
+          if (mode != 0 && (io.v_in == io.v_out || (mode == 2 && (const T*)io.f == io.a_in)))     \
+            throw ArgError("Kelvin-Voigt elements: the fused update needs separate output buffers"); \
+          if (mode == 2) strip_launch<T, NN, 2, 2, true, MK, true, false, 3>(nb, A, s);           \
+          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MK, true, false, 3>(nb, A, s);      \
+          else strip_launch<T, NN, 2, 0, true, MK, true, false, 3>(nb, A, s);                     \
+        } else if (io.dm_state) {                                                                 \
+          if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, 3>(nb, A, s);          \
+          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 3>(nb, A, s);     \
+          else strip_launch<T, NN, 2, 0, true, MP, false, false, 3>(nb, A, s);                    \
+        } else if (io.vs_state) {                                                                 \
+          if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, 2>(nb, A, s);          \
+          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 2>(nb, A, s);     \
+          else strip_launch<T, NN, 2, 0, true, MP, false, false, 2>(nb, A, s);                    \
+        } else {                                                                                  \
+          if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, 1>(nb, A, s);          \
+          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 1>(nb, A, s);     \
+          else strip_launch<T, NN, 2, 0, true, MP, false, false, 1>(nb, A, s);                    \
+        }                                                                                         \
         break;                                                                                    \
       }                                                                                           \
-      throw ArgError("plasticity: ngll <= 6 only");                                               \
+      throw ArgError("stateful rheologies: ngll <= 6 only");                                      \
     }                                                                                             \
     if (io.eta) { /* Kelvin-Voigt elements: plain force evaluation from d + eta*v */               \
       constexpr int MB = strip_min_ctas_kv(NN, sizeof(T), 1), M2 = strip_min_ctas_kv(NN, sizeof(T), 2);  \

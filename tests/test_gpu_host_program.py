@@ -433,18 +433,20 @@ def test_attenuation_deck_visco_elastic_medium(tmp_path):
 
 
 def test_damage_deck_off_fault_damage(tmp_path):
-    """EXAMPLES/Damage (kind='DMG' on both tags, SWF + TWF fault, four absorbing sides, leapfrog; nondimensional units),
-    coarsened to 60 x 24 elements and without the Kelvin-Voigt layer of tag 2 (DMG with KV is not on the B200 path):
-    rupture nucleates, the off-fault medium accumulates damage and damage-related plastic strain.  Velocity and stress
-    snapshots and the fault records against the oracle.  No reference artefact pins this deck: oracle parity."""
+    """EXAMPLES/Damage unchanged but for size and length (60 x 24 elements, 500 steps): kind='DMG' on tag 1,
+    kind='DMG','KV' on the element rows next to the fault (fztag = 2: the damage rheology under a Kelvin-Voigt layer,
+    d + eta*v before the constitutive law, mat_gen.f90:435), background stress Szz / Sxz on the SWF + TWF fault, four
+    absorbing sides, leapfrog, nondimensional units.  Rupture nucleates, the off-fault medium accumulates damage and
+    damage-related plastic strain.  Velocity snapshot and fault records against the oracle.  No reference artefact
+    pins the time series (the deck's prestrain / fault-stress consistency is pinned in tests/test_oracle_golden.py)."""
     nsteps = 500
-    deck = harness.deck("damage").replace("kind='DMG','KV'", "kind='DMG'").replace("nelem=240,100", "nelem=60,24")
+    deck = harness.deck("damage").replace("nelem=240,100", "nelem=60,24")
     deck = deck.replace("TotalTime=30d0", f"NbSteps={nsteps}").replace("itd=200", f"itd={nsteps}").replace("iexec=0", "iexec=1")
-    assert f"NbSteps={nsteps}" in deck and "nelem=60,24" in deck and "'KV'" not in deck
+    assert f"NbSteps={nsteps}" in deck and "nelem=60,24" in deck and "'DMG','KV'" in deck
     p = run(tmp_path, deck, "--quiet", "--natural-order")
     assert p.returncode == 0, p.stdout + p.stderr
     o = orc.Oracle(deck, renumber=False)
-    assert o.i("ndm") == 60 * 24
+    assert o.i("ndm") == 60 * 24 and o.i("nkv") == 2 * 60
     o.step(nsteps)
     st = o.arr("dm_state").reshape(-1, 4, 25)
     assert st[:, 0].max() > 0.05 and np.abs(st[:, 1:]).max() > 1e-3      # damage and plastic strain have grown
