@@ -1,0 +1,12 @@
+// Strip-kernel instantiations: float, NGLL 3, 4, 5 (see launch_strip_case in strip_kernels.cuh).
+#define S2D_STRIP_CASES
+#include "strip_kernels.cuh"
+namespace s2d {
+#ifndef S2D_ONLY_N5
+template void launch_strip_case<float, 3>(const StripGeom&, const StripIO<float>&, cudaStream_t);
+#endif
+#ifndef S2D_ONLY_N5
+template void launch_strip_case<float, 4>(const StripGeom&, const StripIO<float>&, cudaStream_t);
+#endif
+template void launch_strip_case<float, 5>(const StripGeom&, const StripIO<float>&, cudaStream_t);
+}  // namespace s2d

@@ -1681,169 +1681,178 @@ inline void strip_launch(unsigned nb, const StripArgs<T, N>& A, cudaStream_t s) 
   k_elem_strip<T, N, NDOF, FUSED, COMPACT, MINB, KV, TENS, RHEO><<<nb, strip_warps() * 32, smem, s>>>(A);
 }
 
+// Element-force launch of one NGLL (all its instantiations of k_elem_strip).  Defined only in the translation units that
+// set S2D_STRIP_CASES (strip_cases.inc: one TU per precision and NGLL range, so that the ~580 kernel instantiations
+// compile in parallel and only once); everybody else sees the declaration.
+template <typename T, int NN>
+void launch_strip_case(const StripGeom& G, const StripIO<T>& io, cudaStream_t s);
+#ifdef S2D_STRIP_CASES
+template <typename T, int NN>
+void launch_strip_case(const StripGeom& G, const StripIO<T>& io, cudaStream_t s) {
+  const bool fused = io.v_in != nullptr;
+
+    StripArgs<T, NN> A{};
+    A.G = G;
+    A.coef = io.coef;
+    A.d = io.d;
+    A.f = io.f;
+    A.halo_x = io.halo_x;
+    A.halo_z = io.halo_z;
+    A.npoin = io.npoin;
+    A.v_in = io.v_in;
+    A.v_out = io.v_out;
+    A.rmass = io.rmass;
+    A.d_next = io.d_next;
+    A.a_out = io.a_out;
+    A.rowflag = io.rowflag;
+    A.colflag = io.colflag;
+    A.meet = io.meet;
+    A.dt = (T)io.dt;
+    A.c1 = (T)io.c1;
+    A.c2 = (T)io.c2;
+    A.c3 = (T)(fused && !io.newmark ? io.dt : io.c3);
+    A.a_in = io.a_in;
+    A.eta = io.eta;
+    A.v_kv = io.v_kv;
+    A.beta = io.beta;
+    A.prefetch = io.prefetch;
+    for (int k = 0; k < NN * NN; ++k) A.H[k] = (T)io.hprime[k];
+    A.cdx = (T)io.cdx;
+    A.cdz = (T)io.cdz;
+    A.cdet = (T)io.cdet;
+    for (int k = 0; k < NN; ++k) A.wg[k] = io.wgll ? (T)io.wgll[k] : (T)0;
+    for (int k = 0; k < NN * NN; ++k) A.Hz[k] = (T)(io.cdz * io.hprime[k]);
+    A.rzx = (T)(io.cdx != 0.0 ? io.cdz / io.cdx : 0.0);
+    const unsigned nb = (unsigned)G.nitems;
+    const int mode = !fused ? 0 : (io.newmark ? 2 : 1);
+    if constexpr (NN <= 6) { /* CTA-wide tensor-map staging of the fused step (S2D_STRIP_TENSOR) */
+      if (mode >= 1 && io.tm_d && !io.eta && !io.pl_set) {
+        constexpr int MB = strip_min_ctas(NN, sizeof(T));
+        A.tm_d = *io.tm_d;
+        A.tm_v = *io.tm_v;
+        A.tm_r = *io.tm_r;
+        if (mode == 2) A.tm_a = *io.tm_a;
+        if (G.ndof == 1) {
+          if (mode == 2) strip_launch<T, NN, 1, 2, false, MB, false, true>(nb, A, s);
+          else strip_launch<T, NN, 1, 1, false, MB, false, true>(nb, A, s);
+        } else if (io.compact) {
+          if (mode == 2) strip_launch<T, NN, 2, 2, true, MB, false, true>(nb, A, s);
+          else strip_launch<T, NN, 2, 1, true, MB, false, true>(nb, A, s);
+        } else {
+          if (mode == 2) strip_launch<T, NN, 2, 2, false, MB, false, true>(nb, A, s);
+          else strip_launch<T, NN, 2, 1, false, MB, false, true>(nb, A, s);
+        }
+        return;
+      }
+    }
+    if (io.pl_set) { /* stateful rheologies: plasticity / visco-elasticity / damage, state per element GLL point */
+      if constexpr (NN <= STRIP_PLAST_MAXN) {
+        if (!io.compact || G.ndof != 2) throw ArgError("stateful rheologies: isotropic P-SV boxes");
+        A.pl_set = io.pl_set;
+        A.pl_ep = io.pl_ep;
+        A.pl_tab = io.pl_tab;
+        A.vs_state = io.vs_state;
+        A.vs_tab = io.vs_tab;
+        A.vs_nb = io.vs_nb;
+        A.dm_state = io.dm_state;
+        A.dm_tab = io.dm_tab;
+        A.dm_err = io.dm_err;
+        constexpr int MP = sizeof(T) == 8 ? S2D_PLAST_MINB : 3;
+        constexpr int MK = sizeof(T) == 8 ? 2 : 3;
+        if (io.eta) { /* a Kelvin-Voigt layer on top (EXAMPLES/Damage: kind='DMG','KV') */
+          if (!io.dm_state) throw ArgError("Kelvin-Voigt elements together with plastic or visco-elastic ones: not provided");
+          if (mode != 0 && (io.v_in == io.v_out || (mode == 2 && (const T*)io.f == io.a_in)))
+            throw ArgError("Kelvin-Voigt elements: the fused update needs separate output buffers");
+          if (mode == 2) strip_launch<T, NN, 2, 2, true, MK, true, false, 3>(nb, A, s);
+          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MK, true, false, 3>(nb, A, s);
+          else strip_launch<T, NN, 2, 0, true, MK, true, false, 3>(nb, A, s);
+        } else if (io.dm_state) {
+          if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, 3>(nb, A, s);
+          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 3>(nb, A, s);
+          else strip_launch<T, NN, 2, 0, true, MP, false, false, 3>(nb, A, s);
+        } else if (io.vs_state) {
+          if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, 2>(nb, A, s);
+          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 2>(nb, A, s);
+          else strip_launch<T, NN, 2, 0, true, MP, false, false, 2>(nb, A, s);
+        } else {
+          if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, 1>(nb, A, s);
+          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 1>(nb, A, s);
+          else strip_launch<T, NN, 2, 0, true, MP, false, false, 1>(nb, A, s);
+        }
+        return;
+      }
+      throw ArgError("stateful rheologies: ngll <= 6 only");
+    }
+    if (io.eta) { /* Kelvin-Voigt elements: plain force evaluation from d + eta*v */
+      constexpr int MB = strip_min_ctas_kv(NN, sizeof(T), 1), M2 = strip_min_ctas_kv(NN, sizeof(T), 2);
+      if (mode != 0) { /* fused with the node update: v (and a) double-buffered by the caller */
+        if constexpr (NN <= STRIP_KV_FUSED_MAXN) {
+          if (io.v_in == io.v_out || (mode == 2 && (const T*)io.f == io.a_in))
+            throw ArgError("Kelvin-Voigt elements: the fused update needs separate output buffers");
+          if (G.ndof == 1) {
+            if (mode == 2) strip_launch<T, NN, 1, 2, false, MB, true>(nb, A, s);
+            else strip_launch<T, NN, 1, 1, false, MB, true>(nb, A, s);
+          } else if (io.compact) {
+            if (mode == 2) strip_launch<T, NN, 2, 2, true, M2, true>(nb, A, s);
+            else strip_launch<T, NN, 2, 1, true, M2, true>(nb, A, s);
+          } else {
+            if (mode == 2) strip_launch<T, NN, 2, 2, false, M2, true>(nb, A, s);
+            else strip_launch<T, NN, 2, 1, false, M2, true>(nb, A, s);
+          }
+          return;
+        }
+        throw ArgError("Kelvin-Voigt elements: the node update is fused for ngll <= 6 only");
+      }
+      if (G.ndof == 1) strip_launch<T, NN, 1, 0, false, MB, true>(nb, A, s);
+      else if (io.compact) strip_launch<T, NN, 2, 0, true, M2, true>(nb, A, s);
+      else strip_launch<T, NN, 2, 0, false, M2, true>(nb, A, s);
+      return;
+    }
+    if (G.ndof == 1) {
+      if (io.compact) throw ArgError("compact coefficients need ndof = 2");
+      if (mode == 2) strip_launch<T, NN, 1, 2, false>(nb, A, s);
+      else if (mode == 1) strip_launch<T, NN, 1, 1, false>(nb, A, s);
+      else strip_launch<T, NN, 1, 0, false>(nb, A, s);
+    } else if (io.compact) {
+      if constexpr (NN == 5 && sizeof(T) == 8) {  /* measured alternative: 4 CTAs/SM, spills */
+        if (io.occ == 4 && mode < 2) {
+          if (mode == 1) strip_launch<T, NN, 2, 1, true, 4>(nb, A, s);
+          else strip_launch<T, NN, 2, 0, true, 4>(nb, A, s);
+          return;
+        }
+      }
+      if (mode == 2) strip_launch<T, NN, 2, 2, true>(nb, A, s);
+      else if (mode == 1) strip_launch<T, NN, 2, 1, true>(nb, A, s);
+      else strip_launch<T, NN, 2, 0, true>(nb, A, s);
+    } else {
+      if (mode == 2) strip_launch<T, NN, 2, 2, false>(nb, A, s);
+      else if (mode == 1) strip_launch<T, NN, 2, 1, false>(nb, A, s);
+      else strip_launch<T, NN, 2, 0, false>(nb, A, s);
+    }
+
+}
+#endif
+
 // element-force launch over the groups selected by G.it_* (no halo fold)
 template <typename T>
 inline void launch_elem_strip_items(const StripGeom& G, const StripIO<T>& io, cudaStream_t s) {
   if (G.nitems <= 0) return;
-  const bool fused = io.v_in != nullptr;
-#define S2D_STRIP_CASE(NN)                                                                        \
-  case NN: {                                                                                      \
-    StripArgs<T, NN> A{};                                                                         \
-    A.G = G;                                                                                      \
-    A.coef = io.coef;                                                                             \
-    A.d = io.d;                                                                                   \
-    A.f = io.f;                                                                                   \
-    A.halo_x = io.halo_x;                                                                         \
-    A.halo_z = io.halo_z;                                                                         \
-    A.npoin = io.npoin;                                                                           \
-    A.v_in = io.v_in;                                                                             \
-    A.v_out = io.v_out;                                                                           \
-    A.rmass = io.rmass;                                                                           \
-    A.d_next = io.d_next;                                                                         \
-    A.a_out = io.a_out;                                                                           \
-    A.rowflag = io.rowflag;                                                                       \
-    A.colflag = io.colflag;                                                                       \
-    A.meet = io.meet;                                                                             \
-    A.dt = (T)io.dt;                                                                              \
-    A.c1 = (T)io.c1;                                                                              \
-    A.c2 = (T)io.c2;                                                                              \
-    A.c3 = (T)(fused && !io.newmark ? io.dt : io.c3);                                             \
-    A.a_in = io.a_in;                                                                             \
-    A.eta = io.eta;                                                                               \
-    A.v_kv = io.v_kv;                                                                             \
-    A.beta = io.beta;                                                                             \
-    A.prefetch = io.prefetch;                                                                     \
-    for (int k = 0; k < NN * NN; ++k) A.H[k] = (T)io.hprime[k];                                   \
-    A.cdx = (T)io.cdx;                                                                            \
-    A.cdz = (T)io.cdz;                                                                            \
-    A.cdet = (T)io.cdet;                                                                          \
-    for (int k = 0; k < NN; ++k) A.wg[k] = io.wgll ? (T)io.wgll[k] : (T)0;                        \
-    for (int k = 0; k < NN * NN; ++k) A.Hz[k] = (T)(io.cdz * io.hprime[k]);                        \
-    A.rzx = (T)(io.cdx != 0.0 ? io.cdz / io.cdx : 0.0);                                           \
-    const unsigned nb = (unsigned)G.nitems;                                                       \
-    const int mode = !fused ? 0 : (io.newmark ? 2 : 1);                                           \
-    if constexpr (NN <= 6) { /* CTA-wide tensor-map staging of the fused step (S2D_STRIP_TENSOR) */ \
-      if (mode >= 1 && io.tm_d && !io.eta && !io.pl_set) {                                                      \
-        constexpr int MB = strip_min_ctas(NN, sizeof(T));                                         \
-        A.tm_d = *io.tm_d;                                                                        \
-        A.tm_v = *io.tm_v;                                                                        \
-        A.tm_r = *io.tm_r;                                                                        \
-        if (mode == 2) A.tm_a = *io.tm_a;                                                         \
-        if (G.ndof == 1) {                                                                        \
-          if (mode == 2) strip_launch<T, NN, 1, 2, false, MB, false, true>(nb, A, s);             \
-          else strip_launch<T, NN, 1, 1, false, MB, false, true>(nb, A, s);                       \
-        } else if (io.compact) {                                                                  \
-          if (mode == 2) strip_launch<T, NN, 2, 2, true, MB, false, true>(nb, A, s);              \
-          else strip_launch<T, NN, 2, 1, true, MB, false, true>(nb, A, s);                        \
-        } else {                                                                                  \
-          if (mode == 2) strip_launch<T, NN, 2, 2, false, MB, false, true>(nb, A, s);             \
-          else strip_launch<T, NN, 2, 1, false, MB, false, true>(nb, A, s);                       \
-        }                                                                                         \
-        break;                                                                                    \
-      }                                                                                           \
-    }                                                                                             \
-    if (io.pl_set) { /* stateful rheologies: plasticity / visco-elasticity / damage, state per element GLL point */ \
-      if constexpr (NN <= STRIP_PLAST_MAXN) {                                                     \
-        if (!io.compact || G.ndof != 2) throw ArgError("stateful rheologies: isotropic P-SV boxes");  \
-        A.pl_set = io.pl_set;                                                                     \
-        A.pl_ep = io.pl_ep;                                                                       \
-        A.pl_tab = io.pl_tab;                                                                     \
-        A.vs_state = io.vs_state;                                                                 \
-        A.vs_tab = io.vs_tab;                                                                     \
-        A.vs_nb = io.vs_nb;                                                                       \
-        A.dm_state = io.dm_state;                                                                 \
-        A.dm_tab = io.dm_tab;                                                                     \
-        A.dm_err = io.dm_err;                                                                     \
-        constexpr int MP = sizeof(T) == 8 ? S2D_PLAST_MINB : 3;                                   \
-        constexpr int MK = sizeof(T) == 8 ? 2 : 3;                                                \
-        if (io.eta) { /* a Kelvin-Voigt layer on top (EXAMPLES/Damage: kind='DMG','KV') */          \
-          if (!io.dm_state) throw ArgError("Kelvin-Voigt elements together with plastic or visco-elastic ones: not provided"); \
-          if (mode != 0 && (io.v_in == io.v_out || (mode == 2 && (const T*)io.f == io.a_in)))     \
-            throw ArgError("Kelvin-Voigt elements: the fused update needs separate output buffers"); \
-          if (mode == 2) strip_launch<T, NN, 2, 2, true, MK, true, false, 3>(nb, A, s);           \
-          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MK, true, false, 3>(nb, A, s);      \
-          else strip_launch<T, NN, 2, 0, true, MK, true, false, 3>(nb, A, s);                     \
-        } else if (io.dm_state) {                                                                 \
-          if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, 3>(nb, A, s);          \
-          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 3>(nb, A, s);     \
-          else strip_launch<T, NN, 2, 0, true, MP, false, false, 3>(nb, A, s);                    \
-        } else if (io.vs_state) {                                                                 \
-          if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, 2>(nb, A, s);          \
-          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 2>(nb, A, s);     \
-          else strip_launch<T, NN, 2, 0, true, MP, false, false, 2>(nb, A, s);                    \
-        } else {                                                                                  \
-          if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, 1>(nb, A, s);          \
-          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 1>(nb, A, s);     \
-          else strip_launch<T, NN, 2, 0, true, MP, false, false, 1>(nb, A, s);                    \
-        }                                                                                         \
-        break;                                                                                    \
-      }                                                                                           \
-      throw ArgError("stateful rheologies: ngll <= 6 only");                                      \
-    }                                                                                             \
-    if (io.eta) { /* Kelvin-Voigt elements: plain force evaluation from d + eta*v */               \
-      constexpr int MB = strip_min_ctas_kv(NN, sizeof(T), 1), M2 = strip_min_ctas_kv(NN, sizeof(T), 2);  \
-      if (mode != 0) { /* fused with the node update: v (and a) double-buffered by the caller */   \
-        if constexpr (NN <= STRIP_KV_FUSED_MAXN) {                                                \
-          if (io.v_in == io.v_out || (mode == 2 && (const T*)io.f == io.a_in))                    \
-            throw ArgError("Kelvin-Voigt elements: the fused update needs separate output buffers"); \
-          if (G.ndof == 1) {                                                                      \
-            if (mode == 2) strip_launch<T, NN, 1, 2, false, MB, true>(nb, A, s);                  \
-            else strip_launch<T, NN, 1, 1, false, MB, true>(nb, A, s);                            \
-          } else if (io.compact) {                                                                \
-            if (mode == 2) strip_launch<T, NN, 2, 2, true, M2, true>(nb, A, s);                   \
-            else strip_launch<T, NN, 2, 1, true, M2, true>(nb, A, s);                             \
-          } else {                                                                                \
-            if (mode == 2) strip_launch<T, NN, 2, 2, false, M2, true>(nb, A, s);                  \
-            else strip_launch<T, NN, 2, 1, false, M2, true>(nb, A, s);                            \
-          }                                                                                       \
-          break;                                                                                  \
-        }                                                                                         \
-        throw ArgError("Kelvin-Voigt elements: the node update is fused for ngll <= 6 only");      \
-      }                                                                                           \
-      if (G.ndof == 1) strip_launch<T, NN, 1, 0, false, MB, true>(nb, A, s);                      \
-      else if (io.compact) strip_launch<T, NN, 2, 0, true, M2, true>(nb, A, s);                   \
-      else strip_launch<T, NN, 2, 0, false, M2, true>(nb, A, s);                                  \
-      break;                                                                                      \
-    }                                                                                             \
-    if (G.ndof == 1) {                                                                            \
-      if (io.compact) throw ArgError("compact coefficients need ndof = 2");                       \
-      if (mode == 2) strip_launch<T, NN, 1, 2, false>(nb, A, s);                                  \
-      else if (mode == 1) strip_launch<T, NN, 1, 1, false>(nb, A, s);                             \
-      else strip_launch<T, NN, 1, 0, false>(nb, A, s);                                            \
-    } else if (io.compact) {                                                                      \
-      if constexpr (NN == 5 && sizeof(T) == 8) {  /* measured alternative: 4 CTAs/SM, spills */    \
-        if (io.occ == 4 && mode < 2) {                                                            \
-          if (mode == 1) strip_launch<T, NN, 2, 1, true, 4>(nb, A, s);                            \
-          else strip_launch<T, NN, 2, 0, true, 4>(nb, A, s);                                      \
-          break;                                                                                  \
-        }                                                                                         \
-      }                                                                                           \
-      if (mode == 2) strip_launch<T, NN, 2, 2, true>(nb, A, s);                                   \
-      else if (mode == 1) strip_launch<T, NN, 2, 1, true>(nb, A, s);                              \
-      else strip_launch<T, NN, 2, 0, true>(nb, A, s);                                             \
-    } else {                                                                                      \
-      if (mode == 2) strip_launch<T, NN, 2, 2, false>(nb, A, s);                                  \
-      else if (mode == 1) strip_launch<T, NN, 2, 1, false>(nb, A, s);                             \
-      else strip_launch<T, NN, 2, 0, false>(nb, A, s);                                            \
-    }                                                                                             \
-  } break;
   switch (G.N) {
 #ifndef S2D_ONLY_N5
-    S2D_STRIP_CASE(3)
-    S2D_STRIP_CASE(4)
+    case 3: launch_strip_case<T, 3>(G, io, s); break;
+    case 4: launch_strip_case<T, 4>(G, io, s); break;
 #endif
-    S2D_STRIP_CASE(5)
+    case 5: launch_strip_case<T, 5>(G, io, s); break;
 #ifndef S2D_ONLY_N5
-    S2D_STRIP_CASE(6)
-    S2D_STRIP_CASE(7)
-    S2D_STRIP_CASE(8)
-    S2D_STRIP_CASE(9)
-    S2D_STRIP_CASE(10)
+    case 6: launch_strip_case<T, 6>(G, io, s); break;
+    case 7: launch_strip_case<T, 7>(G, io, s); break;
+    case 8: launch_strip_case<T, 8>(G, io, s); break;
+    case 9: launch_strip_case<T, 9>(G, io, s); break;
+    case 10: launch_strip_case<T, 10>(G, io, s); break;
 #endif
     default:
       throw ArgError("ngll must be in 3..10");
   }
-#undef S2D_STRIP_CASE
   S2D_CUDA(cudaGetLastError());
 }
 template <typename T>
