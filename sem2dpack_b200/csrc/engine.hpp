@@ -1251,7 +1251,7 @@ class Engine : public EngineBase {
     tm_ready = false;
     // measured on B200 (4096^2 FP64, ms per launch, per-lane copies -> boxes): compact leapfrog 5.96 -> 5.74, compact
     // Newmark 7.32 -> 6.81, six stored planes 7.39 -> 7.43 (its coefficient block already comes by TMA): not there
-    if (strip_tensor && ngll <= 6 && (cart_compact || ndof == 1)) {
+    if (strip_tensor && ngll <= S2D_STRIP_TENSOR_MAXN && (cart_compact || ndof == 1)) {
       const int bw = strip_box_width(ngll, (int)sizeof(T));
       // the TENS variant keeps its CTAs per SM only while the shared memory fits (static part: tile, hand-over, masks)
       const int fusedk = scheme.kind == 1 ? 2 : 1;

@@ -393,6 +393,10 @@ constexpr size_t strip_stage_bytes(int N, int NDOF, int tsize, int fused, bool c
 // also arrive CTA-wide, by one bulk copy on the displacement box's mbarrier.  Measured on B200, 4096^2 FP64 compact
 // fused, ms per launch: per-lane LDGSTS everywhere 5.84-5.94, boxes for d / v / rmass + per-lane coefficients 5.70-5.75,
 // boxes + CTA-wide coefficient copy 6.18 -- so 0 is the default.
+// largest ngll with a tensor-map instantiation
+#ifndef S2D_STRIP_TENSOR_MAXN
+#define S2D_STRIP_TENSOR_MAXN 10  // NGLL 9 (Lamb x24): 1.169 -> 1.090 ms per step with the boxes
+#endif
 #ifndef S2D_STRIP_TENSOR_COEF
 #define S2D_STRIP_TENSOR_COEF 0
 #endif
@@ -1725,7 +1729,7 @@ void launch_strip_case(const StripGeom& G, const StripIO<T>& io, cudaStream_t s)
     A.rzx = (T)(io.cdx != 0.0 ? io.cdz / io.cdx : 0.0);
     const unsigned nb = (unsigned)G.nitems;
     const int mode = !fused ? 0 : (io.newmark ? 2 : 1);
-    if constexpr (NN <= 6) { /* CTA-wide tensor-map staging of the fused step (S2D_STRIP_TENSOR) */
+    if constexpr (NN <= S2D_STRIP_TENSOR_MAXN) { /* CTA-wide tensor-map staging of the fused step (S2D_STRIP_TENSOR) */
       if (mode >= 1 && io.tm_d && !io.eta && !io.pl_set) {
         constexpr int MB = strip_min_ctas(NN, sizeof(T));
         A.tm_d = *io.tm_d;
