@@ -1725,9 +1725,9 @@ class Engine : public EngineBase {
     // recording 'A', S2D_STORE_ACCEL=1.  Otherwise (leapfrog) they are formed on demand -- ensure_accel(), at
     // s2d_get_fields / s2d_cart_get_window -- from one plain force evaluation of the displacement the step used: no
     // 8 B/DOF of stores per s2d_step call.  Where that evaluation is not repeatable (state advanced by every
-    // evaluation: plasticity; Kelvin-Voigt: v already updated) or needs the neighbours (x-strips), the last step of
-    // every call stores them as before.
-    const bool lazy_ok = store_accel == 2 && accel_lazy && !nmk && !xhalo() && strip_eta.n == 0 && pl_set.n == 0;  // pl_set: plastic or visco
+    // evaluation: the stateful rheologies; Kelvin-Voigt: v already updated), the last step of every call stores
+    // them as before.
+    const bool lazy_ok = store_accel == 2 && accel_lazy && !nmk && strip_eta.n == 0 && pl_set.n == 0;  // pl_set: any stateful rheology
     const bool want_a = nmk || store_accel == 1 ||
                         (store_accel == 2 && ((last_of_call && !lazy_ok) || (rec.present && rec.field == 'A')));
     a_stale = !want_a;
@@ -1955,7 +1955,10 @@ class Engine : public EngineBase {
     const size_t nd = npoin * ndof;
     if (scratch.n != nd) scratch.alloc(nd);
     StripIO<T> io = strip_io(dbuf().p, scratch.p);
-    launch_strips(io);
+    // no interface exchange on x-strips: the interface columns are deferred nodes (their accelerations are stored),
+    // every other node's force is complete with this GPU's elements alone -- so this is not a collective call
+    launch_elem_strip_items<T>(strip_all_groups(cart_S), io, stream);
+    launches += 1 + launch_strip_fold<T>(cart_S, io.f, cart_hx.p, cart_hz.p, npoin, stream, nullptr);
     const long long tot = (long long)cart_S.LX * cart_S.LZ;
     k_strip_accel_fill<T><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(cart_S.LX, cart_S.LXP, cart_S.LZ, ndof, npoin, rowflag.p,
                                                                         colflag.p, scratch.p, rmass.p, a.p);

@@ -54,7 +54,7 @@ def test_strips_match_whole_box(world, nx, nz, ezflt, seg, scheme, peer, monkeyp
     tab = np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)])
     whole, _, _ = _build(nx, nz, 0, nx, ezflt, kind, nsteps, 0, 1, sdir)
     whole.step(nsteps, tab)
-    dw, vw, _ = whole.get_fields()
+    dw, vw, aw = whole.get_fields()
     ibw = whole.get_tables(rmass=False)[0].reshape(nz, nx, 25)
     o.step(nsteps)
     assert rel_l2(dw, o.arr("d")) <= 1e-10
@@ -68,13 +68,14 @@ def test_strips_match_whole_box(world, nx, nz, ezflt, seg, scheme, peer, monkeyp
     fields = []
     for r, (lo, hi) in enumerate(parts):
         e = engines[r]
-        d, v, _ = e.get_fields()
+        d, v, acc = e.get_fields()   # accelerations: formed on demand, one strip at a time (no exchange needed)
         fields.append((d, v))
         ib = e.get_tables(rmass=False)[0].reshape(nz, hi - lo, 25) - 1
         gl = ibw[:, lo:hi, :] - 1
         for c in range(2):
             assert rel_l2(d[ib + c * e.npoin], dw[gl + c * npw]) <= 1e-11
             assert rel_l2(v[ib + c * e.npoin], vw[gl + c * npw]) <= 1e-11
+            assert rel_l2(acc[ib + c * e.npoin], aw[gl + c * npw]) <= 1e-11
     # the two copies of every interface node are bit-identical
     for r in range(world - 1):
         eL, eR = engines[r], engines[r + 1]
