@@ -514,3 +514,86 @@ def test_damage_rheology_force_evaluations_and_state(ngll, nx, nz, ezflt, seg, b
     assert np.abs(st - st_ref).max() <= 1e-12 * np.abs(st_ref).max()
     e.close()
     o.close()
+
+
+@pytest.mark.parametrize("rheology", ["plastic", "visco", "damage"])
+def test_stateful_rheologies_fused_steps_fp64_and_fp32(rheology):
+    """40 fused leapfrog steps (absorbing sides, a Ricker force strong enough to drive the medium into the inelastic
+    range) with each stateful rheology, FP64 at 1e-10 and FP32 fields at 1e-4 against the oracle: the state lives
+    through the fused update, the deferred nodes and the double displacement buffer."""
+    nx, nz, nsteps, h, ngll = 29, 13, 40, 100.0, 5
+    mat = {"plastic": ("PLAST", "&MAT_PLASTIC rho=2670.d0, cp=6000.d0, cs=3464.d0, phi=30d0, coh=1.0d4, Tv=0.01d0, e0=-4d-6,-3d-6,2.5d-6 /"),
+           "visco": ("VISCO", "&MAT_VISCO rho=2670.d0, cp=6000.d0, cs=3464.d0, QP=40d0, QS=25d0, Nbody=3, fmin=0.5d0, fmax=50d0 /"),
+           "damage": ("DMG", "&MAT_DAMAGE rho=2670.d0, cp=6000.d0, cs=3464.d0, beta=0d0, R=1d0, Cd=1d5, phi=30.9638d0, alpha=0d0, e0=-1.487381d-5,-1.708729d-6,3.5d-6 /")}[rheology]
+    L = [f"&GENERAL iexec=1, ngll={ngll}, fmax=3.d0, ndof=2, title='rheology', verbose='0000', ItInfo=1000 /",
+         "&MESH_DEF method='CARTESIAN' /",
+         f"&MESH_CART xlim=0d0,{nx*h}d0, zlim=0d0,{nz*h}d0, nelem={nx},{nz} /",
+         f"&MATERIAL tag=1, kind='{mat[0]}' /", mat[1]]
+    for t in (1, 2, 3, 4):
+        L += [f"&BC_DEF tag={t}, kind='ABSORB' /"]
+    L += [f"&TIME NbSteps={nsteps}, courant=0.5d0, kind='leapfrog' /",
+          f"&SRC_DEF stf='RICKER', coord={0.37*nx*h}d0,{0.61*nz*h}d0, mechanism='FORCE' /",
+          "&STF_RICKER f0=4.d0, onset=0.02d0, ampli=2.d10 /", "&SRC_FORCE angle=30d0 /"]
+    deck = "\n".join(L) + "\n"
+    rho, cp, cs = 2670.0, 6000.0, 3464.0
+    for precision, tol in ((8, 1e-10), (4, 1e-4)):
+        o = orc.Oracle(deck, renumber=False)
+        e = CartEngine(ngll, 2, nx, nz, (0.0, nx * h), (0.0, nz * h), seed=0, rho=rho, cp=cp, cs=cs, precision=precision)
+        e.set_dt(o.f("dt"))
+        one = np.ones(nx * nz, np.int32)
+        if rheology == "plastic":
+            e.set_plastic([[1.0e4, 30.0, 0.01, -4e-6, -3e-6, 2.5e-6]], one)
+        elif rheology == "visco":
+            e.set_visco([3], o.arr("mat.1.moduli"), [o.arr("mat.1.wbody")], [o.arr("mat.1.theta").reshape(3, 3).T], one)
+        else:
+            e.set_damage([[rho * (cp * cp - 2 * cs * cs), rho * cs * cs, 30.9638, 0.0, 1e5, 0.0, 1.0,
+                           -1.487381e-5, -1.708729e-6, 3.5e-6, 0.0, 0.0, 0.0]], one)
+        for side in (1, 2, 3, 4):
+            e.add_abso_side(side)
+        e.add_force_at(0.37 * nx * h, 0.61 * nz * h, [o.f("src.0.dir1"), o.f("src.0.dir2")])
+        e.commit()
+        tab = np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)])
+        e.step(25, tab[:25])
+        e.step(nsteps - 25, tab[25:])
+        o.step(nsteps)
+        d, v, a = e.get_fields()
+        assert np.abs(o.arr("d")).max() > 0
+        for nm, got in (("d", d), ("v", v), ("acc", a)):
+            assert rel_l2(got, o.arr(nm)) <= tol, (rheology, precision, nm, rel_l2(got, o.arr(nm)))
+        if rheology == "plastic":
+            assert np.abs(o.arr("pl_ep")).max() > 0
+        if rheology == "damage":
+            assert o.arr("dm_state").reshape(-1, 4, 25)[:, 0].max() > 0
+        e.close()
+        o.close()
+
+
+def test_damage_beyond_the_critical_value_aborts_like_the_reference():
+    """compute_stress (mat_damage.f90:478-489) stops the run when the damaged moduli lose convexity; with a damage
+    evolution coefficient this large the oracle aborts with 'MAT_DMG: damage exceeded critical value' -- and so does
+    the engine (device error flag raised by the strip kernel, reported by s2d_step)."""
+    from sem2dpack_b200.capi import S2DError
+    nx, nz, nsteps, h, ngll = 29, 13, 40, 100.0, 5
+    L = [f"&GENERAL iexec=1, ngll={ngll}, fmax=3.d0, ndof=2, title='rheology', verbose='0000', ItInfo=1000 /",
+         "&MESH_DEF method='CARTESIAN' /",
+         f"&MESH_CART xlim=0d0,{nx*h}d0, zlim=0d0,{nz*h}d0, nelem={nx},{nz} /",
+         "&MATERIAL tag=1, kind='DMG' /",
+         "&MAT_DAMAGE rho=2670.d0, cp=6000.d0, cs=3464.d0, beta=0d0, R=1d0, Cd=1d9, phi=30.9638d0, alpha=0d0, e0=-1.487381d-5,-1.708729d-6,3.5d-6 /",
+         f"&TIME NbSteps={nsteps}, courant=0.5d0, kind='leapfrog' /",
+         f"&SRC_DEF stf='RICKER', coord={0.37*nx*h}d0,{0.61*nz*h}d0, mechanism='FORCE' /",
+         "&STF_RICKER f0=4.d0, onset=0.02d0, ampli=2.d10 /", "&SRC_FORCE angle=30d0 /"]
+    o = orc.Oracle("\n".join(L) + "\n", renumber=False)
+    with pytest.raises(Exception, match="damage exceeded critical value"):
+        o.step(nsteps)
+    rho, cp, cs = 2670.0, 6000.0, 3464.0
+    e = CartEngine(ngll, 2, nx, nz, (0.0, nx * h), (0.0, nz * h), seed=0, rho=rho, cp=cp, cs=cs)
+    e.set_dt(o.f("dt"))
+    e.set_damage([[rho * (cp * cp - 2 * cs * cs), rho * cs * cs, 30.9638, 0.0, 1e9, 0.0, 1.0, -1.487381e-5, -1.708729e-6, 3.5e-6,
+                   0.0, 0.0, 0.0]], np.ones(nx * nz, np.int32))
+    e.add_force_at(0.37 * nx * h, 0.61 * nz * h, [o.f("src.0.dir1"), o.f("src.0.dir2")])
+    e.commit()
+    tab = np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)])
+    with pytest.raises(S2DError, match="damage exceeded critical value"):
+        e.step(nsteps, tab)
+    e.close()
+    o.close()
