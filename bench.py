@@ -631,24 +631,34 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks,
         "check": {"vmax": vmax, "dmax": dmax, "note": "max over all ranks of max|v|, max|d| after the run"},
     }
+    def guarded(what, fn, *a):   # a sub-record that fails must not take the headline line with it
+        try:
+            return fn(*a)
+        except Exception as ex:
+            print(f"[bench] {what} failed: {ex}", file=sys.stderr)
+            return {"record": what, "error": str(ex)[-300:]}
     if world == 1 and args.generic_n > 0:
-        line["generic_route"] = generic_route_record(min(args.generic_n, args.nx), K, W, local, args.precision, torch)
+        line["generic_route"] = guarded("generic_route", generic_route_record, min(args.generic_n, args.nx), K, W, local,
+                                        args.precision, torch)
     if world == 1 and not args.no_configs:   # BASELINE.json configs[0..3] at scale, same run (records, not the headline)
-        line["reference_configs"] = [run_ref_config(c, max(10, min(K, 30)), local) for c in ("testsh", "lamb", "tpv3", "ratestate", "plastic25d")]
+        line["reference_configs"] = [guarded(c, run_ref_config, c, max(10, min(K, 30)), local)
+                                     for c in ("testsh", "lamb", "tpv3", "ratestate", "plastic25d")]
     if strong is not None:
         line["strong"] = strong
     if xdev is not None:
         line["xdev"] = xdev
-    if rank == 0 and not args.no_cpu:
+    def cpu_record():
         r, tcpu = cpu_oracle_rate(CPU_SAMPLE_N, CPU_SAMPLE_N, CPU_SAMPLE_STEPS, "o3")
         r2, tcpu2 = cpu_oracle_rate(CPU_SAMPLE_N, CPU_SAMPLE_N, max(2, CPU_SAMPLE_STEPS // 2), "parity")
-        line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": 1, "kind": "port",
+        return {"value": r, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"oracle (C++ port of the serial Fortran path), {CPU_SAMPLE_N}x{CPU_SAMPLE_N}"
                                           f"-element sample of the same workload, {CPU_SAMPLE_STEPS} solve() steps, "
                                           f"{tcpu:.1f} s, 1 thread; of {os.cpu_count()} host cores",
                                 "build": "-O3 -march=x86-64-v3 (BASELINE.md section 4)",
                                 "parity_build_value": r2,
                                 "parity_build": "-O2 -ffp-contract=off (the build the parity tests compare against)"}
+    if rank == 0 and not args.no_cpu:
+        line["cpu_baseline"] = guarded("cpu_baseline", cpu_record)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
