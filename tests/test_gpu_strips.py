@@ -99,3 +99,63 @@ def test_strips_match_whole_box(world, nx, nz, ezflt, seg, scheme, peer, monkeyp
         e.close()
     whole.close()
     o.close()
+
+
+@pytest.mark.parametrize("rheology", ["plastic", "damage"])
+def test_strips_with_a_stateful_rheology_match_the_whole_box(rheology, monkeypatch):
+    """the per-element state of the stateful rheologies partitions with the elements: three x-strips of a plastic /
+    damage box (heterogeneous hash medium, absorbing sides, a force source) against the same box in one piece"""
+    monkeypatch.setenv("S2D_SEG", "4")
+    world, nx, nz, nsteps = 3, 27, 10, 60
+    sdir = [0.5, np.sqrt(0.75)]
+    par_pl = [[2.0e5, 30.0, 0.01, -4e-6, -3e-6, 2.5e-6]]
+    lam_mu = (2670.0 * (6000.0 ** 2 - 2 * 3464.0 ** 2), 2670.0 * 3464.0 ** 2)
+    par_dm = [[lam_mu[0], lam_mu[1], 30.9638, 0.0, 1e6, 0.0, 1.0, -1.487381e-5, -1.708729e-6, 3.5e-6, 0.0, 0.0, 0.0]]
+
+    def build(lo, hi, rank, nworld, dt=None):
+        e = CartEngine(5, 2, hi - lo, nz, (lo * H, hi * H), (0.0, nz * H), seed=0, rho=2670.0, cp=6000.0, cs=3464.0,
+                       scheme_kind=0, courant=0.5, ix0=lo * 4, halo_left=rank > 0, halo_right=rank < nworld - 1)
+        if dt is not None:
+            e.set_dt(dt)
+        one = np.ones((hi - lo) * nz, np.int32)
+        if rheology == "plastic":
+            e.set_plastic(par_pl, one)
+        else:
+            e.set_damage(par_dm, one)
+        for s in sorted([1, 3] + ([4] if rank == 0 else []) + ([2] if rank == nworld - 1 else [])):
+            e.add_abso_side(s, False)
+        xs, zs = 0.37 * nx * H, 0.61 * nz * H
+        has = lo * H <= xs < hi * H
+        if has:
+            e.add_force_at(xs, zs, sdir)
+        e.commit()
+        return e, has
+
+    whole, _ = build(0, nx, 0, 1)
+    t = (np.arange(nsteps) + 1) * whole.dt
+    arg = (np.pi * 4.0 * (t - 0.05)) ** 2
+    amp = 2e10 if rheology == "plastic" else 3e9                # strong enough to leave the elastic range, below critical damage
+    tab = (amp * (1 - 2 * arg) * np.exp(-arg))[:, None]
+    whole.step(nsteps, tab)
+    dw, vw, aw = whole.get_fields()
+    ibw = whole.get_tables(rmass=False)[0].reshape(nz, nx, 25)
+    state_w = (whole.plastic_strain() if rheology == "plastic" else whole.damage_state()).reshape(nz, nx, -1)
+    assert np.abs(state_w).max() > 0
+    parts = strips.partition(nx, world)
+    built = [build(lo, hi, r, world, dt=whole.dt) for r, (lo, hi) in enumerate(parts)]
+    engines = [b[0] for b in built]
+    grp = strips.LocalStrips(engines, peer=False)
+    grp.run(lambda r, e: e.step(nsteps, tab if built[r][1] else None))
+    for r, (lo, hi) in enumerate(parts):
+        e = engines[r]
+        d, v, a = e.get_fields()
+        ib = e.get_tables(rmass=False)[0].reshape(nz, hi - lo, 25) - 1
+        gl = ibw[:, lo:hi, :] - 1
+        for c in range(2):
+            assert rel_l2(d[ib + c * e.npoin], dw[gl + c * whole.npoin]) <= 1e-11
+            assert rel_l2(v[ib + c * e.npoin], vw[gl + c * whole.npoin]) <= 1e-11
+        st = (e.plastic_strain() if rheology == "plastic" else e.damage_state()).reshape(nz, hi - lo, -1)
+        assert np.abs(st - state_w[:, lo:hi]).max() <= 1e-11 * np.abs(state_w).max()
+    for e in engines:
+        e.close()
+    whole.close()
