@@ -287,6 +287,10 @@ def generic_route_record(n, K, W, local, precision, torch):
     torch.cuda.synchronize()
     ms2 = e2.time_steps(K)
     k2 = e2.kernel_ms()
+    try:   # SURVEY 8d's K1 alone, in the reference's own storage (six planes per element), through the drop-in route
+        ms_k1 = e2.time_fint(5)
+    except Exception:
+        ms_k1 = None
     e2.close()
     ndof = npoin * NDOF
     peak, _ = peaks()
@@ -296,6 +300,12 @@ def generic_route_record(n, K, W, local, precision, torch):
             "generic_over_builder": ms1 / ms2, "kernel_route": "strip kernel" if route == 1 else "any-mesh patch kernel",
             "builder_kernel_ms": k1, "generic_kernel_ms": k2, "algorithmic_bytes_per_dof": b,
             "generic_kernel_frac_of_hbm_peak": (b * ndof / (k2 * 1e-3) / 1e9 / peak) if k2 > 0 else None,
+            "k1_alone_reference_storage": None if not ms_k1 else {
+                "kernel": "k_elem_strip + k_strip_fold, plain force evaluation (compute_Fint) of the routed handle",
+                "ms_per_launch": ms_k1, "algorithmic_bytes_per_dof": moved_bytes_per_dof(False, False, False, W8 if precision == 8 else 4),
+                "canonical_bytes_per_dof": B_K1, "gdof_per_s": ndof / (ms_k1 * 1e-3) / 1e9,
+                "frac": moved_bytes_per_dof(False, False, False, W8 if precision == 8 else 4) * ndof / (ms_k1 * 1e-3) / 1e9 / peak,
+                "note": "north_star's K1 target is 60 % of the HBM roofline at the canonical 56.6 B/DOF = 69.4 G DOF/s"},
             "element_order": "anti-diagonal sweeps (ix+iz, ix), node numbering by first occurrence in that order"}
 
 
