@@ -236,6 +236,7 @@ class Engine : public EngineBase {
   // tensor-map staging of the compact fused leapfrog kernel (S2D_STRIP_TENSOR=0 in the environment: per-lane copies)
   int strip_tensor = env_int("S2D_STRIP_TENSOR", S2D_STRIP_TENSOR);
   bool tm_ready = false;
+  int strip_tensor_plain = env_int("S2D_STRIP_TENSOR_PLAIN", 1);
   CUtensorMap tm_d[2], tm_v, tm_r, tm_a;   // d[n] is in either displacement buffer
   std::vector<uint8_t> h_rowflag, h_colflag;
   std::vector<std::vector<int32_t>> h_bc_nodes;  // node lists of every boundary condition (for the flags)
@@ -340,6 +341,12 @@ class Engine : public EngineBase {
       io.dm_err = &ctl.p->err;
     }
     return io;
+  }
+  // plain force evaluation of one of the two displacement buffers: the kernel can take its rows as tensor-map boxes
+  void plain_tensor_map(StripIO<T>& io, const T* dd) {
+    if (!tm_ready || !strip_tensor_plain) return;
+    if (dd == d.p) io.tm_d = &tm_d[0];
+    else if (dd == d2.p) io.tm_d = &tm_d[1];
   }
   // strip kernel over the whole box (+ halo fold, + interface exchange); io.v_in != null = fused update
   // tick: the step counter is advanced by the fold kernel (fused step: one launch less)
@@ -1442,6 +1449,7 @@ class Engine : public EngineBase {
   void launch_fint(const T* dd, const T* vv, T* ff) {
     if (cart_mode) {
       StripIO<T> io = strip_io(dd, ff);
+      plain_tensor_map(io, dd);
       if (strip_eta.n) {  // forces from d + eta*v, element by element (solver.f90:293-295, mat_kelvin_voigt.f90:147)
         io.eta = strip_eta.p;
         io.v_kv = vv;
@@ -1955,6 +1963,7 @@ class Engine : public EngineBase {
     const size_t nd = npoin * ndof;
     if (scratch.n != nd) scratch.alloc(nd);
     StripIO<T> io = strip_io(dbuf().p, scratch.p);
+    plain_tensor_map(io, dbuf().p);
     // no interface exchange on x-strips: the interface columns are deferred nodes (their accelerations are stored),
     // every other node's force is complete with this GPU's elements alone -- so this is not a collective call
     launch_elem_strip_items<T>(strip_all_groups(cart_S), io, stream);

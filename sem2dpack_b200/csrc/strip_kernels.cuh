@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   static_assert(!PLAST || (COMPACT && NDOF == 2 && !TENS && S2D_COMPACT_FOLD != 0),
                 "stateful rheologies: P-SV, (lambda, mu) coefficient stream, folded metric");
   static_assert(!(PLAST && KV) || RHEO == 3, "Kelvin-Voigt on top of a stateful rheology: damage only");
-  static_assert(!TENS || (FUSED >= 1 && !KV), "tensor-map staging: fused leapfrog / explicit Newmark step");
+  static_assert(!TENS || !KV, "tensor-map staging: not with Kelvin-Voigt elements");
   static_assert(!COMPACT || NDOF == 2, "compact coefficients: P-SV only");
   static_assert(!KV || !TENS, "Kelvin-Voigt elements: per-lane staging only");
   constexpr int WARPS = strip_warps();
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tens_issue_A(ez0);
       if (ez0 + 1 < ez1) tens_issue_A(ez0 + 1);
-      tens_issue_B(ez0);
+      if constexpr (FUSED != 0) tens_issue_B(ez0);
     }
     __syncthreads();  // the barriers exist before anybody waits on them
   }
@@ -1186,7 +1186,9 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
       // previous row (end of the previous iteration): both stages are free for rows ez + 2 and ez + 1
       if (threadIdx.x == 0) {
         if (ez + 2 < ez1) tens_issue_A(ez + 2);
-        if (ez + 1 < ez1) tens_issue_B(ez + 1);
+        if constexpr (FUSED != 0) {
+          if (ez + 1 < ez1) tens_issue_B(ez + 1);
+        }
       }
     }
     if (wact) {
@@ -1207,7 +1209,7 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
         // component (mat_mass.f90:56-57; only bc_abso.f90:243 makes the columns differ, on deferred
         // nodes), so one read of component 1 serves all of them.
         T vv[NDOF][N - 1], rm[N - 1];
-        if constexpr (TENS) {
+        if constexpr (TENS && FUSED != 0) {
           const int kk = ez - ez0;
           mbar_wait_or_trap(&tbarB[kk & 1], (unsigned)((kk >> 1) & 1));
           const T* bV = reinterpret_cast<const T*>(tbase + (kk & 1) * TSZ + TSZ_A) + bx;
@@ -1730,6 +1732,14 @@ void launch_strip_case(const StripGeom& G, const StripIO<T>& io, cudaStream_t s)
     const unsigned nb = (unsigned)G.nitems;
     const int mode = !fused ? 0 : (io.newmark ? 2 : 1);
     if constexpr (NN <= S2D_STRIP_TENSOR_MAXN) { /* CTA-wide tensor-map staging of the fused step (S2D_STRIP_TENSOR) */
+      if (mode == 0 && io.tm_d && !io.eta && !io.pl_set && (G.ndof == 1 || io.compact)) {
+        // plain force evaluation: the displacement boxes alone (S2D_STRIP_TENSOR_PLAIN)
+        constexpr int MB = strip_min_ctas(NN, sizeof(T));
+        A.tm_d = *io.tm_d;
+        if (G.ndof == 1) strip_launch<T, NN, 1, 0, false, MB, false, true>(nb, A, s);
+        else strip_launch<T, NN, 2, 0, true, MB, false, true>(nb, A, s);
+        return;
+      }
       if (mode >= 1 && io.tm_d && !io.eta && !io.pl_set) {
         constexpr int MB = strip_min_ctas(NN, sizeof(T));
         A.tm_d = *io.tm_d;
