@@ -597,3 +597,22 @@ def test_damage_beyond_the_critical_value_aborts_like_the_reference():
         e.step(nsteps, tab)
     e.close()
     o.close()
+
+
+@pytest.mark.parametrize("ngll,nx,nz", [(6, 23, 12), (9, 14, 7), (3, 47, 9), (8, 9, 6)])
+def test_fp32_fused_steps_other_orders(ngll, nx, nz):
+    """FP32 fields through the tensor-map instantiations of the other GLL orders (box widths and strides in 4-byte
+    elements): 60 fused leapfrog steps with absorbing sides and a force source, 1e-4 against the FP64 oracle."""
+    nsteps = 60
+    o = orc.Oracle(harness.cart_deck(nx, nz, ngll=ngll, nsteps=nsteps, abso=(1, 2, 3, 4)), synthetic_seed=SEED, renumber=False)
+    e = CartEngine(ngll, 2, nx, nz, (0.0, nx * 100.0), (0.0, nz * 100.0), seed=SEED, precision=4)
+    for side in (1, 2, 3, 4):
+        e.add_abso_side(side)
+    e.add_force_at(0.37 * nx * 100, 0.61 * nz * 100, [o.f("src.0.dir1"), o.f("src.0.dir2")])
+    e.commit()
+    e.step(nsteps, np.array([[o.stf(0, (k + 1) * o.f("dt"))] for k in range(nsteps)]))
+    o.step(nsteps)
+    d, v, a = e.get_fields()
+    assert rel_l2(d, o.arr("d")) <= 1e-4 and rel_l2(v, o.arr("v")) <= 1e-4 and rel_l2(a, o.arr("acc")) <= 1e-3
+    e.close()
+    o.close()
