@@ -398,7 +398,16 @@ inline void read_main(problem_type& pb, const std::string& file) {
     problem_type::material_type& M = pb.mat[(size_t)g.integer("tag", 0) - 1];
     const std::string k1 = g.text("kind", "ELAST", 0), k2 = g.count("kind") >= 2 ? g.text("kind", "", 1) : std::string();
     if (k1 == "PLAST") {  // MAT_PLAST_read (SRC/mat_plastic.f90:66-118): constants only
-      if (!k2.empty()) IO_abort("MAT_read: kind='PLAST' combined with '" + k2 + "' is not on the B200 path");
+      if (!(k2.empty() || k2 == "KV")) IO_abort("MAT_read: kind='PLAST' combined with '" + k2 + "' is not on the B200 path");
+      if (k2 == "KV") {  // MAT_KV_read (SRC/mat_kelvin_voigt.f90:35-66): the one non-exclusive material (mat_gen.f90:350-354)
+        const long q = in.find("MAT_KV", (size_t)m0);
+        if (q < 0) IO_abort("MAT_KV_read: MAT_KV input block not found");
+        size_t c2 = (size_t)q + 1;
+        M.eta = DIST_CD_Read(in, in.at((size_t)q), "eta", 0.0, c2);
+        M.ETAxDT = in.at((size_t)q).logical("etaxdt", true);
+        M.kv = true;
+        pb.has_kv = true;
+      }
       const long m = in.find("MAT_PLASTIC", (size_t)m0);
       if (m < 0) IO_abort("MAT_PLAST_read: MAT_PLASTIC input block not found");
       const nml_group& e = in.at((size_t)m);
@@ -446,7 +455,16 @@ inline void read_main(problem_type& pb, const std::string& file) {
       continue;
     }
     if (k1 == "VISCO") {  // MAT_VISCO_read (SRC/mat_visco.f90:65-113): constants only
-      if (!k2.empty()) IO_abort("MAT_read: kind='VISCO' combined with '" + k2 + "' is not on the B200 path");
+      if (!(k2.empty() || k2 == "KV")) IO_abort("MAT_read: kind='VISCO' combined with '" + k2 + "' is not on the B200 path");
+      if (k2 == "KV") {  // MAT_KV_read (SRC/mat_kelvin_voigt.f90:35-66): the one non-exclusive material (mat_gen.f90:350-354)
+        const long q = in.find("MAT_KV", (size_t)m0);
+        if (q < 0) IO_abort("MAT_KV_read: MAT_KV input block not found");
+        size_t c2 = (size_t)q + 1;
+        M.eta = DIST_CD_Read(in, in.at((size_t)q), "eta", 0.0, c2);
+        M.ETAxDT = in.at((size_t)q).logical("etaxdt", true);
+        M.kv = true;
+        pb.has_kv = true;
+      }
       const long m = in.find("MAT_VISCO", (size_t)m0);
       if (m < 0) IO_abort("MAT_VISCO_read: MAT_VISCO input block not found");
       const nml_group& e = in.at((size_t)m);
@@ -872,7 +890,7 @@ inline void init_main(problem_type& pb) {
   }
   if (pb.has_visco) {  // MAT_VISCO_init_elem_prop (SRC/mat_visco.f90:116-161): get_attenuation per VISCO tag
     if (pb.ndof != 2) IO_abort("MAT_init_work: visco-elasticity requires ndof=2 (P-SV) ");
-    if (pb.has_plastic || pb.has_kv || pb.has_damage) IO_abort("MAT_read: VISCO together with PLAST, DMG or KV materials is not on the B200 path");
+    if (pb.has_plastic || pb.has_damage) IO_abort("MAT_read: VISCO together with PLAST or DMG materials is not on the B200 path");
     std::vector<int> set_of_tag(pb.mat.size(), 0);
     std::vector<int32_t> nbody;
     std::vector<double> moduli, wbody, theta;

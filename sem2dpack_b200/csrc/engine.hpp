@@ -1385,7 +1385,6 @@ class Engine : public EngineBase {
         upload_as(dm_tab, &dm_raw[0][0], (size_t)STRIP_PL_SETS * STRIP_DM_TAB);
       }
       if (vs_state.n) {  // RK_factor of MAT_VISCO_stress (mat_visco.f90:222-224), now that dt is known
-        S2D_REQUIRE(strip_eta.n == 0, "visco-elastic elements together with Kelvin-Voigt elements: not provided");
         double tab[STRIP_PL_SETS][STRIP_VS_TAB];
         std::memcpy(tab, vs_raw, sizeof(tab));
         for (int k = 1; k < STRIP_PL_SETS; ++k)
@@ -1396,7 +1395,6 @@ class Engine : public EngineBase {
         upload_as(vs_tab, &tab[0][0], (size_t)STRIP_PL_SETS * STRIP_VS_TAB);
       }
       if (pl_set.n && !vs_state.n && !dm_state.n) {  // MAT_PLAST_init_elem_work (mat_plastic.f90:165-184); set 0 (elastic elements) never yields
-        S2D_REQUIRE(strip_eta.n == 0, "plastic elements together with Kelvin-Voigt elements: not provided");
         for (int k = 1; k < STRIP_PL_SETS; ++k) {
           const double phi = 3.141592653589793 / 180.0 * pl_raw[k][1];
           pl_par[k][0] = pl_raw[k][0] * std::cos(phi);

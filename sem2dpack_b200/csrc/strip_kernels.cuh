@@ -474,7 +474,6 @@ __global__ void __launch_bounds__(strip_warps() * 32, MINB)
   constexpr bool PLAST = RHEO != 0;
   static_assert(!PLAST || (COMPACT && NDOF == 2 && !TENS && S2D_COMPACT_FOLD != 0),
                 "stateful rheologies: P-SV, (lambda, mu) coefficient stream, folded metric");
-  static_assert(!(PLAST && KV) || RHEO == 3, "Kelvin-Voigt on top of a stateful rheology: damage only");
   static_assert(!TENS || !KV, "tensor-map staging: not with Kelvin-Voigt elements");
   static_assert(!COMPACT || NDOF == 2, "compact coefficients: P-SV only");
   static_assert(!KV || !TENS, "Kelvin-Voigt elements: per-lane staging only");
@@ -1773,13 +1772,22 @@ void launch_strip_case(const StripGeom& G, const StripIO<T>& io, cudaStream_t s)
         A.dm_err = io.dm_err;
         constexpr int MP = sizeof(T) == 8 ? S2D_PLAST_MINB : 3;
         constexpr int MK = sizeof(T) == 8 ? 2 : 3;
-        if (io.eta) { /* a Kelvin-Voigt layer on top (EXAMPLES/Damage: kind='DMG','KV') */
-          if (!io.dm_state) throw ArgError("Kelvin-Voigt elements together with plastic or visco-elastic ones: not provided");
+        if (io.eta) { /* a Kelvin-Voigt layer on top (the one non-exclusive material; EXAMPLES/Damage: kind='DMG','KV') */
           if (mode != 0 && (io.v_in == io.v_out || (mode == 2 && (const T*)io.f == io.a_in)))
             throw ArgError("Kelvin-Voigt elements: the fused update needs separate output buffers");
-          if (mode == 2) strip_launch<T, NN, 2, 2, true, MK, true, false, 3>(nb, A, s);
-          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MK, true, false, 3>(nb, A, s);
-          else strip_launch<T, NN, 2, 0, true, MK, true, false, 3>(nb, A, s);
+          if (io.dm_state) {
+            if (mode == 2) strip_launch<T, NN, 2, 2, true, MK, true, false, 3>(nb, A, s);
+            else if (mode == 1) strip_launch<T, NN, 2, 1, true, MK, true, false, 3>(nb, A, s);
+            else strip_launch<T, NN, 2, 0, true, MK, true, false, 3>(nb, A, s);
+          } else if (io.vs_state) {
+            if (mode == 2) strip_launch<T, NN, 2, 2, true, MK, true, false, 2>(nb, A, s);
+            else if (mode == 1) strip_launch<T, NN, 2, 1, true, MK, true, false, 2>(nb, A, s);
+            else strip_launch<T, NN, 2, 0, true, MK, true, false, 2>(nb, A, s);
+          } else {
+            if (mode == 2) strip_launch<T, NN, 2, 2, true, MK, true, false, 1>(nb, A, s);
+            else if (mode == 1) strip_launch<T, NN, 2, 1, true, MK, true, false, 1>(nb, A, s);
+            else strip_launch<T, NN, 2, 0, true, MK, true, false, 1>(nb, A, s);
+          }
         } else if (io.dm_state) {
           if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, 3>(nb, A, s);
           else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 3>(nb, A, s);

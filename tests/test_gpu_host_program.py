@@ -460,3 +460,51 @@ def test_damage_deck_off_fault_damage(tmp_path):
     for c in range(6):
         assert np.abs(rec[:, c] - want[:, c]).max() <= 5e-6 * max(np.abs(want[:, c]).max(), 1e-30), c
     o.close()
+
+
+@pytest.mark.parametrize("rheology", ["plastic", "visco"])
+def test_kelvin_voigt_layer_on_top_of_plasticity_and_visco_elasticity(tmp_path, rheology):
+    """KV is the one non-exclusive material (mat_gen.f90:350-354,435): kind='PLAST','KV' and kind='VISCO','KV' on the
+    element rows next to the fault (fztag = 2), the plain rheology elsewhere; SWF fault, absorbing sides, leapfrog.
+    Velocity snapshot and fault records against the oracle."""
+    nsteps = 300
+    if rheology == "plastic":
+        kind, block = "PLAST", "&MAT_PLASTIC cp=5770.d0, cs=3330.d0, rho=2705.d0, phi = 30.d0, coh = 4.0d6, Tv = 0.0561d0,\n   e0 = -4.162378e-04, -4.162378e-04, 3.504802e-04 /"
+    else:
+        kind, block = "VISCO", "&MAT_VISCO rho=2705.d0, cp=5770.d0, cs=3330.d0, QP=60d0, QS=30d0, Nbody=3, fmin=0.05d0, fmax=5d0 /"
+    deck = f"""&GENERAL iexec=1, ngll=5, fmax=3.d0 , ndof=2 , title = 'rheology under a KV layer', verbose='0000' , ItInfo = 400/
+&MESH_DEF  method = 'CARTESIAN'/
+&MESH_CART ezflt=-1, fztag=2, xlim=0d3,30d3, zlim=-12d3,12d3, nelem=40,32/
+&MATERIAL tag=1, kind='{kind}'  /
+&MATERIAL tag=2, kind='{kind}','KV'  /
+{block}
+&MAT_KV eta=0.2d0 /
+&BC_DEF  tags = 5,6 , kind = 'DYNFLT' /
+&BC_DYNFLT friction='SWF','TWF', Tn=-50d6, Tt=2.102564d7 /
+&BC_DYNFLT_SWF Dc=2d0, MuS=0.6d0, MuD=0.1d0 /
+&BC_DYNFLT_TWF kind=1, MuS=0.6d0, MuD=0.1d0, Mu0=0.6d0, X=15.d3, Z=0.d0, V=0.333d3, L=0.1665d3, T=60d0 /
+&BC_DEF  tag = 1 , kind = 'ABSORB' /
+&BC_DEF  tag = 2 , kind = 'ABSORB' /
+&BC_DEF  tag = 3 , kind = 'ABSORB' /
+&BC_DEF  tag = 4 , kind = 'ABSORB' /
+&TIME  kind='leapfrog', NbSteps={nsteps}, courant=0.4d0 /
+&SNAP_DEF itd={nsteps}, fields ='V',bin=T,ps=F /
+"""
+    p = run(tmp_path, deck, "--quiet", "--natural-order")
+    assert p.returncode == 0, p.stdout + p.stderr
+    o = orc.Oracle(deck, renumber=False)
+    assert o.i("nkv") == 2 * 40 and o.i("npl" if rheology == "plastic" else "nvs") == 40 * 32
+    o.step(nsteps)
+    n = o.i("npoin")
+    vref = o.arr("v").reshape(2, n)
+    assert np.abs(vref).max() > 0
+    for c, ax in enumerate("xz"):
+        got = np.fromfile(tmp_path / f"v{ax}_001_sem2d.dat", dtype=np.float32)
+        assert np.abs(got - vref[c].astype(np.float32)).max() <= 5e-6 * np.abs(vref).max(), ax
+    x, rec = read_fault(tmp_path, 5)
+    want = o.arr("bc.0.out").reshape(-1, 6, rec.shape[2])
+    assert rec.shape == want.shape
+    floor = 1e-6 * np.abs(want).max()   # a column at rounding level (normal-stress change of a symmetric problem: 1e-7 Pa)
+    for c in range(6):
+        assert np.abs(rec[:, c] - want[:, c]).max() <= 5e-6 * max(np.abs(want[:, c]).max(), floor), c
+    o.close()
