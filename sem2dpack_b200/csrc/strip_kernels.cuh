@@ -1665,7 +1665,10 @@ struct StripIO {
 constexpr int STRIP_KV_FUSED_MAXN = 6;
 constexpr int STRIP_PLAST_MAXN = 6;  // plasticity instantiations
 #ifndef S2D_PLAST_MINB
-#define S2D_PLAST_MINB 3   // CTAs per SM of the FP64 plasticity instantiations: 168 registers with ~300 B of spills beat 2 CTAs without (4.04 vs 4.36 ms, 2560^2)
+// CTAs per SM of the FP64 plasticity instantiation.  With the plastic strain loaded directly, 3 CTAs at 168 registers
+// and ~300 B of spills beat 2 CTAs without spills (4.04 vs 4.36 ms, 2560^2); once the strain was staged one row ahead
+// the order reversed: 2 CTAs 3.90 ms, 3 CTAs 4.31 ms (heavy yielding 4.35 vs 4.87).  Visco / damage keep 3 (not measured).
+#define S2D_PLAST_MINB 2
 #endif
 template <typename T, int N, int NDOF, int FUSED, bool COMPACT, int MINB = strip_min_ctas(N, sizeof(T), COMPACT), bool KV = false,
           bool TENS = false, int RHEO = 0>
@@ -1770,7 +1773,8 @@ void launch_strip_case(const StripGeom& G, const StripIO<T>& io, cudaStream_t s)
         A.dm_state = io.dm_state;
         A.dm_tab = io.dm_tab;
         A.dm_err = io.dm_err;
-        constexpr int MP = sizeof(T) == 8 ? S2D_PLAST_MINB : 3;
+        constexpr int MP1 = sizeof(T) == 8 ? S2D_PLAST_MINB : 3;   // plasticity
+        constexpr int MP = 3;                                      // visco-elasticity, damage
         constexpr int MK = sizeof(T) == 8 ? 2 : 3;
         if (io.eta) { /* a Kelvin-Voigt layer on top (the one non-exclusive material; EXAMPLES/Damage: kind='DMG','KV') */
           if (mode != 0 && (io.v_in == io.v_out || (mode == 2 && (const T*)io.f == io.a_in)))
@@ -1797,9 +1801,9 @@ void launch_strip_case(const StripGeom& G, const StripIO<T>& io, cudaStream_t s)
           else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 2>(nb, A, s);
           else strip_launch<T, NN, 2, 0, true, MP, false, false, 2>(nb, A, s);
         } else {
-          if (mode == 2) strip_launch<T, NN, 2, 2, true, MP, false, false, 1>(nb, A, s);
-          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP, false, false, 1>(nb, A, s);
-          else strip_launch<T, NN, 2, 0, true, MP, false, false, 1>(nb, A, s);
+          if (mode == 2) strip_launch<T, NN, 2, 2, true, MP1, false, false, 1>(nb, A, s);
+          else if (mode == 1) strip_launch<T, NN, 2, 1, true, MP1, false, false, 1>(nb, A, s);
+          else strip_launch<T, NN, 2, 0, true, MP1, false, false, 1>(nb, A, s);
         }
         return;
       }
