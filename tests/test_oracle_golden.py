@@ -228,3 +228,61 @@ def test_damage_deck_prestrain_reproduces_the_fault_stresses():
     s0 = par[10:13]
     assert abs(s0[1] + 2.0) <= 1e-6 and abs(s0[2] - 0.7) <= 1e-6, s0
     o.close()
+
+
+def test_visco_attenuation_fit_is_constant_q_within_the_documented_five_percent():
+    """mat_visco.f90:58-61 documents get_attenuation's accuracy: 'For Nbody=3, constant Q with less than 5% error can be
+    achieved over a maximum bandwidth fmax/fmin ~ 100'.  The oracle's restatement (relaxation frequencies, least-squares
+    anelastic coefficients, theta) must reproduce that: 1/Q(w) of the generalized Maxwell body it builds, evaluated at
+    200 frequencies across the band, stays within 5 % of 1/QP and 1/QS."""
+    QP, QS, nb, fmin, fmax = 30.0, 20.0, 3, 1.8, 180.0
+    deck = harness.deck("attenuation").replace("Nbody=5", f"Nbody={nb}").replace("nelem=44,44", "nelem=4,4")
+    o = orc.Oracle(deck, renumber=False)
+    theta = o.arr("mat.1.theta").reshape(3, nb)
+    wb = o.arr("mat.1.wbody")
+    lam, mu = o.arr("mat.1.moduli")
+    assert np.allclose(wb / (2 * np.pi), [fmin, np.sqrt(fmin * fmax), fmax], rtol=1e-12)
+    Ya, Yb = theta[0] / (lam + 2 * mu), theta[2] / (2 * mu)
+    w = 2 * np.pi * np.exp(np.linspace(np.log(fmin), np.log(fmax), 200))
+    for Y, Q in ((Ya, QP), (Yb, QS)):
+        num = (Y[None, :] * wb[None, :] * w[:, None] / (wb[None, :] ** 2 + w[:, None] ** 2)).sum(axis=1)
+        den = 1.0 - (Y[None, :] * wb[None, :] ** 2 / (wb[None, :] ** 2 + w[:, None] ** 2)).sum(axis=1)
+        qinv = num / den
+        assert np.abs(qinv * Q - 1.0).max() <= 0.05, np.abs(qinv * Q - 1.0).max()
+    # unrelaxed moduli exceed the relaxed (reference-frequency) ones
+    assert mu > 2000.0 * 2000.0 ** 2 and lam + 2 * mu > 2000.0 * 3000.0 ** 2
+    o.close()
+
+
+def test_plastic_return_puts_the_stress_on_the_coulomb_yield_surface():
+    """MAT_PLAST_stress with Tv = 0 (vp_factor = 1, mat_plastic.f90:181-185,320-341) is the classical return mapping:
+    wherever the trial stress exceeds the Coulomb yield stress Y = coh cos(phi) - sin(phi) sigma_m, the updated stress
+    has max shear stress EXACTLY Y, the mean stress is unchanged and the plastic strain increment is deviatoric.  Checked
+    on the oracle after one force evaluation of a large random displacement (absolute stress = snapshot + s0)."""
+    nx, nz, h = 6, 5, 100.0
+    coh, phi, e0 = 2.0e6, 30.0, (-4.0e-4, -3.0e-4, 2.5e-4)
+    L = ["&GENERAL iexec=1, ngll=5, fmax=3.d0, ndof=2, title='plastic', verbose='0000', ItInfo=1000 /",
+         "&MESH_DEF method='CARTESIAN' /", f"&MESH_CART xlim=0d0,{nx*h}d0, zlim=0d0,{nz*h}d0, nelem={nx},{nz} /",
+         "&MATERIAL tag=1, kind='PLAST' /",
+         f"&MAT_PLASTIC rho=2670.d0, cp=6000.d0, cs=3464.d0, phi={phi}d0, coh={coh}d0, Tv=0d0, e0={e0[0]}d0,{e0[1]}d0,{e0[2]}d0 /",
+         "&TIME NbSteps=10, courant=0.5d0, kind='leapfrog' /"]
+    o = orc.Oracle("\n".join(L) + "\n", renumber=False)
+    rng = np.random.default_rng(3)
+    d = 3e-2 * rng.standard_normal(o.i("npoin") * 2)
+    o.set_fields(d, d)
+    o.compute_fint()                                  # advances ep
+    ep = o.arr("pl_ep").reshape(nx * nz, 3, 25)
+    assert np.abs(ep[:, 0] + ep[:, 1]).max() <= 1e-12 * np.abs(ep).max()       # deviatoric
+    par = o.arr("pl_par")[:10]
+    lam, mu = par[0], par[1]
+    s0 = np.array([(lam + 2 * mu) * e0[0] + lam * e0[1], lam * e0[0] + (lam + 2 * mu) * e0[1], 2 * mu * e0[2]])
+    s = o.snapshot("S").astype(np.float64).reshape(3, nx * nz, 25) + s0[:, None, None]   # C:(e - ep) + s0
+    tau = np.sqrt(0.25 * (s[0] - s[1]) ** 2 + s[2] ** 2)
+    Y = coh * np.cos(np.radians(phi)) - np.sin(np.radians(phi)) * 0.5 * (s[0] + s[1])
+    yielded = np.abs(ep).max(axis=1) > 0
+    assert yielded.mean() > 0.5
+    # |Y|: in strong tension Y < 0 and the reference's factor Y/tau reverses the deviator instead of cutting it off
+    # (no tension cut-off in mat_plastic.f90:331-336) -- restated as it is
+    assert np.abs(tau[yielded] / np.abs(Y[yielded]) - 1.0).max() <= 1e-4   # float32 snapshot of stresses up to 5e8 Pa
+    assert (tau[~yielded] <= Y[~yielded] * (1 + 1e-6)).all()
+    o.close()
